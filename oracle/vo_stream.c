@@ -706,7 +706,7 @@ static int overlap_buffers(vo_stream* s, const vo_pinfo* info, float* prev, floa
     float* chan = next + info->left_start + (size_t)size1 * ch;
     for (int i = 0; i < packet_len; i++) {
       float a = chan[i] * slope[i];
-      float b = pv[i] * slope[slope_len - 1 - i];
+      float b = pv[i] * slope[packet_len - 1 - i]; /* slope.AsSpan(0, packetLen)[^(i + 1)] */
       chan[i] = a + b;
     }
   }

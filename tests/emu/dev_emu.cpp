@@ -1,0 +1,118 @@
+// dev_emu.cpp -- TEST INFRASTRUCTURE ONLY: devapi.h on top of cuda_emu.h (see cuda_emu.h).
+#include "cuda_emu.h"
+
+#include <stdlib.h>
+
+#include "../../include/vpz.h"
+#include "../../vorbispizza_b200/csrc/devapi.h"
+#include "../../vorbispizza_b200/csrc/k1_entropy.cuh"
+#include "../../vorbispizza_b200/csrc/k3_imdct.cuh"
+
+thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+namespace emu {
+thread_local BlockCtx* t_block;
+thread_local int t_lane, t_warp;
+
+void launch(unsigned blocks, unsigned threads, size_t smem_bytes, const std::function<void()>& body) {
+  for (unsigned b = 0; b < blocks; b++) {
+    BlockCtx ctx;
+    Barrier bar((int)threads);
+    ctx.bar = &bar;
+    unsigned nw = (threads + 31) / 32;
+    for (unsigned w = 0; w < nw; w++) ctx.warps.push_back(new WarpCtx);
+    ctx.smem = calloc(1, smem_bytes + 64);
+    std::vector<std::thread> ts;
+    for (unsigned t = 0; t < threads; t++) {
+      ts.emplace_back([&, t] {
+        t_block = &ctx;
+        t_lane = (int)(t & 31);
+        t_warp = (int)(t >> 5);
+        threadIdx.x = t;
+        blockIdx.x = b;
+        blockDim.x = threads;
+        gridDim.x = blocks;
+        body();
+      });
+    }
+    for (auto& t : ts) t.join();
+    for (auto* w : ctx.warps) delete w;
+    free(ctx.smem);
+  }
+}
+}  // namespace emu
+
+namespace vpz {
+namespace dev {
+
+struct Stream {
+  int dummy;
+};
+struct Event {
+  int dummy;
+};
+
+int init(int, std::string&) { return VPZ_OK; }
+int device_count() { return 1; }
+int sm_count() { return 1; }
+size_t max_smem_per_block() { return 227 * 1024; }
+void* alloc(size_t bytes, std::string&) { return calloc(1, bytes + 64); }
+void free(void* p) { ::free(p); }
+void* host_alloc(size_t bytes) { return calloc(1, bytes + 64); }
+void host_free(void* p) { ::free(p); }
+Stream* stream_create() { return new Stream; }
+void stream_destroy(Stream* s) { delete s; }
+int stream_sync(Stream*, std::string&) { return VPZ_OK; }
+Event* event_create() { return new Event; }
+void event_destroy(Event* e) { delete e; }
+void event_record(Event*, Stream*) {}
+float event_elapsed_ms(Event*, Event*) { return 0.f; }
+int h2d(void* d, const void* s, size_t n, Stream*, std::string&) {
+  memcpy(d, s, n);
+  return VPZ_OK;
+}
+int d2h(void* d, const void* s, size_t n, Stream*, std::string&) {
+  memcpy(d, s, n);
+  return VPZ_OK;
+}
+int d2d(void* d, const void* s, size_t n, Stream*, std::string&) {
+  memcpy(d, s, n);
+  return VPZ_OK;
+}
+int fill(void* d, int v, size_t n, Stream*, std::string&) {
+  memset(d, v, n);
+  return VPZ_OK;
+}
+
+int launch_k1(const K1Params& p, bool debug, int blocks, int warps, Stream*, std::string&) {
+  if (p.n_pkts == 0) return VPZ_OK;
+  *p.counter = 0;
+  (void)blocks;  // work stealing: one emulated block drains the whole queue
+  emu::launch(1, (unsigned)warps * 32, (size_t)warps * p.smem_words_per_warp * 4, [&] {
+    uint32_t* smem = (uint32_t*)emu::t_block->smem;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* my = smem + (size_t)warp * p.smem_words_per_warp;
+    for (;;) {
+      uint32_t idx = 0;
+      if (lane == 0) idx = atomicAdd(p.counter, 1u);
+      idx = __shfl_sync(0xffffffffu, idx, 0);
+      if (idx >= p.n_pkts) break;
+      if (debug) k1_decode_packet<true>(p, idx, my, lane); else k1_decode_packet<false>(p, idx, my, lane);
+      __syncwarp();
+    }
+  });
+  return VPZ_OK;
+}
+
+int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream*, std::string&) {
+  if (p.n_items == 0) return VPZ_OK;
+  emu::launch(p.n_items, (unsigned)ncb * K3_THREADS_PER_CH, smem_bytes, [&] {
+    float* smem = (float*)emu::t_block->smem;
+    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      if (fast) k3_run_item<true>(p, p.items[item], smem, ncb); else k3_run_item<false>(p, p.items[item], smem, ncb);
+    }
+  });
+  return VPZ_OK;
+}
+
+}  // namespace dev
+}  // namespace vpz

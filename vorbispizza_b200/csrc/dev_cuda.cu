@@ -1,0 +1,218 @@
+// dev_cuda.cu -- CUDA implementation of devapi.h: the sm_100a kernels and their launchers.
+// This is the only device backend linked into libvpz.so; there is no CPU path.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "../../include/vpz.h"
+#include "devapi.h"
+#include "k1_entropy.cuh"
+#include "k3_imdct.cuh"
+
+// ---- kernels ---------------------------------------------------------------------------------
+template <bool DEBUG>
+__global__ void __launch_bounds__(256) vpz_k1_entropy(K1Params P) {
+  extern __shared__ uint32_t k1_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t* my = k1_smem + (size_t)warp * P.smem_words_per_warp;
+  for (;;) {
+    uint32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(P.counter, 1u);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= P.n_pkts) break;
+    k1_decode_packet<DEBUG>(P, idx, my, lane);
+    __syncwarp();
+  }
+}
+
+template <bool FAST>
+__global__ void __launch_bounds__(128) vpz_k3_imdct_ola(K3Params P, int ncb) {
+  extern __shared__ float k3_smem[];
+  for (uint32_t item = blockIdx.x; item < P.n_items; item += gridDim.x)
+    k3_run_item<FAST>(P, P.items[item], k3_smem, ncb);
+}
+
+namespace vpz {
+namespace dev {
+
+struct Stream {
+  cudaStream_t s;
+};
+struct Event {
+  cudaEvent_t e;
+};
+
+static int g_sm_count = 0;
+static size_t g_max_smem = 0;
+
+static int fail(cudaError_t e, const char* what, std::string& err) {
+  err = std::string(what) + ": " + cudaGetErrorString(e);
+  return VPZ_E_CUDA;
+}
+
+int device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int init(int device, std::string& err) {
+  int n = device_count();
+  if (n <= 0) {
+    err = "no CUDA device visible (libvpz has no CPU path)";
+    return VPZ_E_NO_DEVICE;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= n) {
+    err = "device index out of range";
+    return VPZ_E_NO_DEVICE;
+  }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(e, "cudaSetDevice", err);
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(e, "cudaGetDeviceProperties", err);
+  if (prop.major != 10) {
+    err = std::string("device is sm_") + std::to_string(prop.major) + std::to_string(prop.minor) +
+          "; libvpz is built for sm_100a only";
+    return VPZ_E_NO_DEVICE;
+  }
+  g_sm_count = prop.multiProcessorCount;
+  g_max_smem = prop.sharedMemPerBlockOptin;
+  cudaFuncSetAttribute(vpz_k1_entropy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  cudaFuncSetAttribute(vpz_k1_entropy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  cudaFuncSetAttribute(vpz_k3_imdct_ola<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  cudaFuncSetAttribute(vpz_k3_imdct_ola<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute", err);
+  return VPZ_OK;
+}
+
+int sm_count() { return g_sm_count; }
+size_t max_smem_per_block() { return g_max_smem; }
+
+void* alloc(size_t bytes, std::string& err) {
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+  if (e != cudaSuccess) {
+    fail(e, "cudaMalloc", err);
+    return nullptr;
+  }
+  return p;
+}
+void free(void* p) {
+  if (p) cudaFree(p);
+}
+void* host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+Stream* stream_create() {
+  Stream* s = new Stream;
+  if (cudaStreamCreateWithFlags(&s->s, cudaStreamNonBlocking) != cudaSuccess) {
+    delete s;
+    return nullptr;
+  }
+  return s;
+}
+void stream_destroy(Stream* s) {
+  if (!s) return;
+  cudaStreamDestroy(s->s);
+  delete s;
+}
+int stream_sync(Stream* s, std::string& err) {
+  cudaError_t e = cudaStreamSynchronize(s->s);
+  if (e != cudaSuccess) return fail(e, "cudaStreamSynchronize", err);
+  return VPZ_OK;
+}
+
+Event* event_create() {
+  Event* e = new Event;
+  if (cudaEventCreate(&e->e) != cudaSuccess) {
+    delete e;
+    return nullptr;
+  }
+  return e;
+}
+void event_destroy(Event* e) {
+  if (!e) return;
+  cudaEventDestroy(e->e);
+  delete e;
+}
+void event_record(Event* e, Stream* s) { cudaEventRecord(e->e, s->s); }
+float event_elapsed_ms(Event* a, Event* b) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, a->e, b->e) != cudaSuccess) {
+    cudaGetLastError();
+    return -1.f;
+  }
+  return ms;
+}
+
+int h2d(void* dst, const void* src, size_t bytes, Stream* s, std::string& err) {
+  if (!bytes) return VPZ_OK;
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s->s);
+  return e == cudaSuccess ? VPZ_OK : fail(e, "cudaMemcpyAsync H2D", err);
+}
+int d2h(void* dst, const void* src, size_t bytes, Stream* s, std::string& err) {
+  if (!bytes) return VPZ_OK;
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s->s);
+  return e == cudaSuccess ? VPZ_OK : fail(e, "cudaMemcpyAsync D2H", err);
+}
+int d2d(void* dst, const void* src, size_t bytes, Stream* s, std::string& err) {
+  if (!bytes) return VPZ_OK;
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s->s);
+  return e == cudaSuccess ? VPZ_OK : fail(e, "cudaMemcpyAsync D2D", err);
+}
+int fill(void* dst, int byte_value, size_t bytes, Stream* s, std::string& err) {
+  if (!bytes) return VPZ_OK;
+  cudaError_t e = cudaMemsetAsync(dst, byte_value, bytes, s->s);
+  return e == cudaSuccess ? VPZ_OK : fail(e, "cudaMemsetAsync", err);
+}
+
+int launch_k1(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err) {
+  if (p.n_pkts == 0) return VPZ_OK;
+  size_t smem = (size_t)warps * p.smem_words_per_warp * 4;
+  if (smem > g_max_smem) {
+    err = "K1 shared memory request exceeds the device limit";
+    return VPZ_E_UNSUPPORTED;
+  }
+  cudaError_t e = cudaMemsetAsync(p.counter, 0, 4, s->s);
+  if (e != cudaSuccess) return fail(e, "cudaMemsetAsync(counter)", err);
+  if (debug)
+    vpz_k1_entropy<true><<<blocks, warps * 32, smem, s->s>>>(p);
+  else
+    vpz_k1_entropy<false><<<blocks, warps * 32, smem, s->s>>>(p);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k1_entropy", err);
+}
+
+int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream* s, std::string& err) {
+  if (p.n_items == 0) return VPZ_OK;
+  if (smem_bytes > g_max_smem) {
+    err = "K3 shared memory request exceeds the device limit";
+    return VPZ_E_UNSUPPORTED;
+  }
+  int threads = ncb * K3_THREADS_PER_CH;
+  if (fast)
+    vpz_k3_imdct_ola<true><<<p.n_items, threads, smem_bytes, s->s>>>(p, ncb);
+  else
+    vpz_k3_imdct_ola<false><<<p.n_items, threads, smem_bytes, s->s>>>(p, ncb);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k3_imdct_ola", err);
+}
+
+}  // namespace dev
+}  // namespace vpz

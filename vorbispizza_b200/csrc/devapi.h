@@ -1,0 +1,50 @@
+// devapi.h -- the only place the host engine touches the device.  The product implements it with
+// the CUDA runtime + the sm_100a kernels (dev_cuda.cu, no CPU fallback).  tests/emu/ implements
+// the same interface with a thread-per-CUDA-thread emulator so that `pytest -m "not gpu"` can run
+// the unmodified kernel source and the whole host engine on a box without a GPU; that emulator is
+// test infrastructure and is never linked into libvpz.so.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "k1_params.h"
+
+namespace vpz {
+namespace dev {
+
+struct Stream;  // opaque
+struct Event;
+
+int init(int device, std::string& err);  // 0 or VPZ_E_NO_DEVICE / VPZ_E_CUDA
+int device_count();
+int sm_count();
+
+void* alloc(size_t bytes, std::string& err);
+void free(void* p);
+void* host_alloc(size_t bytes);
+void host_free(void* p);
+
+Stream* stream_create();
+void stream_destroy(Stream* s);
+int stream_sync(Stream* s, std::string& err);
+
+Event* event_create();
+void event_destroy(Event* e);
+void event_record(Event* e, Stream* s);
+float event_elapsed_ms(Event* a, Event* b);
+
+int h2d(void* dst, const void* src, size_t bytes, Stream* s, std::string& err);
+int d2h(void* dst, const void* src, size_t bytes, Stream* s, std::string& err);
+int d2d(void* dst, const void* src, size_t bytes, Stream* s, std::string& err);
+int fill(void* dst, int byte_value, size_t bytes, Stream* s, std::string& err);
+
+// K1: `blocks` CTAs of `warps` warps, dynamic shared memory = warps * smem_words_per_warp * 4
+int launch_k1(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err);
+// K3: one CTA per work item, ncb channels side by side (64 threads each)
+int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream* s, std::string& err);
+size_t max_smem_per_block();
+
+}  // namespace dev
+}  // namespace vpz

@@ -1,0 +1,372 @@
+// engine.cpp -- setup cache, packet batcher and launch plan (host side of the batch layer).
+#include "engine.h"
+
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
+#include "../../include/vpz.h"
+#include "bitreader.h"
+
+namespace vpz {
+
+static uint32_t k1_words(const Setup& st) {
+  const VpzSetupHdr* h = st.hdr();
+  const int C = h->channels;
+  const int half_max = 1 << (h->log2_size1 - 1);
+  const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(st.blob.data() + h->residues_off);
+  size_t max_parts = 0;
+  for (int i = 0; i < h->nresidues; i++) {
+    int nvec = rs[i].type == 2 ? 1 : C;
+    int64_t vlen = rs[i].type == 2 ? (int64_t)half_max * C : half_max;
+    int64_t b = std::min<int64_t>(rs[i].begin, vlen), e = std::min<int64_t>(rs[i].end, vlen);
+    int64_t parts = e > b ? (e - b) / rs[i].part_size : 0;
+    max_parts = std::max(max_parts, (size_t)(parts * nvec));
+  }
+  size_t words = (size_t)C * half_max + (size_t)C * 64 + 64 + 66 + 66 + (max_parts + 3) / 4 + 8;
+  return (uint32_t)((words + 31) & ~(size_t)31);
+}
+
+static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
+  const VpzSetupHdr* h = s->host.hdr();
+  s->fast_sizes = h->log2_size0 == 8 && h->log2_size1 == 11;
+  s->k3_floats_per_ch = 2u * (1u << h->log2_size1) + 16u;
+  if (!s->synthetic) s->k1_words_per_warp = k1_words(s->host);
+  size_t bytes = s->host.blob.size() * 4;
+  s->d_blob = dev::alloc(bytes, ctx->last_error);
+  if (!s->d_blob) return VPZ_E_CUDA;
+  int rc = dev::h2d(s->d_blob, s->host.blob.data(), bytes, ctx->stream, ctx->last_error);
+  if (rc) return rc;
+  return dev::stream_sync(ctx->stream, ctx->last_error);
+}
+
+int setup_create(vpz_ctx* ctx, const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt, size_t setup_len,
+                 vpz_setup** out) {
+  uint64_t h = fnv1a64(setup_pkt, setup_len, fnv1a64(id_pkt, id_len));
+  auto range = ctx->setups.equal_range(h);
+  for (auto it = range.first; it != range.second; ++it) {
+    vpz_setup* s = it->second;
+    if (s->id_pkt.size() == id_len && s->setup_pkt.size() == setup_len &&
+        memcmp(s->id_pkt.data(), id_pkt, id_len) == 0 && memcmp(s->setup_pkt.data(), setup_pkt, setup_len) == 0) {
+      s->refs++;
+      *out = s;
+      return VPZ_OK;
+    }
+  }
+  vpz_setup* s = new vpz_setup;
+  s->ctx = ctx;
+  int rc = s->host.parse(id_pkt, id_len, setup_pkt, setup_len, ctx->l1_bits);
+  if (rc) {
+    ctx->last_error = s->host.error;
+    delete s;
+    return rc;
+  }
+  s->id_pkt.assign(id_pkt, id_pkt + id_len);
+  s->setup_pkt.assign(setup_pkt, setup_pkt + setup_len);
+  rc = finish_setup(ctx, s);
+  if (rc) {
+    dev::free(s->d_blob);
+    delete s;
+    return rc;
+  }
+  s->refs = 1;
+  ctx->setups.insert({h, s});
+  *out = s;
+  return VPZ_OK;
+}
+
+// Tables for kernel-only IMDCT runs on caller-provided spectra: window slopes + twiddles only.
+int setup_create_synthetic(vpz_ctx* ctx, int channels, int lg0, int lg1, vpz_setup** out) {
+  if (channels < 1 || channels > VPZ_MAX_CH || lg0 < 6 || lg1 < lg0 || lg1 > 13) {
+    ctx->last_error = "synthetic setup: channels 1..8, block sizes 64..8192";
+    return VPZ_E_ARGUMENT;
+  }
+  vpz_setup* s = new vpz_setup;
+  s->ctx = ctx;
+  s->synthetic = true;
+  Setup& st = s->host;
+  st.id.channels = channels;
+  st.id.size0 = 1 << lg0;
+  st.id.size1 = 1 << lg1;
+  std::vector<uint32_t>& blob = st.blob;
+  blob.assign((sizeof(VpzSetupHdr) + 3) / 4, 0u);
+  while (blob.size() % 4) blob.push_back(0);
+  VpzSetupHdr h;
+  memset(&h, 0, sizeof(h));
+  h.magic = 0x315A5056u;
+  h.channels = (uint8_t)channels;
+  h.log2_size0 = (uint8_t)lg0;
+  h.log2_size1 = (uint8_t)lg1;
+  for (int w = 0; w < 2; w++) {
+    int size = 1 << (w ? lg1 : lg0), M = size / 2, H = size / 4;
+    std::vector<float> slope((size_t)M), tw((size_t)2 * H), roots((size_t)2 * H);
+    window_slope(slope.data(), M);
+    for (int n = 0; n < H; n++) {
+      double a = -M_PI * ((double)n + 0.125) / (double)M, b = -2.0 * M_PI * (double)n / (double)H;
+      tw[2 * n] = (float)cos(a);
+      tw[2 * n + 1] = (float)sin(a);
+      roots[2 * n] = (float)cos(b);
+      roots[2 * n + 1] = (float)sin(b);
+    }
+    auto put = [&](const std::vector<float>& v) {
+      while (blob.size() % 4) blob.push_back(0);
+      uint32_t off = (uint32_t)blob.size();
+      blob.resize(blob.size() + v.size());
+      memcpy(&blob[off], v.data(), v.size() * 4);
+      return off;
+    };
+    h.slope_off[w] = put(slope);
+    h.tw_off[w] = put(tw);
+    h.fft_off[w] = put(roots);
+  }
+  h.total_words = (uint32_t)blob.size();
+  memcpy(blob.data(), &h, sizeof(h));
+  int rc = finish_setup(ctx, s);
+  if (rc) {
+    dev::free(s->d_blob);
+    delete s;
+    return rc;
+  }
+  s->refs = 1;
+  *out = s;
+  return VPZ_OK;
+}
+
+void setup_release(vpz_setup* s) {
+  if (!s) return;
+  if (--s->refs > 0) return;
+  vpz_ctx* ctx = s->ctx;
+  for (auto it = ctx->setups.begin(); it != ctx->setups.end(); ++it)
+    if (it->second == s) {
+      ctx->setups.erase(it);
+      break;
+    }
+  dev::free(s->d_blob);
+  delete s;
+}
+
+static int slot_of(vpz_batch* b, vpz_setup* s) {
+  for (size_t i = 0; i < b->slots.size(); i++)
+    if (b->slots[i] == s) return (int)i;
+  b->slots.push_back(s);
+  return (int)b->slots.size() - 1;
+}
+
+// Plans one run: which packets decode, where their spectra and samples go, and the K3 work items.
+// Mirrors the bookkeeping of StreamDecoder.ReadNextPacket (StreamDecoder.cs:640-694) for a decoder
+// that starts from ResetDecoder state.
+int batch_add_run(vpz_batch* b, vpz_setup* s, const uint8_t* bytes, const uint32_t* offsets, uint32_t n_pkts,
+                  const int32_t* trim) {
+  vpz_ctx* ctx = b->ctx;
+  if (b->synthetic || s->synthetic) {
+    ctx->last_error = "packet runs cannot be added to a synthetic batch";
+    return VPZ_E_INVALID_OP;
+  }
+  const Setup& st = s->host;
+  const int C = st.id.channels;
+  Run run;
+  run.setup = s;
+  run.slot = slot_of(b, s);
+  run.first_valid = (uint32_t)b->pkts_in.n;
+  run.counts.assign(n_pkts, 0);
+  run.out_base = b->total_floats;
+  b->max_channels = std::max(b->max_channels, C);
+  b->uploaded = false;
+
+  bool have_prev = false;
+  int prev_rs = 0, prev_re = 0;
+  int64_t pos = 0;  // samples emitted so far by this run
+  for (uint32_t i = 0; i < n_pkts; i++) {
+    const uint8_t* p = bytes + offsets[i];
+    const uint32_t len = offsets[i + 1] - offsets[i];
+    PacketGeom g = st.packet_geometry(p, len);
+    if (g.bad_mode) {
+      ctx->last_error = "Unused mode index.";  // StreamDecoder.cs:734
+      return VPZ_E_INVALID_DATA;
+    }
+    if (!g.valid) continue;
+    int rs = g.right_start;
+    if (trim && trim[i] > 0) rs = std::max(rs - trim[i], 0);
+    int count = 0;
+    if (have_prev) {
+      int L = prev_re - prev_rs;
+      int slope_len = (g.left_use_size1 ? st.id.size1 : st.id.size0) / 2;
+      if (L > slope_len || L < 0 || g.left_start + L > st.id.size1 || rs < g.left_start) {
+        // the reference slices windowSlope.AsSpan(0, L) and throws; the run ends here
+        run.status = VPZ_E_REF_FAULT;
+        run.stop_packet = (int32_t)i;
+        break;
+      }
+      count = rs - g.left_start;
+    }
+    // stage the bytes: 4-byte aligned start, at least 8 zero bytes after the end
+    size_t off = (b->bytes.n + 3) & ~(size_t)3;
+    size_t end = off + len + 8;
+    end = (end + 3) & ~(size_t)3;
+    if (end > 0xfffffff0ull) {
+      ctx->last_error = "batch exceeds 4 GiB of packet bytes";
+      return VPZ_E_ARGUMENT;
+    }
+    if (!b->bytes.reserve(end)) return VPZ_E_NOMEM;
+    memset(b->bytes.p + b->bytes.n, 0, off - b->bytes.n);
+    if (len) memcpy(b->bytes.p + off, p, len);
+    memset(b->bytes.p + off + len, 0, end - off - len);
+    b->bytes.n = end;
+    b->payload_bytes += len;
+
+    const int M = g.block_size / 2;
+    if (b->spec_floats + (uint64_t)C * M > 0xffffff00ull) {
+      ctx->last_error = "batch exceeds 2^32 spectrum floats; split it";
+      return VPZ_E_ARGUMENT;
+    }
+    VpzPktIn in;
+    in.byte_off = (uint32_t)off;
+    in.byte_len = len;
+    in.spec_off = (uint32_t)b->spec_floats;
+    in.setup_slot = (uint32_t)run.slot;
+    VpzPktOla ola;
+    memset(&ola, 0, sizeof(ola));
+    ola.spec_off = in.spec_off;
+    ola.out_off = (uint32_t)pos;
+    ola.left_start = (uint16_t)g.left_start;
+    ola.right_start = (uint16_t)rs;
+    ola.right_end = (uint16_t)g.right_end;
+    ola.flags = (uint8_t)((g.long_block ? VPZ_OLA_LONG : 0) | (g.left_use_size1 ? VPZ_OLA_LEFT1 : 0) |
+                          (have_prev ? 0 : VPZ_OLA_NOOUT));
+    if (!b->pkts_in.push(in) || !b->pkts_ola.push(ola)) return VPZ_E_NOMEM;
+    b->spec_floats += (uint64_t)C * M;
+    run.counts[i] = count;
+    pos += count;
+    have_prev = true;
+    prev_rs = rs;
+    prev_re = g.right_end;
+  }
+  run.n_valid = (uint32_t)b->pkts_in.n - run.first_valid;
+  run.samples = pos;
+  b->total_floats += (uint64_t)pos * C;
+  // K3 work items: packets 1..n_valid-1 emit; each item re-runs its predecessor as carry seed
+  const uint32_t chunk = (uint32_t)std::max(1, ctx->ola_chunk);
+  for (uint32_t k = 1; k < run.n_valid; k += chunk) {
+    VpzOlaItem it;
+    it.first_pkt = run.first_valid + k;
+    it.n_pkts = std::min(chunk, run.n_valid - k);
+    it.has_pre = 1;
+    it.setup_slot = (uint32_t)run.slot;
+    it.out_base = run.out_base;
+    if (!b->items.push(it)) return VPZ_E_NOMEM;
+  }
+  b->runs.push_back(std::move(run));
+  return (int)b->runs.size() - 1;
+}
+
+int batch_upload(vpz_batch* b) {
+  vpz_ctx* ctx = b->ctx;
+  std::string& err = ctx->last_error;
+  dev::Stream* st = ctx->stream;
+  const size_t np = b->pkts_ola.n;
+  int rc;
+  if (!b->synthetic) {
+    if (!b->d_bytes.reserve(b->bytes.n + 16, err) || !b->d_pkts_in.reserve(np * sizeof(VpzPktIn), err)) return VPZ_E_CUDA;
+    if ((rc = dev::h2d(b->d_bytes.p, b->bytes.p, b->bytes.n, st, err))) return rc;
+    if ((rc = dev::h2d(b->d_pkts_in.p, b->pkts_in.p, np * sizeof(VpzPktIn), st, err))) return rc;
+    if (!b->d_res.reserve(np * sizeof(VpzPktRes), err)) return VPZ_E_CUDA;
+    if (!b->d_spec.reserve(b->spec_floats * 4, err)) return VPZ_E_CUDA;
+  }
+  if (!b->d_pkts_ola.reserve(np * sizeof(VpzPktOla), err) || !b->d_items.reserve(b->items.n * sizeof(VpzOlaItem), err) ||
+      !b->d_pcm.reserve(b->total_floats * 4, err) || !b->d_clip.reserve(np * 4, err) ||
+      !b->d_setups.reserve(b->slots.size() * sizeof(void*), err))
+    return VPZ_E_CUDA;
+  if ((rc = dev::h2d(b->d_pkts_ola.p, b->pkts_ola.p, np * sizeof(VpzPktOla), st, err))) return rc;
+  if ((rc = dev::h2d(b->d_items.p, b->items.p, b->items.n * sizeof(VpzOlaItem), st, err))) return rc;
+  std::vector<const void*> ptrs;
+  for (vpz_setup* s : b->slots) ptrs.push_back(s->d_blob);
+  if ((rc = dev::h2d(b->d_setups.p, ptrs.data(), ptrs.size() * sizeof(void*), st, err))) return rc;
+  if ((rc = dev::stream_sync(st, err))) return rc;  // ptrs is a stack temporary
+  b->uploaded = true;
+  b->decoded = false;
+  return VPZ_OK;
+}
+
+int batch_decode(vpz_batch* b, int clip) {
+  vpz_ctx* ctx = b->ctx;
+  std::string& err = ctx->last_error;
+  dev::Stream* st = ctx->stream;
+  if (!b->uploaded) {
+    int rc = batch_upload(b);
+    if (rc) return rc;
+  }
+  const size_t np = b->pkts_ola.n;
+  int rc;
+  b->launches = 0;
+  dev::event_record(ctx->ev[0], st);
+  bool fast = true;
+  uint32_t k1w = 0, k3f = 0;
+  for (vpz_setup* s : b->slots) {
+    fast = fast && s->fast_sizes;
+    k1w = std::max(k1w, s->k1_words_per_warp);
+    k3f = std::max(k3f, s->k3_floats_per_ch);
+  }
+  if (!b->synthetic && np) {
+    K1Params p;
+    memset(&p, 0, sizeof(p));
+    p.bytes = static_cast<const uint32_t*>(b->d_bytes.p);
+    p.pkts = static_cast<const VpzPktIn*>(b->d_pkts_in.p);
+    p.res = static_cast<VpzPktRes*>(b->d_res.p);
+    p.setups = static_cast<const uint32_t* const*>(b->d_setups.p);
+    p.spec = static_cast<float*>(b->d_spec.p);
+    p.n_pkts = (uint32_t)np;
+    p.counter = ctx->d_counter;
+    p.smem_words_per_warp = k1w;
+    p.dbg = b->dbg;
+    int warps = std::max(1, std::min(8, ctx->k1_warps));
+    size_t smem_block = (size_t)warps * k1w * 4;
+    while (warps > 1 && smem_block > dev::max_smem_per_block()) {
+      warps--;
+      smem_block = (size_t)warps * k1w * 4;
+    }
+    size_t per_sm = std::max<size_t>(1, std::min<size_t>(2048 / (warps * 32), (227 * 1024) / (smem_block + 1024)));
+    size_t blocks = std::min<size_t>((np + warps - 1) / warps, per_sm * (size_t)dev::sm_count());
+    if ((rc = dev::launch_k1(p, b->dbg.hdr != nullptr, (int)std::max<size_t>(1, blocks), warps, st, err))) return rc;
+    b->launches++;
+  }
+  dev::event_record(ctx->ev[1], st);
+  if (b->items.n) {
+    if ((rc = dev::fill(b->d_clip.p, 0xff, np * 4, st, err))) return rc;
+    K3Params p;
+    memset(&p, 0, sizeof(p));
+    p.spec = static_cast<const float*>(b->d_spec.p);
+    p.pkts = static_cast<const VpzPktOla*>(b->d_pkts_ola.p);
+    p.res = b->synthetic ? nullptr : static_cast<const VpzPktRes*>(b->d_res.p);
+    p.items = static_cast<const VpzOlaItem*>(b->d_items.p);
+    p.setups = static_cast<const uint32_t* const*>(b->d_setups.p);
+    p.pcm = static_cast<float*>(b->d_pcm.p);
+    p.clip_first = static_cast<uint32_t*>(b->d_clip.p);
+    p.n_items = (uint32_t)b->items.n;
+    p.clip = clip ? 1 : 0;
+    p.dbg_imdct = b->dbg_imdct;
+    int ncb = std::min(2, b->max_channels);
+    size_t per_ch = fast ? (4 * 576 + 2 * 1024 + 16) : k3f;
+    if ((rc = dev::launch_k3(p, fast, ncb, (size_t)ncb * per_ch * 4, st, err))) return rc;
+    b->launches++;
+  }
+  dev::event_record(ctx->ev[2], st);
+  b->decoded = true;
+  b->clip_fetched = false;
+  return VPZ_OK;
+}
+
+int batch_fetch_clip(vpz_batch* b) {
+  if (b->clip_fetched) return VPZ_OK;
+  vpz_ctx* ctx = b->ctx;
+  const size_t np = b->pkts_ola.n;
+  if (!b->h_clip.reserve(np + 1)) return VPZ_E_NOMEM;
+  b->h_clip.n = np;
+  int rc = dev::d2h(b->h_clip.p, b->d_clip.p, np * 4, ctx->stream, ctx->last_error);
+  if (rc) return rc;
+  if ((rc = dev::stream_sync(ctx->stream, ctx->last_error))) return rc;
+  b->clip_fetched = true;
+  return VPZ_OK;
+}
+
+}  // namespace vpz

@@ -1,0 +1,130 @@
+// engine.h -- host runtime behind the C ABI: context, setup cache, packet batcher, launch plan.
+// Device access goes through devapi.h only.
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "devapi.h"
+#include "setup.h"
+
+struct vpz_ctx;
+
+struct vpz_setup {
+  vpz_ctx* ctx = nullptr;
+  vpz::Setup host;
+  std::vector<uint8_t> id_pkt, setup_pkt;
+  void* d_blob = nullptr;
+  int refs = 0;
+  uint32_t k1_words_per_warp = 0;   // shared memory K1 needs per warp
+  uint32_t k3_floats_per_ch = 0;    // shared memory K3 needs per channel (generic layout)
+  bool fast_sizes = false;          // block sizes 256 / 2048
+  bool synthetic = false;           // window/twiddle tables only (vpz_synth_create)
+};
+
+struct vpz_ctx {
+  int device = 0;
+  vpz::dev::Stream* stream = nullptr;
+  vpz::dev::Event* ev[3] = {nullptr, nullptr, nullptr};
+  std::string last_error;
+  int l1_bits = VPZ_L1_BITS_DEFAULT;
+  int ola_chunk = 32;
+  int k1_warps = 4;
+  std::multimap<uint64_t, vpz_setup*> setups;
+  uint32_t* d_counter = nullptr;
+};
+
+namespace vpz {
+
+template <typename T>
+struct HostBuf {   // growable pinned staging
+  T* p = nullptr;
+  size_t n = 0, cap = 0;
+  ~HostBuf() { dev::host_free(p); }
+  bool reserve(size_t want) {
+    if (want <= cap) return true;
+    size_t nc = cap ? cap : 1024;
+    while (nc < want) nc *= 2;
+    T* np = static_cast<T*>(dev::host_alloc(nc * sizeof(T)));
+    if (!np) return false;
+    if (n) memcpy(np, p, n * sizeof(T));
+    dev::host_free(p);
+    p = np;
+    cap = nc;
+    return true;
+  }
+  bool push(const T& v) {
+    if (!reserve(n + 1)) return false;
+    p[n++] = v;
+    return true;
+  }
+  void clear() { n = 0; }
+};
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  ~DevBuf() { dev::free(p); }
+  bool reserve(size_t bytes, std::string& err) {
+    if (bytes <= cap) return true;
+    dev::free(p);
+    p = nullptr;
+    cap = 0;
+    size_t nc = bytes + bytes / 8 + 256;
+    p = dev::alloc(nc, err);
+    if (!p) return false;
+    cap = nc;
+    return true;
+  }
+};
+
+struct Run {
+  vpz_setup* setup = nullptr;
+  int slot = 0;
+  uint32_t first_valid = 0, n_valid = 0;     // range in the batch packet arrays
+  std::vector<int32_t> counts;               // per submitted packet
+  int64_t samples = 0;
+  uint64_t out_base = 0;                     // float offset in the PCM buffer
+  int status = 0;                            // 0 or VPZ_E_REF_FAULT (run cut short)
+  int32_t stop_packet = -1;                  // submitted-packet index where the run was cut
+};
+
+}  // namespace vpz
+
+struct vpz_batch {
+  vpz_ctx* ctx = nullptr;
+  vpz::HostBuf<uint8_t> bytes;
+  vpz::HostBuf<VpzPktIn> pkts_in;
+  vpz::HostBuf<VpzPktOla> pkts_ola;
+  vpz::HostBuf<VpzOlaItem> items;
+  std::vector<vpz::Run> runs;
+  std::vector<vpz_setup*> slots;
+  uint64_t total_floats = 0, spec_floats = 0;
+  uint64_t payload_bytes = 0;
+  int max_channels = 1;
+  bool uploaded = false, synthetic = false, decoded = false;
+  vpz::DevBuf d_bytes, d_pkts_in, d_pkts_ola, d_items, d_res, d_spec, d_pcm, d_clip, d_setups;
+  vpz::HostBuf<uint32_t> h_clip;
+  bool clip_fetched = false;
+  float ms_k1 = 0, ms_k3 = 0, ms_total = 0;
+  int launches = 0;
+  // debug plumbing (vpz_debug_decode_packet)
+  K1Debug dbg = {nullptr, nullptr, 0, nullptr, 0, nullptr};
+  float* dbg_imdct = nullptr;
+  vpz_setup* owned_setup = nullptr;  // synthetic batches own their table-only setup
+};
+
+namespace vpz {
+int setup_create(vpz_ctx* ctx, const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt, size_t setup_len,
+                 vpz_setup** out);
+int setup_create_synthetic(vpz_ctx* ctx, int channels, int lg0, int lg1, vpz_setup** out);
+void setup_release(vpz_setup* s);
+int batch_add_run(vpz_batch* b, vpz_setup* s, const uint8_t* bytes, const uint32_t* offsets, uint32_t n_pkts,
+                  const int32_t* trim);
+int batch_upload(vpz_batch* b);
+int batch_decode(vpz_batch* b, int clip);
+int batch_fetch_clip(vpz_batch* b);
+}  // namespace vpz

@@ -1,0 +1,39 @@
+// k1_params.h -- kernel parameter blocks (plain structs, shared by host engine and kernels).
+#pragma once
+#include <stdint.h>
+
+#include "vpz_dev.h"
+
+struct K1Debug {                 // all device pointers; used by vpz_debug_decode_packet only
+  int32_t* hdr;                  // vpz_packet_dump as int32 words
+  int32_t* scalars;
+  int32_t scalars_cap;
+  int32_t* classes;
+  int32_t classes_cap;
+  float* residue;                // [ch][n/2] before coupling
+};
+
+struct K1Params {
+  const uint32_t* bytes;         // batch byte buffer (4-byte aligned packets, zero padded)
+  const VpzPktIn* pkts;
+  VpzPktRes* res;
+  const uint32_t* const* setups; // per setup slot: device pointer of the blob
+  float* spec;
+  uint32_t n_pkts;
+  uint32_t* counter;             // work-stealing cursor (zeroed before each launch)
+  uint32_t smem_words_per_warp;
+  K1Debug dbg;
+};
+
+struct K3Params {
+  const float* spec;
+  const VpzPktOla* pkts;
+  const VpzPktRes* res;            // exec masks from K1 (NULL: every channel executes)
+  const VpzOlaItem* items;
+  const uint32_t* const* setups;
+  float* pcm;
+  uint32_t* clip_first;            // per packet: smallest clipped sample index (init 0xffffffff), may be NULL
+  uint32_t n_items;
+  int clip;
+  float* dbg_imdct;                // debug: raw y[0..N) of every packet, [ch][N] at 2*spec_off, may be NULL
+};

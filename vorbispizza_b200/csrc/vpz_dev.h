@@ -1,0 +1,140 @@
+// vpz_dev.h -- structures shared by the host table builder and the sm_100a kernels.
+//
+// One "setup blob" per distinct Vorbis setup (id + setup header pair) is built on the host
+// (setup.cpp) and uploaded once; every kernel argument that refers to codebooks, floors,
+// residues, mappings or modes is an offset into that blob.  The blob is position independent:
+// all references are 32-bit offsets counted in 4-byte words from the start of the blob.
+#pragma once
+#include <stdint.h>
+
+#define VPZ_MAX_CH 8          // channels handled by the GPU path (reference has no limit)
+#define VPZ_MAX_POSTS 64      // Floor1.cs:17 (Posts capacity, quirk Q2)
+#define VPZ_MAX_BOOKS 256
+#define VPZ_MAX_MODES 64
+#define VPZ_L1_BITS_DEFAULT 9 // first-level Huffman table width (reference: 10, Huffman.cs:12)
+
+// ---- codebook (Codebook.cs, Huffman.cs) ------------------------------------------------
+// L1 table entry: (value << 8) | length for codes with length <= l1_bits, replicated over the
+// don't-care bits exactly like Huffman.GenerateTable.  Codes longer than l1_bits:
+// 0x80000000 | range_id, where range_id indexes `ranges` = {lo, hi} into the long-code arrays
+// (sorted by MSB-first left-aligned code).  0 = no code with this prefix (DecodeScalar -> -1).
+struct VpzBook {
+  uint32_t l1_off;      // word offset of the L1 table, 1 << l1_bits entries
+  uint32_t range_off;   // word offset of {lo,hi} pairs
+  uint32_t lcode_off;   // word offset of left-aligned long codes (ascending)
+  uint32_t linfo_off;   // word offset of (value << 8) | length per long code
+  uint32_t vq_off;      // word offset of the float lookup [entries * dims], 0 when map_type == 0
+  uint32_t entries;
+  uint16_t dims;
+  uint8_t l1_bits;
+  uint8_t max_bits;     // Codebook._maxBits (quirk Q7 kept for the record; decode does not need it)
+  uint8_t map_type;
+  uint8_t pad[3];
+  uint32_t long_n;
+};
+
+// ---- floor 1 (Floor1.cs:39-155) ---------------------------------------------------------
+struct VpzFloor1 {
+  uint8_t partitions;
+  uint8_t multiplier;   // 1..4
+  uint8_t ybits;
+  uint8_t xcount;       // posts incl. the two end posts, <= 64
+  uint16_t range;
+  uint16_t pad0;
+  uint8_t part_class[32];
+  uint8_t class_dim[16];
+  uint8_t class_sub[16];
+  uint8_t class_master[16];
+  int16_t sub_books[16][8];  // -1: no book, value 0
+  uint16_t xlist[VPZ_MAX_POSTS + 1];
+  uint8_t lneigh[VPZ_MAX_POSTS + 1];
+  uint8_t hneigh[VPZ_MAX_POSTS + 1];
+  uint8_t sortidx[VPZ_MAX_POSTS + 1];
+  uint8_t pad1[3];
+};
+
+// ---- residue 0/1/2 (Residue0.cs:25-115) -------------------------------------------------
+struct VpzResidue {
+  uint8_t type;
+  uint8_t classifications;
+  uint8_t class_book;
+  uint8_t max_stages;
+  uint32_t begin, end, part_size;
+  uint32_t decode_map_off;   // word offset; one byte per (classword, dim) packed 4 per word
+  uint32_t decode_map_len;   // partvals * classbook.dims (quirk Q8 bound)
+  uint8_t cascade[64];
+  uint8_t has_books[64];
+  uint8_t books[64][8];
+};
+
+// ---- mapping (Mapping.cs:19-95) ---------------------------------------------------------
+struct VpzMapping {
+  uint8_t submaps;
+  uint8_t coupling_steps;
+  uint8_t pad[2];
+  uint8_t mag[32], ang[32];       // GPU path: at most 32 coupling steps
+  uint8_t mux[VPZ_MAX_CH];
+  uint8_t submap_floor[16], submap_residue[16];
+};
+
+struct VpzMode {
+  uint8_t block_flag;
+  uint8_t mapping;
+};
+
+// Header at word 0 of the blob.
+struct VpzSetupHdr {
+  uint32_t magic;           // 'VPZ1'
+  uint32_t total_words;
+  uint8_t channels;
+  uint8_t log2_size0, log2_size1;
+  uint8_t mode_bits;
+  uint8_t nmodes, nmappings, nfloors, nresidues;
+  uint32_t nbooks;
+  uint32_t books_off, floors_off, residues_off, mappings_off, modes_off;
+  uint32_t slope_off[2];    // window slopes, size0/2 and size1/2 floats (BlocksizeDerivedCache.cs)
+  uint32_t tw_off[2];       // IMDCT pre/post twiddle exp(-i*pi*(n+1/8)/M), interleaved re,im, N/4 pairs
+  uint32_t fft_off[2];      // FFT roots exp(-2*pi*i*k/H), interleaved re,im, H = N/4 pairs
+  uint32_t db_off;          // 256 floats, Floor1.cs:407-473
+};
+
+// ---- per-packet descriptors ------------------------------------------------------------
+// K1 input: where the packet bytes are and where its spectrum goes.
+struct VpzPktIn {
+  uint32_t byte_off;        // into the batch byte buffer; packet is followed by >= 8 zero bytes
+  uint32_t byte_len;
+  uint32_t spec_off;        // float offset of [channels][n/2] in the spectrum buffer
+  uint32_t setup_slot;      // index into the batch's setup pointer table
+};
+
+// K1 output / K3 input.
+struct VpzPktRes {
+  uint8_t exec_mask;        // bit ch set: channel has its own floor energy -> IMDCT runs (Mapping.cs:185)
+  uint8_t status;           // 0 ok, 1 residue decode hit end of packet (kept what was decoded)
+  uint16_t bits_used_lo;    // low 16 bits of the final bit cursor (debug / stats)
+};
+
+// K3 per-packet descriptor (host built from Mode.GetPacketInfo, Mode.cs:30-66)
+struct VpzPktOla {
+  uint32_t spec_off;        // as VpzPktIn
+  uint32_t out_off;         // sample offset (per channel) inside the stream's output region
+  uint16_t left_start, right_start;   // right_start already EOS-trimmed (StreamDecoder.cs:658-666)
+  uint16_t right_end;
+  uint8_t flags;            // bit0 long block, bit1 left slope uses size1 (LeftUseSize1), bit2 no output (first after reset)
+  uint8_t pad;
+};
+#define VPZ_OLA_LONG 1
+#define VPZ_OLA_LEFT1 2
+#define VPZ_OLA_NOOUT 4
+
+// K3 work item: a run of consecutive packets of one stream.
+struct VpzOlaItem {
+  uint32_t first_pkt;       // index into the batch packet arrays
+  uint32_t n_pkts;          // packets that emit output
+  uint32_t has_pre;         // 1: packet first_pkt-1 belongs to the same stream and seeds the carry
+  uint32_t setup_slot;
+  uint64_t out_base;        // float offset of the stream's output region in the batch PCM buffer
+};
+// No overlap state lives on the device between batches: the host re-submits the last valid
+// packet of a stream as the "pre" packet of its next batch (it is decoded again and only seeds
+// the carry), which is also exactly how SeekTo pre-roll works (StreamDecoder.cs:817-880).
