@@ -1,0 +1,370 @@
+#!/usr/bin/env python3
+"""bench.py -- decoded channel-samples/s of the B200 Vorbis decode path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE config 4 -- 4,096 concurrent streams per GPU replicated /
+offset from the four TestFiles, full entropy + floor + residue + coupling + IMDCT + window/OLA
+decode.  Streams are independent, so ranks shard them with no collective ("scaling": "weak": each
+GPU gets its own 4,096 streams; `--scaling strong` splits 4,096 over the ranks instead).
+
+A step = one pass of the hot path (K1 entropy/floor/coupling + K3 IMDCT/OLA) over the whole batch.
+  value : whole-job channel-samples/s with packets and tables already resident in HBM, timed with
+          CUDA events on the library's stream, max over ranks.
+  e2e   : the same metric through the reference-facing C ABI with HOST buffers
+          (vpz_decode_files: Ogg images in host memory -> page scan + CRC + header/packet walk on the
+          host -> H2D -> K1 -> K3 -> D2H into pinned host PCM), wall clock, max over ranks.
+  roofline / roofline_k3 : algorithmic bytes / event-timed kernel duration vs the
+          measured HBM copy peak in MEASURED_PEAKS.json.
+  cpu_baseline : the CPU oracle (C restatement of the reference .NET path; .NET is not available
+          here) on all host cores, one stream per thread, bounded sample.  N=1, rank 0 only.
+`--impl reference` times that same oracle as the reference arm.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+FILES = ["1test", "2test", "3test", "issue6test"]
+METRIC = "decoded channel-samples/sec"
+UNIT = "channel-samples/s"
+
+
+def load_files():
+    out = []
+    for n in FILES:
+        with open(os.path.join(ROOT, "tests", "data", n + ".ogg"), "rb") as f:
+            out.append(f.read())
+    return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.path = "/tmp/vpz_clocks_%d_%d.csv" % (os.getpid(), index)
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.proc:
+            return out
+        self.proc.terminate()  # the exact PID we started
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 8:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    mx.append(float(f[2]))
+                    power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nme, v in zip(names, f[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": max(power) if power else None}
+        return out
+
+
+def pinned_array(lib, nfloats):
+    p = lib.vpz_host_alloc(int(nfloats) * 4)
+    if not p:
+        raise MemoryError("vpz_host_alloc(%d floats)" % nfloats)
+    arr = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(int(nfloats),))
+    return arr, p
+
+
+def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path on the host cores.  The
+    reference is C# and cannot be built here, so this is the oracle port (cpu_baseline.kind "port")."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    files = load_files()
+    cores = os.cpu_count() or 1
+    njobs = 16 * cores  # bounded sample: 16 streams per thread per step (4 of each TestFile)
+    for _ in range(args.warmup):
+        ob.bench_decode(files, max(4, njobs // 4), cores)
+    total, sec = 0, 0.0
+    for _ in range(args.steps):
+        n, s = ob.bench_decode(files, njobs, cores)
+        total += n
+        sec += s
+    v = total / sec
+    sample = "%d whole streams per step (%d per thread, round-robin over the 4 TestFiles), %d steps" % (
+        njobs, 16, args.steps)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (TestFiles replicated)",
+        "config": {"workload": "config4: concurrent whole-stream decode of replicated TestFiles (bounded sample)",
+                   "streams_per_step": njobs, "threads": cores,
+                   "note": "C restatement of the reference .NET decoder (oracle/); no .NET runtime in this image"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (weak) / in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--lib", default=None, help=argparse.SUPPRESS)  # dry-run the script logic on the emulated test build
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    dry = args.lib is not None
+    if not dry:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        if world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dry:
+            return
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    from vorbispizza_b200 import Batch, Context, VorbisReader
+
+    ctx = Context(local_rank, lib_path=args.lib)  # raises without libvpz.so / without a B200: no CPU fallback
+    lib = ctx.lib
+    files = load_files()
+    n_streams = args.streams if args.scaling == "weak" else max(1, args.streams // world)
+
+    # ---- workload: packets of every TestFile through the product's own Ogg layer -------------
+    per_file = []
+    for data in files:
+        with VorbisReader(ctx, data) as r:
+            pk = r.audio_packets()
+            st = ctx.create_setup(r.header_packet(0), r.header_packet(2))
+            blob = np.frombuffer(b"".join(p["data"] for p in pk), np.uint8)
+            offs = np.zeros(len(pk) + 1, np.uint32)
+            offs[1:] = np.cumsum([len(p["data"]) for p in pk])
+            per_file.append(dict(setup=st, blob=blob, offs=offs, n=len(pk), ch=r.channels))
+    batch = Batch(ctx)
+    t_plan = time.perf_counter()
+    first_stream = rank * n_streams if args.scaling == "strong" else 0
+    for i in range(n_streams):
+        g = first_stream + i
+        f = per_file[g % len(files)]
+        # replica r starts at audio packet (7 r) mod count; the packets before it form a second run,
+        # so every packet of the file is decoded once per replica (each run re-seeds its overlap)
+        k = (7 * (g // len(files))) % f["n"]
+        batch.add_run_raw(f["setup"], f["blob"], np.ascontiguousarray(f["offs"][k:]))
+        if k > 0:
+            batch.add_run_raw(f["setup"], f["blob"], np.ascontiguousarray(f["offs"][:k + 2]))
+    t_plan = time.perf_counter() - t_plan
+    batch.upload()
+    samples_rank = batch.total_floats          # one channel-sample = one fp32 PCM value
+    packets_rank = batch.total_packets
+    bytes_rank = batch.total_bytes
+
+    # ---- value: device-resident, K steps back to back between two events --------------------
+    for _ in range(args.warmup):
+        batch.decode(clip=True, sync=False)
+    batch.sync()
+    clocks = ClockSampler(local_rank)
+    barrier()
+    clocks.start()
+    launches0 = lib.vpz_ctx_kernel_launches(ctx._h)
+    t_wall = time.perf_counter()
+    lib.vpz_ctx_mark(ctx._h, 0)
+    for _ in range(args.steps):
+        batch.decode(clip=True, sync=False)
+    lib.vpz_ctx_mark(ctx._h, 1)
+    ms = lib.vpz_ctx_elapsed_ms(ctx._h, 0, 1)
+    batch.sync()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = lib.vpz_ctx_kernel_launches(ctx._h) - launches0
+    ms_max = max_over_ranks(ms)
+    total_samples = sum_over_ranks(float(samples_rank))
+    value = total_samples * args.steps / (ms_max * 1e-3)
+
+    # ---- per-kernel durations (events around each kernel), averaged over K more steps ----------
+    k1, k3 = [], []
+    for _ in range(args.steps):
+        batch.decode(clip=True, sync=True)
+        _, a, b, _ = batch.last_ms()
+        k1.append(a)
+        k3.append(b)
+    clk = clocks.stop()
+    k1_ms, k3_ms = float(np.mean(k1)), float(np.mean(k3))
+    peak, peak_src = measured_peak()
+    # algorithmic bytes per launch: K1 reads the packet bytes and writes the fp32
+    # spectrum (4 B per channel-sample); K3 reads that spectrum and writes fp32 PCM (8 B per
+    # channel-sample).
+    k1_bytes = bytes_rank + 4.0 * samples_rank
+    k3_bytes = 8.0 * samples_rank
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
+
+    def roof(name, nbytes, t_ms):
+        a = nbytes / (t_ms * 1e-3) / 1e9
+        return {"kernel": name, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+                "traffic": traffic.get(name), "peak_source": peak_src, "ms_per_launch": t_ms,
+                "algorithmic_bytes_per_launch": nbytes}
+
+    roof_k1 = roof("vpz_k1_entropy", k1_bytes, k1_ms)
+    roof_k3 = roof("vpz_k3_imdct_ola", k3_bytes, k3_ms)
+    dominant = roof_k1 if k1_ms >= k3_ms else roof_k3
+
+    # ---- e2e: Ogg bytes in host memory -> PCM in pinned host memory, through vpz_decode_files ----
+    e2e = None
+    if not args.no_e2e:
+        e_files = [files[(first_stream + i) % len(files)] for i in range(n_streams)]
+        keep = [np.frombuffer(f, np.uint8) for f in e_files]
+        ptrs = (C.c_void_p * n_streams)(*[k.ctypes.data for k in keep])
+        lens = (C.c_size_t * n_streams)(*[k.size for k in keep])
+        counts = np.zeros(n_streams, np.int64)
+        # sizes: whole files emit the same samples as the two-run replicas minus the re-seeded packet
+        e_total = ctx.check(lib.vpz_decode_files(ctx._h, n_streams, ptrs, lens, 1, None, 0, counts.ctypes.data))
+        dst, dst_p = pinned_array(lib, e_total)
+        for _ in range(2):
+            ctx.check(lib.vpz_decode_files(ctx._h, n_streams, ptrs, lens, 1, dst.ctypes.data, dst.size,
+                                           counts.ctypes.data))
+        h0, d0 = lib.vpz_transfer_bytes(0), lib.vpz_transfer_bytes(1)
+        e_steps = args.steps
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            got = ctx.check(lib.vpz_decode_files(ctx._h, n_streams, ptrs, lens, 1, dst.ctypes.data, dst.size,
+                                                 counts.ctypes.data))
+        barrier()
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        assert got == e_total
+        e_samples = sum_over_ranks(float(e_total))
+        e2e = {"value": e_samples * e_steps / t_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": (lib.vpz_transfer_bytes(0) - h0) // e_steps,
+               "d2h_bytes_per_step": (lib.vpz_transfer_bytes(1) - d0) // e_steps,
+               "ms_per_step": 1e3 * t_e2e / e_steps, "steps": e_steps,
+               "api": "vpz_decode_files (host Ogg images -> pinned host PCM)"}
+        lib.vpz_host_free(dst_p)
+
+    # ---- cpu baseline (rank 0, N=1): the oracle on all host cores, bounded sample ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_binding as ob   # the checker, timed as the reported CPU baseline only
+        cores = os.cpu_count() or 1
+        n0, s0 = ob.bench_decode(files, 4 * cores, cores)
+        njobs = int(max(4 * cores, min(n_streams, (args.cpu_seconds / max(s0, 1e-3)) * 4 * cores)))
+        njobs -= njobs % 4
+        n1, s1 = ob.bench_decode(files, njobs, cores)
+        cpu = {"value": n1 / s1, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "%d of the %d streams (whole files, round-robin over the 4 TestFiles), one stream per thread, "
+                         "%.1f s wall" % (njobs, n_streams, s1)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic (TestFiles replicated/offset)",
+            "config": {
+                "workload": "config4: %d concurrent streams per GPU replicated/offset from TestFiles/{1,2,3,issue6}test.ogg, "
+                            "full entropy+floor+residue+IMDCT decode, stream-sharded" % n_streams,
+                "streams_per_gpu": n_streams, "packets_per_gpu": int(packets_rank),
+                "compressed_bytes_per_gpu": int(bytes_rank), "channel_samples_per_gpu": int(samples_rank),
+                "x_realtime": value / 44100.0, "parallelism": "stream-sharded, no collective",
+                "l2": "inputs larger than L2: %.0f MB packet bytes + %.1f GB spectra per step vs 126 MB L2"
+                      % (bytes_rank / 1e6, 4.0 * samples_rank / 1e9),
+                "host_plan_s": t_plan,
+            },
+            "clocks": clk, "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
+            "roofline": dominant, "roofline_k1": roof_k1, "roofline_k3": roof_k3,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    batch.close()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,14 @@ int vpz_device_count(void);
  * CTA, default 4). */
 int vpz_ctx_set(vpz_ctx* ctx, const char* key, int value);
 
+/* Device-side stopwatch on the context's stream: vpz_ctx_mark records CUDA event `slot` (0..7) on
+ * the stream all of this context's kernels and copies are issued on; vpz_ctx_elapsed_ms waits for
+ * slot b and returns the milliseconds between two marks (< 0 on error). */
+int vpz_ctx_mark(vpz_ctx* ctx, int slot);
+float vpz_ctx_elapsed_ms(vpz_ctx* ctx, int slot_a, int slot_b);
+/* Number of kernels this library has launched on the context so far. */
+int64_t vpz_ctx_kernel_launches(const vpz_ctx* ctx);
+
 /* ---- setup: StreamDecoder.LoadStreamHeader + LoadBooks -------------------------------- */
 typedef struct {
   int32_t channels, sample_rate;
@@ -105,7 +113,9 @@ int vpz_batch_reset(vpz_batch* b);
  * packet again as the first packet of the next run (this is also the seek pre-roll).
  *   bytes/offsets : packet i is bytes[offsets[i] .. offsets[i+1])
  *   trim          : NULL, or per packet the number of samples to pull RightStart back by
- *                   (end-of-stream granule trim, StreamDecoder.cs:658-666)
+ *                   (end-of-stream granule trim, StreamDecoder.cs:658-666); a negative value
+ *                   instead extends the packet's output by that many samples of its raw right
+ *                   half (the drain of StreamDecoder.cs:451-455)
  * Returns the run index (>= 0).  Packets the reference would skip (header bit set, empty decode)
  * are skipped; an unused mode index fails the call with VPZ_E_INVALID_DATA. */
 int vpz_batch_add_run(vpz_batch* b, vpz_setup* s, const uint8_t* bytes, const uint32_t* offsets,
@@ -147,6 +157,9 @@ const float* vpz_batch_device_pcm(const vpz_batch* b);
 /* Device time of the last vpz_batch_decode in milliseconds: which = 0 total, 1 entropy/floor (K1),
  * 3 IMDCT/OLA (K3); number of kernel launches in `launches` (may be NULL). */
 float vpz_batch_last_ms(vpz_batch* b, int which, int* launches);
+
+/* Bytes this process has copied so far: which = 0 host->device, 1 device->host. */
+uint64_t vpz_transfer_bytes(int which);
 
 /* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
 void* vpz_host_alloc(size_t bytes);

@@ -147,6 +147,12 @@ uint32_t vo_crc_ogg(const uint8_t* data, size_t len, uint32_t crc);
 /* Mode.GetPacketInfo given the sizes and flags (Mode.cs:30-66) */
 void vo_packet_info(int size0, int size1, int block_flag, int prev_flag, int next_flag, int32_t info[6]);
 
+/* ---- host-core baseline (vo_bench.c) ---------------------------------------------------- */
+/* Decodes njobs whole streams (job j = file j % nfiles) TestApp-style on nthreads threads; returns
+ * channel-samples decoded, *seconds = wall clock. */
+int64_t vo_bench_decode(const uint8_t* const* datas, const size_t* lens, int nfiles, int njobs, int nthreads,
+                        double* seconds);
+
 #ifdef __cplusplus
 }
 #endif

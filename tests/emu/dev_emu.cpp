@@ -3,6 +3,8 @@
 
 #include <stdlib.h>
 
+#include <chrono>
+
 #include "../../include/vpz.h"
 #include "../../vorbispizza_b200/csrc/devapi.h"
 #include "../../vorbispizza_b200/csrc/k1_entropy.cuh"
@@ -48,7 +50,7 @@ struct Stream {
   int dummy;
 };
 struct Event {
-  int dummy;
+  double t = 0;
 };
 
 int init(int, std::string&) { return VPZ_OK; }
@@ -64,8 +66,12 @@ void stream_destroy(Stream* s) { delete s; }
 int stream_sync(Stream*, std::string&) { return VPZ_OK; }
 Event* event_create() { return new Event; }
 void event_destroy(Event* e) { delete e; }
-void event_record(Event*, Stream*) {}
-float event_elapsed_ms(Event*, Event*) { return 0.f; }
+void event_record(Event* e, Stream*) {
+  e->t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+int event_sync(Event*, std::string&) { return VPZ_OK; }
+float event_elapsed_ms(Event* a, Event* b) { return (float)(b->t - a->t); }
+unsigned long long transfer_bytes(int) { return 0; }
 int h2d(void* d, const void* s, size_t n, Stream*, std::string&) {
   memcpy(d, s, n);
   return VPZ_OK;

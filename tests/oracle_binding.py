@@ -104,6 +104,8 @@ def lib():
     L.vo_crc_ogg.restype = C.c_uint32
     L.vo_crc_ogg.argtypes = [C.c_void_p, C.c_size_t, C.c_uint32]
     L.vo_packet_info.argtypes = [C.c_int] * 5 + [C.POINTER(C.c_int32)]
+    L.vo_bench_decode.restype = C.c_int64
+    L.vo_bench_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -338,3 +340,14 @@ def packet_info(size0, size1, block_flag, prev_flag, next_flag):
     a = (C.c_int32 * 6)()
     lib().vo_packet_info(size0, size1, int(block_flag), int(prev_flag), int(next_flag), a)
     return list(a)
+
+
+def bench_decode(files, njobs, nthreads):
+    """Host-core baseline: decodes njobs whole streams (round-robin over `files`) on nthreads
+    threads inside the oracle; returns (channel_samples, seconds)."""
+    keep = [np.frombuffer(f, np.uint8) for f in files]
+    ptrs = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
+    lens = (C.c_size_t * len(keep))(*[k.size for k in keep])
+    sec = C.c_double(0)
+    n = lib().vo_bench_decode(ptrs, lens, len(keep), njobs, nthreads, C.byref(sec))
+    return n, sec.value

@@ -1,0 +1,56 @@
+"""CPU suite: the host engine (setup tables, batcher, reader, Ogg layer) and the UNMODIFIED kernel
+source compiled against the CUDA emulator (tests/emu), checked against the oracle.  Sized to run in
+a few minutes; the full-size versions of the same cases are in test_gpu_parity.py."""
+import pytest
+
+import cases
+
+
+@pytest.mark.parametrize("name,stride", [("1test", 1), ("2test", 31), ("3test", 37), ("issue6test", 41)])
+def test_stage_parity(emu_ctx, name, stride):
+    assert cases.stage_parity(emu_ctx, name, stride=stride) > 0
+
+
+@pytest.mark.parametrize("name,stride", [("2test", 61), ("3test", 73)])
+def test_stage_parity_truncated_packets(emu_ctx, name, stride):
+    assert cases.stage_parity(emu_ctx, name, stride=stride, truncate=True) > 0
+
+
+@pytest.mark.parametrize("clip", [True, False])
+def test_batch_pcm_1test(emu_ctx, clip):
+    cases.batch_pcm_parity(emu_ctx, "1test", clip)
+
+
+def test_reader_1test(emu_ctx):
+    total, calls = cases.reader_parity(emu_ctx, "1test", lookahead=7)
+    assert total == 17318
+
+
+def test_reader_2test_small_windows(emu_ctx):
+    total, _ = cases.reader_parity(emu_ctx, "2test", lookahead=100)
+    assert total == 315790
+
+
+def test_reader_planar_partial(emu_ctx):
+    cases.reader_planar_and_partial(emu_ctx, "1test")
+
+
+def test_seek_1test(emu_ctx):
+    cases.seek_parity(emu_ctx, "1test", [0, 1, 1000, 5000, 17317, 17318, 17319, 20000, 4000], nread=600, lookahead=4)
+
+
+def test_seek_3test_few(emu_ctx):
+    cases.seek_parity(emu_ctx, "3test", [100000, 250, 287000], nread=1500, lookahead=4)
+
+
+def test_synth_imdct_ola(emu_ctx):
+    cases.synth_parity(emu_ctx, channels=2, n_streams=2, n_blocks=14)
+
+
+def test_synth_generic_block_sizes(emu_ctx):
+    cases.synth_parity(emu_ctx, channels=1, n_streams=1, n_blocks=8, lg0=6, lg1=9)
+    cases.synth_parity(emu_ctx, channels=3, n_streams=1, n_blocks=6, lg0=7, lg1=10, clip=True)
+
+
+def test_decode_files(emu_ctx):
+    cases.decode_files_parity(emu_ctx, ["1test", "1test"])

@@ -53,6 +53,9 @@ _SIGS = {
     "vpz_ctx_destroy": (None, [_P]),
     "vpz_device_count": (C.c_int, []),
     "vpz_ctx_set": (C.c_int, [_P, C.c_char_p, C.c_int]),
+    "vpz_ctx_mark": (C.c_int, [_P, C.c_int]),
+    "vpz_ctx_elapsed_ms": (C.c_float, [_P, C.c_int, C.c_int]),
+    "vpz_ctx_kernel_launches": (C.c_int64, [_P]),
     "vpz_setup_create": (C.c_int, [_P, _P, C.c_size_t, _P, C.c_size_t, C.POINTER(_P)]),
     "vpz_setup_release": (None, [_P]),
     "vpz_setup_get_info": (C.c_int, [_P, C.POINTER(SetupInfo)]),
@@ -77,6 +80,7 @@ _SIGS = {
     "vpz_batch_run_offset": (C.c_int64, [_P, C.c_int]),
     "vpz_batch_device_pcm": (_P, [_P]),
     "vpz_batch_last_ms": (C.c_float, [_P, C.c_int, C.POINTER(C.c_int)]),
+    "vpz_transfer_bytes": (C.c_uint64, [C.c_int]),
     "vpz_host_alloc": (_P, [C.c_size_t]),
     "vpz_host_free": (None, [_P]),
     "vpz_debug_decode_packet": (C.c_int, [_P, _P, _P, C.c_size_t, C.POINTER(PacketDump), _P, C.c_int32, _P,

@@ -152,6 +152,10 @@ void event_destroy(Event* e) {
   delete e;
 }
 void event_record(Event* e, Stream* s) { cudaEventRecord(e->e, s->s); }
+int event_sync(Event* e, std::string& err) {
+  cudaError_t r = cudaEventSynchronize(e->e);
+  return r == cudaSuccess ? VPZ_OK : fail(r, "cudaEventSynchronize", err);
+}
 float event_elapsed_ms(Event* a, Event* b) {
   float ms = 0.f;
   if (cudaEventElapsedTime(&ms, a->e, b->e) != cudaSuccess) {
@@ -161,13 +165,18 @@ float event_elapsed_ms(Event* a, Event* b) {
   return ms;
 }
 
+static unsigned long long g_h2d_bytes = 0, g_d2h_bytes = 0;
+unsigned long long transfer_bytes(int which) { return which ? g_d2h_bytes : g_h2d_bytes; }
+
 int h2d(void* dst, const void* src, size_t bytes, Stream* s, std::string& err) {
   if (!bytes) return VPZ_OK;
+  g_h2d_bytes += bytes;
   cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s->s);
   return e == cudaSuccess ? VPZ_OK : fail(e, "cudaMemcpyAsync H2D", err);
 }
 int d2h(void* dst, const void* src, size_t bytes, Stream* s, std::string& err) {
   if (!bytes) return VPZ_OK;
+  g_d2h_bytes += bytes;
   cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, s->s);
   return e == cudaSuccess ? VPZ_OK : fail(e, "cudaMemcpyAsync D2H", err);
 }

@@ -33,12 +33,14 @@ int stream_sync(Stream* s, std::string& err);
 Event* event_create();
 void event_destroy(Event* e);
 void event_record(Event* e, Stream* s);
+int event_sync(Event* e, std::string& err);
 float event_elapsed_ms(Event* a, Event* b);
 
 int h2d(void* dst, const void* src, size_t bytes, Stream* s, std::string& err);
 int d2h(void* dst, const void* src, size_t bytes, Stream* s, std::string& err);
 int d2d(void* dst, const void* src, size_t bytes, Stream* s, std::string& err);
 int fill(void* dst, int byte_value, size_t bytes, Stream* s, std::string& err);
+unsigned long long transfer_bytes(int which);  // process-wide bytes copied so far: 0 host->device, 1 device->host
 
 // K1: `blocks` CTAs of `warps` warps, dynamic shared memory = warps * smem_words_per_warp * 4
 int launch_k1(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err);

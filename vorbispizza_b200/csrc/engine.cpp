@@ -72,6 +72,15 @@ int setup_create(vpz_ctx* ctx, const uint8_t* id_pkt, size_t id_len, const uint8
   }
   s->refs = 1;
   ctx->setups.insert({h, s});
+  // the context keeps recently built tables alive (parse + upload once per distinct setup even
+  // when every stream that used it has been closed in between)
+  s->refs++;
+  ctx->recent.push_back(s);
+  if (ctx->recent.size() > 64) {
+    vpz_setup* old = ctx->recent.front();
+    ctx->recent.erase(ctx->recent.begin());
+    setup_release(old);
+  }
   *out = s;
   return VPZ_OK;
 }
@@ -188,6 +197,9 @@ int batch_add_run(vpz_batch* b, vpz_setup* s, const uint8_t* bytes, const uint32
     if (!g.valid) continue;
     int rs = g.right_start;
     if (trim && trim[i] > 0) rs = std::max(rs - trim[i], 0);
+    // negative trim: also emit that many samples of the raw right half (the drain of
+    // StreamDecoder.cs:451-455 when the end-of-stream packet that follows cannot be decoded)
+    if (trim && trim[i] < 0) rs = std::min(rs - trim[i], g.right_end);
     int count = 0;
     if (have_prev) {
       int L = prev_re - prev_rs;
@@ -329,6 +341,7 @@ int batch_decode(vpz_batch* b, int clip) {
     size_t blocks = std::min<size_t>((np + warps - 1) / warps, per_sm * (size_t)dev::sm_count());
     if ((rc = dev::launch_k1(p, b->dbg.hdr != nullptr, (int)std::max<size_t>(1, blocks), warps, st, err))) return rc;
     b->launches++;
+    ctx->kernel_launches++;
   }
   dev::event_record(ctx->ev[1], st);
   if (b->items.n) {
@@ -349,6 +362,7 @@ int batch_decode(vpz_batch* b, int clip) {
     size_t per_ch = fast ? (4 * 576 + 2 * 1024 + 16) : k3f;
     if ((rc = dev::launch_k3(p, fast, ncb, (size_t)ncb * per_ch * 4, st, err))) return rc;
     b->launches++;
+    ctx->kernel_launches++;
   }
   dev::event_record(ctx->ev[2], st);
   b->decoded = true;

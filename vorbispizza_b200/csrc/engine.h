@@ -12,6 +12,7 @@
 #include "setup.h"
 
 struct vpz_ctx;
+struct vpz_batch;
 
 struct vpz_setup {
   vpz_ctx* ctx = nullptr;
@@ -34,7 +35,11 @@ struct vpz_ctx {
   int ola_chunk = 32;
   int k1_warps = 4;
   std::multimap<uint64_t, vpz_setup*> setups;
+  std::vector<vpz_setup*> recent;     // setups the context itself holds a reference on (LRU, 64)
   uint32_t* d_counter = nullptr;
+  vpz::dev::Event* marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int64_t kernel_launches = 0;
+  struct vpz_batch* bulk = nullptr;   // reused by vpz_decode_files so device buffers persist between calls
 };
 
 namespace vpz {

@@ -1,0 +1,821 @@
+// reader.cpp -- the IVorbisReader / IStreamDecoder side of the C ABI (include/vpz.h, "reader" and
+// "bulk" layers).
+//
+// The reference decodes one packet per Read call on the CPU (StreamDecoder.Read,
+// StreamDecoder.cs:418-498).  Here a stream is decoded AHEAD in windows of `lookahead` packets: the
+// host walks the packet provider, replays the reference's position / end-of-stream bookkeeping on
+// the packet headers alone (it never needs PCM values), submits the window to the GPU batch layer
+// as one run and parks the interleaved PCM in pinned host memory.  Read() then hands that PCM out
+// with exactly the reference's call-by-call behaviour: at most one packet per call, same sample
+// counts, same SamplePosition / IsEndOfStream / HasClipped transitions, same error points.
+//
+// Reference behaviour followed (file:line):
+//   VorbisReader.Initialize / ProcessNewStream / SwitchStreams / ReadSamples   VorbisReader.cs:56-85,191-253
+//   StreamDecoder.ProcessHeaderPackets / LoadComments                          StreamDecoder.cs:125-260
+//   StreamDecoder.Read / ReadNextPacket / DecodeNextPacket / ResetDecoder      StreamDecoder.cs:357-369,418-498,640-762
+//   StreamDecoder.SeekTo / GetPacketGranuleCount                               StreamDecoder.cs:817-913
+//   StoreInterleaved / StoreContiguous / Utils.ClipValue                       StreamDecoder.cs:515-638, Utils.cs:44-58
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <memory>
+#include <new>
+#include <thread>
+
+#include "../../include/vpz.h"
+#include "bitreader.h"
+#include "engine.h"
+#include "ogg.h"
+
+using namespace vpz;
+
+namespace {
+
+enum {  // EndOfStreamFlags.cs
+  EOS_NONE = 0,
+  EOS_INVALID_PACKET = 1,
+  EOS_PACKET_FLAG = 2,
+  EOS_INVALID_PREROLL = 4
+};
+
+struct Entry {            // one packet handed out by the provider, already planned / decoded
+  bool ok = false;        // decoded (DecodeNextPacket returned a buffer)
+  bool is_resync = false;
+  int eos_flags = 0;
+  int err = 0;            // error the reference raises at this packet (or VPZ_E_REF_FAULT)
+  int count = 0;          // samples this packet makes available (RightStart - LeftStart, trimmed)
+  int tail = 0;           // RightEnd - RightStart (trimmed): overlap length for the next packet
+  int64_t granule = -1;
+  size_t pcm_off = 0;     // float offset of its samples in the PCM cache
+  size_t drain_off = 0;   // float offset of the raw right half (only for a failed end-of-stream packet)
+};
+
+// A planned window: entries in provider order plus the bytes of the packets the GPU has to decode.
+struct Window {
+  std::vector<Entry> entries;
+  std::vector<uint8_t> bytes;
+  std::vector<uint32_t> offs{0};
+  std::vector<int32_t> trims;
+  std::vector<int> entry_of;      // submitted packet -> entry index (-1: carried-over seed packet)
+  // drain of the last decoded packet's raw right half (see resolve_drain)
+  bool drain = false;
+  std::vector<uint8_t> drain_bytes;
+  int drain_tail = 0, drain_entry = -1;
+  void add_packet(const uint8_t* p, size_t n, int32_t trim, int entry) {
+    bytes.insert(bytes.end(), p, p + n);
+    offs.push_back((uint32_t)bytes.size());
+    trims.push_back(trim);
+    entry_of.push_back(entry);
+  }
+};
+
+}  // namespace
+
+// One logical Vorbis stream of the container = one IStreamDecoder.
+struct StreamDec {
+  vpz_ctx* ctx = nullptr;
+  LogicalStream* ls = nullptr;
+  vpz_setup* setup = nullptr;
+  std::vector<uint8_t> hdr[3];
+  std::string vendor;
+  std::vector<std::string> comments;
+  // ---- reference decoder state, consumption side (StreamDecoder.cs:40-49) ----
+  bool have_prev = false;        // _prevPacketBuf != null
+  int prev_avail = 0;            // _prevPacketEnd - _prevPacketStart
+  int prev_tail = 0;             // _prevPacketStop - _prevPacketEnd
+  int eos_found = EOS_NONE;
+  bool has_position = false;
+  int64_t current_position = 0;
+  bool has_clipped = false;
+  bool clip = true;
+  int fault = 0;
+  // ---- decode-ahead state ----
+  std::vector<Entry> q;
+  size_t qh = 0;
+  size_t pcm_cur = 0;            // float offset of the next unread sample of the current packet
+  HostBuf<float> pcm;            // pinned PCM cache of the current window
+  vpz_batch* batch = nullptr;
+  int lookahead = 256;
+  std::vector<uint8_t> carry;    // last decoded packet: re-submitted as the seed of the next window
+  int32_t carry_trim = 0;
+  // SeekTo reads its two packets (pre-roll, target) BEFORE it updates _currentPosition
+  // (StreamDecoder.cs:851-879): the planner must see the stale position for those two and the
+  // new one afterwards.
+  int seek_left = 0;             // packets SeekTo still has to consume
+  int64_t seek_pos = 0;          // position the provider reported for the target packet
+  // packet table for vpz_reader_audio_packet
+  std::vector<OggPacket> table;
+  bool table_built = false;
+
+  ~StreamDec() {
+    if (batch) vpz_batch_destroy(batch);
+    if (setup) setup_release(setup);
+  }
+
+  int channels() const { return setup->host.id.channels; }
+
+  // IPacketGranuleCountProvider.GetPacketGranuleCount (StreamDecoder.cs:882-913)
+  int granule_count(const OggPacket& pk) const {
+    if (pk.is_resync) return 0;
+    PacketGeom g = setup->host.packet_geometry(pk.data.data(), pk.data.size());
+    if (!g.valid) return 0;
+    return g.right_start - g.left_start;
+  }
+
+  void reset_decoder() {  // StreamDecoder.ResetDecoder (StreamDecoder.cs:357-369)
+    have_prev = false;
+    prev_avail = prev_tail = 0;
+    eos_found = EOS_NONE;
+    has_clipped = false;
+    has_position = false;
+    q.clear();
+    qh = 0;
+    carry.clear();
+    carry_trim = 0;
+  }
+};
+
+namespace {
+
+// StreamDecoder.LoadComments (StreamDecoder.cs:242-260)
+int parse_comments(StreamDec* d, const std::vector<uint8_t>& pk) {
+  static const uint8_t sig[7] = {0x03, 'v', 'o', 'r', 'b', 'i', 's'};
+  if (pk.size() < 7 || memcmp(pk.data(), sig, 7) != 0) return VPZ_E_INVALID_DATA;
+  BitReader br(pk.data(), pk.size());
+  br.skip(56);
+  auto read_string = [&](std::string* out) {
+    uint32_t n = br.read(32);
+    if ((int64_t)n * 8 > br.remaining()) return false;
+    out->resize(n);
+    for (uint32_t i = 0; i < n; i++) (*out)[i] = (char)br.read(8);
+    return true;
+  };
+  if (!read_string(&d->vendor)) return VPZ_E_INVALID_DATA;
+  uint32_t n = br.read(32);
+  if ((int64_t)n * 32 > br.remaining()) return VPZ_E_INVALID_DATA;
+  d->comments.resize(n);
+  for (uint32_t i = 0; i < n; i++)
+    if (!read_string(&d->comments[i])) return VPZ_E_INVALID_DATA;
+  return VPZ_OK;
+}
+
+// StreamDecoder.Initialize -> ProcessHeaderPackets (StreamDecoder.cs:71-165)
+int stream_init(StreamDec* d, vpz_ctx* ctx, LogicalStream* ls) {
+  d->ctx = ctx;
+  d->ls = ls;
+  for (int i = 0; i < 3; i++) {
+    OggPacket pk;
+    ls->next_packet(&pk);
+    if (!pk.valid) {
+      ctx->last_error = i == 0 ? "First packet is not valid." : "Could not find Vorbis data to decode.";
+      return VPZ_E_INVALID_DATA;
+    }
+    d->hdr[i] = std::move(pk.data);
+  }
+  IdHeader id;
+  int rc = parse_id_header(d->hdr[0].data(), d->hdr[0].size(), &id);
+  if (rc) {
+    ctx->last_error = "Could not find Vorbis data to decode.";
+    return rc;
+  }
+  if ((rc = parse_comments(d, d->hdr[1]))) {
+    ctx->last_error = "Could not find Vorbis data to decode.";
+    return rc;
+  }
+  rc = setup_create(ctx, d->hdr[0].data(), d->hdr[0].size(), d->hdr[2].data(), d->hdr[2].size(), &d->setup);
+  if (rc) return rc;
+  ls->granule_count = [d](const OggPacket& pk) { return d->granule_count(pk); };
+  d->current_position = 0;
+  d->reset_decoder();
+  d->has_position = true;
+  return VPZ_OK;
+}
+
+// Walks the provider for up to `max_packets` packets and replays ReadNextPacket's bookkeeping
+// (StreamDecoder.cs:640-694) on the packet headers: which packets decode, the end-of-stream trim of
+// RightStart, how many samples each makes available.  Nothing here depends on PCM values, which
+// is what lets the GPU decode the whole window in one pass afterwards.
+void plan_window(StreamDec* d, int max_packets, Window* w) {
+  const Setup& st = d->setup->host;
+  bool have_prev = d->have_prev;
+  int prev_tail = d->prev_tail;
+  int64_t pos = d->current_position;
+  bool has_pos = d->has_position;
+  int seek_left = d->seek_left;
+  if (have_prev && !d->carry.empty()) w->add_packet(d->carry.data(), d->carry.size(), d->carry_trim, -1);
+  for (int n = 0; max_packets <= 0 || n < max_packets; n++) {
+    OggPacket pk;
+    d->ls->next_packet(&pk);
+    Entry e;
+    if (!pk.valid) {  // StreamDecoder.cs:703-711
+      e.eos_flags = EOS_INVALID_PACKET;
+      w->entries.push_back(e);
+      break;
+    }
+    e.eos_flags = pk.is_eos ? EOS_PACKET_FLAG : EOS_NONE;
+    e.is_resync = pk.is_resync;
+    if (pk.is_resync) has_pos = false;
+    PacketGeom g = st.packet_geometry(pk.data.data(), pk.data.size());
+    if (g.bad_mode) {  // the exception leaves DecodeNextPacket before _eosFound is updated
+      e.eos_flags = EOS_NONE;
+      e.err = VPZ_E_INVALID_DATA;
+      w->entries.push_back(e);
+      continue;
+    }
+    if (!g.valid) {
+      w->entries.push_back(e);
+      if (e.eos_flags || seek_left > 0) break;  // a failed packet ends SeekTo early
+      continue;
+    }
+    const int L = prev_tail;
+    int rs = g.right_start;
+    int32_t trim = 0;
+    if (pk.granule != -1 && e.eos_flags != EOS_NONE) {  // StreamDecoder.cs:658-666
+      int diff = (int)(pos + L - pk.granule);
+      if (diff > 0) {
+        trim = diff;
+        rs = std::max(rs - diff, 0);
+      }
+    }
+    if (have_prev) {
+      const int slope_len = (g.left_use_size1 ? st.id.size1 : st.id.size0) / 2;
+      if (L > slope_len || L < 0 || g.left_start + L > st.id.size1 || rs < g.left_start) {
+        e.err = VPZ_E_REF_FAULT;  // OverlapBuffers would throw
+        w->entries.push_back(e);
+        break;
+      }
+    }
+    e.ok = true;
+    e.count = have_prev ? rs - g.left_start : 0;
+    e.tail = g.right_end - rs;
+    e.granule = pk.granule;
+    w->add_packet(pk.data.data(), pk.data.size(), trim, (int)w->entries.size());
+    w->entries.push_back(e);
+    have_prev = true;
+    prev_tail = e.tail;
+    if (seek_left > 0) {
+      // inside SeekTo: no position pick-up; after the target packet the position becomes
+      // samplePosition + (count - rollForward) = provider position + count
+      if (--seek_left == 0) pos = d->seek_pos + e.count;
+    } else {
+      if (pk.granule != -1 && !has_pos) {  // StreamDecoder.cs:459-463
+        has_pos = true;
+        pos = pk.granule - e.count;
+      }
+      pos += e.count;
+    }
+    if (e.eos_flags) break;
+  }
+}
+
+// StreamDecoder.cs:451-455: when the end-of-stream packet itself fails to decode, Read drains the
+// previous packet's raw (unwindowed) right half.  If that previous packet P belongs to this window
+// it simply gets a negative trim, so it emits [LeftStart, RightEnd) in place.  If P is the seed
+// carried over from the previous window (it emits nothing here), an extra run [P, P(trim = -tail)]
+// makes the second copy emit the same range and the last `tail` samples are taken from it.
+void resolve_drain(StreamDec* d, Window* w) {
+  if (w->entries.empty() || w->entry_of.empty()) return;
+  const Entry& last = w->entries.back();
+  if (last.ok || last.err || !(last.eos_flags & EOS_PACKET_FLAG)) return;
+  const size_t k = w->entry_of.size() - 1;
+  const int ei = w->entry_of[k];
+  const int tail = ei >= 0 ? w->entries[(size_t)ei].tail : d->prev_tail;
+  if (tail <= 0) return;
+  w->drain = true;
+  w->drain_tail = tail;
+  w->drain_entry = (int)w->entries.size() - 1;
+  if (ei >= 0) {
+    w->trims[k] = -tail;  // P is never an end-of-stream packet itself, so its trim was 0
+  } else {
+    w->drain_bytes.assign(w->bytes.begin() + w->offs[k], w->bytes.begin() + w->offs[k + 1]);
+  }
+}
+
+// Queues the window on batch `b`.  run_out/drain_run_out receive the run indices (-1: none).
+int submit_window(StreamDec* d, vpz_batch* b, Window* w, int* run_out, int* drain_run_out) {
+  *run_out = *drain_run_out = -1;
+  const uint32_t n = (uint32_t)w->trims.size();
+  bool emits = false;
+  for (int e : w->entry_of) emits |= e >= 0;
+  if (n && emits) {
+    int run = batch_add_run(b, d->setup, w->bytes.data(), w->offs.data(), n, w->trims.data());
+    if (run < 0) return run;
+    *run_out = run;
+  }
+  if (w->drain && !w->drain_bytes.empty()) {
+    std::vector<uint8_t> two(w->drain_bytes);
+    two.insert(two.end(), w->drain_bytes.begin(), w->drain_bytes.end());
+    uint32_t offs[3] = {0, (uint32_t)w->drain_bytes.size(), (uint32_t)two.size()};
+    int32_t trims[2] = {0, -w->drain_tail};
+    int run = batch_add_run(b, d->setup, two.data(), offs, 2, trims);
+    if (run < 0) return run;
+    *drain_run_out = run;
+  }
+  return VPZ_OK;
+}
+
+// After planning the batch: turns per-run sample counts into offsets inside the buffer the PCM of
+// the batch is (or will be) copied to.
+int place_window(StreamDec* d, vpz_batch* b, Window* w, int run, int drain_run) {
+  const int C = d->channels();
+  if (run >= 0) {
+    const Run& r = b->runs[(size_t)run];
+    size_t off = (size_t)r.out_base;
+    for (size_t k = 0; k < w->entry_of.size(); k++) {
+      const int ei = w->entry_of[k];
+      const int cnt = r.counts[k];
+      if (ei >= 0) {
+        Entry& e = w->entries[(size_t)ei];
+        if (r.status == VPZ_E_REF_FAULT && (int32_t)k >= r.stop_packet) {
+          e.ok = false;
+          e.err = VPZ_E_REF_FAULT;
+          continue;
+        }
+        const bool drained = w->drain && w->drain_bytes.empty() && k + 1 == w->entry_of.size();
+        if (cnt != e.count + (drained ? w->drain_tail : 0)) {
+          d->ctx->last_error = "internal: window plan and batch plan disagree";
+          return VPZ_E_INVALID_OP;
+        }
+        e.pcm_off = off;
+        if (drained) w->entries[(size_t)w->drain_entry].drain_off = off + (size_t)e.count * C;
+      }
+      off += (size_t)cnt * C;
+    }
+  }
+  if (drain_run >= 0) {
+    const Run& r = b->runs[(size_t)drain_run];
+    w->entries[(size_t)w->drain_entry].drain_off = (size_t)r.out_base + (size_t)(r.samples - w->drain_tail) * C;
+  }
+  return VPZ_OK;
+}
+
+// Plans, decodes and caches the next window of the stream (the reader path: one stream, own batch).
+int decode_ahead(StreamDec* d) {
+  vpz_ctx* ctx = d->ctx;
+  if (!d->batch) {
+    int rc = vpz_batch_create(ctx, &d->batch);
+    if (rc) return rc;
+  }
+  Window w;
+  plan_window(d, d->lookahead, &w);
+  resolve_drain(d, &w);
+  vpz_batch_reset(d->batch);
+  int run, drain_run;
+  int rc = submit_window(d, d->batch, &w, &run, &drain_run);
+  if (rc) return rc;
+  size_t total = (size_t)d->batch->total_floats;
+  if (total) {
+    if (!d->pcm.reserve(total)) return VPZ_E_NOMEM;
+    // the reader clips while copying into the caller's buffer (partial reads need per-sample HasClipped)
+    if ((rc = batch_decode(d->batch, 0))) return rc;
+    if ((rc = vpz_batch_read_all(d->batch, d->pcm.p))) return rc;
+  }
+  if ((rc = place_window(d, d->batch, &w, run, drain_run))) return rc;
+  // remember the last decoded packet as the seed of the next window
+  for (int k = (int)w.entry_of.size() - 1; k >= 0; k--) {
+    if (w.entry_of[(size_t)k] < 0) break;  // only the seed itself was submitted
+    if (w.entries[(size_t)w.entry_of[(size_t)k]].ok) {
+      d->carry.assign(w.bytes.begin() + w.offs[(size_t)k], w.bytes.begin() + w.offs[(size_t)k + 1]);
+      d->carry_trim = w.trims[(size_t)k];
+      break;
+    }
+  }
+  d->q = std::move(w.entries);
+  d->qh = 0;
+  return VPZ_OK;
+}
+
+// StreamDecoder.ReadNextPacket (StreamDecoder.cs:640-694), consumption side
+bool read_next_packet(StreamDec* d, int64_t* sample_position, int* err) {
+  *sample_position = -1;
+  if (d->qh == d->q.size()) {
+    int rc = decode_ahead(d);
+    if (rc) {
+      *err = rc;
+      return false;
+    }
+    if (d->q.empty()) {
+      d->eos_found |= EOS_INVALID_PACKET;
+      return false;
+    }
+  }
+  const Entry& e = d->q[d->qh++];
+  if (d->seek_left > 0) d->seek_left--;
+  if (e.err) {
+    if (e.is_resync) d->has_position = false;
+    *err = e.err;
+    return false;
+  }
+  d->eos_found |= e.eos_flags;
+  if (e.is_resync) d->has_position = false;
+  if (!e.ok) {
+    if ((e.eos_flags & EOS_PACKET_FLAG) && d->have_prev) {
+      // caller applies _prevPacketEnd = _prevPacketStop; point at the raw right half
+      d->pcm_cur = e.drain_off;
+    }
+    return false;
+  }
+  *sample_position = e.granule;
+  d->prev_avail = d->have_prev ? e.count : 0;
+  d->prev_tail = e.tail;
+  d->pcm_cur = e.pcm_off;
+  d->have_prev = true;
+  return true;
+}
+
+inline float clip_value(float v, bool* clipped) {  // Utils.ClipValue (Utils.cs:44-58)
+  if (v > 0.99999994f) {
+    *clipped = true;
+    return 0.99999994f;
+  }
+  if (v < -0.99999994f) {
+    *clipped = true;
+    return -0.99999994f;
+  }
+  return v;
+}
+
+// StreamDecoder.Read (StreamDecoder.cs:418-498)
+int stream_read(StreamDec* d, float* buffer, int nfloats, int samples_to_read, int channel_stride, bool interleave) {
+  const int C = d->channels();
+  if (d->fault) return d->fault;
+  if (nfloats < 0 || nfloats % C != 0) return VPZ_E_ARGUMENT;
+  if ((int64_t)nfloats < (int64_t)samples_to_read * C) return VPZ_E_ARGUMENT;
+  if (!buffer && nfloats) return VPZ_E_ARGUMENT;
+  int idx = 0;
+  while (idx == 0) {
+    if (d->prev_avail == 0) {
+      if (d->eos_found != EOS_NONE) {
+        d->have_prev = false;
+        break;
+      }
+      int64_t sp = -1;
+      int err = 0;
+      if (!read_next_packet(d, &sp, &err)) {
+        if (err) {
+          if (err == VPZ_E_REF_FAULT) {  // the reference throws here; this path ends the stream instead
+            d->fault = err;
+            d->eos_found |= EOS_INVALID_PACKET;
+            d->have_prev = false;
+            d->prev_avail = d->prev_tail = 0;
+          }
+          return err;
+        }
+        if (d->eos_found & EOS_PACKET_FLAG) {  // StreamDecoder.cs:451-455
+          d->prev_avail = d->prev_tail;
+          d->prev_tail = 0;
+        }
+      }
+      if (sp != -1 && !d->has_position) {
+        d->has_position = true;
+        d->current_position = sp - d->prev_avail - idx;
+      }
+    }
+    int copy_len = std::min(samples_to_read - idx, d->prev_avail);
+    if (copy_len <= 0) {
+      if (samples_to_read - idx <= 0) break;  // the reference spins forever on a zero-length request
+      if (d->prev_avail < 0) return VPZ_E_REF_FAULT;
+      continue;
+    }
+    const float* src = d->pcm.p + d->pcm_cur;
+    bool clipped = false;
+    if (interleave) {
+      float* dst = buffer + (size_t)idx * C;
+      const size_t n = (size_t)copy_len * C;
+      if (d->clip) {
+        for (size_t i = 0; i < n; i++) dst[i] = clip_value(src[i], &clipped);
+      } else {
+        memcpy(dst, src, n * sizeof(float));
+      }
+    } else {
+      for (int ch = 0; ch < C; ch++) {
+        float* dst = buffer + (size_t)ch * channel_stride + idx;
+        if (d->clip) {
+          for (int i = 0; i < copy_len; i++) dst[i] = clip_value(src[(size_t)i * C + ch], &clipped);
+        } else {
+          for (int i = 0; i < copy_len; i++) dst[i] = src[(size_t)i * C + ch];
+        }
+      }
+    }
+    d->has_clipped |= clipped;
+    idx += copy_len;
+    d->pcm_cur += (size_t)copy_len * C;
+    d->prev_avail -= copy_len;
+    d->current_position += copy_len;
+  }
+  return idx;
+}
+
+int64_t stream_total_samples(StreamDec* d, int* err) { return d->ls->total_granules(err); }
+
+// StreamDecoder.SeekTo (StreamDecoder.cs:817-880)
+int stream_seek(StreamDec* d, int64_t sample_position, int origin) {
+  if (!d->ls->can_seek()) return VPZ_E_INVALID_OP;
+  if (sample_position < 0) return VPZ_E_ARGUMENT;
+  int err = 0;
+  switch (origin) {
+    case 0: break;
+    case 1: sample_position = d->current_position - sample_position; break;
+    case 2: {
+      int64_t total = stream_total_samples(d, &err);
+      if (err) return err;
+      sample_position = total - sample_position;
+      break;
+    }
+    default: return VPZ_E_ARGUMENT;
+  }
+  // the provider cursor has run ahead of the consumer; SeekTo repositions it anyway
+  int64_t pos = d->ls->seek_to(sample_position, 1, &err);
+  if (err) return err;
+  int roll_forward = (int)(sample_position - pos);
+  d->reset_decoder();
+  d->fault = 0;
+  d->has_position = true;
+  d->seek_left = 2;
+  d->seek_pos = pos;
+  struct SeekDone {
+    StreamDec* d;
+    ~SeekDone() { d->seek_left = 0; }
+  } seek_done{d};
+  int64_t sp;
+  if (!read_next_packet(d, &sp, &err)) {
+    if (err) return err;
+    d->eos_found |= EOS_INVALID_PREROLL;
+    int64_t max_granule = stream_total_samples(d, &err);
+    if (err) return err;
+    if (sample_position > max_granule) return VPZ_E_SEEK_RANGE;
+    d->prev_avail = 0;
+    d->current_position = sample_position;
+    return VPZ_OK;
+  }
+  if (!read_next_packet(d, &sp, &err)) {
+    if (err == VPZ_E_REF_FAULT) d->fault = err;
+    if (err) return err;
+    d->reset_decoder();
+    d->eos_found |= EOS_INVALID_PACKET;
+    return VPZ_E_PREROLL;
+  }
+  d->prev_avail -= roll_forward;
+  d->pcm_cur += (size_t)roll_forward * d->channels();
+  d->current_position = sample_position;
+  return VPZ_OK;
+}
+
+void build_table(StreamDec* d) {
+  if (d->table_built) return;
+  LogicalStream walker;  // a second cursor over the same pages; the decode cursor is left alone
+  walker.serial = d->ls->serial;
+  walker.pages = d->ls->pages;
+  OggPacket pk;
+  for (int i = 0; i < 3; i++) walker.next_packet(&pk);
+  for (;;) {
+    walker.next_packet(&pk);
+    if (!pk.valid) break;
+    d->table.push_back(std::move(pk));
+  }
+  d->table_built = true;
+}
+
+}  // namespace
+
+struct vpz_reader {
+  vpz_ctx* ctx = nullptr;
+  std::vector<uint8_t> own;
+  OggContainer cont;
+  std::vector<StreamDec*> decs;   // Streams
+  size_t next_logical = 0;        // next logical stream FindNextStream will look at
+  int cur = 0;                    // StreamIndex
+  ~vpz_reader() {
+    for (StreamDec* d : decs) delete d;
+  }
+  StreamDec* dec() const { return decs[(size_t)cur]; }
+};
+
+namespace {
+// ContainerReader.FindNextStream + VorbisReader.ProcessNewStream: 1 found, 0 none, <0 error
+int find_next(vpz_reader* r) {
+  if (r->next_logical >= r->cont.streams.size()) return 0;
+  LogicalStream* ls = r->cont.streams[r->next_logical++];
+  std::unique_ptr<StreamDec> d(new (std::nothrow) StreamDec);
+  if (!d) return VPZ_E_NOMEM;
+  int rc = stream_init(d.get(), r->ctx, ls);
+  if (rc) return rc;
+  r->decs.push_back(d.release());
+  return 1;
+}
+}  // namespace
+
+extern "C" {
+
+int vpz_reader_open_memory(vpz_ctx* ctx, const uint8_t* data, size_t len, int copy, vpz_reader** out) {
+  if (!ctx || !out || (!data && len)) return VPZ_E_ARGUMENT;
+  *out = nullptr;
+  vpz_reader* r = new (std::nothrow) vpz_reader;
+  if (!r) return VPZ_E_NOMEM;
+  r->ctx = ctx;
+  if (copy) {
+    r->own.assign(data, data + len);
+    data = r->own.data();
+  }
+  int rc = r->cont.scan(data, len);
+  if (rc == VPZ_OK) {
+    rc = find_next(r);
+    if (rc == 0) rc = VPZ_E_INVALID_DATA;
+    if (rc == 1) rc = VPZ_OK;
+  }
+  if (rc) {
+    if (rc == VPZ_E_INVALID_DATA && ctx->last_error.empty())
+      ctx->last_error = "Could not load the specified container.";  // VorbisReader.cs:63
+    delete r;
+    return rc;
+  }
+  *out = r;
+  return VPZ_OK;
+}
+
+void vpz_reader_close(vpz_reader* r) { delete r; }
+
+int vpz_reader_stream_count(const vpz_reader* r) { return r ? (int)r->decs.size() : VPZ_E_ARGUMENT; }
+int vpz_reader_stream_index(const vpz_reader* r) { return r ? r->cur : VPZ_E_ARGUMENT; }
+
+int vpz_reader_switch_stream(vpz_reader* r, int index) {  // VorbisReader.SwitchStreams
+  if (!r) return VPZ_E_ARGUMENT;
+  if (index < 0 || (size_t)index >= r->decs.size()) return VPZ_E_ARGUMENT;
+  if (index == r->cur) return 0;
+  StreamDec* nd = r->decs[(size_t)index];
+  StreamDec* od = r->dec();
+  nd->clip = od->clip;
+  r->cur = index;
+  return (nd->channels() != od->channels() || nd->setup->host.id.sample_rate != od->setup->host.id.sample_rate) ? 1 : 0;
+}
+
+int vpz_reader_find_next_stream(vpz_reader* r) { return r ? find_next(r) : VPZ_E_ARGUMENT; }
+int vpz_reader_can_seek(const vpz_reader* r) { return r ? (r->dec()->ls->can_seek() ? 1 : 0) : VPZ_E_ARGUMENT; }
+
+int vpz_reader_channels(const vpz_reader* r) { return r ? r->dec()->channels() : VPZ_E_ARGUMENT; }
+int vpz_reader_sample_rate(const vpz_reader* r) { return r ? r->dec()->setup->host.id.sample_rate : VPZ_E_ARGUMENT; }
+int vpz_reader_bitrate(const vpz_reader* r, int which) {
+  if (!r) return VPZ_E_ARGUMENT;
+  const IdHeader& id = r->dec()->setup->host.id;
+  return which == 0 ? id.br_upper : which == 1 ? id.br_nominal : id.br_lower;
+}
+int vpz_reader_stream_serial(const vpz_reader* r) { return r ? (int)r->dec()->ls->serial : VPZ_E_ARGUMENT; }
+
+int64_t vpz_reader_total_samples(vpz_reader* r) {
+  if (!r) return VPZ_E_ARGUMENT;
+  int err = 0;
+  int64_t n = stream_total_samples(r->dec(), &err);
+  return err ? err : n;
+}
+int64_t vpz_reader_sample_position(const vpz_reader* r) { return r ? r->dec()->current_position : VPZ_E_ARGUMENT; }
+int vpz_reader_is_end_of_stream(const vpz_reader* r) {  // StreamDecoder.cs:1001
+  if (!r) return VPZ_E_ARGUMENT;
+  const StreamDec* d = r->dec();
+  return (d->eos_found != EOS_NONE && !d->have_prev) ? 1 : 0;
+}
+int vpz_reader_has_clipped(const vpz_reader* r) { return r ? (r->dec()->has_clipped ? 1 : 0) : VPZ_E_ARGUMENT; }
+int vpz_reader_get_clip(const vpz_reader* r) { return r ? (r->dec()->clip ? 1 : 0) : VPZ_E_ARGUMENT; }
+void vpz_reader_set_clip(vpz_reader* r, int clip) {
+  if (r) r->dec()->clip = clip != 0;
+}
+int64_t vpz_reader_container_overhead_bits(const vpz_reader* r) {
+  if (!r) return VPZ_E_ARGUMENT;
+  int64_t n = 0;
+  for (const LogicalStream* ls : r->cont.streams) n += ls->container_bits;
+  return n;
+}
+int64_t vpz_reader_container_waste_bits(const vpz_reader* r) { return r ? r->cont.waste_bits : VPZ_E_ARGUMENT; }
+
+const char* vpz_reader_vendor(const vpz_reader* r, int* len) {
+  if (!r) return nullptr;
+  if (len) *len = (int)r->dec()->vendor.size();
+  return r->dec()->vendor.data();
+}
+int vpz_reader_comment_count(const vpz_reader* r) { return r ? (int)r->dec()->comments.size() : VPZ_E_ARGUMENT; }
+const char* vpz_reader_comment(const vpz_reader* r, int i, int* len) {
+  if (!r || i < 0 || (size_t)i >= r->dec()->comments.size()) return nullptr;
+  if (len) *len = (int)r->dec()->comments[(size_t)i].size();
+  return r->dec()->comments[(size_t)i].data();
+}
+
+int vpz_reader_read(vpz_reader* r, float* buf, int nfloats) {
+  if (!r) return VPZ_E_ARGUMENT;
+  StreamDec* d = r->dec();
+  return stream_read(d, buf, nfloats, nfloats / d->channels(), 0, true);
+}
+int vpz_reader_read_planar(vpz_reader* r, float* buf, int nfloats, int samples_to_read, int channel_stride) {
+  if (!r || samples_to_read < 0) return VPZ_E_ARGUMENT;
+  return stream_read(r->dec(), buf, nfloats, samples_to_read, channel_stride, false);
+}
+int vpz_reader_seek(vpz_reader* r, int64_t sample_position, int origin) {
+  return r ? stream_seek(r->dec(), sample_position, origin) : VPZ_E_ARGUMENT;
+}
+int vpz_reader_set_lookahead(vpz_reader* r, int packets) {
+  if (!r || packets < 0) return VPZ_E_ARGUMENT;
+  r->dec()->lookahead = packets;
+  return VPZ_OK;
+}
+
+int vpz_reader_audio_packet_count(vpz_reader* r) {
+  if (!r) return VPZ_E_ARGUMENT;
+  build_table(r->dec());
+  return (int)r->dec()->table.size();
+}
+int vpz_reader_audio_packet(vpz_reader* r, int i, const uint8_t** data, uint32_t* len, int64_t* granule,
+                            int32_t* flags) {
+  if (!r) return VPZ_E_ARGUMENT;
+  StreamDec* d = r->dec();
+  build_table(d);
+  if (i < 0 || (size_t)i >= d->table.size()) return VPZ_E_ARGUMENT;
+  const OggPacket& pk = d->table[(size_t)i];
+  if (data) *data = pk.data.data();
+  if (len) *len = (uint32_t)pk.data.size();
+  if (granule) *granule = pk.granule;
+  if (flags) *flags = (pk.is_resync ? 1 : 0) | (pk.is_eos ? 2 : 0);
+  return VPZ_OK;
+}
+const uint8_t* vpz_reader_header_packet(vpz_reader* r, int which, uint32_t* len) {
+  if (!r || which < 0 || which > 2) return nullptr;
+  if (len) *len = (uint32_t)r->dec()->hdr[which].size();
+  return r->dec()->hdr[which].data();
+}
+vpz_setup* vpz_reader_setup(vpz_reader* r) { return r ? r->dec()->setup : nullptr; }
+
+// ---- bulk: many whole files in one batch ---------------------------------------------------------
+int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, int clip,
+                         float* dst, size_t dst_floats, int64_t* sample_counts) {
+  if (!ctx || (n && (!datas || !lens))) return VPZ_E_ARGUMENT;
+  struct Job {
+    OggContainer cont;
+    StreamDec dec;
+    Window win;
+    int rc = 0;
+    int run = -1, drain_run = -1;
+  };
+  std::vector<std::unique_ptr<Job>> jobs(n);
+  // 1. page scan (CRC) in parallel: pure host work, no shared state
+  unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  nthreads = std::min<unsigned>(nthreads, std::max<uint32_t>(1, n));
+  {
+    std::atomic<uint32_t> next{0};
+    auto work = [&]() {
+      for (;;) {
+        uint32_t i = next.fetch_add(1);
+        if (i >= n) break;
+        jobs[i].reset(new Job);
+        jobs[i]->rc = jobs[i]->cont.scan(datas[i], lens[i]);
+      }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
+  // 2. headers + setup cache (shared, serial: identical header pairs collapse onto one device image)
+  for (uint32_t i = 0; i < n; i++) {
+    Job& j = *jobs[i];
+    if (j.rc) return j.rc;
+    j.rc = stream_init(&j.dec, ctx, j.cont.streams[0]);
+    if (j.rc) return j.rc;
+  }
+  // 3. packet walk + window plan in parallel (per-stream state only)
+  {
+    std::atomic<uint32_t> next{0};
+    auto work = [&]() {
+      for (;;) {
+        uint32_t i = next.fetch_add(1);
+        if (i >= n) break;
+        plan_window(&jobs[i]->dec, 0, &jobs[i]->win);
+        resolve_drain(&jobs[i]->dec, &jobs[i]->win);
+      }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
+    work();
+    for (auto& t : th) t.join();
+  }
+  // 4. one batch for everything
+  int rc = VPZ_OK;
+  if (!ctx->bulk) rc = vpz_batch_create(ctx, &ctx->bulk);
+  if (rc) return rc;
+  vpz_batch* b = ctx->bulk;
+  vpz_batch_reset(b);
+  int64_t total = 0;
+  for (uint32_t i = 0; i < n && !rc; i++) {
+    Job& j = *jobs[i];
+    rc = submit_window(&j.dec, b, &j.win, &j.run, &j.drain_run);
+    if (!rc && sample_counts) sample_counts[i] = j.run >= 0 ? b->runs[(size_t)j.run].samples : 0;
+  }
+  if (!rc) {
+    total = (int64_t)b->total_floats;
+    if (dst && (size_t)total > dst_floats) rc = VPZ_E_ARGUMENT;
+  }
+  if (!rc && total) rc = batch_decode(b, clip);
+  if (!rc && total && dst) rc = vpz_batch_read_all(b, dst);
+  if (!rc && total && !dst) rc = vpz_batch_sync(b);
+  vpz_batch_reset(b);  // drops the setup references of this call; device buffers stay allocated
+  return rc ? rc : total;
+}
+
+}  // extern "C"

@@ -64,6 +64,9 @@ int vpz_ctx_create(int device, vpz_ctx** out) {
 
 void vpz_ctx_destroy(vpz_ctx* c) {
   if (!c) return;
+  if (c->bulk) vpz_batch_destroy(c->bulk);
+  c->bulk = nullptr;
+  for (int i = 0; i < 8; i++) dev::event_destroy(c->marks[i]);
   while (!c->setups.empty()) {
     vpz_setup* s = c->setups.begin()->second;
     s->refs = 1;
@@ -74,6 +77,22 @@ void vpz_ctx_destroy(vpz_ctx* c) {
   dev::stream_destroy(c->stream);
   delete c;
 }
+
+int vpz_ctx_mark(vpz_ctx* c, int slot) {
+  if (!c || slot < 0 || slot >= 8) return VPZ_E_ARGUMENT;
+  if (!c->marks[slot]) c->marks[slot] = dev::event_create();
+  if (!c->marks[slot]) return VPZ_E_CUDA;
+  dev::event_record(c->marks[slot], c->stream);
+  return VPZ_OK;
+}
+
+float vpz_ctx_elapsed_ms(vpz_ctx* c, int a, int b) {
+  if (!c || a < 0 || a >= 8 || b < 0 || b >= 8 || !c->marks[a] || !c->marks[b]) return -1.f;
+  if (dev::event_sync(c->marks[b], c->last_error)) return -1.f;
+  return dev::event_elapsed_ms(c->marks[a], c->marks[b]);
+}
+
+int64_t vpz_ctx_kernel_launches(const vpz_ctx* c) { return c ? c->kernel_launches : VPZ_E_ARGUMENT; }
 
 int vpz_ctx_set(vpz_ctx* c, const char* key, int value) {
   if (!c || !key) return VPZ_E_ARGUMENT;
@@ -248,6 +267,8 @@ float vpz_batch_last_ms(vpz_batch* b, int which, int* launches) {
   if (launches) *launches = b->launches;
   return which == 1 ? b->ms_k1 : which == 3 ? b->ms_k3 : b->ms_total;
 }
+
+uint64_t vpz_transfer_bytes(int which) { return dev::transfer_bytes(which); }
 
 void* vpz_host_alloc(size_t bytes) { return dev::host_alloc(bytes); }
 void vpz_host_free(void* p) { dev::host_free(p); }
