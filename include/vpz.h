@@ -66,7 +66,8 @@ void vpz_ctx_destroy(vpz_ctx* ctx);
 int vpz_device_count(void);
 /* Tunables (call before the first batch): key one of "l1_bits" (Huffman first-level table width,
  * default 9), "ola_chunk" (packets per IMDCT work item, default 32), "k1_warps" (warps per entropy
- * CTA, default 4). */
+ * CTA, default 4), "bulk_group" (streams per pipeline group of vpz_decode_files, default 256),
+ * "host_threads" (host worker threads of the bulk path, default 0 = all cores up to 32). */
 int vpz_ctx_set(vpz_ctx* ctx, const char* key, int value);
 
 /* Device-side stopwatch on the context's stream: vpz_ctx_mark records CUDA event `slot` (0..7) on

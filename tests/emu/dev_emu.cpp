@@ -70,6 +70,7 @@ void event_record(Event* e, Stream*) {
   e->t = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 int event_sync(Event*, std::string&) { return VPZ_OK; }
+void stream_wait_event(Stream*, Event*) {}
 float event_elapsed_ms(Event* a, Event* b) { return (float)(b->t - a->t); }
 unsigned long long transfer_bytes(int) { return 0; }
 int h2d(void* d, const void* s, size_t n, Stream*, std::string&) {

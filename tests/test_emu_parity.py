@@ -48,8 +48,8 @@ def test_synth_imdct_ola(emu_ctx):
 
 
 def test_synth_generic_block_sizes(emu_ctx):
-    cases.synth_parity(emu_ctx, channels=1, n_streams=1, n_blocks=8, lg0=6, lg1=9)
-    cases.synth_parity(emu_ctx, channels=3, n_streams=1, n_blocks=6, lg0=7, lg1=10, clip=True)
+    cases.synth_parity(emu_ctx, channels=1, n_streams=1, n_blocks=8, lg0=8, lg1=9)
+    cases.synth_parity(emu_ctx, channels=3, n_streams=1, n_blocks=6, lg0=9, lg1=10, clip=True)
 
 
 def test_decode_files(emu_ctx):

@@ -65,7 +65,7 @@ def test_synth_vs_oracle(gpu_ctx):
     cases.synth_parity(gpu_ctx, channels=1, n_streams=2, n_blocks=32)
 
 
-@pytest.mark.parametrize("lg0,lg1,ch", [(6, 6, 1), (6, 13, 1), (7, 10, 3), (9, 12, 2), (8, 11, 6), (11, 11, 2)])
+@pytest.mark.parametrize("lg0,lg1,ch", [(8, 8, 1), (8, 13, 1), (8, 10, 3), (9, 12, 2), (8, 11, 6), (11, 11, 2), (10, 12, 8)])
 def test_synth_generic_block_sizes(gpu_ctx, lg0, lg1, ch):
     cases.synth_parity(gpu_ctx, channels=ch, n_streams=2, n_blocks=12, lg0=lg0, lg1=lg1)
 

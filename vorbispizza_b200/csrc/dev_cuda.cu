@@ -152,6 +152,7 @@ void event_destroy(Event* e) {
   delete e;
 }
 void event_record(Event* e, Stream* s) { cudaEventRecord(e->e, s->s); }
+void stream_wait_event(Stream* s, Event* e) { cudaStreamWaitEvent(s->s, e->e, 0); }
 int event_sync(Event* e, std::string& err) {
   cudaError_t r = cudaEventSynchronize(e->e);
   return r == cudaSuccess ? VPZ_OK : fail(r, "cudaEventSynchronize", err);

@@ -34,6 +34,7 @@ Event* event_create();
 void event_destroy(Event* e);
 void event_record(Event* e, Stream* s);
 int event_sync(Event* e, std::string& err);
+void stream_wait_event(Stream* s, Event* e);   // later work on s waits for e
 float event_elapsed_ms(Event* a, Event* b);
 
 int h2d(void* dst, const void* src, size_t bytes, Stream* s, std::string& err);

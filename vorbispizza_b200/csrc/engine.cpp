@@ -43,7 +43,12 @@ static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
 
 int setup_create(vpz_ctx* ctx, const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt, size_t setup_len,
                  vpz_setup** out) {
-  uint64_t h = fnv1a64(setup_pkt, setup_len, fnv1a64(id_pkt, id_len));
+  return setup_create_hashed(ctx, fnv1a64(setup_pkt, setup_len, fnv1a64(id_pkt, id_len)), id_pkt, id_len, setup_pkt,
+                             setup_len, out);
+}
+
+int setup_create_hashed(vpz_ctx* ctx, uint64_t h, const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
+                        size_t setup_len, vpz_setup** out) {
   auto range = ctx->setups.equal_range(h);
   for (auto it = range.first; it != range.second; ++it) {
     vpz_setup* s = it->second;
@@ -162,36 +167,82 @@ static int slot_of(vpz_batch* b, vpz_setup* s) {
   return (int)b->slots.size() - 1;
 }
 
-// Plans one run: which packets decode, where their spectra and samples go, and the K3 work items.
-// Mirrors the bookkeeping of StreamDecoder.ReadNextPacket (StreamDecoder.cs:640-694) for a decoder
-// that starts from ResetDecoder state.
-int batch_add_run(vpz_batch* b, vpz_setup* s, const uint8_t* bytes, const uint32_t* offsets, uint32_t n_pkts,
-                  const int32_t* trim) {
-  vpz_ctx* ctx = b->ctx;
-  if (b->synthetic || s->synthetic) {
-    ctx->last_error = "packet runs cannot be added to a synthetic batch";
-    return VPZ_E_INVALID_OP;
+// ---- host worker pool -----------------------------------------------------------------------
+ThreadPool::ThreadPool(unsigned n) {
+  for (unsigned i = 1; i < n; i++) workers_.emplace_back([this] { worker(); });
+}
+ThreadPool::~ThreadPool() {
+  {
+    std::lock_guard<std::mutex> lk(m_);
+    stop_ = true;
   }
+  cv_.notify_all();
+  for (auto& t : workers_) t.join();
+}
+void ThreadPool::drain() {
+  for (;;) {
+    size_t i = next_.fetch_add(1);
+    if (i >= n_) break;
+    (*fn_)(i);
+  }
+}
+void ThreadPool::worker() {
+  unsigned seen = 0;
+  for (;;) {
+    {
+      std::unique_lock<std::mutex> lk(m_);
+      cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+      if (stop_) return;
+      seen = generation_;
+    }
+    drain();
+    {
+      std::lock_guard<std::mutex> lk(m_);
+      if (--active_ == 0) done_cv_.notify_all();
+    }
+  }
+}
+void ThreadPool::parallel_for(size_t n, const std::function<void(size_t)>& fn) {
+  if (n == 0) return;
+  if (workers_.empty() || n == 1) {
+    for (size_t i = 0; i < n; i++) fn(i);
+    return;
+  }
+  {
+    std::lock_guard<std::mutex> lk(m_);
+    fn_ = &fn;
+    n_ = n;
+    next_.store(0);
+    active_ = (unsigned)workers_.size();
+    generation_++;
+  }
+  cv_.notify_all();
+  drain();
+  std::unique_lock<std::mutex> lk(m_);
+  done_cv_.wait(lk, [&] { return active_ == 0; });
+}
+
+// Plans one run: which packets decode, where their spectra and samples go.  Mirrors the
+// bookkeeping of StreamDecoder.ReadNextPacket (StreamDecoder.cs:640-694) for a decoder that starts
+// from ResetDecoder state.  Pure: touches neither the batch nor the context.
+int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* trim, RunPlan* out, std::string* err) {
   const Setup& st = s->host;
   const int C = st.id.channels;
-  Run run;
-  run.setup = s;
-  run.slot = slot_of(b, s);
-  run.first_valid = (uint32_t)b->pkts_in.n;
-  run.counts.assign(n_pkts, 0);
-  run.out_base = b->total_floats;
-  b->max_channels = std::max(b->max_channels, C);
-  b->uploaded = false;
-
+  out->setup = s;
+  out->counts.assign(n_pkts, 0);
+  out->src.reserve(n_pkts);
+  out->byte_off.reserve(n_pkts);
+  out->ola.reserve(n_pkts);
   bool have_prev = false;
   int prev_rs = 0, prev_re = 0;
   int64_t pos = 0;  // samples emitted so far by this run
+  uint64_t staged = 0;
   for (uint32_t i = 0; i < n_pkts; i++) {
-    const uint8_t* p = bytes + offsets[i];
-    const uint32_t len = offsets[i + 1] - offsets[i];
+    const uint8_t* p = pk[i].p;
+    const uint32_t len = pk[i].len;
     PacketGeom g = st.packet_geometry(p, len);
     if (g.bad_mode) {
-      ctx->last_error = "Unused mode index.";  // StreamDecoder.cs:734
+      if (err) *err = "Unused mode index.";  // StreamDecoder.cs:734
       return VPZ_E_INVALID_DATA;
     }
     if (!g.valid) continue;
@@ -206,70 +257,161 @@ int batch_add_run(vpz_batch* b, vpz_setup* s, const uint8_t* bytes, const uint32
       int slope_len = (g.left_use_size1 ? st.id.size1 : st.id.size0) / 2;
       if (L > slope_len || L < 0 || g.left_start + L > st.id.size1 || rs < g.left_start) {
         // the reference slices windowSlope.AsSpan(0, L) and throws; the run ends here
-        run.status = VPZ_E_REF_FAULT;
-        run.stop_packet = (int32_t)i;
+        out->status = VPZ_E_REF_FAULT;
+        out->stop_packet = (int32_t)i;
         break;
       }
       count = rs - g.left_start;
     }
-    // stage the bytes: 4-byte aligned start, at least 8 zero bytes after the end
-    size_t off = (b->bytes.n + 3) & ~(size_t)3;
-    size_t end = off + len + 8;
-    end = (end + 3) & ~(size_t)3;
-    if (end > 0xfffffff0ull) {
-      ctx->last_error = "batch exceeds 4 GiB of packet bytes";
-      return VPZ_E_ARGUMENT;
-    }
-    if (!b->bytes.reserve(end)) return VPZ_E_NOMEM;
-    memset(b->bytes.p + b->bytes.n, 0, off - b->bytes.n);
-    if (len) memcpy(b->bytes.p + off, p, len);
-    memset(b->bytes.p + off + len, 0, end - off - len);
-    b->bytes.n = end;
-    b->payload_bytes += len;
-
+    // staged layout: 4-byte aligned start, at least 8 zero bytes after the end
+    const uint64_t end = (staged + len + 8 + 3) & ~(uint64_t)3;
     const int M = g.block_size / 2;
-    if (b->spec_floats + (uint64_t)C * M > 0xffffff00ull) {
-      ctx->last_error = "batch exceeds 2^32 spectrum floats; split it";
-      return VPZ_E_ARGUMENT;
-    }
-    VpzPktIn in;
-    in.byte_off = (uint32_t)off;
-    in.byte_len = len;
-    in.spec_off = (uint32_t)b->spec_floats;
-    in.setup_slot = (uint32_t)run.slot;
     VpzPktOla ola;
     memset(&ola, 0, sizeof(ola));
-    ola.spec_off = in.spec_off;
+    if (out->spec_floats + (uint64_t)C * M > 0xffffff00ull || end > 0xfffffff0ull || pos > 0x7fffffff) {
+      if (err) *err = "run exceeds 2^32 spectrum floats / 4 GiB of packet bytes; split it";
+      return VPZ_E_ARGUMENT;
+    }
+    ola.spec_off = (uint32_t)out->spec_floats;
     ola.out_off = (uint32_t)pos;
     ola.left_start = (uint16_t)g.left_start;
     ola.right_start = (uint16_t)rs;
     ola.right_end = (uint16_t)g.right_end;
     ola.flags = (uint8_t)((g.long_block ? VPZ_OLA_LONG : 0) | (g.left_use_size1 ? VPZ_OLA_LEFT1 : 0) |
                           (have_prev ? 0 : VPZ_OLA_NOOUT));
-    if (!b->pkts_in.push(in) || !b->pkts_ola.push(ola)) return VPZ_E_NOMEM;
-    b->spec_floats += (uint64_t)C * M;
-    run.counts[i] = count;
+    out->src.push_back(PktSrc{p, len});
+    out->byte_off.push_back((uint32_t)staged);
+    out->ola.push_back(ola);
+    staged = end;
+    out->payload_bytes += len;
+    out->spec_floats += (uint64_t)C * M;
+    out->counts[i] = count;
     pos += count;
     have_prev = true;
     prev_rs = rs;
     prev_re = g.right_end;
   }
-  run.n_valid = (uint32_t)b->pkts_in.n - run.first_valid;
-  run.samples = pos;
-  b->total_floats += (uint64_t)pos * C;
-  // K3 work items: packets 1..n_valid-1 emit; each item re-runs its predecessor as carry seed
-  const uint32_t chunk = (uint32_t)std::max(1, ctx->ola_chunk);
-  for (uint32_t k = 1; k < run.n_valid; k += chunk) {
-    VpzOlaItem it;
-    it.first_pkt = run.first_valid + k;
-    it.n_pkts = std::min(chunk, run.n_valid - k);
-    it.has_pre = 1;
-    it.setup_slot = (uint32_t)run.slot;
-    it.out_base = run.out_base;
-    if (!b->items.push(it)) return VPZ_E_NOMEM;
+  out->staged_bytes = staged;
+  out->samples = pos;
+  return VPZ_OK;
+}
+
+int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool, int* first_run) {
+  vpz_ctx* ctx = b->ctx;
+  if (b->synthetic) {
+    ctx->last_error = "packet runs cannot be added to a synthetic batch";
+    return VPZ_E_INVALID_OP;
   }
-  b->runs.push_back(std::move(run));
-  return (int)b->runs.size() - 1;
+  if (first_run) *first_run = (int)b->runs.size();
+  if (n == 0) return VPZ_OK;
+  const uint32_t chunk = (uint32_t)std::max(1, ctx->ola_chunk);
+  struct Base {
+    uint64_t bytes, spec, out;
+    size_t pkt, item;
+    int slot;
+  };
+  std::vector<Base> base(n);
+  uint64_t bytes = (b->bytes.n + 3) & ~(size_t)3, spec = b->spec_floats, out = b->total_floats;
+  size_t pkt = b->pkts_in.n, item = b->items.n;
+  for (size_t i = 0; i < n; i++) {
+    const RunPlan& p = *plans[i];
+    if (p.setup->synthetic) {
+      ctx->last_error = "packet runs cannot use a synthetic setup";
+      return VPZ_E_INVALID_OP;
+    }
+    base[i] = Base{bytes, spec, out, pkt, item, slot_of(b, p.setup)};
+    const size_t nv = p.src.size();
+    bytes += p.staged_bytes;
+    spec += p.spec_floats;
+    out += (uint64_t)p.samples * p.setup->host.id.channels;
+    pkt += nv;
+    item += nv > 1 ? (nv - 1 + chunk - 1) / chunk : 0;
+    b->max_channels = std::max(b->max_channels, p.setup->host.id.channels);
+  }
+  if (spec > 0xffffff00ull || bytes > 0xfffffff0ull) {
+    ctx->last_error = "batch exceeds 2^32 spectrum floats / 4 GiB of packet bytes; split it";
+    return VPZ_E_ARGUMENT;
+  }
+  const size_t old_bytes = b->bytes.n;
+  if (!b->bytes.reserve(bytes) || !b->pkts_in.reserve(pkt) || !b->pkts_ola.reserve(pkt) || !b->items.reserve(item))
+    return VPZ_E_NOMEM;
+  memset(b->bytes.p + old_bytes, 0, (size_t)base[0].bytes - old_bytes);
+  auto fill = [&](size_t i) {
+    const RunPlan& p = *plans[i];
+    const Base& bs = base[i];
+    const size_t nv = p.src.size();
+    uint8_t* dst = b->bytes.p + bs.bytes;
+    for (size_t k = 0; k < nv; k++) {
+      const uint32_t off = p.byte_off[k], len = p.src[k].len;
+      const uint32_t next = k + 1 < nv ? p.byte_off[k + 1] : (uint32_t)p.staged_bytes;
+      if (len) memcpy(dst + off, p.src[k].p, len);
+      memset(dst + off + len, 0, next - off - len);
+      VpzPktIn in;
+      in.byte_off = (uint32_t)(bs.bytes + off);
+      in.byte_len = len;
+      in.spec_off = (uint32_t)(bs.spec + p.ola[k].spec_off);
+      in.setup_slot = (uint32_t)bs.slot;
+      b->pkts_in.p[bs.pkt + k] = in;
+      VpzPktOla ola = p.ola[k];
+      ola.spec_off = in.spec_off;
+      b->pkts_ola.p[bs.pkt + k] = ola;
+    }
+    // K3 work items: packets 1..nv-1 emit; each item re-runs its predecessor as carry seed
+    size_t it_idx = bs.item;
+    for (size_t k = 1; k < nv; k += chunk) {
+      VpzOlaItem it;
+      it.first_pkt = (uint32_t)(bs.pkt + k);
+      it.n_pkts = (uint32_t)std::min<size_t>(chunk, nv - k);
+      it.has_pre = 1;
+      it.setup_slot = (uint32_t)bs.slot;
+      it.out_base = bs.out;
+      b->items.p[it_idx++] = it;
+    }
+  };
+  if (pool && n > 1)
+    pool->parallel_for(n, fill);
+  else
+    for (size_t i = 0; i < n; i++) fill(i);
+  b->bytes.n = bytes;
+  b->pkts_in.n = b->pkts_ola.n = pkt;
+  b->items.n = item;
+  b->spec_floats = spec;
+  b->total_floats = out;
+  for (size_t i = 0; i < n; i++) {
+    RunPlan& p = *plans[i];
+    Run run;
+    run.setup = p.setup;
+    run.slot = base[i].slot;
+    run.first_valid = (uint32_t)base[i].pkt;
+    run.n_valid = (uint32_t)p.src.size();
+    run.counts = std::move(p.counts);
+    run.samples = p.samples;
+    run.out_base = base[i].out;
+    run.status = p.status;
+    run.stop_packet = p.stop_packet;
+    b->payload_bytes += p.payload_bytes;
+    b->runs.push_back(std::move(run));
+  }
+  b->uploaded = false;
+  return VPZ_OK;
+}
+
+int batch_add_run(vpz_batch* b, vpz_setup* s, const uint8_t* bytes, const uint32_t* offsets, uint32_t n_pkts,
+                  const int32_t* trim) {
+  vpz_ctx* ctx = b->ctx;
+  if (b->synthetic || s->synthetic) {
+    ctx->last_error = "packet runs cannot be added to a synthetic batch";
+    return VPZ_E_INVALID_OP;
+  }
+  std::vector<PktSrc> src(n_pkts);
+  for (uint32_t i = 0; i < n_pkts; i++) src[i] = PktSrc{bytes + offsets[i], offsets[i + 1] - offsets[i]};
+  RunPlan plan;
+  int rc = plan_run(s, src.data(), n_pkts, trim, &plan, &ctx->last_error);
+  if (rc) return rc;
+  RunPlan* pp = &plan;
+  int first = 0;
+  rc = batch_commit(b, &pp, 1, nullptr, &first);
+  return rc ? rc : first;
 }
 
 int batch_upload(vpz_batch* b) {
@@ -291,10 +433,12 @@ int batch_upload(vpz_batch* b) {
     return VPZ_E_CUDA;
   if ((rc = dev::h2d(b->d_pkts_ola.p, b->pkts_ola.p, np * sizeof(VpzPktOla), st, err))) return rc;
   if ((rc = dev::h2d(b->d_items.p, b->items.p, b->items.n * sizeof(VpzOlaItem), st, err))) return rc;
-  std::vector<const void*> ptrs;
-  for (vpz_setup* s : b->slots) ptrs.push_back(s->d_blob);
-  if ((rc = dev::h2d(b->d_setups.p, ptrs.data(), ptrs.size() * sizeof(void*), st, err))) return rc;
-  if ((rc = dev::stream_sync(st, err))) return rc;  // ptrs is a stack temporary
+  if (!b->h_setups.reserve(b->slots.size() + 1)) return VPZ_E_NOMEM;
+  b->h_setups.n = 0;
+  for (vpz_setup* s : b->slots) b->h_setups.p[b->h_setups.n++] = s->d_blob;
+  if ((rc = dev::h2d(b->d_setups.p, b->h_setups.p, b->h_setups.n * sizeof(void*), st, err))) return rc;
+  // no host sync: every source buffer is pinned memory owned by the batch and stays untouched until
+  // the next reset, which the caller orders after the stream work (vpz_batch_sync / events)
   b->uploaded = true;
   b->decoded = false;
   return VPZ_OK;

@@ -4,8 +4,13 @@
 #include <stdint.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "devapi.h"
@@ -26,9 +31,37 @@ struct vpz_setup {
   bool synthetic = false;           // window/twiddle tables only (vpz_synth_create)
 };
 
+namespace vpz {
+// Host worker pool for the bulk path: page scans, packet walks and the copy of packet bytes into
+// pinned staging are per-stream work with no shared state.
+class ThreadPool {
+ public:
+  explicit ThreadPool(unsigned n);
+  ~ThreadPool();
+  // Runs fn(0..n-1) on the workers and the calling thread; returns when all are done.
+  void parallel_for(size_t n, const std::function<void(size_t)>& fn);
+  unsigned size() const { return (unsigned)workers_.size() + 1; }
+
+ private:
+  void worker();
+  void drain();
+  std::vector<std::thread> workers_;
+  std::mutex m_;
+  std::condition_variable cv_, done_cv_;
+  const std::function<void(size_t)>* fn_ = nullptr;
+  size_t n_ = 0;
+  std::atomic<size_t> next_{0};
+  size_t finished_ = 0;
+  unsigned generation_ = 0, active_ = 0;
+  bool stop_ = false;
+};
+}  // namespace vpz
+
 struct vpz_ctx {
   int device = 0;
   vpz::dev::Stream* stream = nullptr;
+  vpz::dev::Stream* copy_stream = nullptr;   // device->host PCM copies of the bulk pipeline
+  vpz::ThreadPool* pool = nullptr;           // created on first bulk call
   vpz::dev::Event* ev[3] = {nullptr, nullptr, nullptr};
   std::string last_error;
   int l1_bits = VPZ_L1_BITS_DEFAULT;
@@ -39,7 +72,13 @@ struct vpz_ctx {
   uint32_t* d_counter = nullptr;
   vpz::dev::Event* marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int64_t kernel_launches = 0;
-  struct vpz_batch* bulk = nullptr;   // reused by vpz_decode_files so device buffers persist between calls
+  // vpz_decode_files pipeline: groups of streams rotate through these batches so that host planning,
+  // H2D + kernels and the D2H of finished PCM overlap; buffers persist between calls
+  struct vpz_batch* bulk[3] = {nullptr, nullptr, nullptr};
+  vpz::dev::Event* bulk_done[3] = {nullptr, nullptr, nullptr};   // D2H of the batch's PCM finished
+  vpz::dev::Event* bulk_ready[3] = {nullptr, nullptr, nullptr};  // kernels of the batch finished
+  int bulk_group = 256;                      // streams per pipeline group ("bulk_group" tunable)
+  int host_threads = 0;                      // 0: hardware concurrency, capped at 32
 };
 
 namespace vpz {
@@ -86,6 +125,25 @@ struct DevBuf {
   }
 };
 
+struct PktSrc {
+  const uint8_t* p;
+  uint32_t len;
+};
+
+// Everything batch_add_run decides about one run, computed WITHOUT touching the batch so that many
+// runs can be planned on worker threads and committed in one go (batch_commit).
+struct RunPlan {
+  vpz_setup* setup = nullptr;
+  std::vector<PktSrc> src;          // decodable packets, in order
+  std::vector<uint32_t> byte_off;   // staged offset of each, relative to the run's byte base
+  std::vector<VpzPktOla> ola;       // spec_off relative to the run's spectrum base, out_off in samples
+  std::vector<int32_t> counts;      // per SUBMITTED packet
+  uint64_t staged_bytes = 0, payload_bytes = 0, spec_floats = 0;
+  int64_t samples = 0;
+  int status = 0;
+  int32_t stop_packet = -1;
+};
+
 struct Run {
   vpz_setup* setup = nullptr;
   int slot = 0;
@@ -112,6 +170,7 @@ struct vpz_batch {
   int max_channels = 1;
   bool uploaded = false, synthetic = false, decoded = false;
   vpz::DevBuf d_bytes, d_pkts_in, d_pkts_ola, d_items, d_res, d_spec, d_pcm, d_clip, d_setups;
+  vpz::HostBuf<const void*> h_setups;
   vpz::HostBuf<uint32_t> h_clip;
   bool clip_fetched = false;
   float ms_k1 = 0, ms_k3 = 0, ms_total = 0;
@@ -125,10 +184,18 @@ struct vpz_batch {
 namespace vpz {
 int setup_create(vpz_ctx* ctx, const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt, size_t setup_len,
                  vpz_setup** out);
+// same, with fnv1a64(setup, fnv1a64(id)) already computed (the bulk path hashes on worker threads)
+int setup_create_hashed(vpz_ctx* ctx, uint64_t hash, const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
+                        size_t setup_len, vpz_setup** out);
 int setup_create_synthetic(vpz_ctx* ctx, int channels, int lg0, int lg1, vpz_setup** out);
 void setup_release(vpz_setup* s);
 int batch_add_run(vpz_batch* b, vpz_setup* s, const uint8_t* bytes, const uint32_t* offsets, uint32_t n_pkts,
                   const int32_t* trim);
+// Pure planning of one run (thread-safe; `err` receives the text on failure).
+int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* trim, RunPlan* out, std::string* err);
+// Appends planned runs to the batch: serial prefix sums, then the copies on `pool` (may be NULL).
+// first_run receives the index of plans[0]'s run.
+int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool, int* first_run);
 int batch_upload(vpz_batch* b);
 int batch_decode(vpz_batch* b, int clip);
 int batch_fetch_clip(vpz_batch* b);

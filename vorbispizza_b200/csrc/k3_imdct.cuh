@@ -300,37 +300,87 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& it, float* smem, i
         for (int i = t64; i < 2 * M; i += K3_THREADS_PER_CH) dy[i] = exec ? k3_y(D, M, i) : 0.f;
       }
 
-      // ---- window + overlap-add + clip + interleaved store, all threads over (sample, channel) ----
+      // ---- window + overlap-add + clip + interleaved store ---------------------------------------
+      // Every warp takes 32 consecutive samples per step.  y[] is a piecewise mirrored read of D
+      // (k3_y) whose breakpoints, like LeftStart / RightStart of untrimmed packets, are multiples
+      // of 64, so one warp step never straddles a breakpoint: the piece (base, direction, sign) is
+      // picked once per step with warp-uniform branches and each lane does two shared loads, two
+      // window loads, two multiplies and one add per channel -- same rounding order as
+      // OverlapBuffers (StreamDecoder.cs:786-788): two rounded products, one rounded sum.
       if (emit) {
         const int ls = pk.left_start, rs = pk.right_start;
         const int count = rs - ls;
         const int L = prev_re - prev_rs;             // StreamDecoder.cs:654
         const float* w = (pk.flags & VPZ_OLA_LEFT1) ? slope1 : slope0;
-        float* outp = P.pcm + it.out_base + (size_t)pk.out_off * C;
+        float* outp = P.pcm + it.out_base + (size_t)pk.out_off * C + c0;
+        const int lane = tid & 31, wid = tid >> 5, nw = nthreads >> 5;
+        const int h = M >> 1, ph = prevM >> 1;
+        const bool pair_ok = (reinterpret_cast<uintptr_t>(outp) & 7u) == 0;  // runs are packed back to back
+        const float* Dbase = smem + 4 * PA;
         uint32_t clipped_at = 0xffffffffu;
-        for (int e = tid; e < count * ncur; e += nthreads) {
-          int j = e / ncur, cg = e - j * ncur;
-          int c = c0 + cg;
-          const float* Dc = smem + cg * per_ch + 4 * PA + parity * Mmax;
-          const float* Dp = smem + cg * per_ch + 4 * PA + (parity ^ 1) * Mmax;
-          bool cur_on = (mask >> c) & 1u;
-          bool prev_on = !((zero_bits >> (cg * 2 + (parity ^ 1))) & 1u);
-          float v = cur_on ? k3_y(Dc, M, ls + j) : 0.f;
-          if (j < L) {
-            float pv = prev_on ? k3_y(Dp, prevM, prev_rs + j) : 0.f;
-            // OverlapBuffers (StreamDecoder.cs:786-788): two rounded products, one rounded sum
-            v = __fadd_rn(__fmul_rn(v, VPZ_LDG(w + j)), __fmul_rn(pv, VPZ_LDG(w + (L - 1 - j))));
+        uint32_t cur_on = 0, prev_on = 0;
+        for (int cg = 0; cg < ncur; cg++) {
+          if ((mask >> (c0 + cg)) & 1u) cur_on |= 1u << cg;
+          if (!((zero_bits >> (cg * 2 + (parity ^ 1))) & 1u)) prev_on |= 1u << cg;
+        }
+        for (int j0 = wid * 32; j0 < count; j0 += nw * 32) {
+          const int j = j0 + lane;
+          // current block, index i = ls + j
+          const int i0 = ls + j0;
+          int cidx;
+          float csign;
+          if (i0 < h) { cidx = i0 + h + lane; csign = 1.f; }
+          else if (i0 < M + h) { cidx = M + h - 1 - i0 - lane; csign = -1.f; }
+          else { cidx = i0 - M - h + lane; csign = -1.f; }
+          // previous block, index prev_rs + j (only inside the overlap)
+          const int p0 = prev_rs + j0;
+          int pidx;
+          float psign;
+          if (p0 < ph) { pidx = p0 + ph + lane; psign = 1.f; }
+          else if (p0 < prevM + ph) { pidx = prevM + ph - 1 - p0 - lane; psign = -1.f; }
+          else { pidx = p0 - prevM - ph + lane; psign = -1.f; }
+          const bool in_ovl = j < L;
+          float w0 = 1.f, w1 = 0.f;
+          if (in_ovl) {
+            w0 = VPZ_LDG(w + j);
+            w1 = VPZ_LDG(w + (L - 1 - j));
           }
-          if (P.clip) {  // Utils.ClipValue (Utils.cs:44-58)
-            if (v > 0.99999994f) {
-              v = 0.99999994f;
-              clipped_at = clipped_at < (uint32_t)j ? clipped_at : (uint32_t)j;
-            } else if (v < -0.99999994f) {
-              v = -0.99999994f;
-              clipped_at = clipped_at < (uint32_t)j ? clipped_at : (uint32_t)j;
+          if (j < count) {
+            // breakpoints are multiples of 64 except after an end-of-stream trim, where the tail
+            // of the last step may run past a piece; clamp keeps the (discarded) reads in bounds
+            cidx = cidx < 0 ? 0 : (cidx >= M ? M - 1 : cidx);
+            pidx = pidx < 0 ? 0 : (pidx >= prevM ? prevM - 1 : pidx);
+            float v[2];
+#pragma unroll
+            for (int cg = 0; cg < 2; cg++) {
+              if (cg < ncur) {
+                const float* Dc = Dbase + cg * per_ch + parity * Mmax;
+                const float* Dp = Dbase + cg * per_ch + (parity ^ 1) * Mmax;
+                float x = ((cur_on >> cg) & 1u) ? csign * Dc[cidx] : 0.f;
+                if (in_ovl) {
+                  float pv = ((prev_on >> cg) & 1u) ? psign * Dp[pidx] : 0.f;
+                  x = __fadd_rn(__fmul_rn(x, w0), __fmul_rn(pv, w1));
+                }
+                if (P.clip) {  // Utils.ClipValue (Utils.cs:44-58)
+                  if (x > 0.99999994f) {
+                    x = 0.99999994f;
+                    clipped_at = clipped_at < (uint32_t)j ? clipped_at : (uint32_t)j;
+                  } else if (x < -0.99999994f) {
+                    x = -0.99999994f;
+                    clipped_at = clipped_at < (uint32_t)j ? clipped_at : (uint32_t)j;
+                  }
+                }
+                v[cg] = x;
+              }
+            }
+            float* o = outp + (size_t)j * C;
+            if (C == 2 && pair_ok) {
+              *reinterpret_cast<float2*>(o) = float2{v[0], v[1]};
+            } else {
+              o[0] = v[0];
+              if (ncur > 1) o[1] = v[1];
             }
           }
-          outp[(size_t)j * C + c] = v;
         }
         if (P.clip_first && clipped_at != 0xffffffffu) atomicMin(P.clip_first + gp, clipped_at);
       }

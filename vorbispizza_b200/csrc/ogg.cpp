@@ -15,19 +15,35 @@
 
 namespace vpz {
 
-static uint32_t g_crc_table[256];
-static bool g_crc_ready = false;
+// Ogg CRC-32 (poly 0x04c11db7, init 0, MSB first, no final xor), slice-by-8: the same check as the
+// reference's byte-swapped slice-by-8 table (Ogg/Crc.cs:20-63, Ogg/Crc.Table.cs:14-40).
+static uint32_t g_crc_table[8][256];
+static bool crc_init() {
+  for (uint32_t i = 0; i < 256; i++) {
+    uint32_t r = i << 24;
+    for (int j = 0; j < 8; j++) r = (r << 1) ^ ((r & 0x80000000u) ? 0x04c11db7u : 0u);
+    g_crc_table[0][i] = r;
+  }
+  for (uint32_t i = 0; i < 256; i++)
+    for (int k = 1; k < 8; k++) {
+      uint32_t r = g_crc_table[k - 1][i];
+      g_crc_table[k][i] = (r << 8) ^ g_crc_table[0][r >> 24];
+    }
+  return true;
+}
+static const bool g_crc_ready = crc_init();
 
 uint32_t ogg_crc(const uint8_t* data, size_t len, uint32_t crc) {
-  if (!g_crc_ready) {
-    for (uint32_t i = 0; i < 256; i++) {
-      uint32_t r = i << 24;
-      for (int j = 0; j < 8; j++) r = (r << 1) ^ ((r & 0x80000000u) ? 0x04c11db7u : 0u);
-      g_crc_table[i] = r;
-    }
-    g_crc_ready = true;
+  (void)g_crc_ready;
+  size_t i = 0;
+  for (; i + 8 <= len; i += 8) {
+    const uint8_t* p = data + i;
+    uint32_t hi = crc ^ (((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | (uint32_t)p[3]);
+    crc = g_crc_table[7][hi >> 24] ^ g_crc_table[6][(hi >> 16) & 0xff] ^ g_crc_table[5][(hi >> 8) & 0xff] ^
+          g_crc_table[4][hi & 0xff] ^ g_crc_table[3][p[4]] ^ g_crc_table[2][p[5]] ^ g_crc_table[1][p[6]] ^
+          g_crc_table[0][p[7]];
   }
-  for (size_t i = 0; i < len; i++) crc = (crc << 8) ^ g_crc_table[((crc >> 24) ^ data[i]) & 0xff];
+  for (; i < len; i++) crc = (crc << 8) ^ g_crc_table[0][((crc >> 24) ^ data[i]) & 0xff];
   return crc;
 }
 
@@ -193,7 +209,8 @@ void LogicalStream::create_packet(int64_t* pg, int* pk, bool advance, int64_t gr
   out->page_index = *pg;
   out->packet_index = *pk;
   page_packet_slice(first, *pk, &d, &n);
-  out->data.assign(d, d + n);
+  out->ptr = d;
+  out->len = (uint32_t)n;
   bool is_last;
   int64_t final_page = *pg;
   if (is_continued && *pk == packet_count - 1) {
@@ -211,7 +228,10 @@ void LogicalStream::create_packet(int64_t* pg, int* pk, bool advance, int64_t gr
       if (!(np->flags & 1) || is_resync) break;
       if (is_continued && packet_count > 1) is_continued = false;
       page_packet_slice(np, 0, &d, &n);
-      out->data.insert(out->data.end(), d, d + n);
+      if (out->owned.empty() && out->len) out->owned.assign(out->ptr, out->ptr + out->len);
+      out->owned.insert(out->owned.end(), d, d + n);
+      out->len = (uint32_t)out->owned.size();
+      out->ptr = out->owned.data();
     }
     is_last = packet_count == 1;
     final_page = cont;

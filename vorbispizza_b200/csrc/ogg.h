@@ -26,7 +26,13 @@ struct OggPage {
 };
 
 struct OggPacket {
-  std::vector<uint8_t> data;
+  // A packet that lies inside one page is a VIEW into the container image (no copy); only packets
+  // continued across pages are assembled into `owned`.
+  const uint8_t* ptr = nullptr;
+  uint32_t len = 0;
+  std::vector<uint8_t> owned;
+  const uint8_t* data() const { return ptr; }
+  size_t size() const { return len; }
   bool valid = false;
   bool is_resync = false, is_eos = false;
   int64_t granule = -1;

@@ -15,10 +15,14 @@
 //   StreamDecoder.Read / ReadNextPacket / DecodeNextPacket / ResetDecoder      StreamDecoder.cs:357-369,418-498,640-762
 //   StreamDecoder.SeekTo / GetPacketGranuleCount                               StreamDecoder.cs:817-913
 //   StoreInterleaved / StoreContiguous / Utils.ClipValue                       StreamDecoder.cs:515-638, Utils.cs:44-58
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <deque>
 #include <memory>
 #include <new>
 #include <thread>
@@ -51,20 +55,28 @@ struct Entry {            // one packet handed out by the provider, already plan
   size_t drain_off = 0;   // float offset of the raw right half (only for a failed end-of-stream packet)
 };
 
-// A planned window: entries in provider order plus the bytes of the packets the GPU has to decode.
+// A planned window: entries in provider order plus the packets the GPU has to decode.
 struct Window {
   std::vector<Entry> entries;
-  std::vector<uint8_t> bytes;
-  std::vector<uint32_t> offs{0};
+  std::vector<PktSrc> src;        // submitted packets: views into the container image or `arena`
   std::vector<int32_t> trims;
   std::vector<int> entry_of;      // submitted packet -> entry index (-1: carried-over seed packet)
+  std::deque<std::vector<uint8_t>> arena;  // packets assembled across pages
   // drain of the last decoded packet's raw right half (see resolve_drain)
-  bool drain = false;
-  std::vector<uint8_t> drain_bytes;
+  bool drain = false, drain_extra_run = false;
   int drain_tail = 0, drain_entry = -1;
-  void add_packet(const uint8_t* p, size_t n, int32_t trim, int entry) {
-    bytes.insert(bytes.end(), p, p + n);
-    offs.push_back((uint32_t)bytes.size());
+  // filled by plan_submit
+  RunPlan plan, drain_plan;
+  bool has_plan = false, has_drain_plan = false;
+  std::vector<PktSrc> drain_src;
+  int32_t drain_trims[2] = {0, 0};
+  void add_packet(OggPacket* pk, int32_t trim, int entry) {
+    if (!pk->owned.empty()) {
+      arena.push_back(std::move(pk->owned));
+      src.push_back(PktSrc{arena.back().data(), (uint32_t)arena.back().size()});
+    } else {
+      src.push_back(PktSrc{pk->ptr, pk->len});
+    }
     trims.push_back(trim);
     entry_of.push_back(entry);
   }
@@ -78,6 +90,7 @@ struct StreamDec {
   LogicalStream* ls = nullptr;
   vpz_setup* setup = nullptr;
   std::vector<uint8_t> hdr[3];
+  uint64_t setup_hash = 0;
   std::string vendor;
   std::vector<std::string> comments;
   // ---- reference decoder state, consumption side (StreamDecoder.cs:40-49) ----
@@ -118,7 +131,7 @@ struct StreamDec {
   // IPacketGranuleCountProvider.GetPacketGranuleCount (StreamDecoder.cs:882-913)
   int granule_count(const OggPacket& pk) const {
     if (pk.is_resync) return 0;
-    PacketGeom g = setup->host.packet_geometry(pk.data.data(), pk.data.size());
+    PacketGeom g = setup->host.packet_geometry(pk.ptr, pk.len);
     if (!g.valid) return 0;
     return g.right_start - g.left_start;
   }
@@ -160,36 +173,47 @@ int parse_comments(StreamDec* d, const std::vector<uint8_t>& pk) {
   return VPZ_OK;
 }
 
-// StreamDecoder.Initialize -> ProcessHeaderPackets (StreamDecoder.cs:71-165)
-int stream_init(StreamDec* d, vpz_ctx* ctx, LogicalStream* ls) {
-  d->ctx = ctx;
+// StreamDecoder.Initialize -> ProcessHeaderPackets (StreamDecoder.cs:71-165), in two steps so the
+// bulk path can run the per-stream part on worker threads:
+//   stream_prepare : header packets, id / comment parse, content hash        (no shared state)
+//   stream_attach  : setup cache lookup or table build + upload              (touches the context)
+int stream_prepare(StreamDec* d, LogicalStream* ls, std::string* err) {
   d->ls = ls;
   for (int i = 0; i < 3; i++) {
     OggPacket pk;
     ls->next_packet(&pk);
     if (!pk.valid) {
-      ctx->last_error = i == 0 ? "First packet is not valid." : "Could not find Vorbis data to decode.";
+      *err = i == 0 ? "First packet is not valid." : "Could not find Vorbis data to decode.";
       return VPZ_E_INVALID_DATA;
     }
-    d->hdr[i] = std::move(pk.data);
+    d->hdr[i].assign(pk.ptr, pk.ptr + pk.len);
   }
   IdHeader id;
   int rc = parse_id_header(d->hdr[0].data(), d->hdr[0].size(), &id);
+  if (!rc) rc = parse_comments(d, d->hdr[1]);
   if (rc) {
-    ctx->last_error = "Could not find Vorbis data to decode.";
+    *err = "Could not find Vorbis data to decode.";
     return rc;
   }
-  if ((rc = parse_comments(d, d->hdr[1]))) {
-    ctx->last_error = "Could not find Vorbis data to decode.";
-    return rc;
-  }
-  rc = setup_create(ctx, d->hdr[0].data(), d->hdr[0].size(), d->hdr[2].data(), d->hdr[2].size(), &d->setup);
+  d->setup_hash = fnv1a64(d->hdr[2].data(), d->hdr[2].size(), fnv1a64(d->hdr[0].data(), d->hdr[0].size()));
+  return VPZ_OK;
+}
+
+int stream_attach(StreamDec* d, vpz_ctx* ctx) {
+  d->ctx = ctx;
+  int rc = setup_create_hashed(ctx, d->setup_hash, d->hdr[0].data(), d->hdr[0].size(), d->hdr[2].data(),
+                               d->hdr[2].size(), &d->setup);
   if (rc) return rc;
-  ls->granule_count = [d](const OggPacket& pk) { return d->granule_count(pk); };
+  d->ls->granule_count = [d](const OggPacket& pk) { return d->granule_count(pk); };
   d->current_position = 0;
   d->reset_decoder();
   d->has_position = true;
   return VPZ_OK;
+}
+
+int stream_init(StreamDec* d, vpz_ctx* ctx, LogicalStream* ls) {
+  int rc = stream_prepare(d, ls, &ctx->last_error);
+  return rc ? rc : stream_attach(d, ctx);
 }
 
 // Walks the provider for up to `max_packets` packets and replays ReadNextPacket's bookkeeping
@@ -203,7 +227,11 @@ void plan_window(StreamDec* d, int max_packets, Window* w) {
   int64_t pos = d->current_position;
   bool has_pos = d->has_position;
   int seek_left = d->seek_left;
-  if (have_prev && !d->carry.empty()) w->add_packet(d->carry.data(), d->carry.size(), d->carry_trim, -1);
+  if (have_prev && !d->carry.empty()) {
+    w->src.push_back(PktSrc{d->carry.data(), (uint32_t)d->carry.size()});
+    w->trims.push_back(d->carry_trim);
+    w->entry_of.push_back(-1);
+  }
   for (int n = 0; max_packets <= 0 || n < max_packets; n++) {
     OggPacket pk;
     d->ls->next_packet(&pk);
@@ -216,7 +244,7 @@ void plan_window(StreamDec* d, int max_packets, Window* w) {
     e.eos_flags = pk.is_eos ? EOS_PACKET_FLAG : EOS_NONE;
     e.is_resync = pk.is_resync;
     if (pk.is_resync) has_pos = false;
-    PacketGeom g = st.packet_geometry(pk.data.data(), pk.data.size());
+    PacketGeom g = st.packet_geometry(pk.ptr, pk.len);
     if (g.bad_mode) {  // the exception leaves DecodeNextPacket before _eosFound is updated
       e.eos_flags = EOS_NONE;
       e.err = VPZ_E_INVALID_DATA;
@@ -250,7 +278,7 @@ void plan_window(StreamDec* d, int max_packets, Window* w) {
     e.count = have_prev ? rs - g.left_start : 0;
     e.tail = g.right_end - rs;
     e.granule = pk.granule;
-    w->add_packet(pk.data.data(), pk.data.size(), trim, (int)w->entries.size());
+    w->add_packet(&pk, trim, (int)w->entries.size());
     w->entries.push_back(e);
     have_prev = true;
     prev_tail = e.tail;
@@ -288,40 +316,37 @@ void resolve_drain(StreamDec* d, Window* w) {
   if (ei >= 0) {
     w->trims[k] = -tail;  // P is never an end-of-stream packet itself, so its trim was 0
   } else {
-    w->drain_bytes.assign(w->bytes.begin() + w->offs[k], w->bytes.begin() + w->offs[k + 1]);
+    w->drain_extra_run = true;
+    w->drain_src = {w->src[k], w->src[k]};
+    w->drain_trims[0] = 0;
+    w->drain_trims[1] = -tail;
   }
 }
 
-// Queues the window on batch `b`.  run_out/drain_run_out receive the run indices (-1: none).
-int submit_window(StreamDec* d, vpz_batch* b, Window* w, int* run_out, int* drain_run_out) {
-  *run_out = *drain_run_out = -1;
-  const uint32_t n = (uint32_t)w->trims.size();
+// Plans the GPU runs of the window (pure per-stream work: safe on worker threads).
+int plan_submit(StreamDec* d, Window* w, std::string* err) {
   bool emits = false;
   for (int e : w->entry_of) emits |= e >= 0;
-  if (n && emits) {
-    int run = batch_add_run(b, d->setup, w->bytes.data(), w->offs.data(), n, w->trims.data());
-    if (run < 0) return run;
-    *run_out = run;
+  if (!w->src.empty() && emits) {
+    int rc = plan_run(d->setup, w->src.data(), (uint32_t)w->src.size(), w->trims.data(), &w->plan, err);
+    if (rc) return rc;
+    w->has_plan = true;
   }
-  if (w->drain && !w->drain_bytes.empty()) {
-    std::vector<uint8_t> two(w->drain_bytes);
-    two.insert(two.end(), w->drain_bytes.begin(), w->drain_bytes.end());
-    uint32_t offs[3] = {0, (uint32_t)w->drain_bytes.size(), (uint32_t)two.size()};
-    int32_t trims[2] = {0, -w->drain_tail};
-    int run = batch_add_run(b, d->setup, two.data(), offs, 2, trims);
-    if (run < 0) return run;
-    *drain_run_out = run;
+  if (w->drain_extra_run) {
+    int rc = plan_run(d->setup, w->drain_src.data(), 2, w->drain_trims, &w->drain_plan, err);
+    if (rc) return rc;
+    w->has_drain_plan = true;
   }
   return VPZ_OK;
 }
 
-// After planning the batch: turns per-run sample counts into offsets inside the buffer the PCM of
-// the batch is (or will be) copied to.
-int place_window(StreamDec* d, vpz_batch* b, Window* w, int run, int drain_run) {
+// After the runs are committed to a batch: turns per-run sample counts into offsets inside the
+// buffer the PCM of the batch is (or will be) copied to.  `shift` is added to every offset.
+int place_window(StreamDec* d, vpz_batch* b, Window* w, int run, int drain_run, size_t shift) {
   const int C = d->channels();
   if (run >= 0) {
     const Run& r = b->runs[(size_t)run];
-    size_t off = (size_t)r.out_base;
+    size_t off = (size_t)r.out_base + shift;
     for (size_t k = 0; k < w->entry_of.size(); k++) {
       const int ei = w->entry_of[k];
       const int cnt = r.counts[k];
@@ -332,7 +357,7 @@ int place_window(StreamDec* d, vpz_batch* b, Window* w, int run, int drain_run) 
           e.err = VPZ_E_REF_FAULT;
           continue;
         }
-        const bool drained = w->drain && w->drain_bytes.empty() && k + 1 == w->entry_of.size();
+        const bool drained = w->drain && !w->drain_extra_run && k + 1 == w->entry_of.size();
         if (cnt != e.count + (drained ? w->drain_tail : 0)) {
           d->ctx->last_error = "internal: window plan and batch plan disagree";
           return VPZ_E_INVALID_OP;
@@ -345,8 +370,23 @@ int place_window(StreamDec* d, vpz_batch* b, Window* w, int run, int drain_run) 
   }
   if (drain_run >= 0) {
     const Run& r = b->runs[(size_t)drain_run];
-    w->entries[(size_t)w->drain_entry].drain_off = (size_t)r.out_base + (size_t)(r.samples - w->drain_tail) * C;
+    w->entries[(size_t)w->drain_entry].drain_off = (size_t)r.out_base + shift + (size_t)(r.samples - w->drain_tail) * C;
   }
+  return VPZ_OK;
+}
+
+// Commits the planned runs of one window to batch b.
+int commit_window(vpz_batch* b, Window* w, int* run, int* drain_run) {
+  *run = *drain_run = -1;
+  RunPlan* plans[2];
+  size_t n = 0;
+  if (w->has_plan) plans[n++] = &w->plan;
+  if (w->has_drain_plan) plans[n++] = &w->drain_plan;
+  int first = 0;
+  int rc = batch_commit(b, plans, n, nullptr, &first);
+  if (rc) return rc;
+  if (w->has_plan) *run = first++;
+  if (w->has_drain_plan) *drain_run = first;
   return VPZ_OK;
 }
 
@@ -360,10 +400,11 @@ int decode_ahead(StreamDec* d) {
   Window w;
   plan_window(d, d->lookahead, &w);
   resolve_drain(d, &w);
+  int rc = plan_submit(d, &w, &ctx->last_error);
+  if (rc) return rc;
   vpz_batch_reset(d->batch);
   int run, drain_run;
-  int rc = submit_window(d, d->batch, &w, &run, &drain_run);
-  if (rc) return rc;
+  if ((rc = commit_window(d->batch, &w, &run, &drain_run))) return rc;
   size_t total = (size_t)d->batch->total_floats;
   if (total) {
     if (!d->pcm.reserve(total)) return VPZ_E_NOMEM;
@@ -371,12 +412,13 @@ int decode_ahead(StreamDec* d) {
     if ((rc = batch_decode(d->batch, 0))) return rc;
     if ((rc = vpz_batch_read_all(d->batch, d->pcm.p))) return rc;
   }
-  if ((rc = place_window(d, d->batch, &w, run, drain_run))) return rc;
+  if ((rc = place_window(d, d->batch, &w, run, drain_run, 0))) return rc;
   // remember the last decoded packet as the seed of the next window
   for (int k = (int)w.entry_of.size() - 1; k >= 0; k--) {
     if (w.entry_of[(size_t)k] < 0) break;  // only the seed itself was submitted
     if (w.entries[(size_t)w.entry_of[(size_t)k]].ok) {
-      d->carry.assign(w.bytes.begin() + w.offs[(size_t)k], w.bytes.begin() + w.offs[(size_t)k + 1]);
+      std::vector<uint8_t> next(w.src[(size_t)k].p, w.src[(size_t)k].p + w.src[(size_t)k].len);
+      d->carry.swap(next);
       d->carry_trim = w.trims[(size_t)k];
       break;
     }
@@ -729,8 +771,8 @@ int vpz_reader_audio_packet(vpz_reader* r, int i, const uint8_t** data, uint32_t
   build_table(d);
   if (i < 0 || (size_t)i >= d->table.size()) return VPZ_E_ARGUMENT;
   const OggPacket& pk = d->table[(size_t)i];
-  if (data) *data = pk.data.data();
-  if (len) *len = (uint32_t)pk.data.size();
+  if (data) *data = pk.ptr;
+  if (len) *len = pk.len;
   if (granule) *granule = pk.granule;
   if (flags) *flags = (pk.is_resync ? 1 : 0) | (pk.is_eos ? 2 : 0);
   return VPZ_OK;
@@ -742,79 +784,147 @@ const uint8_t* vpz_reader_header_packet(vpz_reader* r, int which, uint32_t* len)
 }
 vpz_setup* vpz_reader_setup(vpz_reader* r) { return r ? r->dec()->setup : nullptr; }
 
-// ---- bulk: many whole files in one batch ---------------------------------------------------------
+// ---- bulk: many whole files, pipelined in groups ---------------------------------------------------
+// Host work (page scan + CRC, header lookup, packet walk, window plan, copy into pinned staging) runs
+// on the worker pool group by group; while the GPU decodes group g (H2D, K1, K3 on the compute
+// stream) and the copy stream moves the PCM of group g-1 to the caller's buffer, the host already
+// plans group g+1.  Three batches rotate so no buffer is reused before its copies have finished.
+namespace {
+struct BulkJob {
+  OggContainer cont;
+  StreamDec dec;
+  Window win;
+  int rc = 0;
+  std::string err;
+};
+}  // namespace
+
 int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, int clip,
                          float* dst, size_t dst_floats, int64_t* sample_counts) {
   if (!ctx || (n && (!datas || !lens))) return VPZ_E_ARGUMENT;
-  struct Job {
-    OggContainer cont;
-    StreamDec dec;
-    Window win;
-    int rc = 0;
-    int run = -1, drain_run = -1;
-  };
-  std::vector<std::unique_ptr<Job>> jobs(n);
-  // 1. page scan (CRC) in parallel: pure host work, no shared state
-  unsigned nthreads = std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
-  nthreads = std::min<unsigned>(nthreads, std::max<uint32_t>(1, n));
-  {
-    std::atomic<uint32_t> next{0};
-    auto work = [&]() {
-      for (;;) {
-        uint32_t i = next.fetch_add(1);
-        if (i >= n) break;
-        jobs[i].reset(new Job);
-        jobs[i]->rc = jobs[i]->cont.scan(datas[i], lens[i]);
-      }
-    };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
+  if (!ctx->pool) {
+    unsigned t = ctx->host_threads > 0 ? (unsigned)ctx->host_threads
+                                       : std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    ctx->pool = new (std::nothrow) ThreadPool(t);
+    if (!ctx->pool) return VPZ_E_NOMEM;
   }
-  // 2. headers + setup cache (shared, serial: identical header pairs collapse onto one device image)
-  for (uint32_t i = 0; i < n; i++) {
-    Job& j = *jobs[i];
-    if (j.rc) return j.rc;
-    j.rc = stream_init(&j.dec, ctx, j.cont.streams[0]);
-    if (j.rc) return j.rc;
-  }
-  // 3. packet walk + window plan in parallel (per-stream state only)
-  {
-    std::atomic<uint32_t> next{0};
-    auto work = [&]() {
-      for (;;) {
-        uint32_t i = next.fetch_add(1);
-        if (i >= n) break;
-        plan_window(&jobs[i]->dec, 0, &jobs[i]->win);
-        resolve_drain(&jobs[i]->dec, &jobs[i]->win);
-      }
-    };
-    std::vector<std::thread> th;
-    for (unsigned t = 1; t < nthreads; t++) th.emplace_back(work);
-    work();
-    for (auto& t : th) t.join();
-  }
-  // 4. one batch for everything
-  int rc = VPZ_OK;
-  if (!ctx->bulk) rc = vpz_batch_create(ctx, &ctx->bulk);
-  if (rc) return rc;
-  vpz_batch* b = ctx->bulk;
-  vpz_batch_reset(b);
+  ThreadPool* pool = ctx->pool;
+  const bool trace = getenv("VPZ_TRACE") != nullptr;
+  double t_scan = 0, t_init = 0, t_plan = 0, t_commit = 0, t_launch = 0, t_wait = 0;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t0 = now(), t1;
+  const uint32_t G = (uint32_t)std::max(1, ctx->bulk_group);
+  std::vector<std::unique_ptr<BulkJob>> held[3];  // jobs stay alive while their batch may still be in flight
+  bool used[3] = {false, false, false};
   int64_t total = 0;
-  for (uint32_t i = 0; i < n && !rc; i++) {
-    Job& j = *jobs[i];
-    rc = submit_window(&j.dec, b, &j.win, &j.run, &j.drain_run);
-    if (!rc && sample_counts) sample_counts[i] = j.run >= 0 ? b->runs[(size_t)j.run].samples : 0;
+  int rc = VPZ_OK;
+  uint32_t group = 0;
+  for (uint32_t first = 0; first < n && !rc; first += G, group++) {
+    const uint32_t cnt = std::min(G, n - first);
+    const int slot = (int)(group % 3);
+    t0 = now();
+    if (dst && used[slot]) {
+      if ((rc = dev::event_sync(ctx->bulk_done[slot], ctx->last_error))) break;
+    }
+    t1 = now(); t_wait += t1 - t0; t0 = t1;
+    std::vector<std::unique_ptr<BulkJob>>& jobs = held[slot];
+    jobs.clear();
+    jobs.resize(cnt);
+    // 1. page scan (CRC) -- parallel, no shared state
+    pool->parallel_for(cnt, [&](size_t i) {
+      jobs[i].reset(new BulkJob);
+      BulkJob& j = *jobs[i];
+      j.rc = j.cont.scan(datas[first + i], lens[first + i]);
+      if (!j.rc) j.rc = stream_prepare(&j.dec, j.cont.streams[0], &j.err);
+    });
+    t1 = now(); t_scan += t1 - t0; t0 = t1;
+    // 2. headers + setup cache (shared, serial: identical header pairs collapse onto one device image)
+    for (uint32_t i = 0; i < cnt && !rc; i++) {
+      BulkJob& j = *jobs[i];
+      if (j.rc) ctx->last_error = j.err;
+      rc = j.rc ? j.rc : stream_attach(&j.dec, ctx);
+    }
+    if (rc) break;
+    t1 = now(); t_init += t1 - t0; t0 = t1;
+    // 3. packet walk + window plan + run plan -- parallel, per-stream state only
+    pool->parallel_for(cnt, [&](size_t i) {
+      BulkJob& j = *jobs[i];
+      plan_window(&j.dec, 0, &j.win);
+      resolve_drain(&j.dec, &j.win);
+      j.rc = plan_submit(&j.dec, &j.win, &j.err);
+    });
+    t1 = now(); t_plan += t1 - t0; t0 = t1;
+    std::vector<RunPlan*> plans;
+    plans.reserve(cnt);
+    uint64_t group_floats = 0;
+    for (uint32_t i = 0; i < cnt; i++) {
+      BulkJob& j = *jobs[i];
+      if (j.rc) {
+        rc = j.rc;
+        ctx->last_error = j.err;
+        break;
+      }
+      int64_t samples = j.win.has_plan ? j.win.plan.samples : 0;
+      if (sample_counts) sample_counts[first + i] = samples;
+      group_floats += (uint64_t)samples * j.dec.channels();
+      if (j.win.has_plan) plans.push_back(&j.win.plan);
+    }
+    if (rc) break;
+    if (!dst) {  // size query: nothing is decoded
+      total += (int64_t)group_floats;
+      continue;
+    }
+    if ((uint64_t)total + group_floats > dst_floats) {
+      ctx->last_error = "destination buffer too small";
+      rc = VPZ_E_ARGUMENT;
+      break;
+    }
+    if (!ctx->bulk[slot]) {
+      if ((rc = vpz_batch_create(ctx, &ctx->bulk[slot]))) break;
+      ctx->bulk_done[slot] = dev::event_create();
+      ctx->bulk_ready[slot] = dev::event_create();
+      if (!ctx->bulk_done[slot] || !ctx->bulk_ready[slot]) {
+        rc = VPZ_E_CUDA;
+        break;
+      }
+    }
+    vpz_batch* b = ctx->bulk[slot];
+    vpz_batch_reset(b);
+    // 4. copy packet bytes + descriptors into pinned staging -- parallel
+    if ((rc = batch_commit(b, plans.data(), plans.size(), pool, nullptr))) break;
+    if (b->total_floats != group_floats) {
+      ctx->last_error = "internal: group plan and batch plan disagree";
+      rc = VPZ_E_INVALID_OP;
+      break;
+    }
+    t1 = now(); t_commit += t1 - t0; t0 = t1;
+    if (group_floats) {
+      // 5. H2D + K1 + K3 on the compute stream, then the PCM of this group on the copy stream
+      if ((rc = batch_decode(b, clip))) break;
+      dev::event_record(ctx->bulk_ready[slot], ctx->stream);
+      dev::stream_wait_event(ctx->copy_stream, ctx->bulk_ready[slot]);
+      if ((rc = dev::d2h(dst + total, b->d_pcm.p, group_floats * 4, ctx->copy_stream, ctx->last_error))) break;
+    }
+    dev::event_record(ctx->bulk_done[slot], ctx->copy_stream);
+    t1 = now(); t_launch += t1 - t0; t0 = t1;
+    used[slot] = true;
+    total += (int64_t)group_floats;
   }
-  if (!rc) {
-    total = (int64_t)b->total_floats;
-    if (dst && (size_t)total > dst_floats) rc = VPZ_E_ARGUMENT;
+  // drain the pipeline (also on errors: buffers must not be in flight when the jobs are freed)
+  for (int s = 0; s < 3; s++)
+    if (used[s]) {
+      int r2 = dev::event_sync(ctx->bulk_done[s], ctx->last_error);
+      if (!rc) rc = r2;
+    }
+  if (dst) {
+    int r2 = dev::stream_sync(ctx->stream, ctx->last_error);
+    if (!rc) rc = r2;
+    for (int s = 0; s < 3; s++)
+      if (ctx->bulk[s]) vpz_batch_reset(ctx->bulk[s]);  // drop setup references; device buffers stay allocated
   }
-  if (!rc && total) rc = batch_decode(b, clip);
-  if (!rc && total && dst) rc = vpz_batch_read_all(b, dst);
-  if (!rc && total && !dst) rc = vpz_batch_sync(b);
-  vpz_batch_reset(b);  // drops the setup references of this call; device buffers stay allocated
+  if (trace)
+    fprintf(stderr, "vpz_decode_files: %u files, %u groups: scan %.1f init %.1f plan %.1f commit %.1f launch %.1f wait %.1f drain %.1f ms\n",
+            n, group, t_scan, t_init, t_plan, t_commit, t_launch, t_wait, now() - t0);
   return rc ? rc : total;
 }
 

@@ -495,6 +495,12 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
     error = "channel count outside the GPU path (1..8)";
     return id.channels < 1 ? VPZ_E_INVALID_DATA : VPZ_E_UNSUPPORTED;
   }
+  if (id.size0 < 256 && id.size0 >= 64 && id.size1 >= id.size0 && id.size1 <= 8192) {
+    // the reference's Mdct.CalcReverse (Mdct.cs:200-249) is not a valid IMDCT for
+    // n = 64 / 128, so "identical to the reference" would mean reproducing noise; refuse instead.
+    error = "block size 64/128: the reference MDCT is not a valid transform below 256 (quirk Q10)";
+    return VPZ_E_UNSUPPORTED;
+  }
   if (id.size0 < 64 || id.size1 < id.size0 || id.size1 > 8192) {
     error = "block sizes outside 64..8192";
     return VPZ_E_INVALID_DATA;

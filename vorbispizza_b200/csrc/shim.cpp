@@ -52,9 +52,10 @@ int vpz_ctx_create(int device, vpz_ctx** out) {
   if (!c) return VPZ_E_NOMEM;
   c->device = device;
   c->stream = dev::stream_create();
+  c->copy_stream = dev::stream_create();
   for (int i = 0; i < 3; i++) c->ev[i] = dev::event_create();
   c->d_counter = static_cast<uint32_t*>(dev::alloc(64, c->last_error));
-  if (!c->stream || !c->ev[0] || !c->ev[1] || !c->ev[2] || !c->d_counter) {
+  if (!c->stream || !c->copy_stream || !c->ev[0] || !c->ev[1] || !c->ev[2] || !c->d_counter) {
     vpz_ctx_destroy(c);
     return VPZ_E_CUDA;
   }
@@ -64,8 +65,14 @@ int vpz_ctx_create(int device, vpz_ctx** out) {
 
 void vpz_ctx_destroy(vpz_ctx* c) {
   if (!c) return;
-  if (c->bulk) vpz_batch_destroy(c->bulk);
-  c->bulk = nullptr;
+  for (int i = 0; i < 3; i++) {
+    if (c->bulk[i]) vpz_batch_destroy(c->bulk[i]);
+    c->bulk[i] = nullptr;
+    dev::event_destroy(c->bulk_done[i]);
+    dev::event_destroy(c->bulk_ready[i]);
+  }
+  delete c->pool;
+  c->pool = nullptr;
   for (int i = 0; i < 8; i++) dev::event_destroy(c->marks[i]);
   while (!c->setups.empty()) {
     vpz_setup* s = c->setups.begin()->second;
@@ -75,6 +82,7 @@ void vpz_ctx_destroy(vpz_ctx* c) {
   dev::free(c->d_counter);
   for (int i = 0; i < 3; i++) dev::event_destroy(c->ev[i]);
   dev::stream_destroy(c->stream);
+  dev::stream_destroy(c->copy_stream);
   delete c;
 }
 
@@ -105,6 +113,12 @@ int vpz_ctx_set(vpz_ctx* c, const char* key, int value) {
   } else if (!strcmp(key, "k1_warps")) {
     if (value < 1 || value > 8) return VPZ_E_ARGUMENT;
     c->k1_warps = value;
+  } else if (!strcmp(key, "bulk_group")) {
+    if (value < 1 || value > (1 << 20)) return VPZ_E_ARGUMENT;
+    c->bulk_group = value;
+  } else if (!strcmp(key, "host_threads")) {
+    if (value < 0 || value > 256 || c->pool) return VPZ_E_ARGUMENT;  // before the first bulk call
+    c->host_threads = value;
   } else {
     return VPZ_E_ARGUMENT;
   }
