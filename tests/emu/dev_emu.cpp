@@ -112,11 +112,10 @@ int launch_k1(const K1Params& p, bool debug, int blocks, int warps, Stream*, std
 
 int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream*, std::string&) {
   if (p.n_items == 0) return VPZ_OK;
-  emu::launch(p.n_items, (unsigned)ncb * K3_THREADS_PER_CH, smem_bytes, [&] {
+  *p.counter = 0;
+  emu::launch(2, (unsigned)ncb * K3_THREADS_PER_CH, smem_bytes, [&] {
     float* smem = (float*)emu::t_block->smem;
-    for (uint32_t item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      if (fast) k3_run_item<true>(p, p.items[item], smem, ncb); else k3_run_item<false>(p, p.items[item], smem, ncb);
-    }
+    if (fast) k3_cta_loop<true>(p, smem, ncb); else k3_cta_loop<false>(p, smem, ncb);
   });
   return VPZ_OK;
 }

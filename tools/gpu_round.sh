@@ -7,7 +7,7 @@ mkdir -p $OUT
 nvidia-smi > $OUT/nvidia-smi_$TAG.txt 2>&1
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu_$TAG.log 2>&1; echo "exit $?"; tail -5 $OUT/pytest_gpu_$TAG.log
 echo "== smoke"; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()' > $OUT/smoke_$TAG.log 2>&1; echo "exit $?"; tail -3 $OUT/smoke_$TAG.log
-echo "== bench"; timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "exit $?"; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
+echo "== bench"; VPZ_TRACE=1 timeout 900 python bench.py --steps 5 --warmup 3 > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "exit $?"; cat $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "exit $?"; cat $OUT/bench_ref_$TAG.json
 echo "== ncu launch list"
 CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --streams 1024"

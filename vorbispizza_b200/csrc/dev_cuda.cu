@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 
+#include <algorithm>
+
 #include "../../include/vpz.h"
 #include "devapi.h"
 #include "k1_entropy.cuh"
@@ -25,10 +27,9 @@ __global__ void __launch_bounds__(256) vpz_k1_entropy(K1Params P) {
 }
 
 template <bool FAST>
-__global__ void __launch_bounds__(128) vpz_k3_imdct_ola(K3Params P, int ncb) {
+__global__ void __launch_bounds__(128, FAST ? 6 : 1) vpz_k3_imdct_ola(K3Params P, int ncb) {
   extern __shared__ float k3_smem[];
-  for (uint32_t item = blockIdx.x; item < P.n_items; item += gridDim.x)
-    k3_run_item<FAST>(P, P.items[item], k3_smem, ncb);
+  k3_cta_loop<FAST>(P, k3_smem, ncb);
 }
 
 namespace vpz {
@@ -216,10 +217,14 @@ int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream* 
     return VPZ_E_UNSUPPORTED;
   }
   int threads = ncb * K3_THREADS_PER_CH;
+  cudaError_t e0 = cudaMemsetAsync(p.counter, 0, 4, s->s);
+  if (e0 != cudaSuccess) return fail(e0, "cudaMemsetAsync(counter)", err);
+  // persistent CTAs: enough to fill every SM, items are handed out by the counter
+  unsigned grid = (unsigned)std::min<size_t>((p.n_items + K3_GRAB - 1) / K3_GRAB, (size_t)8 * g_sm_count);
   if (fast)
-    vpz_k3_imdct_ola<true><<<p.n_items, threads, smem_bytes, s->s>>>(p, ncb);
+    vpz_k3_imdct_ola<true><<<grid, threads, smem_bytes, s->s>>>(p, ncb);
   else
-    vpz_k3_imdct_ola<false><<<p.n_items, threads, smem_bytes, s->s>>>(p, ncb);
+    vpz_k3_imdct_ola<false><<<grid, threads, smem_bytes, s->s>>>(p, ncb);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k3_imdct_ola", err);
 }

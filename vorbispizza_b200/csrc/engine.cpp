@@ -31,7 +31,7 @@ static uint32_t k1_words(const Setup& st) {
 static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
   const VpzSetupHdr* h = s->host.hdr();
   s->fast_sizes = h->log2_size0 == 8 && h->log2_size1 == 11;
-  s->k3_floats_per_ch = 2u * (1u << h->log2_size1) + 16u;
+  s->k3_floats_per_ch = (1u << h->log2_size1) + 3u * (1u << (h->log2_size1 - 2)) + 16u;  // scratch + 3 half-slots
   if (!s->synthetic) s->k1_words_per_warp = k1_words(s->host);
   size_t bytes = s->host.blob.size() * 4;
   s->d_blob = dev::alloc(bytes, ctx->last_error);
@@ -234,7 +234,7 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
   out->byte_off.reserve(n_pkts);
   out->ola.reserve(n_pkts);
   bool have_prev = false;
-  int prev_rs = 0, prev_re = 0;
+  int prev_rs = 0, prev_re = 0, prev_half = 0;
   int64_t pos = 0;  // samples emitted so far by this run
   uint64_t staged = 0;
   for (uint32_t i = 0; i < n_pkts; i++) {
@@ -252,6 +252,13 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
     // StreamDecoder.cs:451-455 when the end-of-stream packet that follows cannot be decoded)
     if (trim && trim[i] < 0) rs = std::min(rs - trim[i], g.right_end);
     int count = 0;
+    if (have_prev && prev_rs < prev_half) {
+      // K3 keeps only the low half of the previous block's D (the right half of its output); a
+      // RightStart pulled back into the left half happens for the end-of-stream packet only, which
+      // has no successor in the reference (StreamDecoder.cs:439-447)
+      if (err) *err = "a packet follows one whose RightStart was trimmed into the left half";
+      return VPZ_E_ARGUMENT;
+    }
     if (have_prev) {
       int L = prev_re - prev_rs;
       int slope_len = (g.left_use_size1 ? st.id.size1 : st.id.size0) / 2;
@@ -290,6 +297,7 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
     have_prev = true;
     prev_rs = rs;
     prev_re = g.right_end;
+    prev_half = M;
   }
   out->staged_bytes = staged;
   out->samples = pos;
@@ -500,11 +508,14 @@ int batch_decode(vpz_batch* b, int clip) {
     p.pcm = static_cast<float*>(b->d_pcm.p);
     p.clip_first = static_cast<uint32_t*>(b->d_clip.p);
     p.n_items = (uint32_t)b->items.n;
+    p.counter = ctx->d_counter + 1;
     p.clip = clip ? 1 : 0;
     p.dbg_imdct = b->dbg_imdct;
     int ncb = std::min(2, b->max_channels);
-    size_t per_ch = fast ? (4 * 576 + 2 * 1024 + 16) : k3f;
-    if ((rc = dev::launch_k3(p, fast, ncb, (size_t)ncb * per_ch * 4, st, err))) return rc;
+    size_t per_ch = fast ? (2 * 576 + 3 * 512 + 16) : k3f;
+    // + K3_DESC_FLOATS of packet descriptors and (fast) K3_TAB_FLOATS of twiddle / window tables
+    size_t k3_smem = ((size_t)ncb * per_ch + 384 + (fast ? 3072 : 0)) * 4;
+    if ((rc = dev::launch_k3(p, fast, ncb, k3_smem, st, err))) return rc;
     b->launches++;
     ctx->kernel_launches++;
   }

@@ -65,7 +65,7 @@ struct vpz_ctx {
   vpz::dev::Event* ev[3] = {nullptr, nullptr, nullptr};
   std::string last_error;
   int l1_bits = VPZ_L1_BITS_DEFAULT;
-  int ola_chunk = 32;
+  int ola_chunk = 63;   // + the seed packet = one descriptor window of the IMDCT kernel
   int k1_warps = 4;
   std::multimap<uint64_t, vpz_setup*> setups;
   std::vector<vpz_setup*> recent;     // setups the context itself holds a reference on (LRU, 64)

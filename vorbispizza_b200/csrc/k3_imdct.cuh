@@ -14,8 +14,9 @@
 //   T = FFT_H(z);  c[p] = T[p] * tw[p];  D[2p] = Re c[p];  D[M-1-2p] = -Im c[p]
 // The FFT runs as radix-8 passes in registers with conflict-free shared-memory transposes
 // (8x8x8 for N = 2048, 8x8 for N = 256); other block sizes use a radix-2 Stockham loop.
-// Only D (M floats per channel) is kept; the right half of a block is never materialised: the
-// next packet reads it straight out of the previous packet's D buffer (ping-pong).
+// Only D (M floats per channel) is kept.  The left half of y reads D[M/2..M) only and the right half
+// D[0..M/2) only, so the next packet needs just the LOW half of its predecessor's D: shared memory
+// holds one high-half slot and two low-half slots (ping-pong) per channel, 1.5 M floats.
 #pragma once
 #include "k1_params.h"
 
@@ -28,6 +29,30 @@
 #endif
 
 #define K3_THREADS_PER_CH 64
+
+// D[i] of the current block lives in two places: i < h (= M/2) in the low-half slot, i >= h in the
+// high-half slot.  `hm` is the high slot minus h, so both take the plain index.
+struct K3D {
+  float* lo;
+  float* hm;
+  int h;
+};
+VPZ_DEV float* k3_dp(const K3D& d, int i) { return (i < d.h ? d.lo : d.hm) + i; }
+
+// barrier of one channel group (64 threads = 2 warps): the transposes of the two channels of a CTA
+// are independent, only the output loop needs the whole CTA
+#ifndef VPZ_EMU
+// (literal barrier ids: a register id makes ptxas reserve all 16 hardware barriers for the CTA)
+#define K3_GSYNC(g)                                         \
+  do {                                                      \
+    if ((g) == 0)                                           \
+      asm volatile("bar.sync 1, 64;" ::: "memory");         \
+    else                                                    \
+      asm volatile("bar.sync 2, 64;" ::: "memory");         \
+  } while (0)
+#else
+#define K3_GSYNC(g) __syncthreads()
+#endif
 
 typedef float2 cpx;
 VPZ_DEV cpx cmul(cpx a, cpx b) {
@@ -71,70 +96,97 @@ VPZ_DEV int k3_remap64(int tid64) {
   return w == 0 ? (l < 16 ? l : 32 + l) : 16 + l;
 }
 
-// transposes: plane stride 576 floats; conflict-free for both the writing and the reading pass
+// transposes: plane size 576 floats; both layouts are conflict-free for the writing and the reading
+// pass (idx2 found by exhaustive search over linear layouts: the reader of pass 3 is thread
+// t = k1 + 8 k2, so its reads B[t + 68 r] and its outputs p = t + 64 k3 are consecutive across lanes)
 VPZ_DEV int idx1(int k1, int r) { return 72 * k1 + r; }                   // r in [0,64)
-VPZ_DEV int idx2(int k1, int k2, int r2) { return 72 * k1 + 9 * r2 + k2; }
+VPZ_DEV int idx2(int k1, int k2, int r2) { return k1 + 8 * k2 + 68 * r2; }
 #define K3_PLANE 576
+// FAST path tables staged in shared memory once per work item (complex entries):
+//   TW[512]  pre/post twiddle of the long block, W1[7][64] = w512^(t k), W2[7][8] = w64^(r2 k)
+#define K3_TAB_TW 0
+#define K3_TAB_W1 512
+#define K3_TAB_W2 (512 + 448)
+#define K3_TAB_CPX (512 + 448 + 56)
+#define K3_TAB_SLOPE 2048    // float offset of the long window slope (1024 floats) behind the complex tables
+#define K3_TAB_FLOATS 3072
+// Both paths: the first K3_DESC_FLOATS words of shared memory hold the descriptors (4 words) and exec
+// masks (1 word) of up to K3_DESC_PKTS packets of the current work item, fetched with one parallel
+// load instead of one dependent global load per packet; the last word is the work-stealing slot.
+#define K3_DESC_PKTS 64
+#define K3_DESC_FLOATS 384
+#define K3_GRAB 4            // consecutive work items a CTA takes per atomic (same stream => same tables)
+#define K3_FAST_PER_CH (2 * K3_PLANE + 3 * 512 + 16)
 
-// N = 2048: H = 512 = 8*8*8, 64 threads.  X: M = 1024 floats in global.  Writes D[0..1024) (smem).
-VPZ_DEV void fft512_to_D(const float* X, float* A, float* B, float* D, const cpx* tw, const cpx* w512,
-                         int t, int lane) {
+// N = 2048: H = 512 = 8*8*8, 64 threads.  The thread's 8 float2 of the spectrum (X[2n], X[2n+1] for
+// n = t + 64 q) arrive in registers (prefetched one packet ahead).  Writes D[0..1024) (smem).
+// T: transpose scratch (2 planes), used for both transposes; tab: the shared-memory tables above.
+VPZ_DEV void k3_load_x(const float* X, int t, float2* xr) {
+#pragma unroll
+  for (int q = 0; q < 8; q++) xr[q] = VPZ_LDG(reinterpret_cast<const float2*>(X) + (t + 64 * q));
+}
+
+VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* tab, int t, int grp) {
   const int M = 1024;
+  const cpx* tw = tab + K3_TAB_TW;
   cpx v[8];
-  float other[8];
+  // X[2n+1] = X[M-1-2n'] of the mirrored element n' = 511-n, held by the mirrored lane
 #pragma unroll
   for (int q = 0; q < 8; q++) {
-    const float2 f = VPZ_LDG(reinterpret_cast<const float2*>(X) + (t + 64 * q));
-    v[q].x = f.x;       // X[2n]
-    other[q] = f.y;     // X[2n+1] = X[M-1-2n'] of the mirrored element n' = 511-n
+    v[q].x = xr[q].x;
+    v[q].y = __shfl_xor_sync(0xffffffffu, xr[7 - q].y, 31);
   }
 #pragma unroll
-  for (int q = 0; q < 8; q++) v[q].y = __shfl_xor_sync(0xffffffffu, other[7 - q], 31);
-#pragma unroll
-  for (int q = 0; q < 8; q++) v[q] = cmul(v[q], VPZ_LDG(tw + t + 64 * q));
+  for (int q = 0; q < 8; q++) v[q] = cmul(v[q], tw[t + 64 * q]);
   dft8(v);
 #pragma unroll
-  for (int k = 1; k < 8; k++) v[k] = cmul(v[k], VPZ_LDG(w512 + ((t * k) & 511)));
+  for (int k = 1; k < 8; k++) v[k] = cmul(v[k], tab[K3_TAB_W1 + (k - 1) * 64 + t]);
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    A[idx1(k, t)] = v[k].x;
-    A[K3_PLANE + idx1(k, t)] = v[k].y;
+    T[idx1(k, t)] = v[k].x;
+    T[K3_PLANE + idx1(k, t)] = v[k].y;
   }
-  __syncthreads();
+  K3_GSYNC(grp);
   const int k1 = t >> 3, r2 = t & 7;
 #pragma unroll
   for (int q = 0; q < 8; q++) {
-    v[q].x = A[idx1(k1, r2 + 8 * q)];
-    v[q].y = A[K3_PLANE + idx1(k1, r2 + 8 * q)];
+    v[q].x = T[idx1(k1, r2 + 8 * q)];
+    v[q].y = T[K3_PLANE + idx1(k1, r2 + 8 * q)];
   }
+  K3_GSYNC(grp);  // the second transpose reuses T
   dft8(v);
 #pragma unroll
-  for (int k = 1; k < 8; k++) v[k] = cmul(v[k], VPZ_LDG(w512 + ((r2 * k) << 3)));  // W_64^{r2 k} = W_512^{8 r2 k}
+  for (int k = 1; k < 8; k++) v[k] = cmul(v[k], tab[K3_TAB_W2 + (k - 1) * 8 + r2]);
 #pragma unroll
   for (int k = 0; k < 8; k++) {
-    B[idx2(k1, k, r2)] = v[k].x;
-    B[K3_PLANE + idx2(k1, k, r2)] = v[k].y;
+    T[idx2(k1, k, r2)] = v[k].x;
+    T[K3_PLANE + idx2(k1, k, r2)] = v[k].y;
   }
-  __syncthreads();
-  const int kk1 = t >> 3, kk2 = t & 7;  // this thread now owns (k1, k2)
+  K3_GSYNC(grp);
+  // pass 3: this thread owns (k1, k2) = (t & 7, t >> 3); idx2(k1, k2, r) = t + 68 r
 #pragma unroll
   for (int r = 0; r < 8; r++) {
-    v[r].x = B[idx2(kk1, kk2, r)];
-    v[r].y = B[K3_PLANE + idx2(kk1, kk2, r)];
+    v[r].x = T[t + 68 * r];
+    v[r].y = T[K3_PLANE + t + 68 * r];
   }
   dft8(v);
 #pragma unroll
   for (int k3 = 0; k3 < 8; k3++) {
-    int p = kk1 + 8 * kk2 + 64 * k3;
-    cpx c = cmul(v[k3], VPZ_LDG(tw + p));
-    D[2 * p] = c.x;
-    D[M - 1 - 2 * p] = -c.y;
+    int p = t + 64 * k3;
+    cpx c = cmul(v[k3], tw[p]);
+    // p < 256: D[2p] is in the low half and D[M-1-2p] in the high half; p >= 256: the other way round
+    if (k3 < 4) {
+      D.lo[2 * p] = c.x;
+      D.hm[M - 1 - 2 * p] = -c.y;
+    } else {
+      D.hm[2 * p] = c.x;
+      D.lo[M - 1 - 2 * p] = -c.y;
+    }
   }
-  (void)lane;
 }
 
 // N = 256: H = 64 = 8*8, threads t < 8 of the channel group work; M = 128.
-VPZ_DEV void fft64_to_D(const float* X, float* A, float* D, const cpx* tw, const cpx* w64, int t, bool active) {
+VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, const cpx* w64, int t, bool active) {
   const int M = 128;
   cpx v[8];
   if (active) {
@@ -166,8 +218,8 @@ VPZ_DEV void fft64_to_D(const float* X, float* A, float* D, const cpx* tw, const
     for (int k2 = 0; k2 < 8; k2++) {
       int p = t + 8 * k2;
       cpx c = cmul(v[k2], VPZ_LDG(tw + p));
-      D[2 * p] = c.x;
-      D[M - 1 - 2 * p] = -c.y;
+      *k3_dp(D, 2 * p) = c.x;
+      *k3_dp(D, M - 1 - 2 * p) = -c.y;
     }
   }
   __syncthreads();
@@ -175,7 +227,7 @@ VPZ_DEV void fft64_to_D(const float* X, float* A, float* D, const cpx* tw, const
 
 // Any power-of-two N in 64..8192: radix-2 Stockham autosort between two shared buffers of 2*H
 // floats (re plane, im plane), 64 threads.
-VPZ_DEV void fft_generic_to_D(const float* X, float* A, float* B, float* D, const cpx* tw, const cpx* roots,
+VPZ_DEV void fft_generic_to_D(const float* X, float* A, float* B, const K3D& D, const cpx* tw, const cpx* roots,
                               int log2H, int t) {
   const int H = 1 << log2H, M = 2 * H;
   for (int n = t; n < H; n += K3_THREADS_PER_CH) {
@@ -210,31 +262,200 @@ VPZ_DEV void fft_generic_to_D(const float* X, float* A, float* B, float* D, cons
   }
   for (int p = t; p < H; p += K3_THREADS_PER_CH) {
     cpx c = cmul(cpx{src[p], src[H + p]}, VPZ_LDG(tw + p));
-    D[2 * p] = c.x;
-    D[M - 1 - 2 * p] = -c.y;
+    *k3_dp(D, 2 * p) = c.x;
+    *k3_dp(D, M - 1 - 2 * p) = -c.y;
   }
   __syncthreads();
 }
 
 // y[i] of a block with M = N/2 from its D buffer
-VPZ_DEV float k3_y(const float* D, int M, int i) {
+VPZ_DEV float k3_y(const K3D& D, int M, int i) {
   int h = M >> 1;
-  if (i < h) return D[i + h];
-  if (i < M + h) return -D[M + h - 1 - i];
-  return -D[i - M - h];
+  if (i < h) return *k3_dp(D, i + h);
+  if (i < M + h) return -*k3_dp(D, M + h - 1 - i);
+  return -*k3_dp(D, i - M - h);
 }
 
-// Shared memory per channel (floats): A[2*PA] B[2*PA] D0[Mmax] D1[Mmax] where PA = plane size.
-// FAST: block sizes 256/2048.  Otherwise generic (PA = Hmax).
+// ---- window + overlap-add + clip + interleaved store ---------------------------------------------
+// y[] of a block is a piecewise mirrored read of its D buffer (k3_y).  The output range [0, count) of
+// a packet is cut at the breakpoints of the current block, of the previous block and at the end of
+// the overlap; inside one segment every sample uses the same (offset, direction, sign), so the inner
+// loop is two shared loads, two window loads, two multiplies and one add per channel -- the rounding
+// order of OverlapBuffers (StreamDecoder.cs:786-788): two rounded products, one rounded sum.
+struct K3Piece {
+  int off, dir;     // D index = off + dir * j
+  float sign;
+  bool low;         // the piece lies in the low half of D (i >= M), else in the high half
+};
+VPZ_DEV K3Piece k3_piece(int M, int start, int j) {  // piece of y[start + j]
+  const int h = M >> 1, i = start + j;
+  K3Piece p;
+  if (i < h) { p.off = start + h; p.dir = 1; p.sign = 1.f; }
+  else if (i < M + h) { p.off = M + h - 1 - start; p.dir = -1; p.sign = -1.f; }
+  else { p.off = start - M - h; p.dir = 1; p.sign = -1.f; }
+  p.low = i >= M;
+  return p;
+}
+VPZ_DEV int k3_next_break(int M, int start, int a, int b) {  // first breakpoint of y[start + j] in (a, b)
+  const int h = M >> 1;
+  int x = h - start;
+  if (x > a && x < b) b = x;
+  x = M - start;
+  if (x > a && x < b) b = x;
+  x = M + h - start;
+  if (x > a && x < b) b = x;
+  return b;
+}
+
+template <int NCUR, bool CLIP>
+VPZ_DEV bool k3_emit(const float* Dc_hm, const float* Dc_lo, const float* Dp_lo, int per_ch, int M, int prevM, int ls,
+                     int count, int prev_rs, int L, const float* w, float* outp, int C, int tid, int nthreads) {
+  bool clipped = false;
+  const bool pair_ok = NCUR == 2 && C == 2 && (reinterpret_cast<uintptr_t>(outp) & 7u) == 0;
+  int a = 0;
+  while (a < count) {
+    int b = k3_next_break(M, ls, a, count);
+    const bool ovl = a < L;
+    if (ovl) {
+      if (L < b) b = L;
+      b = k3_next_break(prevM, prev_rs, a, b);
+    }
+    const K3Piece pc = k3_piece(M, ls, a);
+    const K3Piece pp = k3_piece(prevM, prev_rs, a);
+    const float* Dc0 = pc.low ? Dc_lo : Dc_hm;
+    const float* Dp0 = Dp_lo;  // the overlap lies in the right half of the previous block (host-checked)
+    // two samples per thread and step: the loads of both are in flight together
+    for (int j = a + tid; j < b; j += 2 * nthreads) {
+      const int j2 = j + nthreads;
+      const bool two = j2 < b;
+      float v[NCUR], u[NCUR];
+      float w0 = 0.f, w1 = 0.f, x0 = 0.f, x1 = 0.f;
+      if (ovl) {
+        w0 = VPZ_LDG(w + j);
+        w1 = VPZ_LDG(w + (L - 1 - j));
+        if (two) {
+          x0 = VPZ_LDG(w + j2);
+          x1 = VPZ_LDG(w + (L - 1 - j2));
+        }
+      }
+#pragma unroll
+      for (int cg = 0; cg < NCUR; cg++) {
+        float x = pc.sign * Dc0[cg * per_ch + pc.off + pc.dir * j];
+        float y = two ? pc.sign * Dc0[cg * per_ch + pc.off + pc.dir * j2] : 0.f;
+        if (ovl) {
+          float pv = pp.sign * Dp0[cg * per_ch + pp.off + pp.dir * j];
+          float qv = two ? pp.sign * Dp0[cg * per_ch + pp.off + pp.dir * j2] : 0.f;
+          x = __fadd_rn(__fmul_rn(x, w0), __fmul_rn(pv, w1));
+          y = __fadd_rn(__fmul_rn(y, x0), __fmul_rn(qv, x1));
+        }
+        if (CLIP) {  // Utils.ClipValue (Utils.cs:44-58)
+          const bool hi = x > 0.99999994f, lo = x < -0.99999994f;
+          x = hi ? 0.99999994f : (lo ? -0.99999994f : x);
+          const bool hi2 = y > 0.99999994f, lo2 = y < -0.99999994f;
+          y = hi2 ? 0.99999994f : (lo2 ? -0.99999994f : y);
+          clipped |= hi | lo | hi2 | lo2;
+        }
+        v[cg] = x;
+        u[cg] = y;
+      }
+      float* o = outp + (size_t)j * C;
+      float* o2 = outp + (size_t)j2 * C;
+      if (NCUR == 2) {
+        if (pair_ok) {
+          *reinterpret_cast<float2*>(o) = float2{v[0], v[NCUR - 1]};
+          if (two) *reinterpret_cast<float2*>(o2) = float2{u[0], u[NCUR - 1]};
+        } else {
+          o[0] = v[0];
+          o[1] = v[NCUR - 1];
+          if (two) {
+            o2[0] = u[0];
+            o2[1] = u[NCUR - 1];
+          }
+        }
+      } else {
+        o[0] = v[0];
+        if (two) o2[0] = u[0];
+      }
+    }
+    a = b;
+  }
+  return clipped;
+}
+
+// The common case in full: long block after long block, nothing trimmed (ls = 0, count = L = 1024,
+// previous RightStart = 1024).  Thread tid writes samples j = tid + NT r; in the first half the current block
+// reads +D[j + 512] and the previous one -Dp[511 - j], in the second they read -D[1535 - j] and
+// -Dp[j - 512]; every index is a compile-time offset from a per-thread base and the window comes
+// from shared memory.  Same rounding order as k3_emit.
+template <int NCUR, bool CLIP>
+VPZ_DEV bool k3_emit_long_long(const float* Dc0 /* high slot - 512 */, const float* Dp0 /* previous low slot */,
+                               const float* w, float* outp, int C, int tid) {
+  constexpr int NT = 64 * NCUR;   // threads of the CTA
+  constexpr int R = 512 / NT;     // samples per thread and half
+  bool clipped = false;
+  const bool pair_ok = NCUR == 2 && C == 2 && (reinterpret_cast<uintptr_t>(outp) & 7u) == 0;
+#pragma unroll
+  for (int half = 0; half < 2; half++) {
+    float v[R][NCUR];
+#pragma unroll
+    for (int r4 = 0; r4 < R; r4++) {
+      const int j = tid + NT * (r4 + R * half);
+      const float w0 = w[j], w1 = w[1023 - j];
+#pragma unroll
+      for (int cg = 0; cg < NCUR; cg++) {
+        const float* Dc = Dc0 + cg * K3_FAST_PER_CH;
+        const float* Dp = Dp0 + cg * K3_FAST_PER_CH;
+        float a, b;
+        if (half == 0) {
+          a = __fmul_rn(Dc[j + 512], w0);
+          b = __fmul_rn(-Dp[511 - j], w1);
+        } else {
+          a = __fmul_rn(-Dc[1535 - j], w0);
+          b = __fmul_rn(-Dp[j - 512], w1);
+        }
+        float x = __fadd_rn(a, b);
+        if (CLIP) {  // Utils.ClipValue (Utils.cs:44-58)
+          const bool hi = x > 0.99999994f, lo = x < -0.99999994f;
+          x = hi ? 0.99999994f : (lo ? -0.99999994f : x);
+          clipped |= hi | lo;
+        }
+        v[r4][cg] = x;
+      }
+    }
+#pragma unroll
+    for (int r4 = 0; r4 < R; r4++) {
+      const int j = tid + NT * (r4 + R * half);
+      float* o = outp + (size_t)j * C;
+      if (NCUR == 2) {
+        if (pair_ok) {
+          *reinterpret_cast<float2*>(o) = float2{v[r4][0], v[r4][NCUR - 1]};
+        } else {
+          o[0] = v[r4][0];
+          o[1] = v[r4][NCUR - 1];
+        }
+      } else {
+        o[0] = v[r4][0];
+      }
+    }
+  }
+  return clipped;
+}
+
+// Shared memory (floats): [FAST: K3_TAB_FLOATS of tables] then per channel the transpose scratch
+// (FAST: T[2*576], generic: A[2*Hmax] B[2*Hmax]) and the D slots Hi[Mmax/2] Lo0[Mmax/2] Lo1[Mmax/2] (+16 to
+// stagger channel bases across banks).  FAST: block sizes 256/2048.
 template <bool FAST>
-VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& it, float* smem, int NCB) {
+VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_raw, int NCB, bool stage_tables) {
+  const VpzOlaItem it = item;  // the item lives in global memory: read it once
   const uint32_t* blob = P.setups[it.setup_slot];
   const VpzSetupHdr* Hd = reinterpret_cast<const VpzSetupHdr*>(blob);
   const int C = Hd->channels;
   const int lg0 = Hd->log2_size0, lg1 = Hd->log2_size1;
   const int Mmax = 1 << (lg1 - 1);
   const int PA = FAST ? K3_PLANE : (1 << (lg1 - 2));
-  const int per_ch = 4 * PA + 2 * Mmax + 16;  // +16: stagger channel bases across banks
+  const int SCR = FAST ? 2 * K3_PLANE : 4 * PA;      // transpose scratch per channel
+  const int HS = Mmax >> 1;                          // one half-slot
+  const int per_ch = FAST ? K3_FAST_PER_CH : SCR + 3 * HS + 16;
   const int tid = threadIdx.x;
   const int cgrp = tid / K3_THREADS_PER_CH;          // channel slot inside the CTA
   const int t64 = tid % K3_THREADS_PER_CH;
@@ -242,6 +463,28 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& it, float* smem, i
   const float* slope0 = reinterpret_cast<const float*>(blob + Hd->slope_off[0]);
   const float* slope1 = reinterpret_cast<const float*>(blob + Hd->slope_off[1]);
   const int nthreads = NCB * K3_THREADS_PER_CH;
+  VpzPktOla* spk = reinterpret_cast<VpzPktOla*>(smem_raw);                      // [K3_DESC_PKTS] descriptors
+  uint32_t* smask = reinterpret_cast<uint32_t*>(smem_raw) + 4 * K3_DESC_PKTS;    // [K3_DESC_PKTS] exec masks
+  float* smem_all = smem_raw + K3_DESC_FLOATS;
+  float* smem = smem_all + (FAST ? K3_TAB_FLOATS : 0);
+  const cpx* tab = reinterpret_cast<const cpx*>(smem_all);
+  if (FAST && stage_tables) {
+    // stage the long-block tables (all reads below hit shared memory instead of L1/L2); skipped when
+    // the previous item of this CTA used the same setup
+    cpx* tb = reinterpret_cast<cpx*>(smem_all);
+    const cpx* tw1 = reinterpret_cast<const cpx*>(blob + Hd->tw_off[1]);
+    const cpx* w512 = reinterpret_cast<const cpx*>(blob + Hd->fft_off[1]);
+    for (int i = tid; i < 512; i += nthreads) tb[K3_TAB_TW + i] = VPZ_LDG(tw1 + i);
+    for (int i = tid; i < 448; i += nthreads) {
+      int k = (i >> 6) + 1, tt = i & 63;
+      tb[K3_TAB_W1 + i] = VPZ_LDG(w512 + ((tt * k) & 511));
+    }
+    for (int i = tid; i < 56; i += nthreads) {
+      int k = (i >> 3) + 1, r = i & 7;
+      tb[K3_TAB_W2 + i] = VPZ_LDG(w512 + ((r * k) << 3));
+    }
+    for (int i = tid; i < 1024; i += nthreads) smem_all[K3_TAB_SLOPE + i] = VPZ_LDG(slope1 + i);
+  }
 
   for (int c0 = 0; c0 < C; c0 += NCB) {
     const int ncur = (C - c0) < NCB ? (C - c0) : NCB;  // channels handled in this sweep
@@ -249,22 +492,35 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& it, float* smem, i
     const bool ch_ok = cgrp < ncur;
     float* base = smem + cgrp * per_ch;
     float* A = base;
-    float* B = base + 2 * PA;
-    float* Dbuf[2] = {base + 4 * PA, base + 4 * PA + Mmax};
+    float* B = base + 2 * PA;  // generic path only
 
     int prevM = 0, prev_rs = 0, prev_re = 0;   // previous packet: M, RightStart, RightEnd
     bool have_prev = false;
-    uint32_t zero_bits = 0;                    // bit (cg*2 + parity): that D buffer is all zero
     int parity = 0;
     const int first = (int)it.first_pkt - (it.has_pre ? 1 : 0);
     const int total = (int)it.n_pkts + (it.has_pre ? 1 : 0);
-    for (int pi = 0; pi < total; pi++, parity ^= 1) {
+    float2 xr[8];
+    bool xr_valid = false;
+    for (int pb = 0; pb < total; pb += K3_DESC_PKTS) {
+    const int nb = (total - pb) < K3_DESC_PKTS ? (total - pb) : K3_DESC_PKTS;
+    // descriptors + exec masks of the next nb packets: one parallel fetch
+    __syncthreads();
+    if (tid < nb) {
+      spk[tid] = P.pkts[first + pb + tid];
+      smask[tid] = P.res ? P.res[first + pb + tid].exec_mask : 0xffu;
+    }
+    __syncthreads();
+    for (int pw = 0; pw < nb; pw++, parity ^= 1) {
+      const int pi = pb + pw;
       const uint32_t gp = (uint32_t)(first + pi);
-      const VpzPktOla pk = P.pkts[gp];
+      const VpzPktOla pk = spk[pw];
+      const uint32_t mask = smask[pw];
+      const bool has_next = pw + 1 < nb;
+      const VpzPktOla pk_next = spk[has_next ? pw + 1 : pw];
+      const uint32_t mask_next = smask[has_next ? pw + 1 : pw];
       const bool is_long = pk.flags & VPZ_OLA_LONG;
       const int lgN = is_long ? lg1 : lg0;
       const int M = 1 << (lgN - 1);
-      const uint32_t mask = P.res ? P.res[gp].exec_mask : 0xffu;
       const bool emit = !(pi == 0 && it.has_pre) && !(pk.flags & VPZ_OLA_NOOUT) && have_prev;
 
       // ---- transform every channel of this sweep into its D buffer -------------------------
@@ -272,21 +528,35 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& it, float* smem, i
       const float* X = P.spec + pk.spec_off + (size_t)ch * M;
       const cpx* tw = reinterpret_cast<const cpx*>(blob + Hd->tw_off[is_long ? 1 : 0]);
       const cpx* roots = reinterpret_cast<const cpx*>(blob + Hd->fft_off[is_long ? 1 : 0]);
-      float* D = Dbuf[parity];
+      const int h = M >> 1;
+      K3D D;
+      D.h = h;
+      D.hm = base + SCR - h;
+      D.lo = base + SCR + HS + parity * HS;
+      // a channel without floor energy outputs zeros (Mapping.cs:185-194) but still takes part in the
+      // overlap-add: its D buffer is cleared instead of transformed
+      if (ch_ok && !exec)
+        for (int i = t64; i < M; i += K3_THREADS_PER_CH) *k3_dp(D, i) = 0.f;
       if (FAST) {
         if (is_long) {
           if (exec) {
-            fft512_to_D(X, A, B, D, tw, roots, t, tid & 31);
-          } else {
+            if (!xr_valid) k3_load_x(X, t, xr);
+            fft512_to_D(xr, A, D, tab, t, cgrp);
+          }
+#ifdef VPZ_EMU
+          else {  // the emulator's group barrier is the CTA barrier: keep the counts equal
+            __syncthreads();
             __syncthreads();
             __syncthreads();
           }
+#endif
           __syncthreads();
+          xr_valid = false;
         } else {
           fft64_to_D(exec ? X : P.spec, A, D, tw, roots, t64, exec && t64 < 8);
         }
       } else {
-        // every thread must take the barriers inside; silent channels transform a dummy but skip stores
+        // every thread must take the barriers inside
         if (exec) {
           fft_generic_to_D(X, A, B, D, tw, roots, lgN - 2, t64);
         } else {
@@ -297,109 +567,73 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& it, float* smem, i
 
       if (P.dbg_imdct && ch_ok) {
         float* dy = P.dbg_imdct + 2 * (size_t)pk.spec_off + (size_t)ch * 2 * M;
-        for (int i = t64; i < 2 * M; i += K3_THREADS_PER_CH) dy[i] = exec ? k3_y(D, M, i) : 0.f;
+        for (int i = t64; i < 2 * M; i += K3_THREADS_PER_CH) dy[i] = k3_y(D, M, i);
       }
 
-      // ---- window + overlap-add + clip + interleaved store ---------------------------------------
-      // Every warp takes 32 consecutive samples per step.  y[] is a piecewise mirrored read of D
-      // (k3_y) whose breakpoints, like LeftStart / RightStart of untrimmed packets, are multiples
-      // of 64, so one warp step never straddles a breakpoint: the piece (base, direction, sign) is
-      // picked once per step with warp-uniform branches and each lane does two shared loads, two
-      // window loads, two multiplies and one add per channel -- same rounding order as
-      // OverlapBuffers (StreamDecoder.cs:786-788): two rounded products, one rounded sum.
+      // the spectrum of the next long block is requested now and lands during the output loop
+      if (FAST && has_next && (pk_next.flags & VPZ_OLA_LONG) && ch_ok && ((mask_next >> ch) & 1u)) {
+        k3_load_x(P.spec + pk_next.spec_off + (size_t)ch * Mmax, t, xr);
+        xr_valid = true;
+      }
       if (emit) {
-        const int ls = pk.left_start, rs = pk.right_start;
-        const int count = rs - ls;
+        const int ls = pk.left_start;
+        const int count = (int)pk.right_start - ls;
         const int L = prev_re - prev_rs;             // StreamDecoder.cs:654
         const float* w = (pk.flags & VPZ_OLA_LEFT1) ? slope1 : slope0;
         float* outp = P.pcm + it.out_base + (size_t)pk.out_off * C + c0;
-        const int lane = tid & 31, wid = tid >> 5, nw = nthreads >> 5;
-        const int h = M >> 1, ph = prevM >> 1;
-        const bool pair_ok = (reinterpret_cast<uintptr_t>(outp) & 7u) == 0;  // runs are packed back to back
-        const float* Dbase = smem + 4 * PA;
-        uint32_t clipped_at = 0xffffffffu;
-        uint32_t cur_on = 0, prev_on = 0;
-        for (int cg = 0; cg < ncur; cg++) {
-          if ((mask >> (c0 + cg)) & 1u) cur_on |= 1u << cg;
-          if (!((zero_bits >> (cg * 2 + (parity ^ 1))) & 1u)) prev_on |= 1u << cg;
+        const float* Dc_hm = smem + SCR - h;                       // channel slot 0; + cg * per_ch for the others
+        const float* Dc_lo = smem + SCR + HS + parity * HS;
+        const float* Dp_lo = smem + SCR + HS + (parity ^ 1) * HS;
+        bool clipped;
+        const bool long_long = FAST && nthreads == 64 * ncur && M == 1024 && prevM == 1024 && ls == 0 && count == 1024 &&
+                               L == 1024 && prev_rs == 1024 && (pk.flags & VPZ_OLA_LEFT1);
+        if (long_long) {
+          const float* ws = smem_all + K3_TAB_SLOPE;
+          if (ncur == 2)
+            clipped = P.clip ? k3_emit_long_long<2, true>(Dc_hm, Dp_lo, ws, outp, C, tid)
+                             : k3_emit_long_long<2, false>(Dc_hm, Dp_lo, ws, outp, C, tid);
+          else
+            clipped = P.clip ? k3_emit_long_long<1, true>(Dc_hm, Dp_lo, ws, outp, C, tid)
+                             : k3_emit_long_long<1, false>(Dc_hm, Dp_lo, ws, outp, C, tid);
+        } else if (ncur == 2) {
+          clipped = P.clip ? k3_emit<2, true>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads)
+                           : k3_emit<2, false>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads);
+        } else {
+          clipped = P.clip ? k3_emit<1, true>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads)
+                           : k3_emit<1, false>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads);
         }
-        for (int j0 = wid * 32; j0 < count; j0 += nw * 32) {
-          const int j = j0 + lane;
-          // current block, index i = ls + j
-          const int i0 = ls + j0;
-          int cidx;
-          float csign;
-          if (i0 < h) { cidx = i0 + h + lane; csign = 1.f; }
-          else if (i0 < M + h) { cidx = M + h - 1 - i0 - lane; csign = -1.f; }
-          else { cidx = i0 - M - h + lane; csign = -1.f; }
-          // previous block, index prev_rs + j (only inside the overlap)
-          const int p0 = prev_rs + j0;
-          int pidx;
-          float psign;
-          if (p0 < ph) { pidx = p0 + ph + lane; psign = 1.f; }
-          else if (p0 < prevM + ph) { pidx = prevM + ph - 1 - p0 - lane; psign = -1.f; }
-          else { pidx = p0 - prevM - ph + lane; psign = -1.f; }
-          const bool in_ovl = j < L;
-          float w0 = 1.f, w1 = 0.f;
-          if (in_ovl) {
-            w0 = VPZ_LDG(w + j);
-            w1 = VPZ_LDG(w + (L - 1 - j));
-          }
-          if (j < count) {
-            // breakpoints are multiples of 64 except after an end-of-stream trim, where the tail
-            // of the last step may run past a piece; clamp keeps the (discarded) reads in bounds
-            cidx = cidx < 0 ? 0 : (cidx >= M ? M - 1 : cidx);
-            pidx = pidx < 0 ? 0 : (pidx >= prevM ? prevM - 1 : pidx);
-            float v[2];
-#pragma unroll
-            for (int cg = 0; cg < 2; cg++) {
-              if (cg < ncur) {
-                const float* Dc = Dbase + cg * per_ch + parity * Mmax;
-                const float* Dp = Dbase + cg * per_ch + (parity ^ 1) * Mmax;
-                float x = ((cur_on >> cg) & 1u) ? csign * Dc[cidx] : 0.f;
-                if (in_ovl) {
-                  float pv = ((prev_on >> cg) & 1u) ? psign * Dp[pidx] : 0.f;
-                  x = __fadd_rn(__fmul_rn(x, w0), __fmul_rn(pv, w1));
-                }
-                if (P.clip) {  // Utils.ClipValue (Utils.cs:44-58)
-                  if (x > 0.99999994f) {
-                    x = 0.99999994f;
-                    clipped_at = clipped_at < (uint32_t)j ? clipped_at : (uint32_t)j;
-                  } else if (x < -0.99999994f) {
-                    x = -0.99999994f;
-                    clipped_at = clipped_at < (uint32_t)j ? clipped_at : (uint32_t)j;
-                  }
-                }
-                v[cg] = x;
-              }
-            }
-            float* o = outp + (size_t)j * C;
-            if (C == 2 && pair_ok) {
-              *reinterpret_cast<float2*>(o) = float2{v[0], v[1]};
-            } else {
-              o[0] = v[0];
-              if (ncur > 1) o[1] = v[1];
-            }
-          }
-        }
-        if (P.clip_first && clipped_at != 0xffffffffu) atomicMin(P.clip_first + gp, clipped_at);
-      }
-      // remember this packet as "previous"; its D buffer stays untouched until the packet after next
-      for (int cg = 0; cg < ncur; cg++) {
-        uint32_t bit = 1u << (cg * 2 + parity);
-        if ((mask >> (c0 + cg)) & 1u) zero_bits &= ~bit; else zero_bits |= bit;
+        // per packet: 0 when any sample was clamped (HasClipped), else stays 0xffffffff
+        if (P.clip_first && clipped) atomicMin(P.clip_first + gp, 0u);
       }
       prevM = M;
       prev_rs = pk.right_start;
       prev_re = pk.right_end;
       have_prev = true;
-      // The output loop above reads Dbuf[parity^1]; the next packet writes Dbuf[parity^1] only after
-      // its own transform barriers, and A/B are rewritten only after a barrier too, except the very
-      // first stores of the next transform (A) which race with nothing read here.  One barrier keeps
-      // the D ping-pong safe when the next transform is barrier-free up to its D stores (N=256 path
-      // writes A before its first barrier, D after it).
+      // The output loop above reads the previous D buffer; the next packet overwrites it only after
+      // its own transform barriers, except on the N = 256 path and for the zero fill of a silent
+      // channel, which store before their first barrier: one barrier here keeps the ping-pong safe.
       __syncthreads();
     }
+    }
     __syncthreads();
+  }
+}
+
+// CTA main loop: work items are taken K3_GRAB at a time from a global counter.
+template <bool FAST>
+VPZ_DEV void k3_cta_loop(const K3Params& P, float* smem_raw, int ncb) {
+  uint32_t* s_next = reinterpret_cast<uint32_t*>(smem_raw) + (K3_DESC_FLOATS - 1);
+  const uint32_t* prev_blob = nullptr;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) *s_next = atomicAdd(P.counter, (uint32_t)K3_GRAB);
+    __syncthreads();
+    const uint32_t first = *s_next;
+    if (first >= P.n_items) break;
+    for (uint32_t k = 0; k < K3_GRAB && first + k < P.n_items; k++) {
+      const uint32_t* blob = P.setups[P.items[first + k].setup_slot];
+      k3_run_item<FAST>(P, P.items[first + k], smem_raw, ncb, blob != prev_blob);
+      prev_blob = blob;
+    }
   }
 }

@@ -115,7 +115,7 @@ struct VpzPktRes {
 };
 
 // K3 per-packet descriptor (host built from Mode.GetPacketInfo, Mode.cs:30-66)
-struct VpzPktOla {
+struct alignas(16) VpzPktOla {
   uint32_t spec_off;        // as VpzPktIn
   uint32_t out_off;         // sample offset (per channel) inside the stream's output region
   uint16_t left_start, right_start;   // right_start already EOS-trimmed (StreamDecoder.cs:658-666)
