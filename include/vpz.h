@@ -137,8 +137,8 @@ int64_t vpz_batch_total_bytes(const vpz_batch* b);
 
 /* Uploads the queued packets (host -> device) and builds the device work lists. */
 int vpz_batch_upload(vpz_batch* b);
-/* Launches entropy decode + floor/coupling (K1) and IMDCT + window + overlap-add + store (K3) on
- * the context's stream.  clip != 0 clamps to +-0.99999994f like Utils.ClipValue (Utils.cs:44-58).
+/* Launches symbol decode (K1a), spectrum build (K1b: VQ accumulate, coupling, floor) and IMDCT +
+ * window + overlap-add + store (K3) on the context's stream.  clip != 0 clamps to +-0.99999994f like Utils.ClipValue (Utils.cs:44-58).
  * Asynchronous; vpz_batch_sync waits.  May be called repeatedly on the same uploaded batch. */
 int vpz_batch_decode(vpz_batch* b, int clip);
 int vpz_batch_sync(vpz_batch* b);
@@ -155,8 +155,9 @@ int vpz_batch_read_all(vpz_batch* b, float* dst);
 int64_t vpz_batch_run_offset(const vpz_batch* b, int run);
 const float* vpz_batch_device_pcm(const vpz_batch* b);
 
-/* Device time of the last vpz_batch_decode in milliseconds: which = 0 total, 1 entropy/floor (K1),
- * 3 IMDCT/OLA (K3); number of kernel launches in `launches` (may be NULL). */
+/* Device time of the last vpz_batch_decode in milliseconds: which = 0 total, 1 entropy stage (K1a +
+ * K1b), 11 symbol decode (K1a), 12 spectrum build (K1b), 3 IMDCT/OLA (K3); number of kernel launches
+ * in `launches` (may be NULL). */
 float vpz_batch_last_ms(vpz_batch* b, int which, int* launches);
 
 /* Bytes this process has copied so far: which = 0 host->device, 1 device->host. */

@@ -85,6 +85,8 @@ template <typename T>
 inline T __shfl_sync(unsigned, T v, int src) { return emu_shfl_idx(v, src); }
 template <typename T>
 inline T __shfl_xor_sync(unsigned, T v, int x) { return emu_shfl_idx(v, emu::t_lane ^ x); }
+template <typename T>
+inline T __shfl_up_sync(unsigned, T v, int d) { return emu_shfl_idx(v, emu::t_lane >= d ? emu::t_lane - d : emu::t_lane); }
 
 inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
   sh &= 31;

@@ -7,7 +7,7 @@
 
 #include "../../include/vpz.h"
 #include "../../vorbispizza_b200/csrc/devapi.h"
-#include "../../vorbispizza_b200/csrc/k1_entropy.cuh"
+#include "../../vorbispizza_b200/csrc/k1_symbols.cuh"
 #include "../../vorbispizza_b200/csrc/k3_imdct.cuh"
 
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
@@ -90,20 +90,40 @@ int fill(void* d, int v, size_t n, Stream*, std::string&) {
   return VPZ_OK;
 }
 
-int launch_k1(const K1Params& p, bool debug, int blocks, int warps, Stream*, std::string&) {
+int launch_k1a(const K1Params& p, bool debug, int blocks, Stream*, std::string&) {
   if (p.n_pkts == 0) return VPZ_OK;
-  *p.counter = 0;
+  memset(p.counter, 0, 16);
   (void)blocks;  // work stealing: one emulated block drains the whole queue
+  emu::launch(1, 128, 0, [&] {
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(p.counter, 32u);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= p.n_pkts) break;
+      const uint32_t i = base + lane;
+      if (i < p.n_pkts) {
+        if (debug) k1a_decode_packet<true>(p, p.order ? p.order[i] : i); else k1a_decode_packet<false>(p, p.order ? p.order[i] : i);
+      }
+      __syncwarp();
+    }
+  });
+  return VPZ_OK;
+}
+
+int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream*, std::string&) {
+  if (p.n_pkts == 0) return VPZ_OK;
+  (void)blocks;
   emu::launch(1, (unsigned)warps * 32, (size_t)warps * p.smem_words_per_warp * 4, [&] {
     uint32_t* smem = (uint32_t*)emu::t_block->smem;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t* my = smem + (size_t)warp * p.smem_words_per_warp;
     for (;;) {
       uint32_t idx = 0;
-      if (lane == 0) idx = atomicAdd(p.counter, 1u);
+      if (lane == 0) idx = atomicAdd(p.counter + 2, 1u);
       idx = __shfl_sync(0xffffffffu, idx, 0);
       if (idx >= p.n_pkts) break;
-      if (debug) k1_decode_packet<true>(p, idx, my, lane); else k1_decode_packet<false>(p, idx, my, lane);
+      if (debug) k1b_build_packet<true>(p, idx, my, lane); else k1b_build_packet<false>(p, idx, my, lane);
       __syncwarp();
     }
   });

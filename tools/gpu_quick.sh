@@ -12,8 +12,8 @@ echo "== bench"; VPZ_TRACE=1 timeout 600 python bench.py --steps 5 --warmup 3 --
 import json
 try:
     d = json.load(open("$OUT/bench_$TAG.json"))
-    print("value %.3f G/s  ms/step %.2f | K1 %.2f ms frac %.4f | K3 %.2f ms %.0f GB/s frac %.3f | e2e %.3f G/s %.1f ms" % (
-        d["value"]/1e9, d["ms_per_step"], d["roofline_k1"]["ms_per_launch"], d["roofline_k1"]["frac"],
+    print("value %.3f G/s  ms/step %.2f | K1a %.2f ms | K1b %.2f ms frac %.3f | K3 %.2f ms %.0f GB/s frac %.3f | e2e %.3f G/s %.1f ms" % (
+        d["value"]/1e9, d["ms_per_step"], d["roofline_k1a"]["ms_per_launch"], d["roofline_k1b"]["ms_per_launch"], d["roofline_k1b"]["frac"],
         d["roofline_k3"]["ms_per_launch"], d["roofline_k3"]["achieved"], d["roofline_k3"]["frac"],
         d.get("e2e",{}).get("value",0)/1e9, d.get("e2e",{}).get("ms_per_step",0)))
 except Exception as e:

@@ -219,10 +219,14 @@ class Batch:
         return dst
 
     def last_ms(self):
-        """(total, entropy/floor, imdct/ola) device milliseconds and kernel launches of the last decode."""
+        """(total, entropy stage, imdct/ola) device milliseconds and kernel launches of the last decode."""
         ln = C.c_int(0)
         tot = self.lib.vpz_batch_last_ms(self._h, 0, C.byref(ln))
         return tot, self.lib.vpz_batch_last_ms(self._h, 1, None), self.lib.vpz_batch_last_ms(self._h, 3, None), ln.value
+
+    def last_ms_k1(self):
+        """(symbol decode K1a, spectrum build K1b) device milliseconds of the last decode."""
+        return self.lib.vpz_batch_last_ms(self._h, 11, None), self.lib.vpz_batch_last_ms(self._h, 12, None)
 
     def device_pcm(self):
         return self.lib.vpz_batch_device_pcm(self._h)

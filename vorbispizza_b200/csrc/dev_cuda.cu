@@ -7,21 +7,35 @@
 
 #include "../../include/vpz.h"
 #include "devapi.h"
-#include "k1_entropy.cuh"
+#include "k1_symbols.cuh"
 #include "k3_imdct.cuh"
 
 // ---- kernels ---------------------------------------------------------------------------------
 template <bool DEBUG>
-__global__ void __launch_bounds__(256) vpz_k1_entropy(K1Params P) {
+__global__ void __launch_bounds__(128) vpz_k1a_symbols(K1Params P) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(P.counter, 32u);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= P.n_pkts) break;
+    const uint32_t i = base + lane;
+    if (i < P.n_pkts) k1a_decode_packet<DEBUG>(P, P.order ? P.order[i] : i);
+    __syncwarp();
+  }
+}
+
+template <bool DEBUG>
+__global__ void __launch_bounds__(256) vpz_k1b_spectrum(K1Params P) {
   extern __shared__ uint32_t k1_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint32_t* my = k1_smem + (size_t)warp * P.smem_words_per_warp;
   for (;;) {
     uint32_t idx = 0;
-    if (lane == 0) idx = atomicAdd(P.counter, 1u);
+    if (lane == 0) idx = atomicAdd(P.counter + 2, 1u);
     idx = __shfl_sync(0xffffffffu, idx, 0);
     if (idx >= P.n_pkts) break;
-    k1_decode_packet<DEBUG>(P, idx, my, lane);
+    k1b_build_packet<DEBUG>(P, idx, my, lane);
     __syncwarp();
   }
 }
@@ -84,8 +98,8 @@ int init(int device, std::string& err) {
   }
   g_sm_count = prop.multiProcessorCount;
   g_max_smem = prop.sharedMemPerBlockOptin;
-  cudaFuncSetAttribute(vpz_k1_entropy<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
-  cudaFuncSetAttribute(vpz_k1_entropy<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  cudaFuncSetAttribute(vpz_k1b_spectrum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  cudaFuncSetAttribute(vpz_k1b_spectrum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
   cudaFuncSetAttribute(vpz_k3_imdct_ola<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
   cudaFuncSetAttribute(vpz_k3_imdct_ola<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
   e = cudaGetLastError();
@@ -193,21 +207,31 @@ int fill(void* dst, int byte_value, size_t bytes, Stream* s, std::string& err) {
   return e == cudaSuccess ? VPZ_OK : fail(e, "cudaMemsetAsync", err);
 }
 
-int launch_k1(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err) {
+int launch_k1a(const K1Params& p, bool debug, int blocks, Stream* s, std::string& err) {
+  if (p.n_pkts == 0) return VPZ_OK;
+  cudaError_t e = cudaMemsetAsync(p.counter, 0, 16, s->s);
+  if (e != cudaSuccess) return fail(e, "cudaMemsetAsync(counter)", err);
+  if (debug)
+    vpz_k1a_symbols<true><<<blocks, 128, 0, s->s>>>(p);
+  else
+    vpz_k1a_symbols<false><<<blocks, 128, 0, s->s>>>(p);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k1a_symbols", err);
+}
+
+int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err) {
   if (p.n_pkts == 0) return VPZ_OK;
   size_t smem = (size_t)warps * p.smem_words_per_warp * 4;
   if (smem > g_max_smem) {
-    err = "K1 shared memory request exceeds the device limit";
+    err = "K1b shared memory request exceeds the device limit";
     return VPZ_E_UNSUPPORTED;
   }
-  cudaError_t e = cudaMemsetAsync(p.counter, 0, 4, s->s);
-  if (e != cudaSuccess) return fail(e, "cudaMemsetAsync(counter)", err);
   if (debug)
-    vpz_k1_entropy<true><<<blocks, warps * 32, smem, s->s>>>(p);
+    vpz_k1b_spectrum<true><<<blocks, warps * 32, smem, s->s>>>(p);
   else
-    vpz_k1_entropy<false><<<blocks, warps * 32, smem, s->s>>>(p);
-  e = cudaGetLastError();
-  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k1_entropy", err);
+    vpz_k1b_spectrum<false><<<blocks, warps * 32, smem, s->s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k1b_spectrum", err);
 }
 
 int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream* s, std::string& err) {
@@ -217,7 +241,7 @@ int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream* 
     return VPZ_E_UNSUPPORTED;
   }
   int threads = ncb * K3_THREADS_PER_CH;
-  cudaError_t e0 = cudaMemsetAsync(p.counter, 0, 4, s->s);
+  cudaError_t e0 = cudaMemsetAsync(p.counter, 0, 4, s->s);  // word 1 of the counter block (K1a/K1b use 0 and 2)
   if (e0 != cudaSuccess) return fail(e0, "cudaMemsetAsync(counter)", err);
   // persistent CTAs: enough to fill every SM, items are handed out by the counter
   unsigned grid = (unsigned)std::min<size_t>((p.n_items + K3_GRAB - 1) / K3_GRAB, (size_t)8 * g_sm_count);

@@ -43,8 +43,11 @@ int d2d(void* dst, const void* src, size_t bytes, Stream* s, std::string& err);
 int fill(void* dst, int byte_value, size_t bytes, Stream* s, std::string& err);
 unsigned long long transfer_bytes(int which);  // process-wide bytes copied so far: 0 host->device, 1 device->host
 
-// K1: `blocks` CTAs of `warps` warps, dynamic shared memory = warps * smem_words_per_warp * 4
-int launch_k1(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err);
+// K1a: one lane per packet, `blocks` CTAs of 128 threads.  K1b: one warp per packet, `blocks` CTAs of
+// `warps` warps, dynamic shared memory = warps * smem_words_per_warp * 4.  Both take packets from
+// p.counter (K1a uses word 0, K1b word 2 of the context's counter block).
+int launch_k1a(const K1Params& p, bool debug, int blocks, Stream* s, std::string& err);
+int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err);
 // K3: one CTA per work item, ncb channels side by side (64 threads each)
 int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream* s, std::string& err);
 size_t max_smem_per_block();

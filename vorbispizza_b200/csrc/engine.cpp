@@ -11,20 +11,28 @@
 
 namespace vpz {
 
-static uint32_t k1_words(const Setup& st) {
+// vectors * partitions of the largest residue of the setup (units of K1a/K1b)
+static size_t max_units(const Setup& st) {
   const VpzSetupHdr* h = st.hdr();
   const int C = h->channels;
   const int half_max = 1 << (h->log2_size1 - 1);
   const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(st.blob.data() + h->residues_off);
-  size_t max_parts = 0;
+  size_t units = 0;
   for (int i = 0; i < h->nresidues; i++) {
     int nvec = rs[i].type == 2 ? 1 : C;
     int64_t vlen = rs[i].type == 2 ? (int64_t)half_max * C : half_max;
     int64_t b = std::min<int64_t>(rs[i].begin, vlen), e = std::min<int64_t>(rs[i].end, vlen);
     int64_t parts = e > b ? (e - b) / rs[i].part_size : 0;
-    max_parts = std::max(max_parts, (size_t)(parts * nvec));
+    units = std::max(units, (size_t)(parts * nvec));
   }
-  size_t words = (size_t)C * half_max + (size_t)C * 64 + 64 + 66 + 66 + (max_parts + 3) / 4 + 8;
+  return units;
+}
+
+// K1b shared memory per warp: swizzled residue (one pad word per 32) + unit start offsets
+static uint32_t k1_words(const Setup& st) {
+  const VpzSetupHdr* h = st.hdr();
+  const size_t n = (size_t)h->channels << (h->log2_size1 - 1);
+  size_t words = n + (n >> 5) + 1 + 512 + 32 + 8;
   return (uint32_t)((words + 31) & ~(size_t)31);
 }
 
@@ -32,7 +40,15 @@ static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
   const VpzSetupHdr* h = s->host.hdr();
   s->fast_sizes = h->log2_size0 == 8 && h->log2_size1 == 11;
   s->k3_floats_per_ch = (1u << h->log2_size1) + 3u * (1u << (h->log2_size1 - 2)) + 16u;  // scratch + 3 half-slots
-  if (!s->synthetic) s->k1_words_per_warp = k1_words(s->host);
+  if (!s->synthetic) {
+    const size_t units = max_units(s->host);
+    if (units > 512) {  // K1_MAX_UNITS
+      ctx->last_error = "more than 512 residue partitions per packet are not on the GPU path";
+      return VPZ_E_UNSUPPORTED;
+    }
+    s->k1_words_per_warp = k1_words(s->host);
+    s->rec_words = (uint32_t)(4 + h->channels * 68 + (units + 3) / 4 + 1);  // K1_REC_HDR, K1_SEG_WORDS
+  }
   size_t bytes = s->host.blob.size() * 4;
   s->d_blob = dev::alloc(bytes, ctx->last_error);
   if (!s->d_blob) return VPZ_E_CUDA;
@@ -232,6 +248,7 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
   out->counts.assign(n_pkts, 0);
   out->src.reserve(n_pkts);
   out->byte_off.reserve(n_pkts);
+  out->ent_off.reserve(n_pkts);
   out->ola.reserve(n_pkts);
   bool have_prev = false;
   int prev_rs = 0, prev_re = 0, prev_half = 0;
@@ -288,6 +305,9 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
                           (have_prev ? 0 : VPZ_OLA_NOOUT));
     out->src.push_back(PktSrc{p, len});
     out->byte_off.push_back((uint32_t)staged);
+    // every codeword is at least one bit long: 8 * len bounds the entry indices of the packet
+    out->ent_off.push_back((uint32_t)out->ent_total);
+    out->ent_total += ((uint64_t)len * 8 + 8 + 1) & ~(uint64_t)1;
     out->ola.push_back(ola);
     staged = end;
     out->payload_bytes += len;
@@ -314,12 +334,13 @@ int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool
   if (n == 0) return VPZ_OK;
   const uint32_t chunk = (uint32_t)std::max(1, ctx->ola_chunk);
   struct Base {
-    uint64_t bytes, spec, out;
+    uint64_t bytes, spec, out, rec, ent;
     size_t pkt, item;
     int slot;
   };
   std::vector<Base> base(n);
   uint64_t bytes = (b->bytes.n + 3) & ~(size_t)3, spec = b->spec_floats, out = b->total_floats;
+  uint64_t rec = b->rec_words, ent = b->ent_total;
   size_t pkt = b->pkts_in.n, item = b->items.n;
   for (size_t i = 0; i < n; i++) {
     const RunPlan& p = *plans[i];
@@ -327,8 +348,10 @@ int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool
       ctx->last_error = "packet runs cannot use a synthetic setup";
       return VPZ_E_INVALID_OP;
     }
-    base[i] = Base{bytes, spec, out, pkt, item, slot_of(b, p.setup)};
+    base[i] = Base{bytes, spec, out, rec, ent, pkt, item, slot_of(b, p.setup)};
     const size_t nv = p.src.size();
+    rec += (uint64_t)nv * p.setup->rec_words;
+    ent += p.ent_total;
     bytes += p.staged_bytes;
     spec += p.spec_floats;
     out += (uint64_t)p.samples * p.setup->host.id.channels;
@@ -336,7 +359,7 @@ int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool
     item += nv > 1 ? (nv - 1 + chunk - 1) / chunk : 0;
     b->max_channels = std::max(b->max_channels, p.setup->host.id.channels);
   }
-  if (spec > 0xffffff00ull || bytes > 0xfffffff0ull) {
+  if (spec > 0xffffff00ull || bytes > 0xfffffff0ull || rec > 0xffffff00ull || ent > 0xffffff00ull) {
     ctx->last_error = "batch exceeds 2^32 spectrum floats / 4 GiB of packet bytes; split it";
     return VPZ_E_ARGUMENT;
   }
@@ -359,6 +382,9 @@ int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool
       in.byte_len = len;
       in.spec_off = (uint32_t)(bs.spec + p.ola[k].spec_off);
       in.setup_slot = (uint32_t)bs.slot;
+      in.rec_off = (uint32_t)(bs.rec + (uint64_t)k * p.setup->rec_words);
+      in.ent_off = (uint32_t)(bs.ent + p.ent_off[k]);
+      in.pad[0] = in.pad[1] = 0;
       b->pkts_in.p[bs.pkt + k] = in;
       VpzPktOla ola = p.ola[k];
       ola.spec_off = in.spec_off;
@@ -385,6 +411,8 @@ int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool
   b->items.n = item;
   b->spec_floats = spec;
   b->total_floats = out;
+  b->rec_words = rec;
+  b->ent_total = ent;
   for (size_t i = 0; i < n; i++) {
     RunPlan& p = *plans[i];
     Run run;
@@ -434,6 +462,21 @@ int batch_upload(vpz_batch* b) {
     if ((rc = dev::h2d(b->d_pkts_in.p, b->pkts_in.p, np * sizeof(VpzPktIn), st, err))) return rc;
     if (!b->d_res.reserve(np * sizeof(VpzPktRes), err)) return VPZ_E_CUDA;
     if (!b->d_spec.reserve(b->spec_floats * 4, err)) return VPZ_E_CUDA;
+    if (!b->d_rec.reserve(b->rec_words * 4 + 16, err) || !b->d_ent.reserve(b->ent_total * 2 + 16, err) ||
+        !b->d_order.reserve(np * 4 + 16, err))
+      return VPZ_E_CUDA;
+    // K1a order: packets sorted by byte length, longest first (counting sort), so the 32 lanes of a
+    // warp get packets of like size and the long ones do not form the tail of the launch
+    if (!b->order.reserve(np + 1)) return VPZ_E_NOMEM;
+    {
+      std::vector<uint32_t> bucket(4098, 0);
+      auto key = [&](size_t i) { return (size_t)(4096 - std::min<uint32_t>(b->pkts_in.p[i].byte_len >> 2, 4096)); };
+      for (size_t i = 0; i < np; i++) bucket[key(i) + 1]++;
+      for (size_t k = 1; k < bucket.size(); k++) bucket[k] += bucket[k - 1];
+      for (size_t i = 0; i < np; i++) b->order.p[bucket[key(i)]++] = (uint32_t)i;
+      b->order.n = np;
+    }
+    if ((rc = dev::h2d(b->d_order.p, b->order.p, np * 4, st, err))) return rc;
   }
   if (!b->d_pkts_ola.reserve(np * sizeof(VpzPktOla), err) || !b->d_items.reserve(b->items.n * sizeof(VpzOlaItem), err) ||
       !b->d_pcm.reserve(b->total_floats * 4, err) || !b->d_clip.reserve(np * 4, err) ||
@@ -482,7 +525,18 @@ int batch_decode(vpz_batch* b, int clip) {
     p.n_pkts = (uint32_t)np;
     p.counter = ctx->d_counter;
     p.smem_words_per_warp = k1w;
+    p.rec = static_cast<uint32_t*>(b->d_rec.p);
+    p.ent = static_cast<uint16_t*>(b->d_ent.p);
+    p.order = static_cast<const uint32_t*>(b->d_order.p);
     p.dbg = b->dbg;
+    const bool debug = b->dbg.hdr != nullptr;
+    // K1a: one lane per packet, 4 warps per CTA
+    size_t a_blocks = std::min<size_t>((np + 127) / 128, (size_t)16 * dev::sm_count());
+    if ((rc = dev::launch_k1a(p, debug, (int)std::max<size_t>(1, a_blocks), st, err))) return rc;
+    b->launches++;
+    ctx->kernel_launches++;
+    dev::event_record(ctx->ev[1], st);
+    // K1b: one warp per packet
     int warps = std::max(1, std::min(8, ctx->k1_warps));
     size_t smem_block = (size_t)warps * k1w * 4;
     while (warps > 1 && smem_block > dev::max_smem_per_block()) {
@@ -491,11 +545,13 @@ int batch_decode(vpz_batch* b, int clip) {
     }
     size_t per_sm = std::max<size_t>(1, std::min<size_t>(2048 / (warps * 32), (227 * 1024) / (smem_block + 1024)));
     size_t blocks = std::min<size_t>((np + warps - 1) / warps, per_sm * (size_t)dev::sm_count());
-    if ((rc = dev::launch_k1(p, b->dbg.hdr != nullptr, (int)std::max<size_t>(1, blocks), warps, st, err))) return rc;
+    if ((rc = dev::launch_k1b(p, debug, (int)std::max<size_t>(1, blocks), warps, st, err))) return rc;
     b->launches++;
     ctx->kernel_launches++;
+  } else {
+    dev::event_record(ctx->ev[1], st);
   }
-  dev::event_record(ctx->ev[1], st);
+  dev::event_record(ctx->ev[2], st);
   if (b->items.n) {
     if ((rc = dev::fill(b->d_clip.p, 0xff, np * 4, st, err))) return rc;
     K3Params p;
@@ -519,7 +575,7 @@ int batch_decode(vpz_batch* b, int clip) {
     b->launches++;
     ctx->kernel_launches++;
   }
-  dev::event_record(ctx->ev[2], st);
+  dev::event_record(ctx->ev[3], st);
   b->decoded = true;
   b->clip_fetched = false;
   return VPZ_OK;

@@ -25,7 +25,8 @@ struct vpz_setup {
   std::vector<uint8_t> id_pkt, setup_pkt;
   void* d_blob = nullptr;
   int refs = 0;
-  uint32_t k1_words_per_warp = 0;   // shared memory K1 needs per warp
+  uint32_t k1_words_per_warp = 0;   // shared memory K1b needs per warp
+  uint32_t rec_words = 0;           // size of one packet's symbol record (K1a -> K1b)
   uint32_t k3_floats_per_ch = 0;    // shared memory K3 needs per channel (generic layout)
   bool fast_sizes = false;          // block sizes 256 / 2048
   bool synthetic = false;           // window/twiddle tables only (vpz_synth_create)
@@ -62,7 +63,7 @@ struct vpz_ctx {
   vpz::dev::Stream* stream = nullptr;
   vpz::dev::Stream* copy_stream = nullptr;   // device->host PCM copies of the bulk pipeline
   vpz::ThreadPool* pool = nullptr;           // created on first bulk call
-  vpz::dev::Event* ev[3] = {nullptr, nullptr, nullptr};
+  vpz::dev::Event* ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start, after K1a, after K1b, after K3
   std::string last_error;
   int l1_bits = VPZ_L1_BITS_DEFAULT;
   int ola_chunk = 63;   // + the seed packet = one descriptor window of the IMDCT kernel
@@ -136,6 +137,8 @@ struct RunPlan {
   vpz_setup* setup = nullptr;
   std::vector<PktSrc> src;          // decodable packets, in order
   std::vector<uint32_t> byte_off;   // staged offset of each, relative to the run's byte base
+  std::vector<uint32_t> ent_off;    // uint16 offset of each packet's entry-index area, relative to the run
+  uint64_t ent_total = 0;
   std::vector<VpzPktOla> ola;       // spec_off relative to the run's spectrum base, out_off in samples
   std::vector<int32_t> counts;      // per SUBMITTED packet
   uint64_t staged_bytes = 0, payload_bytes = 0, spec_floats = 0;
@@ -167,13 +170,16 @@ struct vpz_batch {
   std::vector<vpz_setup*> slots;
   uint64_t total_floats = 0, spec_floats = 0;
   uint64_t payload_bytes = 0;
+  uint64_t rec_words = 0, ent_total = 0;      // symbol records / entry indices of all packets
+  vpz::HostBuf<uint32_t> order;               // K1a packet order (by byte length)
+  vpz::DevBuf d_rec, d_ent, d_order;
   int max_channels = 1;
   bool uploaded = false, synthetic = false, decoded = false;
   vpz::DevBuf d_bytes, d_pkts_in, d_pkts_ola, d_items, d_res, d_spec, d_pcm, d_clip, d_setups;
   vpz::HostBuf<const void*> h_setups;
   vpz::HostBuf<uint32_t> h_clip;
   bool clip_fetched = false;
-  float ms_k1 = 0, ms_k3 = 0, ms_total = 0;
+  float ms_k1 = 0, ms_k1a = 0, ms_k1b = 0, ms_k3 = 0, ms_total = 0;
   int launches = 0;
   // debug plumbing (vpz_debug_decode_packet)
   K1Debug dbg = {nullptr, nullptr, 0, nullptr, 0, nullptr};

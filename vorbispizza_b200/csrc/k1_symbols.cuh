@@ -1,0 +1,613 @@
+// k1_symbols.cuh -- the entropy stage, split by the shape of its parallelism.
+//
+//   K1a  vpz_k1a_symbols : ONE LANE PER PACKET.  The bit cursor of a packet is strictly serial, so a
+//        warp decodes 32 packets at once, each lane running the reference's symbol sequence for its
+//        own packet: floor1 unpack + unwrap, partition classwords, VQ entry indices.  It produces a
+//        compact symbol record (floor line segments, partition classes, entry indices) and never
+//        touches a float.  The residue walk is flattened into one loop with one DecodeScalar per
+//        iteration so that lanes at different (stage, partition) positions still share every
+//        instruction.
+//   K1b  vpz_k1b_spectrum : ONE WARP PER PACKET, all data-parallel: VQ lookups accumulated in shared
+//        memory in the reference's order, inverse coupling, floor line render, dB multiply, spectrum
+//        store.
+//
+// Replaces, per audio packet (reference file:line):
+//   Floor1.Unpack / UnwrapPosts         Floor1.cs:162-219, 270-370          (K1a)
+//   Mapping.DecodePacket flag logic     Mapping.cs:121-130                  (K1a)
+//   Residue0/1/2.Decode control flow    Residue0.cs:117-206, Residue2.cs:12-52   (K1a)
+//   Codebook.DecodeScalar               Codebook.cs:301-335  (two-level table, same symbol + bits) (K1a)
+//   Residue0/1.WriteVectors             Residue0.cs:208-231, Residue1.cs:12-34   (K1b)
+//   Mapping.ApplyCoupling               Mapping.cs:198-269                  (K1b)
+//   Floor1.Apply / RenderLineMulti      Floor1.cs:222-268, 372-397          (K1b, closed-form line)
+#pragma once
+#include "k1_params.h"
+
+#ifndef VPZ_EMU
+#define VPZ_DEV __device__ __forceinline__
+#define VPZ_DEVN __device__ __noinline__
+#define VPZ_LDG(p) __ldg(p)
+#else
+#define VPZ_DEV inline
+#define VPZ_DEVN inline
+#define VPZ_LDG(p) (*(p))
+#endif
+
+// word offsets inside vpz_packet_dump (include/vpz.h) -- keep in sync
+#define DUMP_STATUS 0
+#define DUMP_MODE 1
+#define DUMP_BLOCK 2
+#define DUMP_INFO 3
+#define DUMP_BITS 9
+#define DUMP_EXEC 10
+#define DUMP_NOEXEC 11
+#define DUMP_SCALARS_N 12
+#define DUMP_CLASSES_N 13
+#define DUMP_POSTCOUNT 14
+#define DUMP_RAWPOSTS (14 + 8)
+#define DUMP_FINALY (14 + 8 + 8 * 64)
+#define DUMP_STEPFLAGS (14 + 8 + 16 * 64)
+
+// ---- symbol record (K1a -> K1b), 32-bit words at P.rec + pkt.rec_off --------------------------
+//   [0] own_mask | noexec_mask << 8 | status << 16 | long_block << 24
+//   [1] number of VQ entries written at P.ent + pkt.ent_off (uint16 each)
+//   [2] final bit cursor
+//   [3] reserved
+//   then per channel K1_SEG_WORDS words: [0] = number of line segments n, [1..n+1] = points x | y << 16
+//   then one byte per (vector, partition): the partition class
+#define K1_REC_HDR 4
+#define K1_SEG_WORDS 68
+#define K1_MAX_UNITS 512      // vectors * partitions per packet (setup.cpp refuses more)
+
+struct K1Bits {
+  const uint32_t* w;
+  int pos, nbits;
+  int is_short;
+};
+
+VPZ_DEV uint32_t k1_peek32(const K1Bits& b) {
+  int i = b.pos >> 5;
+  uint32_t lo = VPZ_LDG(b.w + i), hi = VPZ_LDG(b.w + i + 1);
+  return __funnelshift_r(lo, hi, b.pos & 31);
+}
+
+// VorbisPacket.ReadBits (VorbisPacket.cs:157-164): zero-extended, truncated at the end, n <= 32
+VPZ_DEV uint32_t k1_read(K1Bits& b, int n) {
+  if (n <= 0) return 0;
+  uint32_t v = k1_peek32(b);
+  if (n < 32) v &= (1u << n) - 1u;
+  int np = b.pos + n;
+  b.pos = np < b.nbits ? np : b.nbits;
+  return v;
+}
+
+struct K1Book {
+  const uint32_t* l1;
+  const VpzBook* bk;
+  uint32_t l1_mask;
+  int dims;
+};
+
+VPZ_DEV K1Book k1_book(const uint32_t* blob, const VpzBook* books, int idx) {
+  const VpzBook* bk = books + idx;
+  K1Book r;
+  r.bk = bk;
+  r.l1 = blob + VPZ_LDG(&bk->l1_off);
+  // dims (u16) and l1_bits (u8) share one 32-bit word at byte offset 24
+  uint32_t packed = VPZ_LDG(reinterpret_cast<const uint32_t*>(bk) + 6);
+  r.dims = (int)(packed & 0xffffu);
+  r.l1_mask = (1u << ((packed >> 16) & 0xffu)) - 1u;
+  return r;
+}
+
+// Codebook.DecodeScalar (Codebook.cs:301-335).  -1: no bits left or no code matches.
+template <bool DEBUG>
+VPZ_DEV int k1_decode(K1Bits& b, const K1Book& bk, const uint32_t* blob, const K1Params& P, int& nscal) {
+  int sym = -1;
+  if (b.pos < b.nbits) {
+    uint32_t x = k1_peek32(b);
+    uint32_t e = VPZ_LDG(bk.l1 + (x & bk.l1_mask));
+    if (e & 0x80000000u) {  // longer than the first-level table: binary search in the sorted long codes
+      const uint32_t* ranges = blob + VPZ_LDG(&bk.bk->range_off);
+      const uint32_t* lcode = blob + VPZ_LDG(&bk.bk->lcode_off);
+      const uint32_t* linfo = blob + VPZ_LDG(&bk.bk->linfo_off);
+      uint32_t id = e & 0x7fffffffu;
+      uint32_t lo = VPZ_LDG(ranges + 2 * id), hi = VPZ_LDG(ranges + 2 * id + 1);
+      uint32_t m = __brev(x);
+      while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (VPZ_LDG(lcode + mid) <= m) lo = mid; else hi = mid;
+      }
+      uint32_t info = VPZ_LDG(linfo + lo);
+      uint32_t len = info & 0xffu;
+      e = (((m ^ VPZ_LDG(lcode + lo)) >> (32u - len)) == 0u) ? info : 0u;
+    }
+    if (e != 0u) {
+      int len = (int)(e & 0xffu);
+      sym = (int)(e >> 8);
+      int np = b.pos + len;
+      if (np > b.nbits) {  // SkipBits past the end: VorbisPacket.cs:248-292
+        np = b.nbits;
+        b.is_short = 1;
+      }
+      b.pos = np;
+    }
+  }
+  if (DEBUG) {
+    if (P.dbg.scalars && nscal < P.dbg.scalars_cap) P.dbg.scalars[nscal] = sym;
+    nscal++;
+  }
+  return sym;
+}
+
+// Floor1.RenderPoint (Floor1.cs:355-370)
+VPZ_DEV int k1_render_point(int x0, int y0, int x1, int y1, int X) {
+  int dy = y1 - y0, adx = x1 - x0;
+  int ady = dy < 0 ? -dy : dy;
+  int off = ady * (X - x0) / adx;
+  return dy < 0 ? y0 - off : y0 + off;
+}
+
+// Geometry of the residue vectors of one packet (Residue0.Decode, Residue0.cs:117-143; type 2 via
+// Residue2.cs:12-52).  Shared by K1a and K1b so both walk the same units.
+struct K1ResGeom {
+  int rtype, nvec, vlen, begin, psize, part_count;
+  uint32_t skip;       // bit v: vector v is not decoded
+  bool any;
+};
+VPZ_DEV K1ResGeom k1_res_geom(const VpzResidue* rs, int C, int half, uint32_t noexec) {
+  K1ResGeom g;
+  g.rtype = rs->type;
+  g.nvec = g.rtype == 2 ? 1 : C;
+  g.vlen = g.rtype == 2 ? half * C : half;
+  g.skip = g.rtype == 2 ? ((noexec == ((1u << C) - 1u)) ? 1u : 0u) : noexec;
+  g.begin = (int)rs->begin < g.vlen ? (int)rs->begin : g.vlen;
+  int end = (int)rs->end < g.vlen ? (int)rs->end : g.vlen;
+  int n = end - g.begin;
+  g.psize = (int)rs->part_size;
+  g.part_count = n > 0 ? n / g.psize : 0;
+  g.any = false;
+  for (int v = 0; v < g.nvec; v++) g.any |= !((g.skip >> v) & 1u);
+  return g;
+}
+// entries one (class, stage) unit holds: Residue0.WriteVectors decodes psize / dims entries,
+// Residue1.WriteVectors steps i += dims until i >= psize
+VPZ_DEV int k1_unit_entries(int rtype, int psize, int dims) {
+  return rtype == 0 ? psize / dims : (psize + dims - 1) / dims;
+}
+
+// =============================================================================================
+// K1a: one lane decodes one packet
+// =============================================================================================
+template <bool DEBUG>
+VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
+  const VpzPktIn pk = P.pkts[pkt_idx];
+  const uint32_t* blob = P.setups[pk.setup_slot];
+  const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
+  const int C = H->channels;
+  const VpzBook* books = reinterpret_cast<const VpzBook*>(blob + H->books_off);
+  const int half_max = 1 << (H->log2_size1 - 1);
+  uint32_t* rec = P.rec + pk.rec_off;
+  uint16_t* ent = P.ent + pk.ent_off;
+
+  K1Bits b;
+  b.w = P.bytes + (pk.byte_off >> 2);
+  b.pos = 0;
+  b.nbits = (int)pk.byte_len * 8;
+  b.is_short = 0;
+  int nscal = 0, ncls = 0;
+
+  // StreamDecoder.DecodeNextPacket (StreamDecoder.cs:728-741): the host only queues packets whose
+  // type bit is 0 and whose mode exists, so these reads just advance the cursor.
+  k1_read(b, 1);
+  const int mode_idx = (int)k1_read(b, H->mode_bits);
+  const VpzMode* modes = reinterpret_cast<const VpzMode*>(blob + H->modes_off);
+  const int long_block = modes[mode_idx].block_flag;
+  const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + modes[mode_idx].mapping;
+  if (long_block) k1_read(b, 2);  // prev/next window flags (Mode.cs:38), geometry is the host's job
+  const int half = long_block ? half_max : (1 << (H->log2_size0 - 1));
+
+  // ---- floor unpack + unwrap, channel by channel (Mapping.cs:106-116, Floor1.cs:162-219, 270-353) ----
+  uint32_t own_mask = 0;  // bit ch: floor has energy (FloorData.ExecuteChannel)
+  for (int ch = 0; ch < C; ch++) {
+    const VpzFloor1* fl = reinterpret_cast<const VpzFloor1*>(blob + H->floors_off) + mp->submap_floor[mp->mux[ch]];
+    short po[VPZ_MAX_POSTS + 1];   // raw posts
+    short fy[VPZ_MAX_POSTS + 1];   // unwrapped Y
+    int count = 0, written = 0;  // written: posts stored before a failed decode reset the count
+    if (k1_read(b, 1) == 1) {
+      const int ybits = fl->ybits;
+      po[0] = (short)k1_read(b, ybits);
+      po[1] = (short)k1_read(b, ybits);
+      count = written = 2;
+      const int nparts = fl->partitions;
+      for (int i = 0; i < nparts && count > 0; i++) {
+        const int c = fl->part_class[i];
+        const int cdim = fl->class_dim[c], cbits = fl->class_sub[c];
+        const uint32_t csub = (1u << cbits) - 1u;
+        uint32_t cval = 0;
+        if (cbits > 0) {
+          K1Book mb = k1_book(blob, books, fl->class_master[c]);
+          int v = k1_decode<DEBUG>(b, mb, blob, P, nscal);
+          if (v < 0) {
+            count = 0;
+            break;
+          }
+          cval = (uint32_t)v;
+        }
+        for (int j = 0; j < cdim; j++) {
+          const int book_idx = fl->sub_books[c][cval & csub];
+          cval >>= cbits;
+          int post = 0;
+          if (book_idx >= 0) {
+            K1Book sb = k1_book(blob, books, book_idx);
+            post = k1_decode<DEBUG>(b, sb, blob, P, nscal);
+            if (post < 0) {
+              count = 0;
+              break;
+            }
+          }
+          po[count++] = (short)post;
+          written = count;
+        }
+      }
+    }
+    if (DEBUG && P.dbg.hdr) {
+      P.dbg.hdr[DUMP_POSTCOUNT + ch] = count;
+      for (int i = 0; i < 64; i++) P.dbg.hdr[DUMP_RAWPOSTS + ch * 64 + i] = i < written ? po[i] : 0;
+    }
+    uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
+    if (count == 0) {
+      seg[0] = 0;
+      continue;
+    }
+    own_mask |= 1u << ch;
+    // UnwrapPosts (Floor1.cs:270-353): serial dependency through earlier posts
+    const int range = fl->range;
+    unsigned long long flags = 3ull;
+    fy[0] = po[0];
+    fy[1] = po[1];
+    for (int i = 2; i < count; i++) {
+      const int lo = fl->lneigh[i], hi = fl->hneigh[i];
+      const int predicted = k1_render_point(fl->xlist[lo], fy[lo], fl->xlist[hi], fy[hi], fl->xlist[i]);
+      const int val = po[i];
+      const int highroom = range - predicted, lowroom = predicted;
+      const int room = (highroom < lowroom ? highroom : lowroom) * 2;
+      int result = predicted;
+      if (val != 0) {
+        flags |= (1ull << lo) | (1ull << hi) | (1ull << i);
+        if (val >= room)
+          result = highroom > lowroom ? val - lowroom + predicted : predicted - val + highroom - 1;
+        else
+          result = (val & 1) ? predicted - ((val + 1) >> 1) : predicted + (val >> 1);
+      }
+      fy[i] = (short)result;
+    }
+    if (DEBUG && P.dbg.hdr) {
+      for (int i = 0; i < 64; i++) {
+        P.dbg.hdr[DUMP_FINALY + ch * 64 + i] = i < count ? fy[i] : 0;
+        P.dbg.hdr[DUMP_STEPFLAGS + ch * 64 + i] = i < count ? (int)((flags >> i) & 1ull) : 0;
+      }
+    }
+    // flagged posts in X order -> line segments (Floor1.Apply, Floor1.cs:222-268).  A segment that
+    // is clamped at `half` (quirk Q1: clamp before the slope) is the last one: the loop breaks.
+    const int mult = fl->multiplier;
+    int nseg = 0, lx = 0, ly = fy[0] * mult;
+    seg[1] = (uint32_t)0 | ((uint32_t)(ly & 0xffff) << 16);
+    for (int i = 1; i < count; i++) {
+      const int idx = fl->sortidx[i];
+      if ((flags >> idx) & 1ull) {
+        const int hx = fl->xlist[idx], hy = fy[idx] * mult;
+        if (lx < half) {
+          nseg++;
+          seg[1 + nseg] = (uint32_t)(hx < half ? hx : half) | ((uint32_t)(hy & 0xffff) << 16);
+        }
+        lx = hx;
+        ly = hy;
+      }
+      if (lx >= half) break;
+    }
+    if (lx < half) {  // flat tail
+      nseg++;
+      seg[1 + nseg] = (uint32_t)half | ((uint32_t)(ly & 0xffff) << 16);
+    }
+    seg[0] = (uint32_t)nseg;
+  }
+  // no-energy propagation through the coupling steps (Mapping.cs:121-130)
+  uint32_t noexec = ~own_mask & ((1u << C) - 1u);
+  for (int i = 0; i < mp->coupling_steps; i++) {
+    uint32_t mb = 1u << mp->mag[i], ab = 1u << mp->ang[i];
+    if (!((noexec & mb) && (noexec & ab))) noexec &= ~(mb | ab);
+  }
+
+  // ---- residue: classwords + VQ entry indices (single submap: Setup::parse refuses more) ------
+  const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(blob + H->residues_off) + mp->submap_residue[0];
+  const K1ResGeom g = k1_res_geom(rs, C, half, noexec);
+  int status = 0;
+  uint32_t n_ent = 0;
+  if (g.part_count > 0 && g.any) {
+    uint8_t cls[K1_MAX_UNITS];                       // [v * part_count + part]
+    uint8_t* rec_cls = reinterpret_cast<uint8_t*>(rec + K1_REC_HDR + C * K1_SEG_WORDS);
+    const K1Book cb = k1_book(blob, books, rs->class_book);
+    const int cdim = cb.dims;
+    const uint8_t* dmap = reinterpret_cast<const uint8_t*>(blob + rs->decode_map_off);
+    const int partvals = (int)rs->decode_map_len / cdim;
+    const int max_stages = rs->max_stages;
+    const int nvec = g.nvec, part_count = g.part_count;
+    // classes of groups a truncated packet never reaches must still be valid indices for K1b
+    for (int u = 0; u < nvec * part_count; u++) rec_cls[u] = 0;
+    // Flattened walk of  stage -> partition group -> [stage 0: classwords] -> partition -> vector:
+    // every trip round the loop below decodes exactly ONE codeword, so lanes that sit at different
+    // places of their packets still execute the same instructions.
+    int stage = 0, gpart = 0, k = 0, v = 0;
+    bool in_class = true;      // stage 0 starts every group with its classwords
+    int rem = 0;               // entries still to decode in the current (partition, vector) unit
+    K1Book cur = cb;
+    bool done = max_stages == 0;
+    while (!done) {
+      if (rem == 0) {
+        // ---- find the next codeword to decode ----
+        bool found = false;
+        while (!found && !done) {
+          if (in_class) {
+            while (v < nvec && ((g.skip >> v) & 1u)) v++;
+            if (v < nvec) {
+              cur = cb;
+              found = true;       // classword of vector v for the group starting at gpart
+            } else {
+              in_class = false;
+              k = 0;
+              v = 0;
+            }
+          } else {
+            if (k == cdim || gpart + k >= part_count) {  // group finished
+              gpart += k;
+              if (gpart >= part_count) {
+                gpart = 0;
+                stage++;
+                if (stage >= max_stages) done = true;
+              }
+              in_class = stage == 0;
+              k = 0;
+              v = 0;
+            } else {
+              while (v < nvec && ((g.skip >> v) & 1u)) v++;
+              if (v == nvec) {
+                k++;
+                v = 0;
+              } else {
+                const int part = gpart + k;
+                const int c = cls[v * part_count + part];
+                if (DEBUG && stage == 0) {
+                  if (P.dbg.classes && ncls < P.dbg.classes_cap) P.dbg.classes[ncls] = c;
+                  ncls++;
+                }
+                if (((rs->cascade[c] >> stage) & 1u) && rs->has_books[c]) {
+                  cur = k1_book(blob, books, rs->books[c][stage]);
+                  rem = k1_unit_entries(g.rtype, g.psize, cur.dims);
+                  found = rem > 0;
+                }
+                v++;
+              }
+            }
+          }
+        }
+        if (done) break;
+      }
+      const int sym = k1_decode<DEBUG>(b, cur, blob, P, nscal);
+      if (in_class) {
+        // quirk Q8 accepts idx < partvals*dim; beyond partvals the reference indexes past
+        // _decodeMap and throws, so both ends are treated as "stop decoding this packet"
+        if (sym < 0 || sym >= partvals) {
+          status = 1;
+          break;
+        }
+        for (int kk = 0; kk < cdim; kk++)
+          if (gpart + kk < part_count) {
+            const uint8_t c = dmap[sym * cdim + kk];
+            cls[v * part_count + gpart + kk] = c;
+            rec_cls[v * part_count + gpart + kk] = c;
+          }
+        v++;
+      } else {
+        if (sym < 0) {  // Residue0.cs:195-201: keep what was decoded
+          status = 1;
+          break;
+        }
+        ent[n_ent++] = (uint16_t)sym;
+        rem--;
+      }
+    }
+  }
+  rec[0] = own_mask | (noexec << 8) | ((uint32_t)status << 16) | ((uint32_t)long_block << 24);
+  rec[1] = n_ent;
+  rec[2] = (uint32_t)b.pos;
+  rec[3] = 0;
+  if (DEBUG && P.dbg.hdr) {
+    int32_t* h = P.dbg.hdr;
+    h[DUMP_STATUS] = 0;
+    h[DUMP_MODE] = mode_idx;
+    h[DUMP_BLOCK] = half * 2;
+    h[DUMP_BITS] = b.pos;
+    h[DUMP_EXEC] = (int)own_mask;
+    h[DUMP_NOEXEC] = (int)noexec;
+    h[DUMP_SCALARS_N] = nscal;
+    h[DUMP_CLASSES_N] = ncls;
+  }
+}
+
+// =============================================================================================
+// K1b: one warp turns one symbol record into a spectrum
+// =============================================================================================
+// swizzled shared index: one pad word per 32 keeps lanes that own consecutive partitions (a
+// partition is 16 or 32 floats) on different banks
+VPZ_DEV int k1b_sw(int i) { return i + (i >> 5); }
+
+// Per-warp shared memory (32-bit words): res[sw(C * half_max)] then ustart[K1_MAX_UNITS + 32]
+template <bool DEBUG>
+VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, int lane) {
+  const VpzPktIn pk = P.pkts[pkt_idx];
+  const uint32_t* blob = P.setups[pk.setup_slot];
+  const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
+  const int C = H->channels;
+  const VpzBook* books = reinterpret_cast<const VpzBook*>(blob + H->books_off);
+  const int half_max = 1 << (H->log2_size1 - 1);
+  const uint32_t* rec = P.rec + pk.rec_off;
+  const uint16_t* ent = P.ent + pk.ent_off;
+  const uint32_t hdr = rec[0];
+  const uint32_t own_mask = hdr & 0xffu, noexec = (hdr >> 8) & 0xffu;
+  const int long_block = (int)(hdr >> 24) & 1;
+  const uint32_t n_ent = rec[1];
+  const int half = long_block ? half_max : (1 << (H->log2_size0 - 1));
+
+  float* res = reinterpret_cast<float*>(smem);
+  int* ustart = reinterpret_cast<int*>(smem + k1b_sw(C * half_max) + 1);
+
+  if (lane == 0) {
+    VpzPktRes r;
+    r.exec_mask = (uint8_t)own_mask;
+    r.status = (uint8_t)((hdr >> 16) & 0xffu);
+    r.bits_used_lo = (uint16_t)rec[2];
+    P.res[pkt_idx] = r;
+  }
+  if (own_mask == 0 && !(DEBUG && P.dbg.residue)) return;  // every channel silent: K3 outputs zeros
+
+  // modes / mapping are only needed through the record: the mapping is found from the packet header
+  // bits again (mode index), cheaper than storing it
+  const uint32_t w0 = VPZ_LDG(P.bytes + (pk.byte_off >> 2));
+  const int mode_idx = (int)((w0 >> 1) & ((1u << H->mode_bits) - 1u));
+  const VpzMode* modes = reinterpret_cast<const VpzMode*>(blob + H->modes_off);
+  const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + modes[mode_idx].mapping;
+  const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(blob + H->residues_off) + mp->submap_residue[0];
+  const K1ResGeom g = k1_res_geom(rs, C, half, noexec);
+
+  const int total = C * half;
+  for (int i = lane; i < total; i += 32) res[k1b_sw(i)] = 0.f;
+  __syncwarp();
+
+  // ---- residue: stage by stage, every lane owns whole (partition, vector) units ----------------
+  if (g.part_count > 0 && g.any && n_ent > 0) {
+    const uint8_t* rec_cls = reinterpret_cast<const uint8_t*>(rec + K1_REC_HDR + C * K1_SEG_WORDS);
+    const int nunits = g.part_count * g.nvec;       // decode order inside a stage: partition major
+    uint32_t stage_base = 0;
+    for (int stage = 0; stage < rs->max_stages && stage_base < n_ent; stage++) {
+      // entries per unit -> exclusive prefix sum = where each unit's entries start
+      uint32_t carry = 0;
+      for (int u0 = 0; u0 < nunits; u0 += 32) {
+        const int u = u0 + lane;
+        int cnt = 0;
+        if (u < nunits) {
+          const int part = u / g.nvec, v = u - part * g.nvec;
+          if (!((g.skip >> v) & 1u)) {
+            const int c = rec_cls[v * g.part_count + part];
+            if (((rs->cascade[c] >> stage) & 1u) && rs->has_books[c]) {
+              const int dims = (int)(VPZ_LDG(reinterpret_cast<const uint32_t*>(books + rs->books[c][stage]) + 6) & 0xffffu);
+              cnt = k1_unit_entries(g.rtype, g.psize, dims);
+            }
+          }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          int n = __shfl_up_sync(0xffffffffu, incl, d);
+          if (lane >= d) incl += n;
+        }
+        if (u < nunits) ustart[u] = (int)carry + incl - cnt;
+        carry += (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
+      }
+      __syncwarp();
+      for (int u = lane; u < nunits; u += 32) {
+        const int part = u / g.nvec, v = u - part * g.nvec;
+        if ((g.skip >> v) & 1u) continue;
+        const int c = rec_cls[v * g.part_count + part];
+        if (!(((rs->cascade[c] >> stage) & 1u) && rs->has_books[c])) continue;
+        const VpzBook* bk = books + rs->books[c][stage];
+        const int dims = (int)(VPZ_LDG(reinterpret_cast<const uint32_t*>(bk) + 6) & 0xffffu);
+        const float* vq = reinterpret_cast<const float*>(blob + VPZ_LDG(&bk->vq_off));
+        const int cnt = k1_unit_entries(g.rtype, g.psize, dims);
+        uint32_t e = stage_base + (uint32_t)ustart[u];
+        const int offset = g.begin + part * g.psize;
+        const int vbase = v * half;   // rtype 2: v == 0
+        if (g.rtype == 0) {
+          // Residue0.WriteVectors (Residue0.cs:208-231), quirk Q6: dims summed into one bin
+          for (int s = 0; s < cnt && e < n_ent; s++, e++) {
+            const float* lk = vq + (size_t)ent[e] * dims;
+            float r = 0.f;
+            for (int d = 0; d < dims; d++) r = __fadd_rn(r, VPZ_LDG(lk + d));
+            if (offset + s < g.vlen) {
+              const int at = k1b_sw(vbase + offset + s);
+              res[at] = __fadd_rn(res[at], r);
+            }
+          }
+        } else {
+          // Residue1.WriteVectors (Residue1.cs:12-34)
+          int i = 0;
+          for (int s = 0; s < cnt && e < n_ent; s++, e++) {
+            const float* lk = vq + (size_t)ent[e] * dims;
+            for (int d = 0; d < dims; d++, i++) {
+              if (offset + i < g.vlen) {
+                const int at = k1b_sw(vbase + offset + i);
+                res[at] = __fadd_rn(res[at], VPZ_LDG(lk + d));
+              }
+            }
+          }
+        }
+      }
+      stage_base += carry;
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+
+  // accessor of channel c, bin i after the Residue2 de-interleave (Residue2.cs:42-50)
+#define RES_AT(c, i) res[k1b_sw(g.rtype == 2 ? (i) * C + (c) : (c) * half + (i))]
+
+  if (DEBUG && P.dbg.residue) {
+    for (int c = 0; c < C; c++)
+      for (int i = lane; i < half; i += 32) P.dbg.residue[c * half + i] = RES_AT(c, i);
+  }
+
+  // ---- inverse coupling, last step first (Mapping.cs:166-172, 235-267) ----------------------
+  for (int s = mp->coupling_steps - 1; s >= 0; s--) {
+    const int cm = mp->mag[s], ca = mp->ang[s];
+    for (int i = lane; i < half; i += 32) {
+      float m = RES_AT(cm, i), a = RES_AT(ca, i);
+      float nm = m, na = m;
+      if (m > 0.f) {
+        if (a > 0.f) na = __fsub_rn(m, a); else nm = __fadd_rn(m, a);
+      } else {
+        if (a > 0.f) na = __fadd_rn(m, a); else nm = __fsub_rn(m, a);
+      }
+      RES_AT(cm, i) = nm;
+      RES_AT(ca, i) = na;
+    }
+    __syncwarp();
+  }
+
+  // ---- floor line render + dB multiply + store (Floor1.cs:222-268, 372-397) -------------------
+  const float* db = reinterpret_cast<const float*>(blob + H->db_off);
+  float* out = P.spec + pk.spec_off;
+  for (int ch = 0; ch < C; ch++) {
+    if (!((own_mask >> ch) & 1u)) continue;  // Mapping.cs:185-194: silent channel, K3 sees zeros
+    const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
+    const int nseg = (int)seg[0];
+    // RenderLineMulti in closed form: after k steps of the DDA
+    // y = y0 + k*base + sy*floor(k*rem/adx), rem = |dy| - |base|*adx
+    for (int s = 0; s < nseg; s++) {
+      const uint32_t p0 = seg[1 + s], p1 = seg[2 + s];
+      const int x0 = (int)(p0 & 0xffffu), y0 = (int)(short)(p0 >> 16);
+      const int x1 = (int)(p1 & 0xffffu), y1 = (int)(short)(p1 >> 16);
+      const int dy = y1 - y0, adx = x1 - x0;
+      const int ady = dy < 0 ? -dy : dy;
+      const int sy = dy < 0 ? -1 : 1;
+      const int base = dy / adx;
+      const int rem = ady - (base < 0 ? -base : base) * adx;
+      for (int x = x0 + lane; x < x1; x += 32) {
+        const int kx = x - x0;
+        int y = y0 + kx * base + sy * ((kx * rem) / adx);
+        y = y < 0 ? 0 : (y > 255 ? 255 : y);  // the reference reads the table unchecked (quirk Q2)
+        out[ch * half + x] = __fmul_rn(RES_AT(ch, x), VPZ_LDG(db + y));
+      }
+    }
+  }
+#undef RES_AT
+  __syncwarp();
+}

@@ -53,9 +53,9 @@ int vpz_ctx_create(int device, vpz_ctx** out) {
   c->device = device;
   c->stream = dev::stream_create();
   c->copy_stream = dev::stream_create();
-  for (int i = 0; i < 3; i++) c->ev[i] = dev::event_create();
+  for (int i = 0; i < 4; i++) c->ev[i] = dev::event_create();
   c->d_counter = static_cast<uint32_t*>(dev::alloc(64, c->last_error));
-  if (!c->stream || !c->copy_stream || !c->ev[0] || !c->ev[1] || !c->ev[2] || !c->d_counter) {
+  if (!c->stream || !c->copy_stream || !c->ev[0] || !c->ev[1] || !c->ev[2] || !c->ev[3] || !c->d_counter) {
     vpz_ctx_destroy(c);
     return VPZ_E_CUDA;
   }
@@ -80,7 +80,7 @@ void vpz_ctx_destroy(vpz_ctx* c) {
     setup_release(s);
   }
   dev::free(c->d_counter);
-  for (int i = 0; i < 3; i++) dev::event_destroy(c->ev[i]);
+  for (int i = 0; i < 4; i++) dev::event_destroy(c->ev[i]);
   dev::stream_destroy(c->stream);
   dev::stream_destroy(c->copy_stream);
   delete c;
@@ -195,6 +195,7 @@ int vpz_batch_reset(vpz_batch* b) {
   b->runs.clear();
   b->slots.clear();
   b->total_floats = b->spec_floats = b->payload_bytes = 0;
+  b->rec_words = b->ent_total = 0;
   b->max_channels = 1;
   b->uploaded = b->decoded = false;
   return VPZ_OK;
@@ -236,9 +237,11 @@ int vpz_batch_sync(vpz_batch* b) {
   int rc = dev::stream_sync(b->ctx->stream, b->ctx->last_error);
   if (rc) return rc;
   if (b->decoded) {
-    b->ms_k1 = dev::event_elapsed_ms(b->ctx->ev[0], b->ctx->ev[1]);
-    b->ms_k3 = dev::event_elapsed_ms(b->ctx->ev[1], b->ctx->ev[2]);
-    b->ms_total = dev::event_elapsed_ms(b->ctx->ev[0], b->ctx->ev[2]);
+    b->ms_k1a = dev::event_elapsed_ms(b->ctx->ev[0], b->ctx->ev[1]);
+    b->ms_k1b = dev::event_elapsed_ms(b->ctx->ev[1], b->ctx->ev[2]);
+    b->ms_k1 = dev::event_elapsed_ms(b->ctx->ev[0], b->ctx->ev[2]);
+    b->ms_k3 = dev::event_elapsed_ms(b->ctx->ev[2], b->ctx->ev[3]);
+    b->ms_total = dev::event_elapsed_ms(b->ctx->ev[0], b->ctx->ev[3]);
   }
   return VPZ_OK;
 }
@@ -279,7 +282,7 @@ int vpz_batch_read_all(vpz_batch* b, float* dst) {
 float vpz_batch_last_ms(vpz_batch* b, int which, int* launches) {
   if (!b) return -1.f;
   if (launches) *launches = b->launches;
-  return which == 1 ? b->ms_k1 : which == 3 ? b->ms_k3 : b->ms_total;
+  return which == 1 ? b->ms_k1 : which == 3 ? b->ms_k3 : which == 11 ? b->ms_k1a : which == 12 ? b->ms_k1b : b->ms_total;
 }
 
 uint64_t vpz_transfer_bytes(int which) { return dev::transfer_bytes(which); }

@@ -100,11 +100,14 @@ struct VpzSetupHdr {
 
 // ---- per-packet descriptors ------------------------------------------------------------
 // K1 input: where the packet bytes are and where its spectrum goes.
-struct VpzPktIn {
+struct alignas(16) VpzPktIn {
   uint32_t byte_off;        // into the batch byte buffer; packet is followed by >= 8 zero bytes
   uint32_t byte_len;
   uint32_t spec_off;        // float offset of [channels][n/2] in the spectrum buffer
   uint32_t setup_slot;      // index into the batch's setup pointer table
+  uint32_t rec_off;         // word offset of the packet's symbol record (K1a -> K1b)
+  uint32_t ent_off;         // uint16 offset of the packet's VQ entry indices; room for 8 * byte_len + 8
+  uint32_t pad[2];
 };
 
 // K1 output / K3 input.
