@@ -20,6 +20,9 @@
 struct float2 {
   float x, y;
 };
+struct alignas(16) float4 {
+  float x, y, z, w;
+};
 struct emu_dim3 {
   unsigned x = 1, y = 1, z = 1;
 };
@@ -93,6 +96,8 @@ inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
   uint64_t v = ((uint64_t)hi << 32) | lo;
   return (uint32_t)(v >> sh);
 }
+inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 inline uint32_t __brev(uint32_t n) {
   n = ((n & 0xAAAAAAAAu) >> 1) | ((n & 0x55555555u) << 1);
   n = ((n & 0xCCCCCCCCu) >> 2) | ((n & 0x33333333u) << 2);

@@ -87,6 +87,11 @@ struct K1Book {
   int dims;
 };
 
+// dims (u16) and l1_bits (u8) share one 32-bit word at byte offset 24 of VpzBook
+VPZ_DEV int k1_book_dims(const VpzBook* bk) {
+  return (int)(VPZ_LDG(reinterpret_cast<const uint32_t*>(bk) + 6) & 0xffffu);
+}
+
 VPZ_DEV K1Book k1_book(const uint32_t* blob, const VpzBook* books, int idx) {
   const VpzBook* bk = books + idx;
   K1Book r;
@@ -336,59 +341,76 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
     for (int u = 0; u < nvec * part_count; u++) rec_cls[u] = 0;
     // Flattened walk of  stage -> partition group -> [stage 0: classwords] -> partition -> vector:
     // every trip round the loop below decodes exactly ONE codeword, so lanes that sit at different
-    // places of their packets still execute the same instructions.
-    int stage = 0, gpart = 0, k = 0, v = 0;
-    bool in_class = true;      // stage 0 starts every group with its classwords
-    int rem = 0;               // entries still to decode in the current (partition, vector) unit
+    // places of their packets still execute the same instructions.  Per (group, stage) the units
+    // that actually carry codewords are collected in a bit mask (slot = k * nvec + v, decode
+    // order), so finding the next codeword is a find-first-set, not a scan over idle units.
+    uint32_t vecmask = 0;                  // vectors that are decoded
+    for (int v = 0; v < nvec; v++)
+      if (!((g.skip >> v) & 1u)) vecmask |= 1u << v;
+    int stage = 0, gpart = 0;
+    uint32_t cwmask = vecmask;             // classwords still to read for the current group (stage 0)
+    unsigned long long slotmask = 0;       // units of the current (group, stage) still to decode
+    bool need_build = true;
+    int cw_v = 0;                          // vector of the classword being decoded
+    int dbg_slot = 0;                      // DEBUG: next unit of the group whose class goes to the dump
+    bool in_class = false;
+    int rem = 0;                           // entries still to decode in the current unit
     K1Book cur = cb;
     bool done = max_stages == 0;
     while (!done) {
       if (rem == 0) {
         // ---- find the next codeword to decode ----
-        bool found = false;
-        while (!found && !done) {
-          if (in_class) {
-            while (v < nvec && ((g.skip >> v) & 1u)) v++;
-            if (v < nvec) {
-              cur = cb;
-              found = true;       // classword of vector v for the group starting at gpart
-            } else {
-              in_class = false;
-              k = 0;
-              v = 0;
-            }
-          } else {
-            if (k == cdim || gpart + k >= part_count) {  // group finished
-              gpart += k;
-              if (gpart >= part_count) {
-                gpart = 0;
-                stage++;
-                if (stage >= max_stages) done = true;
+        for (;;) {
+          if (cwmask) {                    // classword of the lowest pending vector
+            cw_v = __ffs((int)cwmask) - 1;
+            cur = cb;
+            in_class = true;
+            break;
+          }
+          in_class = false;
+          if (need_build) {
+            need_build = false;
+            slotmask = 0;
+            for (int k = 0; k < cdim && gpart + k < part_count; k++)
+              for (int v = 0; v < nvec; v++) {
+                if (!((vecmask >> v) & 1u)) continue;
+                const int c = cls[v * part_count + gpart + k];
+                if (((rs->cascade[c] >> stage) & 1u) && rs->has_books[c]) slotmask |= 1ull << (k * nvec + v);
               }
-              in_class = stage == 0;
-              k = 0;
-              v = 0;
-            } else {
-              while (v < nvec && ((g.skip >> v) & 1u)) v++;
-              if (v == nvec) {
-                k++;
-                v = 0;
-              } else {
-                const int part = gpart + k;
-                const int c = cls[v * part_count + part];
-                if (DEBUG && stage == 0) {
-                  if (P.dbg.classes && ncls < P.dbg.classes_cap) P.dbg.classes[ncls] = c;
-                  ncls++;
-                }
-                if (((rs->cascade[c] >> stage) & 1u) && rs->has_books[c]) {
-                  cur = k1_book(blob, books, rs->books[c][stage]);
-                  rem = k1_unit_entries(g.rtype, g.psize, cur.dims);
-                  found = rem > 0;
-                }
-                v++;
-              }
+            dbg_slot = 0;
+          }
+          if (DEBUG && stage == 0) {
+            // the dump lists the class of every unit the reference VISITS, in order, idle ones too
+            const int upto = slotmask ? __ffsll((long long)slotmask) - 1 : cdim * nvec - 1;
+            for (; dbg_slot <= upto; dbg_slot++) {
+              const int k = dbg_slot / nvec, v = dbg_slot - k * nvec;
+              if (gpart + k >= part_count || !((vecmask >> v) & 1u)) continue;
+              if (P.dbg.classes && ncls < P.dbg.classes_cap) P.dbg.classes[ncls] = cls[v * part_count + gpart + k];
+              ncls++;
             }
           }
+          if (slotmask) {
+            const int slot = __ffsll((long long)slotmask) - 1;
+            slotmask &= slotmask - 1;
+            const int k = slot / nvec, v = slot - k * nvec;
+            const int c = cls[v * part_count + gpart + k];
+            cur = k1_book(blob, books, rs->books[c][stage]);
+            rem = k1_unit_entries(g.rtype, g.psize, cur.dims);
+            if (rem > 0) break;
+            continue;
+          }
+          // group finished: next group, next stage
+          gpart += cdim;
+          if (gpart >= part_count) {
+            gpart = 0;
+            stage++;
+            if (stage >= max_stages) {
+              done = true;
+              break;
+            }
+          }
+          if (stage == 0) cwmask = vecmask;
+          need_build = true;
         }
         if (done) break;
       }
@@ -403,10 +425,10 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
         for (int kk = 0; kk < cdim; kk++)
           if (gpart + kk < part_count) {
             const uint8_t c = dmap[sym * cdim + kk];
-            cls[v * part_count + gpart + kk] = c;
-            rec_cls[v * part_count + gpart + kk] = c;
+            cls[cw_v * part_count + gpart + kk] = c;
+            rec_cls[cw_v * part_count + gpart + kk] = c;
           }
-        v++;
+        cwmask &= cwmask - 1;
       } else {
         if (sym < 0) {  // Residue0.cs:195-201: keep what was decoded
           status = 1;
@@ -499,7 +521,7 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
           if (!((g.skip >> v) & 1u)) {
             const int c = rec_cls[v * g.part_count + part];
             if (((rs->cascade[c] >> stage) & 1u) && rs->has_books[c]) {
-              const int dims = (int)(VPZ_LDG(reinterpret_cast<const uint32_t*>(books + rs->books[c][stage]) + 6) & 0xffffu);
+              const int dims = k1_book_dims(books + rs->books[c][stage]);
               cnt = k1_unit_entries(g.rtype, g.psize, dims);
             }
           }
@@ -520,31 +542,55 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
         const int c = rec_cls[v * g.part_count + part];
         if (!(((rs->cascade[c] >> stage) & 1u) && rs->has_books[c])) continue;
         const VpzBook* bk = books + rs->books[c][stage];
-        const int dims = (int)(VPZ_LDG(reinterpret_cast<const uint32_t*>(bk) + 6) & 0xffffu);
+        const int dims = k1_book_dims(bk);
         const float* vq = reinterpret_cast<const float*>(blob + VPZ_LDG(&bk->vq_off));
-        const int cnt = k1_unit_entries(g.rtype, g.psize, dims);
-        uint32_t e = stage_base + (uint32_t)ustart[u];
-        const int offset = g.begin + part * g.psize;
-        const int vbase = v * half;   // rtype 2: v == 0
+        int cnt = k1_unit_entries(g.rtype, g.psize, dims);
+        const uint32_t e0 = stage_base + (uint32_t)ustart[u];
+        if (e0 >= n_ent) continue;
+        if ((uint32_t)cnt > n_ent - e0) cnt = (int)(n_ent - e0);   // truncated packet: keep what was decoded
+        const uint16_t* ep = ent + e0;
+        const int offset = g.begin + part * g.psize + v * half;   // rtype 2: v == 0
         if (g.rtype == 0) {
           // Residue0.WriteVectors (Residue0.cs:208-231), quirk Q6: dims summed into one bin
-          for (int s = 0; s < cnt && e < n_ent; s++, e++) {
-            const float* lk = vq + (size_t)ent[e] * dims;
+          for (int s = 0; s < cnt; s++) {
+            const float* lk = vq + (size_t)ep[s] * dims;
             float r = 0.f;
             for (int d = 0; d < dims; d++) r = __fadd_rn(r, VPZ_LDG(lk + d));
-            if (offset + s < g.vlen) {
-              const int at = k1b_sw(vbase + offset + s);
-              res[at] = __fadd_rn(res[at], r);
+            const int at = k1b_sw(offset + s);
+            res[at] = __fadd_rn(res[at], r);
+          }
+        } else if ((dims == 2 || dims == 4 || dims == 8) && g.psize % dims == 0) {
+          // Residue1.WriteVectors (Residue1.cs:12-34), vector loads; the next entry index is fetched
+          // while the current vector is added.  A bin is touched once per stage, stages in order.
+          uint32_t idx = ep[0];
+          for (int s = 0; s < cnt; s++) {
+            const uint32_t nidx = s + 1 < cnt ? ep[s + 1] : 0u;
+            const float* lk = vq + (size_t)idx * dims;
+            const int o = offset + s * dims;
+            if (dims == 2) {
+              const float2 a = VPZ_LDG(reinterpret_cast<const float2*>(lk));
+              const int a0 = k1b_sw(o), a1 = k1b_sw(o + 1);
+              res[a0] = __fadd_rn(res[a0], a.x);
+              res[a1] = __fadd_rn(res[a1], a.y);
+            } else {
+              for (int d = 0; d < dims; d += 4) {
+                const float4 a = VPZ_LDG(reinterpret_cast<const float4*>(lk + d));
+                const int a0 = k1b_sw(o + d), a1 = k1b_sw(o + d + 1), a2 = k1b_sw(o + d + 2), a3 = k1b_sw(o + d + 3);
+                res[a0] = __fadd_rn(res[a0], a.x);
+                res[a1] = __fadd_rn(res[a1], a.y);
+                res[a2] = __fadd_rn(res[a2], a.z);
+                res[a3] = __fadd_rn(res[a3], a.w);
+              }
             }
+            idx = nidx;
           }
         } else {
-          // Residue1.WriteVectors (Residue1.cs:12-34)
           int i = 0;
-          for (int s = 0; s < cnt && e < n_ent; s++, e++) {
-            const float* lk = vq + (size_t)ent[e] * dims;
+          for (int s = 0; s < cnt; s++) {
+            const float* lk = vq + (size_t)ep[s] * dims;
             for (int d = 0; d < dims; d++, i++) {
-              if (offset + i < g.vlen) {
-                const int at = k1b_sw(vbase + offset + i);
+              if (g.begin + part * g.psize + i < g.vlen) {
+                const int at = k1b_sw(offset + i);
                 res[at] = __fadd_rn(res[at], VPZ_LDG(lk + d));
               }
             }
@@ -583,29 +629,51 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
   }
 
   // ---- floor line render + dB multiply + store (Floor1.cs:222-268, 372-397) -------------------
+  // RenderLineMulti in closed form: after k steps of the DDA  y = y0 + sy * floor(k * |dy| / adx)
+  // (base*k + sy*floor(k*rem/adx) with |dy| = |base|*adx + rem).  k * |dy| < 2^24, so the quotient
+  // comes from one float multiply by 1/adx plus an exact integer correction of +-1.  Lanes walk the
+  // bins 32 at a time; every lane keeps its own (monotone) segment cursor.
   const float* db = reinterpret_cast<const float*>(blob + H->db_off);
   float* out = P.spec + pk.spec_off;
+  uint32_t* sg = reinterpret_cast<uint32_t*>(ustart);   // per segment: x0 | x1 << 16, y0 | (|dy| << 16), sy, 1/adx
   for (int ch = 0; ch < C; ch++) {
     if (!((own_mask >> ch) & 1u)) continue;  // Mapping.cs:185-194: silent channel, K3 sees zeros
     const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
     const int nseg = (int)seg[0];
-    // RenderLineMulti in closed form: after k steps of the DDA
-    // y = y0 + k*base + sy*floor(k*rem/adx), rem = |dy| - |base|*adx
-    for (int s = 0; s < nseg; s++) {
+    __syncwarp();
+    for (int s = lane; s < nseg; s += 32) {
       const uint32_t p0 = seg[1 + s], p1 = seg[2 + s];
       const int x0 = (int)(p0 & 0xffffu), y0 = (int)(short)(p0 >> 16);
       const int x1 = (int)(p1 & 0xffffu), y1 = (int)(short)(p1 >> 16);
       const int dy = y1 - y0, adx = x1 - x0;
-      const int ady = dy < 0 ? -dy : dy;
-      const int sy = dy < 0 ? -1 : 1;
-      const int base = dy / adx;
-      const int rem = ady - (base < 0 ? -base : base) * adx;
-      for (int x = x0 + lane; x < x1; x += 32) {
-        const int kx = x - x0;
-        int y = y0 + kx * base + sy * ((kx * rem) / adx);
-        y = y < 0 ? 0 : (y > 255 ? 255 : y);  // the reference reads the table unchecked (quirk Q2)
-        out[ch * half + x] = __fmul_rn(RES_AT(ch, x), VPZ_LDG(db + y));
+      sg[4 * s] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+      sg[4 * s + 1] = (uint32_t)(y0 & 0xffff) | ((uint32_t)(dy < 0 ? -dy : dy) << 16);
+      sg[4 * s + 2] = dy < 0 ? 1u : 0u;
+      reinterpret_cast<float*>(sg)[4 * s + 3] = 1.0f / (float)(adx > 0 ? adx : 1);
+    }
+    __syncwarp();
+    if (nseg == 0) continue;
+    int si = 0;
+    uint32_t w0 = sg[0], w1 = sg[1], w2 = sg[2];
+    float inv = reinterpret_cast<float*>(sg)[3];
+    const int xend = (int)(sg[4 * (nseg - 1)] >> 16);   // the last segment ends at `half` (or where the floor ends)
+    for (int x = lane; x < xend; x += 32) {
+      while (x >= (int)(w0 >> 16) && si + 1 < nseg) {
+        si++;
+        w0 = sg[4 * si];
+        w1 = sg[4 * si + 1];
+        w2 = sg[4 * si + 2];
+        inv = reinterpret_cast<float*>(sg)[4 * si + 3];
       }
+      const int x0 = (int)(w0 & 0xffffu), adx = (int)(w0 >> 16) - x0;
+      const int y0 = (int)(short)(w1 & 0xffffu), ady = (int)(w1 >> 16);
+      const int t = (x - x0) * ady;
+      int q = (int)((float)t * inv);
+      const int r = t - q * adx;
+      q += r < 0 ? -1 : (r >= adx ? 1 : 0);
+      int y = w2 ? y0 - q : y0 + q;
+      y = y < 0 ? 0 : (y > 255 ? 255 : y);  // the reference reads the table unchecked (quirk Q2)
+      out[ch * half + x] = __fmul_rn(RES_AT(ch, x), VPZ_LDG(db + y));
     }
   }
 #undef RES_AT
