@@ -114,17 +114,17 @@ int launch_k1a(const K1Params& p, bool debug, int blocks, Stream*, std::string&)
 int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream*, std::string&) {
   if (p.n_pkts == 0) return VPZ_OK;
   (void)blocks;
-  emu::launch(1, (unsigned)warps * 32, (size_t)warps * p.smem_words_per_warp * 4, [&] {
+  (void)warps;
+  static uint32_t s_idx;  // the emulator runs one block at a time
+  emu::launch(1, K1B_THREADS, (size_t)p.smem_words_per_warp * 4, [&] {
     uint32_t* smem = (uint32_t*)emu::t_block->smem;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint32_t* my = smem + (size_t)warp * p.smem_words_per_warp;
     for (;;) {
-      uint32_t idx = 0;
-      if (lane == 0) idx = atomicAdd(p.counter + 2, 1u);
-      idx = __shfl_sync(0xffffffffu, idx, 0);
+      __syncthreads();
+      if (threadIdx.x == 0) s_idx = atomicAdd(p.counter + 2, 1u);
+      __syncthreads();
+      const uint32_t idx = s_idx;
       if (idx >= p.n_pkts) break;
-      if (debug) k1b_build_packet<true>(p, idx, my, lane); else k1b_build_packet<false>(p, idx, my, lane);
-      __syncwarp();
+      if (debug) k1b_build_packet<true>(p, idx, smem, (int)threadIdx.x); else k1b_build_packet<false>(p, idx, smem, (int)threadIdx.x);
     }
   });
   return VPZ_OK;

@@ -26,17 +26,16 @@ __global__ void __launch_bounds__(128) vpz_k1a_symbols(K1Params P) {
 }
 
 template <bool DEBUG>
-__global__ void __launch_bounds__(256) vpz_k1b_spectrum(K1Params P) {
+__global__ void __launch_bounds__(K1B_THREADS) vpz_k1b_spectrum(K1Params P) {
   extern __shared__ uint32_t k1_smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint32_t* my = k1_smem + (size_t)warp * P.smem_words_per_warp;
+  __shared__ uint32_t s_idx;
   for (;;) {
-    uint32_t idx = 0;
-    if (lane == 0) idx = atomicAdd(P.counter + 2, 1u);
-    idx = __shfl_sync(0xffffffffu, idx, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) s_idx = atomicAdd(P.counter + 2, 1u);
+    __syncthreads();
+    const uint32_t idx = s_idx;
     if (idx >= P.n_pkts) break;
-    k1b_build_packet<DEBUG>(P, idx, my, lane);
-    __syncwarp();
+    k1b_build_packet<DEBUG>(P, idx, k1_smem, threadIdx.x);
   }
 }
 
@@ -221,15 +220,16 @@ int launch_k1a(const K1Params& p, bool debug, int blocks, Stream* s, std::string
 
 int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err) {
   if (p.n_pkts == 0) return VPZ_OK;
-  size_t smem = (size_t)warps * p.smem_words_per_warp * 4;
+  (void)warps;
+  size_t smem = (size_t)p.smem_words_per_warp * 4;
   if (smem > g_max_smem) {
     err = "K1b shared memory request exceeds the device limit";
     return VPZ_E_UNSUPPORTED;
   }
   if (debug)
-    vpz_k1b_spectrum<true><<<blocks, warps * 32, smem, s->s>>>(p);
+    vpz_k1b_spectrum<true><<<blocks, K1B_THREADS, smem, s->s>>>(p);
   else
-    vpz_k1b_spectrum<false><<<blocks, warps * 32, smem, s->s>>>(p);
+    vpz_k1b_spectrum<false><<<blocks, K1B_THREADS, smem, s->s>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k1b_spectrum", err);
 }

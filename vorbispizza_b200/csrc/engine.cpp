@@ -32,7 +32,7 @@ static size_t max_units(const Setup& st) {
 static uint32_t k1_words(const Setup& st) {
   const VpzSetupHdr* h = st.hdr();
   const size_t n = (size_t)h->channels << (h->log2_size1 - 1);
-  size_t words = n + (n >> 5) + 1 + 512 + 32 + 8;
+  size_t words = n + (n >> 5) + 1 + (512 + 32) + 512 + 512 + 8 + 8;  // res, ustart, uinfo, uvq, scan
   return (uint32_t)((words + 31) & ~(size_t)31);
 }
 
@@ -536,15 +536,11 @@ int batch_decode(vpz_batch* b, int clip) {
     b->launches++;
     ctx->kernel_launches++;
     dev::event_record(ctx->ev[1], st);
-    // K1b: one warp per packet
-    int warps = std::max(1, std::min(8, ctx->k1_warps));
-    size_t smem_block = (size_t)warps * k1w * 4;
-    while (warps > 1 && smem_block > dev::max_smem_per_block()) {
-      warps--;
-      smem_block = (size_t)warps * k1w * 4;
-    }
-    size_t per_sm = std::max<size_t>(1, std::min<size_t>(2048 / (warps * 32), (227 * 1024) / (smem_block + 1024)));
-    size_t blocks = std::min<size_t>((np + warps - 1) / warps, per_sm * (size_t)dev::sm_count());
+    // K1b: one CTA (128 threads) per packet, persistent CTAs fed by a counter
+    const int warps = 4;
+    size_t smem_block = (size_t)k1w * 4;
+    size_t per_sm = std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem_block + 1024)));
+    size_t blocks = std::min<size_t>(np, per_sm * (size_t)dev::sm_count());
     if ((rc = dev::launch_k1b(p, debug, (int)std::max<size_t>(1, blocks), warps, st, err))) return rc;
     b->launches++;
     ctx->kernel_launches++;

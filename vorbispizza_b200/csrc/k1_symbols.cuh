@@ -57,6 +57,7 @@
 #define K1_REC_HDR 4
 #define K1_SEG_WORDS 68
 #define K1_MAX_UNITS 512      // vectors * partitions per packet (setup.cpp refuses more)
+#define K1B_THREADS 128       // K1b: threads (one CTA) per packet
 
 struct K1Bits {
   const uint32_t* w;
@@ -463,9 +464,12 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
 // partition is 16 or 32 floats) on different banks
 VPZ_DEV int k1b_sw(int i) { return i + (i >> 5); }
 
-// Per-warp shared memory (32-bit words): res[sw(C * half_max)] then ustart[K1_MAX_UNITS + 32]
+// One CTA of K1B_THREADS threads per packet.  Shared memory (32-bit words): res[sw(C * half_max)] then
+// ustart[K1_MAX_UNITS + 32] (reused for the floor segments), uinfo[K1_MAX_UNITS], uvq[K1_MAX_UNITS], then
+// 8 words of scan scratch
 template <bool DEBUG>
-VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, int lane) {
+VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, int tid) {
+  const int lane = tid & 31, wid = tid >> 5;
   const VpzPktIn pk = P.pkts[pkt_idx];
   const uint32_t* blob = P.setups[pk.setup_slot];
   const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
@@ -482,8 +486,11 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
 
   float* res = reinterpret_cast<float*>(smem);
   int* ustart = reinterpret_cast<int*>(smem + k1b_sw(C * half_max) + 1);
+  uint32_t* uinfo = reinterpret_cast<uint32_t*>(ustart + K1_MAX_UNITS + 32);
+  uint32_t* uvq = uinfo + K1_MAX_UNITS;
+  int* scan = reinterpret_cast<int*>(uvq + K1_MAX_UNITS);
 
-  if (lane == 0) {
+  if (tid == 0) {
     VpzPktRes r;
     r.exec_mask = (uint8_t)own_mask;
     r.status = (uint8_t)((hdr >> 16) & 0xffu);
@@ -502,10 +509,10 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
   const K1ResGeom g = k1_res_geom(rs, C, half, noexec);
 
   const int total = C * half;
-  for (int i = lane; i < total; i += 32) res[k1b_sw(i)] = 0.f;
-  __syncwarp();
+  for (int i = tid; i < total; i += K1B_THREADS) res[k1b_sw(i)] = 0.f;
+  __syncthreads();
 
-  // ---- residue: stage by stage, every lane owns whole (partition, vector) units ----------------
+  // ---- residue: stage by stage, per stage: unit scan, then entry-parallel accumulate --------------
   if (g.part_count > 0 && g.any && n_ent > 0) {
     const uint8_t* rec_cls = reinterpret_cast<const uint8_t*>(rec + K1_REC_HDR + C * K1_SEG_WORDS);
     const int nunits = g.part_count * g.nvec;       // decode order inside a stage: partition major
@@ -513,16 +520,20 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
     for (int stage = 0; stage < rs->max_stages && stage_base < n_ent; stage++) {
       // entries per unit -> exclusive prefix sum = where each unit's entries start
       uint32_t carry = 0;
-      for (int u0 = 0; u0 < nunits; u0 += 32) {
-        const int u = u0 + lane;
+      for (int u0 = 0; u0 < nunits; u0 += K1B_THREADS) {
+        const int u = u0 + tid;
         int cnt = 0;
+        uint32_t info = 0, vqoff = 0;   // info: dims | first bin << 8
         if (u < nunits) {
           const int part = u / g.nvec, v = u - part * g.nvec;
           if (!((g.skip >> v) & 1u)) {
             const int c = rec_cls[v * g.part_count + part];
             if (((rs->cascade[c] >> stage) & 1u) && rs->has_books[c]) {
-              const int dims = k1_book_dims(books + rs->books[c][stage]);
+              const VpzBook* bk = books + rs->books[c][stage];
+              const int dims = k1_book_dims(bk);
               cnt = k1_unit_entries(g.rtype, g.psize, dims);
+              vqoff = VPZ_LDG(&bk->vq_off);
+              info = (uint32_t)(dims & 0xff) | ((uint32_t)(g.begin + part * g.psize + v * half) << 8);   // rtype 2: v == 0
             }
           }
         }
@@ -532,89 +543,96 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
           int n = __shfl_up_sync(0xffffffffu, incl, d);
           if (lane >= d) incl += n;
         }
-        if (u < nunits) ustart[u] = (int)carry + incl - cnt;
-        carry += (uint32_t)__shfl_sync(0xffffffffu, incl, 31);
+        if (lane == 31) scan[wid] = incl;
+        __syncthreads();
+        int before = 0, round_total = 0;
+#pragma unroll
+        for (int w = 0; w < K1B_THREADS / 32; w++) {
+          const int t = scan[w];
+          if (w < wid) before += t;
+          round_total += t;
+        }
+        if (u < nunits) {
+          ustart[u] = (int)carry + before + incl - cnt;
+          uinfo[u] = info;
+          uvq[u] = vqoff;
+        }
+        carry += (uint32_t)round_total;
+        __syncthreads();
       }
-      __syncwarp();
-      for (int u = lane; u < nunits; u += 32) {
-        const int part = u / g.nvec, v = u - part * g.nvec;
-        if ((g.skip >> v) & 1u) continue;
-        const int c = rec_cls[v * g.part_count + part];
-        if (!(((rs->cascade[c] >> stage) & 1u) && rs->has_books[c])) continue;
-        const VpzBook* bk = books + rs->books[c][stage];
-        const int dims = k1_book_dims(bk);
-        const float* vq = reinterpret_cast<const float*>(blob + VPZ_LDG(&bk->vq_off));
-        int cnt = k1_unit_entries(g.rtype, g.psize, dims);
-        const uint32_t e0 = stage_base + (uint32_t)ustart[u];
-        if (e0 >= n_ent) continue;
-        if ((uint32_t)cnt > n_ent - e0) cnt = (int)(n_ent - e0);   // truncated packet: keep what was decoded
-        const uint16_t* ep = ent + e0;
-        const int offset = g.begin + part * g.psize + v * half;   // rtype 2: v == 0
+      // ---- every thread takes single ENTRIES (codewords) of the stage, not whole units: the work is
+      // spread evenly however the active units are distributed.  The unit of entry e is the last one
+      // whose start is <= e (idle units have zero length and sort before the active unit that shares
+      // their start).  A bin is touched once per stage and the stages run in order, so the sums
+      // round exactly like the reference's stage-major accumulation.
+      uint32_t stage_n = carry;
+      if (stage_base + stage_n > n_ent) stage_n = n_ent - stage_base;   // truncated packet: keep what was decoded
+      const uint16_t* ep = ent + stage_base;
+      for (uint32_t e = (uint32_t)tid; e < stage_n; e += K1B_THREADS) {
+        int lo = 0, hi = nunits;   // ustart[lo] <= e < ustart[hi] (virtual ustart[nunits] = +inf)
+        while (hi - lo > 1) {
+          const int mid = (lo + hi) >> 1;
+          if ((uint32_t)ustart[mid] <= e) lo = mid; else hi = mid;
+        }
+        const uint32_t info = uinfo[lo];
+        const int dims = (int)(info & 0xffu);
+        const int si = (int)(e - (uint32_t)ustart[lo]);        // index of the entry inside its unit
+        const int dest = (int)(info >> 8);                     // first bin of the unit
+        const float* lk = reinterpret_cast<const float*>(blob + uvq[lo]) + (size_t)ep[e] * dims;
         if (g.rtype == 0) {
           // Residue0.WriteVectors (Residue0.cs:208-231), quirk Q6: dims summed into one bin
-          for (int s = 0; s < cnt; s++) {
-            const float* lk = vq + (size_t)ep[s] * dims;
-            float r = 0.f;
-            for (int d = 0; d < dims; d++) r = __fadd_rn(r, VPZ_LDG(lk + d));
-            const int at = k1b_sw(offset + s);
-            res[at] = __fadd_rn(res[at], r);
-          }
-        } else if ((dims == 2 || dims == 4 || dims == 8) && g.psize % dims == 0) {
-          // Residue1.WriteVectors (Residue1.cs:12-34), vector loads; the next entry index is fetched
-          // while the current vector is added.  A bin is touched once per stage, stages in order.
-          uint32_t idx = ep[0];
-          for (int s = 0; s < cnt; s++) {
-            const uint32_t nidx = s + 1 < cnt ? ep[s + 1] : 0u;
-            const float* lk = vq + (size_t)idx * dims;
-            const int o = offset + s * dims;
-            if (dims == 2) {
-              const float2 a = VPZ_LDG(reinterpret_cast<const float2*>(lk));
-              const int a0 = k1b_sw(o), a1 = k1b_sw(o + 1);
-              res[a0] = __fadd_rn(res[a0], a.x);
-              res[a1] = __fadd_rn(res[a1], a.y);
-            } else {
-              for (int d = 0; d < dims; d += 4) {
-                const float4 a = VPZ_LDG(reinterpret_cast<const float4*>(lk + d));
-                const int a0 = k1b_sw(o + d), a1 = k1b_sw(o + d + 1), a2 = k1b_sw(o + d + 2), a3 = k1b_sw(o + d + 3);
-                res[a0] = __fadd_rn(res[a0], a.x);
-                res[a1] = __fadd_rn(res[a1], a.y);
-                res[a2] = __fadd_rn(res[a2], a.z);
-                res[a3] = __fadd_rn(res[a3], a.w);
-              }
-            }
-            idx = nidx;
+          float r = 0.f;
+          for (int d = 0; d < dims; d++) r = __fadd_rn(r, VPZ_LDG(lk + d));
+          const int at = k1b_sw(dest + si);
+          res[at] = __fadd_rn(res[at], r);
+        } else if (dims == 2) {
+          // Residue1.WriteVectors (Residue1.cs:12-34)
+          const float2 v2 = VPZ_LDG(reinterpret_cast<const float2*>(lk));
+          const int o = dest + si * 2;
+          const int a0 = k1b_sw(o), a1 = k1b_sw(o + 1);
+          res[a0] = __fadd_rn(res[a0], v2.x);
+          res[a1] = __fadd_rn(res[a1], v2.y);
+        } else if (dims == 4 || dims == 8) {
+          const int o = dest + si * dims;
+          for (int d = 0; d < dims; d += 4) {
+            const float4 v4 = VPZ_LDG(reinterpret_cast<const float4*>(lk + d));
+            const int a0 = k1b_sw(o + d), a1 = k1b_sw(o + d + 1), a2 = k1b_sw(o + d + 2), a3 = k1b_sw(o + d + 3);
+            res[a0] = __fadd_rn(res[a0], v4.x);
+            res[a1] = __fadd_rn(res[a1], v4.y);
+            res[a2] = __fadd_rn(res[a2], v4.z);
+            res[a3] = __fadd_rn(res[a3], v4.w);
           }
         } else {
-          int i = 0;
-          for (int s = 0; s < cnt; s++) {
-            const float* lk = vq + (size_t)ep[s] * dims;
-            for (int d = 0; d < dims; d++, i++) {
-              if (g.begin + part * g.psize + i < g.vlen) {
-                const int at = k1b_sw(offset + i);
-                res[at] = __fadd_rn(res[at], VPZ_LDG(lk + d));
-              }
+          // any other dimension; the last entry of a unit may run past the partition when dims does
+          // not divide it, and the reference then keeps writing (bounded by the vector length)
+          const int vend = g.rtype == 2 ? g.vlen : (dest / half) * half + half;
+          for (int d = 0; d < dims; d++) {
+            const int o = dest + si * dims + d;
+            if (o < vend) {
+              const int at = k1b_sw(o);
+              res[at] = __fadd_rn(res[at], VPZ_LDG(lk + d));
             }
           }
         }
       }
       stage_base += carry;
-      __syncwarp();
+      __syncthreads();
     }
   }
-  __syncwarp();
+  __syncthreads();
 
   // accessor of channel c, bin i after the Residue2 de-interleave (Residue2.cs:42-50)
 #define RES_AT(c, i) res[k1b_sw(g.rtype == 2 ? (i) * C + (c) : (c) * half + (i))]
 
   if (DEBUG && P.dbg.residue) {
     for (int c = 0; c < C; c++)
-      for (int i = lane; i < half; i += 32) P.dbg.residue[c * half + i] = RES_AT(c, i);
+      for (int i = tid; i < half; i += K1B_THREADS) P.dbg.residue[c * half + i] = RES_AT(c, i);
   }
 
   // ---- inverse coupling, last step first (Mapping.cs:166-172, 235-267) ----------------------
   for (int s = mp->coupling_steps - 1; s >= 0; s--) {
     const int cm = mp->mag[s], ca = mp->ang[s];
-    for (int i = lane; i < half; i += 32) {
+    for (int i = tid; i < half; i += K1B_THREADS) {
       float m = RES_AT(cm, i), a = RES_AT(ca, i);
       float nm = m, na = m;
       if (m > 0.f) {
@@ -625,14 +643,14 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
       RES_AT(cm, i) = nm;
       RES_AT(ca, i) = na;
     }
-    __syncwarp();
+    __syncthreads();
   }
 
   // ---- floor line render + dB multiply + store (Floor1.cs:222-268, 372-397) -------------------
   // RenderLineMulti in closed form: after k steps of the DDA  y = y0 + sy * floor(k * |dy| / adx)
   // (base*k + sy*floor(k*rem/adx) with |dy| = |base|*adx + rem).  k * |dy| < 2^24, so the quotient
   // comes from one float multiply by 1/adx plus an exact integer correction of +-1.  Lanes walk the
-  // bins 32 at a time; every lane keeps its own (monotone) segment cursor.
+  // bins K1B_THREADS at a time; every thread keeps its own (monotone) segment cursor.
   const float* db = reinterpret_cast<const float*>(blob + H->db_off);
   float* out = P.spec + pk.spec_off;
   uint32_t* sg = reinterpret_cast<uint32_t*>(ustart);   // per segment: x0 | x1 << 16, y0 | (|dy| << 16), sy, 1/adx
@@ -640,8 +658,8 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
     if (!((own_mask >> ch) & 1u)) continue;  // Mapping.cs:185-194: silent channel, K3 sees zeros
     const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
     const int nseg = (int)seg[0];
-    __syncwarp();
-    for (int s = lane; s < nseg; s += 32) {
+    __syncthreads();
+    for (int s = tid; s < nseg; s += K1B_THREADS) {
       const uint32_t p0 = seg[1 + s], p1 = seg[2 + s];
       const int x0 = (int)(p0 & 0xffffu), y0 = (int)(short)(p0 >> 16);
       const int x1 = (int)(p1 & 0xffffu), y1 = (int)(short)(p1 >> 16);
@@ -651,13 +669,13 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
       sg[4 * s + 2] = dy < 0 ? 1u : 0u;
       reinterpret_cast<float*>(sg)[4 * s + 3] = 1.0f / (float)(adx > 0 ? adx : 1);
     }
-    __syncwarp();
+    __syncthreads();
     if (nseg == 0) continue;
     int si = 0;
     uint32_t w0 = sg[0], w1 = sg[1], w2 = sg[2];
     float inv = reinterpret_cast<float*>(sg)[3];
     const int xend = (int)(sg[4 * (nseg - 1)] >> 16);   // the last segment ends at `half` (or where the floor ends)
-    for (int x = lane; x < xend; x += 32) {
+    for (int x = tid; x < xend; x += K1B_THREADS) {
       while (x >= (int)(w0 >> 16) && si + 1 < nseg) {
         si++;
         w0 = sg[4 * si];
@@ -677,5 +695,5 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
     }
   }
 #undef RES_AT
-  __syncwarp();
+  __syncthreads();
 }

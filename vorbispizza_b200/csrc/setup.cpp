@@ -595,6 +595,11 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
     VpzBook& d = dbooks[i];
     memset(&d, 0, sizeof(d));
     d.entries = (uint32_t)books[i].entries;
+    if (books[i].map_type != 0 && (books[i].entries > 65535 || books[i].dims > 255)) {
+      // K1a stores VQ entry indices as uint16 and K1b packs the dimension in 8 bits
+      error = "VQ codebook with more than 65535 entries or 255 dimensions is not on the GPU path";
+      return VPZ_E_UNSUPPORTED;
+    }
     d.dims = (uint16_t)books[i].dims;
     d.max_bits = (uint8_t)books[i].max_bits;
     d.map_type = (uint8_t)books[i].map_type;
