@@ -97,6 +97,7 @@ inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
   return (uint32_t)(v >> sh);
 }
 inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 inline uint32_t __brev(uint32_t n) {
   n = ((n & 0xAAAAAAAAu) >> 1) | ((n & 0x55555555u) << 1);

@@ -114,18 +114,10 @@ int launch_k1a(const K1Params& p, bool debug, int blocks, Stream*, std::string&)
 int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream*, std::string&) {
   if (p.n_pkts == 0) return VPZ_OK;
   (void)blocks;
-  (void)warps;
   static uint32_t s_idx;  // the emulator runs one block at a time
-  emu::launch(1, K1B_THREADS, (size_t)p.smem_words_per_warp * 4, [&] {
+  emu::launch(1, K1B_THREADS, (size_t)p.smem_words_per_warp * 4 * (p.gather_ok ? warps : 1), [&] {
     uint32_t* smem = (uint32_t*)emu::t_block->smem;
-    for (;;) {
-      __syncthreads();
-      if (threadIdx.x == 0) s_idx = atomicAdd(p.counter + 2, 1u);
-      __syncthreads();
-      const uint32_t idx = s_idx;
-      if (idx >= p.n_pkts) break;
-      if (debug) k1b_build_packet<true>(p, idx, smem, (int)threadIdx.x); else k1b_build_packet<false>(p, idx, smem, (int)threadIdx.x);
-    }
+    if (debug) k1b_cta_loop<true>(p, smem, &s_idx); else k1b_cta_loop<false>(p, smem, &s_idx);
   });
   return VPZ_OK;
 }

@@ -29,14 +29,7 @@ template <bool DEBUG>
 __global__ void __launch_bounds__(K1B_THREADS) vpz_k1b_spectrum(K1Params P) {
   extern __shared__ uint32_t k1_smem[];
   __shared__ uint32_t s_idx;
-  for (;;) {
-    __syncthreads();
-    if (threadIdx.x == 0) s_idx = atomicAdd(P.counter + 2, 1u);
-    __syncthreads();
-    const uint32_t idx = s_idx;
-    if (idx >= P.n_pkts) break;
-    k1b_build_packet<DEBUG>(P, idx, k1_smem, threadIdx.x);
-  }
+  k1b_cta_loop<DEBUG>(P, k1_smem, &s_idx);
 }
 
 template <bool FAST>
@@ -220,8 +213,8 @@ int launch_k1a(const K1Params& p, bool debug, int blocks, Stream* s, std::string
 
 int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err) {
   if (p.n_pkts == 0) return VPZ_OK;
-  (void)warps;
-  size_t smem = (size_t)p.smem_words_per_warp * 4;
+  // gather path: smem_words_per_warp per warp; general path: per CTA
+  size_t smem = (size_t)p.smem_words_per_warp * 4 * (p.gather_ok ? warps : 1);
   if (smem > g_max_smem) {
     err = "K1b shared memory request exceeds the device limit";
     return VPZ_E_UNSUPPORTED;

@@ -47,6 +47,35 @@ static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
       return VPZ_E_UNSUPPORTED;
     }
     s->k1_words_per_warp = k1_words(s->host);
+    // K1b gather path (k1_symbols.cuh): mono / stereo, residue 1 / 2, VQ dimensions that divide the
+    // partition size and, for the interleaved type 2 vector of a stereo stream, are even
+    {
+      const Setup& st = s->host;
+      const int C = h->channels;
+      const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(st.blob.data() + h->residues_off);
+      const VpzBook* bk = reinterpret_cast<const VpzBook*>(st.blob.data() + h->books_off);
+      bool ok = C <= 2 && h->nbooks <= 256 && h->log2_size0 >= 5;
+      int max_stages = 1;
+      for (int i = 0; i < h->nresidues && ok; i++) {
+        if (rs[i].type != 1 && rs[i].type != 2) ok = false;
+        // a thread gathers chunks of 8 positions (16 for the interleaved stereo vector): chunks must
+        // not straddle partitions and every VQ dimension must be a power of two that divides the chunk
+        const int chunk = rs[i].type == 2 && C == 2 ? 16 : 8;
+        if ((rs[i].begin % chunk) || (rs[i].part_size % chunk)) ok = false;
+        max_stages = std::max<int>(max_stages, rs[i].max_stages);
+        for (int c = 0; c < rs[i].classifications && ok; c++)
+          for (int sg = 0; sg < 8 && ok; sg++)
+            if (((rs[i].cascade[c] >> sg) & 1) && rs[i].has_books[c]) {
+              const int dims = bk[rs[i].books[c][sg]].dims;
+              if (dims < 1 || (dims & (dims - 1)) || dims > chunk) ok = false;
+            }
+      }
+      s->gather_ok = ok;
+      const size_t U = (units + 31) & ~(size_t)31;
+      const size_t half_max = (size_t)1 << (h->log2_size1 - 1);
+      // k1b gather layout per warp: urec stages*U*4 + ybuf C*half_max/4 + sg C*4*66 (+ pad, multiple of 32)
+      s->k1g_words = (uint32_t)(((size_t)max_stages * U * 4 + (size_t)C * half_max / 4 + (size_t)C * 4 * 66 + 8 + 31) & ~(size_t)31);
+    }
     s->rec_words = (uint32_t)(4 + h->channels * 68 + (units + 3) / 4 + 1);  // K1_REC_HDR, K1_SEG_WORDS
   }
   size_t bytes = s->host.blob.size() * 4;
@@ -507,10 +536,12 @@ int batch_decode(vpz_batch* b, int clip) {
   int rc;
   b->launches = 0;
   dev::event_record(ctx->ev[0], st);
-  bool fast = true;
-  uint32_t k1w = 0, k3f = 0;
+  bool fast = true, gather = true;
+  uint32_t k1w = 0, k1g = 0, k3f = 0;
   for (vpz_setup* s : b->slots) {
     fast = fast && s->fast_sizes;
+    gather = gather && s->gather_ok;
+    k1g = std::max(k1g, s->k1g_words);
     k1w = std::max(k1w, s->k1_words_per_warp);
     k3f = std::max(k3f, s->k3_floats_per_ch);
   }
@@ -524,6 +555,8 @@ int batch_decode(vpz_batch* b, int clip) {
     p.spec = static_cast<float*>(b->d_spec.p);
     p.n_pkts = (uint32_t)np;
     p.counter = ctx->d_counter;
+    p.gather_ok = gather ? 1 : 0;
+    if (gather) k1w = k1g;   // the gather path needs only its index tables
     p.smem_words_per_warp = k1w;
     p.rec = static_cast<uint32_t*>(b->d_rec.p);
     p.ent = static_cast<uint16_t*>(b->d_ent.p);
@@ -536,11 +569,12 @@ int batch_decode(vpz_batch* b, int clip) {
     b->launches++;
     ctx->kernel_launches++;
     dev::event_record(ctx->ev[1], st);
-    // K1b: one CTA (128 threads) per packet, persistent CTAs fed by a counter
+    // K1b: persistent CTAs of 4 warps fed by a counter; gather path = one warp per packet (shared
+    // memory per warp), general path = one CTA per packet
     const int warps = 4;
-    size_t smem_block = (size_t)k1w * 4;
+    size_t smem_block = (size_t)k1w * 4 * (gather ? warps : 1);
     size_t per_sm = std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem_block + 1024)));
-    size_t blocks = std::min<size_t>(np, per_sm * (size_t)dev::sm_count());
+    size_t blocks = std::min<size_t>(gather ? (np + warps - 1) / warps : np, per_sm * (size_t)dev::sm_count());
     if ((rc = dev::launch_k1b(p, debug, (int)std::max<size_t>(1, blocks), warps, st, err))) return rc;
     b->launches++;
     ctx->kernel_launches++;

@@ -25,6 +25,7 @@ struct K1Params {
   uint32_t* rec;                 // symbol records (K1a -> K1b), VpzPktIn.rec_off
   uint16_t* ent;                 // VQ entry indices (K1a -> K1b), VpzPktIn.ent_off
   const uint32_t* order;         // K1a: packet indices sorted by byte length (neighbouring lanes get like work)
+  int gather_ok;                 // K1b: every setup of the batch can take the gather path
   K1Debug dbg;
 };
 

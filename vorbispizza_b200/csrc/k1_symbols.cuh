@@ -464,11 +464,12 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
 // partition is 16 or 32 floats) on different banks
 VPZ_DEV int k1b_sw(int i) { return i + (i >> 5); }
 
+// GENERAL path (any channel count, residue type 0, dimensions that do not divide the partition):
 // One CTA of K1B_THREADS threads per packet.  Shared memory (32-bit words): res[sw(C * half_max)] then
 // ustart[K1_MAX_UNITS + 32] (reused for the floor segments), uinfo[K1_MAX_UNITS], uvq[K1_MAX_UNITS], then
 // 8 words of scan scratch
 template <bool DEBUG>
-VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, int tid) {
+VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, int tid) {
   const int lane = tid & 31, wid = tid >> 5;
   const VpzPktIn pk = P.pkts[pkt_idx];
   const uint32_t* blob = P.setups[pk.setup_slot];
@@ -696,4 +697,400 @@ VPZ_DEV void k1b_build_packet(const K1Params& P, uint32_t pkt_idx, uint32_t* sme
   }
 #undef RES_AT
   __syncthreads();
+}
+
+// =============================================================================================
+// K1b, gather path (mono / stereo, residue 1 / 2, partitions aligned to 8 / 16 positions, power-of-two
+// VQ dimensions): no residue buffer at all.  Every thread owns 8 CONSECUTIVE FREQUENCY BINS (for the
+// interleaved type 2 vector of a stereo stream: the 16 positions 2x .. 2x+15, both channels).  Such
+// a chunk lies inside one partition, so per stage ONE lookup finds the unit, its first entry and its
+// VQ table; the 16/dims entries that cover the chunk are fetched and summed into registers in stage
+// order -- the same rounded sums as the reference's stage-major accumulation into a zeroed buffer.
+// Inverse coupling, floor multiply and two 128-bit stores per channel follow.  The floor curve is
+// rendered beforehand by an exact integer DDA (RenderLineMulti, Floor1.cs:372-397), 16 bins per
+// thread, into one byte per bin of shared memory.
+//   per-warp words: urec[stages][U][4] | per channel ybuf[half_max/4] | sg[C][4*66]
+// =============================================================================================
+
+struct K1Gather {
+  const uint32_t* urec;       // [stage][U][4]: info (0 idle; dims | log2 dims << 8), first entry (absolute), vq word offset
+  const uint32_t* blob;
+  const uint16_t* ent;
+  uint32_t n_ent;
+  int max_stages, U, nvec, begin, psize, pshift, span;   // span = part_count * psize
+};
+
+// acc[0..CH) += the VQ components of positions p .. p+CH-1 of vector v, stage after stage.
+// CH = 16 (stereo type 2: 8 bins of both channels) or 8; p - begin is a multiple of CH.
+template <int CH>
+VPZ_DEV void k1g_fetch_chunk(const K1Gather& G, int v, int p, float* acc) {
+  const int rel = p - G.begin;
+  if (rel < 0 || rel >= G.span) return;
+  const int part = G.pshift >= 0 ? (rel >> G.pshift) : rel / G.psize;
+  const int off = rel - part * G.psize;
+  const int u = part * G.nvec + v;
+  for (int s = 0; s < G.max_stages; s++) {
+    const uint32_t* R = G.urec + (size_t)(s * G.U + u) * 4;
+    const uint32_t info = R[0];
+    if (!info) continue;
+    const int dsh = (int)((info >> 8) & 0xfu);
+    const uint32_t e0 = R[1] + (uint32_t)(off >> dsh);
+    const float* vq = reinterpret_cast<const float*>(G.blob + R[2]);
+    const uint16_t* ep = G.ent + e0;
+    const uint32_t left = e0 < G.n_ent ? G.n_ent - e0 : 0u;   // truncated packet: keep what was decoded
+    if (dsh == 1) {
+#pragma unroll
+      for (int k = 0; k < CH / 2; k++)
+        if ((uint32_t)k < left) {
+          const float2 t = VPZ_LDG(reinterpret_cast<const float2*>(vq + (size_t)ep[k] * 2));
+          acc[2 * k] = __fadd_rn(acc[2 * k], t.x);
+          acc[2 * k + 1] = __fadd_rn(acc[2 * k + 1], t.y);
+        }
+    } else if (dsh == 2) {
+#pragma unroll
+      for (int k = 0; k < CH / 4; k++)
+        if ((uint32_t)k < left) {
+          const float4 t = VPZ_LDG(reinterpret_cast<const float4*>(vq + (size_t)ep[k] * 4));
+          acc[4 * k] = __fadd_rn(acc[4 * k], t.x);
+          acc[4 * k + 1] = __fadd_rn(acc[4 * k + 1], t.y);
+          acc[4 * k + 2] = __fadd_rn(acc[4 * k + 2], t.z);
+          acc[4 * k + 3] = __fadd_rn(acc[4 * k + 3], t.w);
+        }
+    } else if (dsh == 3) {
+#pragma unroll
+      for (int k = 0; k < CH / 8; k++)
+        if ((uint32_t)k < left) {
+          const float* lk = vq + (size_t)ep[k] * 8;
+#pragma unroll
+          for (int d = 0; d < 8; d += 4) {
+            const float4 t = VPZ_LDG(reinterpret_cast<const float4*>(lk + d));
+            acc[8 * k + d] = __fadd_rn(acc[8 * k + d], t.x);
+            acc[8 * k + d + 1] = __fadd_rn(acc[8 * k + d + 1], t.y);
+            acc[8 * k + d + 2] = __fadd_rn(acc[8 * k + d + 2], t.z);
+            acc[8 * k + d + 3] = __fadd_rn(acc[8 * k + d + 3], t.w);
+          }
+        }
+    } else if (dsh == 0) {
+#pragma unroll
+      for (int k = 0; k < CH; k++)
+        if ((uint32_t)k < left) acc[k] = __fadd_rn(acc[k], VPZ_LDG(vq + ep[k]));
+    } else if (CH == 16 && dsh == 4) {
+      if (left > 0) {
+        const float* lk = vq + (size_t)ep[0] * 16;
+#pragma unroll
+        for (int d = 0; d < 16; d += 4) {
+          const float4 t = VPZ_LDG(reinterpret_cast<const float4*>(lk + d));
+          acc[d] = __fadd_rn(acc[d], t.x);
+          acc[d + 1] = __fadd_rn(acc[d + 1], t.y);
+          acc[d + 2] = __fadd_rn(acc[d + 2], t.z);
+          acc[d + 3] = __fadd_rn(acc[d + 3], t.w);
+        }
+      }
+    }
+  }
+}
+
+// Inverse square-polar coupling of one (magnitude, angle) pair (Mapping.cs:235-267)
+VPZ_DEV void k1_uncouple(float& m, float& a) {
+  float nm = m, na = m;
+  if (m > 0.f) {
+    if (a > 0.f) na = __fsub_rn(m, a); else nm = __fadd_rn(m, a);
+  } else {
+    if (a > 0.f) na = __fadd_rn(m, a); else nm = __fsub_rn(m, a);
+  }
+  m = nm;
+  a = na;
+}
+
+template <bool DEBUG>
+VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, int tid) {
+  const int lane = tid;   // ONE WARP per packet: many packets in flight per SM hide the per-packet load latency
+  const VpzPktIn pk = P.pkts[pkt_idx];
+  const uint32_t* blob = P.setups[pk.setup_slot];
+  const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
+  const int C = H->channels;
+  const VpzBook* books = reinterpret_cast<const VpzBook*>(blob + H->books_off);
+  const int half_max = 1 << (H->log2_size1 - 1);
+  const uint32_t* rec = P.rec + pk.rec_off;
+  const uint32_t hdr = rec[0];
+  const uint32_t own_mask = hdr & 0xffu, noexec = (hdr >> 8) & 0xffu;
+  const int long_block = (int)(hdr >> 24) & 1;
+  const int half = long_block ? half_max : (1 << (H->log2_size0 - 1));
+
+  if (tid == 0) {
+    VpzPktRes r;
+    r.exec_mask = (uint8_t)own_mask;
+    r.status = (uint8_t)((hdr >> 16) & 0xffu);
+    r.bits_used_lo = (uint16_t)rec[2];
+    P.res[pkt_idx] = r;
+  }
+  if (own_mask == 0 && !(DEBUG && P.dbg.residue)) return;  // every channel silent: K3 outputs zeros
+
+  const uint32_t w0 = VPZ_LDG(P.bytes + (pk.byte_off >> 2));
+  const int mode_idx = (int)((w0 >> 1) & ((1u << H->mode_bits) - 1u));
+  const VpzMode* modes = reinterpret_cast<const VpzMode*>(blob + H->modes_off);
+  const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + modes[mode_idx].mapping;
+  const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(blob + H->residues_off) + mp->submap_residue[0];
+  const K1ResGeom g = k1_res_geom(rs, C, half, noexec);
+  const int nunits = g.part_count * g.nvec;
+  const int U = (nunits + 31) & ~31;
+  const int max_stages = rs->max_stages;
+
+  const float* dbtab = reinterpret_cast<const float*>(blob + H->db_off);   // 1 KB, L1 resident
+  uint32_t* urec = smem;
+  uint8_t* ybuf = reinterpret_cast<uint8_t*>(urec + (size_t)max_stages * U * 4);   // [C][half_max] bytes
+  uint32_t* sgbase = reinterpret_cast<uint32_t*>(ybuf) + (C * half_max) / 4;        // [C][4*66]
+
+  K1Gather G;
+  G.urec = urec;
+  G.blob = blob;
+  G.ent = P.ent + pk.ent_off;
+  G.n_ent = rec[1];
+  G.max_stages = max_stages;
+  G.U = U;
+  G.nvec = g.nvec;
+  G.begin = g.begin;
+  G.psize = g.psize;
+  G.pshift = (g.psize & (g.psize - 1)) == 0 ? 31 - __clz(g.psize) : -1;
+  G.span = g.part_count * g.psize;
+  const bool have_res = g.part_count > 0 && g.any && G.n_ent > 0;
+
+  // ---- phase A: floor segments of every channel with energy ------------------------------------
+  for (int ch = 0; ch < C; ch++) {
+    if (!((own_mask >> ch) & 1u)) continue;
+    const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
+    uint32_t* sg = sgbase + ch * 4 * 66;
+    const int nseg = (int)seg[0];
+    for (int s = tid; s < nseg; s += 32) {
+      const uint32_t p0 = seg[1 + s], p1 = seg[2 + s];
+      const int x0 = (int)(p0 & 0xffffu), y0 = (int)(short)(p0 >> 16);
+      const int x1 = (int)(p1 & 0xffffu), y1 = (int)(short)(p1 >> 16);
+      const int dy = y1 - y0, adx = x1 - x0;
+      const int ady = dy < 0 ? -dy : dy;
+      const int base = adx > 0 ? ady / adx : 0;
+      sg[4 * s] = (uint32_t)x0 | ((uint32_t)x1 << 16);
+      sg[4 * s + 1] = (uint32_t)(y0 & 0xffff) | ((uint32_t)base << 16);          // |base| of the DDA
+      sg[4 * s + 2] = (uint32_t)(ady - base * adx) | (dy < 0 ? 0x80000000u : 0u); // remainder step, sign
+      sg[4 * s + 3] = 0;
+    }
+  }
+
+  // ---- phase B: per unit and stage, how many entries it holds -> first entry (all stages at once) ----
+  if (have_res) {
+    const uint8_t* rec_cls = reinterpret_cast<const uint8_t*>(rec + K1_REC_HDR + C * K1_SEG_WORDS);
+    int carry[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) carry[s] = 0;
+    for (int u0 = 0; u0 < nunits; u0 += 32) {
+      const int u = u0 + tid;
+      int cnt[8];
+      uint32_t info[8], vqo[8];
+      int c = -1;
+      if (u < nunits) {
+        const int part = u / g.nvec, v = u - part * g.nvec;
+        if (!((g.skip >> v) & 1u)) c = rec_cls[v * g.part_count + part];
+      }
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        cnt[s] = 0;
+        info[s] = vqo[s] = 0;
+        if (s < max_stages) {
+          if (c >= 0 && ((rs->cascade[c] >> s) & 1u) && rs->has_books[c]) {
+            const int book = rs->books[c][s];
+            const int dims = k1_book_dims(books + book);
+            cnt[s] = k1_unit_entries(g.rtype, g.psize, dims);
+            if (cnt[s] > 0) {
+              info[s] = (uint32_t)(dims & 0xff) | ((uint32_t)(31 - __clz(dims)) << 8);   // dims is a power of two (host-checked)
+              vqo[s] = VPZ_LDG(&books[book].vq_off);
+            }
+          }
+          int incl = cnt[s];
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+          }
+          const int round_total = __shfl_sync(0xffffffffu, incl, 31);
+          cnt[s] = carry[s] + incl - cnt[s];   // first entry of the unit inside the stage
+          carry[s] += round_total;
+        }
+      }
+      // absolute first entry = entries of all earlier stages + offset inside the stage; the stage
+      // totals are only complete after the last round, so the stage bases are added below
+      if (u < nunits) {
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+          if (s < max_stages) {
+            uint32_t* R = urec + (size_t)(s * U + u) * 4;
+            R[0] = info[s];
+            R[1] = (uint32_t)cnt[s];
+            R[2] = vqo[s];
+          }
+      }
+      __syncwarp();
+    }
+    // add the stage bases
+    uint32_t sbase[8];
+    uint32_t acc = 0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      sbase[s] = acc;
+      if (s < max_stages) acc += (uint32_t)carry[s];
+    }
+    for (int u = tid; u < nunits; u += 32) {
+#pragma unroll
+      for (int s = 1; s < 8; s++)
+        if (s < max_stages) urec[(size_t)(s * U + u) * 4 + 1] += sbase[s];
+    }
+  }
+  __syncwarp();
+
+  // ---- phase C: floor curve as one byte per bin: exact integer DDA, 16 bins per thread ----------
+  for (int ch = 0; ch < C; ch++) {
+    if (!((own_mask >> ch) & 1u)) continue;
+    const uint32_t* sg = sgbase + ch * 4 * 66;
+    uint8_t* yb = ybuf + ch * half_max;
+    const int nseg = (int)rec[K1_REC_HDR + ch * K1_SEG_WORDS];
+    for (int xb = tid * 16; xb < half; xb += 32 * 16) {
+      int lo = 0, hi = nseg;                                   // x0[lo] <= xb < x0[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)(sg[4 * mid] & 0xffffu) <= xb) lo = mid; else hi = mid;
+      }
+      int si = lo;
+      uint32_t w0s = sg[4 * si], w1s = sg[4 * si + 1], w2s = sg[4 * si + 2];
+      int x1 = (int)(w0s >> 16), adx = x1 - (int)(w0s & 0xffffu);
+      int base = (int)(w1s >> 16), rem = (int)(w2s & 0x7fffffffu), sy = (w2s >> 31) ? -1 : 1;
+      // state of the DDA after k = xb - x0 steps: y = y0 + sy * (k * base + floor(k * rem / adx))
+      const int k = xb - (int)(w0s & 0xffffu);
+      int t = k * rem;
+      int q = adx > 0 ? t / adx : 0;
+      int err = t - q * adx;
+      int y = (int)(short)(w1s & 0xffffu) + sy * (k * base + q);
+      const int xe = xb + 16 < half ? xb + 16 : half;
+      for (int x = xb; x < xe; x++) {
+        if (x >= x1 && si + 1 < nseg) {   // next segment starts exactly at its first post
+          si++;
+          w0s = sg[4 * si];
+          w1s = sg[4 * si + 1];
+          w2s = sg[4 * si + 2];
+          x1 = (int)(w0s >> 16);
+          adx = x1 - (int)(w0s & 0xffffu);
+          base = (int)(w1s >> 16);
+          rem = (int)(w2s & 0x7fffffffu);
+          sy = (w2s >> 31) ? -1 : 1;
+          err = 0;
+          y = (int)(short)(w1s & 0xffffu);
+        }
+        yb[x] = (uint8_t)(y < 0 ? 0 : (y > 255 ? 255 : y));   // the reference reads the table unchecked (quirk Q2)
+        err += rem;
+        y += sy * base;
+        if (err >= adx) {
+          err -= adx;
+          y += sy;
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  // ---- phase D: 8 bins per thread: gather the residue, inverse coupling, floor, store ------------
+  float* out = P.spec + pk.spec_off;
+  const bool pair = g.rtype == 2 && C == 2;
+  const bool coupled = C == 2 && mp->coupling_steps > 0;   // stereo: the only possible pair is (0,1) / (1,0)
+  for (int x0 = tid * 8; x0 < half; x0 += 32 * 8) {
+    float r[16];   // pair: r[2i] = channel 0, r[2i+1] = channel 1 of bin x0+i; else r[i] = ch 0, r[8+i] = ch 1
+#pragma unroll
+    for (int i = 0; i < 16; i++) r[i] = 0.f;
+    if (have_res) {
+      if (pair) {
+        k1g_fetch_chunk<16>(G, 0, 2 * x0, r);   // Residue2 de-interleave: positions (2x, 2x+1) = (ch0, ch1)
+      } else if (g.rtype == 2) {
+        k1g_fetch_chunk<8>(G, 0, x0, r);
+      } else {
+        if (!(g.skip & 1u)) k1g_fetch_chunk<8>(G, 0, x0, r);
+        if (C == 2 && !(g.skip & 2u)) k1g_fetch_chunk<8>(G, 1, x0, r + 8);
+      }
+    }
+    float c0[8], c1[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      c0[i] = pair ? r[2 * i] : r[i];
+      c1[i] = pair ? r[2 * i + 1] : r[8 + i];
+    }
+    if (DEBUG && P.dbg.residue) {
+      for (int i = 0; i < 8; i++) {
+        P.dbg.residue[x0 + i] = c0[i];
+        if (C == 2) P.dbg.residue[half + x0 + i] = c1[i];
+      }
+    }
+    // inverse coupling, last step first (Mapping.cs:166-172)
+    if (coupled) {
+      for (int sidx = mp->coupling_steps - 1; sidx >= 0; sidx--) {
+        if (mp->mag[sidx] == 0) {
+#pragma unroll
+          for (int i = 0; i < 8; i++) k1_uncouple(c0[i], c1[i]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; i++) k1_uncouple(c1[i], c0[i]);
+        }
+      }
+    }
+    // floor multiply (one rounded product per bin, Floor1.cs:383,395) and store
+    if (own_mask & 1u) {
+      const uint8_t* yb = ybuf + x0;
+      float4 o0, o1;
+      o0.x = __fmul_rn(c0[0], VPZ_LDG(dbtab + yb[0]));
+      o0.y = __fmul_rn(c0[1], VPZ_LDG(dbtab + yb[1]));
+      o0.z = __fmul_rn(c0[2], VPZ_LDG(dbtab + yb[2]));
+      o0.w = __fmul_rn(c0[3], VPZ_LDG(dbtab + yb[3]));
+      o1.x = __fmul_rn(c0[4], VPZ_LDG(dbtab + yb[4]));
+      o1.y = __fmul_rn(c0[5], VPZ_LDG(dbtab + yb[5]));
+      o1.z = __fmul_rn(c0[6], VPZ_LDG(dbtab + yb[6]));
+      o1.w = __fmul_rn(c0[7], VPZ_LDG(dbtab + yb[7]));
+      reinterpret_cast<float4*>(out + x0)[0] = o0;
+      reinterpret_cast<float4*>(out + x0)[1] = o1;
+    }
+    if (C == 2 && (own_mask & 2u)) {
+      const uint8_t* yb = ybuf + half_max + x0;
+      float4 o0, o1;
+      o0.x = __fmul_rn(c1[0], VPZ_LDG(dbtab + yb[0]));
+      o0.y = __fmul_rn(c1[1], VPZ_LDG(dbtab + yb[1]));
+      o0.z = __fmul_rn(c1[2], VPZ_LDG(dbtab + yb[2]));
+      o0.w = __fmul_rn(c1[3], VPZ_LDG(dbtab + yb[3]));
+      o1.x = __fmul_rn(c1[4], VPZ_LDG(dbtab + yb[4]));
+      o1.y = __fmul_rn(c1[5], VPZ_LDG(dbtab + yb[5]));
+      o1.z = __fmul_rn(c1[6], VPZ_LDG(dbtab + yb[6]));
+      o1.w = __fmul_rn(c1[7], VPZ_LDG(dbtab + yb[7]));
+      reinterpret_cast<float4*>(out + half + x0)[0] = o0;
+      reinterpret_cast<float4*>(out + half + x0)[1] = o1;
+    }
+  }
+  __syncwarp();
+}
+
+// The kernel body: gather path = every warp takes its own packets; general path = the CTA takes them.
+template <bool DEBUG>
+VPZ_DEV void k1b_cta_loop(const K1Params& P, uint32_t* smem, uint32_t* s_idx) {
+  const int tid = (int)threadIdx.x;
+  if (P.gather_ok) {
+    const int lane = tid & 31, warp = tid >> 5;
+    uint32_t* my = smem + (size_t)warp * P.smem_words_per_warp;
+    for (;;) {
+      uint32_t idx = 0;
+      if (lane == 0) idx = atomicAdd(P.counter + 2, 1u);
+      idx = __shfl_sync(0xffffffffu, idx, 0);
+      if (idx >= P.n_pkts) break;
+      k1b_build_packet_gather<DEBUG>(P, idx, my, lane);
+    }
+  } else {
+    for (;;) {
+      __syncthreads();
+      if (tid == 0) *s_idx = atomicAdd(P.counter + 2, 1u);
+      __syncthreads();
+      const uint32_t idx = *s_idx;
+      if (idx >= P.n_pkts) break;
+      k1b_build_packet_general<DEBUG>(P, idx, smem, tid);
+    }
+  }
 }
