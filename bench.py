@@ -110,6 +110,24 @@ class ClockSampler:
         return out
 
 
+def stream_assignment(streams, rank, world, scaling):
+    """Streams are independent units: rank r decodes `count` streams starting at global stream index
+    `first`; no rank ever needs another rank's data (no collective on the data path).
+    weak: every rank gets `streams` of its own; strong: `streams` in total are split."""
+    if scaling == "weak":
+        return rank * streams, streams
+    base, extra = divmod(streams, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
+def stream_file_and_start(g, n_files, n_packets):
+    """Global stream g decodes file g % n_files; replica r = g // n_files starts at audio packet
+    (7 r) mod count (replicated / offset)."""
+    f = g % n_files
+    return f, (7 * (g // n_files)) % n_packets[f]
+
+
 def pinned_array(lib, nfloats):
     p = lib.vpz_host_alloc(int(nfloats) * 4)
     if not p:
@@ -207,7 +225,7 @@ def main():
     ctx = Context(local_rank, lib_path=args.lib)  # raises without libvpz.so / without a B200: no CPU fallback
     lib = ctx.lib
     files = load_files()
-    n_streams = args.streams if args.scaling == "weak" else max(1, args.streams // world)
+    first_stream, n_streams = stream_assignment(args.streams, rank, world, args.scaling)
 
     # ---- workload: packets of every TestFile through the product's own Ogg layer -------------
     per_file = []
@@ -221,13 +239,13 @@ def main():
             per_file.append(dict(setup=st, blob=blob, offs=offs, n=len(pk), ch=r.channels))
     batch = Batch(ctx)
     t_plan = time.perf_counter()
-    first_stream = rank * n_streams if args.scaling == "strong" else 0
+    n_pk = [f["n"] for f in per_file]
     for i in range(n_streams):
         g = first_stream + i
-        f = per_file[g % len(files)]
+        fi, k = stream_file_and_start(g, len(files), n_pk)
+        f = per_file[fi]
         # replica r starts at audio packet (7 r) mod count; the packets before it form a second run,
         # so every packet of the file is decoded once per replica (each run re-seeds its overlap)
-        k = (7 * (g // len(files))) % f["n"]
         batch.add_run_raw(f["setup"], f["blob"], np.ascontiguousarray(f["offs"][k:]))
         if k > 0:
             batch.add_run_raw(f["setup"], f["blob"], np.ascontiguousarray(f["offs"][:k + 2]))

@@ -14,7 +14,7 @@ CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --streams 1024"
 $CMD > $OUT/plain_$TAG.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/launches_$TAG.csv $CMD > $OUT/ncu_launch_$TAG.log 2>&1
 echo "exit $?"; tail -2 $OUT/ncu_launch_$TAG.log
 echo "== ncu full"
-CMD2="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --streams 256"
-$CMD2 > $OUT/plain2_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:vpz_k -s 6 -c 2 -o $OUT/prof_$TAG -f $CMD2 > $OUT/ncu_full_$TAG.log 2>&1
+CMD2="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu --streams 1024"
+$CMD2 > $OUT/plain2_$TAG.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:vpz_k -s 9 -c 3 -o $OUT/prof_$TAG -f $CMD2 > $OUT/ncu_full_$TAG.log 2>&1
 echo "exit $?"; tail -2 $OUT/ncu_full_$TAG.log
 ls -la $OUT
