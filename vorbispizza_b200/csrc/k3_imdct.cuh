@@ -61,8 +61,31 @@ VPZ_DEV cpx cmul(cpx a, cpx b) {
   r.y = a.x * b.y + a.y * b.x;
   return r;
 }
+#ifndef VPZ_EMU
+// Blackwell packed fp32: one FADD2 adds both parts of a complex number (a float2 already sits in an
+// aligned register pair, so no moves are needed); same round-to-nearest result as two FADDs.
+VPZ_DEV cpx cadd(cpx a, cpx b) {
+  cpx r;
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+  return r;
+}
+VPZ_DEV cpx csub(cpx a, cpx b) {
+  cpx r;
+  unsigned long long ra, rb, rc;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1,%2};" : "=l"(rb) : "f"(-b.x), "f"(-b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rc) : "l"(ra), "l"(rb));
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(rc));
+  return r;
+}
+#else
 VPZ_DEV cpx cadd(cpx a, cpx b) { return cpx{a.x + b.x, a.y + b.y}; }
 VPZ_DEV cpx csub(cpx a, cpx b) { return cpx{a.x - b.x, a.y - b.y}; }
+#endif
 VPZ_DEV cpx cmul_mi(cpx a) { return cpx{a.y, -a.x}; }  // a * (-i)
 
 // 8-point forward DFT (e^{-2 pi i qk/8}), natural order in and out.
