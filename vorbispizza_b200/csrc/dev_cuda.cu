@@ -237,7 +237,7 @@ int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream* 
   cudaError_t e0 = cudaMemsetAsync(p.counter, 0, 4, s->s);  // word 1 of the counter block (K1a/K1b use 0 and 2)
   if (e0 != cudaSuccess) return fail(e0, "cudaMemsetAsync(counter)", err);
   // persistent CTAs: enough to fill every SM, items are handed out by the counter
-  unsigned grid = (unsigned)std::min<size_t>((p.n_items + K3_GRAB - 1) / K3_GRAB, (size_t)8 * g_sm_count);
+  unsigned grid = (unsigned)std::min<size_t>((p.n_items + p.grab - 1) / p.grab, (size_t)8 * g_sm_count);
   if (fast)
     vpz_k3_imdct_ola<true><<<grid, threads, smem_bytes, s->s>>>(p, ncb);
   else

@@ -595,6 +595,7 @@ int batch_decode(vpz_batch* b, int clip) {
     p.clip_first = static_cast<uint32_t*>(b->d_clip.p);
     p.n_items = (uint32_t)b->items.n;
     p.counter = ctx->d_counter + 1;
+    p.grab = b->items.n >= (size_t)64 * dev::sm_count() ? 4u : 1u;   // small batches: spread items over all SMs
     p.clip = clip ? 1 : 0;
     p.dbg_imdct = b->dbg_imdct;
     int ncb = std::min(2, b->max_channels);

@@ -138,7 +138,7 @@ VPZ_DEV int idx2(int k1, int k2, int r2) { return k1 + 8 * k2 + 68 * r2; }
 // load instead of one dependent global load per packet; the last word is the work-stealing slot.
 #define K3_DESC_PKTS 64
 #define K3_DESC_FLOATS 384
-#define K3_GRAB 4            // consecutive work items a CTA takes per atomic (same stream => same tables)
+#define K3_GRAB 4            // consecutive work items a CTA takes per atomic when there are plenty (K3Params.grab)
 #define K3_FAST_PER_CH (2 * K3_PLANE + 3 * 512 + 16)
 
 // N = 2048: H = 512 = 8*8*8, 64 threads.  The thread's 8 float2 of the spectrum (X[2n], X[2n+1] for
@@ -209,7 +209,7 @@ VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* ta
 }
 
 // N = 256: H = 64 = 8*8, threads t < 8 of the channel group work; M = 128.
-VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, const cpx* w64, int t, bool active) {
+VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, const cpx* w64, int t, bool active, int grp) {
   const int M = 128;
   cpx v[8];
   if (active) {
@@ -229,7 +229,7 @@ VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, c
       A[K3_PLANE + 9 * k + t] = v[k].y;
     }
   }
-  __syncthreads();
+  K3_GSYNC(grp);
   if (active) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
@@ -245,7 +245,7 @@ VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, c
       *k3_dp(D, M - 1 - 2 * p) = -c.y;
     }
   }
-  __syncthreads();
+  K3_GSYNC(grp);
 }
 
 // Any power-of-two N in 64..8192: radix-2 Stockham autosort between two shared buffers of 2*H
@@ -573,10 +573,10 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_
             __syncthreads();
           }
 #endif
-          __syncthreads();
+          K3_GSYNC(cgrp);
           xr_valid = false;
         } else {
-          fft64_to_D(exec ? X : P.spec, A, D, tw, roots, t64, exec && t64 < 8);
+          fft64_to_D(exec ? X : P.spec, A, D, tw, roots, t64, exec && t64 < 8, cgrp);
         }
       } else {
         // every thread must take the barriers inside
@@ -598,32 +598,30 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_
         k3_load_x(P.spec + pk_next.spec_off + (size_t)ch * Mmax, t, xr);
         xr_valid = true;
       }
-      if (emit) {
+      // ---- output: every channel group writes its own channel (samples j * C + ch).  The two groups of
+      // a CTA only meet at a CTA barrier every 8 packets, so their partial sector writes to the same
+      // interleaved PCM lines reach L2 within microseconds of each other and merge there.
+      if (emit && ch_ok) {
         const int ls = pk.left_start;
         const int count = (int)pk.right_start - ls;
         const int L = prev_re - prev_rs;             // StreamDecoder.cs:654
         const float* w = (pk.flags & VPZ_OLA_LEFT1) ? slope1 : slope0;
-        float* outp = P.pcm + it.out_base + (size_t)pk.out_off * C + c0;
-        const float* Dc_hm = smem + SCR - h;                       // channel slot 0; + cg * per_ch for the others
-        const float* Dc_lo = smem + SCR + HS + parity * HS;
-        const float* Dp_lo = smem + SCR + HS + (parity ^ 1) * HS;
+        float* outp = P.pcm + it.out_base + (size_t)pk.out_off * C + ch;
+        const float* Dc_hm = base + SCR - h;
+        const float* Dc_lo = base + SCR + HS + parity * HS;
+        const float* Dp_lo = base + SCR + HS + (parity ^ 1) * HS;
         bool clipped;
-        const bool long_long = FAST && nthreads == 64 * ncur && M == 1024 && prevM == 1024 && ls == 0 && count == 1024 &&
-                               L == 1024 && prev_rs == 1024 && (pk.flags & VPZ_OLA_LEFT1);
+        const bool long_long = FAST && M == 1024 && prevM == 1024 && ls == 0 && count == 1024 && L == 1024 &&
+                               prev_rs == 1024 && (pk.flags & VPZ_OLA_LEFT1);
         if (long_long) {
           const float* ws = smem_all + K3_TAB_SLOPE;
-          if (ncur == 2)
-            clipped = P.clip ? k3_emit_long_long<2, true>(Dc_hm, Dp_lo, ws, outp, C, tid)
-                             : k3_emit_long_long<2, false>(Dc_hm, Dp_lo, ws, outp, C, tid);
-          else
-            clipped = P.clip ? k3_emit_long_long<1, true>(Dc_hm, Dp_lo, ws, outp, C, tid)
-                             : k3_emit_long_long<1, false>(Dc_hm, Dp_lo, ws, outp, C, tid);
-        } else if (ncur == 2) {
-          clipped = P.clip ? k3_emit<2, true>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads)
-                           : k3_emit<2, false>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads);
+          clipped = P.clip ? k3_emit_long_long<1, true>(Dc_hm, Dp_lo, ws, outp, C, t64)
+                           : k3_emit_long_long<1, false>(Dc_hm, Dp_lo, ws, outp, C, t64);
         } else {
-          clipped = P.clip ? k3_emit<1, true>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads)
-                           : k3_emit<1, false>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads);
+          clipped = P.clip ? k3_emit<1, true>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, t64,
+                                              K3_THREADS_PER_CH)
+                           : k3_emit<1, false>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, t64,
+                                               K3_THREADS_PER_CH);
         }
         // per packet: 0 when any sample was clamped (HasClipped), else stays 0xffffffff
         if (P.clip_first && clipped) atomicMin(P.clip_first + gp, 0u);
@@ -632,10 +630,15 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_
       prev_rs = pk.right_start;
       prev_re = pk.right_end;
       have_prev = true;
-      // The output loop above reads the previous D buffer; the next packet overwrites it only after
-      // its own transform barriers, except on the N = 256 path and for the zero fill of a silent
-      // channel, which store before their first barrier: one barrier here keeps the ping-pong safe.
-      __syncthreads();
+      // The output loop above reads the previous D slot; the next packet overwrites it only after its
+      // own transform barriers, except on the N = 256 path and for the zero fill of a silent
+      // channel, which store before their first barrier: one (group) barrier here keeps that safe.
+      if (FAST) {
+        K3_GSYNC(cgrp);
+        if ((pw & 7) == 7) __syncthreads();   // keep the channel groups within 8 packets of each other
+      } else {
+        __syncthreads();
+      }
     }
     }
     __syncthreads();
@@ -649,11 +652,11 @@ VPZ_DEV void k3_cta_loop(const K3Params& P, float* smem_raw, int ncb) {
   const uint32_t* prev_blob = nullptr;
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) *s_next = atomicAdd(P.counter, (uint32_t)K3_GRAB);
+    if (threadIdx.x == 0) *s_next = atomicAdd(P.counter, P.grab);
     __syncthreads();
     const uint32_t first = *s_next;
     if (first >= P.n_items) break;
-    for (uint32_t k = 0; k < K3_GRAB && first + k < P.n_items; k++) {
+    for (uint32_t k = 0; k < P.grab && first + k < P.n_items; k++) {
       const uint32_t* blob = P.setups[P.items[first + k].setup_slot];
       k3_run_item<FAST>(P, P.items[first + k], smem_raw, ncb, blob != prev_blob);
       prev_blob = blob;
