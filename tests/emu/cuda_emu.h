@@ -20,6 +20,12 @@
 struct float2 {
   float x, y;
 };
+struct alignas(8) uint2 {
+  uint32_t x, y;
+};
+struct alignas(16) uint4 {
+  uint32_t x, y, z, w;
+};
 struct alignas(16) float4 {
   float x, y, z, w;
 };

@@ -12,7 +12,7 @@
 
 // ---- kernels ---------------------------------------------------------------------------------
 template <bool DEBUG>
-__global__ void __launch_bounds__(128) vpz_k1a_symbols(K1Params P) {
+__global__ void __launch_bounds__(128, 8) vpz_k1a_symbols(K1Params P) {
   const int lane = threadIdx.x & 31;
   for (;;) {
     uint32_t base = 0;

@@ -63,12 +63,37 @@ struct K1Bits {
   const uint32_t* w;
   int pos, nbits;
   int is_short;
+  // register window over the packet: lo = w[wi], hi = w[wi + 1], nx = w[wi + 2] with wi = pos >> 5.
+  // A peek is one funnel shift; the word after next is requested when the cursor enters a new word,
+  // so its latency hides behind the ~8 codewords that fit in a word.
+  uint32_t lo, hi, nx;
+  int wi, maxw;   // maxw: last word that may hold packet bits or the zero padding behind them
 };
 
-VPZ_DEV uint32_t k1_peek32(const K1Bits& b) {
-  int i = b.pos >> 5;
-  uint32_t lo = VPZ_LDG(b.w + i), hi = VPZ_LDG(b.w + i + 1);
-  return __funnelshift_r(lo, hi, b.pos & 31);
+VPZ_DEV void k1_bits_init(K1Bits& b, const uint32_t* w, int byte_len) {
+  b.w = w;
+  b.pos = 0;
+  b.nbits = byte_len * 8;
+  b.is_short = 0;
+  b.wi = 0;
+  b.maxw = (byte_len >> 2) + 1;   // the packet is followed by >= 8 zero bytes (VpzPktIn)
+  b.lo = VPZ_LDG(w);
+  b.hi = VPZ_LDG(w + 1);
+  b.nx = 2 <= b.maxw ? VPZ_LDG(w + 2) : 0u;
+}
+
+VPZ_DEV uint32_t k1_peek32(const K1Bits& b) { return __funnelshift_r(b.lo, b.hi, b.pos & 31); }
+
+// move the cursor forward by at most 32 bits
+VPZ_DEV void k1_bits_seek(K1Bits& b, int np) {
+  b.pos = np;
+  const int ni = np >> 5;
+  if (ni != b.wi) {
+    b.lo = b.hi;
+    b.hi = b.nx;
+    b.nx = ni + 2 <= b.maxw ? VPZ_LDG(b.w + ni + 2) : 0u;
+    b.wi = ni;
+  }
 }
 
 // VorbisPacket.ReadBits (VorbisPacket.cs:157-164): zero-extended, truncated at the end, n <= 32
@@ -77,7 +102,7 @@ VPZ_DEV uint32_t k1_read(K1Bits& b, int n) {
   uint32_t v = k1_peek32(b);
   if (n < 32) v &= (1u << n) - 1u;
   int np = b.pos + n;
-  b.pos = np < b.nbits ? np : b.nbits;
+  k1_bits_seek(b, np < b.nbits ? np : b.nbits);
   return v;
 }
 
@@ -135,7 +160,7 @@ VPZ_DEV int k1_decode(K1Bits& b, const K1Book& bk, const uint32_t* blob, const K
         np = b.nbits;
         b.is_short = 1;
       }
-      b.pos = np;
+      k1_bits_seek(b, np);
     }
   }
   if (DEBUG) {
@@ -196,10 +221,7 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   uint16_t* ent = P.ent + pk.ent_off;
 
   K1Bits b;
-  b.w = P.bytes + (pk.byte_off >> 2);
-  b.pos = 0;
-  b.nbits = (int)pk.byte_len * 8;
-  b.is_short = 0;
+  k1_bits_init(b, P.bytes + (pk.byte_off >> 2), (int)pk.byte_len);
   int nscal = 0, ncls = 0;
 
   // StreamDecoder.DecodeNextPacket (StreamDecoder.cs:728-741): the host only queues packets whose
@@ -329,35 +351,46 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   const K1ResGeom g = k1_res_geom(rs, C, half, noexec);
   int status = 0;
   uint32_t n_ent = 0;
-  if (g.part_count > 0 && g.any) {
-    uint8_t cls[K1_MAX_UNITS];                       // [v * part_count + part]
+  if (g.part_count > 0 && g.any && rs->max_stages > 0) {
+    // Residue0.Decode (Residue0.cs:117-206) walks  stage -> partition group -> [stage 0: classwords] ->
+    // partition -> vector.  Here the walk is flattened so that every trip round the loop decodes
+    // exactly ONE codeword (lanes at different places of their packets still share every instruction)
+    // and finding the next codeword never loops over classes or cascades:
+    //  * a classword value indexes cw_tab (setup.cpp), which holds for every stage the units of its
+    //    partition group that carry codewords; stage 0 consumes that mask right away, the masks of the
+    //    later stages are OR-ed into a per-stage bit array over all units (unit = partition * nvec + vector,
+    //    which is also the decode order inside a stage);
+    //  * stages >= 1 walk their bit array with find-first-set;
+    //  * the book and the codeword count of a unit come from unit_tab[class][stage] in one 8-byte load.
+    uint8_t cls[K1_MAX_UNITS];                       // class per unit, decode order
+    uint32_t smask[8 * (K1_MAX_UNITS / 32)];         // [stage][chunk of 32 units]; row 0 unused
     uint8_t* rec_cls = reinterpret_cast<uint8_t*>(rec + K1_REC_HDR + C * K1_SEG_WORDS);
     const K1Book cb = k1_book(blob, books, rs->class_book);
-    const int cdim = cb.dims;
-    const uint8_t* dmap = reinterpret_cast<const uint8_t*>(blob + rs->decode_map_off);
-    const int partvals = (int)rs->decode_map_len / cdim;
+    const int cdim = rs->cdim, nvec = g.nvec, part_count = g.part_count;
+    const int partvals = (int)rs->partvals;
     const int max_stages = rs->max_stages;
-    const int nvec = g.nvec, part_count = g.part_count;
+    const uint8_t* dmap = reinterpret_cast<const uint8_t*>(blob + rs->decode_map_off);
+    const uint2* unit_tab = reinterpret_cast<const uint2*>(blob + rs->unit_tab_off);
+    const uint32_t* cw_tab = blob + rs->cw_tab_off;
+    const int nunits = part_count * nvec;
+    const int nchunks = (nunits + 31) >> 5;
     // classes of groups a truncated packet never reaches must still be valid indices for K1b
-    for (int u = 0; u < nvec * part_count; u++) rec_cls[u] = 0;
-    // Flattened walk of  stage -> partition group -> [stage 0: classwords] -> partition -> vector:
-    // every trip round the loop below decodes exactly ONE codeword, so lanes that sit at different
-    // places of their packets still execute the same instructions.  Per (group, stage) the units
-    // that actually carry codewords are collected in a bit mask (slot = k * nvec + v, decode
-    // order), so finding the next codeword is a find-first-set, not a scan over idle units.
+    for (int u = 0; u < nunits; u++) rec_cls[u] = 0;
+    for (int i = nchunks; i < max_stages * nchunks; i++) smask[i] = 0;
     uint32_t vecmask = 0;                  // vectors that are decoded
     for (int v = 0; v < nvec; v++)
       if (!((g.skip >> v) & 1u)) vecmask |= 1u << v;
-    int stage = 0, gpart = 0;
+    int stage = 0, gpart = 0, chunk = 0;
     uint32_t cwmask = vecmask;             // classwords still to read for the current group (stage 0)
-    unsigned long long slotmask = 0;       // units of the current (group, stage) still to decode
-    bool need_build = true;
-    int cw_v = 0;                          // vector of the classword being decoded
+    uint32_t grp_acc = 0;                  // stage-0 units of the current group, collected from its classwords
+    uint32_t cur_mask = 0;                 // units still to decode; bit i = unit ubase + i
+    int ubase = 0;
     int dbg_slot = 0;                      // DEBUG: next unit of the group whose class goes to the dump
+    int cw_v = 0;                          // vector of the classword being decoded
     bool in_class = false;
     int rem = 0;                           // entries still to decode in the current unit
     K1Book cur = cb;
-    bool done = max_stages == 0;
+    bool done = false;
     while (!done) {
       if (rem == 0) {
         // ---- find the next codeword to decode ----
@@ -369,49 +402,46 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
             break;
           }
           in_class = false;
-          if (need_build) {
-            need_build = false;
-            slotmask = 0;
-            for (int k = 0; k < cdim && gpart + k < part_count; k++)
-              for (int v = 0; v < nvec; v++) {
-                if (!((vecmask >> v) & 1u)) continue;
-                const int c = cls[v * part_count + gpart + k];
-                if (((rs->cascade[c] >> stage) & 1u) && rs->has_books[c]) slotmask |= 1ull << (k * nvec + v);
-              }
-            dbg_slot = 0;
-          }
           if (DEBUG && stage == 0) {
             // the dump lists the class of every unit the reference VISITS, in order, idle ones too
-            const int upto = slotmask ? __ffsll((long long)slotmask) - 1 : cdim * nvec - 1;
+            const int upto = cur_mask ? __ffs((int)cur_mask) - 1 : cdim * nvec - 1;
             for (; dbg_slot <= upto; dbg_slot++) {
               const int k = dbg_slot / nvec, v = dbg_slot - k * nvec;
               if (gpart + k >= part_count || !((vecmask >> v) & 1u)) continue;
-              if (P.dbg.classes && ncls < P.dbg.classes_cap) P.dbg.classes[ncls] = cls[v * part_count + gpart + k];
+              if (P.dbg.classes && ncls < P.dbg.classes_cap) P.dbg.classes[ncls] = cls[(gpart + k) * nvec + v];
               ncls++;
             }
           }
-          if (slotmask) {
-            const int slot = __ffsll((long long)slotmask) - 1;
-            slotmask &= slotmask - 1;
-            const int k = slot / nvec, v = slot - k * nvec;
-            const int c = cls[v * part_count + gpart + k];
-            cur = k1_book(blob, books, rs->books[c][stage]);
-            rem = k1_unit_entries(g.rtype, g.psize, cur.dims);
-            if (rem > 0) break;
-            continue;
+          if (cur_mask) {
+            const int u = ubase + __ffs((int)cur_mask) - 1;
+            cur_mask &= cur_mask - 1;
+            const uint2 t = VPZ_LDG(unit_tab + (cls[u] * 8 + stage));
+            cur.l1 = blob + t.x;
+            cur.l1_mask = (1u << (t.y & 0xffu)) - 1u;
+            cur.bk = books + ((t.y >> 8) & 0xffu);
+            rem = (int)(t.y >> 16);
+            break;
           }
-          // group finished: next group, next stage
-          gpart += cdim;
-          if (gpart >= part_count) {
-            gpart = 0;
-            stage++;
-            if (stage >= max_stages) {
-              done = true;
-              break;
+          if (stage == 0) {                // next partition group: its classwords come first
+            gpart += cdim;
+            if (gpart < part_count) {
+              cwmask = vecmask;
+              dbg_slot = 0;
+              continue;
             }
+            chunk = -1;                    // stage 0 is finished: fall through to the first chunk of stage 1
+            stage = 1;
+          } else if (chunk + 1 >= nchunks) {
+            stage++;
+            chunk = -1;
           }
-          if (stage == 0) cwmask = vecmask;
-          need_build = true;
+          if (stage >= max_stages) {
+            done = true;
+            break;
+          }
+          chunk++;
+          cur_mask = smask[stage * nchunks + chunk];
+          ubase = chunk * 32;
         }
         if (done) break;
       }
@@ -423,13 +453,30 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
           status = 1;
           break;
         }
+        const int left = part_count - gpart;   // partitions of this (possibly partial, last) group
         for (int kk = 0; kk < cdim; kk++)
-          if (gpart + kk < part_count) {
+          if (kk < left) {
             const uint8_t c = dmap[sym * cdim + kk];
-            cls[cw_v * part_count + gpart + kk] = c;
+            cls[(gpart + kk) * nvec + cw_v] = c;
             rec_cls[cw_v * part_count + gpart + kk] = c;
           }
+        const uint32_t lim = left * nvec >= 32 ? 0xffffffffu : (1u << (left * nvec)) - 1u;
+        const uint32_t* ct = cw_tab + ((size_t)cw_v * partvals + sym) * max_stages;
+        grp_acc |= VPZ_LDG(ct) & lim;
+        const int u0 = gpart * nvec, c0 = u0 >> 5, sh = u0 & 31;
+        for (int s2 = 1; s2 < max_stages; s2++) {
+          const uint32_t m = VPZ_LDG(ct + s2) & lim;
+          if (m) {
+            smask[s2 * nchunks + c0] |= m << sh;
+            if (sh && (m >> (32 - sh))) smask[s2 * nchunks + c0 + 1] |= m >> (32 - sh);
+          }
+        }
         cwmask &= cwmask - 1;
+        if (!cwmask) {                     // the group's classwords are complete: its stage-0 units follow
+          cur_mask = grp_acc;
+          grp_acc = 0;
+          ubase = u0;
+        }
       } else {
         if (sym < 0) {  // Residue0.cs:195-201: keep what was decoded
           status = 1;

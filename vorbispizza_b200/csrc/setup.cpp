@@ -614,6 +614,53 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
     bw.align(4);
     residues[i].decode_map_off = bw.reserve((dmaps[i].size() + 3) / 4);
     if (!dmaps[i].empty()) memcpy(&blob[residues[i].decode_map_off], dmaps[i].data(), dmaps[i].size());
+    // ---- K1a walk tables (vpz_dev.h): which (class, stage) units carry codewords and with which book,
+    // and per classword value the units of its partition group that are active in every stage.  They
+    // restate the tests of Residue0.Decode (Residue0.cs:160-190: cascade bit + book present) as lookups.
+    VpzResidue& r = residues[i];
+    const int cdim = books[r.class_book].dims;
+    const int nvec = r.type == 2 ? 1 : id.channels;
+    const int partvals = (int)(r.decode_map_len / (uint32_t)std::max(cdim, 1));
+    r.cdim = (uint16_t)cdim;
+    r.nvec = (uint16_t)nvec;
+    r.partvals = (uint32_t)partvals;
+    if (cdim < 1 || cdim * nvec > 32) {
+      error = "residue classbook dimension x vectors above 32 is not on the GPU path";
+      return VPZ_E_UNSUPPORTED;
+    }
+    if ((uint64_t)partvals * (uint64_t)nvec * std::max<int>(r.max_stages, 1) > (1u << 20)) {
+      error = "residue classword table too large for the GPU path";
+      return VPZ_E_UNSUPPORTED;
+    }
+    uint32_t active[64] = {0};   // per class: bit s set when stage s decodes codewords for a partition of that class
+    bw.align(2);
+    r.unit_tab_off = bw.reserve((size_t)r.classifications * 8 * 2);
+    for (int c = 0; c < r.classifications; c++)
+      for (int s = 0; s < 8; s++) {
+        if (!(((r.cascade[c] >> s) & 1) && r.has_books[c])) continue;
+        const int bk = r.books[c][s];
+        const int dims = books[bk].dims;
+        // Residue0.WriteVectors decodes psize / dims entries, Residue1.WriteVectors steps by dims until psize
+        const uint32_t n = r.type == 0 ? r.part_size / (uint32_t)dims : (r.part_size + (uint32_t)dims - 1) / (uint32_t)dims;
+        if (n == 0) continue;
+        if (n > 65535u) {
+          error = "residue partition with more than 65535 codewords is not on the GPU path";
+          return VPZ_E_UNSUPPORTED;
+        }
+        blob[r.unit_tab_off + (size_t)(c * 8 + s) * 2] = dbooks[bk].l1_off;
+        blob[r.unit_tab_off + (size_t)(c * 8 + s) * 2 + 1] = (uint32_t)dbooks[bk].l1_bits | ((uint32_t)bk << 8) | (n << 16);
+        active[c] |= 1u << s;
+      }
+    const int ns = std::max<int>(r.max_stages, 1);
+    r.cw_tab_off = bw.reserve((size_t)nvec * partvals * ns);
+    for (int v = 0; v < nvec; v++)
+      for (int sym = 0; sym < partvals; sym++)
+        for (int s = 0; s < ns; s++) {
+          uint32_t m = 0;
+          for (int k = 0; k < cdim; k++)
+            if ((active[dmaps[i][(size_t)sym * cdim + k]] >> s) & 1u) m |= 1u << (k * nvec + v);
+          blob[r.cw_tab_off + ((size_t)v * partvals + sym) * ns + s] = m;
+        }
   }
   VpzSetupHdr h;
   memset(&h, 0, sizeof(h));

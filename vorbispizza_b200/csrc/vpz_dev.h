@@ -65,6 +65,16 @@ struct VpzResidue {
   uint8_t cascade[64];
   uint8_t has_books[64];
   uint8_t books[64][8];
+  // K1a walk tables (built by setup.cpp; the lanes of K1a never loop over classes or cascades):
+  //   unit_tab [classifications][8] x {l1 table word offset, l1_bits | book << 8 | entries per unit << 16};
+  //            the second word is 0 when (class, stage) carries no codewords
+  //   cw_tab   [nvec][partvals][max_stages] x uint32: for classword value `sym` of vector v, bit k * nvec + v
+  //            is set when partition k of the group has codewords in that stage
+  uint32_t unit_tab_off;
+  uint32_t cw_tab_off;
+  uint32_t partvals;         // classifications ^ classbook.dims
+  uint16_t cdim;             // classbook.dims (partitions per classword)
+  uint16_t nvec;             // vectors the residue decodes: 1 for type 2, else the channel count
 };
 
 // ---- mapping (Mapping.cs:19-95) ---------------------------------------------------------
