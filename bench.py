@@ -179,6 +179,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--l1-bits", type=int, default=0, help=argparse.SUPPRESS)  # tuning: first-level Huffman table width
     ap.add_argument("--lib", default=None, help=argparse.SUPPRESS)  # dry-run the script logic on the emulated test build
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -224,6 +225,8 @@ def main():
 
     ctx = Context(local_rank, lib_path=args.lib)  # raises without libvpz.so / without a B200: no CPU fallback
     lib = ctx.lib
+    if args.l1_bits:
+        ctx.set("l1_bits", args.l1_bits)
     files = load_files()
     first_stream, n_streams = stream_assignment(args.streams, rank, world, args.scaling)
 

@@ -16,6 +16,20 @@ def test_stage_parity_truncated_packets(emu_ctx, name, stride):
     assert cases.stage_parity(emu_ctx, name, stride=stride, truncate=True) > 0
 
 
+@pytest.mark.parametrize("l1_bits", [3, 6])
+def test_stage_parity_narrow_huffman_tables(emu_lib_path, l1_bits):
+    """Narrow first-level tables push most codewords through the second-level table and the longest
+    ones through the sorted-array fallback of Codebook.DecodeScalar's restatement (k1_decode)."""
+    from vorbispizza_b200 import Context
+    ctx = Context(0, lib_path=emu_lib_path)
+    try:
+        ctx.set("l1_bits", l1_bits)
+        assert cases.stage_parity(ctx, "3test", stride=53) > 0
+        assert cases.stage_parity(ctx, "2test", stride=97, truncate=True) > 0
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("clip", [True, False])
 def test_batch_pcm_1test(emu_ctx, clip):
     cases.batch_pcm_parity(emu_ctx, "1test", clip)

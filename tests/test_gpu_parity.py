@@ -27,6 +27,21 @@ def test_stage_parity_truncated_packets(gpu_ctx, name):
     assert cases.stage_parity(gpu_ctx, name, stride=7, truncate=True) > 0
 
 
+@pytest.mark.parametrize("l1_bits", [3, 6, 11])
+def test_stage_parity_other_huffman_table_widths(l1_bits):
+    """First-level widths that push codewords through the second-level table and the sorted-array
+    fallback (narrow) or resolve nearly everything in one load (wide): same symbols, same bits."""
+    from vorbispizza_b200 import Context
+    ctx = Context(0)
+    try:
+        ctx.set("l1_bits", l1_bits)
+        for name in ("3test", "issue6test"):
+            assert cases.stage_parity(ctx, name, stride=7) > 0
+        assert cases.stage_parity(ctx, "2test", stride=11, truncate=True) > 0
+    finally:
+        ctx.close()
+
+
 @pytest.mark.parametrize("clip", [True, False])
 @pytest.mark.parametrize("name", FILES)
 def test_batch_pcm(gpu_ctx, name, clip):

@@ -30,6 +30,13 @@ for ALT in vorbispizza_b200/alt_*.so; do
   echo "== bench $N"; timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e > $OUT/bench_${TAG}_$N.json 2> $OUT/bench_${TAG}_$N.err; echo "exit $?"; summ $OUT/bench_${TAG}_$N.json; tail -2 $OUT/bench_${TAG}_$N.err
 done
 cp /tmp/libvpz_main.so vorbispizza_b200/libvpz.so
+# extra bench variants of the main build: BENCH_VARIANTS="--l1-bits 8;--l1-bits 10"
+IFS=';' read -ra VARS <<< "$BENCH_VARIANTS"
+for V in "${VARS[@]}"; do
+  [ -n "$V" ] || continue
+  N=$(echo $V | tr -c 'a-zA-Z0-9' '_')
+  echo "== bench $V"; timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu --no-e2e $V > $OUT/bench_${TAG}_$N.json 2> $OUT/bench_${TAG}_$N.err; echo "exit $?"; summ $OUT/bench_${TAG}_$N.json; tail -2 $OUT/bench_${TAG}_$N.err
+done
 if [ "$KRE" != "none" ]; then
 echo "== ncu full"
 CMD2="python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu"

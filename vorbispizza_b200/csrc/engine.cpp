@@ -316,8 +316,8 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
       }
       count = rs - g.left_start;
     }
-    // staged layout: 4-byte aligned start, at least 8 zero bytes after the end
-    const uint64_t end = (staged + len + 8 + 3) & ~(uint64_t)3;
+    // staged layout: 4-byte aligned start, at least 12 zero bytes after the end (K1a reads two words ahead)
+    const uint64_t end = (staged + len + 12 + 3) & ~(uint64_t)3;
     const int M = g.block_size / 2;
     VpzPktOla ola;
     memset(&ola, 0, sizeof(ola));
@@ -336,7 +336,7 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
     out->byte_off.push_back((uint32_t)staged);
     // every codeword is at least one bit long: 8 * len bounds the entry indices of the packet
     out->ent_off.push_back((uint32_t)out->ent_total);
-    out->ent_total += ((uint64_t)len * 8 + 8 + 1) & ~(uint64_t)1;
+    out->ent_total += ((uint64_t)len * 8 + 8 + 3) & ~(uint64_t)3;   // multiple of 4: K1a stores 4 indices at a time
     out->ola.push_back(ola);
     staged = end;
     out->payload_bytes += len;
@@ -494,15 +494,26 @@ int batch_upload(vpz_batch* b) {
     if (!b->d_rec.reserve(b->rec_words * 4 + 16, err) || !b->d_ent.reserve(b->ent_total * 2 + 16, err) ||
         !b->d_order.reserve(np * 4 + 16, err))
       return VPZ_E_CUDA;
-    // K1a order: packets sorted by byte length, longest first (counting sort), so the 32 lanes of a
-    // warp get packets of like size and the long ones do not form the tail of the launch
-    if (!b->order.reserve(np + 1)) return VPZ_E_NOMEM;
+    // K1a order: packets grouped by (setup, block size) and sorted by byte length, longest first,
+    // inside a group (two stable counting sorts).  The 32 lanes of a warp then walk the same floor /
+    // residue configuration with packets of like size (convergent control flow), the warps resident
+    // on an SM share one setup's Huffman tables in L1, and the long packets do not form the tail.
+    if (!b->order.reserve(2 * np + 2)) return VPZ_E_NOMEM;
     {
+      uint32_t* tmp = b->order.p + np + 1;
       std::vector<uint32_t> bucket(4098, 0);
       auto key = [&](size_t i) { return (size_t)(4096 - std::min<uint32_t>(b->pkts_in.p[i].byte_len >> 2, 4096)); };
       for (size_t i = 0; i < np; i++) bucket[key(i) + 1]++;
       for (size_t k = 1; k < bucket.size(); k++) bucket[k] += bucket[k - 1];
-      for (size_t i = 0; i < np; i++) b->order.p[bucket[key(i)]++] = (uint32_t)i;
+      for (size_t i = 0; i < np; i++) tmp[bucket[key(i)]++] = (uint32_t)i;
+      const size_t ngroups = 2 * b->slots.size();
+      std::vector<uint32_t> gb(ngroups + 2, 0);
+      auto gkey = [&](uint32_t i) {
+        return (size_t)b->pkts_in.p[i].setup_slot * 2 + ((b->pkts_ola.p[i].flags & VPZ_OLA_LONG) ? 0 : 1);
+      };
+      for (size_t i = 0; i < np; i++) gb[gkey((uint32_t)i) + 1]++;
+      for (size_t k = 1; k < gb.size(); k++) gb[k] += gb[k - 1];
+      for (size_t i = 0; i < np; i++) b->order.p[gb[gkey(tmp[i])]++] = tmp[i];
       b->order.n = np;
     }
     if ((rc = dev::h2d(b->d_order.p, b->order.p, np * 4, st, err))) return rc;

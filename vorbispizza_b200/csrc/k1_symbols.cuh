@@ -26,10 +26,14 @@
 #define VPZ_DEV __device__ __forceinline__
 #define VPZ_DEVN __device__ __noinline__
 #define VPZ_LDG(p) __ldg(p)
+// packet bytes are read once, one 128-byte line per lane at a time: keep them out of L1 (ld.global.cg) so
+// the lines stay available for the Huffman tables that every lane re-reads
+#define VPZ_LDSTREAM(p) __ldcg(p)
 #else
 #define VPZ_DEV inline
 #define VPZ_DEVN inline
 #define VPZ_LDG(p) (*(p))
+#define VPZ_LDSTREAM(p) (*(p))
 #endif
 
 // word offsets inside vpz_packet_dump (include/vpz.h) -- keep in sync
@@ -53,64 +57,62 @@
 //   [2] final bit cursor
 //   [3] reserved
 //   then per channel K1_SEG_WORDS words: [0] = number of line segments n, [1..n+1] = points x | y << 16
-//   then one byte per (vector, partition): the partition class
+//   then one byte per unit (partition * nvec + vector, the decode order inside a stage): the partition class
 #define K1_REC_HDR 4
 #define K1_SEG_WORDS 68
 #define K1_MAX_UNITS 512      // vectors * partitions per packet (setup.cpp refuses more)
 #define K1B_THREADS 128       // K1b: threads (one CTA) per packet
 
 struct K1Bits {
-  const uint32_t* w;
+  uint32_t woff;   // word offset of the packet in the batch byte buffer (the base stays a kernel parameter)
   int pos, nbits;
-  int is_short;
   // register window over the packet: lo = w[wi], hi = w[wi + 1], nx = w[wi + 2] with wi = pos >> 5.
   // A peek is one funnel shift; the word after next is requested when the cursor enters a new word,
-  // so its latency hides behind the ~8 codewords that fit in a word.
+  // so its latency hides behind the ~8 codewords that fit in a word.  The packet is followed by at
+  // least 12 zero bytes (VpzPktIn), so w[wi + 2] is packet data or zero padding for every pos <= nbits.
   uint32_t lo, hi, nx;
-  int wi, maxw;   // maxw: last word that may hold packet bits or the zero padding behind them
+  int wi;
 };
 
-VPZ_DEV void k1_bits_init(K1Bits& b, const uint32_t* w, int byte_len) {
-  b.w = w;
+VPZ_DEV void k1_bits_init(K1Bits& b, const uint32_t* bytes, uint32_t woff, int byte_len) {
+  b.woff = woff;
   b.pos = 0;
   b.nbits = byte_len * 8;
-  b.is_short = 0;
   b.wi = 0;
-  b.maxw = (byte_len >> 2) + 1;   // the packet is followed by >= 8 zero bytes (VpzPktIn)
-  b.lo = VPZ_LDG(w);
-  b.hi = VPZ_LDG(w + 1);
-  b.nx = 2 <= b.maxw ? VPZ_LDG(w + 2) : 0u;
+  b.lo = VPZ_LDSTREAM(bytes + woff);
+  b.hi = VPZ_LDSTREAM(bytes + woff + 1);
+  b.nx = VPZ_LDSTREAM(bytes + woff + 2);
 }
 
 VPZ_DEV uint32_t k1_peek32(const K1Bits& b) { return __funnelshift_r(b.lo, b.hi, b.pos & 31); }
 
 // move the cursor forward by at most 32 bits
-VPZ_DEV void k1_bits_seek(K1Bits& b, int np) {
+VPZ_DEV void k1_bits_seek(K1Bits& b, const uint32_t* bytes, int np) {
   b.pos = np;
   const int ni = np >> 5;
   if (ni != b.wi) {
     b.lo = b.hi;
     b.hi = b.nx;
-    b.nx = ni + 2 <= b.maxw ? VPZ_LDG(b.w + ni + 2) : 0u;
+    b.nx = VPZ_LDSTREAM(bytes + b.woff + ni + 2);
     b.wi = ni;
   }
 }
 
 // VorbisPacket.ReadBits (VorbisPacket.cs:157-164): zero-extended, truncated at the end, n <= 32
-VPZ_DEV uint32_t k1_read(K1Bits& b, int n) {
+VPZ_DEV uint32_t k1_read(K1Bits& b, const uint32_t* bytes, int n) {
   if (n <= 0) return 0;
   uint32_t v = k1_peek32(b);
   if (n < 32) v &= (1u << n) - 1u;
   int np = b.pos + n;
-  k1_bits_seek(b, np < b.nbits ? np : b.nbits);
+  k1_bits_seek(b, bytes, np < b.nbits ? np : b.nbits);
   return v;
 }
 
+// a codebook as the decoder needs it: three registers, no pointers
 struct K1Book {
-  const uint32_t* l1;
-  const VpzBook* bk;
+  uint32_t l1_off;   // word offset of the first-level table in the blob
   uint32_t l1_mask;
-  int dims;
+  uint32_t meta;     // l1_bits | book index << 8 | (unit_tab only) entries per unit << 16
 };
 
 // dims (u16) and l1_bits (u8) share one 32-bit word at byte offset 24 of VpzBook
@@ -121,12 +123,10 @@ VPZ_DEV int k1_book_dims(const VpzBook* bk) {
 VPZ_DEV K1Book k1_book(const uint32_t* blob, const VpzBook* books, int idx) {
   const VpzBook* bk = books + idx;
   K1Book r;
-  r.bk = bk;
-  r.l1 = blob + VPZ_LDG(&bk->l1_off);
-  // dims (u16) and l1_bits (u8) share one 32-bit word at byte offset 24
-  uint32_t packed = VPZ_LDG(reinterpret_cast<const uint32_t*>(bk) + 6);
-  r.dims = (int)(packed & 0xffffu);
-  r.l1_mask = (1u << ((packed >> 16) & 0xffu)) - 1u;
+  r.l1_off = VPZ_LDG(&bk->l1_off);
+  const uint32_t l1_bits = (VPZ_LDG(reinterpret_cast<const uint32_t*>(bk) + 6) >> 16) & 0xffu;
+  r.l1_mask = (1u << l1_bits) - 1u;
+  r.meta = l1_bits | ((uint32_t)idx << 8);
   return r;
 }
 
@@ -136,31 +136,34 @@ VPZ_DEV int k1_decode(K1Bits& b, const K1Book& bk, const uint32_t* blob, const K
   int sym = -1;
   if (b.pos < b.nbits) {
     uint32_t x = k1_peek32(b);
-    uint32_t e = VPZ_LDG(bk.l1 + (x & bk.l1_mask));
-    if (e & 0x80000000u) {  // longer than the first-level table: binary search in the sorted long codes
-      const uint32_t* ranges = blob + VPZ_LDG(&bk.bk->range_off);
-      const uint32_t* lcode = blob + VPZ_LDG(&bk.bk->lcode_off);
-      const uint32_t* linfo = blob + VPZ_LDG(&bk.bk->linfo_off);
-      uint32_t id = e & 0x7fffffffu;
-      uint32_t lo = VPZ_LDG(ranges + 2 * id), hi = VPZ_LDG(ranges + 2 * id + 1);
-      uint32_t m = __brev(x);
-      while (hi - lo > 1) {
-        uint32_t mid = (lo + hi) >> 1;
-        if (VPZ_LDG(lcode + mid) <= m) lo = mid; else hi = mid;
+    const uint32_t* l1 = blob + bk.l1_off;
+    uint32_t e = VPZ_LDG(l1 + (x & bk.l1_mask));
+    if (e & 0x80000000u) {  // longer than the first-level table: second-level table over the next bits
+      const uint32_t l2b = e & 31u;
+      e = VPZ_LDG(l1 + ((e >> 5) & 0x3ffffffu) + ((x >> (bk.meta & 0xffu)) & ((1u << l2b) - 1u)));
+      if (e & 0x80000000u) {  // longer still: binary search in the sorted long codes of this prefix
+        const VpzBook* vb = reinterpret_cast<const VpzBook*>(blob + reinterpret_cast<const VpzSetupHdr*>(blob)->books_off) +
+                            ((bk.meta >> 8) & 0xffu);
+        const uint32_t* ranges = blob + VPZ_LDG(&vb->range_off);
+        const uint32_t* lcode = blob + VPZ_LDG(&vb->lcode_off);
+        const uint32_t* linfo = blob + VPZ_LDG(&vb->linfo_off);
+        uint32_t id = e & 0x7fffffffu;
+        uint32_t lo = VPZ_LDG(ranges + 2 * id), hi = VPZ_LDG(ranges + 2 * id + 1);
+        uint32_t m = __brev(x);
+        while (hi - lo > 1) {
+          uint32_t mid = (lo + hi) >> 1;
+          if (VPZ_LDG(lcode + mid) <= m) lo = mid; else hi = mid;
+        }
+        uint32_t info = VPZ_LDG(linfo + lo);
+        uint32_t len = info & 0xffu;
+        e = (((m ^ VPZ_LDG(lcode + lo)) >> (32u - len)) == 0u) ? info : 0u;
       }
-      uint32_t info = VPZ_LDG(linfo + lo);
-      uint32_t len = info & 0xffu;
-      e = (((m ^ VPZ_LDG(lcode + lo)) >> (32u - len)) == 0u) ? info : 0u;
     }
     if (e != 0u) {
-      int len = (int)(e & 0xffu);
       sym = (int)(e >> 8);
-      int np = b.pos + len;
-      if (np > b.nbits) {  // SkipBits past the end: VorbisPacket.cs:248-292
-        np = b.nbits;
-        b.is_short = 1;
-      }
-      k1_bits_seek(b, np);
+      int np = b.pos + (int)(e & 0xffu);
+      // SkipBits past the end (VorbisPacket.cs:248-292) stops at the end of the packet
+      k1_bits_seek(b, P.bytes, np > b.nbits ? b.nbits : np);
     }
   }
   if (DEBUG) {
@@ -218,20 +221,19 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   const VpzBook* books = reinterpret_cast<const VpzBook*>(blob + H->books_off);
   const int half_max = 1 << (H->log2_size1 - 1);
   uint32_t* rec = P.rec + pk.rec_off;
-  uint16_t* ent = P.ent + pk.ent_off;
 
   K1Bits b;
-  k1_bits_init(b, P.bytes + (pk.byte_off >> 2), (int)pk.byte_len);
+  k1_bits_init(b, P.bytes, pk.byte_off >> 2, (int)pk.byte_len);
   int nscal = 0, ncls = 0;
 
   // StreamDecoder.DecodeNextPacket (StreamDecoder.cs:728-741): the host only queues packets whose
   // type bit is 0 and whose mode exists, so these reads just advance the cursor.
-  k1_read(b, 1);
-  const int mode_idx = (int)k1_read(b, H->mode_bits);
+  k1_read(b, P.bytes, 1);
+  const int mode_idx = (int)k1_read(b, P.bytes, H->mode_bits);
   const VpzMode* modes = reinterpret_cast<const VpzMode*>(blob + H->modes_off);
   const int long_block = modes[mode_idx].block_flag;
   const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + modes[mode_idx].mapping;
-  if (long_block) k1_read(b, 2);  // prev/next window flags (Mode.cs:38), geometry is the host's job
+  if (long_block) k1_read(b, P.bytes, 2);  // prev/next window flags (Mode.cs:38), geometry is the host's job
   const int half = long_block ? half_max : (1 << (H->log2_size0 - 1));
 
   // ---- floor unpack + unwrap, channel by channel (Mapping.cs:106-116, Floor1.cs:162-219, 270-353) ----
@@ -241,10 +243,10 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
     short po[VPZ_MAX_POSTS + 1];   // raw posts
     short fy[VPZ_MAX_POSTS + 1];   // unwrapped Y
     int count = 0, written = 0;  // written: posts stored before a failed decode reset the count
-    if (k1_read(b, 1) == 1) {
+    if (k1_read(b, P.bytes, 1) == 1) {
       const int ybits = fl->ybits;
-      po[0] = (short)k1_read(b, ybits);
-      po[1] = (short)k1_read(b, ybits);
+      po[0] = (short)k1_read(b, P.bytes, ybits);
+      po[1] = (short)k1_read(b, P.bytes, ybits);
       count = written = 2;
       const int nparts = fl->partitions;
       for (int i = 0; i < nparts && count > 0; i++) {
@@ -350,7 +352,8 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(blob + H->residues_off) + mp->submap_residue[0];
   const K1ResGeom g = k1_res_geom(rs, C, half, noexec);
   int status = 0;
-  uint32_t n_ent = 0;
+  uint32_t ent_pos = pk.ent_off;   // multiple of 4 (engine.cpp)
+  uint32_t ent_lo = 0, ent_hi = 0;
   if (g.part_count > 0 && g.any && rs->max_stages > 0) {
     // Residue0.Decode (Residue0.cs:117-206) walks  stage -> partition group -> [stage 0: classwords] ->
     // partition -> vector.  Here the walk is flattened so that every trip round the loop decodes
@@ -362,20 +365,19 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
     //    which is also the decode order inside a stage);
     //  * stages >= 1 walk their bit array with find-first-set;
     //  * the book and the codeword count of a unit come from unit_tab[class][stage] in one 8-byte load.
-    uint8_t cls[K1_MAX_UNITS];                       // class per unit, decode order
     uint32_t smask[8 * (K1_MAX_UNITS / 32)];         // [stage][chunk of 32 units]; row 0 unused
-    uint8_t* rec_cls = reinterpret_cast<uint8_t*>(rec + K1_REC_HDR + C * K1_SEG_WORDS);
+    // class per unit in decode order: written to the record for K1b and read back from there (plain
+    // loads: the lane reads its own stores)
+    uint8_t* rec_cls = reinterpret_cast<uint8_t*>(P.rec + pk.rec_off + K1_REC_HDR + C * K1_SEG_WORDS);
     const K1Book cb = k1_book(blob, books, rs->class_book);
     const int cdim = rs->cdim, nvec = g.nvec, part_count = g.part_count;
     const int partvals = (int)rs->partvals;
     const int max_stages = rs->max_stages;
-    const uint8_t* dmap = reinterpret_cast<const uint8_t*>(blob + rs->decode_map_off);
-    const uint2* unit_tab = reinterpret_cast<const uint2*>(blob + rs->unit_tab_off);
-    const uint32_t* cw_tab = blob + rs->cw_tab_off;
+    const uint32_t dmap_off = rs->decode_map_off, unit_tab_off = rs->unit_tab_off, cw_tab_off = rs->cw_tab_off;
     const int nunits = part_count * nvec;
     const int nchunks = (nunits + 31) >> 5;
     // classes of groups a truncated packet never reaches must still be valid indices for K1b
-    for (int u = 0; u < nunits; u++) rec_cls[u] = 0;
+    for (int u = 0; u < (nunits + 3) >> 2; u++) reinterpret_cast<uint32_t*>(rec_cls)[u] = 0;
     for (int i = nchunks; i < max_stages * nchunks; i++) smask[i] = 0;
     uint32_t vecmask = 0;                  // vectors that are decoded
     for (int v = 0; v < nvec; v++)
@@ -408,17 +410,17 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
             for (; dbg_slot <= upto; dbg_slot++) {
               const int k = dbg_slot / nvec, v = dbg_slot - k * nvec;
               if (gpart + k >= part_count || !((vecmask >> v) & 1u)) continue;
-              if (P.dbg.classes && ncls < P.dbg.classes_cap) P.dbg.classes[ncls] = cls[(gpart + k) * nvec + v];
+              if (P.dbg.classes && ncls < P.dbg.classes_cap) P.dbg.classes[ncls] = rec_cls[(gpart + k) * nvec + v];
               ncls++;
             }
           }
           if (cur_mask) {
             const int u = ubase + __ffs((int)cur_mask) - 1;
             cur_mask &= cur_mask - 1;
-            const uint2 t = VPZ_LDG(unit_tab + (cls[u] * 8 + stage));
-            cur.l1 = blob + t.x;
+            const uint2 t = VPZ_LDG(reinterpret_cast<const uint2*>(blob + unit_tab_off) + (rec_cls[u] * 8 + stage));
+            cur.l1_off = t.x;
             cur.l1_mask = (1u << (t.y & 0xffu)) - 1u;
-            cur.bk = books + ((t.y >> 8) & 0xffu);
+            cur.meta = t.y;
             rem = (int)(t.y >> 16);
             break;
           }
@@ -454,14 +456,11 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
           break;
         }
         const int left = part_count - gpart;   // partitions of this (possibly partial, last) group
+        const uint8_t* dmap = reinterpret_cast<const uint8_t*>(blob + dmap_off) + sym * cdim;
         for (int kk = 0; kk < cdim; kk++)
-          if (kk < left) {
-            const uint8_t c = dmap[sym * cdim + kk];
-            cls[(gpart + kk) * nvec + cw_v] = c;
-            rec_cls[cw_v * part_count + gpart + kk] = c;
-          }
+          if (kk < left) rec_cls[(gpart + kk) * nvec + cw_v] = dmap[kk];
         const uint32_t lim = left * nvec >= 32 ? 0xffffffffu : (1u << (left * nvec)) - 1u;
-        const uint32_t* ct = cw_tab + ((size_t)cw_v * partvals + sym) * max_stages;
+        const uint32_t* ct = blob + cw_tab_off + ((size_t)cw_v * partvals + sym) * max_stages;
         grp_acc |= VPZ_LDG(ct) & lim;
         const int u0 = gpart * nvec, c0 = u0 >> 5, sh = u0 & 31;
         for (int s2 = 1; s2 < max_stages; s2++) {
@@ -482,13 +481,22 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
           status = 1;
           break;
         }
-        ent[n_ent++] = (uint16_t)sym;
+        // four entry indices per 8-byte store: a lane's store is its own L1 tag lookup, and the entry
+        // stream is the bulk of K1a's memory requests
+        const int q = (int)(ent_pos & 3u) * 16;
+        if (q < 32) ent_lo |= (uint32_t)sym << q; else ent_hi |= (uint32_t)sym << (q - 32);
+        ent_pos++;
+        if (q == 48) {
+          *reinterpret_cast<uint2*>(P.ent + (ent_pos - 4)) = uint2{ent_lo, ent_hi};
+          ent_lo = ent_hi = 0;
+        }
         rem--;
       }
     }
   }
   rec[0] = own_mask | (noexec << 8) | ((uint32_t)status << 16) | ((uint32_t)long_block << 24);
-  rec[1] = n_ent;
+  if (ent_pos & 3u) *reinterpret_cast<uint2*>(P.ent + (ent_pos & ~3u)) = uint2{ent_lo, ent_hi};
+  rec[1] = ent_pos - pk.ent_off;
   rec[2] = (uint32_t)b.pos;
   rec[3] = 0;
   if (DEBUG && P.dbg.hdr) {
@@ -575,7 +583,7 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
         if (u < nunits) {
           const int part = u / g.nvec, v = u - part * g.nvec;
           if (!((g.skip >> v) & 1u)) {
-            const int c = rec_cls[v * g.part_count + part];
+            const int c = rec_cls[u];
             if (((rs->cascade[c] >> stage) & 1u) && rs->has_books[c]) {
               const VpzBook* bk = books + rs->books[c][stage];
               const int dims = k1_book_dims(bk);
@@ -935,7 +943,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
       int c = -1;
       if (u < nunits) {
         const int part = u / g.nvec, v = u - part * g.nvec;
-        if (!((g.skip >> v) & 1u)) c = rec_cls[v * g.part_count + part];
+        if (!((g.skip >> v) & 1u)) c = rec_cls[u];
       }
 #pragma unroll
       for (int s = 0; s < 8; s++) {

@@ -272,18 +272,49 @@ void build_decode_tables(const HostBook& hb, int l1_bits_cfg, BlobWriter& bw, Vp
     }
   }
   std::sort(longs.begin(), longs.end(), [](const LongCode& a, const LongCode& b) { return a.msb < b.msb; });
+  // Second level: per long prefix a table over the next l2 bits (l2 = longest code under the prefix
+  // minus l1, at most VPZ_L2_BITS_MAX), entries as in the first level.  Codes that are longer still
+  // (probability <= 2^-(l1 + VPZ_L2_BITS_MAX) per symbol) keep the sorted-array bisection: their
+  // second-level slot holds 0x80000000 | range id.
   std::vector<uint32_t> ranges;  // {lo, hi} pairs
+  std::vector<uint32_t> l2tab;
+  struct Fix {
+    uint32_t prefix, rel, bits;
+  };
+  std::vector<Fix> fix;
   for (size_t i = 0; i < longs.size();) {
     size_t j = i;
-    while (j < longs.size() && longs[j].prefix == longs[i].prefix) ++j;
+    int longest = 0;
+    while (j < longs.size() && longs[j].prefix == longs[i].prefix) {
+      longest = std::max(longest, (int)(longs[j].info & 0xffu));
+      ++j;
+    }
     uint32_t id = (uint32_t)(ranges.size() / 2);
     ranges.push_back((uint32_t)i);
     ranges.push_back((uint32_t)j);
-    l1tab[longs[i].prefix] = 0x80000000u | id;
+    const int l2 = std::min(longest - l1, VPZ_L2_BITS_MAX);
+    const uint32_t rel = (uint32_t)l2tab.size();
+    l2tab.resize(l2tab.size() + ((size_t)1 << l2), 0u);
+    for (size_t k = i; k < j; k++) {
+      const int len = (int)(longs[k].info & 0xffu);
+      const uint32_t code = bitrev32(longs[k].msb);          // back to the LSB-first stream value
+      const uint32_t sub = code >> l1;                       // the len - l1 bits after the prefix
+      if (len - l1 <= l2) {
+        const int reps = 1 << (l2 - (len - l1));
+        for (int q = 0; q < reps; q++) l2tab[rel + (((uint32_t)q << (len - l1)) | sub)] = longs[k].info;
+      } else {
+        l2tab[rel + (sub & ((1u << l2) - 1u))] = 0x80000000u | id;
+      }
+    }
+    fix.push_back(Fix{longs[i].prefix, rel, (uint32_t)l2});
     i = j;
   }
   bw.align(4);
   out.l1_off = bw.reserve(l1tab.size());
+  const uint32_t l2_off = bw.reserve(l2tab.size());
+  if (!l2tab.empty()) memcpy(&bw.w[l2_off], l2tab.data(), l2tab.size() * 4);
+  // first-level entry of a long prefix: 0x80000000 | (second-level word offset from l1_off) << 5 | l2 bits
+  for (const Fix& f : fix) l1tab[f.prefix] = 0x80000000u | ((l2_off - out.l1_off + f.rel) << 5) | f.bits;
   memcpy(&bw.w[out.l1_off], l1tab.data(), l1tab.size() * 4);
   out.range_off = bw.reserve(ranges.size());
   if (!ranges.empty()) memcpy(&bw.w[out.range_off], ranges.data(), ranges.size() * 4);

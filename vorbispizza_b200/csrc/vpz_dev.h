@@ -12,11 +12,14 @@
 #define VPZ_MAX_BOOKS 256
 #define VPZ_MAX_MODES 64
 #define VPZ_L1_BITS_DEFAULT 9 // first-level Huffman table width (reference: 10, Huffman.cs:12)
+#define VPZ_L2_BITS_MAX 8      // second-level table width
 
 // ---- codebook (Codebook.cs, Huffman.cs) ------------------------------------------------
 // L1 table entry: (value << 8) | length for codes with length <= l1_bits, replicated over the
 // don't-care bits exactly like Huffman.GenerateTable.  Codes longer than l1_bits:
-// 0x80000000 | range_id, where range_id indexes `ranges` = {lo, hi} into the long-code arrays
+// 0x80000000 | (L2 word offset from l1_off) << 5 | l2_bits: a second table over the next l2_bits
+// stream bits with the same entry format; codes longer than l1_bits + VPZ_L2_BITS_MAX leave
+// 0x80000000 | range_id there, where range_id indexes `ranges` = {lo, hi} into the long-code arrays
 // (sorted by MSB-first left-aligned code).  0 = no code with this prefix (DecodeScalar -> -1).
 struct VpzBook {
   uint32_t l1_off;      // word offset of the L1 table, 1 << l1_bits entries
@@ -111,7 +114,7 @@ struct VpzSetupHdr {
 // ---- per-packet descriptors ------------------------------------------------------------
 // K1 input: where the packet bytes are and where its spectrum goes.
 struct alignas(16) VpzPktIn {
-  uint32_t byte_off;        // into the batch byte buffer; packet is followed by >= 8 zero bytes
+  uint32_t byte_off;        // into the batch byte buffer; packet is followed by >= 12 zero bytes
   uint32_t byte_len;
   uint32_t spec_off;        // float offset of [channels][n/2] in the spectrum buffer
   uint32_t setup_slot;      // index into the batch's setup pointer table
