@@ -102,6 +102,7 @@ inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
   uint64_t v = ((uint64_t)hi << 32) | lo;
   return (uint32_t)(v >> sh);
 }
+inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline int __ffs(int x) { return __builtin_ffs(x); }
 inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 inline int __ffsll(long long x) { return __builtin_ffsll(x); }

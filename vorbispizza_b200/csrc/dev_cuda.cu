@@ -214,7 +214,7 @@ int launch_k1a(const K1Params& p, bool debug, int blocks, Stream* s, std::string
 int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err) {
   if (p.n_pkts == 0) return VPZ_OK;
   // gather path: smem_words_per_warp per warp; general path: per CTA
-  size_t smem = (size_t)p.smem_words_per_warp * 4 * (p.gather_ok ? warps : 1);
+  size_t smem = (size_t)p.smem_words_per_warp * 4 * (p.gather_ok ? warps : 1) + (p.gather_ok ? 1024 : 0);  // + the dB table
   if (smem > g_max_smem) {
     err = "K1b shared memory request exceeds the device limit";
     return VPZ_E_UNSUPPORTED;

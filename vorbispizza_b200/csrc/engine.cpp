@@ -76,7 +76,8 @@ static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
       // k1b gather layout per warp: urec stages*U*4 + ybuf C*half_max/4 + sg C*4*66 (+ pad, multiple of 32)
       s->k1g_words = (uint32_t)(((size_t)max_stages * U * 4 + (size_t)C * half_max / 4 + (size_t)C * 4 * 66 + 8 + 31) & ~(size_t)31);
     }
-    s->rec_words = (uint32_t)(4 + h->channels * 68 + (units + 3) / 4 + 1);  // K1_REC_HDR, K1_SEG_WORDS
+    // K1_REC_HDR, K1_SEG_WORDS, classes; a multiple of 4 words so every record starts on a 16-byte boundary
+    s->rec_words = (uint32_t)((4 + h->channels * 68 + (units + 3) / 4 + 1 + 3) & ~(size_t)3);
   }
   size_t bytes = s->host.blob.size() * 4;
   s->d_blob = dev::alloc(bytes, ctx->last_error);
@@ -583,7 +584,7 @@ int batch_decode(vpz_batch* b, int clip) {
     // K1b: persistent CTAs of 4 warps fed by a counter; gather path = one warp per packet (shared
     // memory per warp), general path = one CTA per packet
     const int warps = 4;
-    size_t smem_block = (size_t)k1w * 4 * (gather ? warps : 1);
+    size_t smem_block = (size_t)k1w * 4 * (gather ? warps : 1) + (gather ? 1024 : 0);   // + the dB table
     size_t per_sm = std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem_block + 1024)));
     size_t blocks = std::min<size_t>(gather ? (np + warps - 1) / warps : np, per_sm * (size_t)dev::sm_count());
     if ((rc = dev::launch_k1b(p, debug, (int)std::max<size_t>(1, blocks), warps, st, err))) return rc;

@@ -55,7 +55,7 @@
 //   [0] own_mask | noexec_mask << 8 | status << 16 | long_block << 24
 //   [1] number of VQ entries written at P.ent + pkt.ent_off (uint16 each)
 //   [2] final bit cursor
-//   [3] reserved
+//   [3] mapping index | residue index << 8 (found through the mode; K1b does not walk the packet again)
 //   then per channel K1_SEG_WORDS words: [0] = number of line segments n, [1..n+1] = points x | y << 16
 //   then one byte per unit (partition * nvec + vector, the decode order inside a stage): the partition class
 #define K1_REC_HDR 4
@@ -498,7 +498,7 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   if (ent_pos & 3u) *reinterpret_cast<uint2*>(P.ent + (ent_pos & ~3u)) = uint2{ent_lo, ent_hi};
   rec[1] = ent_pos - pk.ent_off;
   rec[2] = (uint32_t)b.pos;
-  rec[3] = 0;
+  rec[3] = (uint32_t)modes[mode_idx].mapping | ((uint32_t)mp->submap_residue[0] << 8);
   if (DEBUG && P.dbg.hdr) {
     int32_t* h = P.dbg.hdr;
     h[DUMP_STATUS] = 0;
@@ -785,12 +785,12 @@ VPZ_DEV void k1g_fetch_chunk(const K1Gather& G, int v, int p, float* acc) {
   const int off = rel - part * G.psize;
   const int u = part * G.nvec + v;
   for (int s = 0; s < G.max_stages; s++) {
-    const uint32_t* R = G.urec + (size_t)(s * G.U + u) * 4;
-    const uint32_t info = R[0];
+    const uint4 R = *reinterpret_cast<const uint4*>(G.urec + (size_t)(s * G.U + u) * 4);
+    const uint32_t info = R.x;
     if (!info) continue;
     const int dsh = (int)((info >> 8) & 0xfu);
-    const uint32_t e0 = R[1] + (uint32_t)(off >> dsh);
-    const float* vq = reinterpret_cast<const float*>(G.blob + R[2]);
+    const uint32_t e0 = R.y + (uint32_t)(off >> dsh);
+    const float* vq = reinterpret_cast<const float*>(G.blob + R.z);
     const uint16_t* ep = G.ent + e0;
     const uint32_t left = e0 < G.n_ent ? G.n_ent - e0 : 0u;   // truncated packet: keep what was decoded
     if (dsh == 1) {
@@ -847,27 +847,26 @@ VPZ_DEV void k1g_fetch_chunk(const K1Gather& G, int v, int p, float* acc) {
 
 // Inverse square-polar coupling of one (magnitude, angle) pair (Mapping.cs:235-267)
 VPZ_DEV void k1_uncouple(float& m, float& a) {
-  float nm = m, na = m;
-  if (m > 0.f) {
-    if (a > 0.f) na = __fsub_rn(m, a); else nm = __fadd_rn(m, a);
-  } else {
-    if (a > 0.f) na = __fadd_rn(m, a); else nm = __fsub_rn(m, a);
-  }
-  m = nm;
-  a = na;
+  // the four cases of the reference as selects: with t = (m > 0 ? a : -a) the new angle is m - t when
+  // a > 0 and the new magnitude m + t otherwise (x - y and x + (-y) round identically)
+  const float t = m > 0.f ? a : -a;
+  const float d = __fsub_rn(m, t), sm = __fadd_rn(m, t);
+  const bool p = a > 0.f;
+  a = p ? d : m;
+  m = p ? m : sm;
 }
 
 template <bool DEBUG>
-VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, int tid) {
+VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, const float* dbtab, int tid) {
   const int lane = tid;   // ONE WARP per packet: many packets in flight per SM hide the per-packet load latency
   const VpzPktIn pk = P.pkts[pkt_idx];
   const uint32_t* blob = P.setups[pk.setup_slot];
   const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
   const int C = H->channels;
-  const VpzBook* books = reinterpret_cast<const VpzBook*>(blob + H->books_off);
   const int half_max = 1 << (H->log2_size1 - 1);
   const uint32_t* rec = P.rec + pk.rec_off;
-  const uint32_t hdr = rec[0];
+  const uint4 rh = *reinterpret_cast<const uint4*>(rec);   // records start on 16-byte boundaries (engine.cpp)
+  const uint32_t hdr = rh.x;
   const uint32_t own_mask = hdr & 0xffu, noexec = (hdr >> 8) & 0xffu;
   const int long_block = (int)(hdr >> 24) & 1;
   const int half = long_block ? half_max : (1 << (H->log2_size0 - 1));
@@ -876,22 +875,19 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
     VpzPktRes r;
     r.exec_mask = (uint8_t)own_mask;
     r.status = (uint8_t)((hdr >> 16) & 0xffu);
-    r.bits_used_lo = (uint16_t)rec[2];
+    r.bits_used_lo = (uint16_t)rh.z;
     P.res[pkt_idx] = r;
   }
   if (own_mask == 0 && !(DEBUG && P.dbg.residue)) return;  // every channel silent: K3 outputs zeros
 
-  const uint32_t w0 = VPZ_LDG(P.bytes + (pk.byte_off >> 2));
-  const int mode_idx = (int)((w0 >> 1) & ((1u << H->mode_bits) - 1u));
-  const VpzMode* modes = reinterpret_cast<const VpzMode*>(blob + H->modes_off);
-  const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + modes[mode_idx].mapping;
-  const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(blob + H->residues_off) + mp->submap_residue[0];
+  // mapping and residue index come with the record (K1a found them through the mode): no second walk
+  const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + (rh.w & 0xffu);
+  const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(blob + H->residues_off) + ((rh.w >> 8) & 0xffu);
   const K1ResGeom g = k1_res_geom(rs, C, half, noexec);
   const int nunits = g.part_count * g.nvec;
   const int U = (nunits + 31) & ~31;
   const int max_stages = rs->max_stages;
 
-  const float* dbtab = reinterpret_cast<const float*>(blob + H->db_off);   // 1 KB, L1 resident
   uint32_t* urec = smem;
   uint8_t* ybuf = reinterpret_cast<uint8_t*>(urec + (size_t)max_stages * U * 4);   // [C][half_max] bytes
   uint32_t* sgbase = reinterpret_cast<uint32_t*>(ybuf) + (C * half_max) / 4;        // [C][4*66]
@@ -900,7 +896,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   G.urec = urec;
   G.blob = blob;
   G.ent = P.ent + pk.ent_off;
-  G.n_ent = rec[1];
+  G.n_ent = rh.y;
   G.max_stages = max_stages;
   G.U = U;
   G.nvec = g.nvec;
@@ -926,7 +922,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
       sg[4 * s] = (uint32_t)x0 | ((uint32_t)x1 << 16);
       sg[4 * s + 1] = (uint32_t)(y0 & 0xffff) | ((uint32_t)base << 16);          // |base| of the DDA
       sg[4 * s + 2] = (uint32_t)(ady - base * adx) | (dy < 0 ? 0x80000000u : 0u); // remainder step, sign
-      sg[4 * s + 3] = 0;
+      reinterpret_cast<float*>(sg)[4 * s + 3] = 1.0f / (float)(adx > 0 ? adx : 1);
     }
   }
 
@@ -945,19 +941,17 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
         const int part = u / g.nvec, v = u - part * g.nvec;
         if (!((g.skip >> v) & 1u)) c = rec_cls[u];
       }
+      const uint2* ut = reinterpret_cast<const uint2*>(blob + rs->unit_tabb_off) + (c < 0 ? 0 : c) * 8;
 #pragma unroll
       for (int s = 0; s < 8; s++) {
         cnt[s] = 0;
         info[s] = vqo[s] = 0;
         if (s < max_stages) {
-          if (c >= 0 && ((rs->cascade[c] >> s) & 1u) && rs->has_books[c]) {
-            const int book = rs->books[c][s];
-            const int dims = k1_book_dims(books + book);
-            cnt[s] = k1_unit_entries(g.rtype, g.psize, dims);
-            if (cnt[s] > 0) {
-              info[s] = (uint32_t)(dims & 0xff) | ((uint32_t)(31 - __clz(dims)) << 8);   // dims is a power of two (host-checked)
-              vqo[s] = VPZ_LDG(&books[book].vq_off);
-            }
+          if (c >= 0) {   // {dims | log2 dims << 8 | entries << 16, vq word offset}; 0: no codewords for (class, stage)
+            const uint2 t = VPZ_LDG(ut + s);
+            info[s] = t.x & 0xffffu;
+            cnt[s] = (int)(t.x >> 16);
+            vqo[s] = t.y;
           }
           int incl = cnt[s];
 #pragma unroll
@@ -1006,38 +1000,47 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
     const uint32_t* sg = sgbase + ch * 4 * 66;
     uint8_t* yb = ybuf + ch * half_max;
     const int nseg = (int)rec[K1_REC_HDR + ch * K1_SEG_WORDS];
-    for (int xb = tid * 16; xb < half; xb += 32 * 16) {
+    for (int xb = tid * 16; xb < half; xb += 32 * 16) {   // half is a multiple of 16 (host-checked)
       int lo = 0, hi = nseg;                                   // x0[lo] <= xb < x0[hi]
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if ((int)(sg[4 * mid] & 0xffffu) <= xb) lo = mid; else hi = mid;
       }
       int si = lo;
-      uint32_t w0s = sg[4 * si], w1s = sg[4 * si + 1], w2s = sg[4 * si + 2];
-      int x1 = (int)(w0s >> 16), adx = x1 - (int)(w0s & 0xffffu);
-      int base = (int)(w1s >> 16), rem = (int)(w2s & 0x7fffffffu), sy = (w2s >> 31) ? -1 : 1;
-      // state of the DDA after k = xb - x0 steps: y = y0 + sy * (k * base + floor(k * rem / adx))
-      const int k = xb - (int)(w0s & 0xffffu);
-      int t = k * rem;
-      int q = adx > 0 ? t / adx : 0;
+      uint4 w = *reinterpret_cast<const uint4*>(sg + 4 * si);
+      int x1 = (int)(w.x >> 16), adx = x1 - (int)(w.x & 0xffffu);
+      int base = (int)(w.y >> 16), rem = (int)(w.z & 0x7fffffffu), sy = (w.z >> 31) ? -1 : 1;
+      // state of the DDA after k = xb - x0 steps: y = y0 + sy * (k * base + floor(k * rem / adx)).
+      // k * rem < adx^2 <= 2^24, so the quotient is one float multiply by 1/adx and an exact fix-up
+      const int k = xb - (int)(w.x & 0xffffu);
+      const int t = k * rem;
+      int q = (int)((float)t * __uint_as_float(w.w));
       int err = t - q * adx;
-      int y = (int)(short)(w1s & 0xffffu) + sy * (k * base + q);
-      const int xe = xb + 16 < half ? xb + 16 : half;
-      for (int x = xb; x < xe; x++) {
+      if (err < 0) {
+        q--;
+        err += adx;
+      } else if (err >= adx) {
+        q++;
+        err -= adx;
+      }
+      int y = (int)(short)(w.y & 0xffffu) + sy * (k * base + q);
+      uint32_t yw[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        const int x = xb + j;
         if (x >= x1 && si + 1 < nseg) {   // next segment starts exactly at its first post
           si++;
-          w0s = sg[4 * si];
-          w1s = sg[4 * si + 1];
-          w2s = sg[4 * si + 2];
-          x1 = (int)(w0s >> 16);
-          adx = x1 - (int)(w0s & 0xffffu);
-          base = (int)(w1s >> 16);
-          rem = (int)(w2s & 0x7fffffffu);
-          sy = (w2s >> 31) ? -1 : 1;
+          w = *reinterpret_cast<const uint4*>(sg + 4 * si);
+          x1 = (int)(w.x >> 16);
+          adx = x1 - (int)(w.x & 0xffffu);
+          base = (int)(w.y >> 16);
+          rem = (int)(w.z & 0x7fffffffu);
+          sy = (w.z >> 31) ? -1 : 1;
           err = 0;
-          y = (int)(short)(w1s & 0xffffu);
+          y = (int)(short)(w.y & 0xffffu);
         }
-        yb[x] = (uint8_t)(y < 0 ? 0 : (y > 255 ? 255 : y));   // the reference reads the table unchecked (quirk Q2)
+        const int yc = y < 0 ? 0 : (y > 255 ? 255 : y);   // the reference reads the table unchecked (quirk Q2)
+        yw[j >> 2] |= (uint32_t)yc << (8 * (j & 3));
         err += rem;
         y += sy * base;
         if (err >= adx) {
@@ -1045,6 +1048,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
           y += sy;
         }
       }
+      *reinterpret_cast<uint4*>(yb + xb) = uint4{yw[0], yw[1], yw[2], yw[3]};
     }
   }
   __syncwarp();
@@ -1093,30 +1097,30 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
     }
     // floor multiply (one rounded product per bin, Floor1.cs:383,395) and store
     if (own_mask & 1u) {
-      const uint8_t* yb = ybuf + x0;
+      const uint2 yy = *reinterpret_cast<const uint2*>(ybuf + x0);
       float4 o0, o1;
-      o0.x = __fmul_rn(c0[0], VPZ_LDG(dbtab + yb[0]));
-      o0.y = __fmul_rn(c0[1], VPZ_LDG(dbtab + yb[1]));
-      o0.z = __fmul_rn(c0[2], VPZ_LDG(dbtab + yb[2]));
-      o0.w = __fmul_rn(c0[3], VPZ_LDG(dbtab + yb[3]));
-      o1.x = __fmul_rn(c0[4], VPZ_LDG(dbtab + yb[4]));
-      o1.y = __fmul_rn(c0[5], VPZ_LDG(dbtab + yb[5]));
-      o1.z = __fmul_rn(c0[6], VPZ_LDG(dbtab + yb[6]));
-      o1.w = __fmul_rn(c0[7], VPZ_LDG(dbtab + yb[7]));
+      o0.x = __fmul_rn(c0[0], dbtab[yy.x & 0xffu]);
+      o0.y = __fmul_rn(c0[1], dbtab[(yy.x >> 8) & 0xffu]);
+      o0.z = __fmul_rn(c0[2], dbtab[(yy.x >> 16) & 0xffu]);
+      o0.w = __fmul_rn(c0[3], dbtab[yy.x >> 24]);
+      o1.x = __fmul_rn(c0[4], dbtab[yy.y & 0xffu]);
+      o1.y = __fmul_rn(c0[5], dbtab[(yy.y >> 8) & 0xffu]);
+      o1.z = __fmul_rn(c0[6], dbtab[(yy.y >> 16) & 0xffu]);
+      o1.w = __fmul_rn(c0[7], dbtab[yy.y >> 24]);
       reinterpret_cast<float4*>(out + x0)[0] = o0;
       reinterpret_cast<float4*>(out + x0)[1] = o1;
     }
     if (C == 2 && (own_mask & 2u)) {
-      const uint8_t* yb = ybuf + half_max + x0;
+      const uint2 yy = *reinterpret_cast<const uint2*>(ybuf + half_max + x0);
       float4 o0, o1;
-      o0.x = __fmul_rn(c1[0], VPZ_LDG(dbtab + yb[0]));
-      o0.y = __fmul_rn(c1[1], VPZ_LDG(dbtab + yb[1]));
-      o0.z = __fmul_rn(c1[2], VPZ_LDG(dbtab + yb[2]));
-      o0.w = __fmul_rn(c1[3], VPZ_LDG(dbtab + yb[3]));
-      o1.x = __fmul_rn(c1[4], VPZ_LDG(dbtab + yb[4]));
-      o1.y = __fmul_rn(c1[5], VPZ_LDG(dbtab + yb[5]));
-      o1.z = __fmul_rn(c1[6], VPZ_LDG(dbtab + yb[6]));
-      o1.w = __fmul_rn(c1[7], VPZ_LDG(dbtab + yb[7]));
+      o0.x = __fmul_rn(c1[0], dbtab[yy.x & 0xffu]);
+      o0.y = __fmul_rn(c1[1], dbtab[(yy.x >> 8) & 0xffu]);
+      o0.z = __fmul_rn(c1[2], dbtab[(yy.x >> 16) & 0xffu]);
+      o0.w = __fmul_rn(c1[3], dbtab[yy.x >> 24]);
+      o1.x = __fmul_rn(c1[4], dbtab[yy.y & 0xffu]);
+      o1.y = __fmul_rn(c1[5], dbtab[(yy.y >> 8) & 0xffu]);
+      o1.z = __fmul_rn(c1[6], dbtab[(yy.y >> 16) & 0xffu]);
+      o1.w = __fmul_rn(c1[7], dbtab[yy.y >> 24]);
       reinterpret_cast<float4*>(out + half + x0)[0] = o0;
       reinterpret_cast<float4*>(out + half + x0)[1] = o1;
     }
@@ -1130,13 +1134,21 @@ VPZ_DEV void k1b_cta_loop(const K1Params& P, uint32_t* smem, uint32_t* s_idx) {
   const int tid = (int)threadIdx.x;
   if (P.gather_ok) {
     const int lane = tid & 31, warp = tid >> 5;
-    uint32_t* my = smem + (size_t)warp * P.smem_words_per_warp;
+    // inverse_dB_table (Floor1.cs:407-473): identical in every setup image, staged once per CTA
+    float* dbtab = reinterpret_cast<float*>(smem);
+    {
+      const uint32_t* blob0 = P.setups[0];
+      const float* db = reinterpret_cast<const float*>(blob0 + reinterpret_cast<const VpzSetupHdr*>(blob0)->db_off);
+      for (int i = tid; i < 256; i += K1B_THREADS) dbtab[i] = VPZ_LDG(db + i);
+    }
+    __syncthreads();
+    uint32_t* my = smem + 256 + (size_t)warp * P.smem_words_per_warp;
     for (;;) {
       uint32_t idx = 0;
       if (lane == 0) idx = atomicAdd(P.counter + 2, 1u);
       idx = __shfl_sync(0xffffffffu, idx, 0);
       if (idx >= P.n_pkts) break;
-      k1b_build_packet_gather<DEBUG>(P, idx, my, lane);
+      k1b_build_packet_gather<DEBUG>(P, idx, my, dbtab, lane);
     }
   } else {
     for (;;) {

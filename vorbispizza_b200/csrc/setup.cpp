@@ -666,6 +666,7 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
     uint32_t active[64] = {0};   // per class: bit s set when stage s decodes codewords for a partition of that class
     bw.align(2);
     r.unit_tab_off = bw.reserve((size_t)r.classifications * 8 * 2);
+    r.unit_tabb_off = bw.reserve((size_t)r.classifications * 8 * 2);
     for (int c = 0; c < r.classifications; c++)
       for (int s = 0; s < 8; s++) {
         if (!(((r.cascade[c] >> s) & 1) && r.has_books[c])) continue;
@@ -680,6 +681,10 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
         }
         blob[r.unit_tab_off + (size_t)(c * 8 + s) * 2] = dbooks[bk].l1_off;
         blob[r.unit_tab_off + (size_t)(c * 8 + s) * 2 + 1] = (uint32_t)dbooks[bk].l1_bits | ((uint32_t)bk << 8) | (n << 16);
+        int lg = 0;
+        while ((1 << (lg + 1)) <= dims) lg++;   // exact for the power-of-two dimensions the gather path accepts
+        blob[r.unit_tabb_off + (size_t)(c * 8 + s) * 2] = (uint32_t)(dims & 0xff) | ((uint32_t)lg << 8) | (n << 16);
+        blob[r.unit_tabb_off + (size_t)(c * 8 + s) * 2 + 1] = dbooks[bk].vq_off;
         active[c] |= 1u << s;
       }
     const int ns = std::max<int>(r.max_stages, 1);

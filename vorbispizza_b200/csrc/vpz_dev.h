@@ -74,6 +74,7 @@ struct VpzResidue {
   //   cw_tab   [nvec][partvals][max_stages] x uint32: for classword value `sym` of vector v, bit k * nvec + v
   //            is set when partition k of the group has codewords in that stage
   uint32_t unit_tab_off;
+  uint32_t unit_tabb_off;    // K1b: [classifications][8] x {dims | log2 dims << 8 | entries per unit << 16, VQ table word offset}
   uint32_t cw_tab_off;
   uint32_t partvals;         // classifications ^ classbook.dims
   uint16_t cdim;             // classbook.dims (partitions per classword)
