@@ -97,6 +97,15 @@ inline T __shfl_xor_sync(unsigned, T v, int x) { return emu_shfl_idx(v, emu::t_l
 template <typename T>
 inline T __shfl_up_sync(unsigned, T v, int d) { return emu_shfl_idx(v, emu::t_lane >= d ? emu::t_lane - d : emu::t_lane); }
 
+inline int __any_sync(unsigned, int pred) {
+  emu::WarpCtx* w = emu::t_block->warps[emu::t_warp];
+  w->slot[emu::t_lane] = pred ? 1u : 0u;
+  w->bar.wait();
+  int r = 0;
+  for (int i = 0; i < 32; i++) r |= (int)w->slot[i];
+  w->bar.wait();
+  return r;
+}
 inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
   sh &= 31;
   uint64_t v = ((uint64_t)hi << 32) | lo;

@@ -856,6 +856,74 @@ VPZ_DEV void k1_uncouple(float& m, float& a) {
   m = p ? m : sm;
 }
 
+// Floor1.RenderLineMulti (Floor1.cs:372-397) for 16 consecutive bins of one channel per thread: the
+// exact integer DDA, started in the middle of a segment from its closed form, one byte per bin.
+// sg: per segment {x0 | x1 << 16, y0 | |base| << 16, remainder step | sign << 31, 1 / adx}.
+// The body is kept small on purpose (4 bins unrolled, not 16): the warps of an SM sit in different
+// phases of different packets and K1b is sensitive to instruction-cache misses.
+VPZ_DEV void k1b_render_floor(const uint32_t* sg, int nseg, uint8_t* yb, int half, int tid) {
+  for (int xb = tid * 16; xb < half; xb += 32 * 16) {   // half is a multiple of 16 (host-checked)
+    int lo = 0, hi = nseg;                                   // x0[lo] <= xb < x0[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if ((int)(sg[4 * mid] & 0xffffu) <= xb) lo = mid; else hi = mid;
+    }
+    int si = lo;
+    uint4 w = *reinterpret_cast<const uint4*>(sg + 4 * si);
+    int adx = (int)(w.x >> 16) - (int)(w.x & 0xffffu);
+    int x1 = si + 1 < nseg ? (int)(w.x >> 16) : 0x7fffffff;   // the last segment never hands over
+    int rem = (int)(w.z & 0x7fffffffu), sy = (w.z >> 31) ? -1 : 1;
+    int ystep = sy * (int)(w.y >> 16);
+    // state of the DDA after k = xb - x0 steps: y = y0 + sy * (k * base + floor(k * rem / adx)).
+    // k * rem < adx^2 <= 2^24, so the quotient is one float multiply by 1/adx and an exact fix-up
+    const int k = xb - (int)(w.x & 0xffffu);
+    const int t = k * rem;
+    int q = (int)((float)t * __uint_as_float(w.w));
+    int err = t - q * adx;
+    if (err < 0) {
+      q--;
+      err += adx;
+    } else if (err >= adx) {
+      q++;
+      err -= adx;
+    }
+    int y = (int)(short)(w.y & 0xffffu) + k * ystep + sy * q;
+    uint32_t* yout = reinterpret_cast<uint32_t*>(yb + xb);
+    int x = xb;
+#pragma unroll 1
+    for (int jw = 0; jw < 4; jw++) {
+      uint32_t word = 0;
+#pragma unroll
+      for (int j = 0; j < 4; j++, x++) {
+        if (x >= x1) {   // next segment starts exactly at its first post
+          si++;
+          w = *reinterpret_cast<const uint4*>(sg + 4 * si);
+          adx = (int)(w.x >> 16) - (int)(w.x & 0xffffu);
+          x1 = si + 1 < nseg ? (int)(w.x >> 16) : 0x7fffffff;
+          rem = (int)(w.z & 0x7fffffffu);
+          sy = (w.z >> 31) ? -1 : 1;
+          ystep = sy * (int)(w.y >> 16);
+          err = 0;
+          y = (int)(short)(w.y & 0xffffu);
+        }
+        const uint32_t yc = (uint32_t)(y < 0 ? 0 : (y > 255 ? 255 : y));   // the reference reads the table unchecked (quirk Q2)
+#ifndef VPZ_EMU
+        word = __byte_perm(word, yc, j == 0 ? 0x3214 : j == 1 ? 0x3240 : j == 2 ? 0x3410 : 0x4210);   // byte j <- yc
+#else
+        word |= yc << (8 * j);
+#endif
+        err += rem;
+        y += ystep;
+        if (err >= adx) {
+          err -= adx;
+          y += sy;
+        }
+      }
+      yout[jw] = word;
+    }
+  }
+}
+
 template <bool DEBUG>
 VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, const float* dbtab, int tid) {
   const int lane = tid;   // ONE WARP per packet: many packets in flight per SM hide the per-packet load latency
@@ -994,62 +1062,13 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   }
   __syncwarp();
 
-  // ---- phase C: floor curve as one byte per bin: exact integer DDA, 16 bins per thread ----------
+  // ---- phase C: floor curve as one byte per bin: exact integer DDA, 16 bins per thread
   for (int ch = 0; ch < C; ch++) {
     if (!((own_mask >> ch) & 1u)) continue;
     const uint32_t* sg = sgbase + ch * 4 * 66;
     uint8_t* yb = ybuf + ch * half_max;
     const int nseg = (int)rec[K1_REC_HDR + ch * K1_SEG_WORDS];
-    for (int xb = tid * 16; xb < half; xb += 32 * 16) {   // half is a multiple of 16 (host-checked)
-      int lo = 0, hi = nseg;                                   // x0[lo] <= xb < x0[hi]
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if ((int)(sg[4 * mid] & 0xffffu) <= xb) lo = mid; else hi = mid;
-      }
-      int si = lo;
-      uint4 w = *reinterpret_cast<const uint4*>(sg + 4 * si);
-      int x1 = (int)(w.x >> 16), adx = x1 - (int)(w.x & 0xffffu);
-      int base = (int)(w.y >> 16), rem = (int)(w.z & 0x7fffffffu), sy = (w.z >> 31) ? -1 : 1;
-      // state of the DDA after k = xb - x0 steps: y = y0 + sy * (k * base + floor(k * rem / adx)).
-      // k * rem < adx^2 <= 2^24, so the quotient is one float multiply by 1/adx and an exact fix-up
-      const int k = xb - (int)(w.x & 0xffffu);
-      const int t = k * rem;
-      int q = (int)((float)t * __uint_as_float(w.w));
-      int err = t - q * adx;
-      if (err < 0) {
-        q--;
-        err += adx;
-      } else if (err >= adx) {
-        q++;
-        err -= adx;
-      }
-      int y = (int)(short)(w.y & 0xffffu) + sy * (k * base + q);
-      uint32_t yw[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-      for (int j = 0; j < 16; j++) {
-        const int x = xb + j;
-        if (x >= x1 && si + 1 < nseg) {   // next segment starts exactly at its first post
-          si++;
-          w = *reinterpret_cast<const uint4*>(sg + 4 * si);
-          x1 = (int)(w.x >> 16);
-          adx = x1 - (int)(w.x & 0xffffu);
-          base = (int)(w.y >> 16);
-          rem = (int)(w.z & 0x7fffffffu);
-          sy = (w.z >> 31) ? -1 : 1;
-          err = 0;
-          y = (int)(short)(w.y & 0xffffu);
-        }
-        const int yc = y < 0 ? 0 : (y > 255 ? 255 : y);   // the reference reads the table unchecked (quirk Q2)
-        yw[j >> 2] |= (uint32_t)yc << (8 * (j & 3));
-        err += rem;
-        y += sy * base;
-        if (err >= adx) {
-          err -= adx;
-          y += sy;
-        }
-      }
-      *reinterpret_cast<uint4*>(yb + xb) = uint4{yw[0], yw[1], yw[2], yw[3]};
-    }
+    k1b_render_floor(sg, nseg, yb, half, tid);
   }
   __syncwarp();
 
@@ -1064,11 +1083,9 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
     if (have_res) {
       if (pair) {
         k1g_fetch_chunk<16>(G, 0, 2 * x0, r);   // Residue2 de-interleave: positions (2x, 2x+1) = (ch0, ch1)
-      } else if (g.rtype == 2) {
-        k1g_fetch_chunk<8>(G, 0, x0, r);
-      } else {
-        if (!(g.skip & 1u)) k1g_fetch_chunk<8>(G, 0, x0, r);
-        if (C == 2 && !(g.skip & 2u)) k1g_fetch_chunk<8>(G, 1, x0, r + 8);
+      } else {   // type 2 mono: the one vector is channel 0
+        if (g.rtype == 2 || !(g.skip & 1u)) k1g_fetch_chunk<8>(G, 0, x0, r);
+        if (g.rtype != 2 && C == 2 && !(g.skip & 2u)) k1g_fetch_chunk<8>(G, 1, x0, r + 8);
       }
     }
     float c0[8], c1[8];
