@@ -64,6 +64,8 @@ struct BlockCtx {
   Barrier* bar;
   std::vector<WarpCtx*> warps;
   void* smem;
+  std::mutex named_m;
+  Barrier* named[16] = {nullptr};   // bar.sync id, count (created on first use)
 };
 
 extern thread_local BlockCtx* t_block;
@@ -77,6 +79,16 @@ void launch(unsigned blocks, unsigned threads, size_t smem_bytes, const std::fun
 extern thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 inline void __syncthreads() { emu::t_block->bar->wait(); }
+inline void emu_named_barrier(int id, int count) {
+  emu::BlockCtx* b = emu::t_block;
+  emu::Barrier* bar;
+  {
+    std::lock_guard<std::mutex> lk(b->named_m);
+    if (!b->named[id]) b->named[id] = new emu::Barrier(count);
+    bar = b->named[id];
+  }
+  bar->wait();
+}
 inline void __syncwarp(unsigned = 0xffffffffu) { emu::t_block->warps[emu::t_warp]->bar.wait(); }
 
 template <typename T>

@@ -8,7 +8,7 @@
 #include "../../include/vpz.h"
 #include "../../vorbispizza_b200/csrc/devapi.h"
 #include "../../vorbispizza_b200/csrc/k1_symbols.cuh"
-#include "../../vorbispizza_b200/csrc/k3_imdct.cuh"
+#include "../../vorbispizza_b200/csrc/k3_streams.cuh"
 
 thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 namespace emu {
@@ -38,6 +38,7 @@ void launch(unsigned blocks, unsigned threads, size_t smem_bytes, const std::fun
     }
     for (auto& t : ts) t.join();
     for (auto* w : ctx.warps) delete w;
+    for (auto* nb : ctx.named) delete nb;
     free(ctx.smem);
   }
 }
@@ -122,12 +123,22 @@ int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream*, st
   return VPZ_OK;
 }
 
-int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream*, std::string&) {
+int launch_k3(const K3Params& p, int ncb, size_t smem_bytes, Stream*, std::string&) {
   if (p.n_items == 0) return VPZ_OK;
   *p.counter = 0;
   emu::launch(2, (unsigned)ncb * K3_THREADS_PER_CH, smem_bytes, [&] {
     float* smem = (float*)emu::t_block->smem;
-    if (fast) k3_cta_loop<true>(p, smem, ncb); else k3_cta_loop<false>(p, smem, ncb);
+    k3_cta_loop(p, smem, ncb);
+  });
+  return VPZ_OK;
+}
+
+int launch_k3_streams(const K3Params& p, Stream*, std::string&) {
+  if (p.n_items == 0) return VPZ_OK;
+  *p.counter = 0;
+  const unsigned groups = p.n_items >= 3 ? 3 : 1;   // independent 64-thread workers per emulated CTA
+  emu::launch(2, groups * K3_THREADS_PER_CH, ((size_t)K3S_TAB_FLOATS + groups * K3S_GROUP_FLOATS) * 4, [&] {
+    k3s_cta(p, (float*)emu::t_block->smem);
   });
   return VPZ_OK;
 }

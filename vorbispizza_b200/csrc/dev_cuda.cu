@@ -8,7 +8,7 @@
 #include "../../include/vpz.h"
 #include "devapi.h"
 #include "k1_symbols.cuh"
-#include "k3_imdct.cuh"
+#include "k3_streams.cuh"
 
 // ---- kernels ---------------------------------------------------------------------------------
 template <bool DEBUG>
@@ -32,10 +32,16 @@ __global__ void __launch_bounds__(K1B_THREADS) vpz_k1b_spectrum(K1Params P) {
   k1b_cta_loop<DEBUG>(P, k1_smem, &s_idx);
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(128, FAST ? 6 : 1) vpz_k3_imdct_ola(K3Params P, int ncb) {
+// generic block sizes / channel counts
+__global__ void __launch_bounds__(128, 1) vpz_k3_imdct_ola(K3Params P, int ncb) {
   extern __shared__ float k3_smem[];
-  k3_cta_loop<FAST>(P, k3_smem, ncb);
+  k3_cta_loop(P, k3_smem, ncb);
+}
+
+// block sizes 256 / 2048, mono / stereo: one CTA per SM, up to 12 independent 64-thread workers
+__global__ void __launch_bounds__(K3_THREADS_PER_CH * K3S_MAX_GROUPS, 1) vpz_k3_streams(K3Params P) {
+  extern __shared__ float k3_smem[];
+  k3s_cta(P, k3_smem);
 }
 
 namespace vpz {
@@ -92,8 +98,8 @@ int init(int device, std::string& err) {
   g_max_smem = prop.sharedMemPerBlockOptin;
   cudaFuncSetAttribute(vpz_k1b_spectrum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
   cudaFuncSetAttribute(vpz_k1b_spectrum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
-  cudaFuncSetAttribute(vpz_k3_imdct_ola<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
-  cudaFuncSetAttribute(vpz_k3_imdct_ola<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  cudaFuncSetAttribute(vpz_k3_imdct_ola, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  cudaFuncSetAttribute(vpz_k3_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute", err);
   return VPZ_OK;
@@ -227,7 +233,7 @@ int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, 
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k1b_spectrum", err);
 }
 
-int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream* s, std::string& err) {
+int launch_k3(const K3Params& p, int ncb, size_t smem_bytes, Stream* s, std::string& err) {
   if (p.n_items == 0) return VPZ_OK;
   if (smem_bytes > g_max_smem) {
     err = "K3 shared memory request exceeds the device limit";
@@ -237,13 +243,34 @@ int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream* 
   cudaError_t e0 = cudaMemsetAsync(p.counter, 0, 4, s->s);  // word 1 of the counter block (K1a/K1b use 0 and 2)
   if (e0 != cudaSuccess) return fail(e0, "cudaMemsetAsync(counter)", err);
   // persistent CTAs: enough to fill every SM, items are handed out by the counter
-  unsigned grid = (unsigned)std::min<size_t>((p.n_items + p.grab - 1) / p.grab, (size_t)8 * g_sm_count);
-  if (fast)
-    vpz_k3_imdct_ola<true><<<grid, threads, smem_bytes, s->s>>>(p, ncb);
-  else
-    vpz_k3_imdct_ola<false><<<grid, threads, smem_bytes, s->s>>>(p, ncb);
+  unsigned grid = (unsigned)std::min<size_t>(p.n_items, (size_t)8 * g_sm_count);
+  vpz_k3_imdct_ola<<<grid, threads, smem_bytes, s->s>>>(p, ncb);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k3_imdct_ola", err);
+}
+
+int k3_streams_groups(size_t n_items) {
+  // workers per CTA: as many as shared memory holds; small batches are spread over all SMs instead
+  size_t fit = (g_max_smem / 4 - K3S_TAB_FLOATS) / K3S_GROUP_FLOATS;
+  size_t g = std::min<size_t>(K3S_MAX_GROUPS, fit);
+  size_t per_sm = (n_items + (size_t)g_sm_count - 1) / (size_t)std::max(g_sm_count, 1);
+  return (int)std::max<size_t>(1, std::min(g, per_sm));
+}
+
+int launch_k3_streams(const K3Params& p, Stream* s, std::string& err) {
+  if (p.n_items == 0) return VPZ_OK;
+  const int groups = k3_streams_groups(p.n_items);
+  const size_t smem_bytes = ((size_t)K3S_TAB_FLOATS + (size_t)groups * K3S_GROUP_FLOATS) * 4;
+  if (smem_bytes > g_max_smem) {
+    err = "K3 shared memory request exceeds the device limit";
+    return VPZ_E_UNSUPPORTED;
+  }
+  cudaError_t e0 = cudaMemsetAsync(p.counter, 0, 4, s->s);
+  if (e0 != cudaSuccess) return fail(e0, "cudaMemsetAsync(counter)", err);
+  unsigned grid = (unsigned)std::min<size_t>((p.n_items + groups - 1) / groups, (size_t)g_sm_count);
+  vpz_k3_streams<<<grid, groups * K3_THREADS_PER_CH, smem_bytes, s->s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k3_streams", err);
 }
 
 }  // namespace dev

@@ -48,8 +48,10 @@ unsigned long long transfer_bytes(int which);  // process-wide bytes copied so f
 // p.counter (K1a uses word 0, K1b word 2 of the context's counter block).
 int launch_k1a(const K1Params& p, bool debug, int blocks, Stream* s, std::string& err);
 int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err);
-// K3: one CTA per work item, ncb channels side by side (64 threads each)
-int launch_k3(const K3Params& p, bool fast, int ncb, size_t smem_bytes, Stream* s, std::string& err);
+// K3, generic block sizes / channel counts: one CTA per work item, ncb channels side by side (64 threads each)
+int launch_k3(const K3Params& p, int ncb, size_t smem_bytes, Stream* s, std::string& err);
+// K3, block sizes 256 / 2048 and at most 2 channels: one CTA per SM of independent 64-thread workers
+int launch_k3_streams(const K3Params& p, Stream* s, std::string& err);
 size_t max_smem_per_block();
 
 }  // namespace dev

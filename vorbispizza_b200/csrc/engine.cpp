@@ -607,14 +607,16 @@ int batch_decode(vpz_batch* b, int clip) {
     p.clip_first = static_cast<uint32_t*>(b->d_clip.p);
     p.n_items = (uint32_t)b->items.n;
     p.counter = ctx->d_counter + 1;
-    p.grab = b->items.n >= (size_t)64 * dev::sm_count() ? 4u : 1u;   // small batches: spread items over all SMs
     p.clip = clip ? 1 : 0;
     p.dbg_imdct = b->dbg_imdct;
-    int ncb = std::min(2, b->max_channels);
-    size_t per_ch = fast ? (2 * 576 + 3 * 512 + 16) : k3f;
-    // + K3_DESC_FLOATS of packet descriptors and (fast) K3_TAB_FLOATS of twiddle / window tables
-    size_t k3_smem = ((size_t)ncb * per_ch + 384 + (fast ? 3072 : 0)) * 4;
-    if ((rc = dev::launch_k3(p, fast, ncb, k3_smem, st, err))) return rc;
+    if (fast && b->max_channels <= 2) {
+      if ((rc = dev::launch_k3_streams(p, st, err))) return rc;
+    } else {
+      int ncb = std::min(2, b->max_channels);
+      // descriptors (K3_DESC_FLOATS) + per channel slot the Stockham buffers and the three D half-slots
+      size_t k3_smem = ((size_t)ncb * k3f + 384) * 4;
+      if ((rc = dev::launch_k3(p, ncb, k3_smem, st, err))) return rc;
+    }
     b->launches++;
     ctx->kernel_launches++;
   }

@@ -39,7 +39,6 @@ struct K3Params {
   uint32_t* clip_first;            // per packet: smallest clipped sample index (init 0xffffffff), may be NULL
   uint32_t n_items;
   uint32_t* counter;               // work-stealing cursor over items (zeroed before each launch)
-  uint32_t grab;                   // items a CTA takes per atomic: K3_GRAB when the batch is large, else 1
   int clip;
   float* dbg_imdct;                // debug: raw y[0..N) of every packet, [ch][N] at 2*spec_off, may be NULL
 };

@@ -39,19 +39,12 @@ struct K3D {
 };
 VPZ_DEV float* k3_dp(const K3D& d, int i) { return (i < d.h ? d.lo : d.hm) + i; }
 
-// barrier of one channel group (64 threads = 2 warps): the transposes of the two channels of a CTA
-// are independent, only the output loop needs the whole CTA
+// barrier of one 64-thread group (2 warps) of the fast kernel: hardware barrier 1 + group index (a
+// CTA of that kernel is alone on its SM, so reserving all 16 barriers costs nothing)
 #ifndef VPZ_EMU
-// (literal barrier ids: a register id makes ptxas reserve all 16 hardware barriers for the CTA)
-#define K3_GSYNC(g)                                         \
-  do {                                                      \
-    if ((g) == 0)                                           \
-      asm volatile("bar.sync 1, 64;" ::: "memory");         \
-    else                                                    \
-      asm volatile("bar.sync 2, 64;" ::: "memory");         \
-  } while (0)
+#define K3_GSYNC(g) asm volatile("bar.sync %0, 64;" ::"r"((g) + 1) : "memory")
 #else
-#define K3_GSYNC(g) __syncthreads()
+#define K3_GSYNC(g) emu_named_barrier((g) + 1, 64)
 #endif
 
 typedef float2 cpx;
@@ -138,8 +131,6 @@ VPZ_DEV int idx2(int k1, int k2, int r2) { return k1 + 8 * k2 + 68 * r2; }
 // load instead of one dependent global load per packet; the last word is the work-stealing slot.
 #define K3_DESC_PKTS 64
 #define K3_DESC_FLOATS 384
-#define K3_GRAB 4            // consecutive work items a CTA takes per atomic when there are plenty (K3Params.grab)
-#define K3_FAST_PER_CH (2 * K3_PLANE + 3 * 512 + 16)
 
 // N = 2048: H = 512 = 8*8*8, 64 threads.  The thread's 8 float2 of the spectrum (X[2n], X[2n+1] for
 // n = t + 64 q) arrive in registers (prefetched one packet ahead).  Writes D[0..1024) (smem).
@@ -208,7 +199,7 @@ VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* ta
   }
 }
 
-// N = 256: H = 64 = 8*8, threads t < 8 of the channel group work; M = 128.
+// N = 256: H = 64 = 8*8, threads t < 8 of the group work; M = 128.  tw / w64: shared-memory tables.
 VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, const cpx* w64, int t, bool active, int grp) {
   const int M = 128;
   cpx v[8];
@@ -218,11 +209,11 @@ VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, c
       int n = t + 8 * q;
       v[q].x = VPZ_LDG(X + 2 * n);
       v[q].y = VPZ_LDG(X + M - 1 - 2 * n);
-      v[q] = cmul(v[q], VPZ_LDG(tw + n));
+      v[q] = cmul(v[q], tw[n]);
     }
     dft8(v);
 #pragma unroll
-    for (int k = 1; k < 8; k++) v[k] = cmul(v[k], VPZ_LDG(w64 + ((t * k) & 63)));
+    for (int k = 1; k < 8; k++) v[k] = cmul(v[k], w64[(t * k) & 63]);
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       A[9 * k + t] = v[k].x;
@@ -240,7 +231,7 @@ VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, c
 #pragma unroll
     for (int k2 = 0; k2 < 8; k2++) {
       int p = t + 8 * k2;
-      cpx c = cmul(v[k2], VPZ_LDG(tw + p));
+      cpx c = cmul(v[k2], tw[p]);
       *k3_dp(D, 2 * p) = c.x;
       *k3_dp(D, M - 1 - 2 * p) = -c.y;
     }
@@ -405,109 +396,31 @@ VPZ_DEV bool k3_emit(const float* Dc_hm, const float* Dc_lo, const float* Dp_lo,
   return clipped;
 }
 
-// The common case in full: long block after long block, nothing trimmed (ls = 0, count = L = 1024,
-// previous RightStart = 1024).  Thread tid writes samples j = tid + NT r; in the first half the current block
-// reads +D[j + 512] and the previous one -Dp[511 - j], in the second they read -D[1535 - j] and
-// -Dp[j - 512]; every index is a compile-time offset from a per-thread base and the window comes
-// from shared memory.  Same rounding order as k3_emit.
-template <int NCUR, bool CLIP>
-VPZ_DEV bool k3_emit_long_long(const float* Dc0 /* high slot - 512 */, const float* Dp0 /* previous low slot */,
-                               const float* w, float* outp, int C, int tid) {
-  constexpr int NT = 64 * NCUR;   // threads of the CTA
-  constexpr int R = 512 / NT;     // samples per thread and half
-  bool clipped = false;
-  const bool pair_ok = NCUR == 2 && C == 2 && (reinterpret_cast<uintptr_t>(outp) & 7u) == 0;
-#pragma unroll
-  for (int half = 0; half < 2; half++) {
-    float v[R][NCUR];
-#pragma unroll
-    for (int r4 = 0; r4 < R; r4++) {
-      const int j = tid + NT * (r4 + R * half);
-      const float w0 = w[j], w1 = w[1023 - j];
-#pragma unroll
-      for (int cg = 0; cg < NCUR; cg++) {
-        const float* Dc = Dc0 + cg * K3_FAST_PER_CH;
-        const float* Dp = Dp0 + cg * K3_FAST_PER_CH;
-        float a, b;
-        if (half == 0) {
-          a = __fmul_rn(Dc[j + 512], w0);
-          b = __fmul_rn(-Dp[511 - j], w1);
-        } else {
-          a = __fmul_rn(-Dc[1535 - j], w0);
-          b = __fmul_rn(-Dp[j - 512], w1);
-        }
-        float x = __fadd_rn(a, b);
-        if (CLIP) {  // Utils.ClipValue (Utils.cs:44-58)
-          const bool hi = x > 0.99999994f, lo = x < -0.99999994f;
-          x = hi ? 0.99999994f : (lo ? -0.99999994f : x);
-          clipped |= hi | lo;
-        }
-        v[r4][cg] = x;
-      }
-    }
-#pragma unroll
-    for (int r4 = 0; r4 < R; r4++) {
-      const int j = tid + NT * (r4 + R * half);
-      float* o = outp + (size_t)j * C;
-      if (NCUR == 2) {
-        if (pair_ok) {
-          *reinterpret_cast<float2*>(o) = float2{v[r4][0], v[r4][NCUR - 1]};
-        } else {
-          o[0] = v[r4][0];
-          o[1] = v[r4][NCUR - 1];
-        }
-      } else {
-        o[0] = v[r4][0];
-      }
-    }
-  }
-  return clipped;
-}
-
-// Shared memory (floats): [FAST: K3_TAB_FLOATS of tables] then per channel the transpose scratch
-// (FAST: T[2*576], generic: A[2*Hmax] B[2*Hmax]) and the D slots Hi[Mmax/2] Lo0[Mmax/2] Lo1[Mmax/2] (+16 to
-// stagger channel bases across banks).  FAST: block sizes 256/2048.
-template <bool FAST>
-VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_raw, int NCB, bool stage_tables) {
+// ---- generic kernel: any power-of-two block sizes, any channel count --------------------------------
+// Shared memory (floats): descriptors (K3_DESC_FLOATS), then per channel slot the Stockham buffers
+// A[2*Hmax] B[2*Hmax] and the D slots Hi[Mmax/2] Lo0[Mmax/2] Lo1[Mmax/2] (+16 to stagger channel bases).
+// A CTA = NCB channel slots x 64 threads walks one work item; streams with more channels than slots are
+// swept NCB channels at a time.
+VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_raw, int NCB) {
   const VpzOlaItem it = item;  // the item lives in global memory: read it once
   const uint32_t* blob = P.setups[it.setup_slot];
   const VpzSetupHdr* Hd = reinterpret_cast<const VpzSetupHdr*>(blob);
   const int C = Hd->channels;
   const int lg0 = Hd->log2_size0, lg1 = Hd->log2_size1;
   const int Mmax = 1 << (lg1 - 1);
-  const int PA = FAST ? K3_PLANE : (1 << (lg1 - 2));
-  const int SCR = FAST ? 2 * K3_PLANE : 4 * PA;      // transpose scratch per channel
+  const int PA = 1 << (lg1 - 2);
+  const int SCR = 4 * PA;                            // Stockham scratch per channel
   const int HS = Mmax >> 1;                          // one half-slot
-  const int per_ch = FAST ? K3_FAST_PER_CH : SCR + 3 * HS + 16;
+  const int per_ch = SCR + 3 * HS + 16;
   const int tid = threadIdx.x;
   const int cgrp = tid / K3_THREADS_PER_CH;          // channel slot inside the CTA
   const int t64 = tid % K3_THREADS_PER_CH;
-  const int t = FAST ? k3_remap64(t64) : t64;
   const float* slope0 = reinterpret_cast<const float*>(blob + Hd->slope_off[0]);
   const float* slope1 = reinterpret_cast<const float*>(blob + Hd->slope_off[1]);
   const int nthreads = NCB * K3_THREADS_PER_CH;
   VpzPktOla* spk = reinterpret_cast<VpzPktOla*>(smem_raw);                      // [K3_DESC_PKTS] descriptors
   uint32_t* smask = reinterpret_cast<uint32_t*>(smem_raw) + 4 * K3_DESC_PKTS;    // [K3_DESC_PKTS] exec masks
-  float* smem_all = smem_raw + K3_DESC_FLOATS;
-  float* smem = smem_all + (FAST ? K3_TAB_FLOATS : 0);
-  const cpx* tab = reinterpret_cast<const cpx*>(smem_all);
-  if (FAST && stage_tables) {
-    // stage the long-block tables (all reads below hit shared memory instead of L1/L2); skipped when
-    // the previous item of this CTA used the same setup
-    cpx* tb = reinterpret_cast<cpx*>(smem_all);
-    const cpx* tw1 = reinterpret_cast<const cpx*>(blob + Hd->tw_off[1]);
-    const cpx* w512 = reinterpret_cast<const cpx*>(blob + Hd->fft_off[1]);
-    for (int i = tid; i < 512; i += nthreads) tb[K3_TAB_TW + i] = VPZ_LDG(tw1 + i);
-    for (int i = tid; i < 448; i += nthreads) {
-      int k = (i >> 6) + 1, tt = i & 63;
-      tb[K3_TAB_W1 + i] = VPZ_LDG(w512 + ((tt * k) & 511));
-    }
-    for (int i = tid; i < 56; i += nthreads) {
-      int k = (i >> 3) + 1, r = i & 7;
-      tb[K3_TAB_W2 + i] = VPZ_LDG(w512 + ((r * k) << 3));
-    }
-    for (int i = tid; i < 1024; i += nthreads) smem_all[K3_TAB_SLOPE + i] = VPZ_LDG(slope1 + i);
-  }
+  float* smem = smem_raw + K3_DESC_FLOATS;
 
   for (int c0 = 0; c0 < C; c0 += NCB) {
     const int ncur = (C - c0) < NCB ? (C - c0) : NCB;  // channels handled in this sweep
@@ -515,151 +428,100 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_
     const bool ch_ok = cgrp < ncur;
     float* base = smem + cgrp * per_ch;
     float* A = base;
-    float* B = base + 2 * PA;  // generic path only
+    float* B = base + 2 * PA;
 
     int prevM = 0, prev_rs = 0, prev_re = 0;   // previous packet: M, RightStart, RightEnd
     bool have_prev = false;
     int parity = 0;
     const int first = (int)it.first_pkt - (it.has_pre ? 1 : 0);
     const int total = (int)it.n_pkts + (it.has_pre ? 1 : 0);
-    float2 xr[8];
-    bool xr_valid = false;
     for (int pb = 0; pb < total; pb += K3_DESC_PKTS) {
-    const int nb = (total - pb) < K3_DESC_PKTS ? (total - pb) : K3_DESC_PKTS;
-    // descriptors + exec masks of the next nb packets: one parallel fetch
-    __syncthreads();
-    if (tid < nb) {
-      spk[tid] = P.pkts[first + pb + tid];
-      smask[tid] = P.res ? P.res[first + pb + tid].exec_mask : 0xffu;
-    }
-    __syncthreads();
-    for (int pw = 0; pw < nb; pw++, parity ^= 1) {
-      const int pi = pb + pw;
-      const uint32_t gp = (uint32_t)(first + pi);
-      const VpzPktOla pk = spk[pw];
-      const uint32_t mask = smask[pw];
-      const bool has_next = pw + 1 < nb;
-      const VpzPktOla pk_next = spk[has_next ? pw + 1 : pw];
-      const uint32_t mask_next = smask[has_next ? pw + 1 : pw];
-      const bool is_long = pk.flags & VPZ_OLA_LONG;
-      const int lgN = is_long ? lg1 : lg0;
-      const int M = 1 << (lgN - 1);
-      const bool emit = !(pi == 0 && it.has_pre) && !(pk.flags & VPZ_OLA_NOOUT) && have_prev;
+      const int nb = (total - pb) < K3_DESC_PKTS ? (total - pb) : K3_DESC_PKTS;
+      // descriptors + exec masks of the next nb packets: one parallel fetch
+      __syncthreads();
+      if (tid < nb) {
+        spk[tid] = P.pkts[first + pb + tid];
+        smask[tid] = P.res ? P.res[first + pb + tid].exec_mask : 0xffu;
+      }
+      __syncthreads();
+      for (int pw = 0; pw < nb; pw++, parity ^= 1) {
+        const int pi = pb + pw;
+        const uint32_t gp = (uint32_t)(first + pi);
+        const VpzPktOla pk = spk[pw];
+        const uint32_t mask = smask[pw];
+        const bool is_long = pk.flags & VPZ_OLA_LONG;
+        const int lgN = is_long ? lg1 : lg0;
+        const int M = 1 << (lgN - 1);
+        const bool emit = !(pi == 0 && it.has_pre) && !(pk.flags & VPZ_OLA_NOOUT) && have_prev;
 
-      // ---- transform every channel of this sweep into its D buffer -------------------------
-      const bool exec = ch_ok && ((mask >> ch) & 1u);
-      const float* X = P.spec + pk.spec_off + (size_t)ch * M;
-      const cpx* tw = reinterpret_cast<const cpx*>(blob + Hd->tw_off[is_long ? 1 : 0]);
-      const cpx* roots = reinterpret_cast<const cpx*>(blob + Hd->fft_off[is_long ? 1 : 0]);
-      const int h = M >> 1;
-      K3D D;
-      D.h = h;
-      D.hm = base + SCR - h;
-      D.lo = base + SCR + HS + parity * HS;
-      // a channel without floor energy outputs zeros (Mapping.cs:185-194) but still takes part in the
-      // overlap-add: its D buffer is cleared instead of transformed
-      if (ch_ok && !exec)
-        for (int i = t64; i < M; i += K3_THREADS_PER_CH) *k3_dp(D, i) = 0.f;
-      if (FAST) {
-        if (is_long) {
-          if (exec) {
-            if (!xr_valid) k3_load_x(X, t, xr);
-            fft512_to_D(xr, A, D, tab, t, cgrp);
-          }
-#ifdef VPZ_EMU
-          else {  // the emulator's group barrier is the CTA barrier: keep the counts equal
-            __syncthreads();
-            __syncthreads();
-            __syncthreads();
-          }
-#endif
-          K3_GSYNC(cgrp);
-          xr_valid = false;
-        } else {
-          fft64_to_D(exec ? X : P.spec, A, D, tw, roots, t64, exec && t64 < 8, cgrp);
-        }
-      } else {
+        // ---- transform every channel of this sweep into its D buffer -------------------------
+        const bool exec = ch_ok && ((mask >> ch) & 1u);
+        const float* X = P.spec + pk.spec_off + (size_t)ch * M;
+        const cpx* tw = reinterpret_cast<const cpx*>(blob + Hd->tw_off[is_long ? 1 : 0]);
+        const cpx* roots = reinterpret_cast<const cpx*>(blob + Hd->fft_off[is_long ? 1 : 0]);
+        const int h = M >> 1;
+        K3D D;
+        D.h = h;
+        D.hm = base + SCR - h;
+        D.lo = base + SCR + HS + parity * HS;
+        // a channel without floor energy outputs zeros (Mapping.cs:185-194) but still takes part in the
+        // overlap-add: its D buffer is cleared instead of transformed
+        if (ch_ok && !exec)
+          for (int i = t64; i < M; i += K3_THREADS_PER_CH) *k3_dp(D, i) = 0.f;
         // every thread must take the barriers inside
         if (exec) {
           fft_generic_to_D(X, A, B, D, tw, roots, lgN - 2, t64);
         } else {
           for (int s = 0; s < lgN - 2 + 2; s++) __syncthreads();
         }
-      }
-      // D buffers of the sweep are complete here (each path ends with a barrier)
+        // D buffers of the sweep are complete here (the transform ends with a barrier)
 
-      if (P.dbg_imdct && ch_ok) {
-        float* dy = P.dbg_imdct + 2 * (size_t)pk.spec_off + (size_t)ch * 2 * M;
-        for (int i = t64; i < 2 * M; i += K3_THREADS_PER_CH) dy[i] = k3_y(D, M, i);
-      }
-
-      // the spectrum of the next long block is requested now and lands during the output loop
-      if (FAST && has_next && (pk_next.flags & VPZ_OLA_LONG) && ch_ok && ((mask_next >> ch) & 1u)) {
-        k3_load_x(P.spec + pk_next.spec_off + (size_t)ch * Mmax, t, xr);
-        xr_valid = true;
-      }
-      // ---- output: every channel group writes its own channel (samples j * C + ch).  The two groups of
-      // a CTA only meet at a CTA barrier every 8 packets, so their partial sector writes to the same
-      // interleaved PCM lines reach L2 within microseconds of each other and merge there.
-      if (emit && ch_ok) {
-        const int ls = pk.left_start;
-        const int count = (int)pk.right_start - ls;
-        const int L = prev_re - prev_rs;             // StreamDecoder.cs:654
-        const float* w = (pk.flags & VPZ_OLA_LEFT1) ? slope1 : slope0;
-        float* outp = P.pcm + it.out_base + (size_t)pk.out_off * C + ch;
-        const float* Dc_hm = base + SCR - h;
-        const float* Dc_lo = base + SCR + HS + parity * HS;
-        const float* Dp_lo = base + SCR + HS + (parity ^ 1) * HS;
-        bool clipped;
-        const bool long_long = FAST && M == 1024 && prevM == 1024 && ls == 0 && count == 1024 && L == 1024 &&
-                               prev_rs == 1024 && (pk.flags & VPZ_OLA_LEFT1);
-        if (long_long) {
-          const float* ws = smem_all + K3_TAB_SLOPE;
-          clipped = P.clip ? k3_emit_long_long<1, true>(Dc_hm, Dp_lo, ws, outp, C, t64)
-                           : k3_emit_long_long<1, false>(Dc_hm, Dp_lo, ws, outp, C, t64);
-        } else {
-          clipped = P.clip ? k3_emit<1, true>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, t64,
-                                              K3_THREADS_PER_CH)
-                           : k3_emit<1, false>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, t64,
-                                               K3_THREADS_PER_CH);
+        if (P.dbg_imdct && ch_ok) {
+          float* dy = P.dbg_imdct + 2 * (size_t)pk.spec_off + (size_t)ch * 2 * M;
+          for (int i = t64; i < 2 * M; i += K3_THREADS_PER_CH) dy[i] = k3_y(D, M, i);
         }
-        // per packet: 0 when any sample was clamped (HasClipped), else stays 0xffffffff
-        if (P.clip_first && clipped) atomicMin(P.clip_first + gp, 0u);
-      }
-      prevM = M;
-      prev_rs = pk.right_start;
-      prev_re = pk.right_end;
-      have_prev = true;
-      // The output loop above reads the previous D slot; the next packet overwrites it only after its
-      // own transform barriers, except on the N = 256 path and for the zero fill of a silent
-      // channel, which store before their first barrier: one (group) barrier here keeps that safe.
-      if (FAST) {
-        K3_GSYNC(cgrp);
-        if ((pw & 7) == 7) __syncthreads();   // keep the channel groups within 8 packets of each other
-      } else {
+
+        if (emit) {
+          const int ls = pk.left_start;
+          const int count = (int)pk.right_start - ls;
+          const int L = prev_re - prev_rs;             // StreamDecoder.cs:654
+          const float* w = (pk.flags & VPZ_OLA_LEFT1) ? slope1 : slope0;
+          float* outp = P.pcm + it.out_base + (size_t)pk.out_off * C + c0;
+          const float* Dc_hm = smem + SCR - h;                       // channel slot 0; + cg * per_ch for the others
+          const float* Dc_lo = smem + SCR + HS + parity * HS;
+          const float* Dp_lo = smem + SCR + HS + (parity ^ 1) * HS;
+          bool clipped;
+          if (ncur == 2)
+            clipped = P.clip ? k3_emit<2, true>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads)
+                             : k3_emit<2, false>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads);
+          else
+            clipped = P.clip ? k3_emit<1, true>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads)
+                             : k3_emit<1, false>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads);
+          // per packet: 0 when any sample was clamped (HasClipped), else stays 0xffffffff
+          if (P.clip_first && clipped) atomicMin(P.clip_first + gp, 0u);
+        }
+        prevM = M;
+        prev_rs = pk.right_start;
+        prev_re = pk.right_end;
+        have_prev = true;
+        // the output loop reads the previous D slot, which the next packet's zero fill may overwrite
+        // before its first barrier
         __syncthreads();
       }
-    }
     }
     __syncthreads();
   }
 }
 
-// CTA main loop: work items are taken K3_GRAB at a time from a global counter.
-template <bool FAST>
+// CTA main loop: work items are handed out by a global counter.
 VPZ_DEV void k3_cta_loop(const K3Params& P, float* smem_raw, int ncb) {
   uint32_t* s_next = reinterpret_cast<uint32_t*>(smem_raw) + (K3_DESC_FLOATS - 1);
-  const uint32_t* prev_blob = nullptr;
   for (;;) {
     __syncthreads();
-    if (threadIdx.x == 0) *s_next = atomicAdd(P.counter, P.grab);
+    if (threadIdx.x == 0) *s_next = atomicAdd(P.counter, 1u);
     __syncthreads();
-    const uint32_t first = *s_next;
-    if (first >= P.n_items) break;
-    for (uint32_t k = 0; k < P.grab && first + k < P.n_items; k++) {
-      const uint32_t* blob = P.setups[P.items[first + k].setup_slot];
-      k3_run_item<FAST>(P, P.items[first + k], smem_raw, ncb, blob != prev_blob);
-      prev_blob = blob;
-    }
+    const uint32_t idx = *s_next;
+    if (idx >= P.n_items) break;
+    k3_run_item(P, P.items[idx], smem_raw, ncb);
   }
 }

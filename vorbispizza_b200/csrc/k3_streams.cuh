@@ -1,0 +1,286 @@
+// k3_streams.cuh -- K3 for the common case (block sizes 256 / 2048, mono or stereo): one resident CTA
+// per SM, split into independent 64-thread GROUPS; every group is a worker that takes whole work
+// items (a run of <= 63 consecutive packets of one stream + its seed) from the global counter.
+//
+// Per packet a group transforms the channels one after the other (IMDCT through a 512-point complex
+// FFT, k3_imdct.cuh) into the D slots of the stream and then writes the windowed, overlap-added,
+// clipped, INTERLEAVED samples of all channels (full 32-byte sectors for stereo).  Groups never wait
+// for each other: the only barriers are 64-thread named barriers, the twiddle / window tables are
+// staged once per CTA, a mono stream occupies one group like a stereo one, and the spectrum of the
+// next block is already on its way while the current one is written out (channel 0 into registers,
+// channel 1 with cp.async into the D slots of channel 1 that the finished packet no longer needs).
+//
+// Replaces (reference file:line): Mdct.Reverse (Mdct.cs:15-19,77-419), StreamDecoder.OverlapBuffers
+// (StreamDecoder.cs:764-791), the valid-range bookkeeping of ReadNextPacket (StreamDecoder.cs:640-694,
+// geometry from the host) and StoreInterleaved<Clip> (StreamDecoder.cs:515-592, Utils.cs:44-58).
+#pragma once
+#include "k3_imdct.cuh"
+
+// shared memory (floats): tables, then per group: descriptors | transpose scratch | D slots of 2 channels
+#define K3S_TAB_S_TW 3072        // short block: pre/post twiddle, 64 complex
+#define K3S_TAB_S_W64 3200       // short block: 64-point roots, 64 complex
+#define K3S_TAB_S_SLOPE 3328     // short window slope, 128 floats
+#define K3S_TAB_FLOATS 3456
+#define K3S_DESC_PKTS 32
+#define K3S_DESC_FLOATS 192      // 32 x (4 descriptor words + 1 exec mask) + work-stealing slot
+#define K3S_CH_FLOATS 1536       // D slots of one channel: Hi[512] Lo0[512] Lo1[512]
+#define K3S_GROUP_FLOATS (K3S_DESC_FLOATS + 2 * K3_PLANE + 2 * K3S_CH_FLOATS)
+#define K3S_MAX_GROUPS 12
+
+#ifndef VPZ_EMU
+VPZ_DEV void k3s_cp16(float* dst_smem, const float* src) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(src) : "memory");
+}
+VPZ_DEV void k3s_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+#else
+VPZ_DEV void k3s_cp16(float* dst_smem, const float* src) { memcpy(dst_smem, src, 16); }
+VPZ_DEV void k3s_cp_wait() {}
+#endif
+
+// The common case in full: long block after long block, nothing trimmed (ls = 0, count = L = 1024,
+// previous RightStart = 1024).  Sample j < 512 reads +D[j + 512] of the current block and -Dp[511 - j] of
+// the previous one; its mirror image 1023 - j reads the SAME two values with the window pair swapped
+// (time-domain aliasing symmetry), so a thread produces both from one set of loads:
+//   out[j]        = D[512 + j] * w[j]        + (-Dp[511 - j]) * w[1023 - j]
+//   out[1023 - j] = (-D[512 + j]) * w[1023 - j] + (-Dp[511 - j]) * w[j]
+// with the rounding order of OverlapBuffers (two rounded products, one rounded sum).
+template <int NC, bool CLIP>
+VPZ_DEV bool k3s_emit_long_long(const float* hi0 /* D[512..] of channel 0 */, const float* plo0 /* previous D[0..512) */,
+                                const float* ws, float* outp, int t64) {
+  bool clipped = false;
+  const bool pair_ok = NC == 2 && (reinterpret_cast<uintptr_t>(outp) & 7u) == 0;
+#pragma unroll 4
+  for (int r = 0; r < 8; r++) {
+    const int j = t64 + 64 * r;
+    const float w0 = ws[j], w1 = ws[1023 - j];
+    float lo[NC], hi[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const float a = hi0[c * K3S_CH_FLOATS + j];
+      const float b = -plo0[c * K3S_CH_FLOATS + 511 - j];
+      float x = __fadd_rn(__fmul_rn(a, w0), __fmul_rn(b, w1));
+      float y = __fadd_rn(__fmul_rn(-a, w1), __fmul_rn(b, w0));
+      if (CLIP) {  // Utils.ClipValue (Utils.cs:44-58)
+        const bool xh = x > 0.99999994f, xl = x < -0.99999994f;
+        x = xh ? 0.99999994f : (xl ? -0.99999994f : x);
+        const bool yh = y > 0.99999994f, yl = y < -0.99999994f;
+        y = yh ? 0.99999994f : (yl ? -0.99999994f : y);
+        clipped |= xh | xl | yh | yl;
+      }
+      lo[c] = x;
+      hi[c] = y;
+    }
+    if (NC == 2) {
+      if (pair_ok) {
+        *reinterpret_cast<float2*>(outp + 2 * j) = float2{lo[0], lo[NC - 1]};
+        *reinterpret_cast<float2*>(outp + 2 * (1023 - j)) = float2{hi[0], hi[NC - 1]};
+      } else {
+        outp[2 * j] = lo[0];
+        outp[2 * j + 1] = lo[NC - 1];
+        outp[2 * (1023 - j)] = hi[0];
+        outp[2 * (1023 - j) + 1] = hi[NC - 1];
+      }
+    } else {
+      outp[j] = lo[0];
+      outp[1023 - j] = hi[0];
+    }
+  }
+  return clipped;
+}
+
+// one work item, C = 1 or 2 channels, by one 64-thread group
+VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs, float* gbase, int grp, int t64) {
+  const VpzOlaItem it = item;  // the item lives in global memory: read it once
+  const uint32_t* blob = P.setups[it.setup_slot];
+  const VpzSetupHdr* Hd = reinterpret_cast<const VpzSetupHdr*>(blob);
+  const int C = Hd->channels;
+  const int t = k3_remap64(t64);
+  const float* slope0 = reinterpret_cast<const float*>(blob + Hd->slope_off[0]);
+  const float* slope1 = reinterpret_cast<const float*>(blob + Hd->slope_off[1]);
+  VpzPktOla* spk = reinterpret_cast<VpzPktOla*>(gbase);                       // [K3S_DESC_PKTS] descriptors
+  uint32_t* smask = reinterpret_cast<uint32_t*>(gbase) + 4 * K3S_DESC_PKTS;    // [K3S_DESC_PKTS] exec masks
+  float* T = gbase + K3S_DESC_FLOATS;
+  float* Dch = T + 2 * K3_PLANE;
+  const cpx* tab = reinterpret_cast<const cpx*>(tabs);
+  const cpx* tw_s = reinterpret_cast<const cpx*>(tabs + K3S_TAB_S_TW);
+  const cpx* w64_s = reinterpret_cast<const cpx*>(tabs + K3S_TAB_S_W64);
+
+  int prevM = 0, prev_rs = 0, prev_re = 0;   // previous packet: M, RightStart, RightEnd
+  bool have_prev = false;
+  int parity = 0;
+  const int first = (int)it.first_pkt - (it.has_pre ? 1 : 0);
+  const int total = (int)it.n_pkts + (it.has_pre ? 1 : 0);
+  float2 xr[8];            // spectrum of channel 0 of the coming long block (prefetched)
+  bool xr_valid = false;
+  bool staged = false;     // spectrum of channel 1 of the coming long block sits in channel 1's free D slots
+  for (int pb = 0; pb < total; pb += K3S_DESC_PKTS) {
+    const int nb = (total - pb) < K3S_DESC_PKTS ? (total - pb) : K3S_DESC_PKTS;
+    // descriptors + exec masks of the next nb packets: one parallel fetch
+    K3_GSYNC(grp);
+    if (t64 < nb) {
+      spk[t64] = P.pkts[first + pb + t64];
+      smask[t64] = P.res ? P.res[first + pb + t64].exec_mask : 0xffu;
+    }
+    K3_GSYNC(grp);
+    for (int pw = 0; pw < nb; pw++, parity ^= 1) {
+      const int pi = pb + pw;
+      const uint32_t gp = (uint32_t)(first + pi);
+      const VpzPktOla pk = spk[pw];
+      const uint32_t mask = smask[pw];
+      const bool has_next = pw + 1 < nb;
+      const VpzPktOla pk_next = spk[has_next ? pw + 1 : pw];
+      const uint32_t mask_next = smask[has_next ? pw + 1 : pw];
+      const bool next_long = has_next && (pk_next.flags & VPZ_OLA_LONG);
+      const bool is_long = pk.flags & VPZ_OLA_LONG;
+      const int M = is_long ? 1024 : 128;
+      const int h = M >> 1;
+      const bool emit = !(pi == 0 && it.has_pre) && !(pk.flags & VPZ_OLA_NOOUT) && have_prev;
+
+      // ---- transform the channels one after the other into their D slots ---------------------------
+      for (int c = 0; c < C; c++) {
+        float* chb = Dch + c * K3S_CH_FLOATS;
+        K3D D;
+        D.h = h;
+        D.hm = chb - h;
+        D.lo = chb + 512 + parity * 512;
+        const bool exec = (mask >> c) & 1u;
+        const float* X = P.spec + pk.spec_off + (size_t)c * M;
+        if (!exec) {
+          // a channel without floor energy outputs zeros (Mapping.cs:185-194) but still takes part in
+          // the overlap-add: its D slots are cleared instead of transformed
+          for (int i = t64; i < M; i += K3_THREADS_PER_CH) *k3_dp(D, i) = 0.f;
+          k3s_cp_wait();
+          K3_GSYNC(grp);
+        } else if (is_long) {
+          if (c == 1 && staged) {
+            // channel 1's spectrum was copied into its own Hi / Lo[parity] slots after the previous
+            // packet's output (made visible by the barrier that ended channel 0's transform)
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const int n2 = 2 * (t + 64 * q);
+              xr[q] = *reinterpret_cast<const float2*>(n2 < 512 ? chb + n2 : D.lo + (n2 - 512));
+            }
+          } else if (!(c == 0 && xr_valid)) {
+            k3_load_x(X, t, xr);
+          }
+          fft512_to_D(xr, T, D, tab, t, grp);
+          if (c == 0) xr_valid = false;
+          k3s_cp_wait();
+          K3_GSYNC(grp);   // D complete, scratch reusable, staged channel-1 spectrum visible
+        } else {
+          fft64_to_D(X, T, D, tw_s, w64_s, t64, t64 < 8, grp);   // ends with a group barrier
+        }
+        if (P.dbg_imdct) {
+          float* dy = P.dbg_imdct + 2 * (size_t)pk.spec_off + (size_t)c * 2 * M;
+          for (int i = t64; i < 2 * M; i += K3_THREADS_PER_CH) dy[i] = k3_y(D, M, i);
+        }
+      }
+      staged = false;
+
+      // channel 0 of the next long block is requested now and lands during the output loop
+      if (next_long && (mask_next & 1u)) {
+        k3_load_x(P.spec + pk_next.spec_off, t, xr);
+        xr_valid = true;
+      }
+      // ---- output: window + overlap-add + clip, all channels interleaved ----------------------------
+      if (emit) {
+        const int ls = pk.left_start;
+        const int count = (int)pk.right_start - ls;
+        const int L = prev_re - prev_rs;             // StreamDecoder.cs:654
+        float* outp = P.pcm + it.out_base + (size_t)pk.out_off * C;
+        const float* Dp_lo = Dch + 512 + (parity ^ 1) * 512;
+        bool clipped;
+        const bool long_long = M == 1024 && prevM == 1024 && ls == 0 && count == 1024 && L == 1024 && prev_rs == 1024 &&
+                               (pk.flags & VPZ_OLA_LEFT1);
+        if (long_long) {
+          const float* ws = tabs + K3_TAB_SLOPE;
+          if (C == 2)
+            clipped = P.clip ? k3s_emit_long_long<2, true>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_long_long<2, false>(Dch, Dp_lo, ws, outp, t64);
+          else
+            clipped = P.clip ? k3s_emit_long_long<1, true>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_long_long<1, false>(Dch, Dp_lo, ws, outp, t64);
+        } else {
+          const float* w = (pk.flags & VPZ_OLA_LEFT1) ? slope1 : slope0;
+          const float* Dc_hm = Dch - h;
+          const float* Dc_lo = Dch + 512 + parity * 512;
+          if (C == 2)
+            clipped = P.clip ? k3_emit<2, true>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH)
+                             : k3_emit<2, false>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH);
+          else
+            clipped = P.clip ? k3_emit<1, true>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH)
+                             : k3_emit<1, false>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH);
+        }
+        // per packet: 0 when any sample was clamped (HasClipped), else stays 0xffffffff
+        if (P.clip_first && clipped) atomicMin(P.clip_first + gp, 0u);
+      }
+      prevM = M;
+      prev_rs = pk.right_start;
+      prev_re = pk.right_end;
+      have_prev = true;
+      // the output loop read this packet's high slot and the previous packet's low slot: both are free
+      // once every thread of the group is here
+      K3_GSYNC(grp);
+      if (C == 2 && next_long && (mask_next & 2u)) {
+        // channel 1 of the next long block -> its Hi slot (X[0..512)) and the Lo slot of the next parity
+        // (X[512..1024)), asynchronously; channel 0's transform runs meanwhile
+        const float* Xn = P.spec + pk_next.spec_off + 1024;
+        float* hi = Dch + K3S_CH_FLOATS;
+        float* lo = hi + 512 + (parity ^ 1) * 512;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int i4 = t64 + 64 * r;
+          k3s_cp16(i4 < 128 ? hi + 4 * i4 : lo + 4 * (i4 - 128), Xn + 4 * i4);
+        }
+        staged = true;
+      }
+    }
+  }
+  k3s_cp_wait();
+}
+
+// kernel body: `groups` = blockDim.x / 64 workers per CTA
+VPZ_DEV void k3s_cta(const K3Params& P, float* smem) {
+  const int tid = threadIdx.x;
+  const int grp = tid / K3_THREADS_PER_CH, t64 = tid % K3_THREADS_PER_CH;
+  const int nthreads = blockDim.x;
+  {
+    // the tables depend on the two block sizes only (256 / 2048 for every setup of this launch)
+    const uint32_t* blob = P.setups[P.items[0].setup_slot];
+    const VpzSetupHdr* Hd = reinterpret_cast<const VpzSetupHdr*>(blob);
+    cpx* tb = reinterpret_cast<cpx*>(smem);
+    const cpx* tw1 = reinterpret_cast<const cpx*>(blob + Hd->tw_off[1]);
+    const cpx* w512 = reinterpret_cast<const cpx*>(blob + Hd->fft_off[1]);
+    const cpx* tw0 = reinterpret_cast<const cpx*>(blob + Hd->tw_off[0]);
+    const cpx* w64 = reinterpret_cast<const cpx*>(blob + Hd->fft_off[0]);
+    const float* slope0 = reinterpret_cast<const float*>(blob + Hd->slope_off[0]);
+    const float* slope1 = reinterpret_cast<const float*>(blob + Hd->slope_off[1]);
+    for (int i = tid; i < 512; i += nthreads) tb[K3_TAB_TW + i] = VPZ_LDG(tw1 + i);
+    for (int i = tid; i < 448; i += nthreads) {
+      int k = (i >> 6) + 1, tt = i & 63;
+      tb[K3_TAB_W1 + i] = VPZ_LDG(w512 + ((tt * k) & 511));
+    }
+    for (int i = tid; i < 56; i += nthreads) {
+      int k = (i >> 3) + 1, r = i & 7;
+      tb[K3_TAB_W2 + i] = VPZ_LDG(w512 + ((r * k) << 3));
+    }
+    for (int i = tid; i < 1024; i += nthreads) smem[K3_TAB_SLOPE + i] = VPZ_LDG(slope1 + i);
+    cpx* ts = reinterpret_cast<cpx*>(smem + K3S_TAB_S_TW);
+    cpx* tr = reinterpret_cast<cpx*>(smem + K3S_TAB_S_W64);
+    for (int i = tid; i < 64; i += nthreads) {
+      ts[i] = VPZ_LDG(tw0 + i);
+      tr[i] = VPZ_LDG(w64 + i);
+    }
+    for (int i = tid; i < 128; i += nthreads) smem[K3S_TAB_S_SLOPE + i] = VPZ_LDG(slope0 + i);
+  }
+  __syncthreads();
+  float* gbase = smem + K3S_TAB_FLOATS + grp * K3S_GROUP_FLOATS;
+  uint32_t* slot = reinterpret_cast<uint32_t*>(gbase) + (K3S_DESC_FLOATS - 1);
+  for (;;) {
+    K3_GSYNC(grp);
+    if (t64 == 0) *slot = atomicAdd(P.counter, 1u);
+    K3_GSYNC(grp);
+    const uint32_t idx = *slot;
+    if (idx >= P.n_items) break;
+    k3s_run_item(P, P.items[idx], smem, gbase, grp, t64);
+  }
+}
