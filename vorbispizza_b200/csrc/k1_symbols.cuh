@@ -928,6 +928,19 @@ template <bool DEBUG>
 VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, const float* dbtab, int tid) {
   const int lane = tid;   // ONE WARP per packet: many packets in flight per SM hide the per-packet load latency
   const VpzPktIn pk = P.pkts[pkt_idx];
+#ifndef VPZ_EMU
+  {
+    // the record (header, floor segments, classes) and the entry indices are read in four dependent
+    // steps below; ask L2 for all of their lines now (one 128-byte line per lane: the record first,
+    // then ~4 bytes of entry indices per packet byte, the typical rate) so those steps find them there
+    const char* r0 = reinterpret_cast<const char*>(P.rec + pk.rec_off);
+    const char* e0 = reinterpret_cast<const char*>(P.ent + pk.ent_off);
+    const uint32_t rec_lines = 6, ent_bytes = 4u * pk.byte_len;
+    const char* line = lane < (int)rec_lines ? r0 + 128 * lane : e0 + 128 * (lane - (int)rec_lines);
+    if (lane < (int)rec_lines || 128u * (uint32_t)(lane - (int)rec_lines) < ent_bytes)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+  }
+#endif
   const uint32_t* blob = P.setups[pk.setup_slot];
   const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
   const int C = H->channels;
