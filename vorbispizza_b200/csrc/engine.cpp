@@ -354,6 +354,16 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
   return VPZ_OK;
 }
 
+// Packets per K3 work item.  Every item re-transforms its predecessor packet as the overlap seed, so
+// long items are cheaper; but the IMDCT kernel runs 12 workers per SM, and a batch with few packets
+// should still hand every worker about two items.  A user-set "ola_chunk" is taken as is.
+uint32_t pick_ola_chunk(const vpz_ctx* ctx, uint64_t total_packets) {
+  if (ctx->ola_chunk_set) return (uint32_t)std::max(1, ctx->ola_chunk);
+  const uint64_t workers = (uint64_t)std::max(1, dev::sm_count()) * 12u;
+  const uint64_t want = (total_packets + 2 * workers - 1) / (2 * workers);
+  return (uint32_t)std::min<uint64_t>(63, std::max<uint64_t>(16, want));
+}
+
 int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool, int* first_run) {
   vpz_ctx* ctx = b->ctx;
   if (b->synthetic) {
@@ -362,7 +372,10 @@ int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool
   }
   if (first_run) *first_run = (int)b->runs.size();
   if (n == 0) return VPZ_OK;
-  const uint32_t chunk = (uint32_t)std::max(1, ctx->ola_chunk);
+  uint64_t commit_pkts = 0;
+  for (size_t i = 0; i < n; i++) commit_pkts += plans[i]->src.size();
+  // one run at a time (batch layer): the batch total is unknown, keep the long items
+  const uint32_t chunk = n > 1 ? pick_ola_chunk(ctx, commit_pkts) : (uint32_t)std::max(1, ctx->ola_chunk);
   struct Base {
     uint64_t bytes, spec, out, rec, ent;
     size_t pkt, item;

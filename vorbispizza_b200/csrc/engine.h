@@ -68,7 +68,8 @@ struct vpz_ctx {
   vpz::dev::Event* ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start, after K1a, after K1b, after K3
   std::string last_error;
   int l1_bits = VPZ_L1_BITS_DEFAULT;
-  int ola_chunk = 63;   // + the seed packet = one descriptor window of the IMDCT kernel
+  int ola_chunk = 63;   // packets per K3 work item (+ the seed packet)
+  bool ola_chunk_set = false;   // set by the user: do not adapt it to the batch size (pick_ola_chunk)
   int k1_warps = 4;
   std::multimap<uint64_t, vpz_setup*> setups;
   std::vector<vpz_setup*> recent;     // setups the context itself holds a reference on (LRU, 64)
@@ -204,6 +205,7 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
 // Appends planned runs to the batch: serial prefix sums, then the copies on `pool` (may be NULL).
 // first_run receives the index of plans[0]'s run.
 int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool, int* first_run);
+uint32_t pick_ola_chunk(const vpz_ctx* ctx, uint64_t total_packets);
 int batch_upload(vpz_batch* b);
 int batch_decode(vpz_batch* b, int clip);
 int batch_fetch_clip(vpz_batch* b);

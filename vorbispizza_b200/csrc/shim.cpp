@@ -110,6 +110,7 @@ int vpz_ctx_set(vpz_ctx* c, const char* key, int value) {
   } else if (!strcmp(key, "ola_chunk")) {
     if (value < 1 || value > 65536) return VPZ_E_ARGUMENT;
     c->ola_chunk = value;
+    c->ola_chunk_set = true;
   } else if (!strcmp(key, "k1_warps")) {
     if (value < 1 || value > 8) return VPZ_E_ARGUMENT;
     c->k1_warps = value;
@@ -390,7 +391,7 @@ int vpz_synth_create(vpz_ctx* ctx, int channels, int log2_size0, int log2_size1,
   b->slots.push_back(s);
   b->max_channels = channels;
   const int size0 = 1 << log2_size0, size1 = 1 << log2_size1;
-  const uint32_t chunk = (uint32_t)std::max(1, ctx->ola_chunk);
+  const uint32_t chunk = pick_ola_chunk(ctx, (uint64_t)n_streams * n_blocks);
   for (uint32_t st = 0; st < n_streams; st++) {
     Run run;
     run.setup = s;
