@@ -10,7 +10,11 @@ by = sys.argv[5] if len(sys.argv) > 5 else "inst"
 txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + k], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 hdr = rows[1]; ix = {n: i for i, n in enumerate(hdr)}
-data = [r for r in rows[2:] if len(r) > ix["Instructions Executed"]]
+data = []
+for r in rows[2:]:
+    if len(r) <= ix["Instructions Executed"]: continue
+    if r[ix["Instructions Executed"]] == "Instructions Executed": break   # next launch of the report
+    data.append(r)
 tot = sum(int(r[ix["Instructions Executed"]] or 0) for r in data)
 tots = sum(int(r[ix["# Samples"]] or 0) for r in data)
 sel = [(int(r[ix["Instructions Executed"]] or 0), int(r[ix["# Samples"]] or 0), i, r) for i, r in enumerate(data) if flt in r[ix["Source"]]]

@@ -723,7 +723,7 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
       sg[4 * s] = (uint32_t)x0 | ((uint32_t)x1 << 16);
       sg[4 * s + 1] = (uint32_t)(y0 & 0xffff) | ((uint32_t)(dy < 0 ? -dy : dy) << 16);
       sg[4 * s + 2] = dy < 0 ? 1u : 0u;
-      reinterpret_cast<float*>(sg)[4 * s + 3] = 1.0f / (float)(adx > 0 ? adx : 1);
+      sg[4 * s + 3] = adx > 1 ? 0xffffffffu / (uint32_t)adx + 1u : 0u;   // ceil(2^32 / adx); adx = 1 has no remainder steps
     }
     __syncthreads();
     if (nseg == 0) continue;
@@ -856,11 +856,23 @@ VPZ_DEV void k1_uncouple(float& m, float& a) {
   m = p ? m : sm;
 }
 
-// Floor1.RenderLineMulti (Floor1.cs:372-397) for 16 consecutive bins of one channel per thread: the
-// exact integer DDA, started in the middle of a segment from its closed form, one byte per bin.
-// sg: per segment {x0 | x1 << 16, y0 | |base| << 16, remainder step | sign << 31, 1 / adx}.
-// The body is kept small on purpose (4 bins unrolled, not 16): the warps of an SM sit in different
-// phases of different packets and K1b is sensitive to instruction-cache misses.
+// Floor1.RenderLineMulti (Floor1.cs:372-397) for 16 consecutive bins of one channel per thread, one byte
+// per bin, exactly the reference's integer DDA:  y(x0 + k) = y0 + sy * (k * base + floor(k * rem / adx)).
+// sg: per segment {x0 | x1 << 16, y0 | |base| << 16, remainder step | sign << 31, M = ceil(2^32 / adx)}.
+// Divisions are multiply-high by M: exact when dividend * adx < 2^32, which holds for a running remainder
+// plus at most four steps (< 5 adx^2 <= 5 * 2^24); the DDA state in the middle of a segment (dividend up
+// to adx^2) may come out one too high and is fixed up.  Four bins that lie inside one segment are
+// produced WITHOUT a carried dependency (remainders e + j * rem, quotients by multiply-high); only a group
+// that contains a post falls back to bin-by-bin stepping.  The body is kept small on purpose: the warps of
+// an SM sit in different phases of different packets and K1b is sensitive to instruction-cache misses.
+VPZ_DEV uint32_t k1b_ybyte(int y) { return (uint32_t)(y < 0 ? 0 : (y > 255 ? 255 : y)); }   // the reference reads the table unchecked (quirk Q2)
+#ifndef VPZ_EMU
+#define K1B_PACK4(a, b, c, d) __byte_perm(__byte_perm(a, b, 0x3240), __byte_perm(c, d, 0x3240), 0x5410)
+#define K1B_MULHI(a, b) __umulhi(a, b)
+#else
+#define K1B_PACK4(a, b, c, d) ((a) | ((b) << 8) | ((c) << 16) | ((d) << 24))
+#define K1B_MULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
+#endif
 VPZ_DEV void k1b_render_floor(const uint32_t* sg, int nseg, uint8_t* yb, int half, int tid) {
   for (int xb = tid * 16; xb < half; xb += 32 * 16) {   // half is a multiple of 16 (host-checked)
     int lo = 0, hi = nseg;                                   // x0[lo] <= xb < x0[hi]
@@ -874,49 +886,54 @@ VPZ_DEV void k1b_render_floor(const uint32_t* sg, int nseg, uint8_t* yb, int hal
     int x1 = si + 1 < nseg ? (int)(w.x >> 16) : 0x7fffffff;   // the last segment never hands over
     int rem = (int)(w.z & 0x7fffffffu), sy = (w.z >> 31) ? -1 : 1;
     int ystep = sy * (int)(w.y >> 16);
-    // state of the DDA after k = xb - x0 steps: y = y0 + sy * (k * base + floor(k * rem / adx)).
-    // k * rem < adx^2 <= 2^24, so the quotient is one float multiply by 1/adx and an exact fix-up
+    uint32_t magic = w.w;
+    // state of the DDA after k = xb - x0 steps
     const int k = xb - (int)(w.x & 0xffffu);
     const int t = k * rem;
-    int q = (int)((float)t * __uint_as_float(w.w));
+    int q = (int)K1B_MULHI((uint32_t)t, magic);
     int err = t - q * adx;
     if (err < 0) {
       q--;
       err += adx;
-    } else if (err >= adx) {
-      q++;
-      err -= adx;
     }
     int y = (int)(short)(w.y & 0xffffu) + k * ystep + sy * q;
     uint32_t* yout = reinterpret_cast<uint32_t*>(yb + xb);
     int x = xb;
 #pragma unroll 1
-    for (int jw = 0; jw < 4; jw++) {
-      uint32_t word = 0;
-#pragma unroll
-      for (int j = 0; j < 4; j++, x++) {
-        if (x >= x1) {   // next segment starts exactly at its first post
-          si++;
-          w = *reinterpret_cast<const uint4*>(sg + 4 * si);
-          adx = (int)(w.x >> 16) - (int)(w.x & 0xffffu);
-          x1 = si + 1 < nseg ? (int)(w.x >> 16) : 0x7fffffff;
-          rem = (int)(w.z & 0x7fffffffu);
-          sy = (w.z >> 31) ? -1 : 1;
-          ystep = sy * (int)(w.y >> 16);
-          err = 0;
-          y = (int)(short)(w.y & 0xffffu);
-        }
-        const uint32_t yc = (uint32_t)(y < 0 ? 0 : (y > 255 ? 255 : y));   // the reference reads the table unchecked (quirk Q2)
-#ifndef VPZ_EMU
-        word = __byte_perm(word, yc, j == 0 ? 0x3214 : j == 1 ? 0x3240 : j == 2 ? 0x3410 : 0x4210);   // byte j <- yc
-#else
-        word |= yc << (8 * j);
-#endif
-        err += rem;
-        y += ystep;
-        if (err >= adx) {
-          err -= adx;
-          y += sy;
+    for (int jw = 0; jw < 4; jw++, x += 4) {
+      uint32_t word;
+      if (x + 4 <= x1) {
+        // the four bins and the state after them, each from the remainder at the start of the group
+        const int n1 = err + rem, n2 = n1 + rem, n3 = n2 + rem, n4 = n3 + rem;
+        const int q1 = (int)K1B_MULHI((uint32_t)n1, magic), q2 = (int)K1B_MULHI((uint32_t)n2, magic);
+        const int q3 = (int)K1B_MULHI((uint32_t)n3, magic), q4 = (int)K1B_MULHI((uint32_t)n4, magic);
+        const int y1 = y + ystep + sy * q1, y2 = y + 2 * ystep + sy * q2, y3 = y + 3 * ystep + sy * q3;
+        word = K1B_PACK4(k1b_ybyte(y), k1b_ybyte(y1), k1b_ybyte(y2), k1b_ybyte(y3));
+        y += 4 * ystep + sy * q4;
+        err = n4 - q4 * adx;
+      } else {
+        word = 0;
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+          if (x + j >= x1) {   // next segment starts exactly at its first post
+            si++;
+            w = *reinterpret_cast<const uint4*>(sg + 4 * si);
+            adx = (int)(w.x >> 16) - (int)(w.x & 0xffffu);
+            x1 = si + 1 < nseg ? (int)(w.x >> 16) : 0x7fffffff;
+            rem = (int)(w.z & 0x7fffffffu);
+            sy = (w.z >> 31) ? -1 : 1;
+            ystep = sy * (int)(w.y >> 16);
+            magic = w.w;
+            err = 0;
+            y = (int)(short)(w.y & 0xffffu);
+          }
+          word |= k1b_ybyte(y) << (8 * j);
+          err += rem;
+          y += ystep;
+          if (err >= adx) {
+            err -= adx;
+            y += sy;
+          }
         }
       }
       yout[jw] = word;
@@ -1003,7 +1020,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
       sg[4 * s] = (uint32_t)x0 | ((uint32_t)x1 << 16);
       sg[4 * s + 1] = (uint32_t)(y0 & 0xffff) | ((uint32_t)base << 16);          // |base| of the DDA
       sg[4 * s + 2] = (uint32_t)(ady - base * adx) | (dy < 0 ? 0x80000000u : 0u); // remainder step, sign
-      reinterpret_cast<float*>(sg)[4 * s + 3] = 1.0f / (float)(adx > 0 ? adx : 1);
+      sg[4 * s + 3] = adx > 1 ? 0xffffffffu / (uint32_t)adx + 1u : 0u;   // ceil(2^32 / adx); adx = 1 has no remainder steps
     }
   }
 
