@@ -73,8 +73,8 @@ static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
       s->gather_ok = ok;
       const size_t U = (units + 31) & ~(size_t)31;
       const size_t half_max = (size_t)1 << (h->log2_size1 - 1);
-      // k1b gather layout per warp: urec stages*U*4 + ybuf C*half_max/4 + sg C*4*66 (+ pad, multiple of 32)
-      s->k1g_words = (uint32_t)(((size_t)max_stages * U * 4 + (size_t)C * half_max / 4 + (size_t)C * 4 * 66 + 8 + 31) & ~(size_t)31);
+      // k1b gather layout per warp: urec stages*U*2 + ybuf C*half_max/4 + sg C*4*66 (+ pad, multiple of 32)
+      s->k1g_words = (uint32_t)(((size_t)max_stages * U * 2 + (size_t)C * half_max / 4 + (size_t)C * 4 * 66 + 8 + 31) & ~(size_t)31);
     }
     // K1_REC_HDR, K1_SEG_WORDS, classes; a multiple of 4 words so every record starts on a 16-byte boundary
     s->rec_words = (uint32_t)((4 + h->channels * 68 + (units + 3) / 4 + 1 + 3) & ~(size_t)3);
@@ -322,6 +322,10 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
     const int M = g.block_size / 2;
     VpzPktOla ola;
     memset(&ola, 0, sizeof(ola));
+    if (len > (1u << 24)) {   // K1b keeps entry indices of a packet in 28 bits (8 * len + 8 of them at most)
+      if (err) *err = "audio packet larger than 16 MiB is not on the GPU path";
+      return VPZ_E_UNSUPPORTED;
+    }
     if (out->spec_floats + (uint64_t)C * M > 0xffffff00ull || end > 0xfffffff0ull || pos > 0x7fffffff) {
       if (err) *err = "run exceeds 2^32 spectrum floats / 4 GiB of packet bytes; split it";
       return VPZ_E_ARGUMENT;

@@ -764,11 +764,11 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
 // Inverse coupling, floor multiply and two 128-bit stores per channel follow.  The floor curve is
 // rendered beforehand by an exact integer DDA (RenderLineMulti, Floor1.cs:372-397), 16 bins per
 // thread, into one byte per bin of shared memory.
-//   per-warp words: urec[stages][U][4] | per channel ybuf[half_max/4] | sg[C][4*66]
+//   per-warp words: urec[stages][U][2] | per channel ybuf[half_max/4] | sg[C][4*66]
 // =============================================================================================
 
 struct K1Gather {
-  const uint32_t* urec;       // [stage][U][4]: info (0 idle; dims | log2 dims << 8), first entry (absolute), vq word offset
+  const uint32_t* urec;       // [stage][U][2]: (log2 dims + 1) << 28 | first entry (absolute; 0: idle unit), vq word offset
   const uint32_t* blob;
   const uint16_t* ent;
   uint32_t n_ent;
@@ -785,12 +785,11 @@ VPZ_DEV void k1g_fetch_chunk(const K1Gather& G, int v, int p, float* acc) {
   const int off = rel - part * G.psize;
   const int u = part * G.nvec + v;
   for (int s = 0; s < G.max_stages; s++) {
-    const uint4 R = *reinterpret_cast<const uint4*>(G.urec + (size_t)(s * G.U + u) * 4);
-    const uint32_t info = R.x;
-    if (!info) continue;
-    const int dsh = (int)((info >> 8) & 0xfu);
-    const uint32_t e0 = R.y + (uint32_t)(off >> dsh);
-    const float* vq = reinterpret_cast<const float*>(G.blob + R.z);
+    const uint2 R = *reinterpret_cast<const uint2*>(G.urec + (size_t)(s * G.U + u) * 2);
+    if (!R.x) continue;
+    const int dsh = (int)(R.x >> 28) - 1;
+    const uint32_t e0 = (R.x & 0x0fffffffu) + (uint32_t)(off >> dsh);
+    const float* vq = reinterpret_cast<const float*>(G.blob + R.y);
     const uint16_t* ep = G.ent + e0;
     const uint32_t left = e0 < G.n_ent ? G.n_ent - e0 : 0u;   // truncated packet: keep what was decoded
     if (dsh == 1) {
@@ -987,7 +986,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   const int max_stages = rs->max_stages;
 
   uint32_t* urec = smem;
-  uint8_t* ybuf = reinterpret_cast<uint8_t*>(urec + (size_t)max_stages * U * 4);   // [C][half_max] bytes
+  uint8_t* ybuf = reinterpret_cast<uint8_t*>(urec + (size_t)max_stages * U * 2);   // [C][half_max] bytes
   uint32_t* sgbase = reinterpret_cast<uint32_t*>(ybuf) + (C * half_max) / 4;        // [C][4*66]
 
   K1Gather G;
@@ -1068,10 +1067,10 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
 #pragma unroll
         for (int s = 0; s < 8; s++)
           if (s < max_stages) {
-            uint32_t* R = urec + (size_t)(s * U + u) * 4;
-            R[0] = info[s];
-            R[1] = (uint32_t)cnt[s];
-            R[2] = vqo[s];
+            // idle units keep 0; the stage base added below never reaches bit 28 (engine.cpp bounds the packet size)
+            uint32_t* R = urec + (size_t)(s * U + u) * 2;
+            R[0] = info[s] ? ((((info[s] >> 8) & 0xfu) + 1u) << 28) | (uint32_t)cnt[s] : 0u;
+            R[1] = vqo[s];
           }
       }
       __syncwarp();
@@ -1087,7 +1086,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
     for (int u = tid; u < nunits; u += 32) {
 #pragma unroll
       for (int s = 1; s < 8; s++)
-        if (s < max_stages) urec[(size_t)(s * U + u) * 4 + 1] += sbase[s];
+        if (s < max_stages && urec[(size_t)(s * U + u) * 2]) urec[(size_t)(s * U + u) * 2] += sbase[s];
     }
   }
   __syncwarp();
