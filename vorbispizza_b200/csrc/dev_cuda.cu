@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(128, 8) vpz_k1a_symbols(K1Params P) {
 }
 
 template <bool DEBUG>
-__global__ void __launch_bounds__(K1B_THREADS) vpz_k1b_spectrum(K1Params P) {
+__global__ void __launch_bounds__(K1B_THREADS, 9) vpz_k1b_spectrum(K1Params P) {
   extern __shared__ uint32_t k1_smem[];
   __shared__ uint32_t s_idx;
   k1b_cta_loop<DEBUG>(P, k1_smem, &s_idx);
