@@ -232,6 +232,68 @@ def run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
     batch.close()
 
 
+def run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank):
+    """BASELINE config 5: random-access batch -- 16,384 short excerpts per GPU, each = SeekTo(start) + read
+    4,096 samples per channel on one of {2test, 3test, issue6test} (rng(0x5EED0005), start
+    uniform in [0, total - 4096)), through the host API vpz_decode_excerpts (host Ogg images in, host
+    PCM out: provider side of SeekTo on the host, windows of many excerpts in one GPU batch, D2H)."""
+    from vorbispizza_b200 import VorbisReader
+    lib = ctx.lib
+    files = load_files()[1:]
+    totals, chans = [], []
+    for d in files:
+        with VorbisReader(ctx, d) as r:
+            totals.append(int(r.total_samples))
+            chans.append(r.channels)
+    n, nread = 16384, 4096
+    rng = np.random.default_rng(0x5EED0005 + rank)
+    file_of = rng.integers(0, len(files), n).astype(np.uint32)
+    start = np.array([int(rng.integers(0, totals[f] - nread)) for f in file_of], np.int64)
+    count = np.full(n, nread, np.int32)
+    keep = [np.frombuffer(f, np.uint8) for f in files]
+    ptrs = (C.c_void_p * len(files))(*[k.ctypes.data for k in keep])
+    lens = (C.c_size_t * len(files))(*[k.size for k in keep])
+    offsets = np.zeros(n, np.int64)
+    got = np.zeros(n, np.int32)
+    a = (ctx._h, len(files), ptrs, lens, n, file_of.ctypes.data, start.ctypes.data, count.ctypes.data, 1)
+    total = ctx.check(lib.vpz_decode_excerpts(*a, None, 0, offsets.ctypes.data, got.ctypes.data))
+    dst, dst_p = pinned_array(lib, total)
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    for _ in range(max(1, min(args.warmup, 3))):
+        ctx.check(lib.vpz_decode_excerpts(*a, dst.ctypes.data, dst.size, offsets.ctypes.data, got.ctypes.data))
+    assert (got == nread).all(), "every excerpt lies inside its file"
+    h0, d0 = lib.vpz_transfer_bytes(0), lib.vpz_transfer_bytes(1)
+    launches0 = lib.vpz_ctx_kernel_launches(ctx._h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.check(lib.vpz_decode_excerpts(*a, dst.ctypes.data, dst.size, offsets.ctypes.data, got.ctypes.data))
+    barrier()
+    t = max_over_ranks(time.perf_counter() - t0)
+    clk = clocks.stop()
+    launches = lib.vpz_ctx_kernel_launches(ctx._h) - launches0
+    delivered = sum_over_ranks(float(total))
+    v = delivered * args.steps / t
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 3),
+            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic (seeded excerpts of TestFiles)",
+            "config": {"workload": "config5: %d random-access excerpts per GPU (SeekTo + %d samples per channel on "
+                                   "{2,3,issue6}test.ogg), host Ogg images -> host PCM through vpz_decode_excerpts" % (n, nread),
+                       "excerpts_per_gpu": n, "delivered_channel_samples_per_gpu": int(total),
+                       "excerpts_per_s": n * world * args.steps / t,
+                       "note": "value counts the delivered samples only; every excerpt also decodes its pre-roll packet "
+                               "and the unused parts of its first and last packets"},
+            "clocks": clk, "gpu_launches": int(launches),
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": (lib.vpz_transfer_bytes(0) - h0) // args.steps,
+                    "d2h_bytes_per_step": (lib.vpz_transfer_bytes(1) - d0) // args.steps,
+                    "ms_per_step": 1e3 * t / args.steps, "api": "vpz_decode_excerpts"},
+        }))
+    lib.vpz_host_free(dst_p)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -241,9 +303,10 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (weak) / in total (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
-    ap.add_argument("--workload", default="config4", choices=["config4", "config3"],
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config5"],
                     help="config4 (default, the headline): 4,096 streams full decode; config3: kernel-only "
-                         "IMDCT+window+OLA on 65,536 synthetic stereo blocks")
+                         "IMDCT+window+OLA on 65,536 synthetic stereo blocks; config5: 16,384 random-access "
+                         "excerpts (SeekTo + 4,096 samples) per GPU through vpz_decode_excerpts")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--l1-bits", type=int, default=0, help=argparse.SUPPRESS)  # tuning: first-level Huffman table width
@@ -295,6 +358,12 @@ def main():
     if args.l1_bits:
         ctx.set("l1_bits", args.l1_bits)
     files = load_files()
+    if args.workload == "config5":
+        run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank)
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload == "config3":
         run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank)
         ctx.close()

@@ -65,7 +65,7 @@ int vpz_ctx_create(int device, vpz_ctx** out);
 void vpz_ctx_destroy(vpz_ctx* ctx);
 int vpz_device_count(void);
 /* Tunables (call before the first batch): key one of "l1_bits" (Huffman first-level table width,
- * default 9), "ola_chunk" (packets per IMDCT work item, default 32), "k1_warps" (warps per entropy
+ * default 9), "ola_chunk" (packets per IMDCT work item, default: 16..63 chosen per batch), "k1_warps" (warps per entropy
  * CTA, default 4), "bulk_group" (streams per pipeline group of vpz_decode_files, default 256),
  * "host_threads" (host worker threads of the bulk path, default 0 = all cores up to 32). */
 int vpz_ctx_set(vpz_ctx* ctx, const char* key, int value);
@@ -258,6 +258,21 @@ vpz_setup* vpz_reader_setup(vpz_reader* r);
  * receives samples per channel of file k.  Returns total floats written or a negative error. */
 int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens,
                          int clip, float* dst, size_t dst_floats, int64_t* sample_counts);
+
+/* ---- bulk random access: many short excerpts, one call (BASELINE config 5) -------------------- */
+/* Excerpt i is what a fresh VorbisReader over container image file_of[i] delivers for
+ *     reader.SeekTo(start[i]);  then ReadSamples until count[i] samples per channel have been read
+ * (StreamDecoder.SeekTo, StreamDecoder.cs:817-880: one packet of pre-roll, roll forward inside the
+ * target packet; ReadSamples: StreamDecoder.cs:418-498).  The host runs the provider side of every
+ * SeekTo, the windows of a group of excerpts are decoded in one GPU batch, interleaved PCM goes to
+ * dst (host): excerpt i starts at float offset dst_offsets[i] = sum over j < i of count[j] * channels
+ * (fixed layout; returned in dst_offsets when non-NULL).  got[i] receives the samples per channel that
+ * were delivered (fewer than count[i] at the end of the stream) or the negative vpz_status SeekTo
+ * raised (VPZ_E_SEEK_RANGE, VPZ_E_PREROLL, ...).  clip: ClipSamples.  dst == NULL: only the layout is
+ * computed.  Returns the total floats of the layout or a negative error. */
+int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const* datas, const size_t* lens,
+                            uint32_t n, const uint32_t* file_of, const int64_t* start, const int32_t* count,
+                            int clip, float* dst, size_t dst_floats, int64_t* dst_offsets, int32_t* got);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import numpy as np
 
 import oracle_binding as ob
 from conftest import load_file
-from vorbispizza_b200 import Batch, SynthBatch, VorbisReader, VpzError, decode_files
+from vorbispizza_b200 import Batch, SynthBatch, VorbisReader, VpzError, decode_excerpts, decode_files
 from vorbispizza_b200 import _native as N
 
 PCM_TOL = 1e-5
@@ -233,6 +233,59 @@ def seek_parity(ctx, name, positions, nread=4096, lookahead=64):
                 assert_pcm_close(b[:ng * ch], a[:no * ch], "%s after seek %d" % (name, pos))
                 assert r.sample_position == s.sample_position
                 got += no
+
+
+def excerpts_parity(ctx, names, n_excerpts, nread=4096, seed=0x5EED0005, extra_positions=(), clip=True):
+    """BASELINE config 5: a batch of short excerpts (SeekTo + read nread samples, each like a fresh reader)
+    through vpz_decode_excerpts vs the oracle's reader, excerpt by excerpt.  Start samples: seeded uniform
+    in [0, total) of a uniformly chosen file, plus `extra_positions` on every file (edge cases)."""
+    datas = [load_file(n) for n in names]
+    totals, chans = [], []
+    for d in datas:
+        s = ob.OracleStream(d)
+        ref, _, _ = s.decode_all()
+        totals.append(ref.shape[0])
+        chans.append(s.channels)
+    rng = np.random.default_rng(seed)
+    file_of = list(rng.integers(0, len(names), n_excerpts))
+    start = [int(rng.integers(0, max(1, totals[f] - 1))) for f in file_of]
+    for f in range(len(names)):
+        for p in extra_positions:
+            file_of.append(f)
+            start.append(int(p) if p >= 0 else totals[f] + int(p))
+    file_of = np.array(file_of, np.uint32)
+    start = np.array(start, np.int64)
+    count = np.full(file_of.size, nread, np.int32)
+    pcm, offsets, got = decode_excerpts(ctx, datas, file_of, start, count, clip=clip)
+    omap = {0: 0, -1: N.VPZ_E_INVALID_DATA, -2: N.VPZ_E_ARGUMENT, -3: N.VPZ_E_SEEK_RANGE, -4: N.VPZ_E_PREROLL,
+            -6: N.VPZ_E_REF_FAULT}
+    buf = np.zeros(8192 * 2, np.float32)
+    checked = 0
+    for i in range(file_of.size):
+        f = int(file_of[i])
+        ch = chans[f]
+        s = ob.OracleStream(datas[f])   # a fresh reader per excerpt
+        s.set_clip(clip)
+        try:
+            s.seek(int(start[i]))
+        except ob.OracleError as e:
+            assert got[i] == omap[e.code], "excerpt %d (%s @ %d): product %d oracle error %d" % (i, names[f], start[i], got[i], e.code)
+            continue
+        ref = []
+        n = 0
+        while n < nread:
+            want = min(nread - n, 8192)
+            no = s.read(buf[:want * ch])
+            if no <= 0:
+                break
+            ref.append(buf[:no * ch].copy())
+            n += no
+        assert got[i] == n, "excerpt %d (%s @ %d): product %d samples, oracle %d" % (i, names[f], start[i], got[i], n)
+        if n:
+            a = pcm[offsets[i]:offsets[i] + n * ch]
+            assert_pcm_close(a, np.concatenate(ref), "excerpt %d (%s @ %d)" % (i, names[f], start[i]))
+        checked += 1
+    return checked
 
 
 def reference_imdct_ola(flags, spectra, channels, size0, size1):

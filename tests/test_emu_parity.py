@@ -68,3 +68,10 @@ def test_synth_generic_block_sizes(emu_ctx):
 
 def test_decode_files(emu_ctx):
     cases.decode_files_parity(emu_ctx, ["1test", "1test"])
+
+
+def test_excerpts_batch(emu_ctx):
+    """BASELINE config 5 in small: random-access excerpts, every one like a fresh reader's SeekTo + read."""
+    n = cases.excerpts_parity(emu_ctx, ["1test", "2test"], n_excerpts=6, nread=1500,
+                              extra_positions=(0, 1, 1024, -1, -300, 10 ** 7))
+    assert n >= 12

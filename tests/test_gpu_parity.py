@@ -157,3 +157,15 @@ def test_offset_starts_match_seek_semantics(gpu_ctx):
             begin = int(cnt[:k + 1].sum())
             cases.assert_pcm_close(got, full[begin:begin + got.shape[0]], "run from packet %d" % k)
     gpu_ctx.release_setup(st)
+
+
+def test_excerpts_batch(gpu_ctx):
+    """BASELINE config 5: random-access excerpts (SeekTo + 4,096 samples) in one bulk call vs the oracle's
+    reader, incl. starts at 0 / 1 / block boundaries / the last samples / beyond the end."""
+    n = cases.excerpts_parity(gpu_ctx, ["2test", "3test", "issue6test"], n_excerpts=300, nread=4096,
+                              extra_positions=(0, 1, 127, 128, 1023, 1024, -1, -2, -4096, -5000, 10 ** 7))
+    assert n >= 300
+
+
+def test_excerpts_batch_unclipped_small_reads(gpu_ctx):
+    cases.excerpts_parity(gpu_ctx, ["1test", "3test"], n_excerpts=64, nread=700, clip=False, seed=77)

@@ -15,8 +15,9 @@ from .api import (  # noqa: F401
     SeekOutOfRangeError,
     SynthBatch,
     VorbisReader,
+    decode_excerpts,
     decode_files,
 )
 
-__all__ = ["Batch", "Context", "SynthBatch", "VorbisReader", "decode_files", "VpzError", "InvalidDataError",
+__all__ = ["Batch", "Context", "SynthBatch", "VorbisReader", "decode_files", "decode_excerpts", "VpzError", "InvalidDataError",
            "SeekOutOfRangeError", "PreRollPacketError", "load"]

@@ -463,3 +463,26 @@ def decode_files(ctx, files, clip=True, dst=None):
     total = ctx.check(ctx.lib.vpz_decode_files(ctx._h, n, ptrs, lens, int(bool(clip)), dst.ctypes.data, dst.size,
                                                counts.ctypes.data))
     return dst[:total], counts
+
+
+def decode_excerpts(ctx, files, file_of, start, count, clip=True, dst=None):
+    """Bulk random access (vpz_decode_excerpts): excerpt i = SeekTo(start[i]) + read count[i] samples per
+    channel on files[file_of[i]], every excerpt like a fresh reader; the windows of many excerpts share one
+    GPU batch.  Returns (pcm float32 1-D, offsets int64 (float offset of each excerpt in pcm), got int32
+    (samples per channel delivered, or the negative status SeekTo raised))."""
+    keep = [_u8(f) for f in files]
+    nf = len(keep)
+    ptrs = (C.c_void_p * nf)(*[k[1] for k in keep])
+    lens = (C.c_size_t * nf)(*[k[2] for k in keep])
+    file_of = np.ascontiguousarray(file_of, dtype=np.uint32)
+    start = np.ascontiguousarray(start, dtype=np.int64)
+    count = np.ascontiguousarray(count, dtype=np.int32)
+    n = file_of.size
+    offsets = np.zeros(n, np.int64)
+    got = np.zeros(n, np.int32)
+    args = (ctx._h, nf, ptrs, lens, n, file_of.ctypes.data, start.ctypes.data, count.ctypes.data, int(bool(clip)))
+    if dst is None:
+        total = ctx.check(ctx.lib.vpz_decode_excerpts(*args, None, 0, offsets.ctypes.data, got.ctypes.data))
+        dst = np.zeros(total, np.float32)
+    total = ctx.check(ctx.lib.vpz_decode_excerpts(*args, dst.ctypes.data, dst.size, offsets.ctypes.data, got.ctypes.data))
+    return dst[:total], offsets, got

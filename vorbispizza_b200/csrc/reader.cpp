@@ -108,6 +108,8 @@ struct StreamDec {
   size_t qh = 0;
   size_t pcm_cur = 0;            // float offset of the next unread sample of the current packet
   HostBuf<float> pcm;            // pinned PCM cache of the current window
+  const float* pcm_view = nullptr;  // bulk random access: the window's PCM lives in the batch staging instead
+  bool planned_only = false;     // bulk random access: the window was planned and decoded by the caller
   vpz_batch* batch = nullptr;
   int lookahead = 256;
   std::vector<uint8_t> carry;    // last decoded packet: re-submitted as the seed of the next window
@@ -220,13 +222,15 @@ int stream_init(StreamDec* d, vpz_ctx* ctx, LogicalStream* ls) {
 // (StreamDecoder.cs:640-694) on the packet headers: which packets decode, the end-of-stream trim of
 // RightStart, how many samples each makes available.  Nothing here depends on PCM values, which
 // is what lets the GPU decode the whole window in one pass afterwards.
-void plan_window(StreamDec* d, int max_packets, Window* w) {
+// need > 0: stop once the packets from SeekTo's target packet onwards make `need` samples available.
+void plan_window(StreamDec* d, int max_packets, Window* w, int64_t need = 0) {
   const Setup& st = d->setup->host;
   bool have_prev = d->have_prev;
   int prev_tail = d->prev_tail;
   int64_t pos = d->current_position;
   bool has_pos = d->has_position;
   int seek_left = d->seek_left;
+  int64_t produced = 0;
   if (have_prev && !d->carry.empty()) {
     w->src.push_back(PktSrc{d->carry.data(), (uint32_t)d->carry.size()});
     w->trims.push_back(d->carry_trim);
@@ -282,6 +286,7 @@ void plan_window(StreamDec* d, int max_packets, Window* w) {
     w->entries.push_back(e);
     have_prev = true;
     prev_tail = e.tail;
+    if (seek_left <= 1) produced += e.count;
     if (seek_left > 0) {
       // inside SeekTo: no position pick-up; after the target packet the position becomes
       // samplePosition + (count - rollForward) = provider position + count
@@ -294,6 +299,7 @@ void plan_window(StreamDec* d, int max_packets, Window* w) {
       pos += e.count;
     }
     if (e.eos_flags) break;
+    if (need > 0 && seek_left == 0 && produced >= need) break;
   }
 }
 
@@ -431,6 +437,10 @@ int decode_ahead(StreamDec* d) {
 // StreamDecoder.ReadNextPacket (StreamDecoder.cs:640-694), consumption side
 bool read_next_packet(StreamDec* d, int64_t* sample_position, int* err) {
   *sample_position = -1;
+  if (d->qh == d->q.size() && d->planned_only) {  // the caller planned exactly what it reads
+    d->eos_found |= EOS_INVALID_PACKET;
+    return false;
+  }
   if (d->qh == d->q.size()) {
     int rc = decode_ahead(d);
     if (rc) {
@@ -520,7 +530,7 @@ int stream_read(StreamDec* d, float* buffer, int nfloats, int samples_to_read, i
       if (d->prev_avail < 0) return VPZ_E_REF_FAULT;
       continue;
     }
-    const float* src = d->pcm.p + d->pcm_cur;
+    const float* src = (d->pcm_view ? d->pcm_view : d->pcm.p) + d->pcm_cur;
     bool clipped = false;
     if (interleave) {
       float* dst = buffer + (size_t)idx * C;
@@ -551,31 +561,28 @@ int stream_read(StreamDec* d, float* buffer, int nfloats, int samples_to_read, i
 
 int64_t stream_total_samples(StreamDec* d, int* err) { return d->ls->total_granules(err); }
 
-// StreamDecoder.SeekTo (StreamDecoder.cs:817-880)
-int stream_seek(StreamDec* d, int64_t sample_position, int origin) {
-  if (!d->ls->can_seek()) return VPZ_E_INVALID_OP;
-  if (sample_position < 0) return VPZ_E_ARGUMENT;
+// StreamDecoder.SeekTo (StreamDecoder.cs:817-880) in two halves.  seek_begin: the packet provider
+// repositions (pre-roll of one packet) and the decoder is reset; seek_finish: SeekTo consumes the
+// pre-roll and the target packet and rolls forward inside the target.  Between the two the window that
+// starts at the pre-roll packet gets planned and decoded -- by decode_ahead on the reader path, by the
+// caller for a whole batch of excerpts on the bulk random-access path.
+int seek_begin(StreamDec* d, int64_t sample_position, int64_t* pos_out) {
   int err = 0;
-  switch (origin) {
-    case 0: break;
-    case 1: sample_position = d->current_position - sample_position; break;
-    case 2: {
-      int64_t total = stream_total_samples(d, &err);
-      if (err) return err;
-      sample_position = total - sample_position;
-      break;
-    }
-    default: return VPZ_E_ARGUMENT;
-  }
   // the provider cursor has run ahead of the consumer; SeekTo repositions it anyway
   int64_t pos = d->ls->seek_to(sample_position, 1, &err);
   if (err) return err;
-  int roll_forward = (int)(sample_position - pos);
   d->reset_decoder();
   d->fault = 0;
   d->has_position = true;
   d->seek_left = 2;
   d->seek_pos = pos;
+  *pos_out = pos;
+  return VPZ_OK;
+}
+
+int seek_finish(StreamDec* d, int64_t sample_position, int64_t pos) {
+  int err = 0;
+  int roll_forward = (int)(sample_position - pos);
   struct SeekDone {
     StreamDec* d;
     ~SeekDone() { d->seek_left = 0; }
@@ -602,6 +609,27 @@ int stream_seek(StreamDec* d, int64_t sample_position, int origin) {
   d->pcm_cur += (size_t)roll_forward * d->channels();
   d->current_position = sample_position;
   return VPZ_OK;
+}
+
+// StreamDecoder.SeekTo (StreamDecoder.cs:817-880)
+int stream_seek(StreamDec* d, int64_t sample_position, int origin) {
+  if (!d->ls->can_seek()) return VPZ_E_INVALID_OP;
+  if (sample_position < 0) return VPZ_E_ARGUMENT;
+  int err = 0;
+  switch (origin) {
+    case 0: break;
+    case 1: sample_position = d->current_position - sample_position; break;
+    case 2: {
+      int64_t total = stream_total_samples(d, &err);
+      if (err) return err;
+      sample_position = total - sample_position;
+      break;
+    }
+    default: return VPZ_E_ARGUMENT;
+  }
+  int64_t pos = 0;
+  int rc = seek_begin(d, sample_position, &pos);
+  return rc ? rc : seek_finish(d, sample_position, pos);
 }
 
 void build_table(StreamDec* d) {
@@ -925,6 +953,250 @@ int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, 
   if (trace)
     fprintf(stderr, "vpz_decode_files: %u files, %u groups: scan %.1f init %.1f plan %.1f commit %.1f launch %.1f wait %.1f drain %.1f ms\n",
             n, group, t_scan, t_init, t_plan, t_commit, t_launch, t_wait, now() - t0);
+  return rc ? rc : total;
+}
+
+
+// ---- bulk random access (BASELINE config 5): many short excerpts, SeekTo + Read each --------------
+// Every excerpt behaves like a fresh reader on its file that calls SeekTo(start) and then reads `count`
+// samples per channel.  The host runs the provider side of SeekTo for all excerpts (page search, one
+// packet of pre-roll), plans each excerpt's window (plan_window with the seek state, so the stale-position
+// trim of quirk Q5 and the end-of-stream rules are the reader's own), the GPU decodes the windows of
+// a group of excerpts in one batch, and the consumer side of SeekTo / Read (seek_finish, stream_read)
+// runs against that batch's PCM.  Groups are double-buffered: the host delivers group g-1 while the
+// GPU decodes group g.
+namespace {
+struct ExcerptFile {
+  OggContainer cont;
+  StreamDec master;
+  int rc = 0;
+  std::string err;
+};
+struct ExcerptJob {
+  uint32_t index = 0;          // position in the caller's arrays
+  Window win;
+  int64_t pos = 0;             // granule position the provider reported for the target packet
+  int status = 0;              // error of the provider side of SeekTo
+  int run = -1, drain_run = -1;
+};
+struct ExcerptTask {           // consecutive excerpts of one file, handled by one worker with its own cursor
+  uint32_t file = 0;
+  size_t first = 0, count = 0; // range in the sorted job array
+  std::unique_ptr<LogicalStream> ls;
+  std::unique_ptr<StreamDec> dec;
+};
+}  // namespace
+
+int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const* datas, const size_t* lens, uint32_t n,
+                            const uint32_t* file_of, const int64_t* start, const int32_t* count, int clip, float* dst,
+                            size_t dst_floats, int64_t* dst_offsets, int32_t* got) {
+  if (!ctx || !datas || !lens || (n && (!file_of || !start || !count))) return VPZ_E_ARGUMENT;
+  if (!ctx->pool) {
+    unsigned t = ctx->host_threads > 0 ? (unsigned)ctx->host_threads
+                                       : std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    ctx->pool = new (std::nothrow) ThreadPool(t);
+    if (!ctx->pool) return VPZ_E_NOMEM;
+  }
+  ThreadPool* pool = ctx->pool;
+  // ---- files: page scan, headers, setup tables (once per file) ------------------------------------
+  std::vector<std::unique_ptr<ExcerptFile>> files(n_files);
+  pool->parallel_for(n_files, [&](size_t i) {
+    files[i].reset(new ExcerptFile);
+    ExcerptFile& f = *files[i];
+    f.rc = f.cont.scan(datas[i], lens[i]);
+    if (!f.rc) f.rc = stream_prepare(&f.master, f.cont.streams[0], &f.err);
+  });
+  for (uint32_t i = 0; i < n_files; i++) {
+    ExcerptFile& f = *files[i];
+    if (f.rc) {
+      ctx->last_error = f.err;
+      return f.rc;
+    }
+    int rc = stream_attach(&f.master, ctx);
+    if (rc) return rc;
+    int err = 0;
+    f.master.ls->total_granules(&err);   // loads every page and fills the seek cache the copies inherit
+    if (err) return err;
+  }
+  // ---- layout of the destination -------------------------------------------------------------------
+  int64_t total = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (file_of[i] >= n_files || start[i] < 0 || count[i] < 0) return VPZ_E_ARGUMENT;
+    if (dst_offsets) dst_offsets[i] = total;
+    total += (int64_t)count[i] * files[file_of[i]]->master.channels();
+  }
+  if (!dst) return total;
+  if ((uint64_t)total > dst_floats) {
+    ctx->last_error = "destination buffer too small";
+    return VPZ_E_ARGUMENT;
+  }
+  // ---- tasks: excerpts sorted by file, at most 128 per task -------------------------------------------
+  std::vector<ExcerptJob> jobs(n);
+  {
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return file_of[a] < file_of[b]; });
+    for (uint32_t i = 0; i < n; i++) jobs[i].index = order[i];
+  }
+  std::vector<ExcerptTask> tasks;
+  for (size_t i = 0; i < n;) {
+    size_t j = i;
+    const uint32_t f = file_of[jobs[i].index];
+    while (j < n && j - i < 128 && file_of[jobs[j].index] == f) j++;
+    ExcerptTask t;
+    t.file = f;
+    t.first = i;
+    t.count = j - i;
+    tasks.push_back(std::move(t));
+    i = j;
+  }
+  for (ExcerptTask& t : tasks) {   // cursors and decoders of the tasks (serial: setup reference counts)
+    StreamDec& m = files[t.file]->master;
+    t.ls.reset(new LogicalStream(*m.ls));
+    t.dec.reset(new StreamDec);
+    StreamDec* d = t.dec.get();
+    d->ctx = ctx;
+    d->ls = t.ls.get();
+    d->setup = m.setup;
+    m.setup->refs++;
+    d->ls->granule_count = [d](const OggPacket& pk) { return d->granule_count(pk); };
+    d->clip = clip != 0;
+    d->planned_only = true;
+  }
+  // ---- plan every excerpt (provider side of SeekTo + window plan) -------------------------------------
+  pool->parallel_for(tasks.size(), [&](size_t ti) {
+    ExcerptTask& t = tasks[ti];
+    StreamDec* d = t.dec.get();
+    for (size_t k = 0; k < t.count; k++) {
+      ExcerptJob& j = jobs[t.first + k];
+      const int64_t sp = start[j.index];
+      d->current_position = 0;   // a fresh reader (the stale position enters SeekTo's end-of-stream trim, quirk Q5)
+      d->has_clipped = false;
+      j.status = seek_begin(d, sp, &j.pos);
+      if (j.status) continue;
+      plan_window(d, 0, &j.win, (sp - j.pos) + (int64_t)count[j.index]);
+      d->seek_left = 0;
+      resolve_drain(d, &j.win);
+      std::string err;
+      int rc = plan_submit(d, &j.win, &err);
+      if (rc) j.status = rc;
+    }
+  });
+  // ---- groups of tasks through two batches -----------------------------------------------------------
+  const size_t tasks_per_group = 16;
+  HostBuf<float> staging[2];
+  dev::Event* done[2] = {nullptr, nullptr};
+  int rc = VPZ_OK;
+  auto deliver = [&](size_t g, int slot) {
+    const size_t t0 = g * tasks_per_group, t1 = std::min(tasks.size(), t0 + tasks_per_group);
+    vpz_batch* b = ctx->bulk[slot];
+    pool->parallel_for(t1 - t0, [&](size_t k) {
+      ExcerptTask& t = tasks[t0 + k];
+      StreamDec* d = t.dec.get();
+      for (size_t q = 0; q < t.count; q++) {
+        ExcerptJob& j = jobs[t.first + q];
+        const uint32_t i = j.index;
+        if (j.status) {
+          if (got) got[i] = j.status;
+          continue;
+        }
+        int prc = place_window(d, b, &j.win, j.run, j.drain_run, 0);
+        if (prc) {
+          if (got) got[i] = prc;
+          continue;
+        }
+        // consumer side: SeekTo's two packets, then Read until `count` samples or the end
+        d->current_position = 0;
+        d->reset_decoder();
+        d->fault = 0;
+        d->has_position = true;
+        d->seek_left = 2;
+        d->seek_pos = j.pos;
+        d->q = std::move(j.win.entries);
+        d->qh = 0;
+        d->pcm_view = staging[slot].p;
+        int src = seek_finish(d, start[i], j.pos);
+        int have = 0;
+        const int C = d->channels();
+        float* out = dst + (dst_offsets ? dst_offsets[i] : 0);
+        if (!src) {
+          while (have < count[i]) {
+            int r = stream_read(d, out + (size_t)have * C, (count[i] - have) * C, count[i] - have, 0, true);
+            if (r <= 0) break;
+            have += r;
+          }
+        }
+        if (got) got[i] = src ? src : have;
+        j.win = Window();   // release the packet views / arena
+      }
+    });
+  };
+  // dst_offsets is needed by deliver: compute a private copy when the caller passed none
+  std::vector<int64_t> own_offsets;
+  if (!dst_offsets) {
+    own_offsets.resize(n);
+    int64_t acc = 0;
+    for (uint32_t i = 0; i < n; i++) {
+      own_offsets[i] = acc;
+      acc += (int64_t)count[i] * files[file_of[i]]->master.channels();
+    }
+    dst_offsets = own_offsets.data();
+  }
+  const size_t n_groups = (tasks.size() + tasks_per_group - 1) / tasks_per_group;
+  for (size_t g = 0; g < n_groups && !rc; g++) {
+    const int slot = (int)(g & 1);
+    if (!ctx->bulk[slot]) {
+      if ((rc = vpz_batch_create(ctx, &ctx->bulk[slot]))) break;
+    }
+    if (!done[slot]) done[slot] = dev::event_create();
+    vpz_batch* b = ctx->bulk[slot];
+    vpz_batch_reset(b);
+    const size_t t0 = g * tasks_per_group, t1 = std::min(tasks.size(), t0 + tasks_per_group);
+    std::vector<RunPlan*> plans;
+    std::vector<std::pair<ExcerptJob*, int>> owner;   // plan -> (job, 0 run / 1 drain run)
+    for (size_t ti = t0; ti < t1; ti++)
+      for (size_t q = 0; q < tasks[ti].count; q++) {
+        ExcerptJob& j = jobs[tasks[ti].first + q];
+        if (j.status) continue;
+        if (j.win.has_plan) {
+          plans.push_back(&j.win.plan);
+          owner.push_back({&j, 0});
+        }
+        if (j.win.has_drain_plan) {
+          plans.push_back(&j.win.drain_plan);
+          owner.push_back({&j, 1});
+        }
+      }
+    int first = 0;
+    if ((rc = batch_commit(b, plans.data(), plans.size(), pool, &first))) break;
+    for (size_t k = 0; k < owner.size(); k++) (owner[k].second ? owner[k].first->drain_run : owner[k].first->run) = first + (int)k;
+    const size_t floats = (size_t)b->total_floats;
+    if (floats) {
+      if (!staging[slot].reserve(floats)) {
+        rc = VPZ_E_NOMEM;
+        break;
+      }
+      // the reader clips while it copies (per-sample HasClipped): decode unclipped
+      if ((rc = batch_decode(b, 0))) break;
+      if ((rc = dev::d2h(staging[slot].p, b->d_pcm.p, floats * 4, ctx->stream, ctx->last_error))) break;
+    }
+    dev::event_record(done[slot], ctx->stream);
+    if (g > 0) {   // deliver the previous group while this one is on the GPU
+      if ((rc = dev::event_sync(done[slot ^ 1], ctx->last_error))) break;
+      deliver(g - 1, slot ^ 1);
+    }
+  }
+  if (!rc && n_groups) {
+    const int slot = (int)((n_groups - 1) & 1);
+    rc = dev::event_sync(done[slot], ctx->last_error);
+    if (!rc) deliver(n_groups - 1, slot);
+  }
+  int r2 = dev::stream_sync(ctx->stream, ctx->last_error);
+  if (!rc) rc = r2;
+  for (int s2 = 0; s2 < 2; s2++) {
+    if (done[s2]) dev::event_destroy(done[s2]);
+    if (ctx->bulk[s2]) vpz_batch_reset(ctx->bulk[s2]);
+  }
   return rc ? rc : total;
 }
 
