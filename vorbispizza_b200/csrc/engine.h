@@ -81,6 +81,8 @@ struct vpz_ctx {
   struct vpz_batch* bulk[3] = {nullptr, nullptr, nullptr};
   vpz::dev::Event* bulk_done[3] = {nullptr, nullptr, nullptr};   // D2H of the batch's PCM finished
   vpz::dev::Event* bulk_ready[3] = {nullptr, nullptr, nullptr};  // kernels of the batch finished
+  float* xstage[2] = {nullptr, nullptr};     // vpz_decode_excerpts: pinned PCM staging of the two groups in flight
+  size_t xstage_cap[2] = {0, 0};             // (floats)
   int bulk_group = 256;                      // streams per pipeline group ("bulk_group" tunable)
   int host_threads = 0;                      // 0: hardware concurrency, capped at 32
 };

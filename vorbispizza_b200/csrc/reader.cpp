@@ -998,6 +998,9 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
     if (!ctx->pool) return VPZ_E_NOMEM;
   }
   ThreadPool* pool = ctx->pool;
+  const bool trace = getenv("VPZ_TRACE") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_files = 0, t_tasks = 0, t_plan = 0, t_commit = 0, t_launch = 0, t_wait = 0, t_deliver = 0, tt0 = now(), tt1;
   // ---- files: page scan, headers, setup tables (once per file) ------------------------------------
   std::vector<std::unique_ptr<ExcerptFile>> files(n_files);
   pool->parallel_for(n_files, [&](size_t i) {
@@ -1018,6 +1021,7 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
     f.master.ls->total_granules(&err);   // loads every page and fills the seek cache the copies inherit
     if (err) return err;
   }
+  tt1 = now(); t_files = tt1 - tt0; tt0 = tt1;
   // ---- layout of the destination -------------------------------------------------------------------
   int64_t total = 0;
   for (uint32_t i = 0; i < n; i++) {
@@ -1063,6 +1067,7 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
     d->clip = clip != 0;
     d->planned_only = true;
   }
+  tt1 = now(); t_tasks = tt1 - tt0; tt0 = tt1;
   // ---- plan every excerpt (provider side of SeekTo + window plan) -------------------------------------
   pool->parallel_for(tasks.size(), [&](size_t ti) {
     ExcerptTask& t = tasks[ti];
@@ -1082,9 +1087,10 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
       if (rc) j.status = rc;
     }
   });
+  tt1 = now(); t_plan = tt1 - tt0; tt0 = tt1;
   // ---- groups of tasks through two batches -----------------------------------------------------------
   const size_t tasks_per_group = 16;
-  HostBuf<float> staging[2];
+  float** staging = ctx->xstage;   // pinned, kept between calls
   dev::Event* done[2] = {nullptr, nullptr};
   int rc = VPZ_OK;
   auto deliver = [&](size_t g, int slot) {
@@ -1114,7 +1120,7 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
         d->seek_pos = j.pos;
         d->q = std::move(j.win.entries);
         d->qh = 0;
-        d->pcm_view = staging[slot].p;
+        d->pcm_view = staging[slot];
         int src = seek_finish(d, start[i], j.pos);
         int have = 0;
         const int C = d->channels();
@@ -1168,29 +1174,47 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
         }
       }
     int first = 0;
+    tt0 = now();
     if ((rc = batch_commit(b, plans.data(), plans.size(), pool, &first))) break;
+    tt1 = now(); t_commit += tt1 - tt0; tt0 = tt1;
     for (size_t k = 0; k < owner.size(); k++) (owner[k].second ? owner[k].first->drain_run : owner[k].first->run) = first + (int)k;
     const size_t floats = (size_t)b->total_floats;
     if (floats) {
-      if (!staging[slot].reserve(floats)) {
-        rc = VPZ_E_NOMEM;
-        break;
+      if (floats > ctx->xstage_cap[slot]) {
+        dev::host_free(ctx->xstage[slot]);
+        ctx->xstage_cap[slot] = 0;
+        const size_t want = floats + floats / 4;
+        ctx->xstage[slot] = static_cast<float*>(dev::host_alloc(want * sizeof(float)));
+        if (!ctx->xstage[slot]) {
+          rc = VPZ_E_NOMEM;
+          break;
+        }
+        ctx->xstage_cap[slot] = want;
       }
       // the reader clips while it copies (per-sample HasClipped): decode unclipped
       if ((rc = batch_decode(b, 0))) break;
-      if ((rc = dev::d2h(staging[slot].p, b->d_pcm.p, floats * 4, ctx->stream, ctx->last_error))) break;
+      if ((rc = dev::d2h(staging[slot], b->d_pcm.p, floats * 4, ctx->stream, ctx->last_error))) break;
     }
     dev::event_record(done[slot], ctx->stream);
+    tt1 = now(); t_launch += tt1 - tt0; tt0 = tt1;
     if (g > 0) {   // deliver the previous group while this one is on the GPU
       if ((rc = dev::event_sync(done[slot ^ 1], ctx->last_error))) break;
+      tt1 = now(); t_wait += tt1 - tt0; tt0 = tt1;
       deliver(g - 1, slot ^ 1);
+      tt1 = now(); t_deliver += tt1 - tt0; tt0 = tt1;
     }
   }
   if (!rc && n_groups) {
     const int slot = (int)((n_groups - 1) & 1);
+    tt0 = now();
     rc = dev::event_sync(done[slot], ctx->last_error);
+    tt1 = now(); t_wait += tt1 - tt0; tt0 = tt1;
     if (!rc) deliver(n_groups - 1, slot);
+    tt1 = now(); t_deliver += tt1 - tt0; tt0 = tt1;
   }
+  if (trace)
+    fprintf(stderr, "vpz_decode_excerpts: %u excerpts, %zu tasks, %zu groups: files %.1f tasks %.1f plan %.1f commit %.1f launch %.1f wait %.1f deliver %.1f ms\n",
+            n, tasks.size(), n_groups, t_files, t_tasks, t_plan, t_commit, t_launch, t_wait, t_deliver);
   int r2 = dev::stream_sync(ctx->stream, ctx->last_error);
   if (!rc) rc = r2;
   for (int s2 = 0; s2 < 2; s2++) {
