@@ -360,6 +360,10 @@ def main():
     lib = ctx.lib
     if args.l1_bits:
         ctx.set("l1_bits", args.l1_bits)
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+    if local_world > 1:
+        # the ranks of one box share its host cores: split them instead of oversubscribing the bulk path's pool
+        ctx.set("host_threads", max(2, min(32, (os.cpu_count() or 2) // local_world)))
     files = load_files()
     if args.workload == "config5":
         run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank)

@@ -5,11 +5,15 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "../../include/vpz.h"
 #include "bitreader.h"
 
 namespace vpz {
+
+double g_trace_ms[4] = {0, 0, 0, 0};   // VPZ_TRACE: batch_upload sort, batch_upload copies, batch_decode launches, spare
+static double trace_now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 // vectors * partitions of the largest residue of the setup (units of K1a/K1b)
 static size_t max_units(const Setup& st) {
@@ -413,6 +417,7 @@ int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool
   const size_t old_bytes = b->bytes.n;
   if (!b->bytes.reserve(bytes) || !b->pkts_in.reserve(pkt) || !b->pkts_ola.reserve(pkt) || !b->items.reserve(item))
     return VPZ_E_NOMEM;
+  b->sort_key.resize(pkt);
   memset(b->bytes.p + old_bytes, 0, (size_t)base[0].bytes - old_bytes);
   auto fill = [&](size_t i) {
     const RunPlan& p = *plans[i];
@@ -436,6 +441,9 @@ int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool
       VpzPktOla ola = p.ola[k];
       ola.spec_off = in.spec_off;
       b->pkts_ola.p[bs.pkt + k] = ola;
+      // K1a order key: (setup slot, short block) group, then longest packets first
+      b->sort_key[bs.pkt + k] = (((uint32_t)bs.slot * 2u + ((ola.flags & VPZ_OLA_LONG) ? 0u : 1u)) << 13) |
+                                (4096u - std::min<uint32_t>(len >> 2, 4096u));
     }
     // K3 work items: packets 1..nv-1 emit; each item re-runs its predecessor as carry seed
     size_t it_idx = bs.item;
@@ -517,23 +525,32 @@ int batch_upload(vpz_batch* b) {
     // residue configuration with packets of like size (convergent control flow), the warps resident
     // on an SM share one setup's Huffman tables in L1, and the long packets do not form the tail.
     if (!b->order.reserve(2 * np + 2)) return VPZ_E_NOMEM;
+    const double ts0 = trace_now();
     {
-      uint32_t* tmp = b->order.p + np + 1;
-      std::vector<uint32_t> bucket(4098, 0);
-      auto key = [&](size_t i) { return (size_t)(4096 - std::min<uint32_t>(b->pkts_in.p[i].byte_len >> 2, 4096)); };
-      for (size_t i = 0; i < np; i++) bucket[key(i) + 1]++;
-      for (size_t k = 1; k < bucket.size(); k++) bucket[k] += bucket[k - 1];
-      for (size_t i = 0; i < np; i++) tmp[bucket[key(i)]++] = (uint32_t)i;
+      // sort_key = group << 13 | (4096 - min(byte_len / 4, 4096)), group = setup slot * 2 + (short block);
+      // it was written by the threads that filled the batch, so the sort reads 4 bytes per packet
       const size_t ngroups = 2 * b->slots.size();
-      std::vector<uint32_t> gb(ngroups + 2, 0);
-      auto gkey = [&](uint32_t i) {
-        return (size_t)b->pkts_in.p[i].setup_slot * 2 + ((b->pkts_ola.p[i].flags & VPZ_OLA_LONG) ? 0 : 1);
-      };
-      for (size_t i = 0; i < np; i++) gb[gkey((uint32_t)i) + 1]++;
-      for (size_t k = 1; k < gb.size(); k++) gb[k] += gb[k - 1];
-      for (size_t i = 0; i < np; i++) b->order.p[gb[gkey(tmp[i])]++] = tmp[i];
+      const uint32_t* key = b->sort_key.data();
+      if (ngroups * 4097 <= ((size_t)1 << 20)) {
+        std::vector<uint32_t> bucket(ngroups * 4097 + 2, 0);
+        auto k1 = [&](size_t i) { return (size_t)(key[i] >> 13) * 4097 + (key[i] & 8191u); };
+        for (size_t i = 0; i < np; i++) bucket[k1(i) + 1]++;
+        for (size_t k = 1; k < bucket.size(); k++) bucket[k] += bucket[k - 1];
+        for (size_t i = 0; i < np; i++) b->order.p[bucket[k1(i)]++] = (uint32_t)i;
+      } else {   // many setups: two stable passes
+        uint32_t* tmp = b->order.p + np + 1;
+        std::vector<uint32_t> bucket(4098, 0);
+        for (size_t i = 0; i < np; i++) bucket[(key[i] & 8191u) + 1]++;
+        for (size_t k = 1; k < bucket.size(); k++) bucket[k] += bucket[k - 1];
+        for (size_t i = 0; i < np; i++) tmp[bucket[key[i] & 8191u]++] = (uint32_t)i;
+        std::vector<uint32_t> gb(ngroups + 2, 0);
+        for (size_t i = 0; i < np; i++) gb[(key[i] >> 13) + 1]++;
+        for (size_t k = 1; k < gb.size(); k++) gb[k] += gb[k - 1];
+        for (size_t i = 0; i < np; i++) b->order.p[gb[key[tmp[i]] >> 13]++] = tmp[i];
+      }
       b->order.n = np;
     }
+    g_trace_ms[0] += trace_now() - ts0;
     if ((rc = dev::h2d(b->d_order.p, b->order.p, np * 4, st, err))) return rc;
   }
   if (!b->d_pkts_ola.reserve(np * sizeof(VpzPktOla), err) || !b->d_items.reserve(b->items.n * sizeof(VpzOlaItem), err) ||
@@ -558,9 +575,16 @@ int batch_decode(vpz_batch* b, int clip) {
   std::string& err = ctx->last_error;
   dev::Stream* st = ctx->stream;
   if (!b->uploaded) {
+    const double tu0 = trace_now();
     int rc = batch_upload(b);
+    g_trace_ms[1] += trace_now() - tu0;
     if (rc) return rc;
   }
+  const double tl0 = trace_now();
+  struct TraceLaunch {
+    double t0;
+    ~TraceLaunch() { g_trace_ms[2] += trace_now() - t0; }
+  } trace_launch{tl0};
   const size_t np = b->pkts_ola.n;
   int rc;
   b->launches = 0;

@@ -176,7 +176,8 @@ struct vpz_batch {
   uint64_t total_floats = 0, spec_floats = 0;
   uint64_t payload_bytes = 0;
   uint64_t rec_words = 0, ent_total = 0;      // symbol records / entry indices of all packets
-  vpz::HostBuf<uint32_t> order;               // K1a packet order (by byte length)
+  vpz::HostBuf<uint32_t> order;               // K1a packet order (by (setup, block size), then byte length)
+  std::vector<uint32_t> sort_key;             // per packet: group << 13 | length key, written while the batch is filled
   vpz::DevBuf d_rec, d_ent, d_order;
   int max_channels = 1;
   bool uploaded = false, synthetic = false, decoded = false;
@@ -208,6 +209,7 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
 // first_run receives the index of plans[0]'s run.
 int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool, int* first_run);
 uint32_t pick_ola_chunk(const vpz_ctx* ctx, uint64_t total_packets);
+extern double g_trace_ms[4];   // VPZ_TRACE: host milliseconds inside batch_upload / batch_decode (engine.cpp)
 int batch_upload(vpz_batch* b);
 int batch_decode(vpz_batch* b, int clip);
 int batch_fetch_clip(vpz_batch* b);

@@ -950,9 +950,12 @@ int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, 
     for (int s = 0; s < 3; s++)
       if (ctx->bulk[s]) vpz_batch_reset(ctx->bulk[s]);  // drop setup references; device buffers stay allocated
   }
-  if (trace)
+  if (trace) {
     fprintf(stderr, "vpz_decode_files: %u files, %u groups: scan %.1f init %.1f plan %.1f commit %.1f launch %.1f wait %.1f drain %.1f ms\n",
             n, group, t_scan, t_init, t_plan, t_commit, t_launch, t_wait, now() - t0);
+    fprintf(stderr, "  inside launch (cumulative): order sort %.1f, upload incl. sort %.1f, kernel launches %.1f ms\n",
+            vpz::g_trace_ms[0], vpz::g_trace_ms[1], vpz::g_trace_ms[2]);
+  }
   return rc ? rc : total;
 }
 
