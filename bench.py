@@ -497,6 +497,23 @@ def main():
                "ms_per_step": 1e3 * t_e2e / e_steps, "steps": e_steps,
                "api": "vpz_decode_files (host Ogg images -> pinned host PCM)"}
         lib.vpz_host_free(dst_p)
+        # the same call with 16-bit output (conversion fused into the IMDCT kernel, half the
+        # device-to-host bytes) -- reported beside the fp32 number, which stays the headline
+        dst16 = lib.vpz_host_alloc(int(e_total) * 2)
+        if dst16:
+            for _ in range(2):
+                ctx.check(lib.vpz_decode_files_s16(ctx._h, n_streams, ptrs, lens, 1, dst16, e_total, counts.ctypes.data))
+            d1 = lib.vpz_transfer_bytes(1)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e_steps):
+                ctx.check(lib.vpz_decode_files_s16(ctx._h, n_streams, ptrs, lens, 1, dst16, e_total, counts.ctypes.data))
+            barrier()
+            t16 = max_over_ranks(time.perf_counter() - t0)
+            e2e["s16"] = {"value": e_samples * e_steps / t16, "unit": UNIT, "ms_per_step": 1e3 * t16 / e_steps,
+                          "d2h_bytes_per_step": (lib.vpz_transfer_bytes(1) - d1) // e_steps,
+                          "api": "vpz_decode_files_s16 (16-bit PCM by the reference tests' (int)(x*32768f) rule)"}
+            lib.vpz_host_free(dst16)
 
     # ---- cpu baseline (rank 0, N=1): the oracle on all host cores, bounded sample ----------------
     cpu = None

@@ -259,6 +259,13 @@ vpz_setup* vpz_reader_setup(vpz_reader* r);
 int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens,
                          int clip, float* dst, size_t dst_floats, int64_t* sample_counts);
 
+/* The same with 16-bit output: every sample is converted on the GPU by the rule the reference's own
+ * tests apply to the float output, v = (int)(x * 32768f) clamped to [-32768, 32767] (AssetTest.cs:131-132),
+ * after ClipSamples when clip != 0.  Halves the device-to-host bytes.  Block sizes 256 / 2048 and mono /
+ * stereo only (VPZ_E_UNSUPPORTED otherwise).  dst_samples / return value: int16 elements. */
+int64_t vpz_decode_files_s16(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens,
+                             int clip, int16_t* dst, size_t dst_samples, int64_t* sample_counts);
+
 /* ---- bulk random access: many short excerpts, one call (BASELINE config 5) -------------------- */
 /* Excerpt i is what a fresh VorbisReader over container image file_of[i] delivers for
  *     reader.SeekTo(start[i]);  then ReadSamples until count[i] samples per channel have been read

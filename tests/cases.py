@@ -235,6 +235,34 @@ def seek_parity(ctx, name, positions, nread=4096, lookahead=64):
                 got += no
 
 
+def decode_files_s16_parity(ctx, names, clip=True):
+    """16-bit bulk output (vpz_decode_files_s16) vs the oracle's float PCM converted by the reference tests'
+    rule v = (int)(x * 32768f) clamped (AssetTest.cs:131-132): at most 1 LSB apart (the float PCM itself agrees
+    to ~1e-6, which can move a sample across a truncation boundary), and identical to the product's own float
+    output converted by the same rule."""
+    datas = [load_file(n) for n in names]
+    pcm16, counts = decode_files(ctx, datas, clip=clip, s16=True)
+    pcmf, countsf = decode_files(ctx, datas, clip=clip)
+    assert pcm16.dtype == np.int16 and (counts == countsf).all()
+
+    def to_s16(x):
+        v = np.trunc(x.astype(np.float32) * np.float32(32768.0)).astype(np.int64)
+        return np.clip(v, -32768, 32767).astype(np.int16)
+
+    assert np.array_equal(pcm16, to_s16(pcmf)), "GPU conversion differs from the rule applied to the GPU float output"
+    off = 0
+    for n, d, cnt in zip(names, datas, counts):
+        s = ob.OracleStream(d)
+        s.set_clip(clip)
+        ref, _, _ = s.decode_all()
+        assert cnt == ref.shape[0]
+        got = pcm16[off:off + cnt * s.channels].reshape(-1, s.channels)
+        off += cnt * s.channels
+        diff = np.abs(got.astype(np.int32) - to_s16(ref).astype(np.int32))
+        assert diff.max() <= 1, "%s: max 16-bit difference %d" % (n, diff.max())
+    assert off == pcm16.size
+
+
 def excerpts_parity(ctx, names, n_excerpts, nread=4096, seed=0x5EED0005, extra_positions=(), clip=True):
     """BASELINE config 5: a batch of short excerpts (SeekTo + read nread samples, each like a fresh reader)
     through vpz_decode_excerpts vs the oracle's reader, excerpt by excerpt.  Start samples: seeded uniform

@@ -138,7 +138,7 @@ int launch_k3_streams(const K3Params& p, Stream*, std::string&) {
   *p.counter = 0;
   const unsigned groups = p.n_items >= 3 ? 3 : 1;   // independent 64-thread workers per emulated CTA
   emu::launch(2, groups * K3_THREADS_PER_CH, ((size_t)K3S_TAB_FLOATS + groups * K3S_GROUP_FLOATS) * 4, [&] {
-    k3s_cta(p, (float*)emu::t_block->smem);
+    if (p.out16) k3s_cta<true>(p, (float*)emu::t_block->smem); else k3s_cta<false>(p, (float*)emu::t_block->smem);
   });
   return VPZ_OK;
 }

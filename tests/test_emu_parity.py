@@ -75,3 +75,7 @@ def test_excerpts_batch(emu_ctx):
     n = cases.excerpts_parity(emu_ctx, ["1test", "2test"], n_excerpts=6, nread=1500,
                               extra_positions=(0, 1, 1024, -1, -300, 10 ** 7))
     assert n >= 12
+
+
+def test_decode_files_s16(emu_ctx):
+    cases.decode_files_s16_parity(emu_ctx, ["1test"])

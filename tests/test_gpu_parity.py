@@ -169,3 +169,9 @@ def test_excerpts_batch(gpu_ctx):
 
 def test_excerpts_batch_unclipped_small_reads(gpu_ctx):
     cases.excerpts_parity(gpu_ctx, ["1test", "3test"], n_excerpts=64, nread=700, clip=False, seed=77)
+
+
+@pytest.mark.parametrize("clip", [True, False])
+def test_decode_files_s16(gpu_ctx, clip):
+    """16-bit output fused into the IMDCT kernel (half the device-to-host bytes)."""
+    cases.decode_files_s16_parity(gpu_ctx, FILES, clip=clip)

@@ -118,6 +118,7 @@ _SIGS = {
     "vpz_reader_header_packet": (_P, [_P, C.c_int, C.POINTER(C.c_uint32)]),
     "vpz_reader_setup": (_P, [_P]),
     "vpz_decode_files": (C.c_int64, [_P, C.c_uint32, _P, _P, C.c_int, _P, C.c_size_t, _P]),
+    "vpz_decode_files_s16": (C.c_int64, [_P, C.c_uint32, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "vpz_decode_excerpts": (C.c_int64, [_P, C.c_uint32, _P, _P, C.c_uint32, _P, _P, _P, C.c_int, _P, C.c_size_t, _P, _P]),
 }
 

@@ -445,23 +445,24 @@ class VorbisReader:
         return C.c_void_p(self.lib.vpz_reader_setup(self._h))
 
 
-def decode_files(ctx, files, clip=True, dst=None):
-    """Bulk decode of whole container images in ONE GPU batch (vpz_decode_files).
+def decode_files(ctx, files, clip=True, dst=None, s16=False):
+    """Bulk decode of whole container images in ONE GPU batch (vpz_decode_files / vpz_decode_files_s16).
 
-    files: list of bytes / uint8 arrays.  Returns (pcm float32 1-D: file after file, interleaved),
-    per-file samples-per-channel counts.  dst may be a preallocated (pinned) float32 array.
+    files: list of bytes / uint8 arrays.  Returns (pcm 1-D: file after file, interleaved; float32, or
+    int16 with s16=True: the reference tests' (int)(x * 32768f) rule applied on the GPU), per-file
+    samples-per-channel counts.  dst may be a preallocated (pinned) array of the output type.
     """
     keep = [_u8(f) for f in files]
     n = len(keep)
     ptrs = (C.c_void_p * n)(*[k[1] for k in keep])
     lens = (C.c_size_t * n)(*[k[2] for k in keep])
     counts = np.zeros(n, np.int64)
+    fn = ctx.lib.vpz_decode_files_s16 if s16 else ctx.lib.vpz_decode_files
     if dst is None:
         # sizes are only known after the headers are parsed: first pass without output
-        total = ctx.check(ctx.lib.vpz_decode_files(ctx._h, n, ptrs, lens, int(bool(clip)), None, 0, counts.ctypes.data))
-        dst = np.zeros(total, np.float32)
-    total = ctx.check(ctx.lib.vpz_decode_files(ctx._h, n, ptrs, lens, int(bool(clip)), dst.ctypes.data, dst.size,
-                                               counts.ctypes.data))
+        total = ctx.check(fn(ctx._h, n, ptrs, lens, int(bool(clip)), None, 0, counts.ctypes.data))
+        dst = np.zeros(total, np.int16 if s16 else np.float32)
+    total = ctx.check(fn(ctx._h, n, ptrs, lens, int(bool(clip)), dst.ctypes.data, dst.size, counts.ctypes.data))
     return dst[:total], counts
 
 

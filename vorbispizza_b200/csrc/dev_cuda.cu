@@ -39,9 +39,10 @@ __global__ void __launch_bounds__(128, 1) vpz_k3_imdct_ola(K3Params P, int ncb) 
 }
 
 // block sizes 256 / 2048, mono / stereo: one CTA per SM, up to 12 independent 64-thread workers
+template <bool OUT16>
 __global__ void __launch_bounds__(K3_THREADS_PER_CH * K3S_MAX_GROUPS, 1) vpz_k3_streams(K3Params P) {
   extern __shared__ float k3_smem[];
-  k3s_cta(P, k3_smem);
+  k3s_cta<OUT16>(P, k3_smem);
 }
 
 namespace vpz {
@@ -99,7 +100,8 @@ int init(int device, std::string& err) {
   cudaFuncSetAttribute(vpz_k1b_spectrum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
   cudaFuncSetAttribute(vpz_k1b_spectrum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
   cudaFuncSetAttribute(vpz_k3_imdct_ola, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
-  cudaFuncSetAttribute(vpz_k3_streams, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  cudaFuncSetAttribute(vpz_k3_streams<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  cudaFuncSetAttribute(vpz_k3_streams<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute", err);
   return VPZ_OK;
@@ -268,7 +270,10 @@ int launch_k3_streams(const K3Params& p, Stream* s, std::string& err) {
   cudaError_t e0 = cudaMemsetAsync(p.counter, 0, 4, s->s);
   if (e0 != cudaSuccess) return fail(e0, "cudaMemsetAsync(counter)", err);
   unsigned grid = (unsigned)std::min<size_t>((p.n_items + groups - 1) / groups, (size_t)g_sm_count);
-  vpz_k3_streams<<<grid, groups * K3_THREADS_PER_CH, smem_bytes, s->s>>>(p);
+  if (p.out16)
+    vpz_k3_streams<true><<<grid, groups * K3_THREADS_PER_CH, smem_bytes, s->s>>>(p);
+  else
+    vpz_k3_streams<false><<<grid, groups * K3_THREADS_PER_CH, smem_bytes, s->s>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k3_streams", err);
 }

@@ -570,7 +570,7 @@ int batch_upload(vpz_batch* b) {
   return VPZ_OK;
 }
 
-int batch_decode(vpz_batch* b, int clip) {
+int batch_decode(vpz_batch* b, int clip, int out16) {
   vpz_ctx* ctx = b->ctx;
   std::string& err = ctx->last_error;
   dev::Stream* st = ctx->stream;
@@ -650,8 +650,12 @@ int batch_decode(vpz_batch* b, int clip) {
     p.counter = ctx->d_counter + 1;
     p.clip = clip ? 1 : 0;
     p.dbg_imdct = b->dbg_imdct;
+    p.out16 = out16 ? 1 : 0;
     if (fast && b->max_channels <= 2) {
       if ((rc = dev::launch_k3_streams(p, st, err))) return rc;
+    } else if (out16) {
+      err = "16-bit output is only on the 256/2048 mono/stereo IMDCT path";
+      return VPZ_E_UNSUPPORTED;
     } else {
       int ncb = std::min(2, b->max_channels);
       // descriptors (K3_DESC_FLOATS) + per channel slot the Stockham buffers and the three D half-slots

@@ -211,6 +211,6 @@ int batch_commit(vpz_batch* b, RunPlan* const* plans, size_t n, ThreadPool* pool
 uint32_t pick_ola_chunk(const vpz_ctx* ctx, uint64_t total_packets);
 extern double g_trace_ms[4];   // VPZ_TRACE: host milliseconds inside batch_upload / batch_decode (engine.cpp)
 int batch_upload(vpz_batch* b);
-int batch_decode(vpz_batch* b, int clip);
+int batch_decode(vpz_batch* b, int clip, int out16 = 0);   // out16: 16-bit PCM (fast IMDCT kernel only)
 int batch_fetch_clip(vpz_batch* b);
 }  // namespace vpz

@@ -35,7 +35,8 @@ struct K3Params {
   const VpzPktRes* res;            // exec masks from K1 (NULL: every channel executes)
   const VpzOlaItem* items;
   const uint32_t* const* setups;
-  float* pcm;
+  float* pcm;                      // interleaved output; holds int16 elements at the same element offsets when out16 is set
+  int out16;                       // 1: 16-bit PCM by the reference tests' rule (AssetTest.cs:131-132); fast kernel only
   uint32_t* clip_first;            // per packet: smallest clipped sample index (init 0xffffffff), may be NULL
   uint32_t n_items;
   uint32_t* counter;               // work-stealing cursor over items (zeroed before each launch)

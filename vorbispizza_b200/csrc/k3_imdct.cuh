@@ -321,11 +321,38 @@ VPZ_DEV int k3_next_break(int M, int start, int a, int b) {  // first breakpoint
   return b;
 }
 
-template <int NCUR, bool CLIP>
+// 16-bit PCM as the reference's own tests derive it from the float output (AssetTest.cs:131-132):
+// v = (int)(x * 32768f), i.e. the rounded fp32 product truncated toward zero, clamped to [-32768, 32767]
+VPZ_DEV int k3_s16(float x) {
+#ifndef VPZ_EMU
+  int v = __float2int_rz(__fmul_rn(x, 32768.f));
+#else
+  int v = (int)__fmul_rn(x, 32768.f);
+#endif
+  return v < -32768 ? -32768 : (v > 32767 ? 32767 : v);
+}
+// store sample `idx` (element index into the interleaved output) as fp32 or s16
+template <bool OUT16>
+VPZ_DEV void k3_put(float* outp, size_t idx, float v) {
+  if (OUT16) reinterpret_cast<int16_t*>(outp)[idx] = (int16_t)k3_s16(v); else outp[idx] = v;
+}
+template <bool OUT16>
+VPZ_DEV void k3_put2(float* outp, size_t idx, float a, float b) {   // idx even, base suitably aligned
+  if (OUT16) {
+    const uint32_t w = ((uint32_t)k3_s16(a) & 0xffffu) | ((uint32_t)k3_s16(b) << 16);
+    *reinterpret_cast<uint32_t*>(reinterpret_cast<int16_t*>(outp) + idx) = w;
+  } else {
+    *reinterpret_cast<float2*>(outp + idx) = float2{a, b};
+  }
+}
+
+template <int NCUR, bool CLIP, bool OUT16 = false>
 VPZ_DEV bool k3_emit(const float* Dc_hm, const float* Dc_lo, const float* Dp_lo, int per_ch, int M, int prevM, int ls,
                      int count, int prev_rs, int L, const float* w, float* outp, int C, int tid, int nthreads) {
   bool clipped = false;
-  const bool pair_ok = NCUR == 2 && C == 2 && (reinterpret_cast<uintptr_t>(outp) & 7u) == 0;
+  // outp is the float-typed base of the packet's samples; for s16 output the same ELEMENT offsets apply
+  // to an int16 buffer, so the byte address is base + 2 * element (the caller passes base accordingly)
+  const bool pair_ok = NCUR == 2 && C == 2 && (reinterpret_cast<uintptr_t>(outp) & (OUT16 ? 3u : 7u)) == 0;
   int a = 0;
   while (a < count) {
     int b = k3_next_break(M, ls, a, count);
@@ -372,23 +399,22 @@ VPZ_DEV bool k3_emit(const float* Dc_hm, const float* Dc_lo, const float* Dp_lo,
         v[cg] = x;
         u[cg] = y;
       }
-      float* o = outp + (size_t)j * C;
-      float* o2 = outp + (size_t)j2 * C;
+      const size_t o = (size_t)j * C, o2 = (size_t)j2 * C;
       if (NCUR == 2) {
         if (pair_ok) {
-          *reinterpret_cast<float2*>(o) = float2{v[0], v[NCUR - 1]};
-          if (two) *reinterpret_cast<float2*>(o2) = float2{u[0], u[NCUR - 1]};
+          k3_put2<OUT16>(outp, o, v[0], v[NCUR - 1]);
+          if (two) k3_put2<OUT16>(outp, o2, u[0], u[NCUR - 1]);
         } else {
-          o[0] = v[0];
-          o[1] = v[NCUR - 1];
+          k3_put<OUT16>(outp, o, v[0]);
+          k3_put<OUT16>(outp, o + 1, v[NCUR - 1]);
           if (two) {
-            o2[0] = u[0];
-            o2[1] = u[NCUR - 1];
+            k3_put<OUT16>(outp, o2, u[0]);
+            k3_put<OUT16>(outp, o2 + 1, u[NCUR - 1]);
           }
         }
       } else {
-        o[0] = v[0];
-        if (two) o2[0] = u[0];
+        k3_put<OUT16>(outp, o, v[0]);
+        if (two) k3_put<OUT16>(outp, o2, u[0]);
       }
     }
     a = b;

@@ -45,11 +45,11 @@ VPZ_DEV void k3s_cp_wait() {}
 //   out[j]        = D[512 + j] * w[j]        + (-Dp[511 - j]) * w[1023 - j]
 //   out[1023 - j] = (-D[512 + j]) * w[1023 - j] + (-Dp[511 - j]) * w[j]
 // with the rounding order of OverlapBuffers (two rounded products, one rounded sum).
-template <int NC, bool CLIP>
+template <int NC, bool CLIP, bool OUT16>
 VPZ_DEV bool k3s_emit_long_long(const float* hi0 /* D[512..] of channel 0 */, const float* plo0 /* previous D[0..512) */,
                                 const float* ws, float* outp, int t64) {
   bool clipped = false;
-  const bool pair_ok = NC == 2 && (reinterpret_cast<uintptr_t>(outp) & 7u) == 0;
+  const bool pair_ok = NC == 2 && (reinterpret_cast<uintptr_t>(outp) & (OUT16 ? 3u : 7u)) == 0;
 #pragma unroll 4
   for (int r = 0; r < 8; r++) {
     const int j = t64 + 64 * r;
@@ -73,23 +73,24 @@ VPZ_DEV bool k3s_emit_long_long(const float* hi0 /* D[512..] of channel 0 */, co
     }
     if (NC == 2) {
       if (pair_ok) {
-        *reinterpret_cast<float2*>(outp + 2 * j) = float2{lo[0], lo[NC - 1]};
-        *reinterpret_cast<float2*>(outp + 2 * (1023 - j)) = float2{hi[0], hi[NC - 1]};
+        k3_put2<OUT16>(outp, (size_t)(2 * j), lo[0], lo[NC - 1]);
+        k3_put2<OUT16>(outp, (size_t)(2 * (1023 - j)), hi[0], hi[NC - 1]);
       } else {
-        outp[2 * j] = lo[0];
-        outp[2 * j + 1] = lo[NC - 1];
-        outp[2 * (1023 - j)] = hi[0];
-        outp[2 * (1023 - j) + 1] = hi[NC - 1];
+        k3_put<OUT16>(outp, (size_t)(2 * j), lo[0]);
+        k3_put<OUT16>(outp, (size_t)(2 * j + 1), lo[NC - 1]);
+        k3_put<OUT16>(outp, (size_t)(2 * (1023 - j)), hi[0]);
+        k3_put<OUT16>(outp, (size_t)(2 * (1023 - j) + 1), hi[NC - 1]);
       }
     } else {
-      outp[j] = lo[0];
-      outp[1023 - j] = hi[0];
+      k3_put<OUT16>(outp, (size_t)j, lo[0]);
+      k3_put<OUT16>(outp, (size_t)(1023 - j), hi[0]);
     }
   }
   return clipped;
 }
 
-// one work item, C = 1 or 2 channels, by one 64-thread group
+// one work item, C = 1 or 2 channels, by one 64-thread group.  OUT16: 16-bit PCM (k3_s16) instead of fp32
+template <bool OUT16>
 VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs, float* gbase, int grp, int t64) {
   const VpzOlaItem it = item;  // the item lives in global memory: read it once
   const uint32_t* blob = P.setups[it.setup_slot];
@@ -188,27 +189,31 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
         const int ls = pk.left_start;
         const int count = (int)pk.right_start - ls;
         const int L = prev_re - prev_rs;             // StreamDecoder.cs:654
-        float* outp = P.pcm + it.out_base + (size_t)pk.out_off * C;
+        // element offset of the packet's first sample; an s16 element is 2 bytes, so the float-typed base
+        // advances by half the element offset (out_base and out_off * C are element counts)
+        const size_t eoff = (size_t)it.out_base + (size_t)pk.out_off * C;
+        float* outp = OUT16 ? reinterpret_cast<float*>(reinterpret_cast<int16_t*>(P.pcm) + eoff) : P.pcm + eoff;
         const float* Dp_lo = Dch + 512 + (parity ^ 1) * 512;
         bool clipped;
         const bool long_long = M == 1024 && prevM == 1024 && ls == 0 && count == 1024 && L == 1024 && prev_rs == 1024 &&
                                (pk.flags & VPZ_OLA_LEFT1);
+        const bool clip = P.clip != 0;   // ClipSamples applies before the 16-bit conversion, which clamps on its own
         if (long_long) {
           const float* ws = tabs + K3_TAB_SLOPE;
           if (C == 2)
-            clipped = P.clip ? k3s_emit_long_long<2, true>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_long_long<2, false>(Dch, Dp_lo, ws, outp, t64);
+            clipped = clip ? k3s_emit_long_long<2, true, OUT16>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_long_long<2, false, OUT16>(Dch, Dp_lo, ws, outp, t64);
           else
-            clipped = P.clip ? k3s_emit_long_long<1, true>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_long_long<1, false>(Dch, Dp_lo, ws, outp, t64);
+            clipped = clip ? k3s_emit_long_long<1, true, OUT16>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_long_long<1, false, OUT16>(Dch, Dp_lo, ws, outp, t64);
         } else {
           const float* w = (pk.flags & VPZ_OLA_LEFT1) ? slope1 : slope0;
           const float* Dc_hm = Dch - h;
           const float* Dc_lo = Dch + 512 + parity * 512;
           if (C == 2)
-            clipped = P.clip ? k3_emit<2, true>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH)
-                             : k3_emit<2, false>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH);
+            clipped = clip ? k3_emit<2, true, OUT16>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH)
+                           : k3_emit<2, false, OUT16>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH);
           else
-            clipped = P.clip ? k3_emit<1, true>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH)
-                             : k3_emit<1, false>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH);
+            clipped = clip ? k3_emit<1, true, OUT16>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH)
+                           : k3_emit<1, false, OUT16>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH);
         }
         // per packet: 0 when any sample was clamped (HasClipped), else stays 0xffffffff
         if (P.clip_first && clipped) atomicMin(P.clip_first + gp, 0u);
@@ -239,6 +244,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
 }
 
 // kernel body: `groups` = blockDim.x / 64 workers per CTA
+template <bool OUT16>
 VPZ_DEV void k3s_cta(const K3Params& P, float* smem) {
   const int tid = threadIdx.x;
   const int grp = tid / K3_THREADS_PER_CH, t64 = tid % K3_THREADS_PER_CH;
@@ -281,6 +287,6 @@ VPZ_DEV void k3s_cta(const K3Params& P, float* smem) {
     K3_GSYNC(grp);
     const uint32_t idx = *slot;
     if (idx >= P.n_items) break;
-    k3s_run_item(P, P.items[idx], smem, gbase, grp, t64);
+    k3s_run_item<OUT16>(P, P.items[idx], smem, gbase, grp, t64);
   }
 }

@@ -827,8 +827,11 @@ struct BulkJob {
 };
 }  // namespace
 
-int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, int clip,
-                         float* dst, size_t dst_floats, int64_t* sample_counts) {
+}  // extern "C"
+
+// out16: dst holds int16 elements (same element offsets), produced on the GPU by K3
+static int64_t decode_files_impl(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, int clip,
+                                 float* dst, size_t dst_floats, int64_t* sample_counts, int out16) {
   if (!ctx || (n && (!datas || !lens))) return VPZ_E_ARGUMENT;
   if (!ctx->pool) {
     unsigned t = ctx->host_threads > 0 ? (unsigned)ctx->host_threads
@@ -928,10 +931,14 @@ int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, 
     t1 = now(); t_commit += t1 - t0; t0 = t1;
     if (group_floats) {
       // 5. H2D + K1 + K3 on the compute stream, then the PCM of this group on the copy stream
-      if ((rc = batch_decode(b, clip))) break;
+      if ((rc = batch_decode(b, clip, out16))) break;
       dev::event_record(ctx->bulk_ready[slot], ctx->stream);
       dev::stream_wait_event(ctx->copy_stream, ctx->bulk_ready[slot]);
-      if ((rc = dev::d2h(dst + total, b->d_pcm.p, group_floats * 4, ctx->copy_stream, ctx->last_error))) break;
+      if (out16)
+        rc = dev::d2h(reinterpret_cast<int16_t*>(dst) + total, b->d_pcm.p, group_floats * 2, ctx->copy_stream, ctx->last_error);
+      else
+        rc = dev::d2h(dst + total, b->d_pcm.p, group_floats * 4, ctx->copy_stream, ctx->last_error);
+      if (rc) break;
     }
     dev::event_record(ctx->bulk_done[slot], ctx->copy_stream);
     t1 = now(); t_launch += t1 - t0; t0 = t1;
@@ -957,6 +964,18 @@ int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, 
             vpz::g_trace_ms[0], vpz::g_trace_ms[1], vpz::g_trace_ms[2]);
   }
   return rc ? rc : total;
+}
+
+extern "C" {
+
+int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, int clip,
+                         float* dst, size_t dst_floats, int64_t* sample_counts) {
+  return decode_files_impl(ctx, n, datas, lens, clip, dst, dst_floats, sample_counts, 0);
+}
+
+int64_t vpz_decode_files_s16(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, int clip,
+                             int16_t* dst, size_t dst_samples, int64_t* sample_counts) {
+  return decode_files_impl(ctx, n, datas, lens, clip, reinterpret_cast<float*>(dst), dst_samples, sample_counts, 1);
 }
 
 
