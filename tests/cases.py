@@ -157,7 +157,12 @@ def reader_parity_bytes(ctx, data, name, clip=True, lookahead=None, chunk=48000)
             assert r.has_clipped == s.has_clipped, name
             total += no
             calls += 1
-        assert r.total_samples == s.total_samples
+        ot = s.total_samples   # a negative value is the error the reference would throw (damaged granules)
+        try:
+            gt = r.total_samples
+        except VpzError as e:
+            gt = {N.VPZ_E_INVALID_DATA: -1, N.VPZ_E_ARGUMENT: -2, N.VPZ_E_SEEK_RANGE: -3}.get(e.code, e.code)
+        assert gt == ot, (name, gt, ot)
     return total, calls
 
 
