@@ -1091,13 +1091,26 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   }
   __syncwarp();
 
+  // Bins at and above the end of the coded residue range hold an exact +0 residue (zeroed buffer, and the
+  // inverse coupling of (+0, +0) is (+0, +0)), so their spectrum is +0 whatever the floor says: the floor
+  // is rendered and the gather runs only below res_end (a multiple of 16 bins); the rest is a zero fill.
+  // Typical streams code 69-92 % of the bins of a long block.
+  int res_end = 0;
+  if (have_res) {
+    const int span_end = g.begin + G.span;                          // in vector positions
+    const int bins = (g.rtype == 2 && C == 2) ? (span_end + 1) >> 1 : span_end;
+    res_end = (bins + 15) & ~15;
+    if (res_end > half) res_end = half;
+  }
+  if (DEBUG && P.dbg.residue) res_end = half;   // the debug dump wants every bin
+
   // ---- phase C: floor curve as one byte per bin: exact integer DDA, 16 bins per thread
   for (int ch = 0; ch < C; ch++) {
     if (!((own_mask >> ch) & 1u)) continue;
     const uint32_t* sg = sgbase + ch * 4 * 66;
     uint8_t* yb = ybuf + ch * half_max;
     const int nseg = (int)rec[K1_REC_HDR + ch * K1_SEG_WORDS];
-    k1b_render_floor(sg, nseg, yb, half, tid);
+    k1b_render_floor(sg, nseg, yb, res_end, tid);
   }
   __syncwarp();
 
@@ -1105,7 +1118,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   float* out = P.spec + pk.spec_off;
   const bool pair = g.rtype == 2 && C == 2;
   const bool coupled = C == 2 && mp->coupling_steps > 0;   // stereo: the only possible pair is (0,1) / (1,0)
-  for (int x0 = tid * 8; x0 < half; x0 += 32 * 8) {
+  for (int x0 = tid * 8; x0 < res_end; x0 += 32 * 8) {
     float r[16];   // pair: r[2i] = channel 0, r[2i+1] = channel 1 of bin x0+i; else r[i] = ch 0, r[8+i] = ch 1
 #pragma unroll
     for (int i = 0; i < 16; i++) r[i] = 0.f;
@@ -1169,6 +1182,17 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
       o1.w = __fmul_rn(c1[7], dbtab[yy.y >> 24]);
       reinterpret_cast<float4*>(out + half + x0)[0] = o0;
       reinterpret_cast<float4*>(out + half + x0)[1] = o1;
+    }
+  }
+  for (int x0 = res_end + tid * 8; x0 < half; x0 += 32 * 8) {   // no coded residue up here: +0
+    const float4 z = float4{0.f, 0.f, 0.f, 0.f};
+    if (own_mask & 1u) {
+      reinterpret_cast<float4*>(out + x0)[0] = z;
+      reinterpret_cast<float4*>(out + x0)[1] = z;
+    }
+    if (C == 2 && (own_mask & 2u)) {
+      reinterpret_cast<float4*>(out + half + x0)[0] = z;
+      reinterpret_cast<float4*>(out + half + x0)[1] = z;
     }
   }
   __syncwarp();
