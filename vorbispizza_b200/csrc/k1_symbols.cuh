@@ -855,39 +855,39 @@ VPZ_DEV void k1_uncouple(float& m, float& a) {
   m = p ? m : sm;
 }
 
-// Floor1.RenderLineMulti (Floor1.cs:372-397) for 16 consecutive bins of one channel per thread, one byte
-// per bin, exactly the reference's integer DDA:  y(x0 + k) = y0 + sy * (k * base + floor(k * rem / adx)).
-// sg: per segment {x0 | x1 << 16, y0 | |base| << 16, remainder step | sign << 31, M = ceil(2^32 / adx)}.
-// Divisions are multiply-high by M: exact when dividend * adx < 2^32, which holds for a running remainder
-// plus at most four steps (< 5 adx^2 <= 5 * 2^24); the DDA state in the middle of a segment (dividend up
-// to adx^2) may come out one too high and is fixed up.  Four bins that lie inside one segment are
-// produced WITHOUT a carried dependency (remainders e + j * rem, quotients by multiply-high); only a group
-// that contains a post falls back to bin-by-bin stepping.  The body is kept small on purpose: the warps of
-// an SM sit in different phases of different packets and K1b is sensitive to instruction-cache misses.
+// Floor1.RenderLineMulti (Floor1.cs:372-397), one byte per bin, exactly the reference's integer DDA:
+//   y(x0 + k) = y0 + sy * (k * base + floor(k * rem / adx)).
+// The curve is cut into PIECES of at most 16 bins that never cross a post: piece p of a channel belongs
+// to the segment whose piece prefix (phase A) is the largest one <= p.  Every lane renders whole pieces,
+// so no lane ever switches segments: the lanes of a warp stay convergent, and four bins at a time come
+// from the remainder at the start of the group without a carried dependency (remainders e + j * rem,
+// quotients by multiply-high with M = ceil(2^32 / adx): exact while dividend * adx < 2^32, i.e. for
+// e + 4 rem < 5 adx <= 5 * 2^12; the state at the start of a piece, dividend up to adx^2, may come out
+// one too high and is fixed up).
+// sg: per segment {x0 | x1 << 16, y0 | |base| << 16, rem | piece prefix << 16 | sign << 31, M}.
 VPZ_DEV uint32_t k1b_ybyte(int y) { return (uint32_t)(y < 0 ? 0 : (y > 255 ? 255 : y)); }   // the reference reads the table unchecked (quirk Q2)
 #ifndef VPZ_EMU
-#define K1B_PACK4(a, b, c, d) __byte_perm(__byte_perm(a, b, 0x3240), __byte_perm(c, d, 0x3240), 0x5410)
 #define K1B_MULHI(a, b) __umulhi(a, b)
 #else
-#define K1B_PACK4(a, b, c, d) ((a) | ((b) << 8) | ((c) << 16) | ((d) << 24))
 #define K1B_MULHI(a, b) ((uint32_t)(((uint64_t)(a) * (uint64_t)(b)) >> 32))
 #endif
-VPZ_DEV void k1b_render_floor(const uint32_t* sg, int nseg, uint8_t* yb, int half, int tid) {
-  for (int xb = tid * 16; xb < half; xb += 32 * 16) {   // half is a multiple of 16 (host-checked)
-    int lo = 0, hi = nseg;                                   // x0[lo] <= xb < x0[hi]
+VPZ_DEV void k1b_render_floor(const uint32_t* sg, int nseg, int npieces, uint8_t* yb, int x_end, int tid) {
+  for (int p = tid; p < npieces; p += 32) {
+    int lo = 0, hi = nseg;                                   // prefix[lo] <= p < prefix[hi]
     while (hi - lo > 1) {
       const int mid = (lo + hi) >> 1;
-      if ((int)(sg[4 * mid] & 0xffffu) <= xb) lo = mid; else hi = mid;
+      if ((int)((sg[4 * mid + 2] >> 16) & 0x7fffu) <= p) lo = mid; else hi = mid;
     }
-    int si = lo;
-    uint4 w = *reinterpret_cast<const uint4*>(sg + 4 * si);
-    int adx = (int)(w.x >> 16) - (int)(w.x & 0xffffu);
-    int x1 = si + 1 < nseg ? (int)(w.x >> 16) : 0x7fffffff;   // the last segment never hands over
-    int rem = (int)(w.z & 0x7fffffffu), sy = (w.z >> 31) ? -1 : 1;
-    int ystep = sy * (int)(w.y >> 16);
-    uint32_t magic = w.w;
-    // state of the DDA after k = xb - x0 steps
-    const int k = xb - (int)(w.x & 0xffffu);
+    const uint4 w = *reinterpret_cast<const uint4*>(sg + 4 * lo);
+    const int x0 = (int)(w.x & 0xffffu), x1 = (int)(w.x >> 16);
+    const int adx = x1 - x0;
+    const int rem = (int)(w.z & 0xffffu), sy = (w.z >> 31) ? -1 : 1;
+    const int ystep = sy * (int)(w.y >> 16);
+    const uint32_t magic = w.w;
+    const int k = 16 * (p - (int)((w.z >> 16) & 0x7fffu));   // steps into the segment
+    const int xs = x0 + k;
+    int len = (x1 < x_end ? x1 : x_end) - xs;                // bins of this piece
+    len = len > 16 ? 16 : len;
     const int t = k * rem;
     int q = (int)K1B_MULHI((uint32_t)t, magic);
     int err = t - q * adx;
@@ -896,46 +896,20 @@ VPZ_DEV void k1b_render_floor(const uint32_t* sg, int nseg, uint8_t* yb, int hal
       err += adx;
     }
     int y = (int)(short)(w.y & 0xffffu) + k * ystep + sy * q;
-    uint32_t* yout = reinterpret_cast<uint32_t*>(yb + xb);
-    int x = xb;
+    uint8_t* out = yb + xs;
 #pragma unroll 1
-    for (int jw = 0; jw < 4; jw++, x += 4) {
-      uint32_t word;
-      if (x + 4 <= x1) {
-        // the four bins and the state after them, each from the remainder at the start of the group
-        const int n1 = err + rem, n2 = n1 + rem, n3 = n2 + rem, n4 = n3 + rem;
-        const int q1 = (int)K1B_MULHI((uint32_t)n1, magic), q2 = (int)K1B_MULHI((uint32_t)n2, magic);
-        const int q3 = (int)K1B_MULHI((uint32_t)n3, magic), q4 = (int)K1B_MULHI((uint32_t)n4, magic);
-        const int y1 = y + ystep + sy * q1, y2 = y + 2 * ystep + sy * q2, y3 = y + 3 * ystep + sy * q3;
-        word = K1B_PACK4(k1b_ybyte(y), k1b_ybyte(y1), k1b_ybyte(y2), k1b_ybyte(y3));
-        y += 4 * ystep + sy * q4;
-        err = n4 - q4 * adx;
-      } else {
-        word = 0;
-#pragma unroll 1
-        for (int j = 0; j < 4; j++) {
-          if (x + j >= x1) {   // next segment starts exactly at its first post
-            si++;
-            w = *reinterpret_cast<const uint4*>(sg + 4 * si);
-            adx = (int)(w.x >> 16) - (int)(w.x & 0xffffu);
-            x1 = si + 1 < nseg ? (int)(w.x >> 16) : 0x7fffffff;
-            rem = (int)(w.z & 0x7fffffffu);
-            sy = (w.z >> 31) ? -1 : 1;
-            ystep = sy * (int)(w.y >> 16);
-            magic = w.w;
-            err = 0;
-            y = (int)(short)(w.y & 0xffffu);
-          }
-          word |= k1b_ybyte(y) << (8 * j);
-          err += rem;
-          y += ystep;
-          if (err >= adx) {
-            err -= adx;
-            y += sy;
-          }
-        }
-      }
-      yout[jw] = word;
+    for (int g = 0; g < len; g += 4, out += 4) {
+      // four bins and the state after them, each from the remainder at the start of the group
+      const int n1 = err + rem, n2 = n1 + rem, n3 = n2 + rem, n4 = n3 + rem;
+      const int q1 = (int)K1B_MULHI((uint32_t)n1, magic), q2 = (int)K1B_MULHI((uint32_t)n2, magic);
+      const int q3 = (int)K1B_MULHI((uint32_t)n3, magic), q4 = (int)K1B_MULHI((uint32_t)n4, magic);
+      const int left = len - g;
+      out[0] = (uint8_t)k1b_ybyte(y);
+      if (left > 1) out[1] = (uint8_t)k1b_ybyte(y + ystep + sy * q1);
+      if (left > 2) out[2] = (uint8_t)k1b_ybyte(y + 2 * ystep + sy * q2);
+      if (left > 3) out[3] = (uint8_t)k1b_ybyte(y + 3 * ystep + sy * q3);
+      y += 4 * ystep + sy * q4;
+      err = n4 - q4 * adx;
     }
   }
 }
@@ -1003,24 +977,60 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   G.span = g.part_count * g.psize;
   const bool have_res = g.part_count > 0 && g.any && G.n_ent > 0;
 
-  // ---- phase A: floor segments of every channel with energy ------------------------------------
+  // Bins at and above the end of the coded residue range hold an exact +0 residue (zeroed buffer, and the
+  // inverse coupling of (+0, +0) is (+0, +0)), so their spectrum is +0 whatever the floor says: the floor
+  // is rendered and the gather runs only below res_end (a multiple of 16 bins); the rest is a zero fill.
+  // Typical streams code 69-92 % of the bins of a long block.
+  int res_end = 0;
+  if (have_res) {
+    const int span_end = g.begin + G.span;                          // in vector positions
+    const int bins = (g.rtype == 2 && C == 2) ? (span_end + 1) >> 1 : span_end;
+    res_end = (bins + 15) & ~15;
+    if (res_end > half) res_end = half;
+  }
+  if (DEBUG && P.dbg.residue) res_end = half;   // the debug dump wants every bin
+
+  // ---- phase A: floor segments of every channel with energy, and their pieces of <= 16 bins -------
+  int npieces0 = 0, npieces1 = 0;   // per channel (the gather path has at most two)
   for (int ch = 0; ch < C; ch++) {
     if (!((own_mask >> ch) & 1u)) continue;
     const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
     uint32_t* sg = sgbase + ch * 4 * 66;
     const int nseg = (int)seg[0];
-    for (int s = tid; s < nseg; s += 32) {
-      const uint32_t p0 = seg[1 + s], p1 = seg[2 + s];
-      const int x0 = (int)(p0 & 0xffffu), y0 = (int)(short)(p0 >> 16);
-      const int x1 = (int)(p1 & 0xffffu), y1 = (int)(short)(p1 >> 16);
-      const int dy = y1 - y0, adx = x1 - x0;
-      const int ady = dy < 0 ? -dy : dy;
-      const int base = adx > 0 ? ady / adx : 0;
-      sg[4 * s] = (uint32_t)x0 | ((uint32_t)x1 << 16);
-      sg[4 * s + 1] = (uint32_t)(y0 & 0xffff) | ((uint32_t)base << 16);          // |base| of the DDA
-      sg[4 * s + 2] = (uint32_t)(ady - base * adx) | (dy < 0 ? 0x80000000u : 0u); // remainder step, sign
-      sg[4 * s + 3] = adx > 1 ? 0xffffffffu / (uint32_t)adx + 1u : 0u;   // ceil(2^32 / adx); adx = 1 has no remainder steps
+    int carry = 0;
+    for (int s0 = 0; s0 < nseg; s0 += 32) {   // uniform trip count: every lane takes part in the scan
+      const int s = s0 + tid;
+      int np = 0;
+      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+      if (s < nseg) {
+        const uint32_t p0 = seg[1 + s], p1 = seg[2 + s];
+        const int x0 = (int)(p0 & 0xffffu), y0 = (int)(short)(p0 >> 16);
+        const int x1 = (int)(p1 & 0xffffu), y1 = (int)(short)(p1 >> 16);
+        const int dy = y1 - y0, adx = x1 - x0;
+        const int ady = dy < 0 ? -dy : dy;
+        const int base = adx > 0 ? ady / adx : 0;
+        const int xe = x1 < res_end ? x1 : res_end;
+        np = xe > x0 ? (xe - x0 + 15) >> 4 : 0;
+        w0 = (uint32_t)x0 | ((uint32_t)x1 << 16);
+        w1 = (uint32_t)(y0 & 0xffff) | ((uint32_t)base << 16);          // |base| of the DDA
+        w2 = (uint32_t)(ady - base * adx) | (dy < 0 ? 0x80000000u : 0u); // remainder step (< adx <= 4096), sign
+        w3 = adx > 1 ? 0xffffffffu / (uint32_t)adx + 1u : 0u;            // ceil(2^32 / adx); adx = 1 has no remainder steps
+      }
+      int incl = np;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+      }
+      if (s < nseg) {
+        sg[4 * s] = w0;
+        sg[4 * s + 1] = w1;
+        sg[4 * s + 2] = w2 | ((uint32_t)(carry + incl - np) << 16);     // pieces before this segment
+        sg[4 * s + 3] = w3;
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
     }
+    if (ch == 0) npieces0 = carry; else npieces1 = carry;
   }
 
   // ---- phase B: per unit and stage, how many entries it holds -> first entry (all stages at once) ----
@@ -1091,26 +1101,13 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   }
   __syncwarp();
 
-  // Bins at and above the end of the coded residue range hold an exact +0 residue (zeroed buffer, and the
-  // inverse coupling of (+0, +0) is (+0, +0)), so their spectrum is +0 whatever the floor says: the floor
-  // is rendered and the gather runs only below res_end (a multiple of 16 bins); the rest is a zero fill.
-  // Typical streams code 69-92 % of the bins of a long block.
-  int res_end = 0;
-  if (have_res) {
-    const int span_end = g.begin + G.span;                          // in vector positions
-    const int bins = (g.rtype == 2 && C == 2) ? (span_end + 1) >> 1 : span_end;
-    res_end = (bins + 15) & ~15;
-    if (res_end > half) res_end = half;
-  }
-  if (DEBUG && P.dbg.residue) res_end = half;   // the debug dump wants every bin
-
-  // ---- phase C: floor curve as one byte per bin: exact integer DDA, 16 bins per thread
+  // ---- phase C: floor curve as one byte per bin: exact integer DDA, a lane renders pieces of <= 16 bins
   for (int ch = 0; ch < C; ch++) {
     if (!((own_mask >> ch) & 1u)) continue;
     const uint32_t* sg = sgbase + ch * 4 * 66;
     uint8_t* yb = ybuf + ch * half_max;
     const int nseg = (int)rec[K1_REC_HDR + ch * K1_SEG_WORDS];
-    k1b_render_floor(sg, nseg, yb, res_end, tid);
+    k1b_render_floor(sg, nseg, ch == 0 ? npieces0 : npieces1, yb, res_end, tid);
   }
   __syncwarp();
 
