@@ -897,19 +897,25 @@ VPZ_DEV void k1b_render_floor(const uint32_t* sg, int nseg, int npieces, uint8_t
     }
     int y = (int)(short)(w.y & 0xffffu) + k * ystep + sy * q;
     uint8_t* out = yb + xs;
+    int left = len;
 #pragma unroll 1
-    for (int g = 0; g < len; g += 4, out += 4) {
+    for (; left >= 4; left -= 4, out += 4) {
       // four bins and the state after them, each from the remainder at the start of the group
       const int n1 = err + rem, n2 = n1 + rem, n3 = n2 + rem, n4 = n3 + rem;
       const int q1 = (int)K1B_MULHI((uint32_t)n1, magic), q2 = (int)K1B_MULHI((uint32_t)n2, magic);
       const int q3 = (int)K1B_MULHI((uint32_t)n3, magic), q4 = (int)K1B_MULHI((uint32_t)n4, magic);
-      const int left = len - g;
       out[0] = (uint8_t)k1b_ybyte(y);
-      if (left > 1) out[1] = (uint8_t)k1b_ybyte(y + ystep + sy * q1);
-      if (left > 2) out[2] = (uint8_t)k1b_ybyte(y + 2 * ystep + sy * q2);
-      if (left > 3) out[3] = (uint8_t)k1b_ybyte(y + 3 * ystep + sy * q3);
+      out[1] = (uint8_t)k1b_ybyte(y + ystep + sy * q1);
+      out[2] = (uint8_t)k1b_ybyte(y + 2 * ystep + sy * q2);
+      out[3] = (uint8_t)k1b_ybyte(y + 3 * ystep + sy * q3);
       y += 4 * ystep + sy * q4;
       err = n4 - q4 * adx;
+    }
+    if (left > 0) {   // the last 1..3 bins of the piece
+      const int n1 = err + rem, n2 = n1 + rem;
+      out[0] = (uint8_t)k1b_ybyte(y);
+      if (left > 1) out[1] = (uint8_t)k1b_ybyte(y + ystep + sy * (int)K1B_MULHI((uint32_t)n1, magic));
+      if (left > 2) out[2] = (uint8_t)k1b_ybyte(y + 2 * ystep + sy * (int)K1B_MULHI((uint32_t)n2, magic));
     }
   }
 }
