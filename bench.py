@@ -183,6 +183,8 @@ def run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
         for i in range(n_blocks):
             flags[s, i] = cur
             cur = (0 if u[i] < 1 / 16 else 1) if cur else (1 if u[i] < 1 / 4 else 0)
+    if args.all_long:
+        flags[:] = 1
     sizes = np.where(flags.reshape(-1) & 1, 1024, 128)
     total = int(sizes.sum()) * ch
     k = np.concatenate([np.tile(np.arange(m, dtype=np.float32), ch) for m in sizes])
@@ -220,7 +222,8 @@ def run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
             "ms_per_step": k3_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic spectra (seeded)",
             "config": {"workload": "config3: kernel-only IMDCT+window+OLA, 65,536 stereo blocks per GPU "
-                                   "(64 streams x 1,024 blocks, n=2048 long runs with n=256 short transitions)",
+                                   "(64 streams x 1,024 blocks, %s)" % ("all n=2048 (the all-long variant)" if args.all_long else
+                                                                         "n=2048 long runs with n=256 short transitions"),
                        "channel_samples_per_gpu": int(samples_rank), "short_block_fraction": float(1.0 - flags.mean()),
                        "l2": "inputs larger than L2: %.2f GB spectra + %.2f GB PCM per step vs 126 MB L2"
                              % (4.0 * samples_rank / 1e9, 4.0 * samples_rank / 1e9)},
@@ -310,6 +313,7 @@ def main():
                     help="config4 (default, the headline): 4,096 streams full decode; config3: kernel-only "
                          "IMDCT+window+OLA on 65,536 synthetic stereo blocks; config5: 16,384 random-access "
                          "excerpts (SeekTo + 4,096 samples) per GPU through vpz_decode_excerpts")
+    ap.add_argument("--all-long", action="store_true", help="config3 only: pure n=2048 blocks (no short transitions)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--l1-bits", type=int, default=0, help=argparse.SUPPRESS)  # tuning: first-level Huffman table width
@@ -476,7 +480,7 @@ def main():
         counts = np.zeros(n_streams, np.int64)
         # sizes: whole files emit the same samples as the two-run replicas minus the re-seeded packet
         e_total = ctx.check(lib.vpz_decode_files(ctx._h, n_streams, ptrs, lens, 1, None, 0, counts.ctypes.data))
-        dst, dst_p = pinned_array(lib, e_total)
+        dst, dst_p = pinned_array(lib, e_total)   # 8.2 GB of pinned host memory per rank
         for _ in range(2):
             ctx.check(lib.vpz_decode_files(ctx._h, n_streams, ptrs, lens, 1, dst.ctypes.data, dst.size,
                                            counts.ctypes.data))

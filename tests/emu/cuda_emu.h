@@ -1,7 +1,7 @@
 // cuda_emu.h -- TEST INFRASTRUCTURE ONLY.  A minimal CUDA execution-model emulator: every CUDA
 // thread of a block is an OS thread, __syncthreads()/__syncwarp() are barriers and warp shuffles
 // go through a per-warp exchange buffer.  It lets `pytest -m "not gpu"` run the UNMODIFIED kernel
-// bodies (k1_entropy.cuh, k3_imdct.cuh) and the host engine on a machine without a GPU.  It is
+// bodies (k1_symbols.cuh, k3_imdct.cuh, k3_streams.cuh) and the host engine on a machine without a GPU.  It is
 // never compiled into libvpz.so (the product has no CPU path); see tests/emu/README.md.
 #pragma once
 #include <math.h>

@@ -3,7 +3,7 @@
 with instruction counts and stall samples) with `nvdisasm -g` line info of the in-tree libvpz.so
 (row i of the ncu page == instruction i of the function).
 
-    python tools/ncu_by_line.py gpurun_out/prof.ncu-rep vpz_k1_entropyILb0 [top_n]
+    python tools/ncu_by_line.py gpurun_out/prof.ncu-rep vpz_k1b_spectrumILb0 [top_n]
 """
 import csv
 import io

@@ -38,27 +38,29 @@ VPZ_DEV void k3s_cp16(float* dst_smem, const float* src) { memcpy(dst_smem, src,
 VPZ_DEV void k3s_cp_wait() {}
 #endif
 
-// The common case in full: long block after long block, nothing trimmed (ls = 0, count = L = 1024,
-// previous RightStart = 1024).  Sample j < 512 reads +D[j + 512] of the current block and -Dp[511 - j] of
-// the previous one; its mirror image 1023 - j reads the SAME two values with the window pair swapped
-// (time-domain aliasing symmetry), so a thread produces both from one set of loads:
-//   out[j]        = D[512 + j] * w[j]        + (-Dp[511 - j]) * w[1023 - j]
-//   out[1023 - j] = (-D[512 + j]) * w[1023 - j] + (-Dp[511 - j]) * w[j]
+// The common cases in full: a block after a block of the same size, nothing trimmed (ls = 0,
+// count = L = M, previous RightStart = M; M = 1024 long after long, M = 128 short after short).
+// Sample j < M/2 reads +D[j + M/2] of the current block and -Dp[M/2 - 1 - j] of the previous one; its mirror
+// image M - 1 - j reads the SAME two values with the window pair swapped (time-domain aliasing
+// symmetry), so a thread produces both from one set of loads:
+//   out[j]         = D[M/2 + j] * w[j]            + (-Dp[M/2 - 1 - j]) * w[M - 1 - j]
+//   out[M - 1 - j] = (-D[M/2 + j]) * w[M - 1 - j] + (-Dp[M/2 - 1 - j]) * w[j]
 // with the rounding order of OverlapBuffers (two rounded products, one rounded sum).
-template <int NC, bool CLIP, bool OUT16>
-VPZ_DEV bool k3s_emit_long_long(const float* hi0 /* D[512..] of channel 0 */, const float* plo0 /* previous D[0..512) */,
+template <int NC, bool CLIP, bool OUT16, int M>
+VPZ_DEV bool k3s_emit_same_size(const float* hi0 /* D[M/2..] of channel 0 */, const float* plo0 /* previous D[0..M/2) */,
                                 const float* ws, float* outp, int t64) {
   bool clipped = false;
   const bool pair_ok = NC == 2 && (reinterpret_cast<uintptr_t>(outp) & (OUT16 ? 3u : 7u)) == 0;
+  constexpr int HALF = M / 2;
 #pragma unroll 4
-  for (int r = 0; r < 8; r++) {
+  for (int r = 0; r < HALF / 64; r++) {
     const int j = t64 + 64 * r;
-    const float w0 = ws[j], w1 = ws[1023 - j];
+    const float w0 = ws[j], w1 = ws[M - 1 - j];
     float lo[NC], hi[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
       const float a = hi0[c * K3S_CH_FLOATS + j];
-      const float b = -plo0[c * K3S_CH_FLOATS + 511 - j];
+      const float b = -plo0[c * K3S_CH_FLOATS + HALF - 1 - j];
       float x = __fadd_rn(__fmul_rn(a, w0), __fmul_rn(b, w1));
       float y = __fadd_rn(__fmul_rn(-a, w1), __fmul_rn(b, w0));
       if (CLIP) {  // Utils.ClipValue (Utils.cs:44-58)
@@ -74,16 +76,16 @@ VPZ_DEV bool k3s_emit_long_long(const float* hi0 /* D[512..] of channel 0 */, co
     if (NC == 2) {
       if (pair_ok) {
         k3_put2<OUT16>(outp, (size_t)(2 * j), lo[0], lo[NC - 1]);
-        k3_put2<OUT16>(outp, (size_t)(2 * (1023 - j)), hi[0], hi[NC - 1]);
+        k3_put2<OUT16>(outp, (size_t)(2 * (M - 1 - j)), hi[0], hi[NC - 1]);
       } else {
         k3_put<OUT16>(outp, (size_t)(2 * j), lo[0]);
         k3_put<OUT16>(outp, (size_t)(2 * j + 1), lo[NC - 1]);
-        k3_put<OUT16>(outp, (size_t)(2 * (1023 - j)), hi[0]);
-        k3_put<OUT16>(outp, (size_t)(2 * (1023 - j) + 1), hi[NC - 1]);
+        k3_put<OUT16>(outp, (size_t)(2 * (M - 1 - j)), hi[0]);
+        k3_put<OUT16>(outp, (size_t)(2 * (M - 1 - j) + 1), hi[NC - 1]);
       }
     } else {
       k3_put<OUT16>(outp, (size_t)j, lo[0]);
-      k3_put<OUT16>(outp, (size_t)(1023 - j), hi[0]);
+      k3_put<OUT16>(outp, (size_t)(M - 1 - j), hi[0]);
     }
   }
   return clipped;
@@ -138,7 +140,37 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
       const int h = M >> 1;
       const bool emit = !(pi == 0 && it.has_pre) && !(pk.flags & VPZ_OLA_NOOUT) && have_prev;
 
-      // ---- transform the channels one after the other into their D slots ---------------------------
+      // ---- transform the channels into their D slots -------------------------------------------------
+      if (!is_long) {
+        // short block: 8 threads per channel run its 64-point FFT, both channels at the same time; a
+        // channel without floor energy is cleared instead (Mapping.cs:185-194)
+        for (int c = 0; c < C; c++) {
+          if ((mask >> c) & 1u) continue;
+          float* chb = Dch + c * K3S_CH_FLOATS;
+          for (int i = t64; i < 64; i += K3_THREADS_PER_CH) {
+            chb[i] = 0.f;                              // D[64..128): high slot
+            chb[512 + parity * 512 + i] = 0.f;         // D[0..64): low slot of this parity
+          }
+        }
+        const int c = (t64 >> 3) < C ? (t64 >> 3) : 0;
+        float* chb = Dch + c * K3S_CH_FLOATS;
+        K3D D;
+        D.h = h;
+        D.hm = chb - h;
+        D.lo = chb + 512 + parity * 512;
+        const bool active = t64 < 8 * C && ((mask >> c) & 1u);
+        fft64_to_D(P.spec + pk.spec_off + (size_t)c * M, T + 80 * c, D, tw_s, w64_s, t64 & 7, active, grp);   // ends with a group barrier
+        if (P.dbg_imdct) {
+          for (int c2 = 0; c2 < C; c2++) {
+            K3D D2;
+            D2.h = h;
+            D2.hm = Dch + c2 * K3S_CH_FLOATS - h;
+            D2.lo = Dch + c2 * K3S_CH_FLOATS + 512 + parity * 512;
+            float* dy = P.dbg_imdct + 2 * (size_t)pk.spec_off + (size_t)c2 * 2 * M;
+            for (int i = t64; i < 2 * M; i += K3_THREADS_PER_CH) dy[i] = k3_y(D2, M, i);
+          }
+        }
+      } else
       for (int c = 0; c < C; c++) {
         float* chb = Dch + c * K3S_CH_FLOATS;
         K3D D;
@@ -153,7 +185,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
           for (int i = t64; i < M; i += K3_THREADS_PER_CH) *k3_dp(D, i) = 0.f;
           k3s_cp_wait();
           K3_GSYNC(grp);
-        } else if (is_long) {
+        } else {
           if (c == 1 && staged) {
             // channel 1's spectrum was copied into its own Hi / Lo[parity] slots after the previous
             // packet's output (made visible by the barrier that ended channel 0's transform)
@@ -169,8 +201,6 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
           if (c == 0) xr_valid = false;
           k3s_cp_wait();
           K3_GSYNC(grp);   // D complete, scratch reusable, staged channel-1 spectrum visible
-        } else {
-          fft64_to_D(X, T, D, tw_s, w64_s, t64, t64 < 8, grp);   // ends with a group barrier
         }
         if (P.dbg_imdct) {
           float* dy = P.dbg_imdct + 2 * (size_t)pk.spec_off + (size_t)c * 2 * M;
@@ -195,15 +225,20 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
         float* outp = OUT16 ? reinterpret_cast<float*>(reinterpret_cast<int16_t*>(P.pcm) + eoff) : P.pcm + eoff;
         const float* Dp_lo = Dch + 512 + (parity ^ 1) * 512;
         bool clipped;
-        const bool long_long = M == 1024 && prevM == 1024 && ls == 0 && count == 1024 && L == 1024 && prev_rs == 1024 &&
-                               (pk.flags & VPZ_OLA_LEFT1);
+        const bool same = prevM == M && ls == 0 && count == M && L == M && prev_rs == M;
         const bool clip = P.clip != 0;   // ClipSamples applies before the 16-bit conversion, which clamps on its own
-        if (long_long) {
+        if (same && M == 1024 && (pk.flags & VPZ_OLA_LEFT1)) {
           const float* ws = tabs + K3_TAB_SLOPE;
           if (C == 2)
-            clipped = clip ? k3s_emit_long_long<2, true, OUT16>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_long_long<2, false, OUT16>(Dch, Dp_lo, ws, outp, t64);
+            clipped = clip ? k3s_emit_same_size<2, true, OUT16, 1024>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_same_size<2, false, OUT16, 1024>(Dch, Dp_lo, ws, outp, t64);
           else
-            clipped = clip ? k3s_emit_long_long<1, true, OUT16>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_long_long<1, false, OUT16>(Dch, Dp_lo, ws, outp, t64);
+            clipped = clip ? k3s_emit_same_size<1, true, OUT16, 1024>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_same_size<1, false, OUT16, 1024>(Dch, Dp_lo, ws, outp, t64);
+        } else if (same && M == 128) {
+          const float* ws = tabs + K3S_TAB_S_SLOPE;
+          if (C == 2)
+            clipped = clip ? k3s_emit_same_size<2, true, OUT16, 128>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_same_size<2, false, OUT16, 128>(Dch, Dp_lo, ws, outp, t64);
+          else
+            clipped = clip ? k3s_emit_same_size<1, true, OUT16, 128>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_same_size<1, false, OUT16, 128>(Dch, Dp_lo, ws, outp, t64);
         } else {
           const float* w = (pk.flags & VPZ_OLA_LEFT1) ? slope1 : slope0;
           const float* Dc_hm = Dch - h;
