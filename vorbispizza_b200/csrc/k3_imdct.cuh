@@ -184,18 +184,24 @@ VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* ta
     v[r].y = T[K3_PLANE + t + 68 * r];
   }
   dft8(v);
+  // c[p] = T[p] * tw[p] gives D[2p] = Re c[p] and D[M-1-2p] = -Im c[p].  The neighbour of D[2p] in
+  // memory, D[2p+1] = D[M-1-2p'] with p' = 511 - p, belongs to the mirrored thread 63 - t (the other lane of
+  // k3_remap64's pairing, lane ^ 31) at index 7 - k3: one shuffle fetches it, and the pair leaves as one
+  // conflict-free 64-bit store instead of two stride-2 scalar stores.
+  float ny[8];
 #pragma unroll
   for (int k3 = 0; k3 < 8; k3++) {
-    int p = t + 64 * k3;
-    cpx c = cmul(v[k3], tw[p]);
-    // p < 256: D[2p] is in the low half and D[M-1-2p] in the high half; p >= 256: the other way round
-    if (k3 < 4) {
-      D.lo[2 * p] = c.x;
-      D.hm[M - 1 - 2 * p] = -c.y;
-    } else {
-      D.hm[2 * p] = c.x;
-      D.lo[M - 1 - 2 * p] = -c.y;
-    }
+    const cpx c = cmul(v[k3], tw[t + 64 * k3]);
+    v[k3].x = c.x;
+    ny[k3] = -c.y;
+  }
+#pragma unroll
+  for (int k3 = 0; k3 < 8; k3++) {
+    const int p = t + 64 * k3;
+    const float odd = __shfl_xor_sync(0xffffffffu, ny[7 - k3], 31);
+    // 2p < 512: both values lie in the low half, else in the high half
+    float* dst = (k3 < 4 ? D.lo : D.hm) + 2 * p;
+    *reinterpret_cast<float2*>(dst) = float2{v[k3].x, odd};
   }
 }
 
