@@ -140,8 +140,7 @@ VPZ_DEV void k3_load_x(const float* X, int t, float2* xr) {
   for (int q = 0; q < 8; q++) xr[q] = VPZ_LDG(reinterpret_cast<const float2*>(X) + (t + 64 * q));
 }
 
-VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* tab, int t, int grp) {
-  const int M = 1024;
+VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* tab, int t, int grp) {   // M = 1024
   const cpx* tw = tab + K3_TAB_TW;
   cpx v[8];
   // X[2n+1] = X[M-1-2n'] of the mirrored element n' = 511-n, held by the mirrored lane
