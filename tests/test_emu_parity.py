@@ -79,3 +79,20 @@ def test_excerpts_batch(emu_ctx):
 
 def test_decode_files_s16(emu_ctx):
     cases.decode_files_s16_parity(emu_ctx, ["1test"])
+
+
+def test_empty_inputs(emu_ctx):
+    """Empty batches are valid and produce nothing (no kernel launch, no error)."""
+    import numpy as np
+    from vorbispizza_b200 import Batch, decode_excerpts, decode_files
+    pcm, counts = decode_files(emu_ctx, [])
+    assert pcm.size == 0 and counts.size == 0
+    data = cases.load_file("1test")
+    pcm, offsets, got = decode_excerpts(emu_ctx, [data], np.zeros(0, np.uint32), np.zeros(0, np.int64), np.zeros(0, np.int32))
+    assert pcm.size == 0 and offsets.size == 0 and got.size == 0
+    # an excerpt of zero samples beside a normal one
+    pcm, offsets, got = decode_excerpts(emu_ctx, [data], [0, 0], [100, 5000], [0, 50])
+    assert pcm.size == 50 and list(got) == [0, 50] and list(offsets) == [0, 0]
+    with Batch(emu_ctx) as b:
+        b.decode(clip=True)
+        assert b.total_floats == 0
