@@ -335,6 +335,8 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         if world > 1:
+            # the one line rank 0 prints must be the JSON line: keep NCCL's version banner off stdout
+            os.environ["NCCL_DEBUG"] = os.environ.get("VPZ_NCCL_DEBUG", "WARN")
             dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
