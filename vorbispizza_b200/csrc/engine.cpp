@@ -78,7 +78,12 @@ static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
       const size_t U = (units + 31) & ~(size_t)31;
       const size_t half_max = (size_t)1 << (h->log2_size1 - 1);
       // k1b gather layout per warp: urec stages*U*2 + ybuf C*half_max/4 + sg C*4*66 (+ pad, multiple of 32)
-      s->k1g_words = (uint32_t)(((size_t)max_stages * U * 2 + (size_t)C * half_max / 4 + (size_t)C * 4 * 66 + 8 + 31) & ~(size_t)31);
+      // segments per channel <= posts of the largest floor (+ the flat tail): the segment table is sized for this setup
+      const VpzFloor1* fl = reinterpret_cast<const VpzFloor1*>(st.blob.data() + h->floors_off);
+      size_t max_posts = 2;
+      for (int i = 0; i < h->nfloors; i++) max_posts = std::max<size_t>(max_posts, fl[i].xcount);
+      s->k1g_seg_stride = (uint32_t)(4 * (max_posts + 1));
+      s->k1g_words = (uint32_t)(((size_t)max_stages * U * 2 + (size_t)C * half_max / 4 + (size_t)C * s->k1g_seg_stride + 8 + 31) & ~(size_t)31);
     }
     // K1_REC_HDR, K1_SEG_WORDS, classes; a multiple of 4 words so every record starts on a 16-byte boundary
     s->rec_words = (uint32_t)((4 + h->channels * 68 + (units + 3) / 4 + 1 + 3) & ~(size_t)3);
@@ -590,11 +595,12 @@ int batch_decode(vpz_batch* b, int clip, int out16) {
   b->launches = 0;
   dev::event_record(ctx->ev[0], st);
   bool fast = true, gather = true;
-  uint32_t k1w = 0, k1g = 0, k3f = 0;
+  uint32_t k1w = 0, k1g = 0, k3f = 0, k1seg = 0;
   for (vpz_setup* s : b->slots) {
     fast = fast && s->fast_sizes;
     gather = gather && s->gather_ok;
     k1g = std::max(k1g, s->k1g_words);
+    k1seg = std::max(k1seg, s->k1g_seg_stride);
     k1w = std::max(k1w, s->k1_words_per_warp);
     k3f = std::max(k3f, s->k3_floats_per_ch);
   }
@@ -611,6 +617,7 @@ int batch_decode(vpz_batch* b, int clip, int out16) {
     p.gather_ok = gather ? 1 : 0;
     if (gather) k1w = k1g;   // the gather path needs only its index tables
     p.smem_words_per_warp = k1w;
+    p.seg_stride = k1seg;
     p.rec = static_cast<uint32_t*>(b->d_rec.p);
     p.ent = static_cast<uint16_t*>(b->d_ent.p);
     p.order = static_cast<const uint32_t*>(b->d_order.p);

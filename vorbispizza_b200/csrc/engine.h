@@ -28,7 +28,8 @@ struct vpz_setup {
   uint32_t k1_words_per_warp = 0;   // shared memory K1b needs per warp
   uint32_t rec_words = 0;           // size of one packet's symbol record (K1a -> K1b)
   bool gather_ok = false;           // K1b gather path applies (mono/stereo, residue 1/2, dims divide the partition)
-  uint32_t k1g_words = 0;           // shared memory of the gather path per CTA
+  uint32_t k1g_words = 0;           // shared memory of the gather path per warp (words)
+  uint32_t k1g_seg_stride = 0;      // words of the floor segment table per channel (4 per post + flat tail)
   uint32_t k3_floats_per_ch = 0;    // shared memory K3 needs per channel (generic layout)
   bool fast_sizes = false;          // block sizes 256 / 2048
   bool synthetic = false;           // window/twiddle tables only (vpz_synth_create)

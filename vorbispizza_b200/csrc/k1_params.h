@@ -22,6 +22,7 @@ struct K1Params {
   uint32_t n_pkts;
   uint32_t* counter;             // work-stealing cursor (zeroed before each launch)
   uint32_t smem_words_per_warp;  // K1b
+  uint32_t seg_stride;           // K1b gather: words of the floor segment table per channel
   uint32_t* rec;                 // symbol records (K1a -> K1b), VpzPktIn.rec_off
   uint16_t* ent;                 // VQ entry indices (K1a -> K1b), VpzPktIn.ent_off
   const uint32_t* order;         // K1a: packet indices sorted by byte length (neighbouring lanes get like work)

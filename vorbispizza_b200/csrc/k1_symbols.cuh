@@ -764,7 +764,7 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
 // Inverse coupling, floor multiply and two 128-bit stores per channel follow.  The floor curve is
 // rendered beforehand by an exact integer DDA (RenderLineMulti, Floor1.cs:372-397), 16 bins per
 // thread, into one byte per bin of shared memory.
-//   per-warp words: urec[stages][U][2] | per channel ybuf[half_max/4] | sg[C][4*66]
+//   per-warp words: urec[stages][U][2] | per channel ybuf[half_max/4] | sg[C][P.seg_stride]
 // =============================================================================================
 
 struct K1Gather {
@@ -1001,7 +1001,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   for (int ch = 0; ch < C; ch++) {
     if (!((own_mask >> ch) & 1u)) continue;
     const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
-    uint32_t* sg = sgbase + ch * 4 * 66;
+    uint32_t* sg = sgbase + ch * P.seg_stride;
     const int nseg = (int)seg[0];
     int carry = 0;
     for (int s0 = 0; s0 < nseg; s0 += 32) {   // uniform trip count: every lane takes part in the scan
@@ -1110,7 +1110,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   // ---- phase C: floor curve as one byte per bin: exact integer DDA, a lane renders pieces of <= 16 bins
   for (int ch = 0; ch < C; ch++) {
     if (!((own_mask >> ch) & 1u)) continue;
-    const uint32_t* sg = sgbase + ch * 4 * 66;
+    const uint32_t* sg = sgbase + ch * P.seg_stride;
     uint8_t* yb = ybuf + ch * half_max;
     const int nseg = (int)rec[K1_REC_HDR + ch * K1_SEG_WORDS];
     k1b_render_floor(sg, nseg, ch == 0 ? npieces0 : npieces1, yb, res_end, tid);
