@@ -335,9 +335,19 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         if world > 1:
-            # the one line rank 0 prints must be the JSON line: keep NCCL's version banner off stdout
-            os.environ["NCCL_DEBUG"] = os.environ.get("VPZ_NCCL_DEBUG", "WARN")
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            # the one line rank 0 prints must be the JSON line: the "NCCL version" banner that the first
+            # communicator writes to stdout goes to stderr instead
+            sys.stdout.flush()
+            saved = os.dup(1)
+            os.dup2(2, 1)
+            try:
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+                dist.barrier()
+                torch.cuda.synchronize()
+            finally:
+                sys.stdout.flush()
+                os.dup2(saved, 1)
+                os.close(saved)
 
     def barrier():
         if dry:
