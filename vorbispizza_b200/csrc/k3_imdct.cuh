@@ -154,34 +154,26 @@ VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* ta
   dft8(v);
 #pragma unroll
   for (int k = 1; k < 8; k++) v[k] = cmul(v[k], tab[K3_TAB_W1 + (k - 1) * 64 + t]);
+  // transposes through shared memory with COMPLEX (8-byte) elements: layouts 72 k1 + r and
+  // k1 + 8 k2 + 66 r2 are conflict-free for 64-bit accesses (every half-warp touches 16 distinct
+  // 8-byte bank pairs) in the writing and in the reading pass
+  cpx* T2 = reinterpret_cast<cpx*>(T);
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    T[idx1(k, t)] = v[k].x;
-    T[K3_PLANE + idx1(k, t)] = v[k].y;
-  }
+  for (int k = 0; k < 8; k++) T2[72 * k + t] = v[k];
   K3_GSYNC(grp);
   const int k1 = t >> 3, r2 = t & 7;
 #pragma unroll
-  for (int q = 0; q < 8; q++) {
-    v[q].x = T[idx1(k1, r2 + 8 * q)];
-    v[q].y = T[K3_PLANE + idx1(k1, r2 + 8 * q)];
-  }
+  for (int q = 0; q < 8; q++) v[q] = T2[72 * k1 + r2 + 8 * q];
   K3_GSYNC(grp);  // the second transpose reuses T
   dft8(v);
 #pragma unroll
   for (int k = 1; k < 8; k++) v[k] = cmul(v[k], tab[K3_TAB_W2 + (k - 1) * 8 + r2]);
 #pragma unroll
-  for (int k = 0; k < 8; k++) {
-    T[idx2(k1, k, r2)] = v[k].x;
-    T[K3_PLANE + idx2(k1, k, r2)] = v[k].y;
-  }
+  for (int k = 0; k < 8; k++) T2[k1 + 8 * k + 66 * r2] = v[k];
   K3_GSYNC(grp);
-  // pass 3: this thread owns (k1, k2) = (t & 7, t >> 3); idx2(k1, k2, r) = t + 68 r
+  // pass 3: this thread owns (k1, k2) = (t & 7, t >> 3): element t + 66 r
 #pragma unroll
-  for (int r = 0; r < 8; r++) {
-    v[r].x = T[t + 68 * r];
-    v[r].y = T[K3_PLANE + t + 68 * r];
-  }
+  for (int r = 0; r < 8; r++) v[r] = T2[t + 66 * r];
   dft8(v);
   // c[p] = T[p] * tw[p] gives D[2p] = Re c[p] and D[M-1-2p] = -Im c[p].  The neighbour of D[2p] in
   // memory, D[2p+1] = D[M-1-2p'] with p' = 511 - p, belongs to the mirrored thread 63 - t (the other lane of
