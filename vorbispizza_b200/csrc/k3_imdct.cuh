@@ -386,12 +386,11 @@ VPZ_DEV bool k3_emit(const float* Dc_hm, const float* Dc_lo, const float* Dp_lo,
           x = __fadd_rn(__fmul_rn(x, w0), __fmul_rn(pv, w1));
           y = __fadd_rn(__fmul_rn(y, x0), __fmul_rn(qv, x1));
         }
-        if (CLIP) {  // Utils.ClipValue (Utils.cs:44-58)
-          const bool hi = x > 0.99999994f, lo = x < -0.99999994f;
-          x = hi ? 0.99999994f : (lo ? -0.99999994f : x);
-          const bool hi2 = y > 0.99999994f, lo2 = y < -0.99999994f;
-          y = hi2 ? 0.99999994f : (lo2 ? -0.99999994f : y);
-          clipped |= hi | lo | hi2 | lo2;
+        if (CLIP) {  // Utils.ClipValue (Utils.cs:44-58): |v| > c -> +-c, anything else (NaN included) unchanged
+          const bool px = fabsf(x) > 0.99999994f, py = fabsf(y) > 0.99999994f;
+          x = px ? copysignf(0.99999994f, x) : x;
+          y = py ? copysignf(0.99999994f, y) : y;
+          clipped |= px | py;
         }
         v[cg] = x;
         u[cg] = y;

@@ -63,12 +63,11 @@ VPZ_DEV bool k3s_emit_same_size(const float* hi0 /* D[M/2..] of channel 0 */, co
       const float b = -plo0[c * K3S_CH_FLOATS + HALF - 1 - j];
       float x = __fadd_rn(__fmul_rn(a, w0), __fmul_rn(b, w1));
       float y = __fadd_rn(__fmul_rn(-a, w1), __fmul_rn(b, w0));
-      if (CLIP) {  // Utils.ClipValue (Utils.cs:44-58)
-        const bool xh = x > 0.99999994f, xl = x < -0.99999994f;
-        x = xh ? 0.99999994f : (xl ? -0.99999994f : x);
-        const bool yh = y > 0.99999994f, yl = y < -0.99999994f;
-        y = yh ? 0.99999994f : (yl ? -0.99999994f : y);
-        clipped |= xh | xl | yh | yl;
+      if (CLIP) {  // Utils.ClipValue (Utils.cs:44-58): |v| > c -> +-c, anything else (NaN included) unchanged
+        const bool px = fabsf(x) > 0.99999994f, py = fabsf(y) > 0.99999994f;
+        x = px ? copysignf(0.99999994f, x) : x;
+        y = py ? copysignf(0.99999994f, y) : y;
+        clipped |= px | py;
       }
       lo[c] = x;
       hi[c] = y;
