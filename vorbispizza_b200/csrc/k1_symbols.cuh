@@ -777,7 +777,10 @@ struct K1Gather {
 
 // acc[0..CH) += the VQ components of positions p .. p+CH-1 of vector v, stage after stage.
 // CH = 16 (stereo type 2: 8 bins of both channels) or 8; p - begin is a multiple of CH.
-template <int CH>
+// PAIR (CH = 16, stereo type 2): position i of the interleaved vector is channel i & 1, bin i >> 1; the
+// accumulators are kept de-interleaved (channel 0 in the first eight, channel 1 in the last eight): Residue2.cs:42-50
+#define K1G_AT(i) (PAIR ? (((i) & 1) * 8 + ((i) >> 1)) : (i))
+template <int CH, bool PAIR>
 VPZ_DEV void k1g_fetch_chunk(const K1Gather& G, int v, int p, float* acc) {
   const int rel = p - G.begin;
   if (rel < 0 || rel >= G.span) return;
@@ -797,18 +800,18 @@ VPZ_DEV void k1g_fetch_chunk(const K1Gather& G, int v, int p, float* acc) {
       for (int k = 0; k < CH / 2; k++)
         if ((uint32_t)k < left) {
           const float2 t = VPZ_LDG(reinterpret_cast<const float2*>(vq + (size_t)ep[k] * 2));
-          acc[2 * k] = __fadd_rn(acc[2 * k], t.x);
-          acc[2 * k + 1] = __fadd_rn(acc[2 * k + 1], t.y);
+          acc[K1G_AT(2 * k)] = __fadd_rn(acc[K1G_AT(2 * k)], t.x);
+          acc[K1G_AT(2 * k + 1)] = __fadd_rn(acc[K1G_AT(2 * k + 1)], t.y);
         }
     } else if (dsh == 2) {
 #pragma unroll
       for (int k = 0; k < CH / 4; k++)
         if ((uint32_t)k < left) {
           const float4 t = VPZ_LDG(reinterpret_cast<const float4*>(vq + (size_t)ep[k] * 4));
-          acc[4 * k] = __fadd_rn(acc[4 * k], t.x);
-          acc[4 * k + 1] = __fadd_rn(acc[4 * k + 1], t.y);
-          acc[4 * k + 2] = __fadd_rn(acc[4 * k + 2], t.z);
-          acc[4 * k + 3] = __fadd_rn(acc[4 * k + 3], t.w);
+          acc[K1G_AT(4 * k)] = __fadd_rn(acc[K1G_AT(4 * k)], t.x);
+          acc[K1G_AT(4 * k + 1)] = __fadd_rn(acc[K1G_AT(4 * k + 1)], t.y);
+          acc[K1G_AT(4 * k + 2)] = __fadd_rn(acc[K1G_AT(4 * k + 2)], t.z);
+          acc[K1G_AT(4 * k + 3)] = __fadd_rn(acc[K1G_AT(4 * k + 3)], t.w);
         }
     } else if (dsh == 3) {
 #pragma unroll
@@ -818,26 +821,26 @@ VPZ_DEV void k1g_fetch_chunk(const K1Gather& G, int v, int p, float* acc) {
 #pragma unroll
           for (int d = 0; d < 8; d += 4) {
             const float4 t = VPZ_LDG(reinterpret_cast<const float4*>(lk + d));
-            acc[8 * k + d] = __fadd_rn(acc[8 * k + d], t.x);
-            acc[8 * k + d + 1] = __fadd_rn(acc[8 * k + d + 1], t.y);
-            acc[8 * k + d + 2] = __fadd_rn(acc[8 * k + d + 2], t.z);
-            acc[8 * k + d + 3] = __fadd_rn(acc[8 * k + d + 3], t.w);
+            acc[K1G_AT(8 * k + d)] = __fadd_rn(acc[K1G_AT(8 * k + d)], t.x);
+            acc[K1G_AT(8 * k + d + 1)] = __fadd_rn(acc[K1G_AT(8 * k + d + 1)], t.y);
+            acc[K1G_AT(8 * k + d + 2)] = __fadd_rn(acc[K1G_AT(8 * k + d + 2)], t.z);
+            acc[K1G_AT(8 * k + d + 3)] = __fadd_rn(acc[K1G_AT(8 * k + d + 3)], t.w);
           }
         }
     } else if (dsh == 0) {
 #pragma unroll
       for (int k = 0; k < CH; k++)
-        if ((uint32_t)k < left) acc[k] = __fadd_rn(acc[k], VPZ_LDG(vq + ep[k]));
+        if ((uint32_t)k < left) acc[K1G_AT(k)] = __fadd_rn(acc[K1G_AT(k)], VPZ_LDG(vq + ep[k]));
     } else if (CH == 16 && dsh == 4) {
       if (left > 0) {
         const float* lk = vq + (size_t)ep[0] * 16;
 #pragma unroll
         for (int d = 0; d < 16; d += 4) {
           const float4 t = VPZ_LDG(reinterpret_cast<const float4*>(lk + d));
-          acc[d] = __fadd_rn(acc[d], t.x);
-          acc[d + 1] = __fadd_rn(acc[d + 1], t.y);
-          acc[d + 2] = __fadd_rn(acc[d + 2], t.z);
-          acc[d + 3] = __fadd_rn(acc[d + 3], t.w);
+          acc[K1G_AT(d)] = __fadd_rn(acc[K1G_AT(d)], t.x);
+          acc[K1G_AT(d + 1)] = __fadd_rn(acc[K1G_AT(d + 1)], t.y);
+          acc[K1G_AT(d + 2)] = __fadd_rn(acc[K1G_AT(d + 2)], t.z);
+          acc[K1G_AT(d + 3)] = __fadd_rn(acc[K1G_AT(d + 3)], t.w);
         }
       }
     }
@@ -1122,22 +1125,22 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   const bool pair = g.rtype == 2 && C == 2;
   const bool coupled = C == 2 && mp->coupling_steps > 0;   // stereo: the only possible pair is (0,1) / (1,0)
   for (int x0 = tid * 8; x0 < res_end; x0 += 32 * 8) {
-    float r[16];   // pair: r[2i] = channel 0, r[2i+1] = channel 1 of bin x0+i; else r[i] = ch 0, r[8+i] = ch 1
+    float r[16];   // r[i] = channel 0, r[8+i] = channel 1 of bin x0+i
 #pragma unroll
     for (int i = 0; i < 16; i++) r[i] = 0.f;
     if (have_res) {
       if (pair) {
-        k1g_fetch_chunk<16>(G, 0, 2 * x0, r);   // Residue2 de-interleave: positions (2x, 2x+1) = (ch0, ch1)
+        k1g_fetch_chunk<16, true>(G, 0, 2 * x0, r);   // Residue2 de-interleave: positions (2x, 2x+1) = (ch0, ch1)
       } else {   // type 2 mono: the one vector is channel 0
-        if (g.rtype == 2 || !(g.skip & 1u)) k1g_fetch_chunk<8>(G, 0, x0, r);
-        if (g.rtype != 2 && C == 2 && !(g.skip & 2u)) k1g_fetch_chunk<8>(G, 1, x0, r + 8);
+        if (g.rtype == 2 || !(g.skip & 1u)) k1g_fetch_chunk<8, false>(G, 0, x0, r);
+        if (g.rtype != 2 && C == 2 && !(g.skip & 2u)) k1g_fetch_chunk<8, false>(G, 1, x0, r + 8);
       }
     }
     float c0[8], c1[8];
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-      c0[i] = pair ? r[2 * i] : r[i];
-      c1[i] = pair ? r[2 * i + 1] : r[8 + i];
+      c0[i] = r[i];
+      c1[i] = r[8 + i];
     }
     if (DEBUG && P.dbg.residue) {
       for (int i = 0; i < 8; i++) {
