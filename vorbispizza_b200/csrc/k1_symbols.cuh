@@ -1224,7 +1224,9 @@ VPZ_DEV void k1b_cta_loop(const K1Params& P, uint32_t* smem, uint32_t* s_idx) {
       if (lane == 0) idx = atomicAdd(P.counter + 2, 1u);
       idx = __shfl_sync(0xffffffffu, idx, 0);
       if (idx >= P.n_pkts) break;
-      k1b_build_packet_gather<DEBUG>(P, idx, my, dbtab, lane);
+      // same order as K1a: grouped by (setup, block size), so the warps resident on an SM run the same
+      // code paths on the same VQ tables
+      k1b_build_packet_gather<DEBUG>(P, P.order ? P.order[idx] : idx, my, dbtab, lane);
     }
   } else {
     for (;;) {
