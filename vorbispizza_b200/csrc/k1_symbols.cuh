@@ -240,8 +240,10 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   uint32_t own_mask = 0;  // bit ch: floor has energy (FloorData.ExecuteChannel)
   for (int ch = 0; ch < C; ch++) {
     const VpzFloor1* fl = reinterpret_cast<const VpzFloor1*>(blob + H->floors_off) + mp->submap_floor[mp->mux[ch]];
-    short po[VPZ_MAX_POSTS + 1];   // raw posts
-    short fy[VPZ_MAX_POSTS + 1];   // unwrapped Y
+    // raw posts, unwrapped in place into the final Y (post i is read once, at step i, and only earlier
+    // posts are looked at afterwards): one per-lane array in local memory instead of two
+    short po[VPZ_MAX_POSTS + 1];
+    short* const fy = po;
     int count = 0, written = 0;  // written: posts stored before a failed decode reset the count
     if (k1_read(b, P.bytes, 1) == 1) {
       const int ybits = fl->ybits;
@@ -293,8 +295,6 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
     // UnwrapPosts (Floor1.cs:270-353): serial dependency through earlier posts
     const int range = fl->range;
     unsigned long long flags = 3ull;
-    fy[0] = po[0];
-    fy[1] = po[1];
     for (int i = 2; i < count; i++) {
       const int lo = fl->lneigh[i], hi = fl->hneigh[i];
       const int predicted = k1_render_point(fl->xlist[lo], fy[lo], fl->xlist[hi], fy[hi], fl->xlist[i]);
