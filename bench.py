@@ -144,6 +144,31 @@ def run_reference(args, rank, world):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
     files = load_files()
+    if args.workload == "config1":
+        # BASELINE config 1: TestApp-style decode of TestFiles/1test.ogg to float PCM on the CPU, ONE stream on
+        # ONE thread (48,000-float reads until 0, TestApp/Program.cs:42,155); a step = 1,000 whole decodes
+        reps = 1000
+        for _ in range(max(1, args.warmup)):
+            ob.bench_decode(files[:1], reps // 10, 1)
+        total, sec = 0, 0.0
+        for _ in range(args.steps):
+            n, s = ob.bench_decode(files[:1], reps, 1)
+            total += n
+            sec += s
+        v = total / sec
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": 0, "steps": args.steps,
+            "warmup": max(1, args.warmup), "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "TestFiles/1test.ogg",
+            "config": {"workload": "config1: TestApp decode of TestFiles/1test.ogg to float PCM on CPU, single stream, "
+                                   "single thread (%d whole decodes per step)" % reps,
+                       "x_realtime": v / 44100.0, "ms_per_decode": 1e3 * sec / (args.steps * reps),
+                       "note": "C restatement of the reference .NET decoder (oracle/); no .NET runtime in this image"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+                             "sample": "%d decodes of 1test.ogg (17,318 samples, mono) per step" % reps},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
     cores = os.cpu_count() or 1
     njobs = 16 * cores  # bounded sample: 16 streams per thread per step (4 of each TestFile)
     for _ in range(args.warmup):
@@ -309,10 +334,11 @@ def main():
     ap.add_argument("--streams", type=int, default=4096, help="streams per GPU (weak) / in total (strong)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work of the cpu_baseline sample")
-    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config5"],
+    ap.add_argument("--workload", default="config4", choices=["config4", "config3", "config5", "config1"],
                     help="config4 (default, the headline): 4,096 streams full decode; config3: kernel-only "
                          "IMDCT+window+OLA on 65,536 synthetic stereo blocks; config5: 16,384 random-access "
-                         "excerpts (SeekTo + 4,096 samples) per GPU through vpz_decode_excerpts")
+                         "excerpts (SeekTo + 4,096 samples) per GPU through vpz_decode_excerpts; config1 (with --impl "
+                         "reference): single-stream CPU decode of 1test.ogg")
     ap.add_argument("--all-long", action="store_true", help="config3 only: pure n=2048 blocks (no short transitions)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
