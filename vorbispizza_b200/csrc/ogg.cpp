@@ -96,6 +96,7 @@ __attribute__((target("pclmul,ssse3"))) static uint32_t crc_clmul(const uint8_t*
 #undef VPZ_CRC_FOLD
 
 static bool crc_clmul_init() {
+  __builtin_cpu_init();   // this runs from a static initialiser
   if (!__builtin_cpu_supports("pclmul") || !__builtin_cpu_supports("ssse3")) return false;
   g_k64_hi = xpow_mod(512 + 64);
   g_k64_lo = xpow_mod(512);
