@@ -25,7 +25,9 @@
 #define K3S_DESC_FLOATS 192      // 32 x (4 descriptor words + 1 exec mask) + work-stealing slot
 #define K3S_CH_FLOATS 1536       // D slots of one channel: Hi[512] Lo0[512] Lo1[512]
 #define K3S_GROUP_FLOATS (K3S_DESC_FLOATS + 2 * K3_PLANE + 2 * K3S_CH_FLOATS)
+#ifndef K3S_MAX_GROUPS
 #define K3S_MAX_GROUPS 12
+#endif
 
 #ifndef VPZ_EMU
 VPZ_DEV void k3s_cp16(float* dst_smem, const float* src) {
