@@ -28,6 +28,9 @@
 #ifndef K3S_MAX_GROUPS
 #define K3S_MAX_GROUPS 12
 #endif
+#ifndef K3S_EMIT_UNROLL
+#define K3S_EMIT_UNROLL 4
+#endif
 
 #ifndef VPZ_EMU
 VPZ_DEV void k3s_cp16(float* dst_smem, const float* src) {
@@ -54,7 +57,8 @@ VPZ_DEV bool k3s_emit_same_size(const float* hi0 /* D[M/2..] of channel 0 */, co
   bool clipped = false;
   const bool pair_ok = NC == 2 && (reinterpret_cast<uintptr_t>(outp) & (OUT16 ? 3u : 7u)) == 0;
   constexpr int HALF = M / 2;
-#pragma unroll 4
+  constexpr int UNROLL = K3S_EMIT_UNROLL;
+#pragma unroll UNROLL
   for (int r = 0; r < HALF / 64; r++) {
     const int j = t64 + 64 * r;
     const float w0 = ws[j], w1 = ws[M - 1 - j];
