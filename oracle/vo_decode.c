@@ -31,7 +31,101 @@ static inline int decode_scalar(const vo_book* bk, vo_bits* br, vo_packet_dump* 
 typedef struct {
   int posts[64];
   int post_count;
+  /* floor 0 (Floor0.Data, Floor0.cs:11-28) */
+  float amp;
+  float coeff[256];
+  uint32_t amp_raw;
+  int book_num;
 } floor1_data;
+
+/* ------------------------------------------------------------------ floor0 -- */
+/* Floor0.Unpack (Floor0.cs:115-167).  The amplitude is read, then the book number and the
+ * coefficients are read WHATEVER the amplitude is (libvorbis stops at amplitude 0; the reference
+ * does not), so a silent channel still consumes its bits. */
+static void floor0_unpack(const vo_floor1* f, const vo_book* books, vo_bits* br, floor1_data* fd,
+                          vo_packet_dump* d) {
+  memset(fd->coeff, 0, sizeof(fd->coeff));
+  memset(fd->posts, 0, sizeof(fd->posts));
+  fd->post_count = 0;
+  fd->amp_raw = 0;
+  fd->book_num = 0;
+  const uint64_t amp = vo_read_bits(br, f->amp_bits);
+  /* double ampDiv = (1 << _ampBits) - 1 : int arithmetic, shift count taken mod 32, wrapping */
+  const int32_t one_shift = (int32_t)(1u << (f->amp_bits & 31));
+  const double amp_div = (double)(int32_t)((uint32_t)one_shift - 1u);
+  /* (float)(amp * _ampOfs / ampDiv): ulong product (wraps), then double division */
+  fd->amp = (float)((double)(amp * (uint64_t)f->amp_ofs) / amp_div);
+  fd->amp_raw = (uint32_t)amp;
+  const uint32_t book_num = (uint32_t)vo_read_bits(br, vo_ilog(f->nbooks0));
+  fd->book_num = (int)book_num;
+  if (book_num >= (uint32_t)f->nbooks0) {
+    fd->amp = 0;
+    return;
+  }
+  const vo_book* bk = &books[f->books0[book_num]];
+  for (int i = 0; i < f->order;) {
+    int entry = decode_scalar(bk, br, d);
+    if (entry == -1) {
+      fd->amp = 0;
+      return;
+    }
+    const float* lookup = bk->lookup + (size_t)entry * bk->dims;
+    for (int j = 0; i < f->order && j < bk->dims; j++, i++) fd->coeff[i] = lookup[j];
+  }
+  /* the "averaging" */
+  const int dim = bk->dims;
+  float last = 0.f;
+  for (int j = 0; j < f->order;) {
+    for (int k = 0; j < f->order && k < dim; j++, k++) fd->coeff[j] += last;
+    last = fd->coeff[j - 1];
+  }
+  /* the dump keeps the floor-1 fields: post_count = 2 when the channel has energy (Amp != 0,
+   * Floor0.cs:21), posts = {raw amplitude, book number} */
+  if (fd->amp != 0) {
+    fd->post_count = 2;
+    fd->posts[0] = (int)(fd->amp_raw & 0x7fffffffu);
+    fd->posts[1] = fd->book_num;
+  }
+}
+
+/* Floor0.Apply (Floor0.cs:169-224) */
+static void floor0_apply(const vo_floor1* f, floor1_data* fd, int w, int block_size, float* residue) {
+  const int n = block_size / 2;
+  if (fd->amp <= 0.f) {
+    memset(residue, 0, sizeof(float) * (size_t)n);
+    return;
+  }
+  const int* bark = f->bark_map[w];
+  const float* wmap = f->wmap[w];
+  const int order = f->order;
+  for (int j = 0; j < order; j++) fd->coeff[j] = 2.0f * cosf(fd->coeff[j]);
+  const float amp_ofs = (float)f->amp_ofs;
+  int i = 0;
+  while (i < n) {
+    int j;
+    const int k = bark[i];
+    float p = .5f, q = .5f;
+    const float wv = wmap[k];
+    for (j = 1; j < order; j += 2) {
+      q *= wv - fd->coeff[j - 1];
+      p *= wv - fd->coeff[j];
+    }
+    if (j == order) {
+      /* odd order filter; slightly asymmetric */
+      q *= wv - fd->coeff[j - 1];
+      p *= p * (4.f - wv * wv);
+      q *= q;
+    } else {
+      /* even order filter; still symmetric */
+      p *= p * (2.f - wv);
+      q *= q * (2.f + wv);
+    }
+    q = fd->amp / sqrtf(p + q) - amp_ofs;
+    q = expf(q * 0.11512925f);
+    residue[i] *= q;
+    while (bark[++i] == k) residue[i] *= q;
+  }
+}
 
 /* Floor1.Unpack (Floor1.cs:162-219) */
 static void floor1_unpack(const vo_floor1* f, const vo_book* books, vo_bits* br, floor1_data* fd,
@@ -688,7 +782,10 @@ void vo_mapping_decode(vo_setup* st, const vo_mapping* mp, vo_bits* br, int bloc
 
   for (int ch = 0; ch < channels; ch++) {
     const vo_floor1* f = &st->floors[mp->submap_floor[mp->mux[ch]]];
-    floor1_unpack(f, st->books, br, &fd[ch], d);
+    if (f->type == 0)
+      floor0_unpack(f, st->books, br, &fd[ch], d);
+    else
+      floor1_unpack(f, st->books, br, &fd[ch], d);
     no_exec[ch] = fd[ch].post_count <= 0;
     memset(buf + (size_t)ch * stride, 0, sizeof(float) * (size_t)stride);
     if (d) {
@@ -743,7 +840,10 @@ void vo_mapping_decode(vo_setup* st, const vo_mapping* mp, vo_bits* br, int bloc
       const vo_floor1* f = &st->floors[mp->submap_floor[mp->mux[ch]]];
       uint8_t step[64];
       memset(step, 0, sizeof(step));
-      floor1_apply(f, &fd[ch], block_size, span, step);
+      if (f->type == 0)
+        floor0_apply(f, &fd[ch], block_size == st->size0 ? 0 : 1, block_size, span);
+      else
+        floor1_apply(f, &fd[ch], block_size, span, step);
       if (d) {
         memcpy(d->final_y[ch], fd[ch].posts, sizeof(int) * 64);
         for (int k = 0; k < 64; k++) d->step_flags[ch][k] = step[k];

@@ -112,6 +112,13 @@ typedef struct {
 } vo_book;
 
 typedef struct {
+  int type; /* 1 = floor 1 (Floor1.cs), 0 = floor 0 (Floor0.cs) */
+  /* floor 0 (Floor0.cs:29-76) */
+  int order, rate, bark_map_size, amp_bits, amp_ofs, nbooks0;
+  uint8_t books0[16];
+  int* bark_map[2];  /* n + 1 entries per block size (Floor0.cs:83-96) */
+  float* wmap[2];    /* n entries per block size (Floor0.cs:103-113) */
+  /* floor 1 */
   int partitions;
   uint8_t part_class[32];
   int class_count;

@@ -278,10 +278,59 @@ int vo_book_decode_scalar(const vo_book* bk, vo_bits* br) {
 }
 
 /* ----------------------------------------------------------------- floor1 -- */
+/* Floor0.ToBARK (Floor0.cs:98-101): double arithmetic, rounded to float */
+static float floor0_to_bark(double lsp) {
+  return (float)(13.1 * atan(0.00074 * lsp) + 2.24 * atan(0.0000000185 * lsp * lsp) + .0001 * lsp);
+}
+
+/* Floor0 ctor (Floor0.cs:39-76), SynthesizeBarkCurve (:83-96), SynthesizeWDelMap (:103-113) */
+static int floor0_parse(vo_floor1* f, vo_bits* br, const vo_setup* st) {
+  memset(f, 0, sizeof(*f));
+  f->type = 0;
+  f->order = (int)vo_read_bits(br, 8);
+  f->rate = (int)vo_read_bits(br, 16);
+  f->bark_map_size = (int)vo_read_bits(br, 16);
+  f->amp_bits = (int)vo_read_bits(br, 6);
+  f->amp_ofs = (int)vo_read_bits(br, 8);
+  f->nbooks0 = (int)vo_read_bits(br, 4) + 1;
+  if (f->order < 1 || f->rate < 1 || f->bark_map_size < 1) return VO_E_INVALID_DATA;
+  for (int i = 0; i < f->nbooks0; i++) {
+    int num = (int)vo_read_bits(br, 8);
+    if (num >= st->nbooks) return VO_E_INVALID_DATA;
+    if (st->books[num].map_type == 0 || st->books[num].dims < 1) return VO_E_INVALID_DATA;
+    f->books0[i] = (uint8_t)num;
+  }
+  for (int w = 0; w < 2; w++) {
+    const int n = (w ? st->size1 : st->size0) / 2;
+    /* float scale = _bark_map_size / ToBARK(_rate / 2.0) : ushort / float in fp32 */
+    const float scale = (float)f->bark_map_size / floor0_to_bark(f->rate / 2.0);
+    int* map = (int*)calloc((size_t)n + 1, sizeof(int));
+    for (int i = 0; i < n + 1 - 2; i++) { /* i < map.Length - 2: entry n-1 keeps its default 0 */
+      const float prod = floor0_to_bark((f->rate / 2.0) / n * i) * scale; /* float * float */
+      int v = (int)floor((double)prod);
+      map[i] = v < f->bark_map_size - 1 ? v : f->bark_map_size - 1;
+    }
+    map[n] = -1;
+    f->bark_map[w] = map;
+    const float wdel = (float)(3.14159265358979323846 / f->bark_map_size);
+    float* wm = (float*)calloc((size_t)n, sizeof(float));
+    for (int i = 0; i < n; i++) {
+      const float a = wdel * (float)i;
+      wm[i] = 2.0f * cosf(a);
+    }
+    f->wmap[w] = wm;
+    /* Apply reads wMap[barkMap[i]] (Floor0.cs:192): a bark index >= n is an IndexOutOfRangeException there */
+    for (int i = 0; i < n; i++)
+      if (map[i] >= n) return VO_E_REF_FAULT;
+  }
+  return VO_OK;
+}
+
 static int floor1_parse(vo_floor1* f, vo_bits* br, int nbooks) {
   static const uint8_t range_lookup[4] = {128, 64, 43, 32};
   static const uint8_t ybits_lookup[4] = {8, 7, 7, 6};
   memset(f, 0, sizeof(*f));
+  f->type = 1;
   int maximum_class = -1;
   f->partitions = (int)vo_read_bits(br, 5);
   for (int i = 0; i < f->partitions; i++) {
@@ -512,7 +561,10 @@ int vo_setup_parse_books(vo_setup* st, const uint8_t* pkt, int len) {
   st->floors = (vo_floor1*)calloc((size_t)st->nfloors, sizeof(vo_floor1));
   for (int i = 0; i < st->nfloors; i++) {
     int type = (int)vo_read_bits(&br, 16);
-    if (type == 0) return VO_E_UNSUPPORTED; /* Floor0.cs: not restated ("next") */
+    if (type == 0) {
+      if ((rc = floor0_parse(&st->floors[i], &br, st)) != VO_OK) return rc;
+      continue;
+    }
     if (type != 1) return VO_E_INVALID_DATA;
     if ((rc = floor1_parse(&st->floors[i], &br, st->nbooks)) != VO_OK) return rc;
     if (st->floors[i].xcount > 64) return VO_E_UNSUPPORTED; /* Posts[64], quirk Q2 */
@@ -558,6 +610,11 @@ void vo_setup_free(vo_setup* st) {
     free(st->residues[i].decode_map);
     free(st->residues[i].part_word_cache);
   }
+  for (int i = 0; i < st->nfloors && st->floors; i++)
+    for (int w = 0; w < 2; w++) {
+      free(st->floors[i].bark_map[w]);
+      free(st->floors[i].wmap[w]);
+    }
   free(st->books);
   free(st->floors);
   free(st->residues);

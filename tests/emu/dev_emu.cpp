@@ -54,7 +54,11 @@ struct Event {
   double t = 0;
 };
 
-int init(int, std::string&) { return VPZ_OK; }
+int init(int device, int* resolved, std::string&) {
+  if (resolved) *resolved = device < 0 ? 0 : device;
+  return VPZ_OK;
+}
+void make_current(int) {}
 int device_count() { return 1; }
 int sm_count() { return 1; }
 size_t max_smem_per_block() { return 227 * 1024; }
@@ -91,9 +95,8 @@ int fill(void* d, int v, size_t n, Stream*, std::string&) {
   return VPZ_OK;
 }
 
-int launch_k1a(const K1Params& p, bool debug, int blocks, Stream*, std::string&) {
+int launch_k1a(const K1Params& p, bool debug, bool full, int blocks, Stream*, std::string&) {
   if (p.n_pkts == 0) return VPZ_OK;
-  memset(p.counter, 0, 16);
   (void)blocks;  // work stealing: one emulated block drains the whole queue
   emu::launch(1, 128, 0, [&] {
     const int lane = threadIdx.x & 31;
@@ -104,7 +107,12 @@ int launch_k1a(const K1Params& p, bool debug, int blocks, Stream*, std::string&)
       if (base >= p.n_pkts) break;
       const uint32_t i = base + lane;
       if (i < p.n_pkts) {
-        if (debug) k1a_decode_packet<true>(p, p.order ? p.order[i] : i); else k1a_decode_packet<false>(p, p.order ? p.order[i] : i);
+        const uint32_t k = p.order ? p.order[i] : i;
+        if (debug) {
+          if (full) k1a_decode_packet<true, true>(p, k); else k1a_decode_packet<true, false>(p, k);
+        } else {
+          if (full) k1a_decode_packet<false, true>(p, k); else k1a_decode_packet<false, false>(p, k);
+        }
       }
       __syncwarp();
     }
@@ -125,17 +133,15 @@ int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream*, st
 
 int launch_k3(const K3Params& p, int ncb, size_t smem_bytes, Stream*, std::string&) {
   if (p.n_items == 0) return VPZ_OK;
-  *p.counter = 0;
   emu::launch(2, (unsigned)ncb * K3_THREADS_PER_CH, smem_bytes, [&] {
     float* smem = (float*)emu::t_block->smem;
-    k3_cta_loop(p, smem, ncb);
+    if (p.out16) k3_cta_loop<true>(p, smem, ncb); else k3_cta_loop<false>(p, smem, ncb);
   });
   return VPZ_OK;
 }
 
 int launch_k3_streams(const K3Params& p, Stream*, std::string&) {
   if (p.n_items == 0) return VPZ_OK;
-  *p.counter = 0;
   const unsigned groups = p.n_items >= 3 ? 3 : 1;   // independent 64-thread workers per emulated CTA
   emu::launch(2, groups * K3_THREADS_PER_CH, ((size_t)K3S_TAB_FLOATS + groups * K3S_GROUP_FLOATS) * 4, [&] {
     if (p.out16) k3s_cta<true>(p, (float*)emu::t_block->smem); else k3s_cta<false>(p, (float*)emu::t_block->smem);

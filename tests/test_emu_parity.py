@@ -96,3 +96,31 @@ def test_empty_inputs(emu_ctx):
     with Batch(emu_ctx) as b:
         b.decode(clip=True)
         assert b.total_floats == 0
+
+
+# ---- every packet class through every kernel path ---------------------------------------------------
+# The TestFiles are mono / stereo, residue 1 / 2, power-of-two VQ dimensions: left alone they only take
+# the gather spectrum kernel and the 256 / 2048 IMDCT kernel.  "force_general" routes them through the
+# general spectrum kernel (one CTA per packet), the generic IMDCT kernel and (2) the full symbol kernel.
+@pytest.fixture(scope="module", params=[1, 2])
+def general_ctx(emu_lib_path, request):
+    from vorbispizza_b200 import Context
+    ctx = Context(0, lib_path=emu_lib_path)
+    ctx.set("force_general", request.param)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,stride", [("1test", 1), ("2test", 61), ("3test", 73), ("issue6test", 83)])
+def test_general_path_stage_parity(general_ctx, name, stride):
+    assert cases.stage_parity(general_ctx, name, stride=stride) > 0
+
+
+def test_general_path_truncated(general_ctx):
+    assert cases.stage_parity(general_ctx, "3test", stride=131, truncate=True) > 0
+
+
+def test_general_path_pcm(general_ctx):
+    cases.batch_pcm_parity(general_ctx, "1test", True)
+    cases.decode_files_parity(general_ctx, ["1test"])
+    cases.decode_files_s16_parity(general_ctx, ["1test"])

@@ -11,7 +11,7 @@
 #include "k3_streams.cuh"
 
 // ---- kernels ---------------------------------------------------------------------------------
-template <bool DEBUG>
+template <bool DEBUG, bool FULL>
 __global__ void __launch_bounds__(128, 8) vpz_k1a_symbols(K1Params P) {
   const int lane = threadIdx.x & 31;
   for (;;) {
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(128, 8) vpz_k1a_symbols(K1Params P) {
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= P.n_pkts) break;
     const uint32_t i = base + lane;
-    if (i < P.n_pkts) k1a_decode_packet<DEBUG>(P, P.order ? P.order[i] : i);
+    if (i < P.n_pkts) k1a_decode_packet<DEBUG, FULL>(P, P.order ? P.order[i] : i);
     __syncwarp();
   }
 }
@@ -33,9 +33,10 @@ __global__ void __launch_bounds__(K1B_THREADS, 9) vpz_k1b_spectrum(K1Params P) {
 }
 
 // generic block sizes / channel counts
+template <bool OUT16>
 __global__ void __launch_bounds__(128, 1) vpz_k3_imdct_ola(K3Params P, int ncb) {
   extern __shared__ float k3_smem[];
-  k3_cta_loop(P, k3_smem, ncb);
+  k3_cta_loop<OUT16>(P, k3_smem, ncb);
 }
 
 // block sizes 256 / 2048, mono / stereo: one CTA per SM, up to 12 independent 64-thread workers
@@ -55,8 +56,12 @@ struct Event {
   cudaEvent_t e;
 };
 
-static int g_sm_count = 0;
-static size_t g_max_smem = 0;
+// per device (a process may hold contexts on several GPUs); the calling thread's current device is
+// tracked here so that make_current costs nothing when it does not change
+#define VPZ_MAX_DEVICES 64
+static int g_sm_count[VPZ_MAX_DEVICES] = {0};
+static size_t g_max_smem[VPZ_MAX_DEVICES] = {0};
+static thread_local int t_device = -1;
 
 static int fail(cudaError_t e, const char* what, std::string& err) {
   err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -72,7 +77,12 @@ int device_count() {
   return n;
 }
 
-int init(int device, std::string& err) {
+void make_current(int device) {
+  if (device == t_device || device < 0) return;
+  if (cudaSetDevice(device) == cudaSuccess) t_device = device; else cudaGetLastError();
+}
+
+int init(int device, int* resolved, std::string& err) {
   int n = device_count();
   if (n <= 0) {
     err = "no CUDA device visible (libvpz has no CPU path)";
@@ -81,12 +91,14 @@ int init(int device, std::string& err) {
   if (device < 0) {
     if (cudaGetDevice(&device) != cudaSuccess) device = 0;
   }
-  if (device >= n) {
+  if (device >= n || device >= VPZ_MAX_DEVICES) {
     err = "device index out of range";
     return VPZ_E_NO_DEVICE;
   }
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return fail(e, "cudaSetDevice", err);
+  t_device = device;
+  if (resolved) *resolved = device;
   cudaDeviceProp prop;
   e = cudaGetDeviceProperties(&prop, device);
   if (e != cudaSuccess) return fail(e, "cudaGetDeviceProperties", err);
@@ -95,20 +107,22 @@ int init(int device, std::string& err) {
           "; libvpz is built for sm_100a only";
     return VPZ_E_NO_DEVICE;
   }
-  g_sm_count = prop.multiProcessorCount;
-  g_max_smem = prop.sharedMemPerBlockOptin;
-  cudaFuncSetAttribute(vpz_k1b_spectrum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
-  cudaFuncSetAttribute(vpz_k1b_spectrum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
-  cudaFuncSetAttribute(vpz_k3_imdct_ola, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
-  cudaFuncSetAttribute(vpz_k3_streams<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
-  cudaFuncSetAttribute(vpz_k3_streams<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_max_smem);
+  g_sm_count[device] = prop.multiProcessorCount;
+  g_max_smem[device] = prop.sharedMemPerBlockOptin;
+  const int optin = (int)prop.sharedMemPerBlockOptin;   // function attributes are per device
+  cudaFuncSetAttribute(vpz_k1b_spectrum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k1b_spectrum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k3_imdct_ola<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k3_imdct_ola<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k3_streams<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k3_streams<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute", err);
   return VPZ_OK;
 }
 
-int sm_count() { return g_sm_count; }
-size_t max_smem_per_block() { return g_max_smem; }
+int sm_count() { return t_device >= 0 ? g_sm_count[t_device] : 0; }
+size_t max_smem_per_block() { return t_device >= 0 ? g_max_smem[t_device] : 0; }
 
 void* alloc(size_t bytes, std::string& err) {
   void* p = nullptr;
@@ -124,7 +138,8 @@ void free(void* p) {
 }
 void* host_alloc(size_t bytes) {
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+  // portable: pinned for every device, whichever context's thread allocated it
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }
@@ -207,15 +222,14 @@ int fill(void* dst, int byte_value, size_t bytes, Stream* s, std::string& err) {
   return e == cudaSuccess ? VPZ_OK : fail(e, "cudaMemsetAsync", err);
 }
 
-int launch_k1a(const K1Params& p, bool debug, int blocks, Stream* s, std::string& err) {
+int launch_k1a(const K1Params& p, bool debug, bool full, int blocks, Stream* s, std::string& err) {
   if (p.n_pkts == 0) return VPZ_OK;
-  cudaError_t e = cudaMemsetAsync(p.counter, 0, 16, s->s);
-  if (e != cudaSuccess) return fail(e, "cudaMemsetAsync(counter)", err);
-  if (debug)
-    vpz_k1a_symbols<true><<<blocks, 128, 0, s->s>>>(p);
-  else
-    vpz_k1a_symbols<false><<<blocks, 128, 0, s->s>>>(p);
-  e = cudaGetLastError();
+  if (debug) {
+    if (full) vpz_k1a_symbols<true, true><<<blocks, 128, 0, s->s>>>(p); else vpz_k1a_symbols<true, false><<<blocks, 128, 0, s->s>>>(p);
+  } else {
+    if (full) vpz_k1a_symbols<false, true><<<blocks, 128, 0, s->s>>>(p); else vpz_k1a_symbols<false, false><<<blocks, 128, 0, s->s>>>(p);
+  }
+  cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k1a_symbols", err);
 }
 
@@ -223,7 +237,7 @@ int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, 
   if (p.n_pkts == 0) return VPZ_OK;
   // gather path: smem_words_per_warp per warp; general path: per CTA
   size_t smem = (size_t)p.smem_words_per_warp * 4 * (p.gather_ok ? warps : 1) + (p.gather_ok ? 1024 : 0);  // + the dB table
-  if (smem > g_max_smem) {
+  if (smem > max_smem_per_block()) {
     err = "K1b shared memory request exceeds the device limit";
     return VPZ_E_UNSUPPORTED;
   }
@@ -237,25 +251,26 @@ int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, 
 
 int launch_k3(const K3Params& p, int ncb, size_t smem_bytes, Stream* s, std::string& err) {
   if (p.n_items == 0) return VPZ_OK;
-  if (smem_bytes > g_max_smem) {
+  if (smem_bytes > max_smem_per_block()) {
     err = "K3 shared memory request exceeds the device limit";
     return VPZ_E_UNSUPPORTED;
   }
   int threads = ncb * K3_THREADS_PER_CH;
-  cudaError_t e0 = cudaMemsetAsync(p.counter, 0, 4, s->s);  // word 1 of the counter block (K1a/K1b use 0 and 2)
-  if (e0 != cudaSuccess) return fail(e0, "cudaMemsetAsync(counter)", err);
   // persistent CTAs: enough to fill every SM, items are handed out by the counter
-  unsigned grid = (unsigned)std::min<size_t>(p.n_items, (size_t)8 * g_sm_count);
-  vpz_k3_imdct_ola<<<grid, threads, smem_bytes, s->s>>>(p, ncb);
+  unsigned grid = (unsigned)std::min<size_t>(p.n_items, (size_t)8 * sm_count());
+  if (p.out16)
+    vpz_k3_imdct_ola<true><<<grid, threads, smem_bytes, s->s>>>(p, ncb);
+  else
+    vpz_k3_imdct_ola<false><<<grid, threads, smem_bytes, s->s>>>(p, ncb);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k3_imdct_ola", err);
 }
 
 int k3_streams_groups(size_t n_items) {
   // workers per CTA: as many as shared memory holds; small batches are spread over all SMs instead
-  size_t fit = (g_max_smem / 4 - K3S_TAB_FLOATS) / K3S_GROUP_FLOATS;
+  size_t fit = (max_smem_per_block() / 4 - K3S_TAB_FLOATS) / K3S_GROUP_FLOATS;
   size_t g = std::min<size_t>(K3S_MAX_GROUPS, fit);
-  size_t per_sm = (n_items + (size_t)g_sm_count - 1) / (size_t)std::max(g_sm_count, 1);
+  size_t per_sm = (n_items + (size_t)sm_count() - 1) / (size_t)std::max(sm_count(), 1);
   return (int)std::max<size_t>(1, std::min(g, per_sm));
 }
 
@@ -263,13 +278,11 @@ int launch_k3_streams(const K3Params& p, Stream* s, std::string& err) {
   if (p.n_items == 0) return VPZ_OK;
   const int groups = k3_streams_groups(p.n_items);
   const size_t smem_bytes = ((size_t)K3S_TAB_FLOATS + (size_t)groups * K3S_GROUP_FLOATS) * 4;
-  if (smem_bytes > g_max_smem) {
+  if (smem_bytes > max_smem_per_block()) {
     err = "K3 shared memory request exceeds the device limit";
     return VPZ_E_UNSUPPORTED;
   }
-  cudaError_t e0 = cudaMemsetAsync(p.counter, 0, 4, s->s);
-  if (e0 != cudaSuccess) return fail(e0, "cudaMemsetAsync(counter)", err);
-  unsigned grid = (unsigned)std::min<size_t>((p.n_items + groups - 1) / groups, (size_t)g_sm_count);
+  unsigned grid = (unsigned)std::min<size_t>((p.n_items + groups - 1) / groups, (size_t)sm_count());
   if (p.out16)
     vpz_k3_streams<true><<<grid, groups * K3_THREADS_PER_CH, smem_bytes, s->s>>>(p);
   else

@@ -17,9 +17,15 @@ namespace dev {
 struct Stream;  // opaque
 struct Event;
 
-int init(int device, std::string& err);  // 0 or VPZ_E_NO_DEVICE / VPZ_E_CUDA
+// Selects the device (< 0: the calling thread's current one), checks that it is an sm_100 part and
+// caches its properties; *resolved receives the device index.  0 or VPZ_E_NO_DEVICE / VPZ_E_CUDA
+int init(int device, int* resolved, std::string& err);
+// Makes `device` the calling thread's current CUDA device.  Every extern "C" entry point that touches
+// the device calls this first: the current device is per host thread, and one process may hold
+// contexts on several GPUs (include/vpz.h: "one context per GPU").
+void make_current(int device);
 int device_count();
-int sm_count();
+int sm_count();                          // of the calling thread's current device (make_current)
 
 void* alloc(size_t bytes, std::string& err);
 void free(void* p);
@@ -43,16 +49,19 @@ int d2d(void* dst, const void* src, size_t bytes, Stream* s, std::string& err);
 int fill(void* dst, int byte_value, size_t bytes, Stream* s, std::string& err);
 unsigned long long transfer_bytes(int which);  // process-wide bytes copied so far: 0 host->device, 1 device->host
 
-// K1a: one lane per packet, `blocks` CTAs of 128 threads.  K1b: one warp per packet, `blocks` CTAs of
-// `warps` warps, dynamic shared memory = warps * smem_words_per_warp * 4.  Both take packets from
-// p.counter (K1a uses word 0, K1b word 2 of the context's counter block).
-int launch_k1a(const K1Params& p, bool debug, int blocks, Stream* s, std::string& err);
+// Every launcher works on the slice of the batch its parameter block describes (p.order / p.n_pkts for
+// K1, p.items / p.n_items for K3) and hands the work out through *p.counter, which the caller has
+// zeroed on the same stream (one word per launch of a decode pass).
+// K1a: one lane per packet, `blocks` CTAs of 128 threads; full = the variant that also walks floor 0
+// and mappings with several submaps.  K1b: p.gather_ok ? one warp per packet, `blocks` CTAs of `warps`
+// warps, dynamic shared memory = warps * smem_words_per_warp * 4 : one CTA per packet.
+int launch_k1a(const K1Params& p, bool debug, bool full, int blocks, Stream* s, std::string& err);
 int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, std::string& err);
 // K3, generic block sizes / channel counts: one CTA per work item, ncb channels side by side (64 threads each)
 int launch_k3(const K3Params& p, int ncb, size_t smem_bytes, Stream* s, std::string& err);
 // K3, block sizes 256 / 2048 and at most 2 channels: one CTA per SM of independent 64-thread workers
 int launch_k3_streams(const K3Params& p, Stream* s, std::string& err);
-size_t max_smem_per_block();
+size_t max_smem_per_block();             // of the calling thread's current device
 
 }  // namespace dev
 }  // namespace vpz

@@ -32,6 +32,21 @@ static size_t max_units(const Setup& st) {
   return units;
 }
 
+static int fl_type(const Setup& st, int i) {
+  const VpzSetupHdr* h = st.hdr();
+  return reinterpret_cast<const VpzFloor1*>(st.blob.data() + h->floors_off)[i].floor_type;
+}
+
+// Kernel class of a setup (engine.h, vpz_batch::n_class) and whether its K3 items take the fast kernel
+static int k1_class(const vpz_ctx* ctx, const vpz_setup* s) {
+  if (s->k1a_full || ctx->force_general >= 2) return 2;
+  if (!s->gather_ok || ctx->force_general >= 1) return 1;
+  return 0;
+}
+static bool k3_fast(const vpz_ctx* ctx, const vpz_setup* s) {
+  return s->fast_sizes && s->host.id.channels <= 2 && ctx->force_general == 0;
+}
+
 // K1b shared memory per warp: swizzled residue (one pad word per 32) + unit start offsets
 static uint32_t k1_words(const Setup& st) {
   const VpzSetupHdr* h = st.hdr();
@@ -74,7 +89,11 @@ static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
               if (dims < 1 || (dims & (dims - 1)) || dims > chunk) ok = false;
             }
       }
-      s->gather_ok = ok;
+      // floor 0 curves and mappings with several submaps live on the general path only
+      const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(st.blob.data() + h->mappings_off);
+      for (int i = 0; i < h->nmappings; i++) s->k1a_full = s->k1a_full || mp[i].submaps > 1;
+      for (int i = 0; i < h->nfloors; i++) s->k1a_full = s->k1a_full || fl_type(st, i) == 0;
+      s->gather_ok = ok && !s->k1a_full;
       const size_t U = (units + 31) & ~(size_t)31;
       const size_t half_max = (size_t)1 << (h->log2_size1 - 1);
       // k1b gather layout per warp: urec stages*U*2 + ybuf C*half_max/4 + sg C*4*66 (+ pad, multiple of 32)
@@ -218,8 +237,17 @@ void setup_release(vpz_setup* s) {
 static int slot_of(vpz_batch* b, vpz_setup* s) {
   for (size_t i = 0; i < b->slots.size(); i++)
     if (b->slots[i] == s) return (int)i;
+  // the batch holds a reference for as long as the slot exists (vpz_batch_reset / destroy drop it): the
+  // caller may release its own handle right after add_run, and the context's LRU may evict the setup
+  s->refs++;
   b->slots.push_back(s);
   return (int)b->slots.size() - 1;
+}
+
+void batch_drop_slots(vpz_batch* b) {
+  for (vpz_setup* s : b->slots)
+    if (s != b->owned_setup) setup_release(s);
+  b->slots.clear();
 }
 
 // ---- host worker pool -----------------------------------------------------------------------
@@ -532,13 +560,21 @@ int batch_upload(vpz_batch* b) {
     if (!b->order.reserve(2 * np + 2)) return VPZ_E_NOMEM;
     const double ts0 = trace_now();
     {
-      // sort_key = group << 13 | (4096 - min(byte_len / 4, 4096)), group = setup slot * 2 + (short block);
-      // it was written by the threads that filled the batch, so the sort reads 4 bytes per packet
-      const size_t ngroups = 2 * b->slots.size();
+      // sort_key = (setup slot * 2 + short block) << 13 | (4096 - min(byte_len / 4, 4096)); it was written by
+      // the threads that filled the batch, so the sort reads 4 bytes per packet.  The kernel class of the
+      // setup (0 gather, 1 general K1b, 2 full K1a + general K1b) goes on top: every class is one contiguous
+      // slice of the order array and gets its own launches.
+      const size_t nslots = b->slots.size();
+      std::vector<uint32_t> cls_of(nslots);
+      for (size_t i = 0; i < nslots; i++) cls_of[i] = (uint32_t)k1_class(ctx, b->slots[i]);
+      const size_t ngroups = 3 * 2 * nslots;
       const uint32_t* key = b->sort_key.data();
+      auto group_of = [&](size_t i) { return (size_t)cls_of[key[i] >> 14] * 2 * nslots + (key[i] >> 13); };
+      b->n_class[0] = b->n_class[1] = b->n_class[2] = 0;
+      for (size_t i = 0; i < np; i++) b->n_class[cls_of[key[i] >> 14]]++;
       if (ngroups * 4097 <= ((size_t)1 << 20)) {
         std::vector<uint32_t> bucket(ngroups * 4097 + 2, 0);
-        auto k1 = [&](size_t i) { return (size_t)(key[i] >> 13) * 4097 + (key[i] & 8191u); };
+        auto k1 = [&](size_t i) { return group_of(i) * 4097 + (key[i] & 8191u); };
         for (size_t i = 0; i < np; i++) bucket[k1(i) + 1]++;
         for (size_t k = 1; k < bucket.size(); k++) bucket[k] += bucket[k - 1];
         for (size_t i = 0; i < np; i++) b->order.p[bucket[k1(i)]++] = (uint32_t)i;
@@ -549,9 +585,9 @@ int batch_upload(vpz_batch* b) {
         for (size_t k = 1; k < bucket.size(); k++) bucket[k] += bucket[k - 1];
         for (size_t i = 0; i < np; i++) tmp[bucket[key[i] & 8191u]++] = (uint32_t)i;
         std::vector<uint32_t> gb(ngroups + 2, 0);
-        for (size_t i = 0; i < np; i++) gb[(key[i] >> 13) + 1]++;
+        for (size_t i = 0; i < np; i++) gb[group_of(i) + 1]++;
         for (size_t k = 1; k < gb.size(); k++) gb[k] += gb[k - 1];
-        for (size_t i = 0; i < np; i++) b->order.p[gb[key[tmp[i]] >> 13]++] = tmp[i];
+        for (size_t i = 0; i < np; i++) b->order.p[gb[group_of(tmp[i])]++] = tmp[i];
       }
       b->order.n = np;
     }
@@ -563,7 +599,22 @@ int batch_upload(vpz_batch* b) {
       !b->d_setups.reserve(b->slots.size() * sizeof(void*), err))
     return VPZ_E_CUDA;
   if ((rc = dev::h2d(b->d_pkts_ola.p, b->pkts_ola.p, np * sizeof(VpzPktOla), st, err))) return rc;
-  if ((rc = dev::h2d(b->d_items.p, b->items.p, b->items.n * sizeof(VpzOlaItem), st, err))) return rc;
+  {
+    // K3 work items: the ones of 256 / 2048 mono / stereo setups first (fast kernel), the rest behind them
+    if (!b->items_sorted.reserve(b->items.n + 1)) return VPZ_E_NOMEM;
+    std::vector<uint8_t> fast_slot(b->slots.size());
+    for (size_t i = 0; i < b->slots.size(); i++) fast_slot[i] = k3_fast(ctx, b->slots[i]) ? 1 : 0;
+    size_t nf = 0;
+    for (size_t i = 0; i < b->items.n; i++) nf += fast_slot[b->items.p[i].setup_slot];
+    size_t a = 0, g = nf;
+    for (size_t i = 0; i < b->items.n; i++) {
+      const VpzOlaItem& it = b->items.p[i];
+      b->items_sorted.p[fast_slot[it.setup_slot] ? a++ : g++] = it;
+    }
+    b->items_sorted.n = b->items.n;
+    b->n_items_fast = (uint32_t)nf;
+  }
+  if ((rc = dev::h2d(b->d_items.p, b->items_sorted.p, b->items.n * sizeof(VpzOlaItem), st, err))) return rc;
   if (!b->h_setups.reserve(b->slots.size() + 1)) return VPZ_E_NOMEM;
   b->h_setups.n = 0;
   for (vpz_setup* s : b->slots) b->h_setups.p[b->h_setups.n++] = s->d_blob;
@@ -594,15 +645,22 @@ int batch_decode(vpz_batch* b, int clip, int out16) {
   int rc;
   b->launches = 0;
   dev::event_record(ctx->ev[0], st);
-  bool fast = true, gather = true;
+  // one zeroed work-stealing word per launch of this pass: K1a simple 0 / full 1, K1b gather 2 / general 3,
+  // K3 fast 4 / generic 5
+  if ((rc = dev::fill(ctx->d_counter, 0, 32, st, err))) return rc;
   uint32_t k1w = 0, k1g = 0, k3f = 0, k1seg = 0;
+  int gen_channels = 1;
   for (vpz_setup* s : b->slots) {
-    fast = fast && s->fast_sizes;
-    gather = gather && s->gather_ok;
-    k1g = std::max(k1g, s->k1g_words);
-    k1seg = std::max(k1seg, s->k1g_seg_stride);
-    k1w = std::max(k1w, s->k1_words_per_warp);
-    k3f = std::max(k3f, s->k3_floats_per_ch);
+    if (k1_class(ctx, s) == 0) {
+      k1g = std::max(k1g, s->k1g_words);
+      k1seg = std::max(k1seg, s->k1g_seg_stride);
+    } else {
+      k1w = std::max(k1w, s->k1_words_per_warp);
+    }
+    if (!k3_fast(ctx, s)) {
+      k3f = std::max(k3f, s->k3_floats_per_ch);
+      gen_channels = std::max(gen_channels, s->host.id.channels);
+    }
   }
   if (!b->synthetic && np) {
     K1Params p;
@@ -612,32 +670,44 @@ int batch_decode(vpz_batch* b, int clip, int out16) {
     p.res = static_cast<VpzPktRes*>(b->d_res.p);
     p.setups = static_cast<const uint32_t* const*>(b->d_setups.p);
     p.spec = static_cast<float*>(b->d_spec.p);
-    p.n_pkts = (uint32_t)np;
-    p.counter = ctx->d_counter;
-    p.gather_ok = gather ? 1 : 0;
-    if (gather) k1w = k1g;   // the gather path needs only its index tables
-    p.smem_words_per_warp = k1w;
-    p.seg_stride = k1seg;
     p.rec = static_cast<uint32_t*>(b->d_rec.p);
     p.ent = static_cast<uint16_t*>(b->d_ent.p);
-    p.order = static_cast<const uint32_t*>(b->d_order.p);
     p.dbg = b->dbg;
     const bool debug = b->dbg.hdr != nullptr;
-    // K1a: one lane per packet, 4 warps per CTA
-    size_t a_blocks = std::min<size_t>((np + 127) / 128, (size_t)16 * dev::sm_count());
-    if ((rc = dev::launch_k1a(p, debug, (int)std::max<size_t>(1, a_blocks), st, err))) return rc;
-    b->launches++;
-    ctx->kernel_launches++;
+    const uint32_t* order = static_cast<const uint32_t*>(b->d_order.p);
+    const uint32_t n0 = b->n_class[0], n1 = b->n_class[1], n2 = b->n_class[2];
+    // K1a: one lane per packet, 4 warps per CTA; the simple variant for classes 0 and 1, the full one for 2
+    for (int full = 0; full < 2; full++) {
+      const uint32_t cnt = full ? n2 : n0 + n1;
+      if (!cnt) continue;
+      p.order = order + (full ? n0 + n1 : 0);
+      p.n_pkts = cnt;
+      p.counter = ctx->d_counter + full;
+      const size_t a_blocks = std::min<size_t>(((size_t)cnt + 127) / 128, (size_t)16 * dev::sm_count());
+      if ((rc = dev::launch_k1a(p, debug, full != 0, (int)std::max<size_t>(1, a_blocks), st, err))) return rc;
+      b->launches++;
+      ctx->kernel_launches++;
+    }
     dev::event_record(ctx->ev[1], st);
     // K1b: persistent CTAs of 4 warps fed by a counter; gather path = one warp per packet (shared
     // memory per warp), general path = one CTA per packet
     const int warps = 4;
-    size_t smem_block = (size_t)k1w * 4 * (gather ? warps : 1) + (gather ? 1024 : 0);   // + the dB table
-    size_t per_sm = std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem_block + 1024)));
-    size_t blocks = std::min<size_t>(gather ? (np + warps - 1) / warps : np, per_sm * (size_t)dev::sm_count());
-    if ((rc = dev::launch_k1b(p, debug, (int)std::max<size_t>(1, blocks), warps, st, err))) return rc;
-    b->launches++;
-    ctx->kernel_launches++;
+    for (int general = 0; general < 2; general++) {
+      const uint32_t cnt = general ? n1 + n2 : n0;
+      if (!cnt) continue;
+      p.order = order + (general ? n0 : 0);
+      p.n_pkts = cnt;
+      p.counter = ctx->d_counter + 2 + general;
+      p.gather_ok = general ? 0 : 1;
+      p.smem_words_per_warp = general ? k1w : k1g;
+      p.seg_stride = k1seg;
+      const size_t smem_block = (size_t)p.smem_words_per_warp * 4 * (general ? 1 : warps) + (general ? 0 : 1024);   // + the dB table
+      const size_t per_sm = std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem_block + 1024)));
+      const size_t blocks = std::min<size_t>(general ? cnt : ((size_t)cnt + warps - 1) / warps, per_sm * (size_t)dev::sm_count());
+      if ((rc = dev::launch_k1b(p, debug, (int)std::max<size_t>(1, blocks), warps, st, err))) return rc;
+      b->launches++;
+      ctx->kernel_launches++;
+    }
   } else {
     dev::event_record(ctx->ev[1], st);
   }
@@ -649,28 +719,32 @@ int batch_decode(vpz_batch* b, int clip, int out16) {
     p.spec = static_cast<const float*>(b->d_spec.p);
     p.pkts = static_cast<const VpzPktOla*>(b->d_pkts_ola.p);
     p.res = b->synthetic ? nullptr : static_cast<const VpzPktRes*>(b->d_res.p);
-    p.items = static_cast<const VpzOlaItem*>(b->d_items.p);
     p.setups = static_cast<const uint32_t* const*>(b->d_setups.p);
     p.pcm = static_cast<float*>(b->d_pcm.p);
     p.clip_first = static_cast<uint32_t*>(b->d_clip.p);
-    p.n_items = (uint32_t)b->items.n;
-    p.counter = ctx->d_counter + 1;
     p.clip = clip ? 1 : 0;
     p.dbg_imdct = b->dbg_imdct;
     p.out16 = out16 ? 1 : 0;
-    if (fast && b->max_channels <= 2) {
+    const VpzOlaItem* items = static_cast<const VpzOlaItem*>(b->d_items.p);
+    if (b->n_items_fast) {
+      p.items = items;
+      p.n_items = b->n_items_fast;
+      p.counter = ctx->d_counter + 4;
       if ((rc = dev::launch_k3_streams(p, st, err))) return rc;
-    } else if (out16) {
-      err = "16-bit output is only on the 256/2048 mono/stereo IMDCT path";
-      return VPZ_E_UNSUPPORTED;
-    } else {
-      int ncb = std::min(2, b->max_channels);
-      // descriptors (K3_DESC_FLOATS) + per channel slot the Stockham buffers and the three D half-slots
-      size_t k3_smem = ((size_t)ncb * k3f + 384) * 4;
-      if ((rc = dev::launch_k3(p, ncb, k3_smem, st, err))) return rc;
+      b->launches++;
+      ctx->kernel_launches++;
     }
-    b->launches++;
-    ctx->kernel_launches++;
+    if (b->items.n > b->n_items_fast) {
+      p.items = items + b->n_items_fast;
+      p.n_items = (uint32_t)(b->items.n - b->n_items_fast);
+      p.counter = ctx->d_counter + 5;
+      const int ncb = std::min(2, gen_channels);
+      // descriptors (K3_DESC_FLOATS) + per channel slot the Stockham buffers and the three D half-slots
+      const size_t k3_smem = ((size_t)ncb * k3f + 384) * 4;
+      if ((rc = dev::launch_k3(p, ncb, k3_smem, st, err))) return rc;
+      b->launches++;
+      ctx->kernel_launches++;
+    }
   }
   dev::event_record(ctx->ev[3], st);
   b->decoded = true;

@@ -28,6 +28,7 @@ struct vpz_setup {
   uint32_t k1_words_per_warp = 0;   // shared memory K1b needs per warp
   uint32_t rec_words = 0;           // size of one packet's symbol record (K1a -> K1b)
   bool gather_ok = false;           // K1b gather path applies (mono/stereo, residue 1/2, dims divide the partition)
+  bool k1a_full = false;            // needs the K1a variant that walks floor 0 / several submaps
   uint32_t k1g_words = 0;           // shared memory of the gather path per warp (words)
   uint32_t k1g_seg_stride = 0;      // words of the floor segment table per channel (4 per post + flat tail)
   uint32_t k3_floats_per_ch = 0;    // shared memory K3 needs per channel (generic layout)
@@ -72,6 +73,7 @@ struct vpz_ctx {
   int ola_chunk = 63;   // packets per K3 work item (+ the seed packet)
   bool ola_chunk_set = false;   // set by the user: do not adapt it to the batch size (pick_ola_chunk)
   int k1_warps = 4;
+  int force_general = 0;   // tests: 1 = every packet through the general K1b and the generic K3, 2 = also the full K1a
   std::multimap<uint64_t, vpz_setup*> setups;
   std::vector<vpz_setup*> recent;     // setups the context itself holds a reference on (LRU, 64)
   uint32_t* d_counter = nullptr;
@@ -177,8 +179,14 @@ struct vpz_batch {
   uint64_t total_floats = 0, spec_floats = 0;
   uint64_t payload_bytes = 0;
   uint64_t rec_words = 0, ent_total = 0;      // symbol records / entry indices of all packets
-  vpz::HostBuf<uint32_t> order;               // K1a packet order (by (setup, block size), then byte length)
-  std::vector<uint32_t> sort_key;             // per packet: group << 13 | length key, written while the batch is filled
+  vpz::HostBuf<uint32_t> order;               // K1 packet order (by kernel class, (setup, block size), then byte length)
+  std::vector<uint32_t> sort_key;             // per packet: (setup slot * 2 + short) << 13 | length key, written while the batch is filled
+  // Kernel paths are chosen per SETUP, not per batch: the order array is cut into three classes
+  //   0: simple K1a + gather K1b   1: simple K1a + general K1b   2: full K1a + general K1b
+  // and the K3 work items into fast (256 / 2048, <= 2 channels) and generic ones (items_sorted).
+  uint32_t n_class[3] = {0, 0, 0};
+  vpz::HostBuf<VpzOlaItem> items_sorted;
+  uint32_t n_items_fast = 0;
   vpz::DevBuf d_rec, d_ent, d_order;
   int max_channels = 1;
   bool uploaded = false, synthetic = false, decoded = false;
@@ -214,4 +222,9 @@ extern double g_trace_ms[4];   // VPZ_TRACE: host milliseconds inside batch_uplo
 int batch_upload(vpz_batch* b);
 int batch_decode(vpz_batch* b, int clip, int out16 = 0);   // out16: 16-bit PCM (fast IMDCT kernel only)
 int batch_fetch_clip(vpz_batch* b);
+void batch_drop_slots(vpz_batch* b);   // releases the setup references the batch's slots hold
 }  // namespace vpz
+
+// First statement of every extern "C" entry point that may touch the device: the CUDA current device
+// is per host thread, and a process may hold one context per GPU.
+#define VPZ_USE(ctx) vpz::dev::make_current((ctx)->device)

@@ -212,7 +212,7 @@ VPZ_DEV int k1_unit_entries(int rtype, int psize, int dims) {
 // =============================================================================================
 // K1a: one lane decodes one packet
 // =============================================================================================
-template <bool DEBUG>
+template <bool DEBUG, bool FULL>
 VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   const VpzPktIn pk = P.pkts[pkt_idx];
   const uint32_t* blob = P.setups[pk.setup_slot];
@@ -704,12 +704,12 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
 
   // ---- floor line render + dB multiply + store (Floor1.cs:222-268, 372-397) -------------------
   // RenderLineMulti in closed form: after k steps of the DDA  y = y0 + sy * floor(k * |dy| / adx)
-  // (base*k + sy*floor(k*rem/adx) with |dy| = |base|*adx + rem).  k * |dy| < 2^24, so the quotient
-  // comes from one float multiply by 1/adx plus an exact integer correction of +-1.  Lanes walk the
-  // bins K1B_THREADS at a time; every thread keeps its own (monotone) segment cursor.
+  // (base*k + sy*floor(k*rem/adx) with |dy| = |base|*adx + rem).  This path is the rare one: a plain
+  // integer division per bin.  Lanes walk the bins K1B_THREADS at a time; every thread keeps its own
+  // (monotone) segment cursor.
   const float* db = reinterpret_cast<const float*>(blob + H->db_off);
   float* out = P.spec + pk.spec_off;
-  uint32_t* sg = reinterpret_cast<uint32_t*>(ustart);   // per segment: x0 | x1 << 16, y0 | (|dy| << 16), sy, 1/adx
+  uint32_t* sg = reinterpret_cast<uint32_t*>(ustart);   // per segment: x0 | x1 << 16, y0 | (|dy| << 16), sign
   for (int ch = 0; ch < C; ch++) {
     if (!((own_mask >> ch) & 1u)) continue;  // Mapping.cs:185-194: silent channel, K3 sees zeros
     const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
@@ -719,17 +719,15 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
       const uint32_t p0 = seg[1 + s], p1 = seg[2 + s];
       const int x0 = (int)(p0 & 0xffffu), y0 = (int)(short)(p0 >> 16);
       const int x1 = (int)(p1 & 0xffffu), y1 = (int)(short)(p1 >> 16);
-      const int dy = y1 - y0, adx = x1 - x0;
+      const int dy = y1 - y0;
       sg[4 * s] = (uint32_t)x0 | ((uint32_t)x1 << 16);
       sg[4 * s + 1] = (uint32_t)(y0 & 0xffff) | ((uint32_t)(dy < 0 ? -dy : dy) << 16);
       sg[4 * s + 2] = dy < 0 ? 1u : 0u;
-      sg[4 * s + 3] = adx > 1 ? 0xffffffffu / (uint32_t)adx + 1u : 0u;   // ceil(2^32 / adx); adx = 1 has no remainder steps
     }
     __syncthreads();
     if (nseg == 0) continue;
     int si = 0;
     uint32_t w0 = sg[0], w1 = sg[1], w2 = sg[2];
-    float inv = reinterpret_cast<float*>(sg)[3];
     const int xend = (int)(sg[4 * (nseg - 1)] >> 16);   // the last segment ends at `half` (or where the floor ends)
     for (int x = tid; x < xend; x += K1B_THREADS) {
       while (x >= (int)(w0 >> 16) && si + 1 < nseg) {
@@ -737,14 +735,10 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
         w0 = sg[4 * si];
         w1 = sg[4 * si + 1];
         w2 = sg[4 * si + 2];
-        inv = reinterpret_cast<float*>(sg)[4 * si + 3];
       }
       const int x0 = (int)(w0 & 0xffffu), adx = (int)(w0 >> 16) - x0;
       const int y0 = (int)(short)(w1 & 0xffffu), ady = (int)(w1 >> 16);
-      const int t = (x - x0) * ady;
-      int q = (int)((float)t * inv);
-      const int r = t - q * adx;
-      q += r < 0 ? -1 : (r >= adx ? 1 : 0);
+      const int q = adx > 0 ? ((x - x0) * ady) / adx : 0;
       int y = w2 ? y0 - q : y0 + q;
       y = y < 0 ? 0 : (y > 255 ? 255 : y);  // the reference reads the table unchecked (quirk Q2)
       out[ch * half + x] = __fmul_rn(RES_AT(ch, x), VPZ_LDG(db + y));
@@ -1221,7 +1215,7 @@ VPZ_DEV void k1b_cta_loop(const K1Params& P, uint32_t* smem, uint32_t* s_idx) {
     uint32_t* my = smem + 256 + (size_t)warp * P.smem_words_per_warp;
     for (;;) {
       uint32_t idx = 0;
-      if (lane == 0) idx = atomicAdd(P.counter + 2, 1u);
+      if (lane == 0) idx = atomicAdd(P.counter, 1u);
       idx = __shfl_sync(0xffffffffu, idx, 0);
       if (idx >= P.n_pkts) break;
       // same order as K1a: grouped by (setup, block size), so the warps resident on an SM run the same
@@ -1231,11 +1225,11 @@ VPZ_DEV void k1b_cta_loop(const K1Params& P, uint32_t* smem, uint32_t* s_idx) {
   } else {
     for (;;) {
       __syncthreads();
-      if (tid == 0) *s_idx = atomicAdd(P.counter + 2, 1u);
+      if (tid == 0) *s_idx = atomicAdd(P.counter, 1u);
       __syncthreads();
       const uint32_t idx = *s_idx;
       if (idx >= P.n_pkts) break;
-      k1b_build_packet_general<DEBUG>(P, idx, smem, tid);
+      k1b_build_packet_general<DEBUG>(P, P.order ? P.order[idx] : idx, smem, tid);
     }
   }
 }

@@ -239,13 +239,16 @@ VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, c
 // Any power-of-two N in 64..8192: radix-2 Stockham autosort between two shared buffers of 2*H
 // floats (re plane, im plane), 64 threads.
 VPZ_DEV void fft_generic_to_D(const float* X, float* A, float* B, const K3D& D, const cpx* tw, const cpx* roots,
-                              int log2H, int t) {
+                              int log2H, int t, bool active) {
+  // every thread of the CTA takes every barrier in here; `active` only predicates the memory traffic
+  // (a channel slot without work in this pass idles through the same barriers)
   const int H = 1 << log2H, M = 2 * H;
-  for (int n = t; n < H; n += K3_THREADS_PER_CH) {
-    cpx z = cmul(cpx{VPZ_LDG(X + 2 * n), VPZ_LDG(X + M - 1 - 2 * n)}, VPZ_LDG(tw + n));
-    A[n] = z.x;
-    A[H + n] = z.y;
-  }
+  if (active)
+    for (int n = t; n < H; n += K3_THREADS_PER_CH) {
+      cpx z = cmul(cpx{VPZ_LDG(X + 2 * n), VPZ_LDG(X + M - 1 - 2 * n)}, VPZ_LDG(tw + n));
+      A[n] = z.x;
+      A[H + n] = z.y;
+    }
   __syncthreads();
   float* src = A;
   float* dst = B;
@@ -253,29 +256,31 @@ VPZ_DEV void fft_generic_to_D(const float* X, float* A, float* B, const K3D& D, 
   // stride st = 1 << s; natural order in, natural order out after log2H stages.
   for (int s = 0; s < log2H; s++) {
     const int st = 1 << s, m = H >> (s + 1);
-    for (int i = t; i < H / 2; i += K3_THREADS_PER_CH) {
-      int p = i >> s, q = i & (st - 1);
-      cpx w = VPZ_LDG(roots + (p << s));  // exp(-2 pi i p / ns)
-      int ia = q + st * p, ib = q + st * (p + m);
-      cpx c0 = cpx{src[ia], src[H + ia]};
-      cpx c1 = cpx{src[ib], src[H + ib]};
-      cpx u = cadd(c0, c1), d = cmul(csub(c0, c1), w);
-      int oa = q + st * 2 * p, ob = oa + st;
-      dst[oa] = u.x;
-      dst[H + oa] = u.y;
-      dst[ob] = d.x;
-      dst[H + ob] = d.y;
-    }
+    if (active)
+      for (int i = t; i < H / 2; i += K3_THREADS_PER_CH) {
+        int p = i >> s, q = i & (st - 1);
+        cpx w = VPZ_LDG(roots + (p << s));  // exp(-2 pi i p / ns)
+        int ia = q + st * p, ib = q + st * (p + m);
+        cpx c0 = cpx{src[ia], src[H + ia]};
+        cpx c1 = cpx{src[ib], src[H + ib]};
+        cpx u = cadd(c0, c1), d = cmul(csub(c0, c1), w);
+        int oa = q + st * 2 * p, ob = oa + st;
+        dst[oa] = u.x;
+        dst[H + oa] = u.y;
+        dst[ob] = d.x;
+        dst[H + ob] = d.y;
+      }
     __syncthreads();
     float* tmp = src;
     src = dst;
     dst = tmp;
   }
-  for (int p = t; p < H; p += K3_THREADS_PER_CH) {
-    cpx c = cmul(cpx{src[p], src[H + p]}, VPZ_LDG(tw + p));
-    *k3_dp(D, 2 * p) = c.x;
-    *k3_dp(D, M - 1 - 2 * p) = -c.y;
-  }
+  if (active)
+    for (int p = t; p < H; p += K3_THREADS_PER_CH) {
+      cpx c = cmul(cpx{src[p], src[H + p]}, VPZ_LDG(tw + p));
+      *k3_dp(D, 2 * p) = c.x;
+      *k3_dp(D, M - 1 - 2 * p) = -c.y;
+    }
   __syncthreads();
 }
 
@@ -423,6 +428,7 @@ VPZ_DEV bool k3_emit(const float* Dc_hm, const float* Dc_lo, const float* Dp_lo,
 // A[2*Hmax] B[2*Hmax] and the D slots Hi[Mmax/2] Lo0[Mmax/2] Lo1[Mmax/2] (+16 to stagger channel bases).
 // A CTA = NCB channel slots x 64 threads walks one work item; streams with more channels than slots are
 // swept NCB channels at a time.
+template <bool OUT16>
 VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_raw, int NCB) {
   const VpzOlaItem it = item;  // the item lives in global memory: read it once
   const uint32_t* blob = P.setups[it.setup_slot];
@@ -490,12 +496,7 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_
         // overlap-add: its D buffer is cleared instead of transformed
         if (ch_ok && !exec)
           for (int i = t64; i < M; i += K3_THREADS_PER_CH) *k3_dp(D, i) = 0.f;
-        // every thread must take the barriers inside
-        if (exec) {
-          fft_generic_to_D(X, A, B, D, tw, roots, lgN - 2, t64);
-        } else {
-          for (int s = 0; s < lgN - 2 + 2; s++) __syncthreads();
-        }
+        fft_generic_to_D(X, A, B, D, tw, roots, lgN - 2, t64, exec);
         // D buffers of the sweep are complete here (the transform ends with a barrier)
 
         if (P.dbg_imdct && ch_ok) {
@@ -508,17 +509,19 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_
           const int count = (int)pk.right_start - ls;
           const int L = prev_re - prev_rs;             // StreamDecoder.cs:654
           const float* w = (pk.flags & VPZ_OLA_LEFT1) ? slope1 : slope0;
-          float* outp = P.pcm + it.out_base + (size_t)pk.out_off * C + c0;
+          // element offset of the packet's first sample; an s16 element is 2 bytes (k3_put)
+          const size_t eoff = (size_t)it.out_base + (size_t)pk.out_off * C + c0;
+          float* outp = OUT16 ? reinterpret_cast<float*>(reinterpret_cast<int16_t*>(P.pcm) + eoff) : P.pcm + eoff;
           const float* Dc_hm = smem + SCR - h;                       // channel slot 0; + cg * per_ch for the others
           const float* Dc_lo = smem + SCR + HS + parity * HS;
           const float* Dp_lo = smem + SCR + HS + (parity ^ 1) * HS;
           bool clipped;
           if (ncur == 2)
-            clipped = P.clip ? k3_emit<2, true>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads)
-                             : k3_emit<2, false>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads);
+            clipped = P.clip ? k3_emit<2, true, OUT16>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads)
+                             : k3_emit<2, false, OUT16>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads);
           else
-            clipped = P.clip ? k3_emit<1, true>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads)
-                             : k3_emit<1, false>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads);
+            clipped = P.clip ? k3_emit<1, true, OUT16>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads)
+                             : k3_emit<1, false, OUT16>(Dc_hm, Dc_lo, Dp_lo, per_ch, M, prevM, ls, count, prev_rs, L, w, outp, C, tid, nthreads);
           // per packet: 0 when any sample was clamped (HasClipped), else stays 0xffffffff
           if (P.clip_first && clipped) atomicMin(P.clip_first + gp, 0u);
         }
@@ -536,6 +539,7 @@ VPZ_DEV void k3_run_item(const K3Params& P, const VpzOlaItem& item, float* smem_
 }
 
 // CTA main loop: work items are handed out by a global counter.
+template <bool OUT16>
 VPZ_DEV void k3_cta_loop(const K3Params& P, float* smem_raw, int ncb) {
   uint32_t* s_next = reinterpret_cast<uint32_t*>(smem_raw) + (K3_DESC_FLOATS - 1);
   for (;;) {
@@ -544,6 +548,6 @@ VPZ_DEV void k3_cta_loop(const K3Params& P, float* smem_raw, int ncb) {
     __syncthreads();
     const uint32_t idx = *s_next;
     if (idx >= P.n_items) break;
-    k3_run_item(P, P.items[idx], smem_raw, ncb);
+    k3_run_item<OUT16>(P, P.items[idx], smem_raw, ncb);
   }
 }

@@ -679,6 +679,7 @@ int find_next(vpz_reader* r) {
 extern "C" {
 
 int vpz_reader_open_memory(vpz_ctx* ctx, const uint8_t* data, size_t len, int copy, vpz_reader** out) {
+  if (ctx) VPZ_USE(ctx);
   if (!ctx || !out || (!data && len)) return VPZ_E_ARGUMENT;
   *out = nullptr;
   vpz_reader* r = new (std::nothrow) vpz_reader;
@@ -704,7 +705,11 @@ int vpz_reader_open_memory(vpz_ctx* ctx, const uint8_t* data, size_t len, int co
   return VPZ_OK;
 }
 
-void vpz_reader_close(vpz_reader* r) { delete r; }
+void vpz_reader_close(vpz_reader* r) {
+  if (!r) return;
+  VPZ_USE(r->ctx);
+  delete r;
+}
 
 int vpz_reader_stream_count(const vpz_reader* r) { return r ? (int)r->decs.size() : VPZ_E_ARGUMENT; }
 int vpz_reader_stream_index(const vpz_reader* r) { return r ? r->cur : VPZ_E_ARGUMENT; }
@@ -720,7 +725,11 @@ int vpz_reader_switch_stream(vpz_reader* r, int index) {  // VorbisReader.Switch
   return (nd->channels() != od->channels() || nd->setup->host.id.sample_rate != od->setup->host.id.sample_rate) ? 1 : 0;
 }
 
-int vpz_reader_find_next_stream(vpz_reader* r) { return r ? find_next(r) : VPZ_E_ARGUMENT; }
+int vpz_reader_find_next_stream(vpz_reader* r) {
+  if (!r) return VPZ_E_ARGUMENT;
+  VPZ_USE(r->ctx);
+  return find_next(r);
+}
 int vpz_reader_can_seek(const vpz_reader* r) { return r ? (r->dec()->ls->can_seek() ? 1 : 0) : VPZ_E_ARGUMENT; }
 
 int vpz_reader_channels(const vpz_reader* r) { return r ? r->dec()->channels() : VPZ_E_ARGUMENT; }
@@ -771,15 +780,19 @@ const char* vpz_reader_comment(const vpz_reader* r, int i, int* len) {
 
 int vpz_reader_read(vpz_reader* r, float* buf, int nfloats) {
   if (!r) return VPZ_E_ARGUMENT;
+  VPZ_USE(r->ctx);
   StreamDec* d = r->dec();
   return stream_read(d, buf, nfloats, nfloats / d->channels(), 0, true);
 }
 int vpz_reader_read_planar(vpz_reader* r, float* buf, int nfloats, int samples_to_read, int channel_stride) {
   if (!r || samples_to_read < 0) return VPZ_E_ARGUMENT;
+  VPZ_USE(r->ctx);
   return stream_read(r->dec(), buf, nfloats, samples_to_read, channel_stride, false);
 }
 int vpz_reader_seek(vpz_reader* r, int64_t sample_position, int origin) {
-  return r ? stream_seek(r->dec(), sample_position, origin) : VPZ_E_ARGUMENT;
+  if (!r) return VPZ_E_ARGUMENT;
+  VPZ_USE(r->ctx);
+  return stream_seek(r->dec(), sample_position, origin);
 }
 int vpz_reader_set_lookahead(vpz_reader* r, int packets) {
   if (!r || packets < 0) return VPZ_E_ARGUMENT;
@@ -833,6 +846,7 @@ struct BulkJob {
 static int64_t decode_files_impl(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, int clip,
                                  float* dst, size_t dst_floats, int64_t* sample_counts, int out16) {
   if (!ctx || (n && (!datas || !lens))) return VPZ_E_ARGUMENT;
+  VPZ_USE(ctx);
   if (!ctx->pool) {
     unsigned t = ctx->host_threads > 0 ? (unsigned)ctx->host_threads
                                        : std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
@@ -1013,6 +1027,7 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
                             const uint32_t* file_of, const int64_t* start, const int32_t* count, int clip, float* dst,
                             size_t dst_floats, int64_t* dst_offsets, int32_t* got) {
   if (!ctx || !datas || !lens || (n && (!file_of || !start || !count))) return VPZ_E_ARGUMENT;
+  VPZ_USE(ctx);
   if (!ctx->pool) {
     unsigned t = ctx->host_threads > 0 ? (unsigned)ctx->host_threads
                                        : std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));

@@ -182,6 +182,12 @@ int parse_book(BitReader& br, HostBook& bk, std::string& err) {
   }
   bk.map_type = (int)br.read(4);
   if (bk.map_type == 0) return VPZ_OK;
+  if (bk.dims < 1) {
+    // a lookup of zero dimensions: lookup1_values divides by it (Codebook.cs:290-298) and every residue /
+    // floor that names the book divides the partition size by it
+    err = "VQ codebook with zero dimensions";
+    return VPZ_E_INVALID_DATA;
+  }
   if (bk.map_type > 2) {
     // the reference builds no table for other values and faults on first use; we refuse early
     err = "codebook lookup type > 2";
@@ -332,6 +338,7 @@ int parse_floor1(BitReader& br, int nbooks, VpzFloor1& f, std::string& err) {
   static const uint16_t range_lookup[4] = {256, 128, 86, 64};
   static const uint8_t ybits_lookup[4] = {8, 7, 7, 6};
   memset(&f, 0, sizeof(f));
+  f.floor_type = 1;
   int max_class = -1;
   f.partitions = (uint8_t)br.read(5);
   for (int i = 0; i < f.partitions; i++) {

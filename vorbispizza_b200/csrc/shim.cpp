@@ -46,11 +46,12 @@ int vpz_ctx_create(int device, vpz_ctx** out) {
   if (!out) return VPZ_E_ARGUMENT;
   *out = nullptr;
   std::string err;
-  int rc = dev::init(device, err);
+  int resolved = device;
+  int rc = dev::init(device, &resolved, err);
   if (rc) return rc;
   vpz_ctx* c = new (std::nothrow) vpz_ctx;
   if (!c) return VPZ_E_NOMEM;
-  c->device = device;
+  c->device = resolved;
   c->stream = dev::stream_create();
   c->copy_stream = dev::stream_create();
   for (int i = 0; i < 4; i++) c->ev[i] = dev::event_create();
@@ -65,6 +66,7 @@ int vpz_ctx_create(int device, vpz_ctx** out) {
 
 void vpz_ctx_destroy(vpz_ctx* c) {
   if (!c) return;
+  VPZ_USE(c);
   for (int i = 0; i < 3; i++) {
     if (c->bulk[i]) vpz_batch_destroy(c->bulk[i]);
     c->bulk[i] = nullptr;
@@ -89,6 +91,7 @@ void vpz_ctx_destroy(vpz_ctx* c) {
 
 int vpz_ctx_mark(vpz_ctx* c, int slot) {
   if (!c || slot < 0 || slot >= 8) return VPZ_E_ARGUMENT;
+  VPZ_USE(c);
   if (!c->marks[slot]) c->marks[slot] = dev::event_create();
   if (!c->marks[slot]) return VPZ_E_CUDA;
   dev::event_record(c->marks[slot], c->stream);
@@ -97,6 +100,7 @@ int vpz_ctx_mark(vpz_ctx* c, int slot) {
 
 float vpz_ctx_elapsed_ms(vpz_ctx* c, int a, int b) {
   if (!c || a < 0 || a >= 8 || b < 0 || b >= 8 || !c->marks[a] || !c->marks[b]) return -1.f;
+  VPZ_USE(c);
   if (dev::event_sync(c->marks[b], c->last_error)) return -1.f;
   return dev::event_elapsed_ms(c->marks[a], c->marks[b]);
 }
@@ -118,6 +122,11 @@ int vpz_ctx_set(vpz_ctx* c, const char* key, int value) {
   } else if (!strcmp(key, "bulk_group")) {
     if (value < 1 || value > (1 << 20)) return VPZ_E_ARGUMENT;
     c->bulk_group = value;
+  } else if (!strcmp(key, "force_general")) {
+    // test knob: 1 routes every packet through the general spectrum kernel and the generic IMDCT kernel,
+    // 2 also through the full symbol kernel (floor 0 / multi-submap walk); 0 = per-setup choice
+    if (value < 0 || value > 2) return VPZ_E_ARGUMENT;
+    c->force_general = value;
   } else if (!strcmp(key, "host_threads")) {
     if (value < 0 || value > 256 || c->pool) return VPZ_E_ARGUMENT;  // before the first bulk call
     c->host_threads = value;
@@ -130,9 +139,14 @@ int vpz_ctx_set(vpz_ctx* c, const char* key, int value) {
 int vpz_setup_create(vpz_ctx* ctx, const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt, size_t setup_len,
                      vpz_setup** out) {
   if (!ctx || !id_pkt || !setup_pkt || !out) return VPZ_E_ARGUMENT;
+  VPZ_USE(ctx);
   return setup_create(ctx, id_pkt, id_len, setup_pkt, setup_len, out);
 }
-void vpz_setup_release(vpz_setup* s) { setup_release(s); }
+void vpz_setup_release(vpz_setup* s) {
+  if (!s) return;
+  VPZ_USE(s->ctx);
+  setup_release(s);
+}
 
 int vpz_setup_get_info(const vpz_setup* s, vpz_setup_info* info) {
   if (!s || !info) return VPZ_E_ARGUMENT;
@@ -183,6 +197,8 @@ int vpz_batch_create(vpz_ctx* ctx, vpz_batch** out) {
 }
 void vpz_batch_destroy(vpz_batch* b) {
   if (!b) return;
+  VPZ_USE(b->ctx);
+  batch_drop_slots(b);
   if (b->owned_setup) setup_release(b->owned_setup);
   delete b;
 }
@@ -195,7 +211,8 @@ int vpz_batch_reset(vpz_batch* b) {
   b->pkts_ola.clear();
   b->items.clear();
   b->runs.clear();
-  b->slots.clear();
+  VPZ_USE(b->ctx);
+  batch_drop_slots(b);
   b->total_floats = b->spec_floats = b->payload_bytes = 0;
   b->rec_words = b->ent_total = 0;
   b->max_channels = 1;
@@ -232,10 +249,19 @@ int64_t vpz_batch_total_floats(const vpz_batch* b) { return b ? (int64_t)b->tota
 int64_t vpz_batch_total_packets(const vpz_batch* b) { return b ? (int64_t)b->pkts_ola.n : VPZ_E_ARGUMENT; }
 int64_t vpz_batch_total_bytes(const vpz_batch* b) { return b ? (int64_t)b->payload_bytes : VPZ_E_ARGUMENT; }
 
-int vpz_batch_upload(vpz_batch* b) { return b ? batch_upload(b) : VPZ_E_ARGUMENT; }
-int vpz_batch_decode(vpz_batch* b, int clip) { return b ? batch_decode(b, clip) : VPZ_E_ARGUMENT; }
+int vpz_batch_upload(vpz_batch* b) {
+  if (!b) return VPZ_E_ARGUMENT;
+  VPZ_USE(b->ctx);
+  return batch_upload(b);
+}
+int vpz_batch_decode(vpz_batch* b, int clip) {
+  if (!b) return VPZ_E_ARGUMENT;
+  VPZ_USE(b->ctx);
+  return batch_decode(b, clip);
+}
 int vpz_batch_sync(vpz_batch* b) {
   if (!b) return VPZ_E_ARGUMENT;
+  VPZ_USE(b->ctx);
   int rc = dev::stream_sync(b->ctx->stream, b->ctx->last_error);
   if (rc) return rc;
   if (b->decoded) {
@@ -250,6 +276,7 @@ int vpz_batch_sync(vpz_batch* b) {
 
 int vpz_batch_has_clipped(vpz_batch* b) {
   if (!b || !b->decoded) return VPZ_E_INVALID_OP;
+  VPZ_USE(b->ctx);
   int rc = batch_fetch_clip(b);
   if (rc) return rc;
   for (size_t i = 0; i < b->h_clip.n; i++)
@@ -266,6 +293,7 @@ const float* vpz_batch_device_pcm(const vpz_batch* b) { return b ? static_cast<c
 int vpz_batch_read_run(vpz_batch* b, int run, float* dst) {
   if (!b || !dst || run < 0 || (size_t)run >= b->runs.size()) return VPZ_E_ARGUMENT;
   if (!b->decoded) return VPZ_E_INVALID_OP;
+  VPZ_USE(b->ctx);
   const Run& r = b->runs[run];
   size_t n = (size_t)r.samples * r.setup->host.id.channels;
   int rc = dev::d2h(dst, static_cast<const float*>(b->d_pcm.p) + r.out_base, n * 4, b->ctx->stream, b->ctx->last_error);
@@ -276,6 +304,7 @@ int vpz_batch_read_run(vpz_batch* b, int run, float* dst) {
 int vpz_batch_read_all(vpz_batch* b, float* dst) {
   if (!b || !dst) return VPZ_E_ARGUMENT;
   if (!b->decoded) return VPZ_E_INVALID_OP;
+  VPZ_USE(b->ctx);
   int rc = dev::d2h(dst, b->d_pcm.p, b->total_floats * 4, b->ctx->stream, b->ctx->last_error);
   if (rc) return rc;
   return dev::stream_sync(b->ctx->stream, b->ctx->last_error);
@@ -297,6 +326,7 @@ int vpz_debug_decode_packet(vpz_ctx* ctx, vpz_setup* s, const uint8_t* pkt, size
                             int32_t* scalars, int32_t scalars_cap, int32_t* classes, int32_t classes_cap,
                             float* residue, float* spectrum, float* imdct) {
   if (!ctx || !s || !dump || (!pkt && len)) return VPZ_E_ARGUMENT;
+  VPZ_USE(ctx);
   memset(dump, 0, sizeof(*dump));
   dump->status = 1;
   PacketGeom g = s->host.packet_geometry(pkt, len);
@@ -378,6 +408,7 @@ int vpz_debug_decode_packet(vpz_ctx* ctx, vpz_setup* s, const uint8_t* pkt, size
 int vpz_synth_create(vpz_ctx* ctx, int channels, int log2_size0, int log2_size1, uint32_t n_streams,
                      uint32_t n_blocks, const uint8_t* flags, const float* spectra, vpz_batch** out) {
   if (!ctx || !flags || !spectra || !out || n_blocks < 2 || n_streams < 1) return VPZ_E_ARGUMENT;
+  VPZ_USE(ctx);
   vpz_setup* s = nullptr;
   int rc = setup_create_synthetic(ctx, channels, log2_size0, log2_size1, &s);
   if (rc) return rc;

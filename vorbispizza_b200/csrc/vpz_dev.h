@@ -43,7 +43,7 @@ struct VpzFloor1 {
   uint8_t ybits;
   uint8_t xcount;       // posts incl. the two end posts, <= 64
   uint16_t range;
-  uint16_t pad0;
+  uint16_t floor_type;  // 1 = floor 1 (this struct), 0 = floor 0 (the f0 part below; Floor0.cs)
   uint8_t part_class[32];
   uint8_t class_dim[16];
   uint8_t class_sub[16];
