@@ -332,7 +332,11 @@ static void residue_decode(vo_residue* r, const vo_book* books, vo_bits* br, con
         for (int ch = 0; ch < nch; ch++) {
           if (no_decode[ch]) continue;
           int idx = decode_scalar(cb, br, d);
-          if (idx >= 0 && idx < r->decode_map_len) { /* quirk Q8 */
+          /* quirk Q8: the reference accepts idx < decodeMap.Length (= partvals * dim, Residue0.cs:158) and
+           * then indexes decodeMap[idx * dim + k] (:175-176), which for idx >= partvals is an
+           * IndexOutOfRangeException out of Read.  There is no output to agree with; the oracle and the
+           * product both end the packet's residue decode at such a classword, like a failed one. */
+          if (idx >= 0 && idx < r->decode_map_len && idx < r->decode_map_len / (dim > 0 ? dim : 1)) {
             cache[ch * part_words + entry] = idx;
           } else {
             part = part_count;

@@ -409,3 +409,122 @@ def decode_files_parity(ctx, names, clip=True):
         off += cnt * s.channels
         assert_pcm_close(got, ref, "decode_files " + n)
     assert off == pcm.size
+
+
+# ---- generated streams (tests/synthvorbis.py): every setup shape the TestFiles do not have ---------------
+FLOOR0_RTOL = 2e-5   # floor 0 evaluates cos / sqrt / exp in fp32: library functions, not bit-reproducible
+
+
+def compare_stage_dump_tol(g, o, ch, what, rtol):
+    """compare_stage_dump with a relative tolerance on the spectrum (floor 0): integer stages and the
+    residue stay bit-exact."""
+    keep_g, keep_o = g["spectrum"], o["spectrum"]
+    fin = np.isfinite(keep_o)
+    assert np.array_equal(fin, np.isfinite(keep_g)), what + ": non-finite spectrum bins differ"
+    scale = np.maximum(np.abs(keep_o[fin]), 1e-30)
+    assert float((np.abs(keep_g[fin] - keep_o[fin]) / scale).max(initial=0.0)) <= rtol, what + ": spectrum (floor 0)"
+    g = dict(g)
+    o = dict(o)
+    g["spectrum"] = o["spectrum"] = np.zeros(1, np.float32)
+    ok = np.isfinite(o["imdct"]).all() and np.isfinite(g["imdct"]).all()
+    if ok:
+        scale = max(float(np.abs(o["imdct"]).max()), 1.0)
+        assert float(np.abs(g["imdct"] - o["imdct"]).max()) <= (IMDCT_RTOL + 40 * rtol) * scale + 1e-7, what + ": imdct"
+    g["imdct"] = o["imdct"] = np.zeros(1, np.float32)
+    compare_stage_dump(g, o, ch, what)
+
+
+def synth_stage_parity(ctx, shape, seed, n_packets=40, mean_len=120):
+    """Integer stages + residue (+ spectrum) of every generated packet, plus truncated variants."""
+    import synthvorbis as sv
+    st = sv.make_stream(seed, shape, n_packets=n_packets, mean_len=mean_len)
+    s = ob.OracleStream(st["ogg"])
+    setup = setup_for(ctx, s)
+    floor0 = any(f["type"] == 0 for f in st["info"]["floors"])
+    n = 0
+    try:
+        for i, p in enumerate(st["packets"]):
+            for v in (p, p[:max(len(p) * 2 // 3, 1)]):
+                o = s.dump_packet(v)
+                g = ctx.debug_decode_packet(setup, v, s.channels, s.block_sizes[1])
+                what = "%s seed %d packet %d len %d" % (shape, seed, i, len(v))
+                if floor0:
+                    compare_stage_dump_tol(g, o, s.channels, what, FLOOR0_RTOL)
+                else:
+                    compare_stage_dump(g, o, s.channels, what)
+                n += 1
+    finally:
+        ctx.release_setup(setup)
+    return n
+
+
+def assert_pcm_close_scaled(got, ref, what="", rtol=PCM_TOL):
+    """PCM of generated streams is not normalised to +-1: the 1e-5 bar applies relative to the peak."""
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    if got.size == 0:
+        return
+    scale = max(float(np.abs(ref).max()), 1.0)
+    err = float(np.abs(got - ref).max())
+    assert err <= rtol * scale, "%s: max abs err %.3g > %.1g x peak %.3g" % (what, err, rtol, scale)
+
+
+def synth_stream_parity(ctx, shape, seed, n_packets=40, clip=False, lookahead=7, eos_trim=0):
+    """A generated stream end to end: bulk decode (vpz_decode_files) and the reader's ReadSamples loop vs the
+    oracle's reader -- same counts, positions, PCM."""
+    import synthvorbis as sv
+    st = sv.make_stream(seed, shape, n_packets=n_packets, eos_trim=eos_trim)
+    data = st["ogg"]
+    s = ob.OracleStream(data)
+    s.set_clip(clip)
+    ref, _, fault = s.decode_all()
+    assert not fault
+    assert np.isfinite(ref).all(), "generated stream overflows in the oracle: not a usable fixture"
+    floor0 = any(f["type"] == 0 for f in st["info"]["floors"])
+    rtol = PCM_TOL + (40 * FLOOR0_RTOL if floor0 else 0.0)
+    pcm, counts = decode_files(ctx, [data], clip=clip)
+    assert counts[0] == ref.shape[0], (shape, seed, counts[0], ref.shape)
+    assert_pcm_close_scaled(pcm.reshape(-1, s.channels), ref, "%s seed %d bulk" % (shape, seed), rtol)
+    s2 = ob.OracleStream(data)
+    s2.set_clip(clip)
+    with VorbisReader(ctx, data, lookahead=lookahead) as r:
+        r.clip_samples = clip
+        ch = r.channels
+        a = np.zeros(4096 * ch, np.float32)
+        b = np.zeros(4096 * ch, np.float32)
+        total = 0
+        while True:
+            no = s2.read(a)
+            ng = r.lib.vpz_reader_read(r._h, b.ctypes.data, b.size)
+            assert ng == no, "%s seed %d: product %d oracle %d" % (shape, seed, ng, no)
+            assert r.sample_position == s2.sample_position and r.is_end_of_stream == s2.is_end_of_stream
+            if no <= 0:
+                break
+            assert_pcm_close_scaled(b[:ng * ch], a[:no * ch], "%s seed %d read" % (shape, seed), rtol * max(float(np.abs(ref).max()), 1.0))
+            total += no
+        assert total == ref.shape[0]
+    return total
+
+
+def synth_mixed_batch_parity(ctx, shape_seeds, n_packets=20, with_files=(), clip=False):
+    """One vpz_decode_files call over generated streams of different kernel classes plus TestFiles: the
+    per-setup path selection must give every stream the result it has when decoded alone."""
+    import synthvorbis as sv
+    datas, names = [], []
+    for shape, seed in shape_seeds:
+        datas.append(sv.make_stream(seed, shape, n_packets=n_packets)["ogg"])
+        names.append("%s/%d" % (shape, seed))
+    for n in with_files:
+        datas.append(load_file(n))
+        names.append(n)
+    pcm, counts = decode_files(ctx, datas, clip=clip)
+    off = 0
+    for name, d, cnt in zip(names, datas, counts):
+        s = ob.OracleStream(d)
+        s.set_clip(clip)
+        ref, _, _ = s.decode_all()
+        assert cnt == ref.shape[0], (name, cnt, ref.shape)
+        got = pcm[off:off + cnt * s.channels].reshape(-1, s.channels)
+        off += cnt * s.channels
+        rtol = PCM_TOL + (40 * FLOOR0_RTOL if name.startswith("floor0") else 0.0)
+        assert_pcm_close_scaled(got, ref, "mixed batch " + name, rtol)
+    assert off == pcm.size

@@ -126,7 +126,11 @@ int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream*, st
   static uint32_t s_idx;  // the emulator runs one block at a time
   emu::launch(1, K1B_THREADS, (size_t)p.smem_words_per_warp * 4 * (p.gather_ok ? warps : 1) + (p.gather_ok ? 1024 : 0), [&] {
     uint32_t* smem = (uint32_t*)emu::t_block->smem;
-    if (debug) k1b_cta_loop<true>(p, smem, &s_idx); else k1b_cta_loop<false>(p, smem, &s_idx);
+    if (p.gather_ok) {
+      if (debug) k1b_gather_loop<true>(p, smem); else k1b_gather_loop<false>(p, smem);
+    } else {
+      if (debug) k1b_general_loop<true>(p, smem, &s_idx); else k1b_general_loop<false>(p, smem, &s_idx);
+    }
   });
   return VPZ_OK;
 }

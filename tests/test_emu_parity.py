@@ -124,3 +124,37 @@ def test_general_path_pcm(general_ctx):
     cases.batch_pcm_parity(general_ctx, "1test", True)
     cases.decode_files_parity(general_ctx, ["1test"])
     cases.decode_files_s16_parity(general_ctx, ["1test"])
+
+
+# ---- generated streams: every setup shape the TestFiles do not have (tests/synthvorbis.py) -------------
+import synthvorbis  # noqa: E402
+
+
+@pytest.mark.parametrize("shape", list(synthvorbis.SHAPES))
+def test_generated_shape_stage_parity(emu_ctx, shape):
+    """Integer stages, residue and spectrum of generated packets (and truncated copies): residue 0 / 1 / 2,
+    1-8 channels, several coupling steps and submaps, floor 0, long codes, odd VQ dimensions, ..."""
+    assert cases.synth_stage_parity(emu_ctx, shape, seed=11, n_packets=10) == 20
+
+
+@pytest.mark.parametrize("shape", ["res012_3ch", "multi_submap", "floor0_mixed", "posts_beyond_block", "blocks_512_4096"])
+def test_generated_shape_stream_parity(emu_ctx, shape):
+    assert cases.synth_stream_parity(emu_ctx, shape, seed=5, n_packets=10, clip=True, eos_trim=100) > 0
+
+
+def test_generated_mixed_batch(emu_ctx):
+    """One bulk call over streams of different kernel classes (gather / general / full K1 paths, fast and
+    generic IMDCT): every stream must come out as if decoded alone."""
+    cases.synth_mixed_batch_parity(emu_ctx, [("stereo_res2", 3), ("ch6_coupled", 4), ("multi_submap", 5), ("floor0", 6)],
+                                   n_packets=8, with_files=["1test"])
+
+
+def test_65_post_floor_is_refused(emu_ctx):
+    """Floor1.Posts holds 64 values (Floor1.cs:17): a 65-post floor faults in the reference; both sides refuse."""
+    import oracle_binding as ob
+    from vorbispizza_b200 import VpzError
+    st = synthvorbis.make_stream(1, dict(channels=1, res_types=(1,), floor_posts=65), n_packets=2)
+    with pytest.raises(ob.OracleError):
+        ob.OracleStream(st["ogg"])
+    with pytest.raises(VpzError):
+        emu_ctx.create_setup(st["id"], st["setup"])

@@ -175,3 +175,91 @@ def test_excerpts_batch_unclipped_small_reads(gpu_ctx):
 def test_decode_files_s16(gpu_ctx, clip):
     """16-bit output fused into the IMDCT kernel (half the device-to-host bytes)."""
     cases.decode_files_s16_parity(gpu_ctx, FILES, clip=clip)
+
+
+# ---- every kernel path under oracle parity -----------------------------------------------------------
+# (1) the TestFiles forced through the general spectrum kernel, the generic IMDCT kernel and the full
+#     symbol kernel ("force_general"), (2) generated streams of every setup shape the TestFiles do not have
+#     (tests/synthvorbis.py): >= 1,000 packet decodes per shape, bit-exact integer stages / residue / spectrum.
+import synthvorbis  # noqa: E402
+
+
+@pytest.fixture(scope="module", params=[1, 2])
+def general_ctx(request):
+    from vorbispizza_b200 import Context
+    ctx = Context(0)
+    ctx.set("force_general", request.param)
+    yield ctx
+    ctx.close()
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_general_path_stage_parity_every_packet(general_ctx, name):
+    n = cases.stage_parity(general_ctx, name, stride=1)
+    assert n == {"1test": 25, "2test": 310, "3test": 366, "issue6test": 606}[name]
+
+
+def test_general_path_truncated_packets(general_ctx):
+    assert cases.stage_parity(general_ctx, "3test", stride=5, truncate=True) > 0
+    assert cases.stage_parity(general_ctx, "2test", stride=7, truncate=True) > 0
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_general_path_pcm(general_ctx, name):
+    cases.batch_pcm_parity(general_ctx, name, True)
+    cases.batch_pcm_parity(general_ctx, name, False)
+
+
+def test_general_path_bulk_and_s16(general_ctx):
+    cases.decode_files_parity(general_ctx, FILES, clip=True)
+    cases.decode_files_s16_parity(general_ctx, FILES, clip=True)
+    cases.reader_parity(general_ctx, "3test", lookahead=50, chunk=4096)
+
+
+@pytest.mark.parametrize("shape", list(synthvorbis.SHAPES))
+def test_generated_shape_stage_parity(gpu_ctx, shape):
+    n = cases.synth_stage_parity(gpu_ctx, shape, seed=101, n_packets=260, mean_len=150)
+    n += cases.synth_stage_parity(gpu_ctx, shape, seed=202, n_packets=260, mean_len=60)
+    assert n >= 1000
+
+
+@pytest.mark.parametrize("clip", [True, False])
+@pytest.mark.parametrize("shape", list(synthvorbis.SHAPES))
+def test_generated_shape_stream_parity(gpu_ctx, shape, clip):
+    assert cases.synth_stream_parity(gpu_ctx, shape, seed=31 + int(clip), n_packets=120, clip=clip, lookahead=17,
+                                     eos_trim=77) > 0
+
+
+def test_generated_mixed_batch(gpu_ctx):
+    """Streams of every kernel class in ONE bulk call beside the TestFiles: per-setup path selection."""
+    shapes = [(s, 7 + i) for i, s in enumerate(synthvorbis.SHAPES)]
+    cases.synth_mixed_batch_parity(gpu_ctx, shapes, n_packets=60, with_files=FILES, clip=False)
+    cases.synth_mixed_batch_parity(gpu_ctx, shapes[::3], n_packets=30, with_files=["3test"], clip=True)
+
+
+def test_mixed_batch_keeps_fast_streams_fast(gpu_ctx):
+    """A batch of stereo TestFile streams plus ONE 6-channel stream: the stereo packets must still take the
+    gather / fast kernels (same kernel time as without the odd stream, within noise)."""
+    import time
+    from vorbispizza_b200 import decode_files
+    datas = [load_file("3test")] * 256
+    odd = synthvorbis.make_stream(9, "ch6_coupled", n_packets=40)["ogg"]
+
+    def best(ds):
+        t = []
+        for _ in range(4):
+            t0 = time.perf_counter()
+            decode_files(gpu_ctx, ds, clip=True)
+            t.append(time.perf_counter() - t0)
+        return min(t)
+    base = best(datas)
+    mixed = best(datas + [odd])
+    # the batch-wide switch this replaces made such a batch 2-3x slower
+    assert mixed < 1.5 * base + 0.02, (base, mixed)
+
+
+def test_65_post_floor_is_refused(gpu_ctx):
+    from vorbispizza_b200 import VpzError
+    st = synthvorbis.make_stream(1, dict(channels=1, res_types=(1,), floor_posts=65), n_packets=2)
+    with pytest.raises(VpzError):
+        gpu_ctx.create_setup(st["id"], st["setup"])

@@ -25,11 +25,18 @@ __global__ void __launch_bounds__(128, 8) vpz_k1a_symbols(K1Params P) {
   }
 }
 
+// gather path: one warp per packet
 template <bool DEBUG>
 __global__ void __launch_bounds__(K1B_THREADS, 9) vpz_k1b_spectrum(K1Params P) {
   extern __shared__ uint32_t k1_smem[];
+  k1b_gather_loop<DEBUG>(P, k1_smem);
+}
+// general path: one CTA per packet
+template <bool DEBUG>
+__global__ void __launch_bounds__(K1B_THREADS, 4) vpz_k1b_general(K1Params P) {
+  extern __shared__ uint32_t k1_smem[];
   __shared__ uint32_t s_idx;
-  k1b_cta_loop<DEBUG>(P, k1_smem, &s_idx);
+  k1b_general_loop<DEBUG>(P, k1_smem, &s_idx);
 }
 
 // generic block sizes / channel counts
@@ -112,6 +119,8 @@ int init(int device, int* resolved, std::string& err) {
   const int optin = (int)prop.sharedMemPerBlockOptin;   // function attributes are per device
   cudaFuncSetAttribute(vpz_k1b_spectrum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   cudaFuncSetAttribute(vpz_k1b_spectrum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k1b_general<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k1b_general<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   cudaFuncSetAttribute(vpz_k3_imdct_ola<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   cudaFuncSetAttribute(vpz_k3_imdct_ola<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   cudaFuncSetAttribute(vpz_k3_streams<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
@@ -241,10 +250,11 @@ int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, 
     err = "K1b shared memory request exceeds the device limit";
     return VPZ_E_UNSUPPORTED;
   }
-  if (debug)
-    vpz_k1b_spectrum<true><<<blocks, K1B_THREADS, smem, s->s>>>(p);
-  else
-    vpz_k1b_spectrum<false><<<blocks, K1B_THREADS, smem, s->s>>>(p);
+  if (p.gather_ok) {
+    if (debug) vpz_k1b_spectrum<true><<<blocks, K1B_THREADS, smem, s->s>>>(p); else vpz_k1b_spectrum<false><<<blocks, K1B_THREADS, smem, s->s>>>(p);
+  } else {
+    if (debug) vpz_k1b_general<true><<<blocks, K1B_THREADS, smem, s->s>>>(p); else vpz_k1b_general<false><<<blocks, K1B_THREADS, smem, s->s>>>(p);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k1b_spectrum", err);
 }

@@ -15,21 +15,37 @@ namespace vpz {
 double g_trace_ms[4] = {0, 0, 0, 0};   // VPZ_TRACE: batch_upload sort, batch_upload copies, batch_decode launches, spare
 static double trace_now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-// vectors * partitions of the largest residue of the setup (units of K1a/K1b)
+// vectors * partitions of one residue instance in a long block (units of K1a / K1b)
+static size_t instance_units(const Setup& st, const VpzResidue& r) {
+  const VpzSetupHdr* h = st.hdr();
+  const int half_max = 1 << (h->log2_size1 - 1);
+  const int nvec = r.type == 2 ? 1 : r.nch;
+  const int64_t vlen = r.type == 2 ? (int64_t)half_max * r.nch : half_max;
+  const int64_t b = std::min<int64_t>(r.begin, vlen), e = std::min<int64_t>(r.end, vlen);
+  const int64_t parts = e > b ? (e - b) / r.part_size : 0;
+  return (size_t)(parts * nvec);
+}
+// the largest residue instance of the setup
 static size_t max_units(const Setup& st) {
   const VpzSetupHdr* h = st.hdr();
-  const int C = h->channels;
-  const int half_max = 1 << (h->log2_size1 - 1);
   const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(st.blob.data() + h->residues_off);
   size_t units = 0;
-  for (int i = 0; i < h->nresidues; i++) {
-    int nvec = rs[i].type == 2 ? 1 : C;
-    int64_t vlen = rs[i].type == 2 ? (int64_t)half_max * C : half_max;
-    int64_t b = std::min<int64_t>(rs[i].begin, vlen), e = std::min<int64_t>(rs[i].end, vlen);
-    int64_t parts = e > b ? (e - b) / rs[i].part_size : 0;
-    units = std::max(units, (size_t)(parts * nvec));
-  }
+  for (int i = 0; i < h->nresidues; i++) units = std::max(units, instance_units(st, rs[i]));
   return units;
+}
+// words of the class bytes in a packet's symbol record: the submaps of a mapping follow each other, each
+// rounded up to whole words (K1a clears them word-wise)
+static size_t max_class_words(const Setup& st) {
+  const VpzSetupHdr* h = st.hdr();
+  const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(st.blob.data() + h->residues_off);
+  const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(st.blob.data() + h->mappings_off);
+  size_t words = 0;
+  for (int i = 0; i < h->nmappings; i++) {
+    size_t w = 0;
+    for (int j = 0; j < mp[i].submaps; j++) w += (instance_units(st, rs[mp[i].submap_residue[j]]) + 3) / 4;
+    words = std::max(words, w);
+  }
+  return words;
 }
 
 static int fl_type(const Setup& st, int i) {
@@ -105,7 +121,13 @@ static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
       s->k1g_words = (uint32_t)(((size_t)max_stages * U * 2 + (size_t)C * half_max / 4 + (size_t)C * s->k1g_seg_stride + 8 + 31) & ~(size_t)31);
     }
     // K1_REC_HDR, K1_SEG_WORDS, classes; a multiple of 4 words so every record starts on a 16-byte boundary
-    s->rec_words = (uint32_t)((4 + h->channels * 68 + (units + 3) / 4 + 1 + 3) & ~(size_t)3);
+    // + 16 with several submaps: the per-submap entry ends K1a leaves behind the class bytes
+    bool multi_sub = false;
+    {
+      const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(s->host.blob.data() + h->mappings_off);
+      for (int i = 0; i < h->nmappings; i++) multi_sub = multi_sub || mp[i].submaps > 1;
+    }
+    s->rec_words = (uint32_t)((4 + h->channels * 68 + max_class_words(s->host) + 1 + (multi_sub ? 16 : 0) + 3) & ~(size_t)3);
   }
   size_t bytes = s->host.blob.size() * 4;
   s->d_blob = dev::alloc(bytes, ctx->last_error);

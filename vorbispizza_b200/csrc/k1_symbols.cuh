@@ -55,9 +55,13 @@
 //   [0] own_mask | noexec_mask << 8 | status << 16 | long_block << 24
 //   [1] number of VQ entries written at P.ent + pkt.ent_off (uint16 each)
 //   [2] final bit cursor
-//   [3] mapping index | residue index << 8 (found through the mode; K1b does not walk the packet again)
-//   then per channel K1_SEG_WORDS words: [0] = number of line segments n, [1..n+1] = points x | y << 16
-//   then one byte per unit (partition * nvec + vector, the decode order inside a stage): the partition class
+//   [3] mapping index | residue instance of submap 0 << 8 | floor-0 entry indices that precede the residue's << 16
+//       (found through the mode; K1b does not walk the packet again)
+//   then per channel K1_SEG_WORDS words: floor 1: [0] = number of line segments n, [1..n+1] = points x | y << 16;
+//       floor 0 with energy: [0] = 0x80000000 | book number, [1] = raw amplitude, [2] = first entry index
+//       (relative to the packet's entry area), [3] = number of entry indices; 0 in [0] = silent channel
+//   then one byte per unit (partition * nvec + vector, the decode order inside a stage): the partition class;
+//       the submaps of a mapping follow each other, each padded to whole words
 #define K1_REC_HDR 4
 #define K1_SEG_WORDS 68
 #define K1_MAX_UNITS 512      // vectors * partitions per packet (setup.cpp refuses more)
@@ -188,6 +192,7 @@ struct K1ResGeom {
   uint32_t skip;       // bit v: vector v is not decoded
   bool any;
 };
+// C: channels of the submap, noexec: their do-not-decode flags (bit c = c-th channel of the submap)
 VPZ_DEV K1ResGeom k1_res_geom(const VpzResidue* rs, int C, int half, uint32_t noexec) {
   K1ResGeom g;
   g.rtype = rs->type;
@@ -209,151 +214,31 @@ VPZ_DEV int k1_unit_entries(int rtype, int psize, int dims) {
   return rtype == 0 ? psize / dims : (psize + dims - 1) / dims;
 }
 
-// =============================================================================================
-// K1a: one lane decodes one packet
-// =============================================================================================
-template <bool DEBUG, bool FULL>
-VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
-  const VpzPktIn pk = P.pkts[pkt_idx];
-  const uint32_t* blob = P.setups[pk.setup_slot];
-  const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
-  const int C = H->channels;
-  const VpzBook* books = reinterpret_cast<const VpzBook*>(blob + H->books_off);
-  const int half_max = 1 << (H->log2_size1 - 1);
-  uint32_t* rec = P.rec + pk.rec_off;
-
-  K1Bits b;
-  k1_bits_init(b, P.bytes, pk.byte_off >> 2, (int)pk.byte_len);
-  int nscal = 0, ncls = 0;
-
-  // StreamDecoder.DecodeNextPacket (StreamDecoder.cs:728-741): the host only queues packets whose
-  // type bit is 0 and whose mode exists, so these reads just advance the cursor.
-  k1_read(b, P.bytes, 1);
-  const int mode_idx = (int)k1_read(b, P.bytes, H->mode_bits);
-  const VpzMode* modes = reinterpret_cast<const VpzMode*>(blob + H->modes_off);
-  const int long_block = modes[mode_idx].block_flag;
-  const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + modes[mode_idx].mapping;
-  if (long_block) k1_read(b, P.bytes, 2);  // prev/next window flags (Mode.cs:38), geometry is the host's job
-  const int half = long_block ? half_max : (1 << (H->log2_size0 - 1));
-
-  // ---- floor unpack + unwrap, channel by channel (Mapping.cs:106-116, Floor1.cs:162-219, 270-353) ----
-  uint32_t own_mask = 0;  // bit ch: floor has energy (FloorData.ExecuteChannel)
-  for (int ch = 0; ch < C; ch++) {
-    const VpzFloor1* fl = reinterpret_cast<const VpzFloor1*>(blob + H->floors_off) + mp->submap_floor[mp->mux[ch]];
-    // raw posts, unwrapped in place into the final Y (post i is read once, at step i, and only earlier
-    // posts are looked at afterwards): one per-lane array in local memory instead of two
-    short po[VPZ_MAX_POSTS + 1];
-    short* const fy = po;
-    int count = 0, written = 0;  // written: posts stored before a failed decode reset the count
-    if (k1_read(b, P.bytes, 1) == 1) {
-      const int ybits = fl->ybits;
-      po[0] = (short)k1_read(b, P.bytes, ybits);
-      po[1] = (short)k1_read(b, P.bytes, ybits);
-      count = written = 2;
-      const int nparts = fl->partitions;
-      for (int i = 0; i < nparts && count > 0; i++) {
-        const int c = fl->part_class[i];
-        const int cdim = fl->class_dim[c], cbits = fl->class_sub[c];
-        const uint32_t csub = (1u << cbits) - 1u;
-        uint32_t cval = 0;
-        if (cbits > 0) {
-          K1Book mb = k1_book(blob, books, fl->class_master[c]);
-          int v = k1_decode<DEBUG>(b, mb, blob, P, nscal);
-          if (v < 0) {
-            count = 0;
-            break;
-          }
-          cval = (uint32_t)v;
-        }
-        for (int j = 0; j < cdim; j++) {
-          const int book_idx = fl->sub_books[c][cval & csub];
-          cval >>= cbits;
-          int post = 0;
-          if (book_idx >= 0) {
-            K1Book sb = k1_book(blob, books, book_idx);
-            post = k1_decode<DEBUG>(b, sb, blob, P, nscal);
-            if (post < 0) {
-              count = 0;
-              break;
-            }
-          }
-          po[count++] = (short)post;
-          written = count;
-        }
-      }
-    }
-    if (DEBUG && P.dbg.hdr) {
-      P.dbg.hdr[DUMP_POSTCOUNT + ch] = count;
-      for (int i = 0; i < 64; i++) P.dbg.hdr[DUMP_RAWPOSTS + ch * 64 + i] = i < written ? po[i] : 0;
-    }
-    uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
-    if (count == 0) {
-      seg[0] = 0;
-      continue;
-    }
-    own_mask |= 1u << ch;
-    // UnwrapPosts (Floor1.cs:270-353): serial dependency through earlier posts
-    const int range = fl->range;
-    unsigned long long flags = 3ull;
-    for (int i = 2; i < count; i++) {
-      const int lo = fl->lneigh[i], hi = fl->hneigh[i];
-      const int predicted = k1_render_point(fl->xlist[lo], fy[lo], fl->xlist[hi], fy[hi], fl->xlist[i]);
-      const int val = po[i];
-      const int highroom = range - predicted, lowroom = predicted;
-      const int room = (highroom < lowroom ? highroom : lowroom) * 2;
-      int result = predicted;
-      if (val != 0) {
-        flags |= (1ull << lo) | (1ull << hi) | (1ull << i);
-        if (val >= room)
-          result = highroom > lowroom ? val - lowroom + predicted : predicted - val + highroom - 1;
-        else
-          result = (val & 1) ? predicted - ((val + 1) >> 1) : predicted + (val >> 1);
-      }
-      fy[i] = (short)result;
-    }
-    if (DEBUG && P.dbg.hdr) {
-      for (int i = 0; i < 64; i++) {
-        P.dbg.hdr[DUMP_FINALY + ch * 64 + i] = i < count ? fy[i] : 0;
-        P.dbg.hdr[DUMP_STEPFLAGS + ch * 64 + i] = i < count ? (int)((flags >> i) & 1ull) : 0;
-      }
-    }
-    // flagged posts in X order -> line segments (Floor1.Apply, Floor1.cs:222-268).  A segment that
-    // is clamped at `half` (quirk Q1: clamp before the slope) is the last one: the loop breaks.
-    const int mult = fl->multiplier;
-    int nseg = 0, lx = 0, ly = fy[0] * mult;
-    seg[1] = (uint32_t)0 | ((uint32_t)(ly & 0xffff) << 16);
-    for (int i = 1; i < count; i++) {
-      const int idx = fl->sortidx[i];
-      if ((flags >> idx) & 1ull) {
-        const int hx = fl->xlist[idx], hy = fy[idx] * mult;
-        if (lx < half) {
-          nseg++;
-          seg[1 + nseg] = (uint32_t)(hx < half ? hx : half) | ((uint32_t)(hy & 0xffff) << 16);
-        }
-        lx = hx;
-        ly = hy;
-      }
-      if (lx >= half) break;
-    }
-    if (lx < half) {  // flat tail
-      nseg++;
-      seg[1 + nseg] = (uint32_t)half | ((uint32_t)(ly & 0xffff) << 16);
-    }
-    seg[0] = (uint32_t)nseg;
+// The residue walk of one submap (Residue0.Decode, Residue0.cs:117-206; Residue2.Decode, Residue2.cs:12-52):
+// classwords and VQ entry indices.  C = channels of the submap, noexec = their do-not-decode flags,
+// rec_cls = where the class bytes of this submap's units go.  Entry indices continue at ent_pos.
+struct K1aOut {
+  uint32_t ent_pos, ent_lo, ent_hi;   // four entry indices per 8-byte store (k1a_emit)
+  int status, nscal, ncls;
+};
+VPZ_DEV void k1a_emit(const K1Params& P, K1aOut& o, int sym) {
+  // four entry indices per 8-byte store: a lane's store is its own L1 tag lookup, and the entry
+  // stream is the bulk of K1a's memory requests
+  const int q = (int)(o.ent_pos & 3u) * 16;
+  if (q < 32) o.ent_lo |= (uint32_t)sym << q; else o.ent_hi |= (uint32_t)sym << (q - 32);
+  o.ent_pos++;
+  if (q == 48) {
+    *reinterpret_cast<uint2*>(P.ent + (o.ent_pos - 4)) = uint2{o.ent_lo, o.ent_hi};
+    o.ent_lo = o.ent_hi = 0;
   }
-  // no-energy propagation through the coupling steps (Mapping.cs:121-130)
-  uint32_t noexec = ~own_mask & ((1u << C) - 1u);
-  for (int i = 0; i < mp->coupling_steps; i++) {
-    uint32_t mb = 1u << mp->mag[i], ab = 1u << mp->ang[i];
-    if (!((noexec & mb) && (noexec & ab))) noexec &= ~(mb | ab);
-  }
-
-  // ---- residue: classwords + VQ entry indices (single submap: Setup::parse refuses more) ------
-  const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(blob + H->residues_off) + mp->submap_residue[0];
+}
+template <bool DEBUG>
+VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook* books, K1Bits& b, const VpzResidue* rs,
+                         int C, uint32_t noexec, int half, uint8_t* rec_cls, K1aOut& o) {
   const K1ResGeom g = k1_res_geom(rs, C, half, noexec);
-  int status = 0;
-  uint32_t ent_pos = pk.ent_off;   // multiple of 4 (engine.cpp)
-  uint32_t ent_lo = 0, ent_hi = 0;
+  int& status = o.status;
+  int& nscal = o.nscal;
+  int& ncls = o.ncls;
   if (g.part_count > 0 && g.any && rs->max_stages > 0) {
     // Residue0.Decode (Residue0.cs:117-206) walks  stage -> partition group -> [stage 0: classwords] ->
     // partition -> vector.  Here the walk is flattened so that every trip round the loop decodes
@@ -368,7 +253,6 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
     uint32_t smask[8 * (K1_MAX_UNITS / 32)];         // [stage][chunk of 32 units]; row 0 unused
     // class per unit in decode order: written to the record for K1b and read back from there (plain
     // loads: the lane reads its own stores)
-    uint8_t* rec_cls = reinterpret_cast<uint8_t*>(P.rec + pk.rec_off + K1_REC_HDR + C * K1_SEG_WORDS);
     const K1Book cb = k1_book(blob, books, rs->class_book);
     const int cdim = rs->cdim, nvec = g.nvec, part_count = g.part_count;
     const int partvals = (int)rs->partvals;
@@ -481,24 +365,256 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
           status = 1;
           break;
         }
-        // four entry indices per 8-byte store: a lane's store is its own L1 tag lookup, and the entry
-        // stream is the bulk of K1a's memory requests
-        const int q = (int)(ent_pos & 3u) * 16;
-        if (q < 32) ent_lo |= (uint32_t)sym << q; else ent_hi |= (uint32_t)sym << (q - 32);
-        ent_pos++;
-        if (q == 48) {
-          *reinterpret_cast<uint2*>(P.ent + (ent_pos - 4)) = uint2{ent_lo, ent_hi};
-          ent_lo = ent_hi = 0;
-        }
+        k1a_emit(P, o, sym);
         rem--;
       }
     }
   }
+}
+
+// =============================================================================================
+// K1a: one lane decodes one packet
+// =============================================================================================
+template <bool DEBUG, bool FULL>
+VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
+  const VpzPktIn pk = P.pkts[pkt_idx];
+  const uint32_t* blob = P.setups[pk.setup_slot];
+  const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
+  const int C = H->channels;
+  const VpzBook* books = reinterpret_cast<const VpzBook*>(blob + H->books_off);
+  const int half_max = 1 << (H->log2_size1 - 1);
+  uint32_t* rec = P.rec + pk.rec_off;
+
+  K1Bits b;
+  k1_bits_init(b, P.bytes, pk.byte_off >> 2, (int)pk.byte_len);
+  int nscal = 0, ncls = 0;
+
+  // StreamDecoder.DecodeNextPacket (StreamDecoder.cs:728-741): the host only queues packets whose
+  // type bit is 0 and whose mode exists, so these reads just advance the cursor.
+  k1_read(b, P.bytes, 1);
+  const int mode_idx = (int)k1_read(b, P.bytes, H->mode_bits);
+  const VpzMode* modes = reinterpret_cast<const VpzMode*>(blob + H->modes_off);
+  const int long_block = modes[mode_idx].block_flag;
+  const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + modes[mode_idx].mapping;
+  if (long_block) k1_read(b, P.bytes, 2);  // prev/next window flags (Mode.cs:38), geometry is the host's job
+  const int half = long_block ? half_max : (1 << (H->log2_size0 - 1));
+
+  // ---- floor unpack + unwrap, channel by channel (Mapping.cs:106-116, Floor1.cs:162-219, 270-353) ----
+  uint32_t own_mask = 0;  // bit ch: floor has energy (FloorData.ExecuteChannel)
+  uint32_t ent_pos = pk.ent_off;   // multiple of 4 (engine.cpp)
+  uint32_t ent_lo = 0, ent_hi = 0;
+  for (int ch = 0; ch < C; ch++) {
+    const VpzFloor1* fl = reinterpret_cast<const VpzFloor1*>(blob + H->floors_off) + mp->submap_floor[mp->mux[ch]];
+    if (FULL && fl->floor_type == 0) {
+      // Floor0.Unpack (Floor0.cs:115-167): amplitude, book number, then the coefficient vectors -- which the
+      // reference reads WHATEVER the amplitude is.  The entry indices go to the packet's entry area (they
+      // precede the residue's); K1b turns them into the LSP curve.
+      uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
+      const uint32_t amp = k1_read(b, P.bytes, fl->f0.amp_bits);
+      const uint32_t book_num = k1_read(b, P.bytes, fl->f0.book_bits);
+      bool ok = book_num < fl->f0.nbooks;
+      const uint32_t first = ent_pos - pk.ent_off;
+      if (ok) {
+        const int bi = fl->f0.books[book_num];
+        const K1Book fb = k1_book(blob, books, bi);
+        const int dims = k1_book_dims(books + bi);
+        K1aOut o;
+        o.ent_pos = ent_pos;
+        o.ent_lo = ent_lo;
+        o.ent_hi = ent_hi;
+        for (int i = 0; i < (int)fl->f0.order; i += dims) {
+          const int sym = k1_decode<DEBUG>(b, fb, blob, P, nscal);
+          if (sym < 0) {
+            ok = false;
+            break;
+          }
+          k1a_emit(P, o, sym);
+        }
+        ent_pos = o.ent_pos;
+        ent_lo = o.ent_lo;
+        ent_hi = o.ent_hi;
+      }
+      // ExecuteChannel = Amp != 0 with Amp = amp * ampOfs / (2^ampBits - 1) (Floor0.cs:21,121-123)
+      const bool exec = ok && amp != 0 && fl->f0.amp_ofs != 0;
+      seg[0] = exec ? (0x80000000u | book_num) : 0u;
+      seg[1] = amp;
+      seg[2] = first;
+      seg[3] = ent_pos - pk.ent_off - first;
+      if (exec) own_mask |= 1u << ch;
+      if (DEBUG && P.dbg.hdr) {
+        P.dbg.hdr[DUMP_POSTCOUNT + ch] = exec ? 2 : 0;
+        for (int i = 0; i < 64; i++) {
+          const int v = !exec ? 0 : (i == 0 ? (int)(amp & 0x7fffffffu) : (i == 1 ? (int)book_num : 0));
+          P.dbg.hdr[DUMP_RAWPOSTS + ch * 64 + i] = v;
+          P.dbg.hdr[DUMP_FINALY + ch * 64 + i] = v;
+          P.dbg.hdr[DUMP_STEPFLAGS + ch * 64 + i] = 0;
+        }
+      }
+      continue;
+    }
+    // raw posts, unwrapped in place into the final Y (post i is read once, at step i, and only earlier
+    // posts are looked at afterwards): one per-lane array in local memory instead of two
+    short po[VPZ_MAX_POSTS + 1];
+    short* const fy = po;
+    int count = 0, written = 0;  // written: posts stored before a failed decode reset the count
+    if (k1_read(b, P.bytes, 1) == 1) {
+      const int ybits = fl->ybits;
+      po[0] = (short)k1_read(b, P.bytes, ybits);
+      po[1] = (short)k1_read(b, P.bytes, ybits);
+      count = written = 2;
+      const int nparts = fl->partitions;
+      for (int i = 0; i < nparts && count > 0; i++) {
+        const int c = fl->part_class[i];
+        const int cdim = fl->class_dim[c], cbits = fl->class_sub[c];
+        const uint32_t csub = (1u << cbits) - 1u;
+        uint32_t cval = 0;
+        if (cbits > 0) {
+          K1Book mb = k1_book(blob, books, fl->class_master[c]);
+          int v = k1_decode<DEBUG>(b, mb, blob, P, nscal);
+          if (v < 0) {
+            count = 0;
+            break;
+          }
+          cval = (uint32_t)v;
+        }
+        for (int j = 0; j < cdim; j++) {
+          const int book_idx = fl->sub_books[c][cval & csub];
+          cval >>= cbits;
+          int post = 0;
+          if (book_idx >= 0) {
+            K1Book sb = k1_book(blob, books, book_idx);
+            post = k1_decode<DEBUG>(b, sb, blob, P, nscal);
+            if (post < 0) {
+              count = 0;
+              break;
+            }
+          }
+          po[count++] = (short)post;
+          written = count;
+        }
+      }
+    }
+    if (DEBUG && P.dbg.hdr) {
+      P.dbg.hdr[DUMP_POSTCOUNT + ch] = count;
+      for (int i = 0; i < 64; i++) P.dbg.hdr[DUMP_RAWPOSTS + ch * 64 + i] = i < written ? po[i] : 0;
+    }
+    uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
+    if (count == 0) {
+      seg[0] = 0;
+      continue;
+    }
+    own_mask |= 1u << ch;
+    // UnwrapPosts (Floor1.cs:270-353): serial dependency through earlier posts
+    const int range = fl->range;
+    unsigned long long flags = 3ull;
+    for (int i = 2; i < count; i++) {
+      const int lo = fl->lneigh[i], hi = fl->hneigh[i];
+      const int predicted = k1_render_point(fl->xlist[lo], fy[lo], fl->xlist[hi], fy[hi], fl->xlist[i]);
+      const int val = po[i];
+      const int highroom = range - predicted, lowroom = predicted;
+      const int room = (highroom < lowroom ? highroom : lowroom) * 2;
+      int result = predicted;
+      if (val != 0) {
+        flags |= (1ull << lo) | (1ull << hi) | (1ull << i);
+        if (val >= room)
+          result = highroom > lowroom ? val - lowroom + predicted : predicted - val + highroom - 1;
+        else
+          result = (val & 1) ? predicted - ((val + 1) >> 1) : predicted + (val >> 1);
+      }
+      fy[i] = (short)result;
+    }
+    if (DEBUG && P.dbg.hdr) {
+      for (int i = 0; i < 64; i++) {
+        P.dbg.hdr[DUMP_FINALY + ch * 64 + i] = i < count ? fy[i] : 0;
+        P.dbg.hdr[DUMP_STEPFLAGS + ch * 64 + i] = i < count ? (int)((flags >> i) & 1ull) : 0;
+      }
+    }
+    // flagged posts in X order -> line segments (Floor1.Apply, Floor1.cs:222-268).  A segment that
+    // is clamped at `half` (quirk Q1: clamp before the slope) is the last one: the loop breaks.
+    const int mult = fl->multiplier;
+    int nseg = 0, lx = 0, ly = fy[0] * mult;
+    seg[1] = (uint32_t)0 | ((uint32_t)(ly & 0xffff) << 16);
+    for (int i = 1; i < count; i++) {
+      const int idx = fl->sortidx[i];
+      if ((flags >> idx) & 1ull) {
+        const int hx = fl->xlist[idx], hy = fy[idx] * mult;
+        if (lx < half) {
+          nseg++;
+          seg[1 + nseg] = (uint32_t)(hx < half ? hx : half) | ((uint32_t)(hy & 0xffff) << 16);
+        }
+        lx = hx;
+        ly = hy;
+      }
+      if (lx >= half) break;
+    }
+    if (lx < half) {  // flat tail
+      nseg++;
+      seg[1 + nseg] = (uint32_t)half | ((uint32_t)(ly & 0xffff) << 16);
+    }
+    seg[0] = (uint32_t)nseg;
+  }
+  // no-energy propagation through the coupling steps (Mapping.cs:121-130)
+  uint32_t noexec = ~own_mask & ((1u << C) - 1u);
+  for (int i = 0; i < mp->coupling_steps; i++) {
+    uint32_t mb = 1u << mp->mag[i], ab = 1u << mp->ang[i];
+    if (!((noexec & mb) && (noexec & ab))) noexec &= ~(mb | ab);
+  }
+
+  // ---- residue: classwords + VQ entry indices, submap after submap (Mapping.cs:136-163) ------------
+  const uint32_t floor_ents = ent_pos - pk.ent_off;   // floor-0 coefficient entries (0 without floor 0)
+  K1aOut o;
+  o.ent_pos = ent_pos;
+  o.ent_lo = ent_lo;
+  o.ent_hi = ent_hi;
+  o.status = 0;
+  o.nscal = nscal;
+  o.ncls = ncls;
+  uint8_t* rec_cls = reinterpret_cast<uint8_t*>(P.rec + pk.rec_off + K1_REC_HDR + C * K1_SEG_WORDS);
+  const VpzResidue* residues = reinterpret_cast<const VpzResidue*>(blob + H->residues_off);
+  if (!FULL || mp->submaps == 1) {
+    k1a_residue<DEBUG>(P, blob, books, b, residues + mp->submap_residue[0], C, noexec, half, rec_cls, o);
+  } else {
+    // where a submap's entry indices end is only known here: a residue that stops early (no matching
+    // code, quirk Q8) does not stop the submaps after it, which read on from the same bit position.  The
+    // end positions go behind the class bytes of the last submap.
+    int cls_total = 0;
+    for (int sm = 0; sm < mp->submaps; sm++) {
+      int nch = 0;
+      for (int ch = 0; ch < C; ch++) nch += mp->mux[ch] == sm;
+      if (nch == 0) continue;
+      const K1ResGeom g = k1_res_geom(residues + mp->submap_residue[sm], nch, half, 0u);
+      cls_total += (g.part_count * g.nvec + 3) >> 2;
+    }
+    uint32_t* sub_end = reinterpret_cast<uint32_t*>(rec_cls) + cls_total;
+    for (int sm = 0; sm < mp->submaps; sm++) {
+      // the channels of this submap, in channel order, and their flags (Mapping.cs:138-146)
+      int nch = 0;
+      uint32_t flags = 0;
+      for (int ch = 0; ch < C; ch++)
+        if (mp->mux[ch] == sm) {
+          flags |= ((noexec >> ch) & 1u) << nch;
+          nch++;
+        }
+      if (nch > 0) {   // Residue0.Decode with no channels reads nothing
+        const VpzResidue* rs = residues + mp->submap_residue[sm];
+        const K1ResGeom g = k1_res_geom(rs, nch, half, flags);
+        k1a_residue<DEBUG>(P, blob, books, b, rs, nch, flags, half, rec_cls, o);
+        rec_cls += ((g.part_count * g.nvec + 3) >> 2) << 2;
+      }
+      sub_end[sm] = o.ent_pos - pk.ent_off;
+    }
+  }
+  const int status = o.status;
+  ent_pos = o.ent_pos;
+  ent_lo = o.ent_lo;
+  ent_hi = o.ent_hi;
+  nscal = o.nscal;
+  ncls = o.ncls;
   rec[0] = own_mask | (noexec << 8) | ((uint32_t)status << 16) | ((uint32_t)long_block << 24);
   if (ent_pos & 3u) *reinterpret_cast<uint2*>(P.ent + (ent_pos & ~3u)) = uint2{ent_lo, ent_hi};
   rec[1] = ent_pos - pk.ent_off;
   rec[2] = (uint32_t)b.pos;
-  rec[3] = (uint32_t)modes[mode_idx].mapping | ((uint32_t)mp->submap_residue[0] << 8);
+  rec[3] = (uint32_t)modes[mode_idx].mapping | ((uint32_t)mp->submap_residue[0] << 8) | (floor_ents << 16);
   if (DEBUG && P.dbg.hdr) {
     int32_t* h = P.dbg.hdr;
     h[DUMP_STATUS] = 0;
@@ -519,10 +635,10 @@ VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
 // partition is 16 or 32 floats) on different banks
 VPZ_DEV int k1b_sw(int i) { return i + (i >> 5); }
 
-// GENERAL path (any channel count, residue type 0, dimensions that do not divide the partition):
-// One CTA of K1B_THREADS threads per packet.  Shared memory (32-bit words): res[sw(C * half_max)] then
-// ustart[K1_MAX_UNITS + 32] (reused for the floor segments), uinfo[K1_MAX_UNITS], uvq[K1_MAX_UNITS], then
-// 8 words of scan scratch
+// GENERAL path (any channel count, several submaps, residue type 0, dimensions that do not divide the
+// partition, floor 0): one CTA of K1B_THREADS threads per packet.  Shared memory (32-bit words):
+// res[sw(C * half_max)] then ustart[K1_MAX_UNITS + 32] (reused for the floor segments / LSP coefficients),
+// uinfo[K1_MAX_UNITS], uvq[K1_MAX_UNITS], then 8 words of scan scratch
 template <bool DEBUG>
 VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, int tid) {
   const int lane = tid & 31, wid = tid >> 5;
@@ -537,7 +653,7 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
   const uint32_t hdr = rec[0];
   const uint32_t own_mask = hdr & 0xffu, noexec = (hdr >> 8) & 0xffu;
   const int long_block = (int)(hdr >> 24) & 1;
-  const uint32_t n_ent = rec[1];
+  const uint32_t n_ent_all = rec[1];
   const int half = long_block ? half_max : (1 << (H->log2_size0 - 1));
 
   float* res = reinterpret_cast<float*>(smem);
@@ -555,130 +671,194 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
   }
   if (own_mask == 0 && !(DEBUG && P.dbg.residue)) return;  // every channel silent: K3 outputs zeros
 
-  // modes / mapping are only needed through the record: the mapping is found from the packet header
-  // bits again (mode index), cheaper than storing it
-  const uint32_t w0 = VPZ_LDG(P.bytes + (pk.byte_off >> 2));
-  const int mode_idx = (int)((w0 >> 1) & ((1u << H->mode_bits) - 1u));
-  const VpzMode* modes = reinterpret_cast<const VpzMode*>(blob + H->modes_off);
-  const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + modes[mode_idx].mapping;
-  const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(blob + H->residues_off) + mp->submap_residue[0];
-  const K1ResGeom g = k1_res_geom(rs, C, half, noexec);
+  // mapping index and the number of floor-0 entry indices come with the record (K1a found them)
+  const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + (rec[3] & 0xffu);
+  const VpzResidue* residues = reinterpret_cast<const VpzResidue*>(blob + H->residues_off);
+  const int nsub = mp->submaps;
+  const bool multi = nsub > 1;
+  float* out = P.spec + pk.spec_off;
 
   const int total = C * half;
   for (int i = tid; i < total; i += K1B_THREADS) res[k1b_sw(i)] = 0.f;
   __syncthreads();
 
-  // ---- residue: stage by stage, per stage: unit scan, then entry-parallel accumulate --------------
-  if (g.part_count > 0 && g.any && n_ent > 0) {
-    const uint8_t* rec_cls = reinterpret_cast<const uint8_t*>(rec + K1_REC_HDR + C * K1_SEG_WORDS);
-    const int nunits = g.part_count * g.nvec;       // decode order inside a stage: partition major
-    uint32_t stage_base = 0;
-    for (int stage = 0; stage < rs->max_stages && stage_base < n_ent; stage++) {
-      // entries per unit -> exclusive prefix sum = where each unit's entries start
-      uint32_t carry = 0;
-      for (int u0 = 0; u0 < nunits; u0 += K1B_THREADS) {
-        const int u = u0 + tid;
-        int cnt = 0;
-        uint32_t info = 0, vqoff = 0;   // info: dims | first bin << 8
-        if (u < nunits) {
-          const int part = u / g.nvec, v = u - part * g.nvec;
-          if (!((g.skip >> v) & 1u)) {
-            const int c = rec_cls[u];
-            if (((rs->cascade[c] >> stage) & 1u) && rs->has_books[c]) {
-              const VpzBook* bk = books + rs->books[c][stage];
-              const int dims = k1_book_dims(bk);
-              cnt = k1_unit_entries(g.rtype, g.psize, dims);
-              vqoff = VPZ_LDG(&bk->vq_off);
-              info = (uint32_t)(dims & 0xff) | ((uint32_t)(g.begin + part * g.psize + v * half) << 8);   // rtype 2: v == 0
-            }
-          }
-        }
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          int n = __shfl_up_sync(0xffffffffu, incl, d);
-          if (lane >= d) incl += n;
-        }
-        if (lane == 31) scan[wid] = incl;
-        __syncthreads();
-        int before = 0, round_total = 0;
-#pragma unroll
-        for (int w = 0; w < K1B_THREADS / 32; w++) {
-          const int t = scan[w];
-          if (w < wid) before += t;
-          round_total += t;
-        }
-        if (u < nunits) {
-          ustart[u] = (int)carry + before + incl - cnt;
-          uinfo[u] = info;
-          uvq[u] = vqoff;
-        }
-        carry += (uint32_t)round_total;
-        __syncthreads();
+  // ---- residue, submap after submap (Mapping.cs:136-163).  The reference decodes every submap into ONE
+  // scratch buffer that is zeroed once per packet (Mapping.cs:133): channel slot c of a later submap
+  // starts from what slot c of the earlier submaps left behind (types 0 / 1 accumulate; type 2 overwrites).
+  // res[] is that scratch (slot stride = half); with several submaps the slots are copied out to the
+  // channels' spectrum buffers after every submap and fetched back, channel-major, at the end.
+  const uint8_t* rec_cls = reinterpret_cast<const uint8_t*>(rec + K1_REC_HDR + C * K1_SEG_WORDS);
+  uint32_t stage_base = rec[3] >> 16;   // the residue's entry indices follow the floor-0 ones
+  // several submaps: K1a left the end of every submap's entry indices behind the class bytes (a residue
+  // that stops early does not stop the submaps after it)
+  const uint32_t* sub_end = nullptr;
+  if (multi) {
+    int cls_total = 0;
+    for (int sm = 0; sm < nsub; sm++) {
+      int nch = 0;
+      for (int ch = 0; ch < C; ch++) nch += mp->mux[ch] == sm;
+      if (nch == 0) continue;
+      const K1ResGeom g = k1_res_geom(residues + mp->submap_residue[sm], nch, half, 0u);
+      cls_total += (g.part_count * g.nvec + 3) >> 2;
+    }
+    sub_end = rec + K1_REC_HDR + C * K1_SEG_WORDS + cls_total;
+  }
+  int rtype_single = 0;
+  for (int sm = 0; sm < nsub; sm++) {
+    const uint32_t n_ent = multi ? sub_end[sm] : n_ent_all;
+    int nch = 0;
+    uint32_t flags = 0, chans = 0;   // chans: 4 bits per slot = the channel it belongs to
+    for (int ch = 0; ch < C; ch++)
+      if (!multi || mp->mux[ch] == sm) {
+        flags |= ((noexec >> ch) & 1u) << nch;
+        chans |= (uint32_t)ch << (4 * nch);
+        nch++;
       }
-      // ---- every thread takes single ENTRIES (codewords) of the stage, not whole units: the work is
-      // spread evenly however the active units are distributed.  The unit of entry e is the last one
-      // whose start is <= e (idle units have zero length and sort before the active unit that shares
-      // their start).  A bin is touched once per stage and the stages run in order, so the sums
-      // round exactly like the reference's stage-major accumulation.
-      uint32_t stage_n = carry;
-      if (stage_base + stage_n > n_ent) stage_n = n_ent - stage_base;   // truncated packet: keep what was decoded
-      const uint16_t* ep = ent + stage_base;
-      for (uint32_t e = (uint32_t)tid; e < stage_n; e += K1B_THREADS) {
-        int lo = 0, hi = nunits;   // ustart[lo] <= e < ustart[hi] (virtual ustart[nunits] = +inf)
-        while (hi - lo > 1) {
-          const int mid = (lo + hi) >> 1;
-          if ((uint32_t)ustart[mid] <= e) lo = mid; else hi = mid;
-        }
-        const uint32_t info = uinfo[lo];
-        const int dims = (int)(info & 0xffu);
-        const int si = (int)(e - (uint32_t)ustart[lo]);        // index of the entry inside its unit
-        const int dest = (int)(info >> 8);                     // first bin of the unit
-        const float* lk = reinterpret_cast<const float*>(blob + uvq[lo]) + (size_t)ep[e] * dims;
-        if (g.rtype == 0) {
-          // Residue0.WriteVectors (Residue0.cs:208-231), quirk Q6: dims summed into one bin
-          float r = 0.f;
-          for (int d = 0; d < dims; d++) r = __fadd_rn(r, VPZ_LDG(lk + d));
-          const int at = k1b_sw(dest + si);
-          res[at] = __fadd_rn(res[at], r);
-        } else if (dims == 2) {
-          // Residue1.WriteVectors (Residue1.cs:12-34)
-          const float2 v2 = VPZ_LDG(reinterpret_cast<const float2*>(lk));
-          const int o = dest + si * 2;
-          const int a0 = k1b_sw(o), a1 = k1b_sw(o + 1);
-          res[a0] = __fadd_rn(res[a0], v2.x);
-          res[a1] = __fadd_rn(res[a1], v2.y);
-        } else if (dims == 4 || dims == 8) {
-          const int o = dest + si * dims;
-          for (int d = 0; d < dims; d += 4) {
-            const float4 v4 = VPZ_LDG(reinterpret_cast<const float4*>(lk + d));
-            const int a0 = k1b_sw(o + d), a1 = k1b_sw(o + d + 1), a2 = k1b_sw(o + d + 2), a3 = k1b_sw(o + d + 3);
-            res[a0] = __fadd_rn(res[a0], v4.x);
-            res[a1] = __fadd_rn(res[a1], v4.y);
-            res[a2] = __fadd_rn(res[a2], v4.z);
-            res[a3] = __fadd_rn(res[a3], v4.w);
-          }
-        } else {
-          // any other dimension; the last entry of a unit may run past the partition when dims does
-          // not divide it, and the reference then keeps writing (bounded by the vector length)
-          const int vend = g.rtype == 2 ? g.vlen : (dest / half) * half + half;
-          for (int d = 0; d < dims; d++) {
-            const int o = dest + si * dims + d;
-            if (o < vend) {
-              const int at = k1b_sw(o);
-              res[at] = __fadd_rn(res[at], VPZ_LDG(lk + d));
-            }
-          }
-        }
-      }
-      stage_base += carry;
+    if (nch == 0) continue;
+    const VpzResidue* rs = residues + mp->submap_residue[sm];
+    const K1ResGeom g = k1_res_geom(rs, nch, half, flags);
+    rtype_single = g.rtype;
+    if (multi && g.rtype == 2) {
+      // Residue2.Decode (Residue2.cs:12-52): all flagged -> the slots are cleared; else a FRESH zeroed vector
+      // is decoded and de-interleaved over the slots (both overwrite slots 0 .. nch-1 completely)
+      for (int i = tid; i < nch * half; i += K1B_THREADS) res[k1b_sw(i)] = 0.f;
       __syncthreads();
+    }
+    const int nunits = g.part_count * g.nvec;       // decode order inside a stage: partition major
+    // ---- per stage: unit scan, then entry-parallel accumulate --------------------------------------
+    if (g.part_count > 0 && g.any && stage_base < n_ent) {
+      for (int stage = 0; stage < rs->max_stages && stage_base < n_ent; stage++) {
+        // entries per unit -> exclusive prefix sum = where each unit's entries start
+        uint32_t carry = 0;
+        for (int u0 = 0; u0 < nunits; u0 += K1B_THREADS) {
+          const int u = u0 + tid;
+          int cnt = 0;
+          uint32_t info = 0, vqoff = 0;   // info: dims | first bin << 8
+          if (u < nunits) {
+            const int part = u / g.nvec, v = u - part * g.nvec;
+            if (!((g.skip >> v) & 1u)) {
+              const int c = rec_cls[u];
+              if (((rs->cascade[c] >> stage) & 1u) && rs->has_books[c]) {
+                const VpzBook* bk = books + rs->books[c][stage];
+                const int dims = k1_book_dims(bk);
+                cnt = k1_unit_entries(g.rtype, g.psize, dims);
+                vqoff = VPZ_LDG(&bk->vq_off);
+                info = (uint32_t)(dims & 0xff) | ((uint32_t)(g.begin + part * g.psize + v * half) << 8);   // rtype 2: v == 0
+              }
+            }
+          }
+          int incl = cnt;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+          }
+          if (lane == 31) scan[wid] = incl;
+          __syncthreads();
+          int before = 0, round_total = 0;
+#pragma unroll
+          for (int w = 0; w < K1B_THREADS / 32; w++) {
+            const int t = scan[w];
+            if (w < wid) before += t;
+            round_total += t;
+          }
+          if (u < nunits) {
+            ustart[u] = (int)carry + before + incl - cnt;
+            uinfo[u] = info;
+            uvq[u] = vqoff;
+          }
+          carry += (uint32_t)round_total;
+          __syncthreads();
+        }
+        // ---- every thread takes single ENTRIES (codewords) of the stage, not whole units: the work is
+        // spread evenly however the active units are distributed.  The unit of entry e is the last one
+        // whose start is <= e (idle units have zero length and sort before the active unit that shares
+        // their start).  A bin is touched once per stage and the stages run in order, so the sums
+        // round exactly like the reference's stage-major accumulation.
+        uint32_t stage_n = carry;
+        if (stage_base + stage_n > n_ent) stage_n = n_ent - stage_base;   // truncated packet: keep what was decoded
+        const uint16_t* ep = ent + stage_base;
+        for (uint32_t e = (uint32_t)tid; e < stage_n; e += K1B_THREADS) {
+          int lo = 0, hi = nunits;   // ustart[lo] <= e < ustart[hi] (virtual ustart[nunits] = +inf)
+          while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if ((uint32_t)ustart[mid] <= e) lo = mid; else hi = mid;
+          }
+          const uint32_t info = uinfo[lo];
+          const int dims = (int)(info & 0xffu);
+          const int si = (int)(e - (uint32_t)ustart[lo]);        // index of the entry inside its unit
+          const int dest = (int)(info >> 8);                     // first bin of the unit
+          const float* lk = reinterpret_cast<const float*>(blob + uvq[lo]) + (size_t)ep[e] * dims;
+          if (g.rtype == 0) {
+            // Residue0.WriteVectors (Residue0.cs:208-231), quirk Q6: dims summed into one bin
+            float r = 0.f;
+            for (int d = 0; d < dims; d++) r = __fadd_rn(r, VPZ_LDG(lk + d));
+            const int at = k1b_sw(dest + si);
+            res[at] = __fadd_rn(res[at], r);
+          } else if (dims == 2) {
+            // Residue1.WriteVectors (Residue1.cs:12-34)
+            const float2 v2 = VPZ_LDG(reinterpret_cast<const float2*>(lk));
+            const int o = dest + si * 2;
+            const int a0 = k1b_sw(o), a1 = k1b_sw(o + 1);
+            res[a0] = __fadd_rn(res[a0], v2.x);
+            res[a1] = __fadd_rn(res[a1], v2.y);
+          } else if (dims == 4 || dims == 8) {
+            const int o = dest + si * dims;
+            for (int d = 0; d < dims; d += 4) {
+              const float4 v4 = VPZ_LDG(reinterpret_cast<const float4*>(lk + d));
+              const int a0 = k1b_sw(o + d), a1 = k1b_sw(o + d + 1), a2 = k1b_sw(o + d + 2), a3 = k1b_sw(o + d + 3);
+              res[a0] = __fadd_rn(res[a0], v4.x);
+              res[a1] = __fadd_rn(res[a1], v4.y);
+              res[a2] = __fadd_rn(res[a2], v4.z);
+              res[a3] = __fadd_rn(res[a3], v4.w);
+            }
+          } else {
+            // any other dimension; the last entry of a unit may run past the partition when dims does
+            // not divide it, and the reference then keeps writing (bounded by the vector length)
+            const int vend = g.rtype == 2 ? g.vlen : (dest / half) * half + half;
+            for (int d = 0; d < dims; d++) {
+              const int o = dest + si * dims + d;
+              if (o < vend) {
+                const int at = k1b_sw(o);
+                res[at] = __fadd_rn(res[at], VPZ_LDG(lk + d));
+              }
+            }
+          }
+        }
+        stage_base += carry;
+        __syncthreads();
+      }
+    }
+    rec_cls += ((nunits + 3) >> 2) << 2;
+    if (multi) stage_base = n_ent;   // the next submap's entry indices start where this one's really end
+    if (multi) {
+      // Mapping.cs:150-160: slot c -> channel buffer of the c-th channel of the submap, always (also when
+      // nothing was decoded: the slot then still holds what earlier submaps left)
+      __syncthreads();
+      const bool inter = g.rtype == 2 && g.any && nch > 1;   // the interleaved type 2 vector sits in [0, nch * half)
+      for (int c = 0; c < nch; c++) {
+        const int ch = (int)((chans >> (4 * c)) & 15u);
+        for (int i = tid; i < half; i += K1B_THREADS) out[ch * half + i] = res[k1b_sw(inter ? i * nch + c : c * half + i)];
+      }
+      __syncthreads();
+      if (inter) {   // the slots now hold the de-interleaved channels (Residue2.cs:42-50) for the submaps to come
+        for (int c = 0; c < nch; c++) {
+          const int ch = (int)((chans >> (4 * c)) & 15u);
+          for (int i = tid; i < half; i += K1B_THREADS) res[k1b_sw(c * half + i)] = out[ch * half + i];
+        }
+        __syncthreads();
+      }
     }
   }
   __syncthreads();
+  if (multi) {   // every channel belongs to exactly one submap: fetch them back, channel-major
+    for (int i = tid; i < total; i += K1B_THREADS) res[k1b_sw(i)] = out[i];
+    __syncthreads();
+  }
+  const bool interleaved = !multi && rtype_single == 2;
 
   // accessor of channel c, bin i after the Residue2 de-interleave (Residue2.cs:42-50)
-#define RES_AT(c, i) res[k1b_sw(g.rtype == 2 ? (i) * C + (c) : (c) * half + (i))]
+#define RES_AT(c, i) res[k1b_sw(interleaved ? (i) * C + (c) : (c) * half + (i))]
 
   if (DEBUG && P.dbg.residue) {
     for (int c = 0; c < C; c++)
@@ -702,17 +882,69 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
     __syncthreads();
   }
 
-  // ---- floor line render + dB multiply + store (Floor1.cs:222-268, 372-397) -------------------
-  // RenderLineMulti in closed form: after k steps of the DDA  y = y0 + sy * floor(k * |dy| / adx)
-  // (base*k + sy*floor(k*rem/adx) with |dy| = |base|*adx + rem).  This path is the rare one: a plain
-  // integer division per bin.  Lanes walk the bins K1B_THREADS at a time; every thread keeps its own
-  // (monotone) segment cursor.
+  // ---- floor curve + multiply + store ------------------------------------------------------------
+  // Floor 1 (Floor1.cs:222-268, 372-397): RenderLineMulti in closed form: after k steps of the DDA
+  // y = y0 + sy * floor(k * |dy| / adx) (base*k + sy*floor(k*rem/adx) with |dy| = |base|*adx + rem).  This
+  // path is the rare one: a plain integer division per bin.  Lanes walk the bins K1B_THREADS at a time;
+  // every thread keeps its own (monotone) segment cursor.
+  // Floor 0 (Floor0.cs:169-224): the LSP curve, one value per bark band, evaluated per bin.
   const float* db = reinterpret_cast<const float*>(blob + H->db_off);
-  float* out = P.spec + pk.spec_off;
   uint32_t* sg = reinterpret_cast<uint32_t*>(ustart);   // per segment: x0 | x1 << 16, y0 | (|dy| << 16), sign
   for (int ch = 0; ch < C; ch++) {
     if (!((own_mask >> ch) & 1u)) continue;  // Mapping.cs:185-194: silent channel, K3 sees zeros
     const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
+    if (seg[0] & 0x80000000u) {
+      const VpzFloor1* fl = reinterpret_cast<const VpzFloor1*>(blob + H->floors_off) + mp->submap_floor[mp->mux[ch]];
+      const int order = fl->f0.order;
+      float* coeff = reinterpret_cast<float*>(ustart);
+      __syncthreads();
+      if (tid == 0) {
+        // Floor0.Unpack, second half (Floor0.cs:138-166): lookup vectors, the "averaging", then 2 cos (:186-189)
+        const VpzBook* bk = books + fl->f0.books[seg[0] & 0xffu];
+        const int dims = k1_book_dims(bk);
+        const float* vq = reinterpret_cast<const float*>(blob + VPZ_LDG(&bk->vq_off));
+        const uint16_t* fe = ent + seg[2];
+        for (int i = 0, e = 0; i < order; e++) {
+          const float* lk = vq + (size_t)fe[e] * dims;
+          for (int j = 0; i < order && j < dims; j++, i++) coeff[i] = VPZ_LDG(lk + j);
+        }
+        float last = 0.f;
+        for (int j = 0; j < order;) {
+          for (int k = 0; j < order && k < dims; j++, k++) coeff[j] = __fadd_rn(coeff[j], last);
+          last = coeff[j - 1];
+        }
+        for (int j = 0; j < order; j++) coeff[j] = __fmul_rn(2.f, cosf(coeff[j]));
+      }
+      __syncthreads();
+      // Amp = (float)(amp * ampOfs / (double)((1 << ampBits) - 1)) (Floor0.cs:121-123; int shift, wrapping)
+      const double amp_div = (double)(int32_t)((1u << (fl->f0.amp_bits & 31)) - 1u);
+      const float amp = (float)((double)((uint64_t)seg[1] * (uint64_t)fl->f0.amp_ofs) / amp_div);
+      const float amp_ofs = (float)fl->f0.amp_ofs;
+      const int w = long_block ? 1 : 0;   // BlockSizes.IndexOf: equal sizes resolve to index 0, whose tables are identical
+      const uint16_t* bark = reinterpret_cast<const uint16_t*>(blob + fl->f0.bark_off[w]);
+      const float* wmap = reinterpret_cast<const float*>(blob + fl->f0.wmap_off[w]);
+      for (int x = tid; x < half; x += K1B_THREADS) {
+        const float wv = VPZ_LDG(wmap + VPZ_LDG(bark + x));
+        float p = .5f, q = .5f;
+        int j;
+        for (j = 1; j < order; j += 2) {
+          q = __fmul_rn(q, __fsub_rn(wv, coeff[j - 1]));
+          p = __fmul_rn(p, __fsub_rn(wv, coeff[j]));
+        }
+        if (j == order) {   // odd order filter; slightly asymmetric
+          q = __fmul_rn(q, __fsub_rn(wv, coeff[j - 1]));
+          p = __fmul_rn(p, __fmul_rn(p, __fsub_rn(4.f, __fmul_rn(wv, wv))));
+          q = __fmul_rn(q, q);
+        } else {            // even order filter; still symmetric
+          p = __fmul_rn(p, __fmul_rn(p, __fsub_rn(2.f, wv)));
+          q = __fmul_rn(q, __fmul_rn(q, __fadd_rn(2.f, wv)));
+        }
+        q = __fsub_rn(amp / sqrtf(__fadd_rn(p, q)), amp_ofs);
+        q = expf(__fmul_rn(q, 0.11512925f));
+        out[ch * half + x] = __fmul_rn(RES_AT(ch, x), q);
+      }
+      continue;
+    }
     const int nseg = (int)seg[0];
     __syncthreads();
     for (int s = tid; s < nseg; s += K1B_THREADS) {
@@ -1198,38 +1430,39 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   __syncwarp();
 }
 
-// The kernel body: gather path = every warp takes its own packets; general path = the CTA takes them.
+// The kernel bodies: gather path = every warp takes its own packets; general path = the CTA takes them.
 template <bool DEBUG>
-VPZ_DEV void k1b_cta_loop(const K1Params& P, uint32_t* smem, uint32_t* s_idx) {
+VPZ_DEV void k1b_gather_loop(const K1Params& P, uint32_t* smem) {
   const int tid = (int)threadIdx.x;
-  if (P.gather_ok) {
-    const int lane = tid & 31, warp = tid >> 5;
-    // inverse_dB_table (Floor1.cs:407-473): identical in every setup image, staged once per CTA
-    float* dbtab = reinterpret_cast<float*>(smem);
-    {
-      const uint32_t* blob0 = P.setups[0];
-      const float* db = reinterpret_cast<const float*>(blob0 + reinterpret_cast<const VpzSetupHdr*>(blob0)->db_off);
-      for (int i = tid; i < 256; i += K1B_THREADS) dbtab[i] = VPZ_LDG(db + i);
-    }
+  const int lane = tid & 31, warp = tid >> 5;
+  // inverse_dB_table (Floor1.cs:407-473): identical in every setup image, staged once per CTA
+  float* dbtab = reinterpret_cast<float*>(smem);
+  {
+    const uint32_t* blob0 = P.setups[0];
+    const float* db = reinterpret_cast<const float*>(blob0 + reinterpret_cast<const VpzSetupHdr*>(blob0)->db_off);
+    for (int i = tid; i < 256; i += K1B_THREADS) dbtab[i] = VPZ_LDG(db + i);
+  }
+  __syncthreads();
+  uint32_t* my = smem + 256 + (size_t)warp * P.smem_words_per_warp;
+  for (;;) {
+    uint32_t idx = 0;
+    if (lane == 0) idx = atomicAdd(P.counter, 1u);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= P.n_pkts) break;
+    // same order as K1a: grouped by (setup, block size), so the warps resident on an SM run the same
+    // code paths on the same VQ tables
+    k1b_build_packet_gather<DEBUG>(P, P.order ? P.order[idx] : idx, my, dbtab, lane);
+  }
+}
+template <bool DEBUG>
+VPZ_DEV void k1b_general_loop(const K1Params& P, uint32_t* smem, uint32_t* s_idx) {
+  const int tid = (int)threadIdx.x;
+  for (;;) {
     __syncthreads();
-    uint32_t* my = smem + 256 + (size_t)warp * P.smem_words_per_warp;
-    for (;;) {
-      uint32_t idx = 0;
-      if (lane == 0) idx = atomicAdd(P.counter, 1u);
-      idx = __shfl_sync(0xffffffffu, idx, 0);
-      if (idx >= P.n_pkts) break;
-      // same order as K1a: grouped by (setup, block size), so the warps resident on an SM run the same
-      // code paths on the same VQ tables
-      k1b_build_packet_gather<DEBUG>(P, P.order ? P.order[idx] : idx, my, dbtab, lane);
-    }
-  } else {
-    for (;;) {
-      __syncthreads();
-      if (tid == 0) *s_idx = atomicAdd(P.counter, 1u);
-      __syncthreads();
-      const uint32_t idx = *s_idx;
-      if (idx >= P.n_pkts) break;
-      k1b_build_packet_general<DEBUG>(P, P.order ? P.order[idx] : idx, smem, tid);
-    }
+    if (tid == 0) *s_idx = atomicAdd(P.counter, 1u);
+    __syncthreads();
+    const uint32_t idx = *s_idx;
+    if (idx >= P.n_pkts) break;
+    k1b_build_packet_general<DEBUG>(P, P.order ? P.order[idx] : idx, smem, tid);
   }
 }

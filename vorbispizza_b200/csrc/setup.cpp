@@ -409,6 +409,69 @@ int parse_floor1(BitReader& br, int nbooks, VpzFloor1& f, std::string& err) {
   return VPZ_OK;
 }
 
+// Floor0 ctor (Floor0.cs:39-76) with SynthesizeBarkCurve (:83-96) and SynthesizeWDelMap (:103-113).
+// The tables go into the blob later (bark[w], wmap[w]).
+struct HostFloor0 {
+  std::vector<uint16_t> bark[2];
+  std::vector<float> wmap[2];
+};
+float floor0_to_bark(double lsp) {   // Floor0.ToBARK (Floor0.cs:98-101): double arithmetic, rounded to float
+  return (float)(13.1 * atan(0.00074 * lsp) + 2.24 * atan(0.0000000185 * lsp * lsp) + .0001 * lsp);
+}
+int parse_floor0(BitReader& br, const std::vector<HostBook>& books, const IdHeader& id, VpzFloor1& f, HostFloor0& t,
+                 std::string& err) {
+  memset(&f, 0, sizeof(f));
+  f.floor_type = 0;
+  const int order = (int)br.read(8), rate = (int)br.read(16), bark_map_size = (int)br.read(16);
+  const int amp_bits = (int)br.read(6), amp_ofs = (int)br.read(8), nb = (int)br.read(4) + 1;
+  if (order < 1 || rate < 1 || bark_map_size < 1) {
+    err = "floor0 with zero order / rate / bark map size";
+    return VPZ_E_INVALID_DATA;
+  }
+  if (amp_bits < 1 || amp_bits > 32) {
+    // amp_bits 0: the reference divides 0 by 0 and renders NaN; > 32 does not fit the GPU bit reader
+    err = "floor0 amplitude width outside 1..32 bits is not on the GPU path";
+    return VPZ_E_UNSUPPORTED;
+  }
+  f.f0.order = (uint8_t)order;
+  f.f0.rate = (uint16_t)rate;
+  f.f0.bark_map_size = (uint16_t)bark_map_size;
+  f.f0.amp_bits = (uint8_t)amp_bits;
+  f.f0.amp_ofs = (uint8_t)amp_ofs;
+  f.f0.nbooks = (uint8_t)nb;
+  f.f0.book_bits = (uint8_t)ilog(nb);
+  for (int i = 0; i < nb; i++) {
+    const int num = (int)br.read(8);
+    if (num >= (int)books.size() || books[(size_t)num].map_type == 0 || books[(size_t)num].dims < 1) {
+      err = "floor0 book without lookup";
+      return VPZ_E_INVALID_DATA;
+    }
+    f.f0.books[i] = (uint8_t)num;
+  }
+  for (int w = 0; w < 2; w++) {
+    const int n = (w ? id.size1 : id.size0) / 2;
+    volatile float scale = (float)bark_map_size / floor0_to_bark(rate / 2.0);   // ushort / float in fp32
+    t.bark[w].assign((size_t)n, 0);
+    for (int i = 0; i < n - 1; i++) {   // i < map.Length - 2: bin n-1 keeps the default 0 (Floor0.cs:88-94)
+      volatile float prod = floor0_to_bark((rate / 2.0) / n * i) * scale;
+      const int v = std::min(bark_map_size - 1, (int)floor((double)prod));
+      if (v >= n || v < 0) {
+        // Apply reads wMap[barkMap[i]] with wMap of n entries (Floor0.cs:192): the reference faults here
+        err = "floor0 bark map index beyond the block (the reference reads out of range)";
+        return VPZ_E_UNSUPPORTED;
+      }
+      t.bark[w][(size_t)i] = (uint16_t)v;
+    }
+    volatile float wdel = (float)(M_PI / bark_map_size);
+    t.wmap[w].assign((size_t)n, 0.f);
+    for (int i = 0; i < n; i++) {
+      volatile float a = wdel * (float)i;
+      t.wmap[w][(size_t)i] = 2.0f * cosf(a);
+    }
+  }
+  return VPZ_OK;
+}
+
 // Residue0 ctor (Residue0.cs:25-115)
 int parse_residue(BitReader& br, int type, const std::vector<HostBook>& books, VpzResidue& r,
                   std::vector<uint8_t>& decode_map, std::string& err) {
@@ -562,11 +625,12 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
 
   int nfloors = (int)br.read(6) + 1;
   std::vector<VpzFloor1> floors((size_t)nfloors);
+  std::vector<HostFloor0> floors0((size_t)nfloors);
   for (int i = 0; i < nfloors; i++) {
     int type = (int)br.read(16);
     if (type == 0) {
-      error = "floor type 0 (LSP) is not on the GPU path yet";
-      return VPZ_E_UNSUPPORTED;
+      if ((rc = parse_floor0(br, books, id, floors[i], floors0[i], error)) != VPZ_OK) return rc;
+      continue;
     }
     if (type != 1) {
       error = "invalid floor type";
@@ -595,10 +659,39 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
       return VPZ_E_INVALID_DATA;
     }
     if ((rc = parse_mapping(br, id.channels, nfloors, nres, mappings[i], error)) != VPZ_OK) return rc;
-    if (mappings[i].submaps > 1) {
-      error = "mappings with more than one submap are not on the GPU path yet";
-      return VPZ_E_UNSUPPORTED;
+  }
+  // Residue INSTANCES (vpz_dev.h): the first nres are the header's residues serving all channels (what a
+  // single-submap mapping uses); a submap with fewer channels gets its own instance, because the walk
+  // tables depend on the number of vectors.  submap_residue is rewritten to instance indices.
+  n_residues_hdr = nres;
+  {
+    std::vector<int> inst_nch((size_t)nres, id.channels), inst_src((size_t)nres);
+    for (int i = 0; i < nres; i++) inst_src[(size_t)i] = i;
+    for (int i = 0; i < nmaps; i++) {
+      VpzMapping& m = mappings[(size_t)i];
+      for (int j = 0; j < m.submaps; j++) {
+        int nch = 0;
+        for (int c = 0; c < id.channels; c++) nch += (m.submaps > 1 ? m.mux[c] : 0) == j;
+        const int src = m.submap_residue[j];
+        int found = -1;
+        for (size_t k = 0; k < inst_src.size(); k++)
+          if (inst_src[k] == src && inst_nch[k] == std::max(nch, 1)) found = (int)k;
+        if (found < 0) {
+          found = (int)inst_src.size();
+          inst_src.push_back(src);
+          inst_nch.push_back(std::max(nch, 1));
+          dmaps.push_back(dmaps[(size_t)src]);
+          residues.push_back(residues[(size_t)src]);
+        }
+        if (found > 255) {
+          error = "more than 255 (residue, submap width) combinations are not on the GPU path";
+          return VPZ_E_UNSUPPORTED;
+        }
+        m.submap_residue[j] = (uint8_t)found;
+      }
     }
+    for (size_t k = 0; k < residues.size(); k++) residues[k].nch = (uint16_t)inst_nch[k];
+    nres = (int)residues.size();
   }
 
   int nmodes = (int)br.read(6) + 1;
@@ -657,7 +750,7 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
     // restate the tests of Residue0.Decode (Residue0.cs:160-190: cascade bit + book present) as lookups.
     VpzResidue& r = residues[i];
     const int cdim = books[r.class_book].dims;
-    const int nvec = r.type == 2 ? 1 : id.channels;
+    const int nvec = r.type == 2 ? 1 : r.nch;
     const int partvals = (int)(r.decode_map_len / (uint32_t)std::max(cdim, 1));
     r.cdim = (uint16_t)cdim;
     r.nvec = (uint16_t)nvec;
@@ -719,6 +812,16 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
   h.nbooks = (uint32_t)nbooks;
   bw.align(4);
   h.books_off = bw.put_struct_array(dbooks);
+  for (int i = 0; i < nfloors; i++) {
+    if (floors[i].floor_type != 0) continue;
+    for (int w = 0; w < 2; w++) {
+      bw.align(4);
+      floors[i].f0.bark_off[w] = bw.reserve((floors0[i].bark[w].size() + 1) / 2);
+      memcpy(&blob[floors[i].f0.bark_off[w]], floors0[i].bark[w].data(), floors0[i].bark[w].size() * 2);
+      bw.align(4);
+      floors[i].f0.wmap_off[w] = bw.put_floats(floors0[i].wmap[w].data(), floors0[i].wmap[w].size());
+    }
+  }
   bw.align(4);
   h.floors_off = bw.put_struct_array(floors);
   bw.align(4);

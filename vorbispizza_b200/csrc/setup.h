@@ -38,6 +38,7 @@ class Setup {
   int mode_bits = 0;
   uint64_t hash = 0;            // content hash of (id packet, setup packet) for de-duplication
   int max_codeword_bits = 0;
+  int n_residues_hdr = 0;       // residues in the setup header (the device image holds instances, vpz_dev.h)
   std::string error;
 
   // Returns 0 or a negative VPZ_E_* code (include/vpz.h); `error` holds the reason.

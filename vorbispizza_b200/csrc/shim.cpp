@@ -161,7 +161,7 @@ int vpz_setup_get_info(const vpz_setup* s, vpz_setup_info* info) {
   info->block_size1 = s->host.id.size1;
   info->n_books = (int32_t)h->nbooks;
   info->n_floors = h->nfloors;
-  info->n_residues = h->nresidues;
+  info->n_residues = s->host.n_residues_hdr;
   info->n_mappings = h->nmappings;
   info->n_modes = h->nmodes;
   info->max_codeword_bits = s->host.max_codeword_bits;

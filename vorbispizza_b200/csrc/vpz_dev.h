@@ -54,6 +54,19 @@ struct VpzFloor1 {
   uint8_t hneigh[VPZ_MAX_POSTS + 1];
   uint8_t sortidx[VPZ_MAX_POSTS + 1];
   uint8_t pad1[3];
+  // ---- floor 0 (Floor0.cs:39-113), valid when floor_type == 0 ----
+  struct {
+    uint8_t order;          // 1..255 LSP coefficients
+    uint8_t amp_bits;       // 1..32 on the GPU path
+    uint8_t amp_ofs;
+    uint8_t nbooks;         // 1..16
+    uint8_t book_bits;      // ilog(nbooks)
+    uint8_t pad[3];
+    uint16_t rate, bark_map_size;
+    uint8_t books[16];
+    uint32_t bark_off[2];   // per block size: uint16 bark index per bin, n entries (entry n-1 is 0: Floor0.cs:88-94)
+    uint32_t wmap_off[2];   // per block size: 2 cos(pi / bark_map_size * k), n floats, indexed by BARK index
+  } f0;
 };
 
 // ---- residue 0/1/2 (Residue0.cs:25-115) -------------------------------------------------
@@ -78,8 +91,13 @@ struct VpzResidue {
   uint32_t cw_tab_off;
   uint32_t partvals;         // classifications ^ classbook.dims
   uint16_t cdim;             // classbook.dims (partitions per classword)
-  uint16_t nvec;             // vectors the residue decodes: 1 for type 2, else the channel count
+  uint16_t nvec;             // vectors the residue decodes: 1 for type 2, else nch
+  uint16_t nch;              // channels of the submap this INSTANCE serves (Mapping.cs:136-146)
+  uint16_t pad2;
 };
+// The device image holds residue INSTANCES: one per distinct (residue, channels of the submap) pair that a
+// mapping uses, because the walk tables (cw_tab) depend on the number of vectors.  A stream whose mappings
+// have a single submap has exactly one instance per residue, in header order.
 
 // ---- mapping (Mapping.cs:19-95) ---------------------------------------------------------
 struct VpzMapping {
@@ -88,7 +106,7 @@ struct VpzMapping {
   uint8_t pad[2];
   uint8_t mag[32], ang[32];       // GPU path: at most 32 coupling steps
   uint8_t mux[VPZ_MAX_CH];
-  uint8_t submap_floor[16], submap_residue[16];
+  uint8_t submap_floor[16], submap_residue[16];   // submap_residue: residue INSTANCE index (see VpzResidue)
 };
 
 struct VpzMode {
