@@ -458,12 +458,13 @@ def synth_stage_parity(ctx, shape, seed, n_packets=40, mean_len=120):
     return n
 
 
-def assert_pcm_close_scaled(got, ref, what="", rtol=PCM_TOL):
-    """PCM of generated streams is not normalised to +-1: the 1e-5 bar applies relative to the peak."""
+def assert_pcm_close_scaled(got, ref, what="", rtol=PCM_TOL, peak=None):
+    """PCM of generated streams is not normalised to +-1: the 1e-5 bar applies relative to the peak (of the
+    UNCLIPPED signal: clipping hides the peak but not the rounding error of the samples below it)."""
     assert got.shape == ref.shape, (what, got.shape, ref.shape)
     if got.size == 0:
         return
-    scale = max(float(np.abs(ref).max()), 1.0)
+    scale = max(float(np.abs(ref).max()), 1.0) if peak is None else max(peak, 1.0)
     err = float(np.abs(got - ref).max())
     assert err <= rtol * scale, "%s: max abs err %.3g > %.1g x peak %.3g" % (what, err, rtol, scale)
 
@@ -479,11 +480,14 @@ def synth_stream_parity(ctx, shape, seed, n_packets=40, clip=False, lookahead=7,
     ref, _, fault = s.decode_all()
     assert not fault
     assert np.isfinite(ref).all(), "generated stream overflows in the oracle: not a usable fixture"
+    su = ob.OracleStream(data)
+    su.set_clip(False)
+    peak = float(np.abs(su.decode_all()[0]).max(initial=0.0))
     floor0 = any(f["type"] == 0 for f in st["info"]["floors"])
     rtol = PCM_TOL + (40 * FLOOR0_RTOL if floor0 else 0.0)
     pcm, counts = decode_files(ctx, [data], clip=clip)
     assert counts[0] == ref.shape[0], (shape, seed, counts[0], ref.shape)
-    assert_pcm_close_scaled(pcm.reshape(-1, s.channels), ref, "%s seed %d bulk" % (shape, seed), rtol)
+    assert_pcm_close_scaled(pcm.reshape(-1, s.channels), ref, "%s seed %d bulk" % (shape, seed), rtol, peak)
     s2 = ob.OracleStream(data)
     s2.set_clip(clip)
     with VorbisReader(ctx, data, lookahead=lookahead) as r:
@@ -499,7 +503,7 @@ def synth_stream_parity(ctx, shape, seed, n_packets=40, clip=False, lookahead=7,
             assert r.sample_position == s2.sample_position and r.is_end_of_stream == s2.is_end_of_stream
             if no <= 0:
                 break
-            assert_pcm_close_scaled(b[:ng * ch], a[:no * ch], "%s seed %d read" % (shape, seed), rtol * max(float(np.abs(ref).max()), 1.0))
+            assert_pcm_close_scaled(b[:ng * ch], a[:no * ch], "%s seed %d read" % (shape, seed), rtol, peak)
             total += no
         assert total == ref.shape[0]
     return total
@@ -522,9 +526,12 @@ def synth_mixed_batch_parity(ctx, shape_seeds, n_packets=20, with_files=(), clip
         s = ob.OracleStream(d)
         s.set_clip(clip)
         ref, _, _ = s.decode_all()
+        su = ob.OracleStream(d)
+        su.set_clip(False)
+        peak = float(np.abs(su.decode_all()[0]).max(initial=0.0))
         assert cnt == ref.shape[0], (name, cnt, ref.shape)
         got = pcm[off:off + cnt * s.channels].reshape(-1, s.channels)
         off += cnt * s.channels
         rtol = PCM_TOL + (40 * FLOOR0_RTOL if name.startswith("floor0") else 0.0)
-        assert_pcm_close_scaled(got, ref, "mixed batch " + name, rtol)
+        assert_pcm_close_scaled(got, ref, "mixed batch " + name, rtol, peak)
     assert off == pcm.size

@@ -49,7 +49,14 @@ def main():
     rows = list(csv.reader(io.StringIO(txt)))
     hdr = rows[1]
     ix = {k: i for i, k in enumerate(hdr)}
-    data = [r for r in rows[2:] if len(r) > ix["Instructions Executed"]]
+    # ncu prints the SASS listing once per matching launch / view, each behind its own "Kernel Name" row:
+    # the first block is the one joined with the disassembly
+    body = rows[2:]
+    for k, r in enumerate(body):
+        if r and r[0] == "Kernel Name":
+            body = body[:k]
+            break
+    data = [r for r in body if len(r) > ix["Instructions Executed"]]
     sass = sass_lines(func)
     if len(sass) != len(data):
         print("warning: %d SASS instructions vs %d ncu rows (stale .so?)" % (len(sass), len(data)))
