@@ -118,6 +118,15 @@ inline int __any_sync(unsigned, int pred) {
   w->bar.wait();
   return r;
 }
+inline uint32_t __ballot_sync(unsigned, int pred) {
+  emu::WarpCtx* w = emu::t_block->warps[emu::t_warp];
+  w->slot[emu::t_lane] = pred ? 1u : 0u;
+  w->bar.wait();
+  uint32_t r = 0;
+  for (int i = 0; i < 32; i++) r |= w->slot[i] << i;
+  w->bar.wait();
+  return r;
+}
 inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
   sh &= 31;
   uint64_t v = ((uint64_t)hi << 32) | lo;

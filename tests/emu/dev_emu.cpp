@@ -62,7 +62,13 @@ void make_current(int) {}
 int device_count() { return 1; }
 int sm_count() { return 1; }
 size_t max_smem_per_block() { return 227 * 1024; }
-void* alloc(size_t bytes, std::string&) { return calloc(1, bytes + 64); }
+void* alloc(size_t bytes, std::string&) {
+  // device memory is NOT zeroed by cudaMalloc: poison it (0xff bytes = NaN floats, huge indices) so that a
+  // kernel reading something no kernel wrote shows up in the CPU suite
+  void* p = malloc(bytes + 64);
+  if (p) memset(p, 0xff, bytes + 64);
+  return p;
+}
 void free(void* p) { ::free(p); }
 void* host_alloc(size_t bytes) { return calloc(1, bytes + 64); }
 void host_free(void* p) { ::free(p); }

@@ -666,7 +666,7 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
     VpzPktRes r;
     r.exec_mask = (uint8_t)own_mask;
     r.status = (uint8_t)((hdr >> 16) & 0xffu);
-    r.bits_used_lo = (uint16_t)rec[2];
+    r.end16[0] = r.end16[1] = 255;   // this path writes every bin
     P.res[pkt_idx] = r;
   }
   if (own_mask == 0 && !(DEBUG && P.dbg.residue)) return;  // every channel silent: K3 outputs zeros
@@ -1177,14 +1177,16 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   const int long_block = (int)(hdr >> 24) & 1;
   const int half = long_block ? half_max : (1 << (H->log2_size0 - 1));
 
-  if (tid == 0) {
-    VpzPktRes r;
-    r.exec_mask = (uint8_t)own_mask;
-    r.status = (uint8_t)((hdr >> 16) & 0xffu);
-    r.bits_used_lo = (uint16_t)rh.z;
-    P.res[pkt_idx] = r;
+  if (own_mask == 0 && !(DEBUG && P.dbg.residue)) {  // every channel silent: K3 outputs zeros
+    if (tid == 0) {
+      VpzPktRes r;
+      r.exec_mask = 0;
+      r.status = (uint8_t)((hdr >> 16) & 0xffu);
+      r.end16[0] = r.end16[1] = 0;
+      P.res[pkt_idx] = r;
+    }
+    return;
   }
-  if (own_mask == 0 && !(DEBUG && P.dbg.residue)) return;  // every channel silent: K3 outputs zeros
 
   // mapping and residue index come with the record (K1a found them through the mode): no second walk
   const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + (rh.w & 0xffu);
@@ -1211,19 +1213,103 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   G.pshift = (g.psize & (g.psize - 1)) == 0 ? 31 - __clz(g.psize) : -1;
   G.span = g.part_count * g.psize;
   const bool have_res = g.part_count > 0 && g.any && G.n_ent > 0;
+  const bool pair = g.rtype == 2 && C == 2;
 
-  // Bins at and above the end of the coded residue range hold an exact +0 residue (zeroed buffer, and the
-  // inverse coupling of (+0, +0) is (+0, +0)), so their spectrum is +0 whatever the floor says: the floor
-  // is rendered and the gather runs only below res_end (a multiple of 16 bins); the rest is a zero fill.
-  // Typical streams code 69-92 % of the bins of a long block.
-  int res_end = 0;
+  // ---- phase B: per unit and stage, how many entries it holds -> first entry (all stages at once) ----
+  int act_units = 0;   // last unit that carries codewords in any stage, + 1
   if (have_res) {
-    const int span_end = g.begin + G.span;                          // in vector positions
-    const int bins = (g.rtype == 2 && C == 2) ? (span_end + 1) >> 1 : span_end;
+    const uint8_t* rec_cls = reinterpret_cast<const uint8_t*>(rec + K1_REC_HDR + C * K1_SEG_WORDS);
+    int carry[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) carry[s] = 0;
+    for (int u0 = 0; u0 < nunits; u0 += 32) {
+      const int u = u0 + tid;
+      int cnt[8];
+      uint32_t info[8], vqo[8];
+      int c = -1;
+      if (u < nunits) {
+        const int part = u / g.nvec, v = u - part * g.nvec;
+        if (!((g.skip >> v) & 1u)) c = rec_cls[u];
+      }
+      const uint2* ut = reinterpret_cast<const uint2*>(blob + rs->unit_tabb_off) + (c < 0 ? 0 : c) * 8;
+      bool any = false;
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        cnt[s] = 0;
+        info[s] = vqo[s] = 0;
+        if (s < max_stages) {
+          if (c >= 0) {   // {dims | log2 dims << 8 | entries << 16, vq word offset}; 0: no codewords for (class, stage)
+            const uint2 t = VPZ_LDG(ut + s);
+            info[s] = t.x & 0xffffu;
+            cnt[s] = (int)(t.x >> 16);
+            vqo[s] = t.y;
+            any = any || cnt[s] != 0;
+          }
+          int incl = cnt[s];
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+          }
+          const int round_total = __shfl_sync(0xffffffffu, incl, 31);
+          cnt[s] = carry[s] + incl - cnt[s];   // first entry of the unit inside the stage
+          carry[s] += round_total;
+        }
+      }
+      const uint32_t act = __ballot_sync(0xffffffffu, any);
+      if (act) act_units = u0 + 32 - __clz((int)act);
+      // absolute first entry = entries of all earlier stages + offset inside the stage; the stage
+      // totals are only complete after the last round, so the stage bases are added below
+      if (u < nunits) {
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+          if (s < max_stages) {
+            // idle units keep 0; the stage base added below never reaches bit 28 (engine.cpp bounds the packet size)
+            uint32_t* R = urec + (size_t)(s * U + u) * 2;
+            R[0] = info[s] ? ((((info[s] >> 8) & 0xfu) + 1u) << 28) | (uint32_t)cnt[s] : 0u;
+            R[1] = vqo[s];
+          }
+      }
+      __syncwarp();
+    }
+    // add the stage bases
+    uint32_t sbase[8];
+    uint32_t acc = 0;
+#pragma unroll
+    for (int s = 0; s < 8; s++) {
+      sbase[s] = acc;
+      if (s < max_stages) acc += (uint32_t)carry[s];
+    }
+    for (int u = tid; u < nunits; u += 32) {
+#pragma unroll
+      for (int s = 1; s < 8; s++)
+        if (s < max_stages && urec[(size_t)(s * U + u) * 2]) urec[(size_t)(s * U + u) * 2] += sbase[s];
+    }
+  }
+
+  // Bins above the packet's last ACTIVE residue partition hold an exact +0 residue (zeroed buffer, and the
+  // inverse coupling of (+0, +0) is (+0, +0)), so their spectrum is +0 whatever the floor says: the floor
+  // is rendered and the gather runs only below res_end (a multiple of 16 bins).  The TestFiles code nothing
+  // in 20 % (160 kb/s) to 87 % (48 kb/s) of the bins of a block.  For the 256 / 2048 IMDCT kernel the zero
+  // tail is not even written: end16 tells it where to stop reading.
+  int res_end = 0;
+  if (act_units > 0) {
+    const int part = g.nvec == 2 ? (act_units - 1) >> 1 : (act_units - 1);   // the gather path has one or two vectors
+    const int span_end = g.begin + (part + 1) * g.psize;              // in vector positions
+    const int bins = pair ? (span_end + 1) >> 1 : span_end;
     res_end = (bins + 15) & ~15;
     if (res_end > half) res_end = half;
   }
   if (DEBUG && P.dbg.residue) res_end = half;   // the debug dump wants every bin
+  const bool k3_reads_end = !DEBUG && H->log2_size0 == 8 && H->log2_size1 == 11;   // engine.cpp k3_fast (C <= 2 here)
+  if (tid == 0) {
+    VpzPktRes r;
+    r.exec_mask = (uint8_t)own_mask;
+    r.status = (uint8_t)((hdr >> 16) & 0xffu);
+    r.end16[0] = r.end16[1] = (uint8_t)(k3_reads_end ? res_end >> 4 : 255);
+    P.res[pkt_idx] = r;
+  }
+  __syncwarp();
 
   // ---- phase A: floor segments of every channel with energy, and their pieces of <= 16 bins -------
   int npieces0 = 0, npieces1 = 0;   // per channel (the gather path has at most two)
@@ -1267,73 +1353,6 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
     }
     if (ch == 0) npieces0 = carry; else npieces1 = carry;
   }
-
-  // ---- phase B: per unit and stage, how many entries it holds -> first entry (all stages at once) ----
-  if (have_res) {
-    const uint8_t* rec_cls = reinterpret_cast<const uint8_t*>(rec + K1_REC_HDR + C * K1_SEG_WORDS);
-    int carry[8];
-#pragma unroll
-    for (int s = 0; s < 8; s++) carry[s] = 0;
-    for (int u0 = 0; u0 < nunits; u0 += 32) {
-      const int u = u0 + tid;
-      int cnt[8];
-      uint32_t info[8], vqo[8];
-      int c = -1;
-      if (u < nunits) {
-        const int part = u / g.nvec, v = u - part * g.nvec;
-        if (!((g.skip >> v) & 1u)) c = rec_cls[u];
-      }
-      const uint2* ut = reinterpret_cast<const uint2*>(blob + rs->unit_tabb_off) + (c < 0 ? 0 : c) * 8;
-#pragma unroll
-      for (int s = 0; s < 8; s++) {
-        cnt[s] = 0;
-        info[s] = vqo[s] = 0;
-        if (s < max_stages) {
-          if (c >= 0) {   // {dims | log2 dims << 8 | entries << 16, vq word offset}; 0: no codewords for (class, stage)
-            const uint2 t = VPZ_LDG(ut + s);
-            info[s] = t.x & 0xffffu;
-            cnt[s] = (int)(t.x >> 16);
-            vqo[s] = t.y;
-          }
-          int incl = cnt[s];
-#pragma unroll
-          for (int d = 1; d < 32; d <<= 1) {
-            int n = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += n;
-          }
-          const int round_total = __shfl_sync(0xffffffffu, incl, 31);
-          cnt[s] = carry[s] + incl - cnt[s];   // first entry of the unit inside the stage
-          carry[s] += round_total;
-        }
-      }
-      // absolute first entry = entries of all earlier stages + offset inside the stage; the stage
-      // totals are only complete after the last round, so the stage bases are added below
-      if (u < nunits) {
-#pragma unroll
-        for (int s = 0; s < 8; s++)
-          if (s < max_stages) {
-            // idle units keep 0; the stage base added below never reaches bit 28 (engine.cpp bounds the packet size)
-            uint32_t* R = urec + (size_t)(s * U + u) * 2;
-            R[0] = info[s] ? ((((info[s] >> 8) & 0xfu) + 1u) << 28) | (uint32_t)cnt[s] : 0u;
-            R[1] = vqo[s];
-          }
-      }
-      __syncwarp();
-    }
-    // add the stage bases
-    uint32_t sbase[8];
-    uint32_t acc = 0;
-#pragma unroll
-    for (int s = 0; s < 8; s++) {
-      sbase[s] = acc;
-      if (s < max_stages) acc += (uint32_t)carry[s];
-    }
-    for (int u = tid; u < nunits; u += 32) {
-#pragma unroll
-      for (int s = 1; s < 8; s++)
-        if (s < max_stages && urec[(size_t)(s * U + u) * 2]) urec[(size_t)(s * U + u) * 2] += sbase[s];
-    }
-  }
   __syncwarp();
 
   // ---- phase C: floor curve as one byte per bin: exact integer DDA, a lane renders pieces of <= 16 bins
@@ -1348,7 +1367,6 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
 
   // ---- phase D: 8 bins per thread: gather the residue, inverse coupling, floor, store ------------
   float* out = P.spec + pk.spec_off;
-  const bool pair = g.rtype == 2 && C == 2;
   const bool coupled = C == 2 && mp->coupling_steps > 0;   // stereo: the only possible pair is (0,1) / (1,0)
   for (int x0 = tid * 8; x0 < res_end; x0 += 32 * 8) {
     float r[16];   // r[i] = channel 0, r[8+i] = channel 1 of bin x0+i
@@ -1416,6 +1434,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
       reinterpret_cast<float4*>(out + half + x0)[1] = o1;
     }
   }
+  if (!k3_reads_end)
   for (int x0 = res_end + tid * 8; x0 < half; x0 += 32 * 8) {   // no coded residue up here: +0
     const float4 z = float4{0.f, 0.f, 0.f, 0.f};
     if (own_mask & 1u) {

@@ -135,9 +135,11 @@ VPZ_DEV int idx2(int k1, int k2, int r2) { return k1 + 8 * k2 + 68 * r2; }
 // N = 2048: H = 512 = 8*8*8, 64 threads.  The thread's 8 float2 of the spectrum (X[2n], X[2n+1] for
 // n = t + 64 q) arrive in registers (prefetched one packet ahead).  Writes D[0..1024) (smem).
 // T: transpose scratch (2 planes), used for both transposes; tab: the shared-memory tables above.
-VPZ_DEV void k3_load_x(const float* X, int t, float2* xr) {
+// end2: the spectrum holds end2 pairs; the bins above are an exact +0 and were not written (VpzPktRes.end16)
+VPZ_DEV void k3_load_x(const float* X, int t, float2* xr, int end2) {
 #pragma unroll
-  for (int q = 0; q < 8; q++) xr[q] = VPZ_LDG(reinterpret_cast<const float2*>(X) + (t + 64 * q));
+  for (int q = 0; q < 8; q++)
+    xr[q] = (t + 64 * q) < end2 ? VPZ_LDG(reinterpret_cast<const float2*>(X) + (t + 64 * q)) : float2{0.f, 0.f};
 }
 
 VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* tab, int t, int grp) {   // M = 1024
@@ -197,15 +199,17 @@ VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* ta
 }
 
 // N = 256: H = 64 = 8*8, threads t < 8 of the group work; M = 128.  tw / w64: shared-memory tables.
-VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, const cpx* w64, int t, bool active, int grp) {
+// end: bins >= end are an exact +0 and were not written
+VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, const cpx* w64, int t, bool active, int grp,
+                        int end) {
   const int M = 128;
   cpx v[8];
   if (active) {
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       int n = t + 8 * q;
-      v[q].x = VPZ_LDG(X + 2 * n);
-      v[q].y = VPZ_LDG(X + M - 1 - 2 * n);
+      v[q].x = 2 * n < end ? VPZ_LDG(X + 2 * n) : 0.f;
+      v[q].y = M - 1 - 2 * n < end ? VPZ_LDG(X + M - 1 - 2 * n) : 0.f;
       v[q] = cmul(v[q], tw[n]);
     }
     dft8(v);

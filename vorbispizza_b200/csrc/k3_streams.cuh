@@ -128,17 +128,20 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
     K3_GSYNC(grp);
     if (t64 < nb) {
       spk[t64] = P.pkts[first + pb + t64];
-      smask[t64] = P.res ? P.res[first + pb + t64].exec_mask : 0xffu;
+      // exec mask | status << 8 | end16[0] << 16 | end16[1] << 24 (VpzPktRes); no K1: every channel, every bin
+      smask[t64] = P.res ? reinterpret_cast<const uint32_t*>(P.res)[first + pb + t64] : 0xffff00ffu;
     }
     K3_GSYNC(grp);
     for (int pw = 0; pw < nb; pw++, parity ^= 1) {
       const int pi = pb + pw;
       const uint32_t gp = (uint32_t)(first + pi);
       const VpzPktOla pk = spk[pw];
-      const uint32_t mask = smask[pw];
+      const uint32_t rw = smask[pw];
+      const uint32_t mask = rw & 0xffu;
       const bool has_next = pw + 1 < nb;
       const VpzPktOla pk_next = spk[has_next ? pw + 1 : pw];
-      const uint32_t mask_next = smask[has_next ? pw + 1 : pw];
+      const uint32_t rw_next = smask[has_next ? pw + 1 : pw];
+      const uint32_t mask_next = rw_next & 0xffu;
       const bool next_long = has_next && (pk_next.flags & VPZ_OLA_LONG);
       const bool is_long = pk.flags & VPZ_OLA_LONG;
       const int M = is_long ? 1024 : 128;
@@ -164,7 +167,8 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
         D.hm = chb - h;
         D.lo = chb + 512 + parity * 512;
         const bool active = t64 < 8 * C && ((mask >> c) & 1u);
-        fft64_to_D(P.spec + pk.spec_off + (size_t)c * M, T + 80 * c, D, tw_s, w64_s, t64 & 7, active, grp);   // ends with a group barrier
+        fft64_to_D(P.spec + pk.spec_off + (size_t)c * M, T + 80 * c, D, tw_s, w64_s, t64 & 7, active, grp,
+                   (int)((rw >> (16 + 8 * c)) & 0xffu) * 16);   // ends with a group barrier
         if (P.dbg_imdct) {
           for (int c2 = 0; c2 < C; c2++) {
             K3D D2;
@@ -200,7 +204,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
               xr[q] = *reinterpret_cast<const float2*>(n2 < 512 ? chb + n2 : D.lo + (n2 - 512));
             }
           } else if (!(c == 0 && xr_valid)) {
-            k3_load_x(X, t, xr);
+            k3_load_x(X, t, xr, (int)((rw >> (16 + 8 * c)) & 0xffu) * 8);
           }
           fft512_to_D(xr, T, D, tab, t, grp);
           if (c == 0) xr_valid = false;
@@ -216,7 +220,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
 
       // channel 0 of the next long block is requested now and lands during the output loop
       if (next_long && (mask_next & 1u)) {
-        k3_load_x(P.spec + pk_next.spec_off, t, xr);
+        k3_load_x(P.spec + pk_next.spec_off, t, xr, (int)((rw_next >> 16) & 0xffu) * 8);
         xr_valid = true;
       }
       // ---- output: window + overlap-add + clip, all channels interleaved ----------------------------
@@ -271,10 +275,15 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
         const float* Xn = P.spec + pk_next.spec_off + 1024;
         float* hi = Dch + K3S_CH_FLOATS;
         float* lo = hi + 512 + (parity ^ 1) * 512;
+        const int end4 = (int)(rw_next >> 24) * 4;   // float4 groups that were written (the rest is +0)
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           const int i4 = t64 + 64 * r;
-          k3s_cp16(i4 < 128 ? hi + 4 * i4 : lo + 4 * (i4 - 128), Xn + 4 * i4);
+          float* dst = i4 < 128 ? hi + 4 * i4 : lo + 4 * (i4 - 128);
+          if (i4 < end4)
+            k3s_cp16(dst, Xn + 4 * i4);
+          else
+            *reinterpret_cast<float4*>(dst) = float4{0.f, 0.f, 0.f, 0.f};
         }
         staged = true;
       }

@@ -146,7 +146,10 @@ struct alignas(16) VpzPktIn {
 struct VpzPktRes {
   uint8_t exec_mask;        // bit ch set: channel has its own floor energy -> IMDCT runs (Mapping.cs:185)
   uint8_t status;           // 0 ok, 1 residue decode hit end of packet (kept what was decoded)
-  uint16_t bits_used_lo;    // low 16 bits of the final bit cursor (debug / stats)
+  // Spectrum bins >= 16 * end16[ch] of channel ch (ch < 2) are an exact +0 and were NOT written: the packet
+  // codes nothing above its last active residue partition (typically 65 % of the bins of the TestFiles).
+  // The 256 / 2048 IMDCT kernel reads only below it; 255 = everything was written (general K1b).
+  uint8_t end16[2];
 };
 
 // K3 per-packet descriptor (host built from Mode.GetPacketInfo, Mode.cs:30-66)
