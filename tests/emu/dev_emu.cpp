@@ -1,6 +1,7 @@
 // dev_emu.cpp -- TEST INFRASTRUCTURE ONLY: devapi.h on top of cuda_emu.h (see cuda_emu.h).
 #include "cuda_emu.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <chrono>
@@ -22,7 +23,11 @@ void launch(unsigned blocks, unsigned threads, size_t smem_bytes, const std::fun
     ctx.bar = &bar;
     unsigned nw = (threads + 31) / 32;
     for (unsigned w = 0; w < nw; w++) ctx.warps.push_back(new WarpCtx);
-    ctx.smem = calloc(1, smem_bytes + 64);
+    // shared memory with a canary behind it: a kernel writing past its dynamic shared memory (an "illegal
+    // memory access" on the device) fails here instead of corrupting the heap silently
+    const size_t guard = 4096;
+    ctx.smem = calloc(1, smem_bytes + guard);
+    memset(static_cast<char*>(ctx.smem) + smem_bytes, 0xa5, guard);
     std::vector<std::thread> ts;
     for (unsigned t = 0; t < threads; t++) {
       ts.emplace_back([&, t] {
@@ -37,6 +42,11 @@ void launch(unsigned blocks, unsigned threads, size_t smem_bytes, const std::fun
       });
     }
     for (auto& t : ts) t.join();
+    for (size_t i = 0; i < guard; i++)
+      if (static_cast<unsigned char*>(ctx.smem)[smem_bytes + i] != 0xa5) {
+        fprintf(stderr, "emu: block %u wrote %zu bytes past its %zu bytes of shared memory\n", b, i + 1, smem_bytes);
+        abort();
+      }
     for (auto* w : ctx.warps) delete w;
     for (auto* nb : ctx.named) delete nb;
     free(ctx.smem);

@@ -145,8 +145,8 @@ def test_generated_shape_stream_parity(emu_ctx, shape):
 def test_generated_mixed_batch(emu_ctx):
     """One bulk call over streams of different kernel classes (gather / general / full K1 paths, fast and
     generic IMDCT): every stream must come out as if decoded alone."""
-    cases.synth_mixed_batch_parity(emu_ctx, [("stereo_res2", 3), ("ch6_coupled", 4), ("multi_submap", 5), ("floor0", 6)],
-                                   n_packets=8, with_files=["1test"])
+    shapes = [(s, 7 + i) for i, s in enumerate(synthvorbis.SHAPES)]
+    cases.synth_mixed_batch_parity(emu_ctx, shapes, n_packets=5, with_files=["1test"])
 
 
 def test_65_post_floor_is_refused(emu_ctx):

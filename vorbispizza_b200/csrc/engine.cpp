@@ -118,7 +118,8 @@ static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
       size_t max_posts = 2;
       for (int i = 0; i < h->nfloors; i++) max_posts = std::max<size_t>(max_posts, fl[i].xcount);
       s->k1g_seg_stride = (uint32_t)(4 * (max_posts + 1));
-      s->k1g_words = (uint32_t)(((size_t)max_stages * U * 2 + (size_t)C * half_max / 4 + (size_t)C * s->k1g_seg_stride + 8 + 31) & ~(size_t)31);
+      // without the segment tables: a batch sizes those by the LARGEST floor among its gather setups (batch_decode)
+      s->k1g_words = (uint32_t)((size_t)max_stages * U * 2 + (size_t)C * half_max / 4);
     }
     // K1_REC_HDR, K1_SEG_WORDS, classes; a multiple of 4 words so every record starts on a 16-byte boundary
     // + 16 with several submaps: the per-submap entry ends K1a leaves behind the class bytes
@@ -674,7 +675,7 @@ int batch_decode(vpz_batch* b, int clip, int out16) {
   int gen_channels = 1;
   for (vpz_setup* s : b->slots) {
     if (k1_class(ctx, s) == 0) {
-      k1g = std::max(k1g, s->k1g_words);
+      k1g = std::max(k1g, s->k1g_words);      // urec + floor bytes of the largest setup ...
       k1seg = std::max(k1seg, s->k1g_seg_stride);
     } else {
       k1w = std::max(k1w, s->k1_words_per_warp);
@@ -721,7 +722,9 @@ int batch_decode(vpz_batch* b, int clip, int out16) {
       p.n_pkts = cnt;
       p.counter = ctx->d_counter + 2 + general;
       p.gather_ok = general ? 0 : 1;
-      p.smem_words_per_warp = general ? k1w : k1g;
+      // ... + two channels of segment tables at the batch-wide stride (the kernel places them behind the
+      // setup's own urec / floor bytes, so every part is sized by its own maximum)
+      p.smem_words_per_warp = general ? k1w : (uint32_t)((k1g + 2 * (size_t)k1seg + 8 + 31) & ~(size_t)31);
       p.seg_stride = k1seg;
       const size_t smem_block = (size_t)p.smem_words_per_warp * 4 * (general ? 1 : warps) + (general ? 0 : 1024);   // + the dB table
       const size_t per_sm = std::max<size_t>(1, std::min<size_t>(16, (227 * 1024) / (smem_block + 1024)));

@@ -29,7 +29,7 @@ struct vpz_setup {
   uint32_t rec_words = 0;           // size of one packet's symbol record (K1a -> K1b)
   bool gather_ok = false;           // K1b gather path applies (mono/stereo, residue 1/2, dims divide the partition)
   bool k1a_full = false;            // needs the K1a variant that walks floor 0 / several submaps
-  uint32_t k1g_words = 0;           // shared memory of the gather path per warp (words)
+  uint32_t k1g_words = 0;           // shared memory of the gather path per warp (words), without the floor segment tables
   uint32_t k1g_seg_stride = 0;      // words of the floor segment table per channel (4 per post + flat tail)
   uint32_t k3_floats_per_ch = 0;    // shared memory K3 needs per channel (generic layout)
   bool fast_sizes = false;          // block sizes 256 / 2048

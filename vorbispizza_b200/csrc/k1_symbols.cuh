@@ -1115,6 +1115,7 @@ VPZ_DEV void k1b_render_floor(const uint32_t* sg, int nseg, int npieces, uint8_t
     const uint32_t magic = w.w;
     const int k = 16 * (p - (int)((w.z >> 16) & 0x7fffu));   // steps into the segment
     const int xs = x0 + k;
+    if (xs >= x_end) break;                                  // pieces are ordered by x: nothing is coded from here on
     int len = (x1 < x_end ? x1 : x_end) - xs;                // bins of this piece
     len = len > 16 ? 16 : len;
     const int t = k * rem;
@@ -1215,6 +1216,62 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
   const bool have_res = g.part_count > 0 && g.any && G.n_ent > 0;
   const bool pair = g.rtype == 2 && C == 2;
 
+  // Bins at and above the end of the coded residue range hold an exact +0 residue; phase A cuts the floor
+  // into pieces below that bound, phase B then finds the packet's last ACTIVE partition, which is where the
+  // render and the gather really stop.
+  int res_cfg = 0;
+  if (have_res) {
+    const int span_end = g.begin + G.span;                          // in vector positions
+    const int bins = pair ? (span_end + 1) >> 1 : span_end;
+    res_cfg = (bins + 15) & ~15;
+    if (res_cfg > half) res_cfg = half;
+  }
+  if (DEBUG && P.dbg.residue) res_cfg = half;   // the debug dump wants every bin
+
+  // ---- phase A: floor segments of every channel with energy, and their pieces of <= 16 bins -------
+  int npieces0 = 0, npieces1 = 0;   // per channel (the gather path has at most two)
+  for (int ch = 0; ch < C; ch++) {
+    if (!((own_mask >> ch) & 1u)) continue;
+    const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
+    uint32_t* sg = sgbase + ch * P.seg_stride;
+    const int nseg = (int)seg[0];
+    int carry = 0;
+    for (int s0 = 0; s0 < nseg; s0 += 32) {   // uniform trip count: every lane takes part in the scan
+      const int s = s0 + tid;
+      int np = 0;
+      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+      if (s < nseg) {
+        const uint32_t p0 = seg[1 + s], p1 = seg[2 + s];
+        const int x0 = (int)(p0 & 0xffffu), y0 = (int)(short)(p0 >> 16);
+        const int x1 = (int)(p1 & 0xffffu), y1 = (int)(short)(p1 >> 16);
+        const int dy = y1 - y0, adx = x1 - x0;
+        const int ady = dy < 0 ? -dy : dy;
+        const int base = adx > 0 ? ady / adx : 0;
+        const int xe = x1 < res_cfg ? x1 : res_cfg;
+        np = xe > x0 ? (xe - x0 + 15) >> 4 : 0;
+        w0 = (uint32_t)x0 | ((uint32_t)x1 << 16);
+        w1 = (uint32_t)(y0 & 0xffff) | ((uint32_t)base << 16);          // |base| of the DDA
+        w2 = (uint32_t)(ady - base * adx) | (dy < 0 ? 0x80000000u : 0u); // remainder step (< adx <= 4096), sign
+        w3 = adx > 1 ? 0xffffffffu / (uint32_t)adx + 1u : 0u;            // ceil(2^32 / adx); adx = 1 has no remainder steps
+      }
+      int incl = np;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += n;
+      }
+      if (s < nseg) {
+        sg[4 * s] = w0;
+        sg[4 * s + 1] = w1;
+        sg[4 * s + 2] = w2 | ((uint32_t)(carry + incl - np) << 16);     // pieces before this segment
+        sg[4 * s + 3] = w3;
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (ch == 0) npieces0 = carry; else npieces1 = carry;
+  }
+  __syncwarp();
+
   // ---- phase B: per unit and stage, how many entries it holds -> first entry (all stages at once) ----
   int act_units = 0;   // last unit that carries codewords in any stage, + 1
   if (have_res) {
@@ -1232,7 +1289,6 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
         if (!((g.skip >> v) & 1u)) c = rec_cls[u];
       }
       const uint2* ut = reinterpret_cast<const uint2*>(blob + rs->unit_tabb_off) + (c < 0 ? 0 : c) * 8;
-      bool any = false;
 #pragma unroll
       for (int s = 0; s < 8; s++) {
         cnt[s] = 0;
@@ -1243,7 +1299,6 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
             info[s] = t.x & 0xffffu;
             cnt[s] = (int)(t.x >> 16);
             vqo[s] = t.y;
-            any = any || cnt[s] != 0;
           }
           int incl = cnt[s];
 #pragma unroll
@@ -1256,7 +1311,8 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
           carry[s] += round_total;
         }
       }
-      const uint32_t act = __ballot_sync(0xffffffffu, any);
+      // a unit is active when any stage has codewords for its class (info holds the dimension: never 0 then)
+      const uint32_t act = __ballot_sync(0xffffffffu, (info[0] | info[1] | info[2] | info[3] | info[4] | info[5] | info[6] | info[7]) != 0u);
       if (act) act_units = u0 + 32 - __clz((int)act);
       // absolute first entry = entries of all earlier stages + offset inside the stage; the stage
       // totals are only complete after the last round, so the stage bases are added below
@@ -1308,50 +1364,6 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
     r.status = (uint8_t)((hdr >> 16) & 0xffu);
     r.end16[0] = r.end16[1] = (uint8_t)(k3_reads_end ? res_end >> 4 : 255);
     P.res[pkt_idx] = r;
-  }
-  __syncwarp();
-
-  // ---- phase A: floor segments of every channel with energy, and their pieces of <= 16 bins -------
-  int npieces0 = 0, npieces1 = 0;   // per channel (the gather path has at most two)
-  for (int ch = 0; ch < C; ch++) {
-    if (!((own_mask >> ch) & 1u)) continue;
-    const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
-    uint32_t* sg = sgbase + ch * P.seg_stride;
-    const int nseg = (int)seg[0];
-    int carry = 0;
-    for (int s0 = 0; s0 < nseg; s0 += 32) {   // uniform trip count: every lane takes part in the scan
-      const int s = s0 + tid;
-      int np = 0;
-      uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-      if (s < nseg) {
-        const uint32_t p0 = seg[1 + s], p1 = seg[2 + s];
-        const int x0 = (int)(p0 & 0xffffu), y0 = (int)(short)(p0 >> 16);
-        const int x1 = (int)(p1 & 0xffffu), y1 = (int)(short)(p1 >> 16);
-        const int dy = y1 - y0, adx = x1 - x0;
-        const int ady = dy < 0 ? -dy : dy;
-        const int base = adx > 0 ? ady / adx : 0;
-        const int xe = x1 < res_end ? x1 : res_end;
-        np = xe > x0 ? (xe - x0 + 15) >> 4 : 0;
-        w0 = (uint32_t)x0 | ((uint32_t)x1 << 16);
-        w1 = (uint32_t)(y0 & 0xffff) | ((uint32_t)base << 16);          // |base| of the DDA
-        w2 = (uint32_t)(ady - base * adx) | (dy < 0 ? 0x80000000u : 0u); // remainder step (< adx <= 4096), sign
-        w3 = adx > 1 ? 0xffffffffu / (uint32_t)adx + 1u : 0u;            // ceil(2^32 / adx); adx = 1 has no remainder steps
-      }
-      int incl = np;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const int n = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += n;
-      }
-      if (s < nseg) {
-        sg[4 * s] = w0;
-        sg[4 * s + 1] = w1;
-        sg[4 * s + 2] = w2 | ((uint32_t)(carry + incl - np) << 16);     // pieces before this segment
-        sg[4 * s + 3] = w3;
-      }
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (ch == 0) npieces0 = carry; else npieces1 = carry;
   }
   __syncwarp();
 
