@@ -154,3 +154,35 @@ def test_crc_known_answer():
     want = int.from_bytes(page[22:26], "little")
     page[22:26] = b"\0\0\0\0"
     assert ob.crc_ogg(bytes(page)) == want
+
+
+# ---- (5) an independent second reading of the integer stages ------------------------------------------
+def _pin_digest(seq):
+    return hashlib.sha256(",".join(str(int(x)) for x in seq).encode()).hexdigest()[:16]
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_integer_stages_vs_independent_walker(name):
+    """tests/golden/stage_pin.json was produced by tests/golden/make_stage_pin.py: a pure-Python symbol walker
+    written from the algorithm notes and sharing no code with oracle/ -- its own Ogg
+    splitter, codeword assignment and bit reader.  Every audio packet: DecodeScalar sequence, raw posts,
+    final Y, step flags and partition classes of the C oracle must equal that second reading."""
+    pin = json.load(open(os.path.join(GOLDEN, "stage_pin.json")))[name]
+    s = ob.OracleStream(load_file(name))
+    pk = s.audio_packets()
+    assert len(pk) == len(pin)
+    for i, (p, w) in enumerate(zip(pk, pin)):
+        o = s.dump_packet(p["data"])
+        if w is None:
+            assert o["status"] != 0
+            continue
+        what = "%s packet %d" % (name, i)
+        assert o["status"] == 0, what
+        assert o["scalars_n"] == w["n_scalars"] and _pin_digest(o["scalars"][:o["scalars_n"]]) == w["scalars"], what
+        assert o["classes_n"] == w["n_classes"] and _pin_digest(o["classes"][:o["classes_n"]]) == w["classes"], what
+        counts = [max(int(o["post_count"][c]), 0) for c in range(s.channels)]
+        assert counts == w["post_counts"], what
+        assert _pin_digest([v for c in range(s.channels) for v in o["raw_posts"][c][:counts[c]]]) == w["raw_posts"], what
+        assert _pin_digest([v for c in range(s.channels) for v in o["final_y"][c][:counts[c]]]) == w["final_y"], what
+        assert _pin_digest([v for c in range(s.channels) for v in o["step_flags"][c][:counts[c]]]) == w["step_flags"], what
+        assert o["bits_read"] == w["bits"], what

@@ -1189,6 +1189,10 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
     return;
   }
 
+#if defined(K1B_ABLATE) && (K1B_ABLATE & 16)
+  if (tid == 0) P.res[pkt_idx] = VpzPktRes{(uint8_t)own_mask, 0, {0, 0}};
+  return;
+#endif
   // mapping and residue index come with the record (K1a found them through the mode): no second walk
   const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + (rh.w & 0xffu);
   const VpzResidue* rs = reinterpret_cast<const VpzResidue*>(blob + H->residues_off) + ((rh.w >> 8) & 0xffu);
@@ -1373,18 +1377,28 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
     const uint32_t* sg = sgbase + ch * P.seg_stride;
     uint8_t* yb = ybuf + ch * half_max;
     const int nseg = (int)rec[K1_REC_HDR + ch * K1_SEG_WORDS];
+#if !(defined(K1B_ABLATE) && (K1B_ABLATE & 1))
     k1b_render_floor(sg, nseg, ch == 0 ? npieces0 : npieces1, yb, res_end, tid);
+#endif
   }
   __syncwarp();
 
   // ---- phase D: 8 bins per thread: gather the residue, inverse coupling, floor, store ------------
   float* out = P.spec + pk.spec_off;
   const bool coupled = C == 2 && mp->coupling_steps > 0;   // stereo: the only possible pair is (0,1) / (1,0)
+#if defined(K1B_ABLATE) && (K1B_ABLATE & 4)
+  for (int x0 = tid * 8; x0 < 0; x0 += 32 * 8) {
+#else
   for (int x0 = tid * 8; x0 < res_end; x0 += 32 * 8) {
+#endif
     float r[16];   // r[i] = channel 0, r[8+i] = channel 1 of bin x0+i
 #pragma unroll
     for (int i = 0; i < 16; i++) r[i] = 0.f;
+#if defined(K1B_ABLATE) && (K1B_ABLATE & 2)
+    if (false) {
+#else
     if (have_res) {
+#endif
       if (pair) {
         k1g_fetch_chunk<16, true>(G, 0, 2 * x0, r);   // Residue2 de-interleave: positions (2x, 2x+1) = (ch0, ch1)
       } else {   // type 2 mono: the one vector is channel 0
