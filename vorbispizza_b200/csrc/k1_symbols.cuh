@@ -1150,29 +1150,42 @@ VPZ_DEV void k1b_render_floor(const uint32_t* sg, int nseg, int npieces, uint8_t
   }
 }
 
-template <bool DEBUG>
-VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32_t* smem, const float* dbtab, int tid) {
-  const int lane = tid;   // ONE WARP per packet: many packets in flight per SM hide the per-packet load latency
-  const VpzPktIn pk = P.pkts[pkt_idx];
-#ifndef VPZ_EMU
-  {
-    // the record (header, floor segments, classes) and the entry indices are read in four dependent
-    // steps below; ask L2 for all of their lines now (one 128-byte line per lane: the record first,
-    // then ~4 bytes of entry indices per packet byte, the typical rate) so those steps find them there
-    const char* r0 = reinterpret_cast<const char*>(P.rec + pk.rec_off);
-    const char* e0 = reinterpret_cast<const char*>(P.ent + pk.ent_off);
-    const uint32_t rec_lines = 6, ent_bytes = 4u * pk.byte_len;
-    const char* line = lane < (int)rec_lines ? r0 + 128 * lane : e0 + 128 * (lane - (int)rec_lines);
-    if (lane < (int)rec_lines || 128u * (uint32_t)(lane - (int)rec_lines) < ent_bytes)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-  }
+// What the gather path needs of a packet's descriptor, plus the first four words of its symbol record.  A warp
+// fetches these for K1B_GRAB packets at once (one lane each) and hands them round by shuffle: the chain
+// work-stealing counter -> order -> descriptor -> record header is four dependent memory round trips, which
+// cost 0.9 of K1b's 4.3 ms when every packet walked it on its own.
+struct K1bPkt {
+  uint32_t idx, spec_off, setup_slot, rec_off, ent_off, byte_len;
+  uint4 rh;
+};
+#ifndef K1B_GRAB
+#define K1B_GRAB 8
 #endif
+
+VPZ_DEV void k1b_prefetch_packet(const K1Params& P, uint32_t rec_off, uint32_t ent_off, uint32_t byte_len, int lane) {
+#ifndef VPZ_EMU
+  // the record (header, floor segments, classes) and the entry indices are read in dependent steps; ask
+  // L2 for all of their lines now (one 128-byte line per lane: the record first, then ~4 bytes of entry
+  // indices per packet byte, the typical rate) so those steps find them there
+  const char* r0 = reinterpret_cast<const char*>(P.rec + rec_off);
+  const char* e0 = reinterpret_cast<const char*>(P.ent + ent_off);
+  const uint32_t rec_lines = 6, ent_bytes = 4u * byte_len;
+  const char* line = lane < (int)rec_lines ? r0 + 128 * lane : e0 + 128 * (lane - (int)rec_lines);
+  if (lane < (int)rec_lines || 128u * (uint32_t)(lane - (int)rec_lines) < ent_bytes)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+#endif
+}
+
+template <bool DEBUG>
+VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32_t* smem, const float* dbtab, int tid) {
+  const int lane = tid;   // ONE WARP per packet: many packets in flight per SM hide the per-packet load latency
+  const uint32_t pkt_idx = pk.idx;
   const uint32_t* blob = P.setups[pk.setup_slot];
   const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
   const int C = H->channels;
   const int half_max = 1 << (H->log2_size1 - 1);
   const uint32_t* rec = P.rec + pk.rec_off;
-  const uint4 rh = *reinterpret_cast<const uint4*>(rec);   // records start on 16-byte boundaries (engine.cpp)
+  const uint4 rh = pk.rh;   // records start on 16-byte boundaries (engine.cpp)
   const uint32_t hdr = rh.x;
   const uint32_t own_mask = hdr & 0xffu, noexec = (hdr >> 8) & 0xffu;
   const int long_block = (int)(hdr >> 24) & 1;
@@ -1361,12 +1374,17 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
     if (res_end > half) res_end = half;
   }
   if (DEBUG && P.dbg.residue) res_end = half;   // the debug dump wants every bin
+#if defined(VPZ_K3_END) && !VPZ_K3_END
+  const bool k3_reads_end = false;
+#else
   const bool k3_reads_end = !DEBUG && H->log2_size0 == 8 && H->log2_size1 == 11;   // engine.cpp k3_fast (C <= 2 here)
+#endif
   if (tid == 0) {
     VpzPktRes r;
     r.exec_mask = (uint8_t)own_mask;
     r.status = (uint8_t)((hdr >> 16) & 0xffu);
-    r.end16[0] = r.end16[1] = (uint8_t)(k3_reads_end ? res_end >> 4 : 255);
+    // K3 tests the end per 128-bin unit (uniform over its threads): the zero fill below goes up to the next one
+    r.end16[0] = r.end16[1] = (uint8_t)(k3_reads_end ? ((res_end + 127) & ~127) >> 4 : 255);
     P.res[pkt_idx] = r;
   }
   __syncwarp();
@@ -1460,8 +1478,8 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, uint32_t pkt_idx, uint32
       reinterpret_cast<float4*>(out + half + x0)[1] = o1;
     }
   }
-  if (!k3_reads_end)
-  for (int x0 = res_end + tid * 8; x0 < half; x0 += 32 * 8) {   // no coded residue up here: +0
+  const int fill_end = !k3_reads_end ? half : (((res_end + 127) & ~127) < half ? ((res_end + 127) & ~127) : half);
+  for (int x0 = res_end + tid * 8; x0 < fill_end; x0 += 32 * 8) {   // no coded residue up here: +0
     const float4 z = float4{0.f, 0.f, 0.f, 0.f};
     if (own_mask & 1u) {
       reinterpret_cast<float4*>(out + x0)[0] = z;
@@ -1490,13 +1508,47 @@ VPZ_DEV void k1b_gather_loop(const K1Params& P, uint32_t* smem) {
   __syncthreads();
   uint32_t* my = smem + 256 + (size_t)warp * P.smem_words_per_warp;
   for (;;) {
-    uint32_t idx = 0;
-    if (lane == 0) idx = atomicAdd(P.counter, 1u);
-    idx = __shfl_sync(0xffffffffu, idx, 0);
-    if (idx >= P.n_pkts) break;
-    // same order as K1a: grouped by (setup, block size), so the warps resident on an SM run the same
-    // code paths on the same VQ tables
-    k1b_build_packet_gather<DEBUG>(P, P.order ? P.order[idx] : idx, my, dbtab, lane);
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(P.counter, (uint32_t)K1B_GRAB);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (base >= P.n_pkts) break;
+    const int n = (int)(P.n_pkts - base < (uint32_t)K1B_GRAB ? P.n_pkts - base : (uint32_t)K1B_GRAB);
+    // lane j < n fetches packet base + j: same order as K1a (grouped by (setup, block size)), so the warps
+    // resident on an SM run the same code paths on the same VQ tables
+    K1bPkt mine;
+    mine.idx = mine.spec_off = mine.setup_slot = mine.rec_off = mine.ent_off = mine.byte_len = 0;
+    mine.rh = uint4{0, 0, 0, 0};
+    if (lane < n) {
+      mine.idx = P.order ? P.order[base + lane] : base + lane;
+      const uint4* d = reinterpret_cast<const uint4*>(P.pkts + mine.idx);   // VpzPktIn: 32 bytes, 16-byte aligned
+      const uint4 d0 = d[0], d1 = d[1];
+      mine.byte_len = d0.y;
+      mine.spec_off = d0.z;
+      mine.setup_slot = d0.w;
+      mine.rec_off = d1.x;
+      mine.ent_off = d1.y;
+      mine.rh = *reinterpret_cast<const uint4*>(P.rec + mine.rec_off);
+    }
+    k1b_prefetch_packet(P, __shfl_sync(0xffffffffu, mine.rec_off, 0), __shfl_sync(0xffffffffu, mine.ent_off, 0),
+                        __shfl_sync(0xffffffffu, mine.byte_len, 0), lane);
+    for (int j = 0; j < n; j++) {
+      // the lines of the NEXT packet are requested while this one is built
+      if (j + 1 < n)
+        k1b_prefetch_packet(P, __shfl_sync(0xffffffffu, mine.rec_off, j + 1), __shfl_sync(0xffffffffu, mine.ent_off, j + 1),
+                            __shfl_sync(0xffffffffu, mine.byte_len, j + 1), lane);
+      K1bPkt pk;
+      pk.idx = __shfl_sync(0xffffffffu, mine.idx, j);
+      pk.spec_off = __shfl_sync(0xffffffffu, mine.spec_off, j);
+      pk.setup_slot = __shfl_sync(0xffffffffu, mine.setup_slot, j);
+      pk.rec_off = __shfl_sync(0xffffffffu, mine.rec_off, j);
+      pk.ent_off = __shfl_sync(0xffffffffu, mine.ent_off, j);
+      pk.byte_len = __shfl_sync(0xffffffffu, mine.byte_len, j);
+      pk.rh.x = __shfl_sync(0xffffffffu, mine.rh.x, j);
+      pk.rh.y = __shfl_sync(0xffffffffu, mine.rh.y, j);
+      pk.rh.z = __shfl_sync(0xffffffffu, mine.rh.z, j);
+      pk.rh.w = __shfl_sync(0xffffffffu, mine.rh.w, j);
+      k1b_build_packet_gather<DEBUG>(P, pk, my, dbtab, lane);
+    }
   }
 }
 template <bool DEBUG>

@@ -135,11 +135,13 @@ VPZ_DEV int idx2(int k1, int k2, int r2) { return k1 + 8 * k2 + 68 * r2; }
 // N = 2048: H = 512 = 8*8*8, 64 threads.  The thread's 8 float2 of the spectrum (X[2n], X[2n+1] for
 // n = t + 64 q) arrive in registers (prefetched one packet ahead).  Writes D[0..1024) (smem).
 // T: transpose scratch (2 planes), used for both transposes; tab: the shared-memory tables above.
-// end2: the spectrum holds end2 pairs; the bins above are an exact +0 and were not written (VpzPktRes.end16)
+// end2: the spectrum holds end2 pairs, a multiple of 64 (K1b fills up to the next 128-bin boundary); the
+// bins above are an exact +0 and were not written (VpzPktRes.end16).  Load q covers pairs [64 q, 64 q + 64):
+// the test is uniform over the group, so a skipped load costs nothing.
 VPZ_DEV void k3_load_x(const float* X, int t, float2* xr, int end2) {
 #pragma unroll
   for (int q = 0; q < 8; q++)
-    xr[q] = (t + 64 * q) < end2 ? VPZ_LDG(reinterpret_cast<const float2*>(X) + (t + 64 * q)) : float2{0.f, 0.f};
+    xr[q] = 64 * q < end2 ? VPZ_LDG(reinterpret_cast<const float2*>(X) + (t + 64 * q)) : float2{0.f, 0.f};
 }
 
 VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* tab, int t, int grp) {   // M = 1024
@@ -208,8 +210,8 @@ VPZ_DEV void fft64_to_D(const float* X, float* A, const K3D& D, const cpx* tw, c
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       int n = t + 8 * q;
-      v[q].x = 2 * n < end ? VPZ_LDG(X + 2 * n) : 0.f;
-      v[q].y = M - 1 - 2 * n < end ? VPZ_LDG(X + M - 1 - 2 * n) : 0.f;
+      v[q].x = end > 0 ? VPZ_LDG(X + 2 * n) : 0.f;   // a short block is one 128-bin unit: written or not
+      v[q].y = end > 0 ? VPZ_LDG(X + M - 1 - 2 * n) : 0.f;
       v[q] = cmul(v[q], tw[n]);
     }
     dft8(v);

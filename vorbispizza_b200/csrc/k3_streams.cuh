@@ -31,6 +31,16 @@
 #ifndef K3S_EMIT_UNROLL
 #define K3S_EMIT_UNROLL 4
 #endif
+// 1: read a channel's spectrum only below VpzPktRes.end16 (K1b does not write the zero tail); 0: K1b writes
+// every bin and the loads are unconditional
+#ifndef VPZ_K3_END
+#define VPZ_K3_END 1
+#endif
+#if VPZ_K3_END
+#define K3S_END16(rw, c) ((int)(((rw) >> (16 + 8 * (c))) & 0xffu))
+#else
+#define K3S_END16(rw, c) 255
+#endif
 
 #ifndef VPZ_EMU
 VPZ_DEV void k3s_cp16(float* dst_smem, const float* src) {
@@ -168,7 +178,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
         D.lo = chb + 512 + parity * 512;
         const bool active = t64 < 8 * C && ((mask >> c) & 1u);
         fft64_to_D(P.spec + pk.spec_off + (size_t)c * M, T + 80 * c, D, tw_s, w64_s, t64 & 7, active, grp,
-                   (int)((rw >> (16 + 8 * c)) & 0xffu) * 16);   // ends with a group barrier
+                   K3S_END16(rw, c) * 16);   // ends with a group barrier
         if (P.dbg_imdct) {
           for (int c2 = 0; c2 < C; c2++) {
             K3D D2;
@@ -204,7 +214,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
               xr[q] = *reinterpret_cast<const float2*>(n2 < 512 ? chb + n2 : D.lo + (n2 - 512));
             }
           } else if (!(c == 0 && xr_valid)) {
-            k3_load_x(X, t, xr, (int)((rw >> (16 + 8 * c)) & 0xffu) * 8);
+            k3_load_x(X, t, xr, K3S_END16(rw, c) * 8);
           }
           fft512_to_D(xr, T, D, tab, t, grp);
           if (c == 0) xr_valid = false;
@@ -220,7 +230,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
 
       // channel 0 of the next long block is requested now and lands during the output loop
       if (next_long && (mask_next & 1u)) {
-        k3_load_x(P.spec + pk_next.spec_off, t, xr, (int)((rw_next >> 16) & 0xffu) * 8);
+        k3_load_x(P.spec + pk_next.spec_off, t, xr, K3S_END16(rw_next, 0) * 8);
         xr_valid = true;
       }
       // ---- output: window + overlap-add + clip, all channels interleaved ----------------------------
@@ -275,12 +285,12 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
         const float* Xn = P.spec + pk_next.spec_off + 1024;
         float* hi = Dch + K3S_CH_FLOATS;
         float* lo = hi + 512 + (parity ^ 1) * 512;
-        const int end4 = (int)(rw_next >> 24) * 4;   // float4 groups that were written (the rest is +0)
+        const int end4 = K3S_END16(rw_next, 1) * 4;   // float4 groups that were written (the rest is +0)
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           const int i4 = t64 + 64 * r;
           float* dst = i4 < 128 ? hi + 4 * i4 : lo + 4 * (i4 - 128);
-          if (i4 < end4)
+          if ((i4 & ~31) < end4)   // 32 float4 = one 128-bin unit = one warp's share: uniform
             k3s_cp16(dst, Xn + 4 * i4);
           else
             *reinterpret_cast<float4*>(dst) = float4{0.f, 0.f, 0.f, 0.f};
