@@ -19,7 +19,15 @@ A step = one pass of the hot path (K1 entropy/floor/coupling + K3 IMDCT/OLA) ove
           measured HBM copy peak in MEASURED_PEAKS.json.
   cpu_baseline : the CPU oracle (C restatement of the reference .NET path; .NET is not available
           here) on all host cores, one stream per thread, bounded sample.  N=1, rank 0 only.
-`--impl reference` times that same oracle as the reference arm.
+  config3 / config5 : sub-objects of the default line -- BASELINE config 3 (kernel-only IMDCT + window + OLA
+          on 65,536 synthetic stereo blocks: value, roofline incl. ncu DRAM traffic) and config 5 (16,384
+          random-access excerpts through vpz_decode_excerpts: value, excerpts/s, its own cpu_baseline = the
+          oracle's SeekTo + read on all host cores).  `--workload config3|config5` runs them alone.
+  e2e.link_gbs_measured / frac_of_link : copy-only pinned device-to-host bandwidth of this box measured in the
+          same process (all ranks at once) and the share of it the e2e step's D2H traffic reaches.
+`--impl reference` times that same oracle as the reference arm on the SAME workload: the 4,096 streams of
+config 4 per step, whole files, all host cores (both oracle builds: portable -O2 and -O3 -march=native built on
+the box; the faster one is the line's value).
 """
 import argparse
 import ctypes as C
@@ -170,33 +178,130 @@ def run_reference(args, rank, world):
         }))
         return
     cores = os.cpu_count() or 1
-    njobs = 16 * cores  # bounded sample: 16 streams per thread per step (4 of each TestFile)
-    for _ in range(args.warmup):
-        ob.bench_decode(files, max(4, njobs // 4), cores)
-    total, sec = 0, 0.0
-    for _ in range(args.steps):
-        n, s = ob.bench_decode(files, njobs, cores)
-        total += n
-        sec += s
-    v = total / sec
-    sample = "%d whole streams per step (%d per thread, round-robin over the 4 TestFiles), %d steps" % (
-        njobs, 16, args.steps)
+    if args.workload == "config5":
+        # BASELINE config 5 on the CPU: the same 16,384 excerpts (same seed) as the GPU arm, SeekTo + read
+        file_of, start, count, nread = config5_excerpts(0)
+        builds = {}
+        for name, native in (("O2", False), ("O3_march_native", True)):
+            if ob.bench_lib(native) is None:
+                continue
+            for _ in range(max(1, args.warmup)):
+                ob.bench_excerpts(files[1:], file_of[:2048], start[:2048], count[:2048], cores, native)
+            tot, sec = 0, 0.0
+            for _ in range(args.steps):
+                n, s = ob.bench_excerpts(files[1:], file_of, start, count, cores, native)
+                tot += n
+                sec += s
+            builds[name] = {"value": tot / sec, "ms_per_step": 1e3 * sec / args.steps}
+        best = max(builds, key=lambda k: builds[k]["value"])
+        v = builds[best]["value"]
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": max(1, args.warmup), "ms_per_step": builds[best]["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (seeded excerpts of TestFiles)",
+            "config": {"workload": "config5: %d random-access excerpts (SeekTo + %d samples per channel on {2,3,issue6}test.ogg), "
+                                   "one open reader per (thread, file)" % (file_of.size, nread),
+                       "threads": cores, "excerpts_per_s": file_of.size / (builds[best]["ms_per_step"] * 1e-3),
+                       "note": "C restatement of the reference .NET decoder (oracle/); no .NET runtime in this image"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "builds": builds, "build": best,
+                             "sample": "all %d excerpts per step" % file_of.size},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+    # the SAME workload as the GPU arm's e2e: stream g of args.streams decodes the whole file g % 4
+    njobs = args.streams
+    builds = {}
+    for name, native in (("O2", False), ("O3_march_native", True)):
+        if ob.bench_lib(native) is None:
+            continue
+        for _ in range(args.warmup):
+            ob.bench_decode(files, max(4, njobs // 8), cores, native)
+        total, sec = 0, 0.0
+        for _ in range(args.steps):
+            n, s = ob.bench_decode(files, njobs, cores, native)
+            total += n
+            sec += s
+        builds[name] = {"value": total / sec, "ms_per_step": 1e3 * sec / args.steps}
+    best = max(builds, key=lambda k: builds[k]["value"])
+    v = builds[best]["value"]
+    sample = "all %d streams per step (whole files, stream g = TestFile g %% 4, handed to %d threads by a shared cursor)" % (
+        njobs, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic (TestFiles replicated)",
-        "config": {"workload": "config4: concurrent whole-stream decode of replicated TestFiles (bounded sample)",
-                   "streams_per_step": njobs, "threads": cores,
-                   "note": "C restatement of the reference .NET decoder (oracle/); no .NET runtime in this image"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "warmup": args.warmup, "ms_per_step": builds[best]["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic (TestFiles replicated/offset)",
+        "config": {"workload": "config4: %d concurrent streams per GPU replicated/offset from TestFiles/{1,2,3,issue6}test.ogg, "
+                               "full entropy+floor+residue+IMDCT decode, stream-sharded" % njobs,
+                   "streams_per_gpu": njobs, "threads": cores,
+                   "note": "C restatement of the reference .NET decoder (oracle/); no .NET runtime in this image; whole "
+                           "files (the GPU arm's e2e decodes exactly these streams)"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "builds": builds, "build": best,
+                         "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank):
+def config5_excerpts(rank):
+    """The excerpt list of BASELINE config 5: rng(0x5EED0005 + rank), file uniform in {2test, 3test,
+    issue6test}, start uniform in [0, total - 4096); totals are the decodable sample counts of the files."""
+    totals = [315790, 288094, 548160]
+    n, nread = 16384, 4096
+    rng = np.random.default_rng(0x5EED0005 + rank)
+    file_of = rng.integers(0, len(totals), n).astype(np.uint32)
+    start = np.array([int(rng.integers(0, totals[f] - nread)) for f in file_of], np.int64)
+    count = np.full(n, nread, np.int32)
+    return file_of, start, count, nread
+
+
+def d2h_probe(lib, local_rank, barrier, max_over_ranks, sum_over_ranks, seconds=1.0):
+    """Copy-only ceiling of the device-to-host path: a 1 GiB device buffer copied into pinned host memory back
+    to back for about `seconds`, on every rank at once (the ranks of one box share its host side).  Returns the
+    box-wide GB/s (sum of the ranks' bytes / slowest rank's time)."""
+    import torch
+    n = 1 << 30
+    src = torch.empty(n, dtype=torch.uint8, device="cuda")
+    p = lib.vpz_host_alloc(n)
+    if not p:
+        return None
+    dst = torch.frombuffer((C.c_uint8 * n).from_address(p), dtype=torch.uint8)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        dst.copy_(src, non_blocking=True)   # warm-up (first touch of the pinned pages)
+        st.synchronize()
+        reps = 3
+        barrier()
+        while True:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            for _ in range(reps):
+                dst.copy_(src, non_blocking=True)
+            e1.record(st)
+            e1.synchronize()
+            ms = e0.elapsed_time(e1)
+            if ms >= 1e3 * seconds * 0.5 or reps >= 96:
+                break
+            reps *= 2
+    barrier()
+    t = max_over_ranks(ms * 1e-3)
+    total = sum_over_ranks(float(n) * reps)
+    del dst
+    lib.vpz_host_free(p)
+    return total / t / 1e9
+
+
+def load_traffic():
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank, quick=False):
     """BASELINE config 3: kernel-only batched IMDCT + window + overlap-add on synthetic spectra, 65,536
     stereo blocks per GPU (64 streams x 1,024 blocks, long runs with short transitions: the Markov flag
-    sequence and roll-off spectra of SURVEY 8(d), same generator as tests/cases.py)."""
+    sequence and roll-off spectra of SURVEY 8(d), same generator as tests/cases.py).  Returns the JSON line
+    (rank 0) -- printed as is by `--workload config3`, embedded as "config3" in the default line."""
     from vorbispizza_b200 import SynthBatch
     lib = ctx.lib
     n_streams, n_blocks, ch = 64, 1024, 2
@@ -219,7 +324,7 @@ def run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
     clocks = ClockSampler(local_rank)
     clocks.start()
     # one step is ~0.3 ms: warm up for ~0.4 s (also lets the clock sampler collect samples under load)
-    warm = max(args.warmup, 1500)
+    warm = max(args.warmup, 300 if quick else 1500)
     for _ in range(warm):
         batch.decode(clip=True, sync=False)
     batch.sync()
@@ -241,43 +346,35 @@ def run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
     peak, peak_src = measured_peak()
     k3_ms = ms_max / steps
     a = 8.0 * samples_rank / (k3_ms * 1e-3) / 1e9
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
-            "ms_per_step": k3_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic spectra (seeded)",
-            "config": {"workload": "config3: kernel-only IMDCT+window+OLA, 65,536 stereo blocks per GPU "
-                                   "(64 streams x 1,024 blocks, %s)" % ("all n=2048 (the all-long variant)" if args.all_long else
-                                                                         "n=2048 long runs with n=256 short transitions"),
-                       "channel_samples_per_gpu": int(samples_rank), "short_block_fraction": float(1.0 - flags.mean()),
-                       "l2": "inputs larger than L2: %.2f GB spectra + %.2f GB PCM per step vs 126 MB L2"
-                             % (4.0 * samples_rank / 1e9, 4.0 * samples_rank / 1e9)},
-            "clocks": clk, "gpu_launches": int(launches),
-            "roofline": {"kernel": "vpz_k3_streams", "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
-                         "frac": a / peak, "traffic": None, "peak_source": peak_src, "ms_per_launch": k3_ms,
-                         "algorithmic_bytes_per_launch": 8.0 * samples_rank},
-        }))
     batch.close()
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+        "ms_per_step": k3_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic spectra (seeded)",
+        "config": {"workload": "config3: kernel-only IMDCT+window+OLA, 65,536 stereo blocks per GPU "
+                               "(64 streams x 1,024 blocks, %s)" % ("all n=2048 (the all-long variant)" if args.all_long else
+                                                                     "n=2048 long runs with n=256 short transitions"),
+                   "channel_samples_per_gpu": int(samples_rank), "short_block_fraction": float(1.0 - flags.mean()),
+                   "l2": "inputs larger than L2: %.2f GB spectra + %.2f GB PCM per step vs 126 MB L2"
+                         % (4.0 * samples_rank / 1e9, 4.0 * samples_rank / 1e9)},
+        "clocks": clk, "gpu_launches": int(launches),
+        "roofline": {"kernel": "vpz_k3_streams", "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s",
+                     "frac": a / peak, "traffic": load_traffic().get("config3:vpz_k3_streams"), "peak_source": peak_src,
+                     "ms_per_launch": k3_ms, "algorithmic_bytes_per_launch": 8.0 * samples_rank},
+    }
 
 
-def run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank):
+def run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank, with_cpu=True):
     """BASELINE config 5: random-access batch -- 16,384 short excerpts per GPU, each = SeekTo(start) + read
     4,096 samples per channel on one of {2test, 3test, issue6test} (rng(0x5EED0005), start
     uniform in [0, total - 4096)), through the host API vpz_decode_excerpts (host Ogg images in, host
-    PCM out: provider side of SeekTo on the host, windows of many excerpts in one GPU batch, D2H)."""
-    from vorbispizza_b200 import VorbisReader
+    PCM out: provider side of SeekTo on the host, windows of many excerpts in one GPU batch, D2H).
+    Excerpts shard over the ranks like streams do: every rank takes its own 16,384, no collective."""
     lib = ctx.lib
     files = load_files()[1:]
-    totals, chans = [], []
-    for d in files:
-        with VorbisReader(ctx, d) as r:
-            totals.append(int(r.total_samples))
-            chans.append(r.channels)
-    n, nread = 16384, 4096
-    rng = np.random.default_rng(0x5EED0005 + rank)
-    file_of = rng.integers(0, len(files), n).astype(np.uint32)
-    start = np.array([int(rng.integers(0, totals[f] - nread)) for f in file_of], np.int64)
-    count = np.full(n, nread, np.int32)
+    chans = [1, 2, 2]
+    file_of, start, count, nread = config5_excerpts(rank)
+    n = int(file_of.size)
     keep = [np.frombuffer(f, np.uint8) for f in files]
     ptrs = (C.c_void_p * len(files))(*[k.ctypes.data for k in keep])
     lens = (C.c_size_t * len(files))(*[k.size for k in keep])
@@ -306,23 +403,39 @@ def run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
     launches = lib.vpz_ctx_kernel_launches(ctx._h) - launches0
     delivered = sum_over_ranks(float(total_delivered))
     v = delivered * args.steps / t
-    if rank == 0:
-        print(json.dumps({
-            "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 3),
-            "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic (seeded excerpts of TestFiles)",
-            "config": {"workload": "config5: %d random-access excerpts per GPU (SeekTo + %d samples per channel on "
-                                   "{2,3,issue6}test.ogg), host Ogg images -> host PCM through vpz_decode_excerpts" % (n, nread),
-                       "excerpts_per_gpu": n, "delivered_channel_samples_per_gpu": total_delivered,
-                       "excerpts_per_s": n * world * args.steps / t,
-                       "note": "value counts the delivered samples only; every excerpt also decodes its pre-roll packet "
-                               "and the unused parts of its first and last packets"},
-            "clocks": clk, "gpu_launches": int(launches),
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": (lib.vpz_transfer_bytes(0) - h0) // args.steps,
-                    "d2h_bytes_per_step": (lib.vpz_transfer_bytes(1) - d0) // args.steps,
-                    "ms_per_step": 1e3 * t / args.steps, "api": "vpz_decode_excerpts"},
-        }))
+    line = {
+        "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 3),
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (seeded excerpts of TestFiles)",
+        "config": {"workload": "config5: %d random-access excerpts per GPU (SeekTo + %d samples per channel on "
+                               "{2,3,issue6}test.ogg), host Ogg images -> host PCM through vpz_decode_excerpts" % (n, nread),
+                   "excerpts_per_gpu": n, "delivered_channel_samples_per_gpu": total_delivered,
+                   "excerpts_per_s": n * world * args.steps / t, "parallelism": "excerpt-sharded, no collective",
+                   "note": "value counts the delivered samples only; every excerpt also decodes its pre-roll packet "
+                           "and the unused parts of its first and last packets"},
+        "clocks": clk, "gpu_launches": int(launches),
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": (lib.vpz_transfer_bytes(0) - h0) // args.steps,
+                "d2h_bytes_per_step": (lib.vpz_transfer_bytes(1) - d0) // args.steps,
+                "ms_per_step": 1e3 * t / args.steps, "api": "vpz_decode_excerpts"},
+    }
     lib.vpz_host_free(dst_p)
+    if with_cpu and rank == 0 and world == 1 and not args.no_cpu:
+        # the oracle's SeekTo + read on all host cores (one open reader per thread and file), same excerpts
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_binding as ob
+        cores = os.cpu_count() or 1
+        allf = load_files()
+        builds = {}
+        for name, native in (("O2", False), ("O3_march_native", True)):
+            if ob.bench_lib(native) is None:
+                continue
+            ob.bench_excerpts(allf[1:], file_of[:2048], start[:2048], count[:2048], cores, native)
+            nn, ss = ob.bench_excerpts(allf[1:], file_of, start, count, cores, native)
+            builds[name] = nn / ss
+        best = max(builds, key=lambda k: builds[k])
+        line["cpu_baseline"] = {"value": builds[best], "unit": UNIT, "cores": cores, "kind": "port", "build": best,
+                                "builds": builds, "sample": "all %d excerpts, SeekTo + read, one open reader per (thread, file)" % n}
+    return line
 
 
 def main():
@@ -341,6 +454,7 @@ def main():
                          "reference): single-stream CPU decode of 1test.ogg")
     ap.add_argument("--all-long", action="store_true", help="config3 only: pure n=2048 blocks (no short transitions)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="skip the config3 / config5 sub-objects of the default line")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--l1-bits", type=int, default=0, help=argparse.SUPPRESS)  # tuning: first-level Huffman table width
     ap.add_argument("--lib", default=None, help=argparse.SUPPRESS)  # dry-run the script logic on the emulated test build
@@ -408,13 +522,17 @@ def main():
         ctx.set("host_threads", max(2, min(32, (os.cpu_count() or 2) // local_world)))
     files = load_files()
     if args.workload == "config5":
-        run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank)
+        line = run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank)
+        if rank == 0:
+            print(json.dumps(line))
         ctx.close()
         if world > 1:
             dist.destroy_process_group()
         return
     if args.workload == "config3":
-        run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank)
+        line = run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank)
+        if rank == 0:
+            print(json.dumps(line))
         ctx.close()
         if world > 1:
             dist.destroy_process_group()
@@ -490,12 +608,7 @@ def main():
     k1a_bytes = 2.0 * bytes_rank
     k1b_bytes = bytes_rank + 4.0 * samples_rank
     k3_bytes = 8.0 * samples_rank
-    traffic = {}
-    try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f)
-    except Exception:
-        pass
+    traffic = load_traffic()
 
     def roof(name, nbytes, t_ms):
         a = nbytes / (t_ms * 1e-3) / 1e9
@@ -556,6 +669,15 @@ def main():
                           "d2h_bytes_per_step": (lib.vpz_transfer_bytes(1) - d1) // e_steps,
                           "api": "vpz_decode_files_s16 (16-bit PCM by the reference tests' (int)(x*32768f) rule)"}
             lib.vpz_host_free(dst16)
+        if not dry:
+            # what the device-to-host path of this box can carry with nothing but copies on it (all ranks at once)
+            link = d2h_probe(lib, local_rank, barrier, max_over_ranks, sum_over_ranks)
+            if link:
+                d2h_rate = sum_over_ranks(float(e2e["d2h_bytes_per_step"])) / (e2e["ms_per_step"] * 1e-3) / 1e9
+                e2e["link_gbs_measured"] = link
+                e2e["d2h_gbs_in_e2e"] = d2h_rate
+                e2e["frac_of_link"] = d2h_rate / link
+                e2e["link_probe"] = "1 GiB device buffer -> pinned host, back to back for ~1 s, %d rank(s) at once" % world
 
     # ---- cpu baseline (rank 0, N=1): the oracle on all host cores, bounded sample ----------------
     cpu = None
@@ -566,10 +688,36 @@ def main():
         n0, s0 = ob.bench_decode(files, 4 * cores, cores)
         njobs = int(max(4 * cores, min(n_streams, (args.cpu_seconds / max(s0, 1e-3)) * 4 * cores)))
         njobs -= njobs % 4
-        n1, s1 = ob.bench_decode(files, njobs, cores)
-        cpu = {"value": n1 / s1, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "%d of the %d streams (whole files, round-robin over the 4 TestFiles), one stream per thread, "
-                         "%.1f s wall" % (njobs, n_streams, s1)}
+        builds, wall = {}, 0.0
+        for name, native in (("O2", False), ("O3_march_native", True)):
+            if ob.bench_lib(native) is None:
+                continue
+            n1, s1 = ob.bench_decode(files, njobs, cores, native)
+            builds[name] = n1 / s1
+            wall += s1
+        best = max(builds, key=lambda k: builds[k])
+        cpu = {"value": builds[best], "unit": UNIT, "cores": cores, "kind": "port", "build": best, "builds": builds,
+               "sample": "%d of the %d streams (whole files, stream g = TestFile g %% 4), streams handed to %d threads by a "
+                         "shared cursor, %.1f s wall for both builds" % (njobs, n_streams, cores, wall)}
+
+    # ---- BASELINE configs 3 and 5 as sub-objects of this line (the driver records only the default run) ------
+    sub3 = sub5 = None
+    if not args.no_sub and not dry:
+        batch.close()
+        batch = None
+        args_sub = argparse.Namespace(**vars(args))
+        args_sub.all_long = False
+        c3 = run_config3(args_sub, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank, quick=True)
+        c5 = run_config5(args_sub, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank)
+        sub3 = {k: c3[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "roofline")}
+        sub3["workload"] = c3["config"]["workload"]
+        sub3["short_block_fraction"] = c3["config"]["short_block_fraction"]
+        sub5 = {k: c5[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "e2e") if k in c5}
+        sub5["workload"] = c5["config"]["workload"]
+        sub5["excerpts_per_s"] = c5["config"]["excerpts_per_s"]
+        if "cpu_baseline" in c5:
+            sub5["cpu_baseline"] = c5["cpu_baseline"]
+            sub5["vs_cpu_baseline"] = c5["value"] / c5["cpu_baseline"]["value"]
 
     if rank == 0:
         line = {
@@ -593,8 +741,13 @@ def main():
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
+        if sub3:
+            line["config3"] = sub3
+        if sub5:
+            line["config5"] = sub5
         print(json.dumps(line))
-    batch.close()
+    if batch is not None:
+        batch.close()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -152,6 +152,10 @@ void vo_packet_info(int size0, int size1, int block_flag, int prev_flag, int nex
  * channel-samples decoded, *seconds = wall clock. */
 int64_t vo_bench_decode(const uint8_t* const* datas, const size_t* lens, int nfiles, int njobs, int nthreads,
                         double* seconds);
+/* n excerpts: SeekTo(start[i]) + read count[i] samples per channel of file file_of[i]; every thread keeps one
+ * open reader per file.  Returns the channel-samples delivered. */
+int64_t vo_bench_excerpts(const uint8_t* const* datas, const size_t* lens, int nfiles, int n, const uint32_t* file_of,
+                          const int64_t* start, const int32_t* count, int nthreads, double* seconds);
 
 #ifdef __cplusplus
 }

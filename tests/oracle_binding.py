@@ -342,12 +342,62 @@ def packet_info(size0, size1, block_flag, prev_flag, next_flag):
     return list(a)
 
 
-def bench_decode(files, njobs, nthreads):
-    """Host-core baseline: decodes njobs whole streams (round-robin over `files`) on nthreads
-    threads inside the oracle; returns (channel_samples, seconds)."""
+_bench_libs = {}
+
+
+def bench_lib(native=False):
+    """The oracle library used for TIMING: the portable -O2 build, or (native=True) the same sources built
+    -O3 -march=native on THIS machine (oracle/Makefile `native`; rebuilt on every call site's first use so a
+    binary tuned for another CPU is never run).  None when that build is not possible here."""
+    key = bool(native)
+    if key in _bench_libs:
+        return _bench_libs[key]
+    if not native:
+        L = lib()
+    else:
+        try:
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "-s", "-B", "native"], stdout=subprocess.DEVNULL,
+                                  stderr=subprocess.DEVNULL)
+            L = C.CDLL(os.path.join(ORACLE_DIR, "build_native", "libvorbis_oracle.so"))
+        except Exception:
+            L = None
+    if L is not None:
+        L.vo_bench_decode.restype = C.c_int64
+        L.vo_bench_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.vo_bench_excerpts.restype = C.c_int64
+        L.vo_bench_excerpts.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.POINTER(C.c_double)]
+    _bench_libs[key] = L
+    return L
+
+
+def bench_decode(files, njobs, nthreads, native=False):
+    """Host-core baseline: decodes njobs whole streams (job j = file j % len(files)) on nthreads threads
+    inside the oracle, streams handed out by a shared cursor; returns (channel_samples, seconds)."""
+    L = bench_lib(native)
+    if L is None:
+        return None
     keep = [np.frombuffer(f, np.uint8) for f in files]
     ptrs = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
     lens = (C.c_size_t * len(keep))(*[k.size for k in keep])
     sec = C.c_double(0)
-    n = lib().vo_bench_decode(ptrs, lens, len(keep), njobs, nthreads, C.byref(sec))
+    n = L.vo_bench_decode(ptrs, lens, len(keep), njobs, nthreads, C.byref(sec))
+    return n, sec.value
+
+
+def bench_excerpts(files, file_of, start, count, nthreads, native=False):
+    """Host-core baseline of the random-access batch: SeekTo(start[i]) + read count[i] samples per channel of
+    files[file_of[i]], one open reader per (thread, file); returns (channel_samples delivered, seconds)."""
+    L = bench_lib(native)
+    if L is None:
+        return None
+    keep = [np.frombuffer(f, np.uint8) for f in files]
+    ptrs = (C.c_void_p * len(keep))(*[k.ctypes.data for k in keep])
+    lens = (C.c_size_t * len(keep))(*[k.size for k in keep])
+    file_of = np.ascontiguousarray(file_of, np.uint32)
+    start = np.ascontiguousarray(start, np.int64)
+    count = np.ascontiguousarray(count, np.int32)
+    sec = C.c_double(0)
+    n = L.vo_bench_excerpts(ptrs, lens, len(keep), int(file_of.size), file_of.ctypes.data, start.ctypes.data,
+                            count.ctypes.data, nthreads, C.byref(sec))
     return n, sec.value
