@@ -324,7 +324,7 @@ def run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
     clocks = ClockSampler(local_rank)
     clocks.start()
     # one step is ~0.3 ms: warm up for ~0.4 s (also lets the clock sampler collect samples under load)
-    warm = max(args.warmup, 300 if quick else 1500)
+    warm = max(args.warmup, 1500)
     for _ in range(warm):
         batch.decode(clip=True, sync=False)
     batch.sync()
@@ -516,6 +516,11 @@ def main():
     lib = ctx.lib
     if args.l1_bits:
         ctx.set("l1_bits", args.l1_bits)
+    # experiments (tools/gpu_r2e.sh): page scan on the host / a fixed number of host worker threads
+    if os.environ.get("VPZ_BENCH_GPU_SCAN"):
+        ctx.set("gpu_scan", int(os.environ["VPZ_BENCH_GPU_SCAN"]))
+    if os.environ.get("VPZ_BENCH_HOST_THREADS"):
+        ctx.set("host_threads", int(os.environ["VPZ_BENCH_HOST_THREADS"]))
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if local_world > 1:
         # the ranks of one box share its host cores: split them instead of oversubscribing the bulk path's pool

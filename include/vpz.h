@@ -67,7 +67,9 @@ int vpz_device_count(void);
 /* Tunables (call before the first batch): key one of "l1_bits" (Huffman first-level table width,
  * default 9), "ola_chunk" (packets per IMDCT work item, default: 16..63 chosen per batch), "k1_warps" (warps per entropy
  * CTA, default 4), "bulk_group" (streams per pipeline group of vpz_decode_files, default 256),
- * "host_threads" (host worker threads of the bulk path, default 0 = all cores up to 32). */
+ * "host_threads" (host worker threads of the bulk path, default 0 = all cores up to 32), "gpu_scan" (bulk
+ * path: Ogg page scan + CRC on the GPU, default 1), "force_general" (tests: route every packet through the
+ * general kernels). */
 int vpz_ctx_set(vpz_ctx* ctx, const char* key, int value);
 
 /* Device-side stopwatch on the context's stream: vpz_ctx_mark records CUDA event `slot` (0..7) on
@@ -265,6 +267,32 @@ int64_t vpz_decode_files(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, 
  * stereo only (VPZ_E_UNSUPPORTED otherwise).  dst_samples / return value: int16 elements. */
 int64_t vpz_decode_files_s16(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens,
                              int clip, int16_t* dst, size_t dst_samples, int64_t* sample_counts);
+
+/* ---- physical Ogg layer on the GPU ----------------------------------------------- */
+/* One valid Ogg page as PageReaderBase.ReadNextPage / VerifyPage accept it (Ogg/PageReaderBase.cs:41-84,
+ * 286-361): found by capture-pattern search, segment table and body inside the data, CRC-32 (Ogg/Crc.cs:20-63)
+ * verified, packets counted (Ogg/PageHeader.cs:35-59). */
+typedef struct {
+  uint32_t offset;          /* of the page in its container image */
+  uint32_t body_len;
+  uint32_t granule_lo, granule_hi;
+  uint32_t serial, sequence;
+  uint8_t flags;            /* 1 continuation, 2 BOS, 4 EOS (Contracts/Ogg/PageFlags.cs) */
+  uint8_t segments;
+  uint8_t is_resync;        /* bytes were skipped in front of this page */
+  uint8_t is_continued;     /* the last lacing value is 255 */
+  uint16_t packet_count;
+  uint16_t reserved;
+} vpz_page_info;
+
+/* Scans n container images on the GPU, one warp per image: sync search, header parse, lacing sums, page CRC.
+ * The pages of image i are pages[first[i] .. first[i] + count[i]); waste_bits[i] = bits that belong to no
+ * valid page (IVorbisReader.ContainerWasteBits before per-stream filtering), crc_failures[i] = candidates whose
+ * CRC did not match.  Any output pointer may be NULL.  Returns the total number of pages or a negative error.
+ * vpz_decode_files uses the same scan ("gpu_scan" tunable, default 1). */
+int64_t vpz_scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens,
+                       vpz_page_info* pages, size_t pages_cap, uint32_t* first, uint32_t* count,
+                       uint64_t* waste_bits, uint32_t* crc_failures);
 
 /* ---- bulk random access: many short excerpts, one call (BASELINE config 5) -------------------- */
 /* Excerpt i is what a fresh VorbisReader over container image file_of[i] delivers for

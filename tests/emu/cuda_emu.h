@@ -134,6 +134,7 @@ inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
 }
 inline float __uint_as_float(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 inline int __ffs(int x) { return __builtin_ffs(x); }
+inline int __popc(uint32_t x) { return __builtin_popcount(x); }
 inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 inline uint32_t __brev(uint32_t n) {

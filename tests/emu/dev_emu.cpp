@@ -8,6 +8,7 @@
 
 #include "../../include/vpz.h"
 #include "../../vorbispizza_b200/csrc/devapi.h"
+#include "../../vorbispizza_b200/csrc/k0_pages.cuh"
 #include "../../vorbispizza_b200/csrc/k1_symbols.cuh"
 #include "../../vorbispizza_b200/csrc/k3_streams.cuh"
 
@@ -111,6 +112,12 @@ int fill(void* d, int v, size_t n, Stream*, std::string&) {
   return VPZ_OK;
 }
 
+int launch_k0(const K0Params& p, Stream*, std::string&) {
+  if (p.n_files == 0) return VPZ_OK;
+  emu::launch(1, K0_THREADS, K0_SMEM_WORDS * 4, [&] { k0_cta(p, (uint32_t*)emu::t_block->smem); });
+  return VPZ_OK;
+}
+
 int launch_k1a(const K1Params& p, bool debug, bool full, int blocks, Stream*, std::string&) {
   if (p.n_pkts == 0) return VPZ_OK;
   (void)blocks;  // work stealing: one emulated block drains the whole queue
@@ -164,7 +171,12 @@ int launch_k3_streams(const K3Params& p, Stream*, std::string&) {
   if (p.n_items == 0) return VPZ_OK;
   const unsigned groups = p.n_items >= 3 ? 3 : 1;   // independent 64-thread workers per emulated CTA
   emu::launch(2, groups * K3_THREADS_PER_CH, ((size_t)K3S_TAB_FLOATS + groups * K3S_GROUP_FLOATS) * 4, [&] {
-    if (p.out16) k3s_cta<true>(p, (float*)emu::t_block->smem); else k3s_cta<false>(p, (float*)emu::t_block->smem);
+    float* sm = (float*)emu::t_block->smem;
+    if (p.res) {
+      if (p.out16) k3s_cta<true, true>(p, sm); else k3s_cta<false, true>(p, sm);
+    } else {
+      if (p.out16) k3s_cta<true, false>(p, sm); else k3s_cta<false, false>(p, sm);
+    }
   });
   return VPZ_OK;
 }

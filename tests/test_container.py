@@ -155,3 +155,132 @@ def test_damaged_streams(gpu_ctx, name):
 @pytest.mark.gpu
 def test_chained_streams(gpu_ctx):
     _chained_parity(gpu_ctx, ["1test", "3test", "2test"])
+
+
+# ---- K0: the physical Ogg layer on the GPU ------------------------------------------
+def _reference_page_scan(data):
+    """PageReaderBase.ReadNextPage / VerifyHeader / VerifyPage (Ogg/PageReaderBase.cs:41-84,176-212,286-361) in
+    plain Python: byte-by-byte sync search, segment table and body inside the data, CRC over the page with a
+    zeroed CRC field.  Returns (pages, waste_bits, crc_failures)."""
+    import struct
+    pages, pos, waste, crcf, resync, n = [], 0, 0, 0, False, len(data)
+    while pos + 4 <= n:
+        ok = pos + 27 <= n and data[pos:pos + 4] == b"OggS"
+        if ok:
+            nseg = data[pos + 26]
+            ok = pos + 27 + nseg <= n
+        if ok:
+            lacing = data[pos + 27:pos + 27 + nseg]
+            total = 27 + nseg + sum(lacing)
+            ok = pos + total <= n
+        if ok:
+            want = struct.unpack_from("<I", data, pos + 22)[0]
+            page = bytearray(data[pos:pos + total])
+            page[22:26] = b"\0\0\0\0"
+            if oggmux.crc32_ogg(bytes(page)) != want:
+                crcf += 1
+                ok = False
+        if not ok:
+            pos += 1
+            waste += 8
+            resync = True
+            continue
+        gran, serial, seq = struct.unpack_from("<qII", data, pos + 6)
+        cont = nseg > 0 and lacing[-1] == 255
+        pages.append(dict(offset=pos, body_len=total - 27 - nseg, granule=gran, serial=serial, sequence=seq,
+                          flags=data[pos + 5], segments=nseg, is_resync=int(resync), is_continued=int(cont),
+                          packet_count=sum(1 for v in lacing if v < 255) + (1 if cont else 0)))
+        resync = False
+        pos += total
+    if pos < n:
+        waste += 8 * (n - pos)
+    return pages, waste, crcf
+
+
+def _scan_parity(ctx, datas, what):
+    from vorbispizza_b200 import scan_pages
+    got = scan_pages(ctx, datas)
+    assert len(got) == len(datas)
+    for k, (data, (pages, waste, crcf)) in enumerate(zip(datas, got)):
+        ref, rwaste, rcrc = _reference_page_scan(data)
+        assert len(pages) == len(ref), (what, k, len(pages), len(ref))
+        for i, r in enumerate(ref):
+            for key, v in r.items():
+                assert int(pages[i][key]) == v, (what, k, "page", i, key, int(pages[i][key]), v)
+        assert (waste, crcf) == (rwaste, rcrc), (what, k, waste, crcf, rwaste, rcrc)
+        # the oracle's own Ogg layer agrees on the verdicts that it exposes
+        try:
+            s = ob.OracleStream(data)
+            assert s.crc_failures() == crcf, (what, k)
+        except ob.OracleError:
+            pass
+
+
+def _scan_cases(names, limit):
+    out = []
+    for name in names:
+        out.append((name, cases.load_file(name)))
+        for kind, data in damaged_streams(name, limit).items():
+            out.append(("%s/%s" % (name, kind), data))
+    out.append(("garbage only", bytes(range(256)) * 3))
+    out.append(("empty", b""))
+    out.append(("three bytes", b"Ogg"))
+    out.append(("truncated page", cases.load_file("1test")[:5000]))
+    out.append(("capture pattern inside garbage", b"xxOggSOggS" + b"\0" * 40 + cases.load_file("1test")[:4500] + b"OggS"))
+    return out
+
+
+def test_gpu_page_scan_emulated(emu_ctx):
+    cs = _scan_cases(["1test"], None) + _scan_cases(["3test"], 60)[1:4]
+    _scan_parity(emu_ctx, [d for _, d in cs], "page scan")
+
+
+def test_reader_on_device_scanned_pages_emulated(emu_lib_path):
+    """The whole reader surface on top of the DEVICE page scan ("gpu_scan" 2): damaged streams included."""
+    from vorbispizza_b200 import Context
+    ctx = Context(0, lib_path=emu_lib_path)
+    try:
+        ctx.set("gpu_scan", 2)
+        for kind, data in damaged_streams("1test").items():
+            cases.reader_parity_bytes(ctx, data, "1test/%s (device scan)" % kind, lookahead=16)
+        _chained_parity(ctx, ["1test", "2test"], limit=20)
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_gpu_page_scan(gpu_ctx):
+    cs = _scan_cases(["1test", "2test", "3test", "issue6test"], None)
+    _scan_parity(gpu_ctx, [d for _, d in cs], "page scan")
+    # many images in one call (one warp each)
+    _scan_parity(gpu_ctx, [cases.load_file(n) for n in ["1test", "2test", "3test", "issue6test"]] * 40, "page scan x160")
+
+
+@pytest.mark.gpu
+def test_reader_on_device_scanned_pages():
+    from vorbispizza_b200 import Context
+    ctx = Context(0)
+    try:
+        ctx.set("gpu_scan", 2)
+        for name in ["1test", "3test", "issue6test"]:
+            for kind, data in damaged_streams(name).items():
+                cases.reader_parity_bytes(ctx, data, "%s/%s (device scan)" % (name, kind), lookahead=64)
+        _chained_parity(ctx, ["1test", "3test", "2test"])
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_bulk_decode_same_with_host_and_device_scan(gpu_ctx):
+    from vorbispizza_b200 import Context, decode_files
+    datas = [cases.load_file(n) for n in ["1test", "2test", "3test", "issue6test"]]
+    for kind, d in damaged_streams("3test").items():
+        datas.append(d)
+    a, ca = decode_files(gpu_ctx, datas, clip=True)
+    host = Context(0)
+    try:
+        host.set("gpu_scan", 0)
+        b, cb = decode_files(host, datas, clip=True)
+    finally:
+        host.close()
+    assert (ca == cb).all() and np.array_equal(a.view(np.uint32), b.view(np.uint32))

@@ -3,7 +3,7 @@
 TAG=${1:-b}
 OUT=gpurun_out
 mkdir -p $OUT
-echo "== bench (default)"; /usr/bin/time -v -o $OUT/bench_time_$TAG.txt timeout 1200 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "exit $?"; grep -E "Elapsed|Maximum resident" $OUT/bench_time_$TAG.txt; tail -3 $OUT/bench_$TAG.err
+echo "== bench (default)"; T0=$SECONDS; timeout 1200 python bench.py > $OUT/bench_$TAG.json 2> $OUT/bench_$TAG.err; echo "exit $? after $((SECONDS-T0)) s"; tail -3 $OUT/bench_$TAG.err
 python - <<PY
 import json
 d = json.load(open("$OUT/bench_$TAG.json"))
@@ -12,4 +12,4 @@ print("config3", d.get("config3",{}).get("roofline",{}).get("frac"), d.get("conf
 print("config5", d.get("config5",{}).get("value"), d.get("config5",{}).get("ms_per_step"), d.get("config5",{}).get("cpu_baseline"))
 print("cpu", d.get("cpu_baseline"))
 PY
-echo "== bench reference"; /usr/bin/time -v -o $OUT/benchref_time_$TAG.txt timeout 1200 python bench.py --impl reference > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "exit $?"; grep -E "Elapsed" $OUT/benchref_time_$TAG.txt; cat $OUT/bench_ref_$TAG.json | cut -c1-600
+echo "== bench reference"; T0=$SECONDS; timeout 1200 python bench.py --impl reference > $OUT/bench_ref_$TAG.json 2> $OUT/bench_ref_$TAG.err; echo "exit $? after $((SECONDS-T0)) s"; cat $OUT/bench_ref_$TAG.json | cut -c1-600

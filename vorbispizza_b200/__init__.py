@@ -17,7 +17,8 @@ from .api import (  # noqa: F401
     VorbisReader,
     decode_excerpts,
     decode_files,
+    scan_pages,
 )
 
-__all__ = ["Batch", "Context", "SynthBatch", "VorbisReader", "decode_files", "decode_excerpts", "VpzError", "InvalidDataError",
+__all__ = ["Batch", "Context", "SynthBatch", "VorbisReader", "decode_files", "decode_excerpts", "scan_pages", "VpzError", "InvalidDataError",
            "SeekOutOfRangeError", "PreRollPacketError", "load"]

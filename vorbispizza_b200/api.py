@@ -487,3 +487,29 @@ def decode_excerpts(ctx, files, file_of, start, count, clip=True, dst=None):
         dst = np.zeros(total, np.float32)
     total = ctx.check(ctx.lib.vpz_decode_excerpts(*args, dst.ctypes.data, dst.size, offsets.ctypes.data, got.ctypes.data))
     return dst[:total], offsets, got
+
+
+PAGE_DTYPE = np.dtype([("offset", "<u4"), ("body_len", "<u4"), ("granule", "<i8"), ("serial", "<u4"), ("sequence", "<u4"),
+                       ("flags", "u1"), ("segments", "u1"), ("is_resync", "u1"), ("is_continued", "u1"),
+                       ("packet_count", "<u2"), ("reserved", "<u2")])
+
+
+def scan_pages(ctx, datas):
+    """vpz_scan_pages: the physical Ogg layer of many container images on the GPU (capture-pattern search, header
+    parse, lacing sums, page CRC-32; Ogg/PageReaderBase.cs:41-84,286-361).  Returns a list with, per image,
+    (pages: structured array of PAGE_DTYPE, waste_bits, crc_failures)."""
+    n = len(datas)
+    keep = [np.frombuffer(d, np.uint8) for d in datas]
+    ptrs = (C.c_void_p * max(n, 1))(*[k.ctypes.data if k.size else None for k in keep])
+    lens = (C.c_size_t * max(n, 1))(*[k.size for k in keep])
+    first = np.zeros(n, np.uint32)
+    count = np.zeros(n, np.uint32)
+    waste = np.zeros(n, np.uint64)
+    crcf = np.zeros(n, np.uint32)
+    cap = sum(len(d) // 64 + 16 for d in datas) + 1
+    pages = np.zeros(cap, PAGE_DTYPE)
+    assert PAGE_DTYPE.itemsize == 32
+    total = ctx.check(ctx.lib.vpz_scan_pages(ctx._h, n, ptrs, lens, pages.ctypes.data, cap, first.ctypes.data,
+                                              count.ctypes.data, waste.ctypes.data, crcf.ctypes.data))
+    assert total == int(count.sum())
+    return [(pages[int(first[i]):int(first[i]) + int(count[i])].copy(), int(waste[i]), int(crcf[i])) for i in range(n)]

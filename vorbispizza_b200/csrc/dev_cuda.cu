@@ -7,10 +7,16 @@
 
 #include "../../include/vpz.h"
 #include "devapi.h"
+#include "k0_pages.cuh"
 #include "k1_symbols.cuh"
 #include "k3_streams.cuh"
 
 // ---- kernels ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(K0_THREADS) vpz_k0_pages(K0Params P) {
+  __shared__ uint32_t k0_smem[K0_SMEM_WORDS];
+  k0_cta(P, k0_smem);
+}
+
 template <bool DEBUG, bool FULL>
 __global__ void __launch_bounds__(128, 8) vpz_k1a_symbols(K1Params P) {
   const int lane = threadIdx.x & 31;
@@ -47,10 +53,11 @@ __global__ void __launch_bounds__(128, 1) vpz_k3_imdct_ola(K3Params P, int ncb) 
 }
 
 // block sizes 256 / 2048, mono / stereo: one CTA per SM, up to 12 independent 64-thread workers
-template <bool OUT16>
+// ENDS: the spectra come from K1b (exec masks and written ends in P.res); false for caller-provided spectra
+template <bool OUT16, bool ENDS>
 __global__ void __launch_bounds__(K3_THREADS_PER_CH * K3S_MAX_GROUPS, 1) vpz_k3_streams(K3Params P) {
   extern __shared__ float k3_smem[];
-  k3s_cta<OUT16>(P, k3_smem);
+  k3s_cta<OUT16, ENDS>(P, k3_smem);
 }
 
 namespace vpz {
@@ -123,8 +130,10 @@ int init(int device, int* resolved, std::string& err) {
   cudaFuncSetAttribute(vpz_k1b_general<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   cudaFuncSetAttribute(vpz_k3_imdct_ola<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   cudaFuncSetAttribute(vpz_k3_imdct_ola<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k3_streams<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k3_streams<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k3_streams<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k3_streams<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k3_streams<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  cudaFuncSetAttribute(vpz_k3_streams<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute", err);
   return VPZ_OK;
@@ -231,6 +240,15 @@ int fill(void* dst, int byte_value, size_t bytes, Stream* s, std::string& err) {
   return e == cudaSuccess ? VPZ_OK : fail(e, "cudaMemsetAsync", err);
 }
 
+int launch_k0(const K0Params& p, Stream* s, std::string& err) {
+  if (p.n_files == 0) return VPZ_OK;
+  const unsigned warps = K0_THREADS / 32;
+  unsigned grid = (unsigned)std::min<size_t>(((size_t)p.n_files + warps - 1) / warps, (size_t)8 * sm_count());
+  vpz_k0_pages<<<grid, K0_THREADS, 0, s->s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k0_pages", err);
+}
+
 int launch_k1a(const K1Params& p, bool debug, bool full, int blocks, Stream* s, std::string& err) {
   if (p.n_pkts == 0) return VPZ_OK;
   if (debug) {
@@ -293,10 +311,12 @@ int launch_k3_streams(const K3Params& p, Stream* s, std::string& err) {
     return VPZ_E_UNSUPPORTED;
   }
   unsigned grid = (unsigned)std::min<size_t>((p.n_items + groups - 1) / groups, (size_t)sm_count());
-  if (p.out16)
-    vpz_k3_streams<true><<<grid, groups * K3_THREADS_PER_CH, smem_bytes, s->s>>>(p);
-  else
-    vpz_k3_streams<false><<<grid, groups * K3_THREADS_PER_CH, smem_bytes, s->s>>>(p);
+  const int threads = groups * K3_THREADS_PER_CH;
+  if (p.res) {
+    if (p.out16) vpz_k3_streams<true, true><<<grid, threads, smem_bytes, s->s>>>(p); else vpz_k3_streams<false, true><<<grid, threads, smem_bytes, s->s>>>(p);
+  } else {
+    if (p.out16) vpz_k3_streams<true, false><<<grid, threads, smem_bytes, s->s>>>(p); else vpz_k3_streams<false, false><<<grid, threads, smem_bytes, s->s>>>(p);
+  }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k3_streams", err);
 }

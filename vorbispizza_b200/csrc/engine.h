@@ -62,6 +62,17 @@ class ThreadPool {
 };
 }  // namespace vpz
 
+namespace vpz {
+struct ScanBufs;                     // scan.cpp: staging of the device page scan (K0)
+void scan_bufs_destroy(ScanBufs* s);
+struct ScanResult {                  // views into the context's scan buffers, valid until the next scan
+  uint32_t n = 0;
+  const VpzScanFile* files = nullptr;
+  const VpzPageRec* pages = nullptr;
+  const VpzScanOut* out = nullptr;
+};
+}  // namespace vpz
+
 struct vpz_ctx {
   int device = 0;
   vpz::dev::Stream* stream = nullptr;
@@ -74,6 +85,8 @@ struct vpz_ctx {
   bool ola_chunk_set = false;   // set by the user: do not adapt it to the batch size (pick_ola_chunk)
   int k1_warps = 4;
   int force_general = 0;   // tests: 1 = every packet through the general K1b and the generic K3, 2 = also the full K1a
+  int gpu_scan = 1;        // bulk path: page scan + CRC on the device (K0); 0 = on the host worker threads
+  vpz::ScanBufs* scan = nullptr;
   std::multimap<uint64_t, vpz_setup*> setups;
   std::vector<vpz_setup*> recent;     // setups the context itself holds a reference on (LRU, 64)
   uint32_t* d_counter = nullptr;
@@ -223,6 +236,8 @@ int batch_upload(vpz_batch* b);
 int batch_decode(vpz_batch* b, int clip, int out16 = 0);   // out16: 16-bit PCM (fast IMDCT kernel only)
 int batch_fetch_clip(vpz_batch* b);
 void batch_drop_slots(vpz_batch* b);   // releases the setup references the batch's slots hold
+// K0: physical Ogg page scan of n container images on the device (scan.cpp)
+int scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, ThreadPool* pool, ScanResult* res);
 }  // namespace vpz
 
 // First statement of every extern "C" entry point that may touch the device: the CUDA current device

@@ -1,0 +1,208 @@
+// k0_pages.cuh -- K0: the physical Ogg layer on the GPU.  ONE WARP PER CONTAINER IMAGE walks the page chain of
+// its file: capture-pattern search, header parse, lacing sums, packet counts, and the page CRC-32 computed by the
+// 32 lanes together.  It emits one VpzPageRec per valid page plus the file's waste / CRC-failure counters; the
+// host turns the records into its per-serial page lists (ogg.cpp, OggContainer::scan_from_records) without
+// touching the page bytes again.
+//
+// Replaces (reference file:line):
+//   PageReaderBase.ReadNextPage / VerifyHeader / VerifyPage   Ogg/PageReaderBase.cs:41-84,176-212,286-361
+//     (sync search byte by byte, "OggS", segment table inside the data, CRC over the page with a zeroed
+//      CRC field; a candidate that fails is skipped ONE byte and counted as waste)
+//   Crc.Update / Crc.Test                                     Ogg/Crc.cs:20-63, Ogg/Crc.Table.cs:14 (poly 0x04c11db7)
+//   PageHeader.GetPacketCount                                 Ogg/PageHeader.cs:35-59
+#pragma once
+#include "k1_params.h"
+
+#ifndef VPZ_EMU
+#define K0_DEV __device__ __forceinline__
+#else
+#define K0_DEV inline
+#endif
+
+#define K0_POLY 0x04c11db7u
+#define K0_THREADS 128
+// shared memory words: byte table [256], lane constants [32] (x^(128 (31 - l)) mod P), x^4096 mod P
+#define K0_SMEM_WORDS (256 + 32 + 1)
+
+// carry-less a * b mod P (degree < 32 operands)
+K0_DEV uint32_t k0_mulmod(uint32_t a, uint32_t b) {
+  uint32_t r = 0;
+#pragma unroll 4
+  for (int i = 31; i >= 0; i--) {
+    r = (r << 1) ^ ((r & 0x80000000u) ? K0_POLY : 0u);
+    if ((b >> i) & 1u) r ^= a;
+  }
+  return r;
+}
+
+// x^n mod P
+K0_DEV uint32_t k0_xpow(uint32_t n) {
+  uint32_t r = 1;
+  for (uint32_t i = 0; i < n; i++) r = (r << 1) ^ ((r & 0x80000000u) ? K0_POLY : 0u);
+  return r;
+}
+
+// Filled by the whole CTA once: tab[256] = the MSB-first byte table, then the combine constants.
+K0_DEV void k0_init_tables(uint32_t* sm, int tid) {
+  for (int i = tid; i < 256; i += K0_THREADS) {
+    uint32_t r = (uint32_t)i << 24;
+    for (int j = 0; j < 8; j++) r = (r << 1) ^ ((r & 0x80000000u) ? K0_POLY : 0u);
+    sm[i] = r;
+  }
+  if (tid < 32) sm[256 + tid] = k0_xpow(128u * (uint32_t)(31 - tid));
+  if (tid == 32) sm[256 + 32] = k0_xpow(4096u);
+  __syncthreads();
+}
+
+// Ogg page CRC by one warp: the page is `n` bytes at img + pos; bytes 22..25 (the CRC field) count as zero.
+// The CRC starts from 0 and has no final xor, so zero bytes in FRONT of the message do not change it: the
+// message is padded at the front to a multiple of 512 bytes, every round the 32 lanes take 16 bytes each from
+// state 0, their values are brought to the end of the round by the constants x^(128 (31 - lane)) and summed;
+// the running value moves on by x^4096 per round.
+K0_DEV uint32_t k0_page_crc(const uint8_t* img, uint32_t pos, uint32_t n, const uint32_t* sm, int lane) {
+  const int pad = (int)((512u - (n & 511u)) & 511u);
+  const int rounds = (int)((n + (uint32_t)pad) >> 9);
+  const uint32_t klane = sm[256 + lane], kround = sm[256 + 32];
+  uint32_t crc = 0;
+  for (int r = 0; r < rounds; r++) {
+    const int i0 = r * 512 + lane * 16 - pad;   // first message byte of this lane's 16
+    uint32_t c = 0;
+    if (i0 + 16 > 0) {
+#pragma unroll 4
+      for (int k = 0; k < 16; k++) {
+        const int i = i0 + k;
+        const uint32_t b = (i < 0 || (i >= 22 && i < 26)) ? 0u : (uint32_t)img[pos + (uint32_t)i];
+        c = (c << 8) ^ sm[((c >> 24) ^ b) & 0xffu];
+      }
+    }
+    c = k0_mulmod(c, klane);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) c ^= __shfl_xor_sync(0xffffffffu, c, d);
+    crc = k0_mulmod(crc, kround) ^ c;
+  }
+  return crc;
+}
+
+K0_DEV uint32_t k0_load_le32(const uint8_t* p) {
+  return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+
+// One file by one warp.  All control flow is warp-uniform (values come from ballots / shuffles).
+K0_DEV void k0_scan_file(const K0Params& P, uint32_t fi, const uint32_t* sm, int lane) {
+  const VpzScanFile f = P.files[fi];
+  const uint8_t* img = P.images + f.data_off;
+  const uint32_t len = f.len;
+  VpzPageRec* out = P.pages + f.page_base;
+  uint32_t n_pages = 0, crc_fail = 0, overflow = 0;
+  unsigned long long waste = 0;   // bytes
+  uint32_t pos = 0;
+  bool resync = false;
+  while (pos + 4 <= len) {
+    // ---- capture pattern at pos?  else the next candidate among the following positions --------------
+    {
+      const uint32_t q = pos + (uint32_t)lane;
+      const bool hit = q + 4 <= len && img[q] == 'O' && img[q + 1] == 'g' && img[q + 2] == 'g' && img[q + 3] == 'S';
+      const uint32_t m = __ballot_sync(0xffffffffu, hit);
+      if (!m) {
+        // every position tried and refused is one wasted byte (PageReaderBase.cs:56-70); positions with fewer
+        // than four bytes behind them are not tried (they are counted after the loop)
+        const uint32_t valid = len - 3u - pos;   // >= 1 here
+        const uint32_t tried = valid < 32u ? valid : 32u;
+        waste += tried;
+        pos += tried;
+        resync = true;
+        continue;
+      }
+      const uint32_t skip = (uint32_t)__ffs((int)m) - 1u;
+      if (skip) {
+        waste += skip;
+        pos += skip;
+        resync = true;
+      }
+    }
+    // ---- try_page(pos): header inside the data, segment table inside, body inside, CRC ----------------
+    bool ok = pos + 27 <= len;
+    uint32_t nseg = 0, body = 0, npk = 0, last_seg = 0;
+    if (ok) {
+      nseg = img[pos + 26];
+      ok = pos + 27 + nseg <= len;
+    }
+    if (ok) {
+      for (uint32_t s0 = 0; s0 < nseg; s0 += 32) {
+        const uint32_t s = s0 + (uint32_t)lane;
+        const uint32_t v = s < nseg ? (uint32_t)img[pos + 27 + s] : 0u;
+        uint32_t sum = v;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+        body += sum;
+        npk += (uint32_t)__popc(__ballot_sync(0xffffffffu, s < nseg && v < 255u));
+        if (s0 + 32 >= nseg) last_seg = __shfl_sync(0xffffffffu, v, (int)((nseg - 1u) & 31u));
+      }
+      ok = pos + 27 + nseg + body <= len;
+    }
+    const uint32_t total = 27u + nseg + body;
+    if (ok) {
+      const uint32_t want = k0_load_le32(img + pos + 22);
+      const uint32_t crc = k0_page_crc(img, pos, total, sm, lane);
+      if (crc != want) {
+        crc_fail++;
+        ok = false;
+      }
+    }
+    if (!ok) {   // not a page: one byte of waste, search on (PageReaderBase.cs:56-70)
+      pos++;
+      waste++;
+      resync = true;
+      continue;
+    }
+    if (n_pages >= f.page_cap) {   // more pages than the caller sized for: the host scans this file itself
+      overflow = 1;
+      break;
+    }
+    if (lane == 0) {
+      VpzPageRec r;
+      r.offset = pos;
+      r.body_len = body;
+      r.granule_lo = k0_load_le32(img + pos + 6);
+      r.granule_hi = k0_load_le32(img + pos + 10);
+      r.serial = k0_load_le32(img + pos + 14);
+      r.seq = k0_load_le32(img + pos + 18);
+      r.flags = img[pos + 5];
+      r.nseg = (uint8_t)nseg;
+      r.is_resync = resync ? 1 : 0;
+      const bool cont = nseg > 0 && last_seg == 255u;
+      r.is_continued = cont ? 1 : 0;
+      r.packet_count = (uint16_t)(npk + (cont ? 1u : 0u));
+      r.pad = 0;
+      out[n_pages] = r;
+    }
+    n_pages++;
+    resync = false;
+    pos += total;
+  }
+  if (!overflow && pos < len) waste += len - pos;
+  if (lane == 0) {
+    VpzScanOut o;
+    o.n_pages = n_pages;
+    o.crc_failures = crc_fail;
+    o.waste_lo = (uint32_t)waste;
+    o.waste_hi = (uint32_t)(waste >> 32);
+    o.overflow = overflow;
+    o.pad[0] = o.pad[1] = o.pad[2] = 0;
+    P.out[fi] = o;
+  }
+}
+
+// kernel body: warps take files from the counter
+K0_DEV void k0_cta(const K0Params& P, uint32_t* sm) {
+  const int tid = (int)threadIdx.x, lane = tid & 31;
+  k0_init_tables(sm, tid);
+  for (;;) {
+    uint32_t fi = 0;
+    if (lane == 0) fi = atomicAdd(P.counter, 1u);
+    fi = __shfl_sync(0xffffffffu, fi, 0);
+    if (fi >= P.n_files) break;
+    k0_scan_file(P, fi, sm, lane);
+    __syncwarp();
+  }
+}

@@ -44,3 +44,12 @@ struct K3Params {
   int clip;
   float* dbg_imdct;                // debug: raw y[0..N) of every packet, [ch][N] at 2*spec_off, may be NULL
 };
+
+struct K0Params {
+  const uint8_t* images;           // staged container images
+  const VpzScanFile* files;
+  VpzPageRec* pages;
+  VpzScanOut* out;                 // one per file
+  uint32_t n_files;
+  uint32_t* counter;               // work-stealing cursor over files (zeroed before the launch)
+};

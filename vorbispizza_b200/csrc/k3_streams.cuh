@@ -36,8 +36,10 @@
 #ifndef VPZ_K3_END
 #define VPZ_K3_END 1
 #endif
+// ENDS is a template parameter of the kernel: spectra that did not come from K1b (vpz_synth_create) are
+// complete, and the kernel-only path must not pay for the tests
 #if VPZ_K3_END
-#define K3S_END16(rw, c) ((int)(((rw) >> (16 + 8 * (c))) & 0xffu))
+#define K3S_END16(rw, c) (ENDS ? (int)(((rw) >> (16 + 8 * (c))) & 0xffu) : 255)
 #else
 #define K3S_END16(rw, c) 255
 #endif
@@ -107,7 +109,7 @@ VPZ_DEV bool k3s_emit_same_size(const float* hi0 /* D[M/2..] of channel 0 */, co
 }
 
 // one work item, C = 1 or 2 channels, by one 64-thread group.  OUT16: 16-bit PCM (k3_s16) instead of fp32
-template <bool OUT16>
+template <bool OUT16, bool ENDS>
 VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs, float* gbase, int grp, int t64) {
   const VpzOlaItem it = item;  // the item lives in global memory: read it once
   const uint32_t* blob = P.setups[it.setup_slot];
@@ -139,18 +141,18 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
     if (t64 < nb) {
       spk[t64] = P.pkts[first + pb + t64];
       // exec mask | status << 8 | end16[0] << 16 | end16[1] << 24 (VpzPktRes); no K1: every channel, every bin
-      smask[t64] = P.res ? reinterpret_cast<const uint32_t*>(P.res)[first + pb + t64] : 0xffff00ffu;
+      smask[t64] = ENDS ? reinterpret_cast<const uint32_t*>(P.res)[first + pb + t64] : 0xffff00ffu;
     }
     K3_GSYNC(grp);
     for (int pw = 0; pw < nb; pw++, parity ^= 1) {
       const int pi = pb + pw;
       const uint32_t gp = (uint32_t)(first + pi);
       const VpzPktOla pk = spk[pw];
-      const uint32_t rw = smask[pw];
+      const uint32_t rw = ENDS ? smask[pw] : 0xffff00ffu;
       const uint32_t mask = rw & 0xffu;
       const bool has_next = pw + 1 < nb;
       const VpzPktOla pk_next = spk[has_next ? pw + 1 : pw];
-      const uint32_t rw_next = smask[has_next ? pw + 1 : pw];
+      const uint32_t rw_next = ENDS ? smask[has_next ? pw + 1 : pw] : 0xffff00ffu;
       const uint32_t mask_next = rw_next & 0xffu;
       const bool next_long = has_next && (pk_next.flags & VPZ_OLA_LONG);
       const bool is_long = pk.flags & VPZ_OLA_LONG;
@@ -303,7 +305,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
 }
 
 // kernel body: `groups` = blockDim.x / 64 workers per CTA
-template <bool OUT16>
+template <bool OUT16, bool ENDS>
 VPZ_DEV void k3s_cta(const K3Params& P, float* smem) {
   const int tid = threadIdx.x;
   const int grp = tid / K3_THREADS_PER_CH, t64 = tid % K3_THREADS_PER_CH;
@@ -346,6 +348,6 @@ VPZ_DEV void k3s_cta(const K3Params& P, float* smem) {
     K3_GSYNC(grp);
     const uint32_t idx = *slot;
     if (idx >= P.n_items) break;
-    k3s_run_item<OUT16>(P, P.items[idx], smem, gbase, grp, t64);
+    k3s_run_item<OUT16, ENDS>(P, P.items[idx], smem, gbase, grp, t64);
   }
 }

@@ -150,11 +150,44 @@ OggContainer::~OggContainer() {
   for (LogicalStream* s : streams) delete s;
 }
 
+// PageReader.AddPage (Ogg/PageReader.cs:58-102): hands a verified page to the logical stream of its serial
+// number.  `open` / `ignored` live for one scan.
+namespace {
+struct Demux {
+  std::map<uint32_t, LogicalStream*> open;   // serial -> stream still receiving pages
+  std::map<uint32_t, bool> ignored;
+};
+}  // namespace
+
+static void demux_page(OggContainer* c, Demux& dm, const OggPage& p, uint32_t serial, size_t plen) {
+  if (dm.ignored.count(serial) || p.packet_count == 0) {
+    // PageReader.AddPage refuses a page without packets; the serial is ignored from then on
+    if (p.packet_count == 0 && !dm.open.count(serial)) dm.ignored[serial] = true;
+    if (p.packet_count == 0 && dm.open.count(serial)) {
+      dm.open.erase(serial);
+      dm.ignored[serial] = true;
+    }
+    c->waste_bits += (int64_t)plen * 8;
+    return;
+  }
+  LogicalStream* ls;
+  auto it = dm.open.find(serial);
+  if (it == dm.open.end()) {
+    ls = new LogicalStream;
+    ls->serial = serial;
+    c->streams.push_back(ls);
+    dm.open[serial] = ls;
+  } else {
+    ls = it->second;
+  }
+  ls->pages.push_back(p);
+  if (p.flags & 4) dm.open.erase(serial);  // PageReader.cs:76-84: a later page with this serial starts a new stream
+}
+
 int OggContainer::scan(const uint8_t* d, size_t n) {
   data = d;
   len = n;
-  std::map<uint32_t, LogicalStream*> open;   // serial -> stream still receiving pages
-  std::map<uint32_t, bool> ignored;
+  Demux dm;
   size_t pos = 0;
   bool resync = false;
   while (pos + 4 <= len) {
@@ -186,30 +219,40 @@ int OggContainer::scan(const uint8_t* d, size_t n) {
     p.packet_count = cnt;
     resync = false;
     pos += plen;
-    if (ignored.count(serial) || p.packet_count == 0) {
-      // PageReader.AddPage refuses a page without packets; the serial is ignored from then on
-      if (p.packet_count == 0 && !open.count(serial)) ignored[serial] = true;
-      if (p.packet_count == 0 && open.count(serial)) {
-        open.erase(serial);
-        ignored[serial] = true;
-      }
-      waste_bits += (int64_t)plen * 8;
-      continue;
-    }
-    LogicalStream* ls;
-    auto it = open.find(serial);
-    if (it == open.end()) {
-      ls = new LogicalStream;
-      ls->serial = serial;
-      streams.push_back(ls);
-      open[serial] = ls;
-    } else {
-      ls = it->second;
-    }
-    ls->pages.push_back(p);
-    if (p.flags & 4) open.erase(serial);  // PageReader.cs:76-84: a later page with this serial starts a new stream
+    demux_page(this, dm, p, serial, plen);
   }
   if (pos < len) waste_bits += 8 * (int64_t)(len - pos);
+  return streams.empty() ? VPZ_E_INVALID_DATA : VPZ_OK;
+}
+
+// The same container state from the page records of the GPU scan (k0_pages.cuh): the device found the pages,
+// verified their CRCs and counted their packets; the host only files them under their serial numbers.
+int OggContainer::scan_from_records(const uint8_t* d, size_t n, const VpzPageRec* recs, uint32_t count,
+                                    uint64_t waste_bytes, uint32_t crc_fail) {
+  data = d;
+  len = n;
+  waste_bits = 8 * (int64_t)waste_bytes;
+  crc_failures = (int)crc_fail;
+  Demux dm;
+  for (uint32_t i = 0; i < count; i++) {
+    const VpzPageRec& r = recs[i];
+    const size_t plen = 27 + (size_t)r.nseg + r.body_len;
+    if ((size_t)r.offset + plen > n) return VPZ_E_INVALID_DATA;   // a record that does not fit its own file
+    const uint8_t* h = d + r.offset;
+    OggPage p;
+    p.offset = (int64_t)r.offset;
+    p.flags = r.flags;
+    p.granule = (int64_t)(((uint64_t)r.granule_hi << 32) | r.granule_lo);
+    p.seq = r.seq;
+    p.nseg = r.nseg;
+    p.seg = h + 27;
+    p.body = h + 27 + p.nseg;
+    p.body_len = (int)r.body_len;
+    p.is_resync = r.is_resync != 0;
+    p.is_continued = r.is_continued != 0;
+    p.packet_count = r.packet_count;
+    demux_page(this, dm, p, r.serial, plen);
+  }
   return streams.empty() ? VPZ_E_INVALID_DATA : VPZ_OK;
 }
 

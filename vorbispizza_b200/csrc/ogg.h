@@ -9,6 +9,8 @@
 #include <functional>
 #include <vector>
 
+#include "vpz_dev.h"
+
 namespace vpz {
 
 struct OggPage {
@@ -91,6 +93,9 @@ class OggContainer {
   std::vector<LogicalStream*> streams;  // in order of first page
   ~OggContainer();
   int scan(const uint8_t* d, size_t n);  // 0, or <0 when no page was found
+  // the same from the page records of the GPU scan (vpz_dev.h VpzPageRec, k0_pages.cuh)
+  int scan_from_records(const uint8_t* d, size_t n, const VpzPageRec* recs, uint32_t count, uint64_t waste_bytes,
+                        uint32_t crc_fail);
 };
 
 }  // namespace vpz

@@ -689,7 +689,20 @@ int vpz_reader_open_memory(vpz_ctx* ctx, const uint8_t* data, size_t len, int co
     r->own.assign(data, data + len);
     data = r->own.data();
   }
-  int rc = r->cont.scan(data, len);
+  // "gpu_scan" 2: the physical Ogg layer of single readers runs on the device too (the default keeps it on
+  // the host there: one image is one warp of work, not worth a launch and two copies)
+  int rc = VPZ_OK;
+  bool scanned = false;
+  if (ctx->gpu_scan >= 2) {
+    ScanResult sr;
+    rc = scan_pages(ctx, 1, &data, &len, nullptr, &sr);
+    if (rc == VPZ_OK && !sr.out[0].overflow) {
+      rc = r->cont.scan_from_records(data, len, sr.pages + sr.files[0].page_base, sr.out[0].n_pages,
+                                     ((uint64_t)sr.out[0].waste_hi << 32) | sr.out[0].waste_lo, sr.out[0].crc_failures);
+      scanned = true;
+    }
+  }
+  if (rc == VPZ_OK && !scanned) rc = r->cont.scan(data, len);
   if (rc == VPZ_OK) {
     rc = find_next(r);
     if (rc == 0) rc = VPZ_E_INVALID_DATA;
@@ -875,11 +888,22 @@ static int64_t decode_files_impl(vpz_ctx* ctx, uint32_t n, const uint8_t* const*
     std::vector<std::unique_ptr<BulkJob>>& jobs = held[slot];
     jobs.clear();
     jobs.resize(cnt);
-    // 1. page scan (CRC) -- parallel, no shared state
+    // 1. page scan: capture patterns, lacing sums and page CRCs on the device (K0, one warp per image), the
+    //    per-serial filing of the page records on the worker threads; "gpu_scan" 0 = all of it on the host
+    ScanResult sr;
+    if (ctx->gpu_scan) {
+      if ((rc = scan_pages(ctx, cnt, datas + first, lens + first, pool, &sr))) break;
+    }
     pool->parallel_for(cnt, [&](size_t i) {
       jobs[i].reset(new BulkJob);
       BulkJob& j = *jobs[i];
-      j.rc = j.cont.scan(datas[first + i], lens[first + i]);
+      if (ctx->gpu_scan && !sr.out[i].overflow) {
+        const VpzScanOut& o = sr.out[i];
+        j.rc = j.cont.scan_from_records(datas[first + i], lens[first + i], sr.pages + sr.files[i].page_base, o.n_pages,
+                                        ((uint64_t)o.waste_hi << 32) | o.waste_lo, o.crc_failures);
+      } else {
+        j.rc = j.cont.scan(datas[first + i], lens[first + i]);   // host scan (a file of unusually many tiny pages)
+      }
       if (!j.rc) j.rc = stream_prepare(&j.dec, j.cont.streams[0], &j.err);
     });
     t1 = now(); t_scan += t1 - t0; t0 = t1;

@@ -1,0 +1,147 @@
+// scan.cpp -- host side of K0 (k0_pages.cuh): stages container images, runs the page scan on the device and
+// brings the page records back.  The physical Ogg layer (capture-pattern search, header parse, lacing sums,
+// page CRC -- Ogg/PageReaderBase.cs:41-84,286-361, Ogg/Crc.cs:20-63) is the data-parallel part of container
+// parsing; the per-serial bookkeeping stays on the host (ogg.cpp, OggContainer::scan_from_records).
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+
+#include "../../include/vpz.h"
+#include "engine.h"
+
+namespace vpz {
+
+struct ScanBufs {
+  HostBuf<uint8_t> h_img;
+  HostBuf<VpzScanFile> h_files;
+  HostBuf<VpzPageRec> h_pages;
+  HostBuf<VpzScanOut> h_out;
+  DevBuf d_img, d_files, d_pages, d_out;
+  dev::Stream* stream = nullptr;
+  uint32_t* d_counter = nullptr;
+  ~ScanBufs() {
+    dev::stream_destroy(stream);
+    dev::free(d_counter);
+  }
+};
+
+void scan_bufs_destroy(ScanBufs* s) { delete s; }
+
+// Pages a file of `len` bytes may produce before the device gives up on it (the host then scans that file
+// itself): a page is at least 27 bytes; audio pages carry kilobytes.
+static uint32_t page_cap(size_t len) { return (uint32_t)std::min<size_t>(len / 64 + 16, 1u << 24); }
+
+// Scans n images.  On return res->files[i] / res->pages hold file i's records (res->out[i].overflow set when
+// the file has more pages than page_cap).  The buffers belong to the context and stay valid until the next call.
+int scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, ThreadPool* pool,
+               ScanResult* res) {
+  std::string& err = ctx->last_error;
+  if (!ctx->scan) {
+    ctx->scan = new (std::nothrow) ScanBufs;
+    if (!ctx->scan) return VPZ_E_NOMEM;
+    ctx->scan->stream = dev::stream_create();
+    ctx->scan->d_counter = static_cast<uint32_t*>(dev::alloc(64, err));
+    if (!ctx->scan->stream || !ctx->scan->d_counter) return VPZ_E_CUDA;
+  }
+  ScanBufs& b = *ctx->scan;
+  res->n = n;
+  res->files = nullptr;
+  res->pages = nullptr;
+  res->out = nullptr;
+  if (n == 0) return VPZ_OK;
+  if (!b.h_files.reserve(n) || !b.h_out.reserve(n)) return VPZ_E_NOMEM;
+  uint64_t bytes = 0, pages = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    if (lens[i] > 0xfffffff0ull) {
+      err = "container image larger than 4 GiB";
+      return VPZ_E_ARGUMENT;
+    }
+    VpzScanFile f;
+    f.data_off = bytes;
+    f.len = (uint32_t)lens[i];
+    f.page_base = (uint32_t)pages;
+    f.page_cap = page_cap(lens[i]);
+    f.pad = 0;
+    b.h_files.p[i] = f;
+    bytes += (lens[i] + 8 + 15) & ~(uint64_t)15;   // 16-byte aligned images, >= 8 readable bytes behind each
+    pages += f.page_cap;
+    if (pages > 0xfffffff0ull) {
+      err = "too many pages in one scan; split the call";
+      return VPZ_E_ARGUMENT;
+    }
+  }
+  b.h_files.n = b.h_out.n = n;
+  if (!b.h_img.reserve(bytes) || !b.h_pages.reserve(pages)) return VPZ_E_NOMEM;
+  auto stage = [&](size_t i) {
+    const VpzScanFile& f = b.h_files.p[i];
+    uint8_t* dst = b.h_img.p + f.data_off;
+    if (f.len) memcpy(dst, datas[i], f.len);
+    const uint64_t end = i + 1 < n ? b.h_files.p[i + 1].data_off : bytes;
+    memset(dst + f.len, 0, (size_t)(end - f.data_off - f.len));
+  };
+  if (pool)
+    pool->parallel_for(n, stage);
+  else
+    for (uint32_t i = 0; i < n; i++) stage(i);
+  if (!b.d_img.reserve(bytes, err) || !b.d_files.reserve(n * sizeof(VpzScanFile), err) ||
+      !b.d_pages.reserve(pages * sizeof(VpzPageRec), err) || !b.d_out.reserve(n * sizeof(VpzScanOut), err))
+    return VPZ_E_CUDA;
+  int rc;
+  if ((rc = dev::h2d(b.d_img.p, b.h_img.p, bytes, b.stream, err))) return rc;
+  if ((rc = dev::h2d(b.d_files.p, b.h_files.p, n * sizeof(VpzScanFile), b.stream, err))) return rc;
+  if ((rc = dev::fill(b.d_counter, 0, 4, b.stream, err))) return rc;
+  K0Params p;
+  p.images = static_cast<const uint8_t*>(b.d_img.p);
+  p.files = static_cast<const VpzScanFile*>(b.d_files.p);
+  p.pages = static_cast<VpzPageRec*>(b.d_pages.p);
+  p.out = static_cast<VpzScanOut*>(b.d_out.p);
+  p.n_files = n;
+  p.counter = b.d_counter;
+  if ((rc = dev::launch_k0(p, b.stream, err))) return rc;
+  ctx->kernel_launches++;
+  if ((rc = dev::d2h(b.h_out.p, b.d_out.p, n * sizeof(VpzScanOut), b.stream, err))) return rc;
+  // all records in one copy: the table is small (32 bytes per ~4 KB page) and one copy beats n small ones
+  if ((rc = dev::d2h(b.h_pages.p, b.d_pages.p, pages * sizeof(VpzPageRec), b.stream, err))) return rc;
+  if ((rc = dev::stream_sync(b.stream, err))) return rc;
+  res->files = b.h_files.p;
+  res->pages = b.h_pages.p;
+  res->out = b.h_out.p;
+  return VPZ_OK;
+}
+
+}  // namespace vpz
+
+using namespace vpz;
+
+extern "C" int64_t vpz_scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens,
+                                  vpz_page_info* pages, size_t pages_cap, uint32_t* first, uint32_t* count,
+                                  uint64_t* waste_bits, uint32_t* crc_failures) {
+  if (!ctx || (n && (!datas || !lens))) return VPZ_E_ARGUMENT;
+  VPZ_USE(ctx);
+  static_assert(sizeof(vpz_page_info) == sizeof(VpzPageRec), "vpz_page_info mirrors VpzPageRec");
+  ScanResult r;
+  int rc = scan_pages(ctx, n, datas, lens, nullptr, &r);
+  if (rc) return rc;
+  int64_t total = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const VpzScanOut& o = r.out[i];
+    if (o.overflow) {
+      ctx->last_error = "file has more pages than the device scan sized for";
+      return VPZ_E_UNSUPPORTED;
+    }
+    if (first) first[i] = (uint32_t)total;
+    if (count) count[i] = o.n_pages;
+    if (waste_bits) waste_bits[i] = 8 * (((uint64_t)o.waste_hi << 32) | o.waste_lo);
+    if (crc_failures) crc_failures[i] = o.crc_failures;
+    if (pages) {
+      if ((size_t)total + o.n_pages > pages_cap) {
+        ctx->last_error = "page array too small";
+        return VPZ_E_ARGUMENT;
+      }
+      memcpy(pages + total, r.pages + r.files[i].page_base, (size_t)o.n_pages * sizeof(VpzPageRec));
+    }
+    total += o.n_pages;
+  }
+  return total;
+}

@@ -76,6 +76,8 @@ void vpz_ctx_destroy(vpz_ctx* c) {
   for (int i = 0; i < 2; i++) dev::host_free(c->xstage[i]);
   delete c->pool;
   c->pool = nullptr;
+  scan_bufs_destroy(c->scan);
+  c->scan = nullptr;
   for (int i = 0; i < 8; i++) dev::event_destroy(c->marks[i]);
   while (!c->setups.empty()) {
     vpz_setup* s = c->setups.begin()->second;
@@ -127,6 +129,9 @@ int vpz_ctx_set(vpz_ctx* c, const char* key, int value) {
     // 2 also through the full symbol kernel (floor 0 / multi-submap walk); 0 = per-setup choice
     if (value < 0 || value > 2) return VPZ_E_ARGUMENT;
     c->force_general = value;
+  } else if (!strcmp(key, "gpu_scan")) {
+    if (value < 0 || value > 2) return VPZ_E_ARGUMENT;   // 2: single readers too (tests)
+    c->gpu_scan = value;
   } else if (!strcmp(key, "host_threads")) {
     if (value < 0 || value > 256 || c->pool) return VPZ_E_ARGUMENT;  // before the first bulk call
     c->host_threads = value;

@@ -176,3 +176,30 @@ struct VpzOlaItem {
 // No overlap state lives on the device between batches: the host re-submits the last valid
 // packet of a stream as the "pre" packet of its next batch (it is decoded again and only seeds
 // the carry), which is also exactly how SeekTo pre-roll works (StreamDecoder.cs:817-880).
+
+// ---- K0: physical Ogg page scan on the device (k0_pages.cuh) -----------------------------------------------
+struct VpzScanFile {
+  uint64_t data_off;        // of the container image in the staged byte buffer (>= 4 readable bytes follow it)
+  uint32_t len;
+  uint32_t page_base;       // first record of this file in the page array
+  uint32_t page_cap;        // records the file may use
+  uint32_t pad;
+};
+struct VpzPageRec {         // one valid page (PageReaderBase.VerifyPage passed), 32 bytes
+  uint32_t offset;          // of the page in its file image
+  uint32_t body_len;
+  uint32_t granule_lo, granule_hi;
+  uint32_t serial, seq;
+  uint8_t flags;            // 1 continuation, 2 BOS, 4 EOS
+  uint8_t nseg;
+  uint8_t is_resync;        // bytes were skipped in front of this page
+  uint8_t is_continued;     // the last lacing value is 255
+  uint16_t packet_count;    // PageHeader.GetPacketCount (Ogg/PageHeader.cs:35-59)
+  uint16_t pad;
+};
+struct VpzScanOut {
+  uint32_t n_pages, crc_failures;
+  uint32_t waste_lo, waste_hi;   // bytes that belong to no valid page
+  uint32_t overflow;             // 1: page_cap was too small, the records are incomplete
+  uint32_t pad[3];
+};
