@@ -519,7 +519,7 @@ def main():
     # experiments (tools/gpu_r2e.sh): page scan on the host / a fixed number of host worker threads
     if os.environ.get("VPZ_BENCH_GPU_SCAN"):
         ctx.set("gpu_scan", int(os.environ["VPZ_BENCH_GPU_SCAN"]))
-    if os.environ.get("VPZ_BENCH_HOST_THREADS"):
+    if os.environ.get("VPZ_BENCH_HOST_THREADS", "0") != "0":
         ctx.set("host_threads", int(os.environ["VPZ_BENCH_HOST_THREADS"]))
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if local_world > 1:

@@ -70,6 +70,29 @@ def test_decode_files(emu_ctx):
     cases.decode_files_parity(emu_ctx, ["1test", "1test"])
 
 
+def test_decode_files_ramped_groups(emu_lib_path):
+    """The bulk pipeline with several groups in flight: small first groups (1, 2, 4 of a group of 8), the
+    device page scan running one group ahead, three rotating batches; every copy of the file must come out
+    identical, and identical with the host page scan."""
+    import numpy as np
+    from vorbispizza_b200 import Context, decode_files
+    data = cases.load_file("1test")
+    outs = []
+    for gpu_scan in (1, 0):
+        ctx = Context(0, lib_path=emu_lib_path)
+        try:
+            ctx.set("bulk_group", 8)
+            ctx.set("gpu_scan", gpu_scan)
+            pcm, counts = decode_files(ctx, [data] * 13, clip=True)
+        finally:
+            ctx.close()
+        assert len(set(int(c) for c in counts)) == 1
+        per = pcm.reshape(13, -1)
+        assert all(np.array_equal(per[0].view(np.uint32), per[i].view(np.uint32)) for i in range(1, 13))
+        outs.append(per[0].copy())
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
+
+
 def test_excerpts_batch(emu_ctx):
     """BASELINE config 5 in small: random-access excerpts, every one like a fresh reader's SeekTo + read."""
     n = cases.excerpts_parity(emu_ctx, ["1test", "2test"], n_excerpts=6, nread=1500,

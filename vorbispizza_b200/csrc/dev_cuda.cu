@@ -156,8 +156,9 @@ void free(void* p) {
 }
 void* host_alloc(size_t bytes) {
   void* p = nullptr;
-  // portable: pinned for every device, whichever context's thread allocated it
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) {
+  // portable: pinned for every device, whichever context's thread allocated it; mapped: kernels may write
+  // into it under the same address (K0's page records)
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess) {
     cudaGetLastError();
     return nullptr;
   }

@@ -238,6 +238,9 @@ int batch_fetch_clip(vpz_batch* b);
 void batch_drop_slots(vpz_batch* b);   // releases the setup references the batch's slots hold
 // K0: physical Ogg page scan of n container images on the device (scan.cpp)
 int scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, ThreadPool* pool, ScanResult* res);
+// the same in two halves, two slots (0 / 1): begin stages, uploads and launches without waiting; end collects
+int scan_begin(vpz_ctx* ctx, int which, uint32_t n, const uint8_t* const* datas, const size_t* lens, ThreadPool* pool);
+int scan_end(vpz_ctx* ctx, int which, ScanResult* res);
 }  // namespace vpz
 
 // First statement of every extern "C" entry point that may touch the device: the CUDA current device

@@ -160,21 +160,20 @@ K0_DEV void k0_scan_file(const K0Params& P, uint32_t fi, const uint32_t* sm, int
       break;
     }
     if (lane == 0) {
-      VpzPageRec r;
-      r.offset = pos;
-      r.body_len = body;
-      r.granule_lo = k0_load_le32(img + pos + 6);
-      r.granule_hi = k0_load_le32(img + pos + 10);
-      r.serial = k0_load_le32(img + pos + 14);
-      r.seq = k0_load_le32(img + pos + 18);
-      r.flags = img[pos + 5];
-      r.nseg = (uint8_t)nseg;
-      r.is_resync = resync ? 1 : 0;
+      // the record leaves as two 16-byte stores (the array may be pinned host memory written over the link)
       const bool cont = nseg > 0 && last_seg == 255u;
-      r.is_continued = cont ? 1 : 0;
-      r.packet_count = (uint16_t)(npk + (cont ? 1u : 0u));
-      r.pad = 0;
-      out[n_pages] = r;
+      uint4 a, b;
+      a.x = pos;                                  // offset
+      a.y = body;                                 // body_len
+      a.z = k0_load_le32(img + pos + 6);          // granule_lo
+      a.w = k0_load_le32(img + pos + 10);         // granule_hi
+      b.x = k0_load_le32(img + pos + 14);         // serial
+      b.y = k0_load_le32(img + pos + 18);         // seq
+      b.z = (uint32_t)img[pos + 5] | (nseg << 8) | ((resync ? 1u : 0u) << 16) | ((cont ? 1u : 0u) << 24);
+      b.w = (npk + (cont ? 1u : 0u)) & 0xffffu;   // packet_count, pad
+      uint4* dst = reinterpret_cast<uint4*>(out + n_pages);
+      dst[0] = a;
+      dst[1] = b;
     }
     n_pages++;
     resync = false;
@@ -182,14 +181,16 @@ K0_DEV void k0_scan_file(const K0Params& P, uint32_t fi, const uint32_t* sm, int
   }
   if (!overflow && pos < len) waste += len - pos;
   if (lane == 0) {
-    VpzScanOut o;
-    o.n_pages = n_pages;
-    o.crc_failures = crc_fail;
-    o.waste_lo = (uint32_t)waste;
-    o.waste_hi = (uint32_t)(waste >> 32);
-    o.overflow = overflow;
-    o.pad[0] = o.pad[1] = o.pad[2] = 0;
-    P.out[fi] = o;
+    uint4 a, b;
+    a.x = n_pages;
+    a.y = crc_fail;
+    a.z = (uint32_t)waste;
+    a.w = (uint32_t)(waste >> 32);
+    b.x = overflow;
+    b.y = b.z = b.w = 0;
+    uint4* dst = reinterpret_cast<uint4*>(P.out + fi);
+    dst[0] = a;
+    dst[1] = b;
   }
 }
 

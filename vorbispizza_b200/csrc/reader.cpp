@@ -872,13 +872,38 @@ static int64_t decode_files_impl(vpz_ctx* ctx, uint32_t n, const uint8_t* const*
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t0 = now(), t1;
   const uint32_t G = (uint32_t)std::max(1, ctx->bulk_group);
+  // Group boundaries.  The first groups are small (G/8, G/4, G/2): nothing can be copied back before the first
+  // group has been scanned, planned and decoded, and the call is bound by the PCM copy, so a short head start
+  // is worth more than full-size batches there.
+  std::vector<uint32_t> bounds;
+  bounds.push_back(0);
+  // A group also closes when its images reach 128 MiB: a batch addresses its entry-index area (about 8x the
+  // compressed bytes) and its spectra (about 11 floats per compressed byte of typical music) with 32 bits, and
+  // three batches of that size stay far inside the device memory.
+  const uint64_t kGroupBytes = 128ull << 20;
+  for (uint32_t first = 0, g = 0; first < n; g++) {
+    uint32_t want = G;
+    if (dst && g < 3 && G >= 8) want = G >> (3 - g);
+    uint32_t cnt = 0;
+    uint64_t bytes = 0;
+    while (cnt < want && first + cnt < n && (cnt == 0 || bytes + lens[first + cnt] <= kGroupBytes))
+      bytes += lens[first + cnt++];
+    first += cnt;
+    bounds.push_back(first);
+  }
+  const uint32_t n_groups = (uint32_t)bounds.size() - 1;
   std::vector<std::unique_ptr<BulkJob>> held[3];  // jobs stay alive while their batch may still be in flight
   bool used[3] = {false, false, false};
   int64_t total = 0;
   int rc = VPZ_OK;
   uint32_t group = 0;
-  for (uint32_t first = 0; first < n && !rc; first += G, group++) {
-    const uint32_t cnt = std::min(G, n - first);
+  // K0 runs one group AHEAD on its own stream: while the workers plan group g, the images of group g+1 are
+  // already on their way to the device and through the page scan
+  if (ctx->gpu_scan && n_groups)
+    rc = scan_begin(ctx, 0, bounds[1], datas, lens, pool);
+  t1 = now(); t_scan += t1 - t0;
+  for (; group < n_groups && !rc; group++) {
+    const uint32_t first = bounds[group], cnt = bounds[group + 1] - first;
     const int slot = (int)(group % 3);
     t0 = now();
     if (dst && used[slot]) {
@@ -892,7 +917,11 @@ static int64_t decode_files_impl(vpz_ctx* ctx, uint32_t n, const uint8_t* const*
     //    per-serial filing of the page records on the worker threads; "gpu_scan" 0 = all of it on the host
     ScanResult sr;
     if (ctx->gpu_scan) {
-      if ((rc = scan_pages(ctx, cnt, datas + first, lens + first, pool, &sr))) break;
+      if (group + 1 < n_groups) {
+        const uint32_t nf = bounds[group + 1], nc = bounds[group + 2] - nf;
+        if ((rc = scan_begin(ctx, (int)((group + 1) & 1), nc, datas + nf, lens + nf, pool))) break;
+      }
+      if ((rc = scan_end(ctx, (int)(group & 1), &sr))) break;
     }
     pool->parallel_for(cnt, [&](size_t i) {
       jobs[i].reset(new BulkJob);

@@ -12,17 +12,34 @@
 
 namespace vpz {
 
-struct ScanBufs {
+struct ScanSlot {
   HostBuf<uint8_t> h_img;
   HostBuf<VpzScanFile> h_files;
+  // The kernel writes its records STRAIGHT into these pinned (mapped) host arrays: a page record is two
+  // 16-byte posted writes over the link.  No device->host copy is queued, so a scan never waits behind the
+  // bulk pipeline's PCM copies on the copy engine (measured: 8 ms per group when it did).
   HostBuf<VpzPageRec> h_pages;
   HostBuf<VpzScanOut> h_out;
-  DevBuf d_img, d_files, d_pages, d_out;
-  dev::Stream* stream = nullptr;
+  DevBuf d_img, d_files;
+  dev::Event* done = nullptr;
   uint32_t* d_counter = nullptr;
+  uint32_t n = 0;
+  bool in_flight = false;
+};
+
+struct ScanBufs {
+  ScanSlot slot[2];                  // two scans may be in flight: the bulk path scans group g+1 while it plans g
+  dev::Stream* stream = nullptr;
   ~ScanBufs() {
+    for (ScanSlot& s : slot) {
+      if (s.in_flight && s.done) {
+        std::string e;
+        dev::event_sync(s.done, e);
+      }
+      dev::event_destroy(s.done);
+      dev::free(s.d_counter);
+    }
     dev::stream_destroy(stream);
-    dev::free(d_counter);
   }
 };
 
@@ -32,23 +49,28 @@ void scan_bufs_destroy(ScanBufs* s) { delete s; }
 // itself): a page is at least 27 bytes; audio pages carry kilobytes.
 static uint32_t page_cap(size_t len) { return (uint32_t)std::min<size_t>(len / 64 + 16, 1u << 24); }
 
-// Scans n images.  On return res->files[i] / res->pages hold file i's records (res->out[i].overflow set when
-// the file has more pages than page_cap).  The buffers belong to the context and stay valid until the next call.
-int scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, ThreadPool* pool,
-               ScanResult* res) {
+// Starts the scan of n images in slot `which` (0 / 1): stages the images in pinned memory (on `pool`), uploads
+// them and launches K0 on the scan stream.  Returns without waiting; scan_end collects.
+int scan_begin(vpz_ctx* ctx, int which, uint32_t n, const uint8_t* const* datas, const size_t* lens, ThreadPool* pool) {
   std::string& err = ctx->last_error;
   if (!ctx->scan) {
     ctx->scan = new (std::nothrow) ScanBufs;
     if (!ctx->scan) return VPZ_E_NOMEM;
     ctx->scan->stream = dev::stream_create();
-    ctx->scan->d_counter = static_cast<uint32_t*>(dev::alloc(64, err));
-    if (!ctx->scan->stream || !ctx->scan->d_counter) return VPZ_E_CUDA;
+    if (!ctx->scan->stream) return VPZ_E_CUDA;
   }
-  ScanBufs& b = *ctx->scan;
-  res->n = n;
-  res->files = nullptr;
-  res->pages = nullptr;
-  res->out = nullptr;
+  ScanSlot& b = ctx->scan->slot[which & 1];
+  dev::Stream* stream = ctx->scan->stream;
+  if (b.in_flight) {   // a scan nobody collected (an error path): its buffers must be quiet before they are reused
+    dev::event_sync(b.done, err);
+    b.in_flight = false;
+  }
+  if (!b.done) {
+    b.done = dev::event_create();
+    b.d_counter = static_cast<uint32_t*>(dev::alloc(64, err));
+    if (!b.done || !b.d_counter) return VPZ_E_CUDA;
+  }
+  b.n = n;
   if (n == 0) return VPZ_OK;
   if (!b.h_files.reserve(n) || !b.h_out.reserve(n)) return VPZ_E_NOMEM;
   uint64_t bytes = 0, pages = 0;
@@ -84,30 +106,49 @@ int scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size
     pool->parallel_for(n, stage);
   else
     for (uint32_t i = 0; i < n; i++) stage(i);
-  if (!b.d_img.reserve(bytes, err) || !b.d_files.reserve(n * sizeof(VpzScanFile), err) ||
-      !b.d_pages.reserve(pages * sizeof(VpzPageRec), err) || !b.d_out.reserve(n * sizeof(VpzScanOut), err))
-    return VPZ_E_CUDA;
+  if (!b.d_img.reserve(bytes, err) || !b.d_files.reserve(n * sizeof(VpzScanFile), err)) return VPZ_E_CUDA;
   int rc;
-  if ((rc = dev::h2d(b.d_img.p, b.h_img.p, bytes, b.stream, err))) return rc;
-  if ((rc = dev::h2d(b.d_files.p, b.h_files.p, n * sizeof(VpzScanFile), b.stream, err))) return rc;
-  if ((rc = dev::fill(b.d_counter, 0, 4, b.stream, err))) return rc;
+  if ((rc = dev::h2d(b.d_img.p, b.h_img.p, bytes, stream, err))) return rc;
+  if ((rc = dev::h2d(b.d_files.p, b.h_files.p, n * sizeof(VpzScanFile), stream, err))) return rc;
+  if ((rc = dev::fill(b.d_counter, 0, 4, stream, err))) return rc;
   K0Params p;
   p.images = static_cast<const uint8_t*>(b.d_img.p);
   p.files = static_cast<const VpzScanFile*>(b.d_files.p);
-  p.pages = static_cast<VpzPageRec*>(b.d_pages.p);
-  p.out = static_cast<VpzScanOut*>(b.d_out.p);
+  p.pages = b.h_pages.p;   // pinned + mapped: device address == host address (unified addressing)
+  p.out = b.h_out.p;
   p.n_files = n;
   p.counter = b.d_counter;
-  if ((rc = dev::launch_k0(p, b.stream, err))) return rc;
+  if ((rc = dev::launch_k0(p, stream, err))) return rc;
   ctx->kernel_launches++;
-  if ((rc = dev::d2h(b.h_out.p, b.d_out.p, n * sizeof(VpzScanOut), b.stream, err))) return rc;
-  // all records in one copy: the table is small (32 bytes per ~4 KB page) and one copy beats n small ones
-  if ((rc = dev::d2h(b.h_pages.p, b.d_pages.p, pages * sizeof(VpzPageRec), b.stream, err))) return rc;
-  if ((rc = dev::stream_sync(b.stream, err))) return rc;
+  dev::event_record(b.done, stream);
+  b.in_flight = true;
+  return VPZ_OK;
+}
+
+// Waits for slot `which`.  On return res->files[i] / res->pages hold file i's records (res->out[i].overflow
+// set when the file has more pages than page_cap); they stay valid until the slot's next scan_begin.
+int scan_end(vpz_ctx* ctx, int which, ScanResult* res) {
+  ScanSlot& b = ctx->scan->slot[which & 1];
+  res->n = b.n;
+  res->files = nullptr;
+  res->pages = nullptr;
+  res->out = nullptr;
+  if (b.in_flight) {
+    b.in_flight = false;
+    int rc = dev::event_sync(b.done, ctx->last_error);
+    if (rc) return rc;
+  }
+  if (b.n == 0) return VPZ_OK;
   res->files = b.h_files.p;
   res->pages = b.h_pages.p;
   res->out = b.h_out.p;
   return VPZ_OK;
+}
+
+int scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size_t* lens, ThreadPool* pool,
+               ScanResult* res) {
+  int rc = scan_begin(ctx, 0, n, datas, lens, pool);
+  return rc ? rc : scan_end(ctx, 0, res);
 }
 
 }  // namespace vpz

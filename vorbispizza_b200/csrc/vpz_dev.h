@@ -185,7 +185,7 @@ struct VpzScanFile {
   uint32_t page_cap;        // records the file may use
   uint32_t pad;
 };
-struct VpzPageRec {         // one valid page (PageReaderBase.VerifyPage passed), 32 bytes
+struct alignas(16) VpzPageRec {   // one valid page (PageReaderBase.VerifyPage passed), 32 bytes
   uint32_t offset;          // of the page in its file image
   uint32_t body_len;
   uint32_t granule_lo, granule_hi;
@@ -197,7 +197,7 @@ struct VpzPageRec {         // one valid page (PageReaderBase.VerifyPage passed)
   uint16_t packet_count;    // PageHeader.GetPacketCount (Ogg/PageHeader.cs:35-59)
   uint16_t pad;
 };
-struct VpzScanOut {
+struct alignas(16) VpzScanOut {
   uint32_t n_pages, crc_failures;
   uint32_t waste_lo, waste_hi;   // bytes that belong to no valid page
   uint32_t overflow;             // 1: page_cap was too small, the records are incomplete
