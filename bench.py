@@ -241,15 +241,20 @@ def run_reference(args, rank, world):
     }))
 
 
-def config5_excerpts(rank):
+def config5_excerpts(rank, world=1, scaling="weak", n=16384):
     """The excerpt list of BASELINE config 5: rng(0x5EED0005 + rank), file uniform in {2test, 3test,
-    issue6test}, start uniform in [0, total - 4096); totals are the decodable sample counts of the files."""
+    issue6test}, start uniform in [0, total - 4096); totals are the decodable sample counts of the files.
+    weak: every rank draws its own n excerpts; strong ("16,384 excerpts across N GPUs"): rank 0's list is THE
+    list and rank r takes the contiguous slice stream_assignment gives it."""
     totals = [315790, 288094, 548160]
-    n, nread = 16384, 4096
-    rng = np.random.default_rng(0x5EED0005 + rank)
+    nread = 4096
+    rng = np.random.default_rng(0x5EED0005 + (rank if scaling == "weak" else 0))
     file_of = rng.integers(0, len(totals), n).astype(np.uint32)
     start = np.array([int(rng.integers(0, totals[f] - nread)) for f in file_of], np.int64)
     count = np.full(n, nread, np.int32)
+    if scaling == "strong":
+        first, cnt = stream_assignment(n, rank, world, "strong")
+        file_of, start, count = file_of[first:first + cnt].copy(), start[first:first + cnt].copy(), count[first:first + cnt].copy()
     return file_of, start, count, nread
 
 
@@ -373,7 +378,7 @@ def run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
     lib = ctx.lib
     files = load_files()[1:]
     chans = [1, 2, 2]
-    file_of, start, count, nread = config5_excerpts(rank)
+    file_of, start, count, nread = config5_excerpts(rank, world, args.scaling)
     n = int(file_of.size)
     keep = [np.frombuffer(f, np.uint8) for f in files]
     ptrs = (C.c_void_p * len(files))(*[k.ctypes.data for k in keep])
@@ -405,12 +410,14 @@ def run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
     v = delivered * args.steps / t
     line = {
         "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": min(args.warmup, 3),
-        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (seeded excerpts of TestFiles)",
-        "config": {"workload": "config5: %d random-access excerpts per GPU (SeekTo + %d samples per channel on "
-                               "{2,3,issue6}test.ogg), host Ogg images -> host PCM through vpz_decode_excerpts" % (n, nread),
+        "config": {"workload": "config5: %s (SeekTo + %d samples per channel on "
+                               "{2,3,issue6}test.ogg), host Ogg images -> host PCM through vpz_decode_excerpts" % (
+                                   "%d random-access excerpts per GPU" % n if args.scaling == "weak" else
+                                   "16384 random-access excerpts across %d GPU(s)" % world, nread),
                    "excerpts_per_gpu": n, "delivered_channel_samples_per_gpu": total_delivered,
-                   "excerpts_per_s": n * world * args.steps / t, "parallelism": "excerpt-sharded, no collective",
+                   "excerpts_per_s": sum_over_ranks(float(n)) * args.steps / t, "parallelism": "excerpt-sharded, no collective",
                    "note": "value counts the delivered samples only; every excerpt also decodes its pre-roll packet "
                            "and the unused parts of its first and last packets"},
         "clocks": clk, "gpu_launches": int(launches),

@@ -303,8 +303,10 @@ int64_t vpz_scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, co
  * dst (host): excerpt i starts at float offset dst_offsets[i] = sum over j < i of count[j] * channels
  * (fixed layout; returned in dst_offsets when non-NULL).  got[i] receives the samples per channel that
  * were delivered (fewer than count[i] at the end of the stream) or the negative vpz_status SeekTo
- * raised (VPZ_E_SEEK_RANGE, VPZ_E_PREROLL, ...).  clip: ClipSamples.  dst == NULL: only the layout is
- * computed.  Returns the total floats of the layout or a negative error. */
+ * raised (VPZ_E_SEEK_RANGE, VPZ_E_PREROLL, ...); the floats of an excerpt that were not delivered are set
+ * to zero.  clip: ClipSamples.  dst == NULL: only the layout is computed.  The samples are gathered on the
+ * device (K4) and arrive in dst by one copy per ~2,048 excerpts: pinned dst (vpz_host_alloc) is fastest.
+ * Returns the total floats of the layout or a negative error. */
 int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const* datas, const size_t* lens,
                             uint32_t n, const uint32_t* file_of, const int64_t* start, const int32_t* count,
                             int clip, float* dst, size_t dst_floats, int64_t* dst_offsets, int32_t* got);

@@ -303,6 +303,7 @@ def excerpts_parity(ctx, names, n_excerpts, nread=4096, seed=0x5EED0005, extra_p
             s.seek(int(start[i]))
         except ob.OracleError as e:
             assert got[i] == omap[e.code], "excerpt %d (%s @ %d): product %d oracle error %d" % (i, names[f], start[i], got[i], e.code)
+            assert not pcm[offsets[i]:offsets[i] + nread * ch].any(), "a failed excerpt reads as zeros"
             continue
         ref = []
         n = 0
@@ -314,6 +315,7 @@ def excerpts_parity(ctx, names, n_excerpts, nread=4096, seed=0x5EED0005, extra_p
             ref.append(buf[:no * ch].copy())
             n += no
         assert got[i] == n, "excerpt %d (%s @ %d): product %d samples, oracle %d" % (i, names[f], start[i], got[i], n)
+        assert not pcm[offsets[i] + n * ch:offsets[i] + nread * ch].any(), "samples past the end of the stream read as zeros"
         if n:
             a = pcm[offsets[i]:offsets[i] + n * ch]
             assert_pcm_close(a, np.concatenate(ref), "excerpt %d (%s @ %d)" % (i, names[f], start[i]))

@@ -9,6 +9,7 @@
 #include "../../include/vpz.h"
 #include "../../vorbispizza_b200/csrc/devapi.h"
 #include "../../vorbispizza_b200/csrc/k0_pages.cuh"
+#include "../../vorbispizza_b200/csrc/k4_deliver.cuh"
 #include "../../vorbispizza_b200/csrc/k1_symbols.cuh"
 #include "../../vorbispizza_b200/csrc/k3_streams.cuh"
 
@@ -115,6 +116,12 @@ int fill(void* d, int v, size_t n, Stream*, std::string&) {
 int launch_k0(const K0Params& p, Stream*, std::string&) {
   if (p.n_files == 0) return VPZ_OK;
   emu::launch(1, K0_THREADS, K0_SMEM_WORDS * 4, [&] { k0_cta(p, (uint32_t*)emu::t_block->smem); });
+  return VPZ_OK;
+}
+
+int launch_k4(const K4Params& p, Stream*, std::string&) {
+  if (p.n_segs == 0) return VPZ_OK;
+  emu::launch(2, 64, 0, [&] { k4_cta(p); });
   return VPZ_OK;
 }
 

@@ -484,7 +484,7 @@ def decode_excerpts(ctx, files, file_of, start, count, clip=True, dst=None):
     args = (ctx._h, nf, ptrs, lens, n, file_of.ctypes.data, start.ctypes.data, count.ctypes.data, int(bool(clip)))
     if dst is None:
         total = ctx.check(ctx.lib.vpz_decode_excerpts(*args, None, 0, offsets.ctypes.data, got.ctypes.data))
-        dst = np.zeros(total, np.float32)
+        dst = np.full(total, np.nan, np.float32)   # the call defines every float: short reads are zero-filled
     total = ctx.check(ctx.lib.vpz_decode_excerpts(*args, dst.ctypes.data, dst.size, offsets.ctypes.data, got.ctypes.data))
     return dst[:total], offsets, got
 

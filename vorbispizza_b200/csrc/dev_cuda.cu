@@ -10,12 +10,15 @@
 #include "k0_pages.cuh"
 #include "k1_symbols.cuh"
 #include "k3_streams.cuh"
+#include "k4_deliver.cuh"
 
 // ---- kernels ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(K0_THREADS) vpz_k0_pages(K0Params P) {
   __shared__ uint32_t k0_smem[K0_SMEM_WORDS];
   k0_cta(P, k0_smem);
 }
+
+__global__ void __launch_bounds__(K4_THREADS) vpz_k4_deliver(K4Params P) { k4_cta(P); }
 
 template <bool DEBUG, bool FULL>
 __global__ void __launch_bounds__(128, 8) vpz_k1a_symbols(K1Params P) {
@@ -248,6 +251,15 @@ int launch_k0(const K0Params& p, Stream* s, std::string& err) {
   vpz_k0_pages<<<grid, K0_THREADS, 0, s->s>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k0_pages", err);
+}
+
+int launch_k4(const K4Params& p, Stream* s, std::string& err) {
+  if (p.n_segs == 0) return VPZ_OK;
+  const unsigned warps = K4_THREADS / 32;
+  unsigned grid = (unsigned)std::min<size_t>(((size_t)p.n_segs + warps - 1) / warps, (size_t)8 * sm_count());
+  vpz_k4_deliver<<<grid, K4_THREADS, 0, s->s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k4_deliver", err);
 }
 
 int launch_k1a(const K1Params& p, bool debug, bool full, int blocks, Stream* s, std::string& err) {

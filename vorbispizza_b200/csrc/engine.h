@@ -63,6 +63,7 @@ class ThreadPool {
 }  // namespace vpz
 
 namespace vpz {
+struct ExcerptBufs;                  // below: buffers of the bulk random-access path (K4)
 struct ScanBufs;                     // scan.cpp: staging of the device page scan (K0)
 void scan_bufs_destroy(ScanBufs* s);
 struct ScanResult {                  // views into the context's scan buffers, valid until the next scan
@@ -97,8 +98,7 @@ struct vpz_ctx {
   struct vpz_batch* bulk[3] = {nullptr, nullptr, nullptr};
   vpz::dev::Event* bulk_done[3] = {nullptr, nullptr, nullptr};   // D2H of the batch's PCM finished
   vpz::dev::Event* bulk_ready[3] = {nullptr, nullptr, nullptr};  // kernels of the batch finished
-  float* xstage[2] = {nullptr, nullptr};     // vpz_decode_excerpts: pinned PCM staging of the two groups in flight
-  size_t xstage_cap[2] = {0, 0};             // (floats)
+  vpz::ExcerptBufs* xb = nullptr;            // vpz_decode_excerpts: copy segments and dense output of the two groups in flight
   int bulk_group = 256;                      // streams per pipeline group ("bulk_group" tunable)
   int host_threads = 0;                      // 0: hardware concurrency, capped at 32
 };
@@ -144,6 +144,19 @@ struct DevBuf {
     if (!p) return false;
     cap = nc;
     return true;
+  }
+};
+
+struct ExcerptBufs {
+  HostBuf<VpzCopySeg> h_segs[2];
+  DevBuf d_segs[2], d_out[2];
+  dev::Event* ready[2] = {nullptr, nullptr};   // kernels of the group finished
+  dev::Event* done[2] = {nullptr, nullptr};    // its output has reached the caller's buffer
+  ~ExcerptBufs() {
+    for (int i = 0; i < 2; i++) {
+      dev::event_destroy(ready[i]);
+      dev::event_destroy(done[i]);
+    }
   }
 };
 

@@ -53,3 +53,11 @@ struct K0Params {
   uint32_t n_files;
   uint32_t* counter;               // work-stealing cursor over files (zeroed before the launch)
 };
+
+struct K4Params {
+  const float* pcm;                // batch PCM (K3 output, unclipped)
+  float* out;                      // dense output of the group, zero-filled before the launch
+  const VpzCopySeg* segs;
+  uint32_t n_segs;
+  int clip;
+};

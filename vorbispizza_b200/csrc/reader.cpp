@@ -110,6 +110,9 @@ struct StreamDec {
   HostBuf<float> pcm;            // pinned PCM cache of the current window
   const float* pcm_view = nullptr;  // bulk random access: the window's PCM lives in the batch staging instead
   bool planned_only = false;     // bulk random access: the window was planned and decoded by the caller
+  // bulk random access: Read does not copy; it records WHICH floats it would copy (K4 moves them on the device)
+  std::vector<VpzCopySeg>* seg_sink = nullptr;
+  uint64_t seg_dst = 0;          // float offset of buffer[0] in the group's output
   vpz_batch* batch = nullptr;
   int lookahead = 256;
   std::vector<uint8_t> carry;    // last decoded packet: re-submitted as the seed of the next window
@@ -494,7 +497,7 @@ int stream_read(StreamDec* d, float* buffer, int nfloats, int samples_to_read, i
   if (d->fault) return d->fault;
   if (nfloats < 0 || nfloats % C != 0) return VPZ_E_ARGUMENT;
   if ((int64_t)nfloats < (int64_t)samples_to_read * C) return VPZ_E_ARGUMENT;
-  if (!buffer && nfloats) return VPZ_E_ARGUMENT;
+  if (!buffer && nfloats && !d->seg_sink) return VPZ_E_ARGUMENT;
   int idx = 0;
   while (idx == 0) {
     if (d->prev_avail == 0) {
@@ -532,7 +535,14 @@ int stream_read(StreamDec* d, float* buffer, int nfloats, int samples_to_read, i
     }
     const float* src = (d->pcm_view ? d->pcm_view : d->pcm.p) + d->pcm_cur;
     bool clipped = false;
-    if (interleave) {
+    if (d->seg_sink) {
+      VpzCopySeg sg;
+      sg.src = d->pcm_cur;
+      sg.dst = d->seg_dst + (uint64_t)idx * C;
+      sg.n = (uint32_t)copy_len * (uint32_t)C;
+      sg.pad = 0;
+      d->seg_sink->push_back(sg);
+    } else if (interleave) {
       float* dst = buffer + (size_t)idx * C;
       const size_t n = (size_t)copy_len * C;
       if (d->clip) {
@@ -1124,110 +1134,11 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
     ctx->last_error = "destination buffer too small";
     return VPZ_E_ARGUMENT;
   }
-  // ---- tasks: excerpts sorted by file, at most 128 per task -------------------------------------------
-  std::vector<ExcerptJob> jobs(n);
-  {
-    std::vector<uint32_t> order(n);
-    for (uint32_t i = 0; i < n; i++) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return file_of[a] < file_of[b]; });
-    for (uint32_t i = 0; i < n; i++) jobs[i].index = order[i];
-  }
-  std::vector<ExcerptTask> tasks;
-  for (size_t i = 0; i < n;) {
-    size_t j = i;
-    const uint32_t f = file_of[jobs[i].index];
-    while (j < n && j - i < 128 && file_of[jobs[j].index] == f) j++;
-    ExcerptTask t;
-    t.file = f;
-    t.first = i;
-    t.count = j - i;
-    tasks.push_back(std::move(t));
-    i = j;
-  }
-  for (ExcerptTask& t : tasks) {   // cursors and decoders of the tasks (serial: setup reference counts)
-    StreamDec& m = files[t.file]->master;
-    t.ls.reset(new LogicalStream(*m.ls));
-    t.dec.reset(new StreamDec);
-    StreamDec* d = t.dec.get();
-    d->ctx = ctx;
-    d->ls = t.ls.get();
-    d->setup = m.setup;
-    m.setup->refs++;
-    d->ls->granule_count = [d](const OggPacket& pk) { return d->granule_count(pk); };
-    d->clip = clip != 0;
-    d->planned_only = true;
-  }
-  tt1 = now(); t_tasks = tt1 - tt0; tt0 = tt1;
-  // ---- plan every excerpt (provider side of SeekTo + window plan) -------------------------------------
-  pool->parallel_for(tasks.size(), [&](size_t ti) {
-    ExcerptTask& t = tasks[ti];
-    StreamDec* d = t.dec.get();
-    for (size_t k = 0; k < t.count; k++) {
-      ExcerptJob& j = jobs[t.first + k];
-      const int64_t sp = start[j.index];
-      d->current_position = 0;   // a fresh reader (the stale position enters SeekTo's end-of-stream trim, quirk Q5)
-      d->has_clipped = false;
-      j.status = seek_begin(d, sp, &j.pos);
-      if (j.status) continue;
-      plan_window(d, 0, &j.win, (sp - j.pos) + (int64_t)count[j.index]);
-      d->seek_left = 0;
-      resolve_drain(d, &j.win);
-      std::string err;
-      int rc = plan_submit(d, &j.win, &err);
-      if (rc) j.status = rc;
-    }
-  });
-  tt1 = now(); t_plan = tt1 - tt0; tt0 = tt1;
-  // ---- groups of tasks through two batches -----------------------------------------------------------
-  const size_t tasks_per_group = 16;
-  float** staging = ctx->xstage;   // pinned, kept between calls
-  dev::Event* done[2] = {nullptr, nullptr};
-  int rc = VPZ_OK;
-  auto deliver = [&](size_t g, int slot) {
-    const size_t t0 = g * tasks_per_group, t1 = std::min(tasks.size(), t0 + tasks_per_group);
-    vpz_batch* b = ctx->bulk[slot];
-    pool->parallel_for(t1 - t0, [&](size_t k) {
-      ExcerptTask& t = tasks[t0 + k];
-      StreamDec* d = t.dec.get();
-      for (size_t q = 0; q < t.count; q++) {
-        ExcerptJob& j = jobs[t.first + q];
-        const uint32_t i = j.index;
-        if (j.status) {
-          if (got) got[i] = j.status;
-          continue;
-        }
-        int prc = place_window(d, b, &j.win, j.run, j.drain_run, 0);
-        if (prc) {
-          if (got) got[i] = prc;
-          continue;
-        }
-        // consumer side: SeekTo's two packets, then Read until `count` samples or the end
-        d->current_position = 0;
-        d->reset_decoder();
-        d->fault = 0;
-        d->has_position = true;
-        d->seek_left = 2;
-        d->seek_pos = j.pos;
-        d->q = std::move(j.win.entries);
-        d->qh = 0;
-        d->pcm_view = staging[slot];
-        int src = seek_finish(d, start[i], j.pos);
-        int have = 0;
-        const int C = d->channels();
-        float* out = dst + (dst_offsets ? dst_offsets[i] : 0);
-        if (!src) {
-          while (have < count[i]) {
-            int r = stream_read(d, out + (size_t)have * C, (count[i] - have) * C, count[i] - have, 0, true);
-            if (r <= 0) break;
-            have += r;
-          }
-        }
-        if (got) got[i] = src ? src : have;
-        j.win = Window();   // release the packet views / arena
-      }
-    });
-  };
-  // dst_offsets is needed by deliver: compute a private copy when the caller passed none
+  // ---- groups and tasks ---------------------------------------------------------------------------------
+  // A GROUP is a contiguous range of the caller's excerpts (so its samples are one contiguous range of dst:
+  // one device->host copy per group), up to 2,048 excerpts or 2^28 floats.  Inside a group the excerpts are
+  // sorted by file and cut into TASKS of at most 32: consecutive excerpts of one file, planned by one worker
+  // with its own packet cursor.
   std::vector<int64_t> own_offsets;
   if (!dst_offsets) {
     own_offsets.resize(n);
@@ -1238,19 +1149,124 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
     }
     dst_offsets = own_offsets.data();
   }
-  const size_t n_groups = (tasks.size() + tasks_per_group - 1) / tasks_per_group;
-  for (size_t g = 0; g < n_groups && !rc; g++) {
-    const int slot = (int)(g & 1);
+  struct Group {
+    uint32_t i0, i1;       // excerpts
+    size_t t0, t1;         // tasks
+    int64_t base, floats;  // range of dst
+  };
+  std::vector<Group> groups;
+  for (uint32_t i = 0; i < n;) {
+    Group g;
+    g.i0 = i;
+    g.base = dst_offsets[i];
+    int64_t fl = 0;
+    const uint32_t cap = groups.size() < 3 ? 256u << groups.size() : 2048u;   // short first groups: the GPU starts early
+    while (i < n && i - g.i0 < cap && (i == g.i0 || fl < ((int64_t)1 << 28))) {
+      fl += (int64_t)count[i] * files[file_of[i]]->master.channels();
+      i++;
+    }
+    g.i1 = i;
+    g.floats = fl;
+    g.t0 = g.t1 = 0;
+    groups.push_back(g);
+  }
+  std::vector<ExcerptJob> jobs(n);
+  std::vector<ExcerptTask> tasks;
+  {
+    std::vector<uint32_t> order(n);
+    for (uint32_t i = 0; i < n; i++) order[i] = i;
+    for (Group& g : groups) {
+      std::stable_sort(order.begin() + g.i0, order.begin() + g.i1, [&](uint32_t a, uint32_t b) { return file_of[a] < file_of[b]; });
+      g.t0 = tasks.size();
+      for (size_t i = g.i0; i < g.i1;) {
+        size_t j = i;
+        const uint32_t f = file_of[order[i]];
+        while (j < g.i1 && j - i < 32 && file_of[order[j]] == f) j++;
+        ExcerptTask t;
+        t.file = f;
+        t.first = i;
+        t.count = j - i;
+        tasks.push_back(std::move(t));
+        i = j;
+      }
+      g.t1 = tasks.size();
+    }
+    for (uint32_t i = 0; i < n; i++) jobs[i].index = order[i];
+  }
+  for (ExcerptTask& t : tasks) {   // decoders of the tasks (serial: setup reference counts)
+    StreamDec& m = files[t.file]->master;
+    t.dec.reset(new StreamDec);
+    StreamDec* d = t.dec.get();
+    d->ctx = ctx;
+    d->setup = m.setup;
+    m.setup->refs++;
+    d->clip = clip != 0;
+    d->planned_only = true;
+  }
+  tt1 = now(); t_tasks = tt1 - tt0; tt0 = tt1;
+  // Provider side of SeekTo + window plan of every excerpt of tasks [t0, t1): each task works on its own copy of
+  // the file's packet cursor (which inherits the file's page-end granule cache)
+  auto plan_tasks = [&](size_t t0, size_t t1) {
+    pool->parallel_for(t1 - t0, [&](size_t k) {
+      ExcerptTask& t = tasks[t0 + k];
+      StreamDec* d = t.dec.get();
+      t.ls.reset(new LogicalStream(*files[t.file]->master.ls));
+      d->ls = t.ls.get();
+      d->ls->granule_count = [d](const OggPacket& pk) { return d->granule_count(pk); };
+      for (size_t q = 0; q < t.count; q++) {
+        ExcerptJob& j = jobs[t.first + q];
+        const int64_t sp = start[j.index];
+        d->current_position = 0;   // a fresh reader (the stale position enters SeekTo's end-of-stream trim, quirk Q5)
+        d->has_clipped = false;
+        j.status = seek_begin(d, sp, &j.pos);
+        if (j.status) continue;
+        plan_window(d, 0, &j.win, (sp - j.pos) + (int64_t)count[j.index]);
+        d->seek_left = 0;
+        resolve_drain(d, &j.win);
+        std::string err;
+        int rc = plan_submit(d, &j.win, &err);
+        if (rc) j.status = rc;
+      }
+    });
+  };
+  // ---- the groups through two batches -------------------------------------------------------------------
+  // Per group: commit the windows to a batch; replay the consumer side of SeekTo / Read for every excerpt
+  // WITHOUT samples (it only depends on the packets' sample counts) to get got[] and the copy segments; then
+  // on the device H2D + K1a + K1b + K3 + K4 (segments -> the group's dense output) and one copy of that output
+  // into dst on the copy stream.  The host never touches a sample; while the GPU works on group g the host
+  // commits and replays group g + 1.
+  if (!ctx->xb) {
+    ctx->xb = new (std::nothrow) ExcerptBufs;
+    if (!ctx->xb) return VPZ_E_NOMEM;
+  }
+  ExcerptBufs& xb = *ctx->xb;
+  int rc = VPZ_OK;
+  bool used[2] = {false, false};
+  std::vector<std::vector<VpzCopySeg>> task_segs;
+  for (size_t gi = 0; gi < groups.size() && !rc; gi++) {
+    const Group& g = groups[gi];
+    const int slot = (int)(gi & 1);
+    tt0 = now();
     if (!ctx->bulk[slot]) {
       if ((rc = vpz_batch_create(ctx, &ctx->bulk[slot]))) break;
     }
-    if (!done[slot]) done[slot] = dev::event_create();
+    if (!xb.done[slot]) {
+      xb.done[slot] = dev::event_create();
+      xb.ready[slot] = dev::event_create();
+      if (!xb.done[slot] || !xb.ready[slot]) {
+        rc = VPZ_E_CUDA;
+        break;
+      }
+    }
+    if (used[slot] && (rc = dev::event_sync(xb.done[slot], ctx->last_error))) break;   // group gi - 2 has left the slot
+    tt1 = now(); t_wait += tt1 - tt0; tt0 = tt1;
     vpz_batch* b = ctx->bulk[slot];
     vpz_batch_reset(b);
-    const size_t t0 = g * tasks_per_group, t1 = std::min(tasks.size(), t0 + tasks_per_group);
+    plan_tasks(g.t0, g.t1);   // while the GPU still works on the previous group
+    tt1 = now(); t_plan += tt1 - tt0; tt0 = tt1;
     std::vector<RunPlan*> plans;
     std::vector<std::pair<ExcerptJob*, int>> owner;   // plan -> (job, 0 run / 1 drain run)
-    for (size_t ti = t0; ti < t1; ti++)
+    for (size_t ti = g.t0; ti < g.t1; ti++)
       for (size_t q = 0; q < tasks[ti].count; q++) {
         ExcerptJob& j = jobs[tasks[ti].first + q];
         if (j.status) continue;
@@ -1264,53 +1280,114 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
         }
       }
     int first = 0;
-    tt0 = now();
     if ((rc = batch_commit(b, plans.data(), plans.size(), pool, &first))) break;
-    tt1 = now(); t_commit += tt1 - tt0; tt0 = tt1;
     for (size_t k = 0; k < owner.size(); k++) (owner[k].second ? owner[k].first->drain_run : owner[k].first->run) = first + (int)k;
-    const size_t floats = (size_t)b->total_floats;
-    if (floats) {
-      if (floats > ctx->xstage_cap[slot]) {
-        dev::host_free(ctx->xstage[slot]);
-        ctx->xstage_cap[slot] = 0;
-        const size_t want = floats + floats / 4;
-        ctx->xstage[slot] = static_cast<float*>(dev::host_alloc(want * sizeof(float)));
-        if (!ctx->xstage[slot]) {
-          rc = VPZ_E_NOMEM;
-          break;
+    tt1 = now(); t_commit += tt1 - tt0; tt0 = tt1;
+    // consumer side, samples untouched: SeekTo's two packets, then Read until `count` samples or the end
+    task_segs.assign(g.t1 - g.t0, std::vector<VpzCopySeg>());
+    pool->parallel_for(g.t1 - g.t0, [&](size_t k) {
+      ExcerptTask& t = tasks[g.t0 + k];
+      StreamDec* d = t.dec.get();
+      std::vector<VpzCopySeg>& segs = task_segs[k];
+      segs.reserve(t.count * 8);
+      for (size_t q = 0; q < t.count; q++) {
+        ExcerptJob& j = jobs[t.first + q];
+        const uint32_t i = j.index;
+        if (j.status) {
+          if (got) got[i] = j.status;
+          continue;
         }
-        ctx->xstage_cap[slot] = want;
+        int prc = place_window(d, b, &j.win, j.run, j.drain_run, 0);
+        if (prc) {
+          if (got) got[i] = prc;
+          continue;
+        }
+        d->current_position = 0;
+        d->reset_decoder();
+        d->fault = 0;
+        d->has_position = true;
+        d->seek_left = 2;
+        d->seek_pos = j.pos;
+        d->q = std::move(j.win.entries);
+        d->qh = 0;
+        d->seg_sink = &segs;
+        const size_t mark = segs.size();
+        int src = seek_finish(d, start[i], j.pos);
+        int have = 0;
+        const int C = d->channels();
+        if (!src) {
+          while (have < count[i]) {
+            d->seg_dst = (uint64_t)(dst_offsets[i] - g.base) + (uint64_t)have * C;
+            int r = stream_read(d, nullptr, (count[i] - have) * C, count[i] - have, 0, true);
+            if (r <= 0) break;
+            have += r;
+          }
+        } else {
+          segs.resize(mark);
+        }
+        d->seg_sink = nullptr;
+        if (got) got[i] = src ? src : have;
+        j.win = Window();   // release the packet views / arena
       }
-      // the reader clips while it copies (per-sample HasClipped): decode unclipped
-      if ((rc = batch_decode(b, 0))) break;
-      if ((rc = dev::d2h(staging[slot], b->d_pcm.p, floats * 4, ctx->stream, ctx->last_error))) break;
+    });
+    size_t n_segs = 0;
+    for (const auto& v : task_segs) n_segs += v.size();
+    if (!xb.h_segs[slot].reserve(n_segs)) {
+      rc = VPZ_E_NOMEM;
+      break;
     }
-    dev::event_record(done[slot], ctx->stream);
-    tt1 = now(); t_launch += tt1 - tt0; tt0 = tt1;
-    if (g > 0) {   // deliver the previous group while this one is on the GPU
-      if ((rc = dev::event_sync(done[slot ^ 1], ctx->last_error))) break;
-      tt1 = now(); t_wait += tt1 - tt0; tt0 = tt1;
-      deliver(g - 1, slot ^ 1);
-      tt1 = now(); t_deliver += tt1 - tt0; tt0 = tt1;
+    {
+      size_t at = 0;
+      for (const auto& v : task_segs) {
+        if (!v.empty()) memcpy(xb.h_segs[slot].p + at, v.data(), v.size() * sizeof(VpzCopySeg));
+        at += v.size();
+      }
+      xb.h_segs[slot].n = n_segs;
     }
-  }
-  if (!rc && n_groups) {
-    const int slot = (int)((n_groups - 1) & 1);
-    tt0 = now();
-    rc = dev::event_sync(done[slot], ctx->last_error);
-    tt1 = now(); t_wait += tt1 - tt0; tt0 = tt1;
-    if (!rc) deliver(n_groups - 1, slot);
     tt1 = now(); t_deliver += tt1 - tt0; tt0 = tt1;
+    if (g.floats > 0) {
+      if (!xb.d_out[slot].reserve((size_t)g.floats * 4, ctx->last_error) ||
+          !xb.d_segs[slot].reserve(std::max<size_t>(n_segs, 1) * sizeof(VpzCopySeg), ctx->last_error)) {
+        rc = VPZ_E_CUDA;
+        break;
+      }
+      // the reader clips while it copies: K3 decodes unclipped, K4 clips what it hands out
+      if (b->total_floats && (rc = batch_decode(b, 0))) break;
+      // samples no packet delivers (short reads at the end of a stream, failed seeks) read as zero
+      if ((rc = dev::fill(xb.d_out[slot].p, 0, (size_t)g.floats * 4, ctx->stream, ctx->last_error))) break;
+      if (n_segs) {
+        if ((rc = dev::h2d(xb.d_segs[slot].p, xb.h_segs[slot].p, n_segs * sizeof(VpzCopySeg), ctx->stream, ctx->last_error))) break;
+        K4Params kp;
+        kp.pcm = static_cast<const float*>(b->d_pcm.p);
+        kp.out = static_cast<float*>(xb.d_out[slot].p);
+        kp.segs = static_cast<const VpzCopySeg*>(xb.d_segs[slot].p);
+        kp.n_segs = (uint32_t)n_segs;
+        kp.clip = clip ? 1 : 0;
+        if ((rc = dev::launch_k4(kp, ctx->stream, ctx->last_error))) break;
+        ctx->kernel_launches++;
+      }
+      dev::event_record(xb.ready[slot], ctx->stream);
+      dev::stream_wait_event(ctx->copy_stream, xb.ready[slot]);
+      if ((rc = dev::d2h(dst + g.base, xb.d_out[slot].p, (size_t)g.floats * 4, ctx->copy_stream, ctx->last_error))) break;
+    }
+    dev::event_record(xb.done[slot], ctx->copy_stream);
+    used[slot] = true;
+    tt1 = now(); t_launch += tt1 - tt0; tt0 = tt1;
   }
-  if (trace)
-    fprintf(stderr, "vpz_decode_excerpts: %u excerpts, %zu tasks, %zu groups: files %.1f tasks %.1f plan %.1f commit %.1f launch %.1f wait %.1f deliver %.1f ms\n",
-            n, tasks.size(), n_groups, t_files, t_tasks, t_plan, t_commit, t_launch, t_wait, t_deliver);
+  tt0 = now();
+  for (int s2 = 0; s2 < 2; s2++)
+    if (used[s2]) {
+      int r2 = dev::event_sync(xb.done[s2], ctx->last_error);
+      if (!rc) rc = r2;
+    }
   int r2 = dev::stream_sync(ctx->stream, ctx->last_error);
   if (!rc) rc = r2;
-  for (int s2 = 0; s2 < 2; s2++) {
-    if (done[s2]) dev::event_destroy(done[s2]);
+  t_wait += now() - tt0;
+  if (trace)
+    fprintf(stderr, "vpz_decode_excerpts: %u excerpts, %zu tasks, %zu groups: files %.1f tasks %.1f plan %.1f commit %.1f replay %.1f launch %.1f wait %.1f ms\n",
+            n, tasks.size(), groups.size(), t_files, t_tasks, t_plan, t_commit, t_deliver, t_launch, t_wait);
+  for (int s2 = 0; s2 < 2; s2++)
     if (ctx->bulk[s2]) vpz_batch_reset(ctx->bulk[s2]);
-  }
   return rc ? rc : total;
 }
 

@@ -73,7 +73,7 @@ void vpz_ctx_destroy(vpz_ctx* c) {
     dev::event_destroy(c->bulk_done[i]);
     dev::event_destroy(c->bulk_ready[i]);
   }
-  for (int i = 0; i < 2; i++) dev::host_free(c->xstage[i]);
+  delete c->xb;
   delete c->pool;
   c->pool = nullptr;
   scan_bufs_destroy(c->scan);

@@ -203,3 +203,11 @@ struct alignas(16) VpzScanOut {
   uint32_t overflow;             // 1: page_cap was too small, the records are incomplete
   uint32_t pad[3];
 };
+
+// ---- K4: delivery of random-access excerpts (k4_deliver.cuh) -------------------------------------------------
+struct VpzCopySeg {
+  uint64_t src;             // float offset in the batch PCM buffer
+  uint64_t dst;             // float offset in the group's output buffer (the caller's layout)
+  uint32_t n;               // floats
+  uint32_t pad;
+};
