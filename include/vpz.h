@@ -311,6 +311,13 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
                             uint32_t n, const uint32_t* file_of, const int64_t* start, const int32_t* count,
                             int clip, float* dst, size_t dst_floats, int64_t* dst_offsets, int32_t* got);
 
+/* Debug / tests: the page-end granule index SeekTo searches in (PacketProvider.FillPageEndGranuleCache,
+ * Ogg/PacketProvider.cs:203-307) of one container image's first logical stream: entry p = granules up to and
+ * including page p.  on_device 1: built by the GPU (page scan + one warp per file over its pages), VPZ_E_UNSUPPORTED
+ * when the file is not a clean single stream (those keep the host's packet walk); 0: the host's walk.  Returns the
+ * number of pages and writes min(pages, cap) entries. */
+int64_t vpz_debug_page_end_granules(vpz_ctx* ctx, const uint8_t* data, size_t len, int on_device, int64_t* out, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

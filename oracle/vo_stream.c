@@ -479,6 +479,17 @@ int64_t vo_total_samples(vo_stream* s) {
   return start;
 }
 
+/* Test access to the cache FillPageEndGranuleCache (Ogg/PacketProvider.cs:203-307) builds: fills it to the end
+ * of the stream (what GetGranuleCount does) and copies min(n, cap) entries; returns n or a negative error. */
+int vo_page_end_granules(vo_stream* s, int64_t* out, int cap) {
+  int64_t start, end;
+  int err = 0;
+  get_page_range(s, INT64_MAX, &start, &end, &err);
+  if (err) return err;
+  for (int i = 0; i < s->page_end_n && i < cap; i++) out[i] = s->page_end_granules[i];
+  return s->page_end_n;
+}
+
 /* StreamPageReader.FindPage (Ogg/StreamPageReader.cs:152-305): the three search
  * strategies all land on the first page whose header granule exceeds the target
  * (index+1 on a direct hit); restated as a forward scan over header granules. */

@@ -71,6 +71,8 @@ int vo_has_clipped(const vo_stream* s);
 int vo_is_end_of_stream(const vo_stream* s);
 int64_t vo_sample_position(const vo_stream* s);
 int64_t vo_total_samples(vo_stream* s);
+/* the page-end granule cache of PacketProvider (Ogg/PacketProvider.cs:203-307), filled to the end of the stream */
+int vo_page_end_granules(vo_stream* s, int64_t* out, int cap);
 /* interleaved read; nfloats must be a multiple of channels; returns samples per
  * channel (>=0) or a negative error */
 int vo_read(vo_stream* s, float* buf, int nfloats);

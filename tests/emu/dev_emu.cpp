@@ -119,6 +119,12 @@ int launch_k0(const K0Params& p, Stream*, std::string&) {
   return VPZ_OK;
 }
 
+int launch_k0g(const K0gParams& p, Stream*, std::string&) {
+  if (p.n_files == 0) return VPZ_OK;
+  emu::launch(1, 64, 0, [&] { k0g_cta(p); });
+  return VPZ_OK;
+}
+
 int launch_k4(const K4Params& p, Stream*, std::string&) {
   if (p.n_segs == 0) return VPZ_OK;
   emu::launch(2, 64, 0, [&] { k4_cta(p); });

@@ -70,6 +70,8 @@ def lib():
     for name in ("vo_container_bits", "vo_waste_bits", "vo_sample_position", "vo_total_samples"):
         getattr(L, name).restype = C.c_int64
         getattr(L, name).argtypes = [vp]
+    L.vo_page_end_granules.restype = C.c_int
+    L.vo_page_end_granules.argtypes = [vp, C.c_void_p, C.c_int]
     L.vo_vendor.restype = C.c_void_p
     L.vo_vendor.argtypes = [vp, C.POINTER(C.c_int)]
     L.vo_comment.restype = C.c_void_p
@@ -140,6 +142,14 @@ class OracleStream:
             self.close()
         except Exception:
             pass
+
+    def page_end_granules(self):
+        """PacketProvider's page-end granule cache, filled to the end of the stream (raises OracleError)."""
+        out = np.zeros(1 << 16, np.int64)
+        n = lib().vo_page_end_granules(self._h, out.ctypes.data, out.size)
+        if n < 0:
+            raise OracleError(n)
+        return out[:n].copy()
 
     # --- properties
     @property

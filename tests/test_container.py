@@ -284,3 +284,50 @@ def test_bulk_decode_same_with_host_and_device_scan(gpu_ctx):
     finally:
         host.close()
     assert (ca == cb).all() and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+# ---- K0g: the seek index on the GPU -------------------------------------------------
+def _granule_index_parity(ctx, named, what):
+    """Device-built page-end granule index == the oracle's PacketProvider cache == the product's host walk, for
+    every file that qualifies; files that do not (damaged / chained streams) must say so and keep the host walk,
+    which is compared with the oracle as well."""
+    from vorbispizza_b200 import VpzError
+    from vorbispizza_b200 import _native as N
+    from vorbispizza_b200.api import page_end_granules
+    on_device = 0
+    for name, data in named:
+        try:
+            ref = ob.OracleStream(data).page_end_granules()
+        except ob.OracleError:
+            continue   # no stream / a page list the reference refuses
+        host = page_end_granules(ctx, data, False)
+        assert np.array_equal(host, ref), (what, name, "host walk")
+        try:
+            dev = page_end_granules(ctx, data, True)
+        except VpzError as e:
+            assert e.code == N.VPZ_E_UNSUPPORTED, (what, name, e.code)
+            continue
+        assert np.array_equal(dev, ref), (what, name, "device index", dev[:8], ref[:8])
+        on_device += 1
+    return on_device
+
+
+def _index_cases(names, limit):
+    import synthvorbis
+    out = []
+    for name in names:
+        out.append((name, cases.load_file(name)))
+        for kind, data in damaged_streams(name, limit).items():
+            out.append(("%s/%s" % (name, kind), data))
+    return out
+
+
+def test_granule_index_emulated(emu_ctx):
+    n = _granule_index_parity(emu_ctx, _index_cases(["1test"], None) + _index_cases(["3test"], 60), "seek index")
+    assert n >= 6   # the intact files and the damaged ones whose PAGES are in order
+
+
+@pytest.mark.gpu
+def test_granule_index(gpu_ctx):
+    n = _granule_index_parity(gpu_ctx, _index_cases(["1test", "2test", "3test", "issue6test"], None), "seek index")
+    assert n >= 16

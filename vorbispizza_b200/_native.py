@@ -120,6 +120,7 @@ _SIGS = {
     "vpz_decode_files": (C.c_int64, [_P, C.c_uint32, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "vpz_decode_files_s16": (C.c_int64, [_P, C.c_uint32, _P, _P, C.c_int, _P, C.c_size_t, _P]),
     "vpz_decode_excerpts": (C.c_int64, [_P, C.c_uint32, _P, _P, C.c_uint32, _P, _P, _P, C.c_int, _P, C.c_size_t, _P, _P]),
+    "vpz_debug_page_end_granules": (C.c_int64, [_P, _P, C.c_size_t, C.c_int, _P, C.c_size_t]),
     "vpz_scan_pages": (C.c_int64, [_P, C.c_uint32, _P, _P, _P, C.c_size_t, _P, _P, _P, _P]),
 }
 

@@ -513,3 +513,14 @@ def scan_pages(ctx, datas):
                                               count.ctypes.data, waste.ctypes.data, crcf.ctypes.data))
     assert total == int(count.sum())
     return [(pages[int(first[i]):int(first[i]) + int(count[i])].copy(), int(waste[i]), int(crcf[i])) for i in range(n)]
+
+
+def page_end_granules(ctx, data, on_device):
+    """vpz_debug_page_end_granules: the seek index of a container image's first logical stream (entry p = granules
+    up to and including page p; PacketProvider.FillPageEndGranuleCache, Ogg/PacketProvider.cs:203-307), built on the
+    GPU (raises VpzError(VPZ_E_UNSUPPORTED) for files that keep the host path) or by the host's packet walk."""
+    buf = np.frombuffer(data, np.uint8)
+    cap = len(data) // 27 + 16
+    out = np.zeros(cap, np.int64)
+    n = ctx.check(ctx.lib.vpz_debug_page_end_granules(ctx._h, buf.ctypes.data, buf.size, 1 if on_device else 0, out.ctypes.data, cap))
+    return out[:n].copy()

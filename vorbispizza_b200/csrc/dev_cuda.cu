@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(K0_THREADS) vpz_k0_pages(K0Params P) {
   k0_cta(P, k0_smem);
 }
 
+__global__ void __launch_bounds__(K0_THREADS) vpz_k0g_granules(K0gParams P) { k0g_cta(P); }
+
 __global__ void __launch_bounds__(K4_THREADS) vpz_k4_deliver(K4Params P) { k4_cta(P); }
 
 template <bool DEBUG, bool FULL>
@@ -251,6 +253,15 @@ int launch_k0(const K0Params& p, Stream* s, std::string& err) {
   vpz_k0_pages<<<grid, K0_THREADS, 0, s->s>>>(p);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k0_pages", err);
+}
+
+int launch_k0g(const K0gParams& p, Stream* s, std::string& err) {
+  if (p.n_files == 0) return VPZ_OK;
+  const unsigned warps = K0_THREADS / 32;
+  unsigned grid = (unsigned)std::min<size_t>(((size_t)p.n_files + warps - 1) / warps, (size_t)8 * sm_count());
+  vpz_k0g_granules<<<grid, K0_THREADS, 0, s->s>>>(p);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k0g_granules", err);
 }
 
 int launch_k4(const K4Params& p, Stream* s, std::string& err) {

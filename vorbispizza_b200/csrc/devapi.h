@@ -63,6 +63,8 @@ int launch_k3(const K3Params& p, int ncb, size_t smem_bytes, Stream* s, std::str
 int launch_k3_streams(const K3Params& p, Stream* s, std::string& err);
 // K0: physical Ogg page scan, one warp per container image
 int launch_k0(const K0Params& p, Stream* s, std::string& err);
+// K0g: page-end granule index of scanned images, one warp per file
+int launch_k0g(const K0gParams& p, Stream* s, std::string& err);
 // K4: copy segments of decoded excerpts into the caller's layout, one warp per segment
 int launch_k4(const K4Params& p, Stream* s, std::string& err);
 size_t max_smem_per_block();             // of the calling thread's current device

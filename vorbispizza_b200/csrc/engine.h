@@ -254,6 +254,8 @@ int scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const* datas, const size
 // the same in two halves, two slots (0 / 1): begin stages, uploads and launches without waiting; end collects
 int scan_begin(vpz_ctx* ctx, int which, uint32_t n, const uint8_t* const* datas, const size_t* lens, ThreadPool* pool);
 int scan_end(vpz_ctx* ctx, int which, ScanResult* res);
+// K0g: page-end granule index of files of the slot's last scan (scan.cpp)
+int granule_index(vpz_ctx* ctx, int which, const VpzGranFile* gf, uint32_t n, const long long** out);
 }  // namespace vpz
 
 // First statement of every extern "C" entry point that may touch the device: the CUDA current device

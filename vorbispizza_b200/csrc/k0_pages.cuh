@@ -207,3 +207,104 @@ K0_DEV void k0_cta(const K0Params& P, uint32_t* sm) {
     __syncwarp();
   }
 }
+
+// =============================================================================================================
+// K0g: the seek index.  PacketProvider.SeekTo (Ogg/PacketProvider.cs:90-169) searches by the GRANULES EACH PAGE
+// COMPLETES, which the reference derives lazily by walking every packet of every page up to the target and asking
+// the decoder for its sample count (FillPageEndGranuleCache, Ogg/PacketProvider.cs:203-307, with
+// StreamDecoder.GetPacketGranuleCount, StreamDecoder.cs:882-913: mode number and window flags in the packet's
+// first bits).  Here the whole index of a file is built at once: ONE WARP PER FILE, a lane per page (lacing walk,
+// two bytes per packet), a warp prefix sum over the pages.  Only clean single-stream files come here (no resync,
+// consecutive sequence numbers, continuation flags that match; scan.cpp checks), so every packet is valid.
+// =============================================================================================================
+K0_DEV int k0g_packet_granules(const uint8_t* p, uint32_t len, const VpzGranFile& f) {
+  // the first 1 + mode_bits + 2 bits (<= 9); bits past the end of the packet read as 0 (VorbisPacket.cs:157-164)
+  const uint32_t w = (len > 0 ? (uint32_t)p[0] : 0u) | (len > 1 ? (uint32_t)p[1] << 8 : 0u);
+  if (w & 1u) return 0;                                   // not an audio packet (StreamDecoder.cs:889-893)
+  const uint32_t mode = (w >> 1) & ((1u << f.mode_bits) - 1u);
+  if (mode >= f.nmodes) return 0;
+  const bool lb = mode < 32 ? (f.mode_flags_lo >> mode) & 1u : (f.mode_flags_hi >> (mode - 32)) & 1u;
+  const int s0 = 1 << f.log2_size0, s1 = 1 << f.log2_size1;
+  if (!lb) return s0 / 2;
+  const bool prev = (w >> (1 + f.mode_bits)) & 1u, next = (w >> (2 + f.mode_bits)) & 1u;
+  const int left_start = prev ? 0 : (s1 - s0) / 4;        // Mode.GetPacketInfo, Mode.cs:41-66
+  const int right_start = next ? s1 / 2 : (s1 * 3 - s0) / 4;
+  return right_start - left_start;
+}
+
+K0_DEV void k0g_file(const K0gParams& P, uint32_t fi, int lane) {
+  const VpzGranFile f = P.files[fi];
+  const uint8_t* img = P.images + f.data_off;
+  const VpzPageRec* recs = P.pages + f.page_base;
+  long long* out = P.page_end + f.page_base;
+  long long carry = 0;
+  bool found = false;          // the first data page (first header granule > 0) has been seen
+  uint32_t first_data = 0;
+  for (uint32_t p0 = 0; p0 < f.n_pages; p0 += 32) {
+    const uint32_t p = p0 + (uint32_t)lane;
+    const bool in = p < f.n_pages;
+    uint4 a = uint4{0, 0, 0, 0}, b = uint4{0, 0, 0, 0};
+    if (in) {
+      a = reinterpret_cast<const uint4*>(recs + p)[0];     // offset, body_len, granule lo / hi
+      b = reinterpret_cast<const uint4*>(recs + p)[1];     // serial, seq, flags | nseg << 8 | resync << 16 | continued << 24, packet_count
+    }
+    const bool data_page = in && (int)a.w >= 0 && (a.z | a.w) != 0u;   // granule > 0 as a signed 64-bit number
+    const uint32_t m = __ballot_sync(0xffffffffu, data_page);
+    if (!found && m) {
+      found = true;
+      first_data = p0 + (uint32_t)__ffs((int)m) - 1u;
+    }
+    int length = 0;
+    if (in && found && p >= first_data) {
+      int first_real = 0;
+      if (p > 0) {
+        const uint4 pa = reinterpret_cast<const uint4*>(recs + p - 1)[0];
+        const uint4 pb = reinterpret_cast<const uint4*>(recs + p - 1)[1];
+        if ((pb.z >> 24) & 1u) {   // the previous page ends inside a packet, which this page (or a later one) completes
+          const uint32_t nsp = (pb.z >> 8) & 0xffu;
+          const uint8_t* seg = img + pa.x + 27;
+          uint32_t off = 0, start = 0;
+          for (uint32_t s = 0; s < nsp; s++) {
+            const uint32_t v = seg[s];
+            off += v;
+            if (v < 255u) start = off;
+          }
+          length += k0g_packet_granules(seg + nsp + start, pa.y - start, f);   // >= 255 bytes of it lie in that page
+          first_real = 1;
+        }
+      }
+      uint32_t k = (uint32_t)first_real;
+      if (p == first_data) k = 1;                             // PacketProvider.cs:266-270
+      const uint32_t cont = (b.z >> 24) & 1u;
+      const uint32_t p_count = (b.w & 0xffffu) - cont;
+      const uint32_t ns = (b.z >> 8) & 0xffu;
+      const uint8_t* seg = img + a.x + 27;
+      const uint8_t* body = seg + ns;
+      uint32_t acc = 0, pkt_start = 0, idx = 0;
+      for (uint32_t s = 0; s < ns; s++) {
+        const uint32_t v = seg[s];
+        acc += v;
+        if (v < 255u) {
+          if (idx >= k && idx < p_count) length += k0g_packet_granules(body + pkt_start, acc - pkt_start, f);
+          idx++;
+          pkt_start = acc;
+        }
+      }
+    }
+    int incl = length;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int n = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += n;
+    }
+    if (in) out[p] = carry + (long long)incl;
+    carry += (long long)__shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+K0_DEV void k0g_cta(const K0gParams& P) {
+  const int lane = (int)threadIdx.x & 31;
+  const uint32_t warps_per_cta = blockDim.x >> 5;
+  for (uint32_t fi = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); fi < P.n_files; fi += gridDim.x * warps_per_cta)
+    k0g_file(P, fi, lane);
+}

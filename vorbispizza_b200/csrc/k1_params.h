@@ -61,3 +61,11 @@ struct K4Params {
   uint32_t n_segs;
   int clip;
 };
+
+struct K0gParams {
+  const uint8_t* images;           // the staged images of the K0 scan
+  const VpzGranFile* files;
+  const VpzPageRec* pages;         // K0's records
+  long long* page_end;             // out: per page, granules up to and including it (same indexing as pages)
+  uint32_t n_files;
+};

@@ -1086,6 +1086,110 @@ struct ExcerptTask {           // consecutive excerpts of one file, handled by o
 };
 }  // namespace
 
+// A file may take the device seek index when it holds ONE logical stream whose pages are in perfect order: then
+// every packet FillPageEndGranuleCache (Ogg/PacketProvider.cs:203-307) walks is valid and K0g's page-parallel
+// walk (k0_pages.cuh) adds up the same numbers.  Anything else keeps the host's lazy cache (ogg.cpp).
+static bool clean_single_stream(const ExcerptFile& f, const VpzPageRec* r, uint32_t n) {
+  if (f.cont.streams.size() != 1 || n == 0 || f.cont.streams[0]->pages.size() != n) return false;
+  bool data = false;
+  int64_t last_granule = -1;
+  for (uint32_t i = 0; i < n; i++) {
+    if (r[i].is_resync || r[i].serial != r[0].serial) return false;
+    if (i > 0 && r[i].seq != r[i - 1].seq + 1) return false;
+    const bool continuation = (r[i].flags & 1) != 0;
+    if (continuation != (i > 0 && r[i - 1].is_continued)) return false;
+    if (continuation && r[i].is_continued && r[i].packet_count == 1) return false;   // a packet over three pages
+    if ((r[i].flags & 4) && i + 1 != n) return false;                                 // pages behind the end of the stream
+    const int64_t g = (int64_t)(((uint64_t)r[i].granule_hi << 32) | r[i].granule_lo);
+    if (g != -1) {
+      if (g < last_granule) return false;
+      last_granule = g;
+      data |= g > 0;
+    }
+  }
+  return data && !r[n - 1].is_continued;
+}
+
+// Opens the files of a random-access batch: page scan (K0, or the host with "gpu_scan" 0), headers and setup
+// tables, and the page-end granule index SeekTo searches in (K0g for clean files; files_on_device counts them).
+static int open_excerpt_files(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const* datas, const size_t* lens,
+                              std::vector<std::unique_ptr<ExcerptFile>>& files, uint32_t* files_on_device) {
+  ThreadPool* pool = ctx->pool;
+  ScanResult sr;
+  const bool dev_scan = ctx->gpu_scan != 0 && n_files > 0;
+  if (dev_scan) {
+    int rc = scan_begin(ctx, 0, n_files, datas, lens, pool);
+    if (!rc) rc = scan_end(ctx, 0, &sr);
+    if (rc) return rc;
+  }
+  pool->parallel_for(n_files, [&](size_t i) {
+    files[i].reset(new ExcerptFile);
+    ExcerptFile& f = *files[i];
+    if (dev_scan && !sr.out[i].overflow) {
+      const VpzScanOut& o = sr.out[i];
+      f.rc = f.cont.scan_from_records(datas[i], lens[i], sr.pages + sr.files[i].page_base, o.n_pages,
+                                      ((uint64_t)o.waste_hi << 32) | o.waste_lo, o.crc_failures);
+    } else {
+      f.rc = f.cont.scan(datas[i], lens[i]);
+    }
+    if (!f.rc) f.rc = stream_prepare(&f.master, f.cont.streams[0], &f.err);
+  });
+  for (uint32_t i = 0; i < n_files; i++) {
+    ExcerptFile& f = *files[i];
+    if (f.rc) {
+      ctx->last_error = f.err;
+      return f.rc;
+    }
+    int rc = stream_attach(&f.master, ctx);
+    if (rc) return rc;
+  }
+  uint32_t on_device = 0;
+  if (dev_scan) {
+    std::vector<VpzGranFile> gf;
+    std::vector<uint32_t> which;
+    for (uint32_t i = 0; i < n_files; i++) {
+      ExcerptFile& f = *files[i];
+      if (sr.out[i].overflow || !clean_single_stream(f, sr.pages + sr.files[i].page_base, sr.out[i].n_pages)) continue;
+      const Setup& st = f.master.setup->host;
+      if (st.modes.size() > 64) continue;
+      VpzGranFile g;
+      memset(&g, 0, sizeof(g));
+      g.data_off = sr.files[i].data_off;
+      g.page_base = sr.files[i].page_base;
+      g.n_pages = sr.out[i].n_pages;
+      for (size_t m = 0; m < st.modes.size(); m++)
+        if (st.modes[m].block_flag) (m < 32 ? g.mode_flags_lo : g.mode_flags_hi) |= 1u << (m & 31);
+      g.mode_bits = (uint8_t)st.mode_bits;
+      g.nmodes = (uint8_t)st.modes.size();
+      int l0 = 0, l1 = 0;
+      while ((1 << l0) < st.id.size0) l0++;
+      while ((1 << l1) < st.id.size1) l1++;
+      g.log2_size0 = (uint8_t)l0;
+      g.log2_size1 = (uint8_t)l1;
+      gf.push_back(g);
+      which.push_back(i);
+    }
+    const long long* idx = nullptr;
+    if (!gf.empty()) {
+      int rc = granule_index(ctx, 0, gf.data(), (uint32_t)gf.size(), &idx);
+      if (rc) return rc;
+    }
+    for (size_t k = 0; k < gf.size(); k++) {
+      LogicalStream* ls = files[which[k]]->master.ls;
+      if (!ls->get_page((int64_t)gf[k].n_pages - 1)) continue;   // the host refuses the page list: its own path reports it
+      ls->page_end_granules.assign(idx + gf[k].page_base, idx + gf[k].page_base + gf[k].n_pages);
+      on_device++;
+    }
+  }
+  for (uint32_t i = 0; i < n_files; i++) {
+    int err = 0;
+    files[i]->master.ls->total_granules(&err);   // host cache: walks every page once; the copies of the cursor inherit it
+    if (err) return err;
+  }
+  if (files_on_device) *files_on_device = on_device;
+  return VPZ_OK;
+}
+
 int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const* datas, const size_t* lens, uint32_t n,
                             const uint32_t* file_of, const int64_t* start, const int32_t* count, int clip, float* dst,
                             size_t dst_floats, int64_t* dst_offsets, int32_t* got) {
@@ -1101,25 +1205,11 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
   const bool trace = getenv("VPZ_TRACE") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   double t_files = 0, t_tasks = 0, t_plan = 0, t_commit = 0, t_launch = 0, t_wait = 0, t_deliver = 0, tt0 = now(), tt1;
-  // ---- files: page scan, headers, setup tables (once per file) ------------------------------------
+  // ---- files: page scan, headers, setup tables, seek index (once per file) ---------------------------
   std::vector<std::unique_ptr<ExcerptFile>> files(n_files);
-  pool->parallel_for(n_files, [&](size_t i) {
-    files[i].reset(new ExcerptFile);
-    ExcerptFile& f = *files[i];
-    f.rc = f.cont.scan(datas[i], lens[i]);
-    if (!f.rc) f.rc = stream_prepare(&f.master, f.cont.streams[0], &f.err);
-  });
-  for (uint32_t i = 0; i < n_files; i++) {
-    ExcerptFile& f = *files[i];
-    if (f.rc) {
-      ctx->last_error = f.err;
-      return f.rc;
-    }
-    int rc = stream_attach(&f.master, ctx);
+  {
+    int rc = open_excerpt_files(ctx, n_files, datas, lens, files, nullptr);
     if (rc) return rc;
-    int err = 0;
-    f.master.ls->total_granules(&err);   // loads every page and fills the seek cache the copies inherit
-    if (err) return err;
   }
   tt1 = now(); t_files = tt1 - tt0; tt0 = tt1;
   // ---- layout of the destination -------------------------------------------------------------------
@@ -1389,6 +1479,33 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
   for (int s2 = 0; s2 < 2; s2++)
     if (ctx->bulk[s2]) vpz_batch_reset(ctx->bulk[s2]);
   return rc ? rc : total;
+}
+
+// Debug / tests: the page-end granule index of one container image (first logical stream), built on the device
+// (K0 + K0g; VPZ_E_UNSUPPORTED when the file does not qualify) or by the host's packet walk.  Returns the number
+// of pages, writes min(pages, cap) entries.
+int64_t vpz_debug_page_end_granules(vpz_ctx* ctx, const uint8_t* data, size_t len, int on_device, int64_t* out, size_t cap) {
+  if (!ctx || !data) return VPZ_E_ARGUMENT;
+  VPZ_USE(ctx);
+  if (!ctx->pool) {
+    ctx->pool = new (std::nothrow) ThreadPool(ctx->host_threads > 0 ? (unsigned)ctx->host_threads
+                                                                    : std::max(1u, std::min(std::thread::hardware_concurrency(), 32u)));
+    if (!ctx->pool) return VPZ_E_NOMEM;
+  }
+  std::vector<std::unique_ptr<ExcerptFile>> files(1);
+  const int saved = ctx->gpu_scan;
+  ctx->gpu_scan = on_device ? 1 : 0;
+  uint32_t on_dev = 0;
+  int rc = open_excerpt_files(ctx, 1, &data, &len, files, &on_dev);
+  ctx->gpu_scan = saved;
+  if (rc) return rc;
+  if (on_device && !on_dev) {
+    ctx->last_error = "file does not qualify for the device seek index";
+    return VPZ_E_UNSUPPORTED;
+  }
+  const std::vector<int64_t>& v = files[0]->master.ls->page_end_granules;
+  for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
+  return (int64_t)v.size();
 }
 
 }  // extern "C"

@@ -21,6 +21,10 @@ struct ScanSlot {
   HostBuf<VpzPageRec> h_pages;
   HostBuf<VpzScanOut> h_out;
   DevBuf d_img, d_files;
+  // K0g (granule_index): per-file parameters in, the page-end granule index out (pinned + mapped like h_pages)
+  HostBuf<VpzGranFile> h_gfiles;
+  DevBuf d_gfiles;
+  HostBuf<long long> h_page_end;
   dev::Event* done = nullptr;
   uint32_t* d_counter = nullptr;
   uint32_t n = 0;
@@ -142,6 +146,35 @@ int scan_end(vpz_ctx* ctx, int which, ScanResult* res) {
   res->files = b.h_files.p;
   res->pages = b.h_pages.p;
   res->out = b.h_out.p;
+  return VPZ_OK;
+}
+
+// K0g on the images slot `which` still holds from its last scan: the page-end granule index of the n files described
+// by gf (page_base / data_off as in the scan's VpzScanFile records).  *out is indexed like the slot's page records and
+// stays valid until the slot's next scan_begin.  Waits for the kernel.
+int granule_index(vpz_ctx* ctx, int which, const VpzGranFile* gf, uint32_t n, const long long** out) {
+  std::string& err = ctx->last_error;
+  if (!ctx->scan) return VPZ_E_INVALID_OP;
+  ScanSlot& b = ctx->scan->slot[which & 1];
+  dev::Stream* stream = ctx->scan->stream;
+  *out = nullptr;
+  if (n == 0) return VPZ_OK;
+  if (b.in_flight || !b.h_pages.p) return VPZ_E_INVALID_OP;
+  if (!b.h_gfiles.reserve(n) || !b.h_page_end.reserve(b.h_pages.cap)) return VPZ_E_NOMEM;
+  memcpy(b.h_gfiles.p, gf, n * sizeof(VpzGranFile));
+  if (!b.d_gfiles.reserve(n * sizeof(VpzGranFile), err)) return VPZ_E_CUDA;
+  int rc;
+  if ((rc = dev::h2d(b.d_gfiles.p, b.h_gfiles.p, n * sizeof(VpzGranFile), stream, err))) return rc;
+  K0gParams p;
+  p.images = static_cast<const uint8_t*>(b.d_img.p);
+  p.files = static_cast<const VpzGranFile*>(b.d_gfiles.p);
+  p.pages = b.h_pages.p;          // pinned + mapped (the scan wrote them there)
+  p.page_end = b.h_page_end.p;
+  p.n_files = n;
+  if ((rc = dev::launch_k0g(p, stream, err))) return rc;
+  ctx->kernel_launches++;
+  if ((rc = dev::stream_sync(stream, err))) return rc;
+  *out = b.h_page_end.p;
   return VPZ_OK;
 }
 

@@ -204,6 +204,16 @@ struct alignas(16) VpzScanOut {
   uint32_t pad[3];
 };
 
+// ---- K0g: page-end granule index on the device (k0_pages.cuh) -------------------------------------------------
+struct VpzGranFile {        // one container image holding one clean logical stream
+  uint64_t data_off;        // of the image in the staged byte buffer (the K0 scan's)
+  uint32_t page_base;       // first page record / first index entry of the file
+  uint32_t n_pages;
+  uint32_t mode_flags_lo, mode_flags_hi;   // bit m: mode m is a long block (Mode.cs:30-37)
+  uint8_t mode_bits, log2_size0, log2_size1, nmodes;
+  uint32_t pad;
+};
+
 // ---- K4: delivery of random-access excerpts (k4_deliver.cuh) -------------------------------------------------
 struct VpzCopySeg {
   uint64_t src;             // float offset in the batch PCM buffer
