@@ -44,7 +44,7 @@ enum {
   VPZ_E_ARGUMENT = -2,      /* ArgumentException / ArgumentOutOfRangeException (StreamDecoder.cs:423-430,825,842) */
   VPZ_E_SEEK_RANGE = -3,    /* SeekOutOfRangeException (StreamDecoder.cs:861) */
   VPZ_E_PREROLL = -4,       /* PreRollPacketException (StreamDecoder.cs:874) */
-  VPZ_E_UNSUPPORTED = -5,   /* valid Vorbis the GPU path does not cover yet (floor 0, >8 channels, >1 submap) */
+  VPZ_E_UNSUPPORTED = -5,   /* valid Vorbis the GPU path does not cover (> 8 channels, block size < 256, > 64 floor posts) */
   VPZ_E_CUDA = -6,          /* CUDA runtime error; vpz_last_error() has the text */
   VPZ_E_NOMEM = -7,
   VPZ_E_DISPOSED = -8,      /* ObjectDisposedException (StreamDecoder.cs:401) */
