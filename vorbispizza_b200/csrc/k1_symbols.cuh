@@ -29,7 +29,15 @@
 // packet bytes are read once, one 128-byte line per lane at a time: keep them out of L1 (ld.global.cg) so
 // the lines stay available for the Huffman tables that every lane re-reads
 #define VPZ_LDSTREAM(p) __ldcg(p)
+// setup images are reached through a pointer table in global memory: tell the compiler that what they point to is
+// global memory too (LDG instead of generic loads with an address-space check)
+#ifndef VPZ_NO_ASSUME
+#define VPZ_ASSUME_GLOBAL(p) __builtin_assume(__isGlobal(p))
 #else
+#define VPZ_ASSUME_GLOBAL(p)
+#endif
+#else
+#define VPZ_ASSUME_GLOBAL(p)
 #define VPZ_DEV inline
 #define VPZ_DEVN inline
 #define VPZ_LDG(p) (*(p))
@@ -393,9 +401,10 @@ VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook*
 // K1a: one lane decodes one packet
 // =============================================================================================
 template <bool DEBUG, bool FULL>
-VPZ_DEVN void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
+VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   const VpzPktIn pk = P.pkts[pkt_idx];
   const uint32_t* blob = P.setups[pk.setup_slot];
+  VPZ_ASSUME_GLOBAL(blob);
   const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
   const int C = H->channels;
   const VpzBook* books = reinterpret_cast<const VpzBook*>(blob + H->books_off);
@@ -661,6 +670,7 @@ VPZ_DEV void k1b_build_packet_general(const K1Params& P, uint32_t pkt_idx, uint3
   const int lane = tid & 31, wid = tid >> 5;
   const VpzPktIn pk = P.pkts[pkt_idx];
   const uint32_t* blob = P.setups[pk.setup_slot];
+  VPZ_ASSUME_GLOBAL(blob);
   const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
   const int C = H->channels;
   const VpzBook* books = reinterpret_cast<const VpzBook*>(blob + H->books_off);
@@ -1198,6 +1208,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
   const int lane = tid;   // ONE WARP per packet: many packets in flight per SM hide the per-packet load latency
   const uint32_t pkt_idx = pk.idx;
   const uint32_t* blob = P.setups[pk.setup_slot];
+  VPZ_ASSUME_GLOBAL(blob);
   const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
   const int C = H->channels;
   const int half_max = 1 << (H->log2_size1 - 1);
