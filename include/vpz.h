@@ -66,7 +66,8 @@ void vpz_ctx_destroy(vpz_ctx* ctx);
 int vpz_device_count(void);
 /* Tunables (call before the first batch): key one of "l1_bits" (Huffman first-level table width,
  * default 9), "ola_chunk" (packets per IMDCT work item, default: 16..63 chosen per batch), "k1_warps" (warps per entropy
- * CTA, default 4), "bulk_group" (streams per pipeline group of vpz_decode_files, default 256),
+ * CTA, default 4), "bulk_group" (streams per pipeline group of vpz_decode_files, default 256), "bulk_group_mib" (a group also closes
+ * at this many MiB of container images, default 128, at most 384),
  * "host_threads" (host worker threads of the bulk path, default 0 = all cores up to 32), "gpu_scan" (bulk
  * path: Ogg page scan + CRC on the GPU, default 1), "force_general" (tests: route every packet through the
  * general kernels). */

@@ -93,6 +93,26 @@ def test_decode_files_ramped_groups(emu_lib_path):
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
 
 
+def test_decode_files_groups_close_by_bytes(emu_lib_path):
+    """A pipeline group closes when its container images reach the byte budget (long files: a music library does
+    not fit 256 files into the 32-bit offsets of one batch): same PCM whatever the grouping."""
+    import numpy as np
+    from vorbispizza_b200 import Context, decode_files
+    datas = [cases.load_file("1test"), cases.load_file("2test")[:60000], cases.load_file("1test")] * 2
+    outs = []
+    for budget in (0, 70000, 1):     # default (one group), two or three files per group, one file per group
+        ctx = Context(0, lib_path=emu_lib_path)
+        try:
+            ctx.set("bulk_group", 256)
+            ctx.set("bulk_group_bytes", budget)
+            pcm, counts = decode_files(ctx, datas, clip=True)
+        finally:
+            ctx.close()
+        outs.append((pcm.copy(), counts.copy()))
+    for pcm, counts in outs[1:]:
+        assert np.array_equal(counts, outs[0][1]) and np.array_equal(pcm.view(np.uint32), outs[0][0].view(np.uint32))
+
+
 def test_excerpts_batch(emu_ctx):
     """BASELINE config 5 in small: random-access excerpts, every one like a fresh reader's SeekTo + read."""
     n = cases.excerpts_parity(emu_ctx, ["1test", "2test"], n_excerpts=6, nread=1500,

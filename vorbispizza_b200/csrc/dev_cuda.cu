@@ -37,8 +37,11 @@ __global__ void __launch_bounds__(128, 8) vpz_k1a_symbols(K1Params P) {
 }
 
 // gather path: one warp per packet
+#ifndef K1B_MIN_CTAS
+#define K1B_MIN_CTAS 9
+#endif
 template <bool DEBUG>
-__global__ void __launch_bounds__(K1B_THREADS, 9) vpz_k1b_spectrum(K1Params P) {
+__global__ void __launch_bounds__(K1B_THREADS, K1B_MIN_CTAS) vpz_k1b_spectrum(K1Params P) {
   extern __shared__ uint32_t k1_smem[];
   k1b_gather_loop<DEBUG>(P, k1_smem);
 }

@@ -100,6 +100,8 @@ struct vpz_ctx {
   vpz::dev::Event* bulk_ready[3] = {nullptr, nullptr, nullptr};  // kernels of the batch finished
   vpz::ExcerptBufs* xb = nullptr;            // vpz_decode_excerpts: copy segments and dense output of the two groups in flight
   int bulk_group = 256;                      // streams per pipeline group ("bulk_group" tunable)
+  int bulk_group_mib = 128;                  // ... and at most this many MiB of container images ("bulk_group_mib")
+  int bulk_group_bytes = 0;                  // tests: the same limit in bytes (overrides bulk_group_mib when > 0)
   int host_threads = 0;                      // 0: hardware concurrency, capped at 32
 };
 

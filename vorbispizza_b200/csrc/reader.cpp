@@ -887,10 +887,11 @@ static int64_t decode_files_impl(vpz_ctx* ctx, uint32_t n, const uint8_t* const*
   // is worth more than full-size batches there.
   std::vector<uint32_t> bounds;
   bounds.push_back(0);
-  // A group also closes when its images reach 128 MiB: a batch addresses its entry-index area (about 8x the
-  // compressed bytes) and its spectra (about 11 floats per compressed byte of typical music) with 32 bits, and
-  // three batches of that size stay far inside the device memory.
-  const uint64_t kGroupBytes = 128ull << 20;
+  // A group also closes when its images reach "bulk_group_mib" (128 MiB): a batch addresses its entry-index area
+  // (about 8x the compressed bytes) and its spectra (about 11 floats per compressed byte of typical music) with
+  // 32 bits, and three batches of that size stay far inside the device memory.  One file alone may be larger
+  // (up to ~384 MiB, hours of audio, before batch_commit refuses it).
+  const uint64_t kGroupBytes = ctx->bulk_group_bytes > 0 ? (uint64_t)ctx->bulk_group_bytes : (uint64_t)ctx->bulk_group_mib << 20;
   for (uint32_t first = 0, g = 0; first < n; g++) {
     uint32_t want = G;
     if (dst && g < 3 && G >= 8) want = G >> (3 - g);

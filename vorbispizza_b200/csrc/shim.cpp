@@ -124,6 +124,14 @@ int vpz_ctx_set(vpz_ctx* c, const char* key, int value) {
   } else if (!strcmp(key, "bulk_group")) {
     if (value < 1 || value > (1 << 20)) return VPZ_E_ARGUMENT;
     c->bulk_group = value;
+  } else if (!strcmp(key, "bulk_group_mib")) {
+    // a batch addresses its entry-index area (~8x the compressed bytes) and its spectra (~11 floats per compressed
+    // byte) with 32 bits: 384 MiB of images is the most one group can hold
+    if (value < 1 || value > 384) return VPZ_E_ARGUMENT;
+    c->bulk_group_mib = value;
+  } else if (!strcmp(key, "bulk_group_bytes")) {
+    if (value < 0) return VPZ_E_ARGUMENT;
+    c->bulk_group_bytes = value;
   } else if (!strcmp(key, "force_general")) {
     // test knob: 1 routes every packet through the general spectrum kernel and the generic IMDCT kernel,
     // 2 also through the full symbol kernel (floor 0 / multi-submap walk); 0 = per-setup choice
