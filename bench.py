@@ -464,6 +464,7 @@ def main():
     ap.add_argument("--no-sub", action="store_true", help="skip the config3 / config5 sub-objects of the default line")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--l1-bits", type=int, default=0, help=argparse.SUPPRESS)  # tuning: first-level Huffman table width
+    ap.add_argument("--set", action="append", default=[], metavar="KEY=VALUE", help=argparse.SUPPRESS)  # any vpz_ctx_set tunable
     ap.add_argument("--lib", default=None, help=argparse.SUPPRESS)  # dry-run the script logic on the emulated test build
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -523,6 +524,9 @@ def main():
     lib = ctx.lib
     if args.l1_bits:
         ctx.set("l1_bits", args.l1_bits)
+    for kv in args.set:
+        k, v = kv.split("=")
+        ctx.set(k, int(v))
     # experiments (tools/gpu_r2e.sh): page scan on the host / a fixed number of host worker threads
     if os.environ.get("VPZ_BENCH_GPU_SCAN"):
         ctx.set("gpu_scan", int(os.environ["VPZ_BENCH_GPU_SCAN"]))

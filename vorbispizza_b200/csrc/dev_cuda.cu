@@ -22,8 +22,11 @@ __global__ void __launch_bounds__(K0_THREADS) vpz_k0g_granules(K0gParams P) { k0
 
 __global__ void __launch_bounds__(K4_THREADS) vpz_k4_deliver(K4Params P) { k4_cta(P); }
 
+#ifndef K1A_MIN_CTAS
+#define K1A_MIN_CTAS 8
+#endif
 template <bool DEBUG, bool FULL>
-__global__ void __launch_bounds__(128, 8) vpz_k1a_symbols(K1Params P) {
+__global__ void __launch_bounds__(128, K1A_MIN_CTAS) vpz_k1a_symbols(K1Params P) {
   const int lane = threadIdx.x & 31;
   for (;;) {
     uint32_t base = 0;
@@ -31,9 +34,15 @@ __global__ void __launch_bounds__(128, 8) vpz_k1a_symbols(K1Params P) {
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= P.n_pkts) break;
     const uint32_t i = base + lane;
-    if (i < P.n_pkts) k1a_decode_packet<DEBUG, FULL>(P, P.order ? P.order[i] : i);
+    if (i < P.n_pkts) k1a_decode_packet<DEBUG, FULL>(P, P.order ? P.order[i] : i, reinterpret_cast<uint4*>(k1a_sm) + 2 * threadIdx.x);
     __syncwarp();
   }
+}
+
+// the same walk with the first-level Huffman tables of the CTA's current (setup, block size) in shared memory
+__global__ void __launch_bounds__(K1A_SM_THREADS, 2) vpz_k1a_symbols_sm(K1Params P) {
+  __shared__ uint32_t s_ctl[2];
+  k1a_sm_loop(P, s_ctl);
 }
 
 // gather path: one warp per packet
@@ -85,6 +94,14 @@ static int g_sm_count[VPZ_MAX_DEVICES] = {0};
 static size_t g_max_smem[VPZ_MAX_DEVICES] = {0};
 static thread_local int t_device = -1;
 
+// lets a kernel use all of the opt-in shared memory: the dynamic part may be what its static part leaves
+template <typename F>
+static void allow_max_smem(F func, int optin) {
+  cudaFuncAttributes a;
+  if (cudaFuncGetAttributes(&a, func) != cudaSuccess) return;
+  cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)a.sharedSizeBytes);
+}
+
 static int fail(cudaError_t e, const char* what, std::string& err) {
   err = std::string(what) + ": " + cudaGetErrorString(e);
   return VPZ_E_CUDA;
@@ -132,16 +149,17 @@ int init(int device, int* resolved, std::string& err) {
   g_sm_count[device] = prop.multiProcessorCount;
   g_max_smem[device] = prop.sharedMemPerBlockOptin;
   const int optin = (int)prop.sharedMemPerBlockOptin;   // function attributes are per device
-  cudaFuncSetAttribute(vpz_k1b_spectrum<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k1b_spectrum<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k1b_general<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k1b_general<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k3_imdct_ola<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k3_imdct_ola<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k3_streams<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k3_streams<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k3_streams<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
-  cudaFuncSetAttribute(vpz_k3_streams<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, optin);
+  allow_max_smem(vpz_k1a_symbols_sm, optin);
+  allow_max_smem(vpz_k1b_spectrum<false>, optin);
+  allow_max_smem(vpz_k1b_spectrum<true>, optin);
+  allow_max_smem(vpz_k1b_general<false>, optin);
+  allow_max_smem(vpz_k1b_general<true>, optin);
+  allow_max_smem(vpz_k3_imdct_ola<false>, optin);
+  allow_max_smem(vpz_k3_imdct_ola<true>, optin);
+  allow_max_smem(vpz_k3_streams<false, false>, optin);
+  allow_max_smem(vpz_k3_streams<true, false>, optin);
+  allow_max_smem(vpz_k3_streams<false, true>, optin);
+  allow_max_smem(vpz_k3_streams<true, true>, optin);
   e = cudaGetLastError();
   if (e != cudaSuccess) return fail(e, "cudaFuncSetAttribute", err);
   return VPZ_OK;
@@ -278,10 +296,25 @@ int launch_k4(const K4Params& p, Stream* s, std::string& err) {
 
 int launch_k1a(const K1Params& p, bool debug, bool full, int blocks, Stream* s, std::string& err) {
   if (p.n_pkts == 0) return VPZ_OK;
+  if (!debug && !full && p.k1a_smem) {
+    const size_t smem = ((size_t)K1A_SM_WORDS + 128) * 4 + K1A_RING_BYTES(K1A_SM_THREADS);
+    const unsigned grid = (unsigned)std::min<size_t>(((size_t)p.n_pkts + K1A_SM_THREADS - 1) / K1A_SM_THREADS, (size_t)2 * sm_count());
+    vpz_k1a_symbols_sm<<<grid, K1A_SM_THREADS, smem, s->s>>>(p);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+      cudaFuncAttributes a;
+      cudaFuncGetAttributes(&a, vpz_k1a_symbols_sm);
+      char buf[256];
+      snprintf(buf, sizeof(buf), "launch vpz_k1a_symbols_sm (grid %u, smem %zu, max dynamic %d, static %zu, regs %d, max threads %d)",
+               grid, smem, a.maxDynamicSharedSizeBytes, a.sharedSizeBytes, a.numRegs, a.maxThreadsPerBlock);
+      return fail(e, buf, err);
+    }
+    return VPZ_OK;
+  }
   if (debug) {
-    if (full) vpz_k1a_symbols<true, true><<<blocks, 128, 0, s->s>>>(p); else vpz_k1a_symbols<true, false><<<blocks, 128, 0, s->s>>>(p);
+    if (full) vpz_k1a_symbols<true, true><<<blocks, 128, K1A_RING_BYTES(128), s->s>>>(p); else vpz_k1a_symbols<true, false><<<blocks, 128, K1A_RING_BYTES(128), s->s>>>(p);
   } else {
-    if (full) vpz_k1a_symbols<false, true><<<blocks, 128, 0, s->s>>>(p); else vpz_k1a_symbols<false, false><<<blocks, 128, 0, s->s>>>(p);
+    if (full) vpz_k1a_symbols<false, true><<<blocks, 128, K1A_RING_BYTES(128), s->s>>>(p); else vpz_k1a_symbols<false, false><<<blocks, 128, K1A_RING_BYTES(128), s->s>>>(p);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k1a_symbols", err);

@@ -377,8 +377,9 @@ int plan_run(vpz_setup* s, const PktSrc* pk, uint32_t n_pkts, const int32_t* tri
       }
       count = rs - g.left_start;
     }
-    // staged layout: 4-byte aligned start, at least 12 zero bytes after the end (K1a reads two words ahead)
-    const uint64_t end = (staged + len + 12 + 3) & ~(uint64_t)3;
+    // staged layout: 16-byte aligned start (K1a fetches the packet in 16-byte chunks), at least 12 zero bytes
+    // after the end (a peek reads up to two words ahead of the cursor)
+    const uint64_t end = (staged + len + 12 + 15) & ~(uint64_t)15;
     const int M = g.block_size / 2;
     VpzPktOla ola;
     memset(&ola, 0, sizeof(ola));
@@ -696,6 +697,7 @@ int batch_decode(vpz_batch* b, int clip, int out16) {
     p.rec = static_cast<uint32_t*>(b->d_rec.p);
     p.ent = static_cast<uint16_t*>(b->d_ent.p);
     p.dbg = b->dbg;
+    p.k1a_smem = ctx->k1a_smem;
     const bool debug = b->dbg.hdr != nullptr;
     const uint32_t* order = static_cast<const uint32_t*>(b->d_order.p);
     const uint32_t n0 = b->n_class[0], n1 = b->n_class[1], n2 = b->n_class[2];

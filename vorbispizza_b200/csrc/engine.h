@@ -85,6 +85,7 @@ struct vpz_ctx {
   int ola_chunk = 63;   // packets per K3 work item (+ the seed packet)
   bool ola_chunk_set = false;   // set by the user: do not adapt it to the batch size (pick_ola_chunk)
   int k1_warps = 4;
+  int k1a_smem = 0;        // K1a: 1 = first-level Huffman tables in shared memory (vpz_k1a_symbols_sm; measured slower, k_history.md)
   int force_general = 0;   // tests: 1 = every packet through the general K1b and the generic K3, 2 = also the full K1a
   int gpu_scan = 1;        // bulk path: page scan + CRC on the device (K0); 0 = on the host worker threads
   vpz::ScanBufs* scan = nullptr;

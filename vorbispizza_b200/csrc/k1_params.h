@@ -27,6 +27,7 @@ struct K1Params {
   uint16_t* ent;                 // VQ entry indices (K1a -> K1b), VpzPktIn.ent_off
   const uint32_t* order;         // K1a: packet indices sorted by byte length (neighbouring lanes get like work)
   int gather_ok;                 // K1b: every setup of the batch can take the gather path
+  int k1a_smem;                  // K1a: first-level Huffman tables in shared memory (simple, non-debug variant)
   K1Debug dbg;
 };
 

@@ -28,7 +28,11 @@
 #define VPZ_LDG(p) __ldg(p)
 // packet bytes are read once, one 128-byte line per lane at a time: keep them out of L1 (ld.global.cg) so
 // the lines stay available for the Huffman tables that every lane re-reads
+#ifdef VPZ_STREAM_CA
+#define VPZ_LDSTREAM(p) __ldca(p)
+#else
 #define VPZ_LDSTREAM(p) __ldcg(p)
+#endif
 // setup images are reached through a pointer table in global memory: tell the compiler that what they point to is
 // global memory too (LDG instead of generic loads with an address-space check)
 #ifndef VPZ_NO_ASSUME
@@ -75,25 +79,49 @@
 #define K1_MAX_UNITS 512      // vectors * partitions per packet (setup.cpp refuses more)
 #define K1B_THREADS 128       // K1b: threads (one CTA) per packet
 
+// Asynchronous 16-byte copies global -> shared (LDGSTS, L2 only): how K1a streams its packet bytes.
+#ifndef VPZ_EMU
+#define K1_CP16(dst, src) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#define K1_CP_WAIT() asm volatile("cp.async.wait_all;" ::: "memory")
+#else
+#define K1_CP16(dst, src) memcpy((dst), (src), 16)
+#define K1_CP_WAIT() ((void)0)
+#endif
+
+#define K1A_RING_BYTES(threads) ((size_t)(threads) * 32)   // two 16-byte slots per thread
+
 struct K1Bits {
-  uint32_t woff;   // word offset of the packet in the batch byte buffer (the base stays a kernel parameter)
+  uint32_t woff;   // word offset of the packet in the batch byte buffer (a multiple of 4: packets start on 16 bytes)
   int pos, nbits;
-  // register window over the packet: lo = w[wi], hi = w[wi + 1], nx = w[wi + 2] with wi = pos >> 5.
-  // A peek is one funnel shift; the word after next is requested when the cursor enters a new word,
-  // so its latency hides behind the ~8 codewords that fit in a word.  The packet is followed by at
-  // least 12 zero bytes (VpzPktIn), so w[wi + 2] is packet data or zero padding for every pos <= nbits.
+  // register window over the packet: lo = w[wi], hi = w[wi + 1], nx = w[wi + 2] with wi = pos >> 5; a peek is
+  // one funnel shift.  The words come from a per-thread RING of two 16-byte chunks in shared memory that
+  // cp.async fills one chunk AHEAD: when the window enters chunk c, chunk c + 1 is requested and lands while
+  // the ~28 codewords of chunk c are decoded.  (A plain load of w[wi + 2] at every word crossing looked like a
+  // prefetch in the source, but the compiler parked the result in a temporary and moved it into `nx` at the
+  // end of the same trip: 19 % of K1a's stall samples waited for that L2 round trip.)  The packet is followed
+  // by at least 12 zero bytes (VpzPktIn), so w[wi + 2] is packet data or zero padding for every pos <= nbits;
+  // chunk reads may run up to 32 bytes further (into the next packet or the buffer's slack), never used.
   uint32_t lo, hi, nx;
   int wi;
+  uint4* ring;     // this thread's two slots (32 consecutive bytes): word j of the packet sits at word j & 7
 };
 
-VPZ_DEV void k1_bits_init(K1Bits& b, const uint32_t* bytes, uint32_t woff, int byte_len) {
+VPZ_DEV uint32_t k1_ring_word(const K1Bits& b, int j) {   // word j of the packet; its chunk is resident
+  return reinterpret_cast<const uint32_t*>(b.ring)[j & 7];
+}
+
+VPZ_DEV void k1_bits_init(K1Bits& b, const uint32_t* bytes, uint32_t woff, int byte_len, uint4* ring) {
   b.woff = woff;
   b.pos = 0;
   b.nbits = byte_len * 8;
   b.wi = 0;
-  b.lo = VPZ_LDSTREAM(bytes + woff);
-  b.hi = VPZ_LDSTREAM(bytes + woff + 1);
-  b.nx = VPZ_LDSTREAM(bytes + woff + 2);
+  b.ring = ring;
+  K1_CP16(ring, bytes + woff);
+  K1_CP16(ring + 1, bytes + woff + 4);
+  K1_CP_WAIT();
+  b.lo = k1_ring_word(b, 0);
+  b.hi = k1_ring_word(b, 1);
+  b.nx = k1_ring_word(b, 2);
 }
 
 VPZ_DEV uint32_t k1_peek32(const K1Bits& b) { return __funnelshift_r(b.lo, b.hi, b.pos & 31); }
@@ -105,8 +133,17 @@ VPZ_DEV void k1_bits_seek(K1Bits& b, const uint32_t* bytes, int np) {
   if (ni != b.wi) {
     b.lo = b.hi;
     b.hi = b.nx;
-    b.nx = VPZ_LDSTREAM(bytes + b.woff + ni + 2);
     b.wi = ni;
+    const int j = ni + 2;
+    if ((j & 3) == 0) {
+      // the window enters a new chunk: it was requested four words ago; its predecessor's slot is free now
+      // (those words are in lo / hi or used up), so the chunk after it goes there
+      K1_CP_WAIT();
+      b.nx = k1_ring_word(b, j);
+      K1_CP16(b.ring + (((j >> 2) + 1) & 1), bytes + b.woff + j + 4);
+    } else {
+      b.nx = k1_ring_word(b, j);
+    }
   }
 }
 
@@ -124,32 +161,51 @@ VPZ_DEV uint32_t k1_read(K1Bits& b, const uint32_t* bytes, int n) {
 struct K1Book {
   uint32_t l1_off;   // word offset of the first-level table in the blob
   uint32_t l1_mask;
-  uint32_t meta;     // l1_bits | book index << 8 | (unit_tab only) entries per unit << 16
+  uint32_t meta;     // l1_bits | book index << 8 | shared-memory offset of the first-level table << 16 (K1A_SM_NONE: global)
 };
+
+// K1a shared-memory tables (vpz_k1a_symbols_sm): [K1A_SM_WORDS words of first-level tables][256 x uint16 offsets]
+#ifndef VPZ_EMU
+extern __shared__ uint32_t k1a_sm[];
+#define K1A_SM k1a_sm
+#else
+#define K1A_SM (reinterpret_cast<uint32_t*>(emu::t_block->smem))
+#endif
+// shared-memory word offset of a book's first-level table, K1A_SM_NONE when the lane is not on the staged setup
+// or the book is not staged
+template <bool SM>
+VPZ_DEV uint32_t k1a_soff(uint32_t sm_on, int book) {
+  if (!SM || !sm_on) return K1A_SM_NONE;
+  return (K1A_SM[K1A_SM_WORDS + (book >> 1)] >> ((book & 1) * 16)) & 0xffffu;
+}
 
 // dims (u16) and l1_bits (u8) share one 32-bit word at byte offset 24 of VpzBook
 VPZ_DEV int k1_book_dims(const VpzBook* bk) {
   return (int)(VPZ_LDG(reinterpret_cast<const uint32_t*>(bk) + 6) & 0xffffu);
 }
 
-VPZ_DEV K1Book k1_book(const uint32_t* blob, const VpzBook* books, int idx) {
+VPZ_DEV K1Book k1_book(const uint32_t* blob, const VpzBook* books, int idx, uint32_t soff = K1A_SM_NONE) {
   const VpzBook* bk = books + idx;
   K1Book r;
   r.l1_off = VPZ_LDG(&bk->l1_off);
   const uint32_t l1_bits = (VPZ_LDG(reinterpret_cast<const uint32_t*>(bk) + 6) >> 16) & 0xffu;
   r.l1_mask = (1u << l1_bits) - 1u;
-  r.meta = l1_bits | ((uint32_t)idx << 8);
+  r.meta = l1_bits | ((uint32_t)idx << 8) | (soff << 16);
   return r;
 }
 
 // Codebook.DecodeScalar (Codebook.cs:301-335).  -1: no bits left or no code matches.
-template <bool DEBUG>
+template <bool DEBUG, bool SM = false>
 VPZ_DEV int k1_decode(K1Bits& b, const K1Book& bk, const uint32_t* blob, const K1Params& P, int& nscal) {
   int sym = -1;
   if (b.pos < b.nbits) {
     uint32_t x = k1_peek32(b);
     const uint32_t* l1 = blob + bk.l1_off;
-    uint32_t e = VPZ_LDG(l1 + (x & bk.l1_mask));
+    // first level from shared memory when the book's table is staged there: a warp's 32 lookups go to 32
+    // unrelated entries, and from L1 the warp waits for its slowest lane (any miss = an L2 round trip)
+    uint32_t e;
+    if (SM && (bk.meta >> 16) != K1A_SM_NONE) e = K1A_SM[(bk.meta >> 16) + (x & bk.l1_mask)];
+    else e = VPZ_LDG(l1 + (x & bk.l1_mask));
     if (e & 0x80000000u) {  // longer than the first-level table: second-level table over the next bits
       const uint32_t l2b = e & 31u;
       e = VPZ_LDG(l1 + ((e >> 5) & 0x3ffffffu) + ((x >> (bk.meta & 0xffu)) & ((1u << l2b) - 1u)));
@@ -231,18 +287,24 @@ struct K1aOut {
 };
 VPZ_DEV void k1a_emit(const K1Params& P, K1aOut& o, int sym) {
   // four entry indices per 8-byte store: a lane's store is its own L1 tag lookup, and the entry
-  // stream is the bulk of K1a's memory requests
-  const int q = (int)(o.ent_pos & 3u) * 16;
-  if (q < 32) o.ent_lo |= (uint32_t)sym << q; else o.ent_hi |= (uint32_t)sym << (q - 32);
+  // stream is the bulk of K1a's memory requests.  The indices are shifted in from the top of a 64-bit window
+  // (two instructions, no branch); after four of them the window is exactly the four in order.
+  o.ent_lo = __funnelshift_r(o.ent_lo, o.ent_hi, 16);
+  o.ent_hi = (o.ent_hi >> 16) | ((uint32_t)sym << 16);
   o.ent_pos++;
-  if (q == 48) {
-    *reinterpret_cast<uint2*>(P.ent + (o.ent_pos - 4)) = uint2{o.ent_lo, o.ent_hi};
-    o.ent_lo = o.ent_hi = 0;
+  if ((o.ent_pos & 3u) == 0u) *reinterpret_cast<uint2*>(P.ent + (o.ent_pos - 4)) = uint2{o.ent_lo, o.ent_hi};
+}
+// the 1..3 indices behind the last full store: bring them down to the bottom of the window (zeros above)
+VPZ_DEV void k1a_emit_flush(const K1Params& P, uint32_t ent_pos, uint32_t ent_lo, uint32_t ent_hi) {
+  const uint32_t k = ent_pos & 3u;
+  if (k) {
+    const unsigned long long w = (((unsigned long long)ent_hi << 32) | ent_lo) >> (16u * (4u - k));
+    *reinterpret_cast<uint2*>(P.ent + (ent_pos & ~3u)) = uint2{(uint32_t)w, (uint32_t)(w >> 32)};
   }
 }
-template <bool DEBUG>
+template <bool DEBUG, bool SM>
 VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook* books, K1Bits& b, const VpzResidue* rs,
-                         int C, uint32_t noexec, int half, uint8_t* rec_cls, K1aOut& o) {
+                         int C, uint32_t noexec, int half, uint8_t* rec_cls, K1aOut& o, uint32_t sm_on) {
   const K1ResGeom g = k1_res_geom(rs, C, half, noexec);
   int& status = o.status;
   int& nscal = o.nscal;
@@ -261,7 +323,7 @@ VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook*
     uint32_t smask[8 * (K1_MAX_UNITS / 32)];         // [stage][chunk of 32 units]; row 0 unused
     // class per unit in decode order: written to the record for K1b and read back from there (plain
     // loads: the lane reads its own stores)
-    const K1Book cb = k1_book(blob, books, rs->class_book);
+    const K1Book cb = k1_book(blob, books, rs->class_book, k1a_soff<SM>(sm_on, rs->class_book));
     const int cdim = rs->cdim, nvec = g.nvec, part_count = g.part_count;
     const int partvals = (int)rs->partvals;
     const int max_stages = rs->max_stages;
@@ -325,7 +387,7 @@ VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook*
               const uint2 t = VPZ_LDG(reinterpret_cast<const uint2*>(blob + unit_tab_off) + (rec_cls[u] * 8 + stage));
               cur.l1_off = t.x;
               cur.l1_mask = (1u << (t.y & 0xffu)) - 1u;
-              cur.meta = t.y;
+              cur.meta = (t.y & 0xffffu) | (k1a_soff<SM>(sm_on, (int)((t.y >> 8) & 0xffu)) << 16);
               rem = (int)(t.y >> 16);
               break;
             }
@@ -351,7 +413,7 @@ VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook*
             ubase = chunk * 32;
           }
           if (done || !in_class) break;
-          const int sym = k1_decode<DEBUG>(b, cb, blob, P, nscal);
+          const int sym = k1_decode<DEBUG, SM>(b, cb, blob, P, nscal);
           // quirk Q8 accepts idx < partvals*dim; beyond partvals the reference indexes past
           // _decodeMap and throws, so both ends are treated as "stop decoding this packet"
           if (sym < 0 || sym >= partvals) {
@@ -385,7 +447,7 @@ VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook*
       }
       trip++;
       if (rem > 0) {
-        const int sym = k1_decode<DEBUG>(b, cur, blob, P, nscal);
+        const int sym = k1_decode<DEBUG, SM>(b, cur, blob, P, nscal);
         if (sym < 0) {  // Residue0.cs:195-201: keep what was decoded
           status = 1;
           break;
@@ -400,8 +462,10 @@ VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook*
 // =============================================================================================
 // K1a: one lane decodes one packet
 // =============================================================================================
-template <bool DEBUG, bool FULL>
-VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
+// staged_key: (setup slot * 2 + long block flag) whose tables the CTA holds in shared memory (SM variant only)
+// ring: this thread's two 16-byte slots for the packet bytes (K1Bits)
+template <bool DEBUG, bool FULL, bool SM = false>
+VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx, uint4* ring, uint32_t staged_key = 0xffffffffu) {
   const VpzPktIn pk = P.pkts[pkt_idx];
   const uint32_t* blob = P.setups[pk.setup_slot];
   VPZ_ASSUME_GLOBAL(blob);
@@ -412,7 +476,7 @@ VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   uint32_t* rec = P.rec + pk.rec_off;
 
   K1Bits b;
-  k1_bits_init(b, P.bytes, pk.byte_off >> 2, (int)pk.byte_len);
+  k1_bits_init(b, P.bytes, pk.byte_off >> 2, (int)pk.byte_len, ring);
   int nscal = 0, ncls = 0;
 
   // StreamDecoder.DecodeNextPacket (StreamDecoder.cs:728-741): the host only queues packets whose
@@ -424,6 +488,7 @@ VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   const VpzMapping* mp = reinterpret_cast<const VpzMapping*>(blob + H->mappings_off) + modes[mode_idx].mapping;
   if (long_block) k1_read(b, P.bytes, 2);  // prev/next window flags (Mode.cs:38), geometry is the host's job
   const int half = long_block ? half_max : (1 << (H->log2_size0 - 1));
+  const uint32_t sm_on = SM && (pk.setup_slot * 2u + (uint32_t)long_block) == staged_key ? 1u : 0u;
 
   // ---- floor unpack + unwrap, channel by channel (Mapping.cs:106-116, Floor1.cs:162-219, 270-353) ----
   uint32_t own_mask = 0;  // bit ch: floor has energy (FloorData.ExecuteChannel)
@@ -489,14 +554,20 @@ VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
       po[1] = (short)k1_read(b, P.bytes, ybits);
       count = written = 2;
       const int nparts = fl->partitions;
+      // book of a codeword: one 8-byte load from the floor's book table (VpzFloor1.fbook_tab_off)
+      const uint2* ftab = reinterpret_cast<const uint2*>(blob + fl->fbook_tab_off);
       for (int i = 0; i < nparts && count > 0; i++) {
         const int c = fl->part_class[i];
         const int cdim = fl->class_dim[c], cbits = fl->class_sub[c];
         const uint32_t csub = (1u << cbits) - 1u;
         uint32_t cval = 0;
         if (cbits > 0) {
-          K1Book mb = k1_book(blob, books, fl->class_master[c]);
-          int v = k1_decode<DEBUG>(b, mb, blob, P, nscal);
+          const uint2 t = VPZ_LDG(ftab + c * 9);
+          K1Book mb;
+          mb.l1_off = t.x;
+          mb.l1_mask = (1u << (t.y & 0xffu)) - 1u;
+          mb.meta = (t.y & 0xffffu) | (k1a_soff<SM>(sm_on, (int)((t.y >> 8) & 0xffu)) << 16);
+          int v = k1_decode<DEBUG, SM>(b, mb, blob, P, nscal);
           if (v < 0) {
             count = 0;
             break;
@@ -504,12 +575,15 @@ VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
           cval = (uint32_t)v;
         }
         for (int j = 0; j < cdim; j++) {
-          const int book_idx = fl->sub_books[c][cval & csub];
+          const uint2 t = VPZ_LDG(ftab + c * 9 + 1 + (int)(cval & csub));
           cval >>= cbits;
           int post = 0;
-          if (book_idx >= 0) {
-            K1Book sb = k1_book(blob, books, book_idx);
-            post = k1_decode<DEBUG>(b, sb, blob, P, nscal);
+          if (t.y != 0u) {
+            K1Book sb;
+            sb.l1_off = t.x;
+            sb.l1_mask = (1u << (t.y & 0xffu)) - 1u;
+            sb.meta = (t.y & 0xffffu) | (k1a_soff<SM>(sm_on, (int)((t.y >> 8) & 0xffu)) << 16);
+            post = k1_decode<DEBUG, SM>(b, sb, blob, P, nscal);
             if (post < 0) {
               count = 0;
               break;
@@ -598,7 +672,7 @@ VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   uint8_t* rec_cls = reinterpret_cast<uint8_t*>(P.rec + pk.rec_off + K1_REC_HDR + C * K1_SEG_WORDS);
   const VpzResidue* residues = reinterpret_cast<const VpzResidue*>(blob + H->residues_off);
   if (!FULL || mp->submaps == 1) {
-    k1a_residue<DEBUG>(P, blob, books, b, residues + mp->submap_residue[0], C, noexec, half, rec_cls, o);
+    k1a_residue<DEBUG, SM>(P, blob, books, b, residues + mp->submap_residue[0], C, noexec, half, rec_cls, o, sm_on);
   } else {
     // where a submap's entry indices end is only known here: a residue that stops early (no matching
     // code, quirk Q8) does not stop the submaps after it, which read on from the same bit position.  The
@@ -624,7 +698,7 @@ VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
       if (nch > 0) {   // Residue0.Decode with no channels reads nothing
         const VpzResidue* rs = residues + mp->submap_residue[sm];
         const K1ResGeom g = k1_res_geom(rs, nch, half, flags);
-        k1a_residue<DEBUG>(P, blob, books, b, rs, nch, flags, half, rec_cls, o);
+        k1a_residue<DEBUG, SM>(P, blob, books, b, rs, nch, flags, half, rec_cls, o, sm_on);
         rec_cls += ((g.part_count * g.nvec + 3) >> 2) << 2;
       }
       sub_end[sm] = o.ent_pos - pk.ent_off;
@@ -637,7 +711,7 @@ VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
   nscal = o.nscal;
   ncls = o.ncls;
   rec[0] = own_mask | (noexec << 8) | ((uint32_t)status << 16) | ((uint32_t)long_block << 24);
-  if (ent_pos & 3u) *reinterpret_cast<uint2*>(P.ent + (ent_pos & ~3u)) = uint2{ent_lo, ent_hi};
+  k1a_emit_flush(P, ent_pos, ent_lo, ent_hi);
   rec[1] = ent_pos - pk.ent_off;
   rec[2] = (uint32_t)b.pos;
   rec[3] = (uint32_t)modes[mode_idx].mapping | ((uint32_t)mp->submap_residue[0] << 8) | (floor_ents << 16);
@@ -651,6 +725,59 @@ VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx) {
     h[DUMP_NOEXEC] = (int)noexec;
     h[DUMP_SCALARS_N] = nscal;
     h[DUMP_CLASSES_N] = ncls;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1a with the first-level Huffman tables in SHARED memory (vpz_k1a_symbols_sm; the north-star's "shared-memory
+// lookahead table").  A CTA of K1A_SM_THREADS threads takes K1A_SM_THREADS consecutive packets of the grouped
+// order at a time; the tables of the (setup, block size) the range starts with are staged once (VpzSetupHdr.
+// k1a_stage_off, <= 64 KB) and stay until a range starts with another group.  Lanes whose packet belongs to
+// another group (the few at a group boundary) keep the global-memory path.
+// ---------------------------------------------------------------------------------------------
+#define K1A_SM_THREADS 512
+VPZ_DEV void k1a_sm_loop(const K1Params& P, uint32_t* s_ctl) {
+  const uint32_t tid = threadIdx.x;
+  uint32_t staged = 0xffffffffu;   // the same in every thread of the CTA
+  for (;;) {
+    __syncthreads();               // every warp has left the previous range: its tables may go
+    if (tid == 0) {
+      const uint32_t base = atomicAdd(P.counter, (uint32_t)K1A_SM_THREADS);
+      uint32_t key = 0xffffffffu;
+      if (base < P.n_pkts) {
+        const VpzPktIn pk = P.pkts[P.order ? P.order[base] : base];
+        const uint32_t* blob = P.setups[pk.setup_slot];
+        const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
+        // bit 0 of an audio packet is its type, the mode number follows (StreamDecoder.cs:728-741)
+        const uint32_t mode = (P.bytes[pk.byte_off >> 2] >> 1) & ((1u << H->mode_bits) - 1u);
+        const VpzMode* modes = reinterpret_cast<const VpzMode*>(blob + H->modes_off);
+        key = pk.setup_slot * 2u + ((mode < H->nmodes && modes[mode].block_flag) ? 1u : 0u);
+      }
+      s_ctl[0] = base;
+      s_ctl[1] = key;
+    }
+    __syncthreads();
+    const uint32_t base = s_ctl[0];
+    if (base >= P.n_pkts) break;
+    const uint32_t key = s_ctl[1];
+    if (key != staged) {
+      const uint32_t* blob = P.setups[key >> 1];
+      const VpzSetupHdr* H = reinterpret_cast<const VpzSetupHdr*>(blob);
+      const uint32_t* plan = blob + H->k1a_stage_off[key & 1u];
+      const uint32_t n = VPZ_LDG(plan);
+      for (uint32_t i = 0; i < n; i++) {
+        const uint32_t* src = blob + VPZ_LDG(plan + 2 + 3 * i);
+        const uint32_t words = VPZ_LDG(plan + 3 + 3 * i);
+        uint32_t* dst = K1A_SM + VPZ_LDG(plan + 4 + 3 * i);
+        for (uint32_t w = tid; w < words; w += K1A_SM_THREADS) dst[w] = VPZ_LDG(src + w);
+      }
+      if (tid < 128) K1A_SM[K1A_SM_WORDS + tid] = VPZ_LDG(blob + H->k1a_soff_off[key & 1u] + tid);
+      staged = key;
+      __syncthreads();
+    }
+    const uint32_t i = base + tid;
+    if (i < P.n_pkts)
+      k1a_decode_packet<false, false, true>(P, P.order ? P.order[i] : i, reinterpret_cast<uint4*>(K1A_SM + K1A_SM_WORDS + 128) + 2 * tid, staged);
   }
 }
 

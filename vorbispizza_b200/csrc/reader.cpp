@@ -61,7 +61,7 @@ struct Window {
   std::vector<PktSrc> src;        // submitted packets: views into the container image or `arena`
   std::vector<int32_t> trims;
   std::vector<int> entry_of;      // submitted packet -> entry index (-1: carried-over seed packet)
-  std::deque<std::vector<uint8_t>> arena;  // packets assembled across pages
+  std::vector<std::vector<uint8_t>> arena;  // packets assembled across pages (moving an inner vector keeps its buffer: the views stay valid)
   // drain of the last decoded packet's raw right half (see resolve_drain)
   bool drain = false, drain_extra_run = false;
   int drain_tail = 0, drain_entry = -1;

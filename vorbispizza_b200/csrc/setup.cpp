@@ -822,6 +822,21 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
       floors[i].f0.wmap_off[w] = bw.put_floats(floors0[i].wmap[w].data(), floors0[i].wmap[w].size());
     }
   }
+  for (int i = 0; i < nfloors; i++) {
+    if (floors[i].floor_type != 1) continue;
+    VpzFloor1& f = floors[i];
+    bw.align(2);
+    f.fbook_tab_off = bw.reserve(16 * 9 * 2);
+    auto put = [&](int c, int k, int bk) {
+      if (bk < 0 || bk >= nbooks) return;
+      blob[f.fbook_tab_off + (size_t)(c * 9 + k) * 2] = dbooks[(size_t)bk].l1_off;
+      blob[f.fbook_tab_off + (size_t)(c * 9 + k) * 2 + 1] = (uint32_t)dbooks[(size_t)bk].l1_bits | ((uint32_t)bk << 8) | 0x10000u;   // bit 16: a book is there (l1_bits may be 0)
+    };
+    for (int c = 0; c < 16; c++) {
+      if (f.class_sub[c] > 0) put(c, 0, f.class_master[c]);
+      for (int k = 0; k < 8; k++) put(c, 1 + k, f.sub_books[c][k]);
+    }
+  }
   bw.align(4);
   h.floors_off = bw.put_struct_array(floors);
   bw.align(4);
@@ -855,6 +870,62 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
   }
   bw.align(4);
   h.db_off = bw.put_floats(reinterpret_cast<const float*>(k_db_bits), 256);
+  // ---- K1a shared-memory table plan (vpz_dev.h, VpzSetupHdr.k1a_stage_off) ------------------------------
+  for (int flag = 0; flag < 2; flag++) {
+    std::vector<int> list;
+    std::vector<char> seen((size_t)nbooks, 0);
+    auto add = [&](int bk) {
+      if (bk < 0 || bk >= nbooks || seen[(size_t)bk]) return;
+      seen[(size_t)bk] = 1;
+      list.push_back(bk);
+    };
+    for (int pass = 0; pass < 3; pass++)
+      for (const VpzMode& md : modes) {
+        if ((md.block_flag != 0) != (flag != 0)) continue;
+        const VpzMapping& mp = mappings[md.mapping];
+        for (int j = 0; j < mp.submaps; j++) {
+          const VpzResidue& r = residues[mp.submap_residue[j]];
+          if (pass == 0) {
+            for (int c = 0; c < r.classifications; c++)
+              for (int st = 0; st < 8; st++)
+                if (((r.cascade[c] >> st) & 1) && r.has_books[c]) add(r.books[c][st]);
+          } else if (pass == 1) {
+            add(r.class_book);
+          } else {
+            const VpzFloor1& fl = floors[mp.submap_floor[j]];
+            if (fl.floor_type == 1) {
+              for (int i = 0; i < fl.partitions; i++) {
+                const int c = fl.part_class[i];
+                if (fl.class_sub[c] > 0) add(fl.class_master[c]);
+                for (int k = 0; k < (1 << fl.class_sub[c]); k++) add(fl.sub_books[c][k]);
+              }
+            } else {
+              for (int b2 = 0; b2 < fl.f0.nbooks; b2++) add(fl.f0.books[b2]);
+            }
+          }
+        }
+      }
+    std::vector<uint32_t> plan;
+    std::vector<uint16_t> soff(256, (uint16_t)K1A_SM_NONE);
+    uint32_t cur = 0;
+    for (int bk : list) {
+      const uint32_t words = 1u << dbooks[(size_t)bk].l1_bits;
+      if (bk > 255 || cur + words > K1A_SM_WORDS) continue;
+      soff[(size_t)bk] = (uint16_t)cur;
+      plan.push_back(dbooks[(size_t)bk].l1_off);
+      plan.push_back(words);
+      plan.push_back(cur);
+      cur += words;
+    }
+    bw.align(4);
+    h.k1a_stage_off[flag] = bw.reserve(2 + plan.size());
+    blob[h.k1a_stage_off[flag]] = (uint32_t)(plan.size() / 3);
+    blob[h.k1a_stage_off[flag] + 1] = cur;
+    if (!plan.empty()) memcpy(&blob[h.k1a_stage_off[flag] + 2], plan.data(), plan.size() * 4);
+    bw.align(4);
+    h.k1a_soff_off[flag] = bw.reserve(128);
+    memcpy(&blob[h.k1a_soff_off[flag]], soff.data(), 512);
+  }
   bw.align(4);
   h.total_words = bw.here();
   memcpy(blob.data(), &h, sizeof(h));

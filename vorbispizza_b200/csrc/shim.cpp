@@ -118,6 +118,9 @@ int vpz_ctx_set(vpz_ctx* c, const char* key, int value) {
     if (value < 1 || value > 65536) return VPZ_E_ARGUMENT;
     c->ola_chunk = value;
     c->ola_chunk_set = true;
+  } else if (!strcmp(key, "k1a_smem")) {
+    if (value < 0 || value > 1) return VPZ_E_ARGUMENT;
+    c->k1a_smem = value;
   } else if (!strcmp(key, "k1_warps")) {
     if (value < 1 || value > 8) return VPZ_E_ARGUMENT;
     c->k1_warps = value;

@@ -54,6 +54,10 @@ struct VpzFloor1 {
   uint8_t hneigh[VPZ_MAX_POSTS + 1];
   uint8_t sortidx[VPZ_MAX_POSTS + 1];
   uint8_t pad1[3];
+  // K1a: [16 classes][9] x {first-level table word offset, l1_bits | book << 8}; entry 0 of a class is its master
+  // book, entries 1..8 the sub books; the second word is 0 for "no book" (the post is 0, nothing is read).  One
+  // 8-byte load per codeword instead of sub_books -> VpzBook.l1_off -> VpzBook.l1_bits.
+  uint32_t fbook_tab_off;
   // ---- floor 0 (Floor0.cs:39-113), valid when floor_type == 0 ----
   struct {
     uint8_t order;          // 1..255 LSP coefficients
@@ -128,7 +132,15 @@ struct VpzSetupHdr {
   uint32_t tw_off[2];       // IMDCT pre/post twiddle exp(-i*pi*(n+1/8)/M), interleaved re,im, N/4 pairs
   uint32_t fft_off[2];      // FFT roots exp(-2*pi*i*k/H), interleaved re,im, H = N/4 pairs
   uint32_t db_off;          // 256 floats, Floor1.cs:407-473
+  // K1a shared-memory tables, per block flag (0 short, 1 long): the first-level Huffman tables of the books the
+  // packets of that block size decode with (residue books first, then classbooks, then floor books, up to
+  // K1A_SM_WORDS words).  stage_off: {n, total words, n x {l1 table word offset, words, shared-memory word
+  // offset}}; soff_off: 256 x uint16 shared-memory word offset per book, 0xffff = not staged.
+  uint32_t k1a_stage_off[2];
+  uint32_t k1a_soff_off[2];
 };
+#define K1A_SM_WORDS 16384    // 64 KB of tables per CTA
+#define K1A_SM_NONE 0xffffu
 
 // ---- per-packet descriptors ------------------------------------------------------------
 // K1 input: where the packet bytes are and where its spectrum goes.
