@@ -532,6 +532,7 @@ def main():
         ctx.set("gpu_scan", int(os.environ["VPZ_BENCH_GPU_SCAN"]))
     if os.environ.get("VPZ_BENCH_HOST_THREADS", "0") != "0":
         ctx.set("host_threads", int(os.environ["VPZ_BENCH_HOST_THREADS"]))
+        ctx.set("bulk_threads", 0)
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
     if local_world > 1:
         # the ranks of one box share its host cores: split them instead of oversubscribing the bulk path's pool

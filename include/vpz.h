@@ -68,7 +68,9 @@ int vpz_device_count(void);
  * default 9), "ola_chunk" (packets per IMDCT work item, default: 16..63 chosen per batch), "k1_warps" (warps per entropy
  * CTA, default 4), "bulk_group" (streams per pipeline group of vpz_decode_files, default 256), "bulk_group_mib" (a group also closes
  * at this many MiB of container images, default 128, at most 384),
- * "host_threads" (host worker threads of the bulk path, default 0 = all cores up to 32), "gpu_scan" (bulk
+ * "host_threads" (size of the host worker pool of the bulk calls, default 0 = all cores up to 32), "bulk_threads"
+ * (how many of them vpz_decode_files uses, default 4: the call is bound by the PCM copy, which more staging
+ * threads slow down; 0 = all), "gpu_scan" (bulk
  * path: Ogg page scan + CRC on the GPU, default 1), "force_general" (tests: route every packet through the
  * general kernels). */
 int vpz_ctx_set(vpz_ctx* ctx, const char* key, int value);

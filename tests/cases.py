@@ -268,16 +268,21 @@ def decode_files_s16_parity(ctx, names, clip=True):
     assert off == pcm16.size
 
 
-def excerpts_parity(ctx, names, n_excerpts, nread=4096, seed=0x5EED0005, extra_positions=(), clip=True):
+def excerpts_parity(ctx, names, n_excerpts, nread=4096, seed=0x5EED0005, extra_positions=(), clip=True, datas=None):
     """BASELINE config 5: a batch of short excerpts (SeekTo + read nread samples, each like a fresh reader)
     through vpz_decode_excerpts vs the oracle's reader, excerpt by excerpt.  Start samples: seeded uniform
-    in [0, total) of a uniformly chosen file, plus `extra_positions` on every file (edge cases)."""
-    datas = [load_file(n) for n in names]
+    in [0, total) of a uniformly chosen file, plus `extra_positions` on every file (edge cases).
+    datas: container images to use instead of the TestFiles `names` (damaged streams: names label them)."""
+    if datas is None:
+        datas = [load_file(n) for n in names]
     totals, chans = [], []
     for d in datas:
         s = ob.OracleStream(d)
-        ref, _, _ = s.decode_all()
-        totals.append(ref.shape[0])
+        try:
+            ref, _, _ = s.decode_all()
+            totals.append(max(ref.shape[0], 2))
+        except ob.OracleError:
+            totals.append(100000)
         chans.append(s.channels)
     rng = np.random.default_rng(seed)
     file_of = list(rng.integers(0, len(names), n_excerpts))

@@ -331,3 +331,22 @@ def test_granule_index_emulated(emu_ctx):
 def test_granule_index(gpu_ctx):
     n = _granule_index_parity(gpu_ctx, _index_cases(["1test", "2test", "3test", "issue6test"], None), "seek index")
     assert n >= 16
+
+
+# ---- random access on damaged containers: files that do not qualify for the device seek index keep the host walk,
+# ---- and every excerpt still has to be what a fresh reference reader delivers (SeekTo errors included)
+def _excerpts_on_damaged(ctx, name, limit, n_excerpts, nread):
+    named = [(k, d) for k, d in damaged_streams(name, limit).items()]
+    named.append(("intact", cases.load_file(name)))
+    return cases.excerpts_parity(ctx, ["%s/%s" % (name, k) for k, _ in named], n_excerpts=n_excerpts, nread=nread,
+                                 extra_positions=(0, 1, -1, -200, 10 ** 7), datas=[d for _, d in named], seed=1234)
+
+
+def test_excerpts_on_damaged_streams_emulated(emu_ctx):
+    _excerpts_on_damaged(emu_ctx, "1test", None, 10, 900)
+
+
+@pytest.mark.gpu
+def test_excerpts_on_damaged_streams(gpu_ctx):
+    _excerpts_on_damaged(gpu_ctx, "3test", None, 200, 3000)
+    _excerpts_on_damaged(gpu_ctx, "2test", None, 120, 4096)

@@ -275,7 +275,7 @@ void batch_drop_slots(vpz_batch* b) {
 
 // ---- host worker pool -----------------------------------------------------------------------
 ThreadPool::ThreadPool(unsigned n) {
-  for (unsigned i = 1; i < n; i++) workers_.emplace_back([this] { worker(); });
+  for (unsigned i = 1; i < n; i++) workers_.emplace_back([this, i] { worker(i); });
 }
 ThreadPool::~ThreadPool() {
   {
@@ -292,16 +292,22 @@ void ThreadPool::drain() {
     (*fn_)(i);
   }
 }
-void ThreadPool::worker() {
+void ThreadPool::set_limit(unsigned k) {
+  std::lock_guard<std::mutex> lk(m_);
+  limit_ = k;
+}
+void ThreadPool::worker(unsigned id) {
   unsigned seen = 0;
   for (;;) {
+    bool take;
     {
       std::unique_lock<std::mutex> lk(m_);
       cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
       if (stop_) return;
       seen = generation_;
+      take = limit_ == 0 || id < limit_;   // the caller is thread 0
     }
-    drain();
+    if (take) drain();
     {
       std::lock_guard<std::mutex> lk(m_);
       if (--active_ == 0) done_cv_.notify_all();

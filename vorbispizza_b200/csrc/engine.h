@@ -46,10 +46,13 @@ class ThreadPool {
   // Runs fn(0..n-1) on the workers and the calling thread; returns when all are done.
   void parallel_for(size_t n, const std::function<void(size_t)>& fn);
   unsigned size() const { return (unsigned)workers_.size() + 1; }
+  // At most k threads (the caller included) take part in the parallel_for calls that follow; 0 = all.
+  void set_limit(unsigned k);
 
  private:
-  void worker();
+  void worker(unsigned id);
   void drain();
+  unsigned limit_ = 0;
   std::vector<std::thread> workers_;
   std::mutex m_;
   std::condition_variable cv_, done_cv_;
@@ -103,7 +106,8 @@ struct vpz_ctx {
   int bulk_group = 256;                      // streams per pipeline group ("bulk_group" tunable)
   int bulk_group_mib = 128;                  // ... and at most this many MiB of container images ("bulk_group_mib")
   int bulk_group_bytes = 0;                  // tests: the same limit in bytes (overrides bulk_group_mib when > 0)
-  int host_threads = 0;                      // 0: hardware concurrency, capped at 32
+  int host_threads = 0;                      // size of the worker pool; 0: hardware concurrency, capped at 32
+  int bulk_threads = 4;                      // of those, how many vpz_decode_files uses ("bulk_threads"; 0: all)
 };
 
 namespace vpz {

@@ -877,6 +877,14 @@ static int64_t decode_files_impl(vpz_ctx* ctx, uint32_t n, const uint8_t* const*
     if (!ctx->pool) return VPZ_E_NOMEM;
   }
   ThreadPool* pool = ctx->pool;
+  // The call is bound by the PCM copy, and the copy gets SLOWER the more host threads stage packets beside it
+  // (16-core box, 4,096 streams: 2 / 4 / 8 / 16 threads = 169 / 167 / 171 / 178 ms; with 2 the 16-bit path turns
+  // host-bound): a few threads are the optimum, "bulk_threads" (default 4).
+  struct PoolLimit {
+    ThreadPool* p;
+    PoolLimit(ThreadPool* pool_, unsigned k) : p(pool_) { p->set_limit(k); }
+    ~PoolLimit() { p->set_limit(0); }
+  } pool_limit(pool, (unsigned)std::max(0, ctx->bulk_threads));
   const bool trace = getenv("VPZ_TRACE") != nullptr;
   double t_scan = 0, t_init = 0, t_plan = 0, t_commit = 0, t_launch = 0, t_wait = 0;
   auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };

@@ -143,6 +143,9 @@ int vpz_ctx_set(vpz_ctx* c, const char* key, int value) {
   } else if (!strcmp(key, "gpu_scan")) {
     if (value < 0 || value > 2) return VPZ_E_ARGUMENT;   // 2: single readers too (tests)
     c->gpu_scan = value;
+  } else if (!strcmp(key, "bulk_threads")) {
+    if (value < 0 || value > 256) return VPZ_E_ARGUMENT;
+    c->bulk_threads = value;
   } else if (!strcmp(key, "host_threads")) {
     if (value < 0 || value > 256 || c->pool) return VPZ_E_ARGUMENT;  // before the first bulk call
     c->host_threads = value;
