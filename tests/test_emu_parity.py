@@ -120,6 +120,23 @@ def test_excerpts_batch(emu_ctx):
     assert n >= 12
 
 
+def test_bulk_calls_in_any_order(emu_lib_path):
+    """vpz_decode_excerpts and vpz_decode_files share the context's pipeline batches: either may come first."""
+    import numpy as np
+    from vorbispizza_b200 import Context, decode_excerpts, decode_files
+    data = cases.load_file("1test")
+    ctx = Context(0, lib_path=emu_lib_path)
+    try:
+        pcm, _, got = decode_excerpts(ctx, [data], [0, 0], [100, 5000], [300, 300])
+        assert list(got) == [300, 300]
+        full, counts = decode_files(ctx, [data, data, data, data], clip=True)
+        n = int(counts[0])
+        assert np.array_equal(full[:n].view(np.uint32), full[n:2 * n].view(np.uint32))
+        assert np.array_equal(pcm[:300].view(np.uint32), full[100:400].view(np.uint32))
+    finally:
+        ctx.close()
+
+
 def test_decode_files_s16(emu_ctx):
     cases.decode_files_s16_parity(emu_ctx, ["1test"])
 

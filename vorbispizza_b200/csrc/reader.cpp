@@ -996,8 +996,8 @@ static int64_t decode_files_impl(vpz_ctx* ctx, uint32_t n, const uint8_t* const*
       rc = VPZ_E_ARGUMENT;
       break;
     }
-    if (!ctx->bulk[slot]) {
-      if ((rc = vpz_batch_create(ctx, &ctx->bulk[slot]))) break;
+    if (!ctx->bulk[slot] && (rc = vpz_batch_create(ctx, &ctx->bulk[slot]))) break;
+    if (!ctx->bulk_done[slot]) {   // (the batches are shared with vpz_decode_excerpts, which may have made them first)
       ctx->bulk_done[slot] = dev::event_create();
       ctx->bulk_ready[slot] = dev::event_create();
       if (!ctx->bulk_done[slot] || !ctx->bulk_ready[slot]) {
