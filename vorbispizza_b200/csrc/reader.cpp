@@ -234,6 +234,12 @@ void plan_window(StreamDec* d, int max_packets, Window* w, int64_t need = 0) {
   bool has_pos = d->has_position;
   int seek_left = d->seek_left;
   int64_t produced = 0;
+  if (need > 0) {   // a short excerpt: a handful of packets, one allocation per array
+    w->entries.reserve(12);
+    w->src.reserve(12);
+    w->trims.reserve(12);
+    w->entry_of.reserve(12);
+  }
   if (have_prev && !d->carry.empty()) {
     w->src.push_back(PktSrc{d->carry.data(), (uint32_t)d->carry.size()});
     w->trims.push_back(d->carry_trim);
@@ -1082,7 +1088,7 @@ struct ExcerptFile {
 };
 struct ExcerptJob {
   uint32_t index = 0;          // position in the caller's arrays
-  Window win;
+  std::unique_ptr<Window> win; // made by the planning worker, dropped by the replaying one (a Window is ~600 bytes)
   int64_t pos = 0;             // granule position the provider reported for the target packet
   int status = 0;              // error of the provider side of SeekTo
   int run = -1, drain_run = -1;
@@ -1292,23 +1298,27 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
     }
     for (uint32_t i = 0; i < n; i++) jobs[i].index = order[i];
   }
-  for (ExcerptTask& t : tasks) {   // decoders of the tasks (serial: setup reference counts)
-    StreamDec& m = files[t.file]->master;
-    t.dec.reset(new StreamDec);
-    StreamDec* d = t.dec.get();
-    d->ctx = ctx;
-    d->setup = m.setup;
-    m.setup->refs++;
-    d->clip = clip != 0;
-    d->planned_only = true;
-  }
+  for (ExcerptTask& t : tasks) files[t.file]->master.setup->refs++;   // one reference per task decoder (serial: plain counters)
+  struct TaskRefs {   // a task whose decoder was never made (an error on the way) gives its reference back here
+    std::vector<ExcerptTask>& tasks;
+    std::vector<std::unique_ptr<ExcerptFile>>& files;
+    ~TaskRefs() {
+      for (ExcerptTask& t : tasks)
+        if (!t.dec) setup_release(files[t.file]->master.setup);
+    }
+  } task_refs{tasks, files};
   tt1 = now(); t_tasks = tt1 - tt0; tt0 = tt1;
   // Provider side of SeekTo + window plan of every excerpt of tasks [t0, t1): each task works on its own copy of
   // the file's packet cursor (which inherits the file's page-end granule cache)
   auto plan_tasks = [&](size_t t0, size_t t1) {
     pool->parallel_for(t1 - t0, [&](size_t k) {
       ExcerptTask& t = tasks[t0 + k];
+      t.dec.reset(new StreamDec);
       StreamDec* d = t.dec.get();
+      d->ctx = ctx;
+      d->setup = files[t.file]->master.setup;
+      d->clip = clip != 0;
+      d->planned_only = true;
       t.ls.reset(new LogicalStream(*files[t.file]->master.ls));
       d->ls = t.ls.get();
       d->ls->granule_count = [d](const OggPacket& pk) { return d->granule_count(pk); };
@@ -1319,11 +1329,12 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
         d->has_clipped = false;
         j.status = seek_begin(d, sp, &j.pos);
         if (j.status) continue;
-        plan_window(d, 0, &j.win, (sp - j.pos) + (int64_t)count[j.index]);
+        j.win.reset(new Window);
+        plan_window(d, 0, j.win.get(), (sp - j.pos) + (int64_t)count[j.index]);
         d->seek_left = 0;
-        resolve_drain(d, &j.win);
+        resolve_drain(d, j.win.get());
         std::string err;
-        int rc = plan_submit(d, &j.win, &err);
+        int rc = plan_submit(d, j.win.get(), &err);
         if (rc) j.status = rc;
       }
     });
@@ -1369,12 +1380,12 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
       for (size_t q = 0; q < tasks[ti].count; q++) {
         ExcerptJob& j = jobs[tasks[ti].first + q];
         if (j.status) continue;
-        if (j.win.has_plan) {
-          plans.push_back(&j.win.plan);
+        if (j.win->has_plan) {
+          plans.push_back(&j.win->plan);
           owner.push_back({&j, 0});
         }
-        if (j.win.has_drain_plan) {
-          plans.push_back(&j.win.drain_plan);
+        if (j.win->has_drain_plan) {
+          plans.push_back(&j.win->drain_plan);
           owner.push_back({&j, 1});
         }
       }
@@ -1396,7 +1407,7 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
           if (got) got[i] = j.status;
           continue;
         }
-        int prc = place_window(d, b, &j.win, j.run, j.drain_run, 0);
+        int prc = place_window(d, b, j.win.get(), j.run, j.drain_run, 0);
         if (prc) {
           if (got) got[i] = prc;
           continue;
@@ -1407,7 +1418,7 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
         d->has_position = true;
         d->seek_left = 2;
         d->seek_pos = j.pos;
-        d->q = std::move(j.win.entries);
+        d->q = std::move(j.win->entries);
         d->qh = 0;
         d->seg_sink = &segs;
         const size_t mark = segs.size();
@@ -1426,7 +1437,7 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
         }
         d->seg_sink = nullptr;
         if (got) got[i] = src ? src : have;
-        j.win = Window();   // release the packet views / arena
+        j.win.reset();   // release the packet views / arena
       }
     });
     size_t n_segs = 0;
