@@ -352,7 +352,25 @@ def run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
     k3_ms = ms_max / steps
     a = 8.0 * samples_rank / (k3_ms * 1e-3) / 1e9
     batch.close()
-    return {
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        # the oracle's Mdct.Reverse + OverlapBuffers + interleaved store on the same synthetic streams, all host cores
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_binding as ob
+        cores = os.cpu_count() or 1
+        builds = {}
+        for name, native in (("O2", False), ("O3_march_native", True)):
+            if ob.bench_lib(native) is None:
+                continue
+            ob.bench_imdct_ola(spectra, flags, ch, 256, 2048, cores, native)
+            nn, ss, _ = ob.bench_imdct_ola(spectra, flags, ch, 256, 2048, cores, native)
+            assert nn == samples_rank, (nn, samples_rank)
+            builds[name] = nn / ss
+        if builds:
+            best = max(builds, key=lambda k: builds[k])
+            cpu = {"value": builds[best], "unit": UNIT, "cores": cores, "kind": "port", "build": best, "builds": builds,
+                   "sample": "all 65,536 blocks: Mdct.Reverse + OverlapBuffers + interleaved clipped store, one stream per thread"}
+    line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
         "ms_per_step": k3_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic spectra (seeded)",
@@ -367,6 +385,10 @@ def run_config3(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks,
                      "frac": a / peak, "traffic": load_traffic().get("config3:vpz_k3_streams"), "peak_source": peak_src,
                      "ms_per_launch": k3_ms, "algorithmic_bytes_per_launch": 8.0 * samples_rank},
     }
+    if cpu:
+        line["cpu_baseline"] = cpu
+        line["vs_cpu_baseline"] = value / cpu["value"]
+    return line
 
 
 def run_config5(args, ctx, rank, world, barrier, max_over_ranks, sum_over_ranks, local_rank, with_cpu=True):
@@ -735,6 +757,9 @@ def main():
         sub3 = {k: c3[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "roofline")}
         sub3["workload"] = c3["config"]["workload"]
         sub3["short_block_fraction"] = c3["config"]["short_block_fraction"]
+        for k in ("cpu_baseline", "vs_cpu_baseline"):
+            if k in c3:
+                sub3[k] = c3[k]
         sub5 = {k: c5[k] for k in ("value", "unit", "ms_per_step", "steps", "gpu_launches", "e2e") if k in c5}
         sub5["workload"] = c5["config"]["workload"]
         sub5["excerpts_per_s"] = c5["config"]["excerpts_per_s"]

@@ -717,6 +717,14 @@ static void mdct_reverse(const mdct_setup* s, float* buffer, float* buf2) {
   }
 }
 
+/* the same with caller-provided scratch of n / 2 floats (no allocation per call) */
+int vo_imdct2(float* buf, int n, float* buf2) {
+  const mdct_setup* s = mdct_get(n);
+  if (!s) return VO_E_ARGUMENT;
+  mdct_reverse(s, buf, buf2);
+  return VO_OK;
+}
+
 int vo_imdct(float* buf, int n) {
   const mdct_setup* s = mdct_get(n);
   if (!s) return VO_E_ARGUMENT;

@@ -156,6 +156,16 @@ int64_t vo_bench_decode(const uint8_t* const* datas, const size_t* lens, int nfi
                         double* seconds);
 /* n excerpts: SeekTo(start[i]) + read count[i] samples per channel of file file_of[i]; every thread keeps one
  * open reader per file.  Returns the channel-samples delivered. */
+/* BASELINE config 3 on host cores: synthetic streams of `n_blocks` blocks each (flags bit 0: long block; window
+ * flags of a long block follow its neighbours like Mode.GetPacketInfo would read them), `channels` spectra of n / 2
+ * floats per block back to back in `spectra`.  Per block Mdct.Reverse (Mdct.cs:77-419), OverlapBuffers
+ * (StreamDecoder.cs:764-791) and the interleaved clipped store of StoreInterleaved (StreamDecoder.cs:515-592) into a
+ * per-thread buffer; streams are handed to `nthreads` threads by a shared cursor.  Returns the channel-samples
+ * produced; *seconds = wall time; *checksum (may be NULL) = sum of all samples, so the work cannot be elided. */
+int64_t vo_bench_imdct_ola(const float* spectra, const uint8_t* flags, int n_streams, int n_blocks, int channels,
+                           int size0, int size1, int nthreads, double* seconds, double* checksum);
+int vo_imdct2(float* buf, int n, float* scratch);
+
 int64_t vo_bench_excerpts(const uint8_t* const* datas, const size_t* lens, int nfiles, int n, const uint32_t* file_of,
                           const int64_t* start, const int32_t* count, int nthreads, double* seconds);
 

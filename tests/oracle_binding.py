@@ -411,3 +411,20 @@ def bench_excerpts(files, file_of, start, count, nthreads, native=False):
     n = L.vo_bench_excerpts(ptrs, lens, len(keep), int(file_of.size), file_of.ctypes.data, start.ctypes.data,
                             count.ctypes.data, nthreads, C.byref(sec))
     return n, sec.value
+
+
+def bench_imdct_ola(spectra, flags, channels, size0, size1, nthreads, native=False):
+    """Host-core baseline of BASELINE config 3: Mdct.Reverse + OverlapBuffers + interleaved clipped store on the
+    synthetic streams (flags [n_streams][n_blocks], spectra back to back); returns (channel_samples, seconds)."""
+    L = bench_lib(native)
+    if L is None:
+        return None
+    L.vo_bench_imdct_ola.restype = C.c_int64
+    L.vo_bench_imdct_ola.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                     C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    spectra = np.ascontiguousarray(spectra, np.float32)
+    flags = np.ascontiguousarray(flags, np.uint8)
+    sec, chk = C.c_double(0), C.c_double(0)
+    n = L.vo_bench_imdct_ola(spectra.ctypes.data, flags.ctypes.data, flags.shape[0], flags.shape[1], channels, size0, size1,
+                             nthreads, C.byref(sec), C.byref(chk))
+    return n, sec.value, chk.value

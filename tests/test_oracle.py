@@ -186,3 +186,24 @@ def test_integer_stages_vs_independent_walker(name):
         assert _pin_digest([v for c in range(s.channels) for v in o["final_y"][c][:counts[c]]]) == w["final_y"], what
         assert _pin_digest([v for c in range(s.channels) for v in o["step_flags"][c][:counts[c]]]) == w["step_flags"], what
         assert o["bits_read"] == w["bits"], what
+
+
+def test_bench_imdct_ola_matches_the_reference_restatement():
+    """bench.py's config-3 CPU baseline (oracle/vo_bench.c: Mdct.Reverse + OverlapBuffers + interleaved clipped
+    store per synthetic stream) produces the samples tests/cases.py's block-by-block restatement produces."""
+    import cases
+    rng = np.random.default_rng(5)
+    ch, n_streams, n_blocks = 2, 3, 17
+    flags = rng.integers(0, 2, (n_streams, n_blocks)).astype(np.uint8)
+    sizes = np.where(flags.reshape(-1) & 1, 1024, 128)
+    spectra = (rng.standard_normal(int(sizes.sum()) * ch) * 0.05).astype(np.float32)
+    n, _, chk = ob.bench_imdct_ola(spectra, flags, ch, 256, 2048, 2)
+    total, ref_sum, off = 0, 0.0, 0
+    for s in range(n_streams):
+        nfl = int(sum((2048 if f & 1 else 256) // 2 * ch for f in flags[s]))
+        ref = cases.reference_imdct_ola(flags[s], spectra[off:off + nfl], ch, 256, 2048)
+        off += nfl
+        total += ref.size
+        ref_sum += float(np.clip(ref, -0.99999994, 0.99999994).astype(np.float64).sum())
+    assert n == total
+    assert abs(chk - ref_sum) <= 1e-3 * max(1.0, abs(ref_sum)) + 1e-2
