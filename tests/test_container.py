@@ -350,3 +350,46 @@ def test_excerpts_on_damaged_streams_emulated(emu_ctx):
 def test_excerpts_on_damaged_streams(gpu_ctx):
     _excerpts_on_damaged(gpu_ctx, "3test", None, 200, 3000)
     _excerpts_on_damaged(gpu_ctx, "2test", None, 120, 4096)
+
+
+# ---- a file with more pages than the device scan sizes its record area for (len / 64 + 16) falls back to the host scan
+def _many_empty_pages(name, limit, every):
+    hdr, pk = _parts(name)
+    pages = _pages(hdr, pk[:limit] if limit else pk)
+    out = []
+    for i, (packets, gran) in enumerate(pages):
+        out.append((packets, gran))
+        if i >= 2:
+            out += [([], gran)] * every      # 27-byte pages that complete no packet and repeat the granule
+    return oggmux.mux(out)
+
+
+def _overflow_parity(lib_path, name, limit, every):
+    from vorbispizza_b200 import Context, decode_files, scan_pages, VpzError
+    from vorbispizza_b200 import _native as N
+    data = _many_empty_pages(name, limit, every)
+    n_pages = data.count(b"OggS")
+    assert n_pages > len(data) // 64 + 16, "the case must overflow the record area"
+    outs = []
+    for gpu_scan in (1, 0):
+        ctx = Context(0, lib_path=lib_path) if lib_path else Context(0)
+        try:
+            ctx.set("gpu_scan", gpu_scan)
+            if gpu_scan:
+                with pytest.raises(VpzError) as e:      # the explicit scan call reports it ...
+                    scan_pages(ctx, [data])
+                assert e.value.code == N.VPZ_E_UNSUPPORTED
+            outs.append(decode_files(ctx, [data, cases.load_file(name)], clip=True))   # ... the bulk path scans that file on the host
+        finally:
+            ctx.close()
+    assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0].view(np.uint32), outs[1][0].view(np.uint32))
+    cases.reader_parity_bytes(Context(0, lib_path=lib_path) if lib_path else Context(0), data, name + " with empty pages", lookahead=32)
+
+
+def test_record_area_overflow_emulated(emu_lib_path):
+    _overflow_parity(emu_lib_path, "1test", None, 120)
+
+
+@pytest.mark.gpu
+def test_record_area_overflow():
+    _overflow_parity(None, "2test", None, 150)
