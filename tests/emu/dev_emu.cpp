@@ -139,9 +139,10 @@ int launch_k1a(const K1Params& p, bool debug, bool full, int blocks, Stream*, st
     emu::launch(1, K1A_SM_THREADS, ((size_t)K1A_SM_WORDS + 128) * 4 + K1A_RING_BYTES(K1A_SM_THREADS), [&] { k1a_sm_loop(p, s_ctl); });
     return VPZ_OK;
   }
-  emu::launch(1, 128, K1A_RING_BYTES(128), [&] {
+  emu::launch(1, 128, K1A_RING_BYTES(128) + K1A_CLS_BYTES(128), [&] {
     const int lane = threadIdx.x & 31;
     uint4* ring = reinterpret_cast<uint4*>(emu::t_block->smem) + 2 * threadIdx.x;
+    uint32_t* cls = reinterpret_cast<uint32_t*>(emu::t_block->smem) + K1A_RING_BYTES(128) / 4 + threadIdx.x;
     for (;;) {
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(p.counter, 32u);
@@ -151,9 +152,9 @@ int launch_k1a(const K1Params& p, bool debug, bool full, int blocks, Stream*, st
       if (i < p.n_pkts) {
         const uint32_t k = p.order ? p.order[i] : i;
         if (debug) {
-          if (full) k1a_decode_packet<true, true>(p, k, ring); else k1a_decode_packet<true, false>(p, k, ring);
+          if (full) k1a_decode_packet<true, true>(p, k, ring, cls); else k1a_decode_packet<true, false>(p, k, ring, cls);
         } else {
-          if (full) k1a_decode_packet<false, true>(p, k, ring); else k1a_decode_packet<false, false>(p, k, ring);
+          if (full) k1a_decode_packet<false, true>(p, k, ring, cls); else k1a_decode_packet<false, false>(p, k, ring, cls);
         }
       }
       __syncwarp();

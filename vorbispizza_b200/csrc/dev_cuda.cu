@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(128, K1A_MIN_CTAS) vpz_k1a_symbols(K1Params P)
     base = __shfl_sync(0xffffffffu, base, 0);
     if (base >= P.n_pkts) break;
     const uint32_t i = base + lane;
-    if (i < P.n_pkts) k1a_decode_packet<DEBUG, FULL>(P, P.order ? P.order[i] : i, reinterpret_cast<uint4*>(k1a_sm) + 2 * threadIdx.x);
+    if (i < P.n_pkts) k1a_decode_packet<DEBUG, FULL>(P, P.order ? P.order[i] : i, reinterpret_cast<uint4*>(k1a_sm) + 2 * threadIdx.x,
+                                                     k1a_sm + K1A_RING_BYTES(128) / 4 + threadIdx.x);
     __syncwarp();
   }
 }
@@ -312,9 +313,9 @@ int launch_k1a(const K1Params& p, bool debug, bool full, int blocks, Stream* s, 
     return VPZ_OK;
   }
   if (debug) {
-    if (full) vpz_k1a_symbols<true, true><<<blocks, 128, K1A_RING_BYTES(128), s->s>>>(p); else vpz_k1a_symbols<true, false><<<blocks, 128, K1A_RING_BYTES(128), s->s>>>(p);
+    if (full) vpz_k1a_symbols<true, true><<<blocks, 128, K1A_RING_BYTES(128) + K1A_CLS_BYTES(128), s->s>>>(p); else vpz_k1a_symbols<true, false><<<blocks, 128, K1A_RING_BYTES(128) + K1A_CLS_BYTES(128), s->s>>>(p);
   } else {
-    if (full) vpz_k1a_symbols<false, true><<<blocks, 128, K1A_RING_BYTES(128), s->s>>>(p); else vpz_k1a_symbols<false, false><<<blocks, 128, K1A_RING_BYTES(128), s->s>>>(p);
+    if (full) vpz_k1a_symbols<false, true><<<blocks, 128, K1A_RING_BYTES(128) + K1A_CLS_BYTES(128), s->s>>>(p); else vpz_k1a_symbols<false, false><<<blocks, 128, K1A_RING_BYTES(128) + K1A_CLS_BYTES(128), s->s>>>(p);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k1a_symbols", err);

@@ -89,6 +89,10 @@
 #endif
 
 #define K1A_RING_BYTES(threads) ((size_t)(threads) * 32)   // two 16-byte slots per thread
+// K1a keeps the partition classes of a packet's first K1A_CLS_CACHE units in shared memory as well: the walk reads a
+// unit's class back to find its book, and the read-back of its own global store missed L1 (stores do not allocate)
+#define K1A_CLS_CACHE 64
+#define K1A_CLS_BYTES(threads) ((size_t)(threads) * K1A_CLS_CACHE)
 
 struct K1Bits {
   uint32_t woff;   // word offset of the packet in the batch byte buffer (a multiple of 4: packets start on 16 bytes)
@@ -104,10 +108,15 @@ struct K1Bits {
   uint32_t lo, hi, nx;
   int wi;
   uint4* ring;     // this thread's two slots (32 consecutive bytes): word j of the packet sits at word j & 7
+  uint32_t* cls;   // class cache: this thread's word of row 0, rows are blockDim.x words apart (NULL: no cache)
 };
 
 VPZ_DEV uint32_t k1_ring_word(const K1Bits& b, int j) {   // word j of the packet; its chunk is resident
   return reinterpret_cast<const uint32_t*>(b.ring)[j & 7];
+}
+
+VPZ_DEV uint8_t* k1_cls_slot(const K1Bits& b, int u) {   // u < K1A_CLS_CACHE
+  return reinterpret_cast<uint8_t*>(b.cls + (u >> 2) * blockDim.x) + (u & 3);
 }
 
 VPZ_DEV void k1_bits_init(K1Bits& b, const uint32_t* bytes, uint32_t woff, int byte_len, uint4* ring) {
@@ -116,6 +125,7 @@ VPZ_DEV void k1_bits_init(K1Bits& b, const uint32_t* bytes, uint32_t woff, int b
   b.nbits = byte_len * 8;
   b.wi = 0;
   b.ring = ring;
+  b.cls = nullptr;
   K1_CP16(ring, bytes + woff);
   K1_CP16(ring + 1, bytes + woff + 4);
   K1_CP_WAIT();
@@ -384,7 +394,8 @@ VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook*
             if (cur_mask) {
               const int u = ubase + __ffs((int)cur_mask) - 1;
               cur_mask &= cur_mask - 1;
-              const uint2 t = VPZ_LDG(reinterpret_cast<const uint2*>(blob + unit_tab_off) + (rec_cls[u] * 8 + stage));
+              const int cu = (b.cls && u < K1A_CLS_CACHE) ? *k1_cls_slot(b, u) : rec_cls[u];
+              const uint2 t = VPZ_LDG(reinterpret_cast<const uint2*>(blob + unit_tab_off) + (cu * 8 + stage));
               cur.l1_off = t.x;
               cur.l1_mask = (1u << (t.y & 0xffu)) - 1u;
               cur.meta = (t.y & 0xffffu) | (k1a_soff<SM>(sm_on, (int)((t.y >> 8) & 0xffu)) << 16);
@@ -424,7 +435,12 @@ VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook*
           const int left = part_count - gpart;   // partitions of this (possibly partial, last) group
           const uint8_t* dmap = reinterpret_cast<const uint8_t*>(blob + dmap_off) + sym * cdim;
           for (int kk = 0; kk < cdim; kk++)
-            if (kk < left) rec_cls[(gpart + kk) * nvec + cw_v] = dmap[kk];
+            if (kk < left) {
+              const int u2 = (gpart + kk) * nvec + cw_v;
+              const uint8_t c2 = dmap[kk];
+              rec_cls[u2] = c2;
+              if (b.cls && u2 < K1A_CLS_CACHE) *k1_cls_slot(b, u2) = c2;
+            }
           const uint32_t lim = left * nvec >= 32 ? 0xffffffffu : (1u << (left * nvec)) - 1u;
           const uint32_t* ct = blob + cw_tab_off + ((size_t)cw_v * partvals + sym) * max_stages;
           grp_acc |= VPZ_LDG(ct) & lim;
@@ -465,7 +481,7 @@ VPZ_DEV void k1a_residue(const K1Params& P, const uint32_t* blob, const VpzBook*
 // staged_key: (setup slot * 2 + long block flag) whose tables the CTA holds in shared memory (SM variant only)
 // ring: this thread's two 16-byte slots for the packet bytes (K1Bits)
 template <bool DEBUG, bool FULL, bool SM = false>
-VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx, uint4* ring, uint32_t staged_key = 0xffffffffu) {
+VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx, uint4* ring, uint32_t* cls, uint32_t staged_key = 0xffffffffu) {
   const VpzPktIn pk = P.pkts[pkt_idx];
   const uint32_t* blob = P.setups[pk.setup_slot];
   VPZ_ASSUME_GLOBAL(blob);
@@ -477,6 +493,7 @@ VPZ_DEV void k1a_decode_packet(const K1Params& P, uint32_t pkt_idx, uint4* ring,
 
   K1Bits b;
   k1_bits_init(b, P.bytes, pk.byte_off >> 2, (int)pk.byte_len, ring);
+  b.cls = cls;
   int nscal = 0, ncls = 0;
 
   // StreamDecoder.DecodeNextPacket (StreamDecoder.cs:728-741): the host only queues packets whose
@@ -777,7 +794,7 @@ VPZ_DEV void k1a_sm_loop(const K1Params& P, uint32_t* s_ctl) {
     }
     const uint32_t i = base + tid;
     if (i < P.n_pkts)
-      k1a_decode_packet<false, false, true>(P, P.order ? P.order[i] : i, reinterpret_cast<uint4*>(K1A_SM + K1A_SM_WORDS + 128) + 2 * tid, staged);
+      k1a_decode_packet<false, false, true>(P, P.order ? P.order[i] : i, reinterpret_cast<uint4*>(K1A_SM + K1A_SM_WORDS + 128) + 2 * tid, nullptr, staged);
   }
 }
 
