@@ -115,7 +115,11 @@ int fill(void* d, int v, size_t n, Stream*, std::string&) {
 
 int launch_k0(const K0Params& p, Stream*, std::string&) {
   if (p.n_files == 0) return VPZ_OK;
-  emu::launch(1, K0_THREADS, K0_SMEM_WORDS * 4, [&] { k0_cta(p, (uint32_t*)emu::t_block->smem); });
+  emu::launch(1, K0_THREADS, 0, [&] { k0_walk_cta(p); });
+  emu::launch(2, K0_THREADS, K0_SMEM_WORDS * 4, [&] { k0_crc_cta(p, (uint32_t*)emu::t_block->smem); });
+  K0Params q = p;
+  q.only_irregular = 1;
+  emu::launch(1, K0_THREADS, K0_SMEM_WORDS * 4, [&] { k0_cta(q, (uint32_t*)emu::t_block->smem); });
   return VPZ_OK;
 }
 

@@ -17,6 +17,11 @@ __global__ void __launch_bounds__(K0_THREADS) vpz_k0_pages(K0Params P) {
   __shared__ uint32_t k0_smem[K0_SMEM_WORDS];
   k0_cta(P, k0_smem);
 }
+__global__ void __launch_bounds__(K0_THREADS) vpz_k0_walk(K0Params P) { k0_walk_cta(P); }
+__global__ void __launch_bounds__(K0_THREADS) vpz_k0_crc(K0Params P) {
+  __shared__ uint32_t k0_smem[K0_SMEM_WORDS];
+  k0_crc_cta(P, k0_smem);
+}
 
 __global__ void __launch_bounds__(K0_THREADS) vpz_k0g_granules(K0gParams P) { k0g_cta(P); }
 
@@ -272,9 +277,13 @@ int launch_k0(const K0Params& p, Stream* s, std::string& err) {
   if (p.n_files == 0) return VPZ_OK;
   const unsigned warps = K0_THREADS / 32;
   unsigned grid = (unsigned)std::min<size_t>(((size_t)p.n_files + warps - 1) / warps, (size_t)8 * sm_count());
-  vpz_k0_pages<<<grid, K0_THREADS, 0, s->s>>>(p);
+  vpz_k0_walk<<<grid, K0_THREADS, 0, s->s>>>(p);
+  vpz_k0_crc<<<8 * sm_count(), K0_THREADS, 0, s->s>>>(p);   // as many warps as fit: the jobs are pages, not files
+  K0Params q = p;
+  q.only_irregular = 1;
+  vpz_k0_pages<<<grid, K0_THREADS, 0, s->s>>>(q);           // a no-op pass over the flags when every file was regular
   cudaError_t e = cudaGetLastError();
-  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k0_pages", err);
+  return e == cudaSuccess ? VPZ_OK : fail(e, "launch vpz_k0_walk / crc / pages", err);
 }
 
 int launch_k0g(const K0gParams& p, Stream* s, std::string& err) {

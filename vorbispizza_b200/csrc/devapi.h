@@ -61,7 +61,8 @@ int launch_k1b(const K1Params& p, bool debug, int blocks, int warps, Stream* s, 
 int launch_k3(const K3Params& p, int ncb, size_t smem_bytes, Stream* s, std::string& err);
 // K3, block sizes 256 / 2048 and at most 2 channels: one CTA per SM of independent 64-thread workers
 int launch_k3_streams(const K3Params& p, Stream* s, std::string& err);
-// K0: physical Ogg page scan, one warp per container image
+// K0: physical Ogg page scan.  Three launches on s: the header-chain walk (one warp per image), the page CRCs of
+// the files the walk accepted (one warp per page), the serial scan of the files either of them flagged.
 int launch_k0(const K0Params& p, Stream* s, std::string& err);
 // K0g: page-end granule index of scanned images, one warp per file
 int launch_k0g(const K0gParams& p, Stream* s, std::string& err);

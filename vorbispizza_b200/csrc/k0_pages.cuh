@@ -194,16 +194,137 @@ K0_DEV void k0_scan_file(const K0Params& P, uint32_t fi, const uint32_t* sm, int
   }
 }
 
-// kernel body: warps take files from the counter
+// kernel body of the SERIAL pass: warps take files from the counter (word 3); with only_irregular set, the files the
+// fast path finished are skipped
 K0_DEV void k0_cta(const K0Params& P, uint32_t* sm) {
   const int tid = (int)threadIdx.x, lane = tid & 31;
   k0_init_tables(sm, tid);
   for (;;) {
     uint32_t fi = 0;
+    if (lane == 0) fi = atomicAdd(P.counter + 3, 1u);
+    fi = __shfl_sync(0xffffffffu, fi, 0);
+    if (fi >= P.n_files) break;
+    if (P.only_irregular && P.irregular[fi] == 0u) continue;
+    k0_scan_file(P, fi, sm, lane);
+    __syncwarp();
+  }
+}
+
+// =============================================================================================================
+// Fast path.  One warp per file is enough for thousands of small files, but it is a serial walk: a single 47 MB
+// file took 200 ms (234 MB/s).  Almost every file is ONE GAPLESS CHAIN of valid pages, and for those the work
+// splits: k0_walk follows the chain from header to header (capture pattern exactly where the previous page ended,
+// segment table and body inside the file; no CRC) and writes the page records; k0_crc then checks the CRC of every
+// such page with ALL warps of the GPU, one page per warp.  A file that is not such a chain -- garbage, a truncated
+// page, trailing bytes, or a CRC that fails -- is flagged `irregular` and scanned by the serial pass above, which
+// alone knows the reference's resynchronisation and waste accounting (PageReaderBase.cs:56-70).
+// =============================================================================================================
+K0_DEV void k0_walk_file(const K0Params& P, uint32_t fi, int lane) {
+  const VpzScanFile f = P.files[fi];
+  const uint8_t* img = P.images + f.data_off;
+  const uint32_t len = f.len;
+  VpzPageRec* out = P.pages + f.page_base;
+  uint32_t n_pages = 0, overflow = 0, pos = 0;
+  bool regular = len >= 27u;
+  while (regular && pos < len) {
+    if (pos + 27u > len) {
+      regular = false;
+      break;
+    }
+    // the 27 header bytes, one per lane
+    const uint32_t hb = lane < 27 ? (uint32_t)img[pos + (uint32_t)lane] : 0u;
+    const uint32_t want = lane == 0 ? 'O' : (lane == 1 || lane == 2 ? 'g' : 'S');
+    if ((__ballot_sync(0xffffffffu, lane < 4 && hb == want) & 0xfu) != 0xfu) {
+      regular = false;
+      break;
+    }
+    const uint32_t nseg = __shfl_sync(0xffffffffu, hb, 26);
+    if (pos + 27u + nseg > len) {
+      regular = false;
+      break;
+    }
+    uint32_t body = 0, npk = 0, last_seg = 0;
+    for (uint32_t s0 = 0; s0 < nseg; s0 += 32) {
+      const uint32_t s = s0 + (uint32_t)lane;
+      const uint32_t v = s < nseg ? (uint32_t)img[pos + 27 + s] : 0u;
+      uint32_t sum = v;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+      body += sum;
+      npk += (uint32_t)__popc(__ballot_sync(0xffffffffu, s < nseg && v < 255u));
+      if (s0 + 32 >= nseg) last_seg = __shfl_sync(0xffffffffu, v, (int)((nseg - 1u) & 31u));
+    }
+    const uint32_t total = 27u + nseg + body;
+    if (pos + total > len) {
+      regular = false;
+      break;
+    }
+    if (n_pages >= f.page_cap) {   // more pages than the caller sized for: the host scans this file itself
+      overflow = 1;
+      break;
+    }
+    if (lane == 0) {
+      const bool cont = nseg > 0 && last_seg == 255u;
+      uint4 a, b;
+      a.x = pos;
+      a.y = body;
+      a.z = k0_load_le32(img + pos + 6);
+      a.w = k0_load_le32(img + pos + 10);
+      b.x = k0_load_le32(img + pos + 14);
+      b.y = k0_load_le32(img + pos + 18);
+      b.z = (uint32_t)img[pos + 5] | (nseg << 8) | ((cont ? 1u : 0u) << 24);   // no resync in a gapless chain
+      b.w = (npk + (cont ? 1u : 0u)) & 0xffffu;
+      uint4* dst = reinterpret_cast<uint4*>(out + n_pages);
+      dst[0] = a;
+      dst[1] = b;
+      P.jobs[atomicAdd(P.counter + 1, 1u)] = VpzCrcJob{fi, pos, total, 0u};   // its CRC is checked by k0_crc
+    }
+    n_pages++;
+    pos += total;
+  }
+  if (!regular) {
+    if (lane == 0) P.irregular[fi] = 1u;   // the serial pass redoes this file and writes its records and counters
+    return;
+  }
+  if (lane == 0) {
+    uint4 a, b;
+    a.x = n_pages;
+    a.y = a.z = a.w = 0u;     // no CRC failures, no waste: otherwise the file is not regular
+    b.x = overflow;
+    b.y = b.z = b.w = 0u;
+    uint4* dst = reinterpret_cast<uint4*>(P.out + fi);
+    dst[0] = a;
+    dst[1] = b;
+  }
+}
+
+K0_DEV void k0_walk_cta(const K0Params& P) {
+  const int lane = (int)threadIdx.x & 31;
+  for (;;) {
+    uint32_t fi = 0;
     if (lane == 0) fi = atomicAdd(P.counter, 1u);
     fi = __shfl_sync(0xffffffffu, fi, 0);
     if (fi >= P.n_files) break;
-    k0_scan_file(P, fi, sm, lane);
+    k0_walk_file(P, fi, lane);
+    __syncwarp();
+  }
+}
+
+// one page per warp: a CRC that does not match flags the file
+K0_DEV void k0_crc_cta(const K0Params& P, uint32_t* sm) {
+  const int tid = (int)threadIdx.x, lane = tid & 31;
+  k0_init_tables(sm, tid);
+  const uint32_t njobs = P.counter[1];
+  for (;;) {
+    uint32_t j = 0;
+    if (lane == 0) j = atomicAdd(P.counter + 2, 1u);
+    j = __shfl_sync(0xffffffffu, j, 0);
+    if (j >= njobs) break;
+    const VpzCrcJob job = P.jobs[j];
+    const uint8_t* img = P.images + P.files[job.file].data_off;
+    const uint32_t want = k0_load_le32(img + job.offset + 22);
+    const uint32_t crc = k0_page_crc(img, job.offset, job.length, sm, lane);
+    if (crc != want && lane == 0) P.irregular[job.file] = 1u;
     __syncwarp();
   }
 }

@@ -52,7 +52,13 @@ struct K0Params {
   VpzPageRec* pages;
   VpzScanOut* out;                 // one per file
   uint32_t n_files;
-  uint32_t* counter;               // work-stealing cursor over files (zeroed before the launch)
+  uint32_t* counter;               // four zeroed words: file cursor of the walk, number of CRC jobs, job cursor, file
+                                   // cursor of the serial pass
+  // fast path (k0_walk / k0_crc): a file that is one gapless chain of pages is walked header by header, its page
+  // CRCs are checked by all warps in parallel; anything else is flagged and left to the serial pass
+  VpzCrcJob* jobs;                 // one CRC job per page the walk accepted
+  uint32_t* irregular;             // per file, zeroed: 1 = the serial pass scans this file
+  int only_irregular;              // serial pass: skip the files whose flag is 0
 };
 
 struct K4Params {

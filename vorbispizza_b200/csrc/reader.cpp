@@ -1230,7 +1230,8 @@ int64_t vpz_decode_excerpts(vpz_ctx* ctx, uint32_t n_files, const uint8_t* const
   // ---- layout of the destination -------------------------------------------------------------------
   int64_t total = 0;
   for (uint32_t i = 0; i < n; i++) {
-    if (file_of[i] >= n_files || start[i] < 0 || count[i] < 0) return VPZ_E_ARGUMENT;
+    // (count * channels is handed to Read as an int, like Span<float>.Length in the reference)
+    if (file_of[i] >= n_files || start[i] < 0 || count[i] < 0 || count[i] > INT32_MAX / VPZ_MAX_CH) return VPZ_E_ARGUMENT;
     if (dst_offsets) dst_offsets[i] = total;
     total += (int64_t)count[i] * files[file_of[i]]->master.channels();
   }

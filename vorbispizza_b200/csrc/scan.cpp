@@ -20,7 +20,7 @@ struct ScanSlot {
   // bulk pipeline's PCM copies on the copy engine (measured: 8 ms per group when it did).
   HostBuf<VpzPageRec> h_pages;
   HostBuf<VpzScanOut> h_out;
-  DevBuf d_img, d_files;
+  DevBuf d_img, d_files, d_jobs, d_irregular;   // + CRC jobs and per-file flags of the fast path (k0_walk / k0_crc)
   // K0g (granule_index): per-file parameters in, the page-end granule index out (pinned + mapped like h_pages)
   HostBuf<VpzGranFile> h_gfiles;
   DevBuf d_gfiles;
@@ -110,11 +110,14 @@ int scan_begin(vpz_ctx* ctx, int which, uint32_t n, const uint8_t* const* datas,
     pool->parallel_for(n, stage);
   else
     for (uint32_t i = 0; i < n; i++) stage(i);
-  if (!b.d_img.reserve(bytes, err) || !b.d_files.reserve(n * sizeof(VpzScanFile), err)) return VPZ_E_CUDA;
+  if (!b.d_img.reserve(bytes, err) || !b.d_files.reserve(n * sizeof(VpzScanFile), err) ||
+      !b.d_jobs.reserve(pages * sizeof(VpzCrcJob), err) || !b.d_irregular.reserve((size_t)n * 4, err))
+    return VPZ_E_CUDA;
   int rc;
   if ((rc = dev::h2d(b.d_img.p, b.h_img.p, bytes, stream, err))) return rc;
   if ((rc = dev::h2d(b.d_files.p, b.h_files.p, n * sizeof(VpzScanFile), stream, err))) return rc;
-  if ((rc = dev::fill(b.d_counter, 0, 4, stream, err))) return rc;
+  if ((rc = dev::fill(b.d_counter, 0, 16, stream, err))) return rc;
+  if ((rc = dev::fill(b.d_irregular.p, 0, (size_t)n * 4, stream, err))) return rc;
   K0Params p;
   p.images = static_cast<const uint8_t*>(b.d_img.p);
   p.files = static_cast<const VpzScanFile*>(b.d_files.p);
@@ -122,8 +125,11 @@ int scan_begin(vpz_ctx* ctx, int which, uint32_t n, const uint8_t* const* datas,
   p.out = b.h_out.p;
   p.n_files = n;
   p.counter = b.d_counter;
+  p.jobs = static_cast<VpzCrcJob*>(b.d_jobs.p);
+  p.irregular = static_cast<uint32_t*>(b.d_irregular.p);
+  p.only_irregular = 0;
   if ((rc = dev::launch_k0(p, stream, err))) return rc;
-  ctx->kernel_launches++;
+  ctx->kernel_launches += 3;
   dev::event_record(b.done, stream);
   b.in_flight = true;
   return VPZ_OK;

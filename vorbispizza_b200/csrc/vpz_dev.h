@@ -209,6 +209,9 @@ struct alignas(16) VpzPageRec {   // one valid page (PageReaderBase.VerifyPage p
   uint16_t packet_count;    // PageHeader.GetPacketCount (Ogg/PageHeader.cs:35-59)
   uint16_t pad;
 };
+struct alignas(16) VpzCrcJob {    // fast path of K0: one page whose CRC is still to be checked
+  uint32_t file, offset, length, pad;
+};
 struct alignas(16) VpzScanOut {
   uint32_t n_pages, crc_failures;
   uint32_t waste_lo, waste_hi;   // bytes that belong to no valid page
