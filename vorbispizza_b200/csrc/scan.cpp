@@ -200,8 +200,13 @@ extern "C" int64_t vpz_scan_pages(vpz_ctx* ctx, uint32_t n, const uint8_t* const
   if (!ctx || (n && (!datas || !lens))) return VPZ_E_ARGUMENT;
   VPZ_USE(ctx);
   static_assert(sizeof(vpz_page_info) == sizeof(VpzPageRec), "vpz_page_info mirrors VpzPageRec");
+  if (!ctx->pool && n > 16) {   // staging many images is a parallel memcpy
+    unsigned t = ctx->host_threads > 0 ? (unsigned)ctx->host_threads
+                                       : std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+    ctx->pool = new (std::nothrow) ThreadPool(t);
+  }
   ScanResult r;
-  int rc = scan_pages(ctx, n, datas, lens, nullptr, &r);
+  int rc = scan_pages(ctx, n, datas, lens, n > 16 ? ctx->pool : nullptr, &r);
   if (rc) return rc;
   int64_t total = 0;
   for (uint32_t i = 0; i < n; i++) {
