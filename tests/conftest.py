@@ -33,6 +33,10 @@ def load_file(name):
 
 @pytest.fixture(scope="session")
 def emu_lib_path():
+    # VPZ_EMU_LIB: another build of the emulated library (e.g. one compiled with -fsanitize=address and run with
+    # LD_PRELOAD=libasan.so: out-of-bounds accesses of the kernels show up as host heap errors)
+    if os.environ.get("VPZ_EMU_LIB"):
+        return os.environ["VPZ_EMU_LIB"]
     d = os.path.join(ROOT, "tests", "emu")
     subprocess.check_call(["make", "-C", d, "-s"])
     return os.path.join(d, "libvpz_emu.so")
