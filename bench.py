@@ -696,6 +696,27 @@ def main():
                "d2h_bytes_per_step": (lib.vpz_transfer_bytes(1) - d0) // e_steps,
                "ms_per_step": 1e3 * t_e2e / e_steps, "steps": e_steps,
                "api": "vpz_decode_files (host Ogg images -> pinned host PCM)"}
+        if not dry:
+            # copy-only ceiling of exactly this destination: the whole pinned PCM buffer filled once from the device in
+            # the pieces the pipeline uses (512 MiB), all ranks at once -- the 1 GiB probe below re-uses one small
+            # buffer, which the IOMMU / TLBs of some boxes serve faster than 8 GB of fresh pages
+            import torch
+            piece = 512 << 20
+            src = torch.empty(piece, dtype=torch.uint8, device="cuda")
+            view = torch.frombuffer((C.c_uint8 * (e_total * 4)).from_address(dst_p), dtype=torch.uint8)
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for off in range(0, e_total * 4, piece):
+                    n_b = min(piece, e_total * 4 - off)
+                    view[off:off + n_b].copy_(src[:n_b], non_blocking=True)
+                e1.record(st)
+                e1.synchronize()
+            t_dst = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+            e2e["link_gbs_into_pcm_buffer"] = sum_over_ranks(float(e_total * 4)) / t_dst / 1e9
+            del view, src
         lib.vpz_host_free(dst_p)
         # the same call with 16-bit output (conversion fused into the IMDCT kernel, half the
         # device-to-host bytes) -- reported beside the fp32 number, which stays the headline
@@ -722,6 +743,8 @@ def main():
                 e2e["link_gbs_measured"] = link
                 e2e["d2h_gbs_in_e2e"] = d2h_rate
                 e2e["frac_of_link"] = d2h_rate / link
+                if e2e.get("link_gbs_into_pcm_buffer"):
+                    e2e["frac_of_link_into_pcm_buffer"] = d2h_rate / e2e["link_gbs_into_pcm_buffer"]
                 e2e["link_probe"] = "1 GiB device buffer -> pinned host, back to back for ~1 s, %d rank(s) at once" % world
 
     # ---- cpu baseline (rank 0, N=1): the oracle on all host cores, bounded sample ----------------
