@@ -97,6 +97,9 @@ static int finish_setup(vpz_ctx* ctx, vpz_setup* s) {
         // not straddle partitions and every VQ dimension must be a power of two that divides the chunk
         const int chunk = rs[i].type == 2 && C == 2 ? 16 : 8;
         if ((rs[i].begin % chunk) || (rs[i].part_size % chunk)) ok = false;
+        // K1b's phase B scans the entry counts of two stages in one 32-bit prefix sum: 32 units of a stage
+        // must stay below 2^16 entries (a unit has at most part_size of them)
+        if (rs[i].part_size > 2047) ok = false;
         max_stages = std::max<int>(max_stages, rs[i].max_stages);
         for (int c = 0; c < rs[i].classifications && ok; c++)
           for (int sg = 0; sg < 8 && ok; sg++)

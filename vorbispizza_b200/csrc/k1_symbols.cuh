@@ -1332,6 +1332,13 @@ struct K1bPkt {
 #ifndef K1B_GRAB
 #define K1B_GRAB 8
 #endif
+// 1: phase B scans the entry counts of two stages in one 32-bit prefix sum
+#ifndef K1B_PIN_REGS
+#define K1B_PIN_REGS 1
+#endif
+#ifndef K1B_SCAN2
+#define K1B_SCAN2 1
+#endif
 
 VPZ_DEV void k1b_prefetch_packet(const K1Params& P, uint32_t rec_off, uint32_t ent_off, uint32_t byte_len, int lane) {
 #ifndef VPZ_EMU
@@ -1478,6 +1485,39 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
         if (!((g.skip >> v) & 1u)) c = rec_cls[u];
       }
       const uint2* ut = reinterpret_cast<const uint2*>(blob + rs->unit_tabb_off) + (c < 0 ? 0 : c) * 8;
+#if K1B_SCAN2
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        cnt[s] = 0;
+        info[s] = vqo[s] = 0;
+        if (s < max_stages && c >= 0) {   // {dims | log2 dims << 8 | entries << 16, vq word offset}; 0: no codewords for (class, stage)
+          const uint2 t = VPZ_LDG(ut + s);
+          info[s] = t.x & 0xffffu;
+          cnt[s] = (int)(t.x >> 16);
+          vqo[s] = t.y;
+        }
+      }
+      // two stages per prefix sum, 16 bits each: a unit holds <= part_size <= 2047 entries (engine.cpp), so the
+      // 32 lanes of a round stay below 2^16 and no field carries into its neighbour
+#pragma unroll
+      for (int s = 0; s < 8; s += 2) {
+        if (s < max_stages) {
+          const uint32_t both = (uint32_t)cnt[s] | ((uint32_t)cnt[s + 1] << 16);
+          uint32_t incl = both;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += n;
+          }
+          const uint32_t round_total = __shfl_sync(0xffffffffu, incl, 31);
+          const uint32_t excl = incl - both;
+          cnt[s] = carry[s] + (int)(excl & 0xffffu);   // first entry of the unit inside the stage
+          cnt[s + 1] = carry[s + 1] + (int)(excl >> 16);
+          carry[s] += (int)(round_total & 0xffffu);
+          carry[s + 1] += (int)(round_total >> 16);
+        }
+      }
+#else
 #pragma unroll
       for (int s = 0; s < 8; s++) {
         cnt[s] = 0;
@@ -1500,6 +1540,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
           carry[s] += round_total;
         }
       }
+#endif
       // a unit is active when any stage has codewords for its class (info holds the dimension: never 0 then)
       const uint32_t act = __ballot_sync(0xffffffffu, (info[0] | info[1] | info[2] | info[3] | info[4] | info[5] | info[6] | info[7]) != 0u);
       if (act) act_units = u0 + 32 - __clz((int)act);
@@ -1669,7 +1710,8 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
 template <bool DEBUG>
 VPZ_DEV void k1b_gather_loop(const K1Params& P, uint32_t* smem) {
   const int tid = (int)threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
+  int lane = tid & 31;
+  const int warp = tid >> 5;
   // inverse_dB_table (Floor1.cs:407-473): identical in every setup image, staged once per CTA
   float* dbtab = reinterpret_cast<float*>(smem);
   {
@@ -1678,7 +1720,17 @@ VPZ_DEV void k1b_gather_loop(const K1Params& P, uint32_t* smem) {
     for (int i = tid; i < 256; i += K1B_THREADS) dbtab[i] = VPZ_LDG(db + i);
   }
   __syncthreads();
+#if K1B_PIN_REGS && !defined(VPZ_EMU)
+  // At 56 registers the compiler re-derived the lane and the warp's shared-memory base from threadIdx wherever
+  // they were used (56 S2R per packet, a tenth of the kernel's instructions on these three source lines): opaque
+  // values cannot be rematerialised
+  uint32_t woff = 256u + (uint32_t)warp * P.smem_words_per_warp;
+  asm volatile("" : "+r"(woff));
+  asm volatile("" : "+r"(lane));
+  uint32_t* my = smem + woff;
+#else
   uint32_t* my = smem + 256 + (size_t)warp * P.smem_words_per_warp;
+#endif
   for (;;) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(P.counter, (uint32_t)K1B_GRAB);

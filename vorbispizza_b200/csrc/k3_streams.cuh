@@ -44,6 +44,69 @@
 #define K3S_END16(rw, c) 255
 #endif
 
+// 1: the spectrum of the coming long block arrives by bulk copies (cp.async.bulk + mbarrier, one elected
+// thread per group): channel 0 into the transpose scratch -- in the 72-strided layout of the first transpose,
+// so every thread reads back exactly the words it will overwrite and no extra barrier is needed -- and
+// channel 1 into its own free D slots.  0: channel 0 in registers (8 LDG.64 per thread, live across the output
+// loop), channel 1 by per-thread 16-byte cp.async.
+#ifndef K3S_BULK
+#define K3S_BULK 0
+#endif
+// 1: the global packet index (needed only when a packet clipped) is rebuilt from shared memory instead of being
+// carried -- and spilled -- through the packet loop
+// 1: per-item values the packet loop needs once per packet (output base) live in shared memory, the window slopes of
+// the rare general output path come from the staged tables instead of two global pointers
+#ifndef K3S_LEAN
+#define K3S_LEAN 1
+#endif
+#ifndef K3S_PIN_REGS
+#define K3S_PIN_REGS 0
+#endif
+#ifndef K3S_GP_SMEM
+#define K3S_GP_SMEM 1
+#endif
+#define K3S_MBAR_FLOAT 176       // two mbarriers (channel 0, channel 1) in the unused tail of the descriptor area
+
+#ifndef VPZ_EMU
+VPZ_DEV unsigned k3s_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+VPZ_DEV void k3s_mbar_init(uint64_t* b) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(k3s_saddr(b)) : "memory");
+}
+VPZ_DEV void k3s_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// the scratch / D slots were last read through the generic proxy (ordered by the group barrier before this point)
+VPZ_DEV void k3s_bulk_begin(uint64_t* b, unsigned bytes) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k3s_saddr(b)), "r"(bytes) : "memory");
+}
+VPZ_DEV void k3s_proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+VPZ_DEV void k3s_bulk(float* dst_smem, const float* src, unsigned bytes, uint64_t* b) {   // 16-byte aligned, bytes % 16 == 0
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(k3s_saddr(dst_smem)),
+               "l"(src), "r"(bytes), "r"(k3s_saddr(b))
+               : "memory");
+}
+VPZ_DEV void k3s_mbar_wait(uint64_t* b, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}" ::"r"(k3s_saddr(b)),
+      "r"(parity)
+      : "memory");
+}
+#else
+// emulator: the copy happens at issue; the consumer is always behind a group barrier
+VPZ_DEV void k3s_mbar_init(uint64_t*) {}
+VPZ_DEV void k3s_mbar_init_fence() {}
+VPZ_DEV void k3s_bulk_begin(uint64_t*, unsigned) {}
+VPZ_DEV void k3s_proxy_fence() {}
+VPZ_DEV void k3s_bulk(float* dst_smem, const float* src, unsigned bytes, uint64_t*) { memcpy(dst_smem, src, bytes); }
+VPZ_DEV void k3s_mbar_wait(uint64_t*, unsigned) {}
+#endif
+
 #ifndef VPZ_EMU
 VPZ_DEV void k3s_cp16(float* dst_smem, const float* src) {
   const unsigned a = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -110,19 +173,23 @@ VPZ_DEV bool k3s_emit_same_size(const float* hi0 /* D[M/2..] of channel 0 */, co
 
 // one work item, C = 1 or 2 channels, by one 64-thread group.  OUT16: 16-bit PCM (k3_s16) instead of fp32
 template <bool OUT16, bool ENDS>
-VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs, float* gbase, int grp, int t64) {
+VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs, float* gbase, int grp, int t64, unsigned& mph, const K3TwRegs& twr) {
   const VpzOlaItem it = item;  // the item lives in global memory: read it once
   const uint32_t* blob = P.setups[it.setup_slot];
   const VpzSetupHdr* Hd = reinterpret_cast<const VpzSetupHdr*>(blob);
   const int C = Hd->channels;
   const int t = k3_remap64(t64);
+#if !K3S_LEAN
   const float* slope0 = reinterpret_cast<const float*>(blob + Hd->slope_off[0]);
   const float* slope1 = reinterpret_cast<const float*>(blob + Hd->slope_off[1]);
+#endif
   VpzPktOla* spk = reinterpret_cast<VpzPktOla*>(gbase);                       // [K3S_DESC_PKTS] descriptors
   uint32_t* smask = reinterpret_cast<uint32_t*>(gbase) + 4 * K3S_DESC_PKTS;    // [K3S_DESC_PKTS] exec masks
   volatile int* snb = reinterpret_cast<volatile int*>(gbase) + (K3S_DESC_FLOATS - 2);   // packets staged in this batch
   float* T = gbase + K3S_DESC_FLOATS;
   float* Dch = T + 2 * K3_PLANE;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(gbase + K3S_MBAR_FLOAT);   // [0]: channel 0, [1]: channel 1; phases in mph
+  (void)mbar;
   const cpx* tab = reinterpret_cast<const cpx*>(tabs);
   const cpx* tw_s = reinterpret_cast<const cpx*>(tabs + K3S_TAB_S_TW);
   const cpx* w64_s = reinterpret_cast<const cpx*>(tabs + K3S_TAB_S_W64);
@@ -139,7 +206,15 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
     const int nb = (total - pb) < K3S_DESC_PKTS ? (total - pb) : K3S_DESC_PKTS;
     // descriptors + exec masks of the next nb packets: one parallel fetch
     K3_GSYNC(grp);
-    if (t64 == 0) snb[0] = nb;
+    if (t64 == 0) {
+      snb[0] = nb;
+#if K3S_LEAN
+      *reinterpret_cast<volatile unsigned long long*>(snb - 4) = (unsigned long long)it.out_base;   // read back per packet
+#endif
+#if K3S_GP_SMEM
+      snb[-1] = first + pb;   // global index of the batch's first packet (only a clipped packet needs it)
+#endif
+    }
     if (t64 < nb) {
       spk[t64] = P.pkts[first + pb + t64];
       // exec mask | status << 8 | end16[0] << 16 | end16[1] << 24 (VpzPktRes); no K1: every channel, every bin
@@ -150,7 +225,9 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
     // packet missed L1 (7.6 % of the kernel's stall samples on one compare)
     for (int pw = 0; pw < snb[0]; pw++, parity ^= 1) {
       const int pi = pb + pw;
+#if !K3S_GP_SMEM
       const uint32_t gp = (uint32_t)(first + pi);
+#endif
       const VpzPktOla pk = spk[pw];
       const uint32_t rw = ENDS ? smask[pw] : 0xffff00ffu;
       const uint32_t mask = rw & 0xffu;
@@ -208,12 +285,31 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
           // a channel without floor energy outputs zeros (Mapping.cs:185-194) but still takes part in
           // the overlap-add: its D slots are cleared instead of transformed
           for (int i = t64; i < M; i += K3_THREADS_PER_CH) *k3_dp(D, i) = 0.f;
+#if !(K3S_BULK & 1)
           k3s_cp_wait();
+#endif
           K3_GSYNC(grp);
         } else {
+#if K3S_BULK & 2
+          if (c == 0 && xr_valid) {
+            // channel 0's spectrum was bulk-copied into the transpose scratch during the previous packet's
+            // output, chunk q (64 pairs) at complex offset 72 q: thread t reads T2[72 q + t], the very words it
+            // writes in the first transpose
+            k3s_mbar_wait(mbar, mph & 1u);
+            mph ^= 1u;
+            const int end2 = K3S_END16(rw, 0) * 8;
+            const float2* T2 = reinterpret_cast<const float2*>(T);
+#pragma unroll
+            for (int q = 0; q < 8; q++) xr[q] = 64 * q < end2 ? T2[72 * q + t] : float2{0.f, 0.f};
+          } else
+#endif
           if (c == 1 && staged) {
             // channel 1's spectrum was copied into its own Hi / Lo[parity] slots after the previous
             // packet's output (made visible by the barrier that ended channel 0's transform)
+#if K3S_BULK & 1
+            k3s_mbar_wait(mbar + 1, (mph >> 1) & 1u);
+            mph ^= 2u;
+#endif
 #pragma unroll
             for (int q = 0; q < 8; q++) {
               const int n2 = 2 * (t + 64 * q);
@@ -222,9 +318,11 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
           } else if (!(c == 0 && xr_valid)) {
             k3_load_x(X, t, xr, K3S_END16(rw, c) * 8);
           }
-          fft512_to_D(xr, T, D, tab, t, grp);
+          fft512_to_D(xr, T, D, tab, t, grp, twr);
           if (c == 0) xr_valid = false;
+#if !(K3S_BULK & 1)
           k3s_cp_wait();
+#endif
           K3_GSYNC(grp);   // D complete, scratch reusable, staged channel-1 spectrum visible
         }
         if (P.dbg_imdct) {
@@ -236,7 +334,21 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
 
       // channel 0 of the next long block is requested now and lands during the output loop
       if (next_long && (mask_next & 1u)) {
+#if K3S_BULK & 2
+        // every transform above ended with a group barrier: the scratch is free until the next transform
+        if (t64 < 8) {   // lane q issues chunk q
+          int nq = (K3S_END16(rw_next, 0) * 8 + 63) >> 6;   // 64-pair chunks that were written (<= 8)
+          nq = nq < 8 ? nq : 8;
+          const float* Xn = P.spec + pk_next.spec_off;
+          if (t64 == 0) k3s_bulk_begin(mbar, 512u * (unsigned)nq);
+          if (t64 < nq) {
+            if (t64 != 0) k3s_proxy_fence();
+            k3s_bulk(T + 144 * t64, Xn + 128 * t64, 512u, mbar);
+          }
+        }
+#else
         k3_load_x(P.spec + pk_next.spec_off, t, xr, K3S_END16(rw_next, 0) * 8);
+#endif
         xr_valid = true;
       }
       // ---- output: window + overlap-add + clip, all channels interleaved ----------------------------
@@ -246,7 +358,11 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
         const int L = prev_re - prev_rs;             // StreamDecoder.cs:654
         // element offset of the packet's first sample; an s16 element is 2 bytes, so the float-typed base
         // advances by half the element offset (out_base and out_off * C are element counts)
+#if K3S_LEAN
+        const size_t eoff = (size_t)*reinterpret_cast<volatile const unsigned long long*>(snb - 4) + (size_t)pk.out_off * C;
+#else
         const size_t eoff = (size_t)it.out_base + (size_t)pk.out_off * C;
+#endif
         float* outp = OUT16 ? reinterpret_cast<float*>(reinterpret_cast<int16_t*>(P.pcm) + eoff) : P.pcm + eoff;
         const float* Dp_lo = Dch + 512 + (parity ^ 1) * 512;
         bool clipped;
@@ -265,7 +381,12 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
           else
             clipped = clip ? k3s_emit_same_size<1, true, OUT16, 128>(Dch, Dp_lo, ws, outp, t64) : k3s_emit_same_size<1, false, OUT16, 128>(Dch, Dp_lo, ws, outp, t64);
         } else {
+#if K3S_LEAN
+          // every setup of this launch has the block sizes 256 / 2048: both window slopes are in the staged tables
+          const float* w = tabs + ((pk.flags & VPZ_OLA_LEFT1) ? K3_TAB_SLOPE : K3S_TAB_S_SLOPE);
+#else
           const float* w = (pk.flags & VPZ_OLA_LEFT1) ? slope1 : slope0;
+#endif
           const float* Dc_hm = Dch - h;
           const float* Dc_lo = Dch + 512 + parity * 512;
           if (C == 2)
@@ -276,7 +397,11 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
                            : k3_emit<1, false, OUT16>(Dc_hm, Dc_lo, Dp_lo, K3S_CH_FLOATS, M, prevM, ls, count, prev_rs, L, w, outp, C, t64, K3_THREADS_PER_CH);
         }
         // per packet: 0 when any sample was clamped (HasClipped), else stays 0xffffffff
+#if K3S_GP_SMEM
+        if (P.clip_first && clipped) atomicMin(P.clip_first + (uint32_t)(snb[-1] + pw), 0u);
+#else
         if (P.clip_first && clipped) atomicMin(P.clip_first + gp, 0u);
+#endif
       }
       prevM = M;
       prev_rs = pk.right_start;
@@ -291,7 +416,22 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
         const float* Xn = P.spec + pk_next.spec_off + 1024;
         float* hi = Dch + K3S_CH_FLOATS;
         float* lo = hi + 512 + (parity ^ 1) * 512;
-        const int end4 = K3S_END16(rw_next, 1) * 4;   // float4 groups that were written (the rest is +0)
+        int end4 = K3S_END16(rw_next, 1) * 4;   // float4 groups that were written (the rest is +0)
+#if K3S_BULK & 1
+        end4 = end4 > 256 ? 256 : ((end4 + 31) & ~31);   // whole 128-bin units, as K1b fills them
+        if (t64 == 0) {
+          const unsigned nh = (unsigned)(end4 < 128 ? end4 : 128), nl = (unsigned)(end4 - (int)nh);
+          k3s_bulk_begin(mbar + 1, 16u * (nh + nl));
+          if (nh) k3s_bulk(hi, Xn, 16u * nh, mbar + 1);
+          if (nl) k3s_bulk(lo, Xn + 512, 16u * nl, mbar + 1);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          const int i4 = t64 + 64 * r;
+          float* dst = i4 < 128 ? hi + 4 * i4 : lo + 4 * (i4 - 128);
+          if (i4 >= end4) *reinterpret_cast<float4*>(dst) = float4{0.f, 0.f, 0.f, 0.f};
+        }
+#else
 #pragma unroll
         for (int r = 0; r < 4; r++) {
           const int i4 = t64 + 64 * r;
@@ -301,18 +441,21 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
           else
             *reinterpret_cast<float4*>(dst) = float4{0.f, 0.f, 0.f, 0.f};
         }
+#endif
         staged = true;
       }
     }
   }
+#if !(K3S_BULK & 1)
   k3s_cp_wait();
+#endif
 }
 
 // kernel body: `groups` = blockDim.x / 64 workers per CTA
 template <bool OUT16, bool ENDS>
 VPZ_DEV void k3s_cta(const K3Params& P, float* smem) {
   const int tid = threadIdx.x;
-  const int grp = tid / K3_THREADS_PER_CH, t64 = tid % K3_THREADS_PER_CH;
+  int grp = tid / K3_THREADS_PER_CH, t64 = tid % K3_THREADS_PER_CH;
   const int nthreads = blockDim.x;
   {
     // the tables depend on the two block sizes only (256 / 2048 for every setup of this launch)
@@ -343,15 +486,31 @@ VPZ_DEV void k3s_cta(const K3Params& P, float* smem) {
     }
     for (int i = tid; i < 128; i += nthreads) smem[K3S_TAB_S_SLOPE + i] = VPZ_LDG(slope0 + i);
   }
-  __syncthreads();
+#if K3S_PIN_REGS && !defined(VPZ_EMU)
+  // opaque copies: the compiler otherwise re-derives the group (barrier id) and the thread index from threadIdx
+  // at every use inside the packet loop
+  asm volatile("" : "+r"(grp));
+  asm volatile("" : "+r"(t64));
+#endif
   float* gbase = smem + K3S_TAB_FLOATS + grp * K3S_GROUP_FLOATS;
+  unsigned mph = 0;   // phase bits of the group's two mbarriers
+#if K3S_BULK
+  if (t64 == 0) {
+    k3s_mbar_init(reinterpret_cast<uint64_t*>(gbase + K3S_MBAR_FLOAT));
+    k3s_mbar_init(reinterpret_cast<uint64_t*>(gbase + K3S_MBAR_FLOAT) + 1);
+    k3s_mbar_init_fence();
+  }
+#endif
+  __syncthreads();
   uint32_t* slot = reinterpret_cast<uint32_t*>(gbase) + (K3S_DESC_FLOATS - 1);
+  K3TwRegs twr;
+  k3_tw_regs_load(twr, reinterpret_cast<const cpx*>(smem), k3_remap64(t64));
   for (;;) {
     K3_GSYNC(grp);
     if (t64 == 0) *slot = atomicAdd(P.counter, 1u);
     K3_GSYNC(grp);
     const uint32_t idx = *slot;
     if (idx >= P.n_items) break;
-    k3s_run_item<OUT16, ENDS>(P, P.items[idx], smem, gbase, grp, t64);
+    k3s_run_item<OUT16, ENDS>(P, P.items[idx], smem, gbase, grp, t64, mph, twr);
   }
 }
