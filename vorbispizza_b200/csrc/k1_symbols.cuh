@@ -277,7 +277,11 @@ VPZ_DEV K1ResGeom k1_res_geom(const VpzResidue* rs, int C, int half, uint32_t no
   int end = (int)rs->end < g.vlen ? (int)rs->end : g.vlen;
   int n = end - g.begin;
   g.psize = (int)rs->part_size;
-  g.part_count = n > 0 ? n / g.psize : 0;
+  // partition sizes are powers of two in every stream an encoder has produced: a shift instead of the ~20
+  // instructions of an integer division (same quotient)
+  if (n <= 0) g.part_count = 0;
+  else if ((g.psize & (g.psize - 1)) == 0) g.part_count = n >> (31 - __clz(g.psize));
+  else g.part_count = n / g.psize;
   g.any = false;
   for (int v = 0; v < g.nvec; v++) g.any |= !((g.skip >> v) & 1u);
   return g;
@@ -1394,8 +1398,16 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
   const int max_stages = rs->max_stages;
 
   uint32_t* urec = smem;
+#if K1B_PIN_REGS >= 2 && !defined(VPZ_EMU)
+  uint32_t yoff = (uint32_t)max_stages * (uint32_t)U * 2u, sgoff = yoff + (uint32_t)(C * half_max) / 4u;
+  asm volatile("" : "+r"(yoff));
+  asm volatile("" : "+r"(sgoff));
+  uint8_t* ybuf = reinterpret_cast<uint8_t*>(urec + yoff);   // [C][half_max] bytes
+  uint32_t* sgbase = urec + sgoff;                            // [C][4*66]
+#else
   uint8_t* ybuf = reinterpret_cast<uint8_t*>(urec + (size_t)max_stages * U * 2);   // [C][half_max] bytes
   uint32_t* sgbase = reinterpret_cast<uint32_t*>(ybuf) + (C * half_max) / 4;        // [C][4*66]
+#endif
 
   K1Gather G;
   G.urec = urec;
@@ -1430,6 +1442,9 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
     if (!((own_mask >> ch) & 1u)) continue;
     const uint32_t* seg = rec + K1_REC_HDR + ch * K1_SEG_WORDS;
     uint32_t* sg = sgbase + ch * P.seg_stride;
+    // the points of the first 32 segments are requested together with the count (the record has room for 67 points
+    // per channel whatever the count says): one memory round trip instead of two dependent ones
+    const uint32_t sp0 = seg[1 + tid], sp1 = seg[2 + tid];
     const int nseg = (int)seg[0];
     int carry = 0;
     for (int s0 = 0; s0 < nseg; s0 += 32) {   // uniform trip count: every lane takes part in the scan
@@ -1437,7 +1452,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
       int np = 0;
       uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
       if (s < nseg) {
-        const uint32_t p0 = seg[1 + s], p1 = seg[2 + s];
+        const uint32_t p0 = s0 == 0 ? sp0 : seg[1 + s], p1 = s0 == 0 ? sp1 : seg[2 + s];
         const int x0 = (int)(p0 & 0xffffu), y0 = (int)(short)(p0 >> 16);
         const int x1 = (int)(p1 & 0xffffu), y1 = (int)(short)(p1 >> 16);
         const int dy = y1 - y0, adx = x1 - x0;
@@ -1464,7 +1479,8 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
       }
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (ch == 0) npieces0 = carry; else npieces1 = carry;
+    // pieces | segments << 16: phase C needs both
+    if (ch == 0) npieces0 = carry | (nseg << 16); else npieces1 = carry | (nseg << 16);
   }
   __syncwarp();
 
@@ -1481,7 +1497,7 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
       uint32_t info[8], vqo[8];
       int c = -1;
       if (u < nunits) {
-        const int part = u / g.nvec, v = u - part * g.nvec;
+        const int v = g.nvec == 2 ? (u & 1) : 0;   // the gather path has one or two vectors
         if (!((g.skip >> v) & 1u)) c = rec_cls[u];
       }
       const uint2* ut = reinterpret_cast<const uint2*>(blob + rs->unit_tabb_off) + (c < 0 ? 0 : c) * 8;
@@ -1607,9 +1623,9 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
     if (!((own_mask >> ch) & 1u)) continue;
     const uint32_t* sg = sgbase + ch * P.seg_stride;
     uint8_t* yb = ybuf + ch * half_max;
-    const int nseg = (int)rec[K1_REC_HDR + ch * K1_SEG_WORDS];
+    const int np_ns = ch == 0 ? npieces0 : npieces1;
 #if !(defined(K1B_ABLATE) && (K1B_ABLATE & 1))
-    k1b_render_floor(sg, nseg, ch == 0 ? npieces0 : npieces1, yb, res_end, tid);
+    k1b_render_floor(sg, np_ns >> 16, np_ns & 0xffff, yb, res_end, tid);
 #endif
   }
   __syncwarp();
