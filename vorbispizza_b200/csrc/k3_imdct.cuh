@@ -48,12 +48,46 @@ VPZ_DEV float* k3_dp(const K3D& d, int i) { return (i < d.h ? d.lo : d.hm) + i; 
 #endif
 
 typedef float2 cpx;
+// 1: complex multiplies and the W8 rotations of the 8-point DFT in packed fp32 (Blackwell FMUL2 / FFMA2).  A packed
+// operand may be a scalar broadcast (`R.F32`) or a register pair with its halves swapped and one half negated
+// (`-R.F32x2.LO_HI.NP`), so a * b = (a.x, a.y) * b.x + (-a.y, a.x) * b.y is TWO instructions instead of four and
+// needs no moves: ptxas folds the pack / swap / negate of the inline PTX below into the operand modifiers.
+// Only the transform uses it (results within the IMDCT tolerance, same contraction as the scalar code: one rounded
+// product, one fused multiply-add); the overlap-add keeps its scalar, explicitly rounded form.
+#ifndef K3_PACKED_MUL
+#define K3_PACKED_MUL 1
+#endif
+#if !defined(VPZ_EMU) && K3_PACKED_MUL
+VPZ_DEV unsigned long long k3_pk(float a, float b) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+VPZ_DEV float2 k3_up(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0,%1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+VPZ_DEV float2 cmul(float2 a, float2 b) {
+  unsigned long long p, r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p) : "l"(k3_pk(a.x, a.y)), "l"(k3_pk(b.x, b.x)));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(k3_pk(-a.y, a.x)), "l"(k3_pk(b.y, b.y)), "l"(p));
+  return k3_up(r);
+}
+VPZ_DEV float2 cscale(float2 a, float h) {   // a * h
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(k3_pk(a.x, a.y)), "l"(k3_pk(h, h)));
+  return k3_up(r);
+}
+#else
 VPZ_DEV cpx cmul(cpx a, cpx b) {
   cpx r;
   r.x = a.x * b.x - a.y * b.y;
   r.y = a.x * b.y + a.y * b.x;
   return r;
 }
+VPZ_DEV cpx cscale(cpx a, float h) { return cpx{a.x * h, a.y * h}; }
+#endif
 #ifndef VPZ_EMU
 // Blackwell packed fp32: one FADD2 adds both parts of a complex number (a float2 already sits in an
 // aligned register pair, so no moves are needed); same round-to-nearest result as two FADDs.
@@ -93,8 +127,10 @@ VPZ_DEV void dft8(cpx* v) {
   cpx c0 = cadd(a4, a6), c2 = cmul_mi(csub(a4, a6));  // odd part, 4-point DFT of (v1,v3,v5,v7)
   cpx c1 = cadd(a5, a7), c3 = csub(a5, a7);
   // twiddles W8^1 = (1-i)/sqrt2, W8^2 = -i (already applied to c2), W8^3 = (-1-i)/sqrt2
-  cpx d1 = cpx{h * (c1.x + c1.y), h * (c1.y - c1.x)};
-  cpx d3 = cpx{h * (c3.y - c3.x), -h * (c3.x + c3.y)};
+  // d1 = c1 * (1 - i) / sqrt2 = h * (c1 + (c1.y, -c1.x)),  d3 = c3 * (-1 - i) / sqrt2 = h * ((c3.y, -c3.x) - c3):
+  // one (packed) add and one (packed) scaling each, the same rounded sums and products as the scalar form
+  cpx d1 = cscale(cadd(c1, cmul_mi(c1)), h);
+  cpx d3 = cscale(csub(cmul_mi(c3), c3), h);
   v[0] = cadd(b0, c0);
   v[4] = csub(b0, c0);
   v[1] = cadd(b1, d1);
@@ -247,6 +283,91 @@ VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* ta
     // 2p < 512: both values lie in the low half, else in the high half
     float* dst = (k3 < 4 ? D.lo : D.hm) + 2 * p;
     *reinterpret_cast<float2*>(dst) = float2{v[k3].x, odd};
+  }
+}
+
+// Both channels of a stereo long block in ONE pass (K3S_PAIR): the same statements as fft512_to_D on two independent
+// register sets and two transpose scratches.  Every twiddle is loaded once for both channels, the group barriers are
+// shared (3 per block instead of 6), and twice as many independent loads / multiplies are in flight per thread between
+// them -- the workers wait on exactly these chains.
+VPZ_DEV void fft512_pair_to_D(const float2* xa, const float2* xb, float* Ta, float* Tb, const K3D& Da, const K3D& Db,
+                              const cpx* tab, int t, int grp) {
+  const cpx* tw = tab + K3_TAB_TW;
+  cpx v[8], u[8];
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    v[q].x = xa[q].x;
+    v[q].y = __shfl_xor_sync(0xffffffffu, xa[7 - q].y, 31);
+    u[q].x = xb[q].x;
+    u[q].y = __shfl_xor_sync(0xffffffffu, xb[7 - q].y, 31);
+  }
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    const cpx w = tw[t + 64 * q];
+    v[q] = cmul(v[q], w);
+    u[q] = cmul(u[q], w);
+  }
+  dft8(v);
+  dft8(u);
+#pragma unroll
+  for (int k = 1; k < 8; k++) {
+    const cpx w = tab[K3_TAB_W1 + (k - 1) * 64 + t];
+    v[k] = cmul(v[k], w);
+    u[k] = cmul(u[k], w);
+  }
+  cpx* A2 = reinterpret_cast<cpx*>(Ta);
+  cpx* B2 = reinterpret_cast<cpx*>(Tb);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    A2[72 * k + t] = v[k];
+    B2[72 * k + t] = u[k];
+  }
+  K3_GSYNC(grp);
+  const int k1 = t >> 3, r2 = t & 7;
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    v[q] = A2[72 * k1 + r2 + 8 * q];
+    u[q] = B2[72 * k1 + r2 + 8 * q];
+  }
+  K3_GSYNC(grp);  // the second transpose reuses the scratches
+  dft8(v);
+  dft8(u);
+#pragma unroll
+  for (int k = 1; k < 8; k++) {
+    const cpx w = tab[K3_TAB_W2 + (k - 1) * 8 + r2];
+    v[k] = cmul(v[k], w);
+    u[k] = cmul(u[k], w);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    A2[k1 + 8 * k + 66 * r2] = v[k];
+    B2[k1 + 8 * k + 66 * r2] = u[k];
+  }
+  K3_GSYNC(grp);
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    v[r] = A2[t + 66 * r];
+    u[r] = B2[t + 66 * r];
+  }
+  dft8(v);
+  dft8(u);
+  float ny[8], my[8];
+#pragma unroll
+  for (int k3 = 0; k3 < 8; k3++) {
+    const cpx w = tw[t + 64 * k3];
+    const cpx c = cmul(v[k3], w), d = cmul(u[k3], w);
+    v[k3].x = c.x;
+    ny[k3] = -c.y;
+    u[k3].x = d.x;
+    my[k3] = -d.y;
+  }
+#pragma unroll
+  for (int k3 = 0; k3 < 8; k3++) {
+    const int p = t + 64 * k3;
+    const float odd_a = __shfl_xor_sync(0xffffffffu, ny[7 - k3], 31);
+    const float odd_b = __shfl_xor_sync(0xffffffffu, my[7 - k3], 31);
+    *reinterpret_cast<float2*>((k3 < 4 ? Da.lo : Da.hm) + 2 * p) = float2{v[k3].x, odd_a};
+    *reinterpret_cast<float2*>((k3 < 4 ? Db.lo : Db.hm) + 2 * p) = float2{u[k3].x, odd_b};
   }
 }
 

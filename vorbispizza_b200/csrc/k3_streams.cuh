@@ -24,9 +24,15 @@
 #define K3S_DESC_PKTS 32
 #define K3S_DESC_FLOATS 192      // 32 x (4 descriptor words + 1 exec mask) + work-stealing slot
 #define K3S_CH_FLOATS 1536       // D slots of one channel: Hi[512] Lo0[512] Lo1[512]
-#define K3S_GROUP_FLOATS (K3S_DESC_FLOATS + 2 * K3_PLANE + 2 * K3S_CH_FLOATS)
+// 1: both channels of a stereo long block are transformed in one pass (fft512_pair_to_D): a second transpose scratch
+// per worker, fewer workers with more registers each
+#ifndef K3S_PAIR
+#define K3S_PAIR 0
+#endif
+#define K3S_SCRATCH_FLOATS ((K3S_PAIR ? 4 : 2) * K3_PLANE)
+#define K3S_GROUP_FLOATS (K3S_DESC_FLOATS + K3S_SCRATCH_FLOATS + 2 * K3S_CH_FLOATS)
 #ifndef K3S_MAX_GROUPS
-#define K3S_MAX_GROUPS 12
+#define K3S_MAX_GROUPS (K3S_PAIR ? 9 : 12)
 #endif
 #ifndef K3S_EMIT_UNROLL
 #define K3S_EMIT_UNROLL 4
@@ -112,9 +118,14 @@ VPZ_DEV void k3s_cp16(float* dst_smem, const float* src) {
   const unsigned a = (unsigned)__cvta_generic_to_shared(dst_smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(a), "l"(src) : "memory");
 }
+VPZ_DEV void k3s_cp8(float2* dst_smem, const float2* src) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a), "l"(src) : "memory");
+}
 VPZ_DEV void k3s_cp_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 #else
 VPZ_DEV void k3s_cp16(float* dst_smem, const float* src) { memcpy(dst_smem, src, 16); }
+VPZ_DEV void k3s_cp8(float2* dst_smem, const float2* src) { memcpy(dst_smem, src, 8); }
 VPZ_DEV void k3s_cp_wait() {}
 #endif
 
@@ -187,7 +198,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
   uint32_t* smask = reinterpret_cast<uint32_t*>(gbase) + 4 * K3S_DESC_PKTS;    // [K3S_DESC_PKTS] exec masks
   volatile int* snb = reinterpret_cast<volatile int*>(gbase) + (K3S_DESC_FLOATS - 2);   // packets staged in this batch
   float* T = gbase + K3S_DESC_FLOATS;
-  float* Dch = T + 2 * K3_PLANE;
+  float* Dch = T + K3S_SCRATCH_FLOATS;
   uint64_t* mbar = reinterpret_cast<uint64_t*>(gbase + K3S_MBAR_FLOAT);   // [0]: channel 0, [1]: channel 1; phases in mph
   (void)mbar;
   const cpx* tab = reinterpret_cast<const cpx*>(tabs);
@@ -202,6 +213,9 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
   float2 xr[8];            // spectrum of channel 0 of the coming long block (prefetched)
   bool xr_valid = false;
   bool staged = false;     // spectrum of channel 1 of the coming long block sits in channel 1's free D slots
+#if K3S_PAIR
+  bool xb_valid = false;   // ... or, when both channels go through the paired transform, in the second scratch
+#endif
   for (int pb = 0; pb < total; pb += K3S_DESC_PKTS) {
     const int nb = (total - pb) < K3S_DESC_PKTS ? (total - pb) : K3S_DESC_PKTS;
     // descriptors + exec masks of the next nb packets: one parallel fetch
@@ -273,6 +287,40 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
           }
         }
       } else
+#if K3S_PAIR
+      if (C == 2 && (mask & 3u) == 3u) {
+        K3D Da, Db;
+        Da.h = Db.h = h;
+        Da.hm = Dch - h;
+        Da.lo = Dch + 512 + parity * 512;
+        Db.hm = Dch + K3S_CH_FLOATS - h;
+        Db.lo = Dch + K3S_CH_FLOATS + 512 + parity * 512;
+        const float* X = P.spec + pk.spec_off;
+        float2 xb[8];
+        if (xb_valid) {
+          // channel 1's pairs were copied into the second scratch by this very thread (8-byte cp.async during the
+          // previous packet's output), at the places it overwrites in the first transpose: no barrier needed
+          k3s_cp_wait();
+          const int end2 = K3S_END16(rw, 1) * 8;
+          const float2* B2 = reinterpret_cast<const float2*>(T + 2 * K3_PLANE);
+#pragma unroll
+          for (int q = 0; q < 8; q++) xb[q] = 64 * q < end2 ? B2[72 * q + t] : float2{0.f, 0.f};
+          xb_valid = false;
+        } else {
+          k3_load_x(X + M, t, xb, K3S_END16(rw, 1) * 8);
+        }
+        if (!xr_valid) k3_load_x(X, t, xr, K3S_END16(rw, 0) * 8);
+        xr_valid = false;
+        fft512_pair_to_D(xr, xb, T, T + 2 * K3_PLANE, Da, Db, tab, t, grp);
+        K3_GSYNC(grp);   // D complete, scratches reusable
+        if (P.dbg_imdct) {
+          for (int c = 0; c < 2; c++) {
+            float* dy = P.dbg_imdct + 2 * (size_t)pk.spec_off + (size_t)c * 2 * M;
+            for (int i = t64; i < 2 * M; i += K3_THREADS_PER_CH) dy[i] = k3_y(c ? Db : Da, M, i);
+          }
+        }
+      } else
+#endif
       for (int c = 0; c < C; c++) {
         float* chb = Dch + c * K3S_CH_FLOATS;
         K3D D;
@@ -351,6 +399,18 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
 #endif
         xr_valid = true;
       }
+#if K3S_PAIR
+      if (C == 2 && next_long && (mask_next & 3u) == 3u) {
+        // channel 1 of a block that will take the paired transform: every thread copies its own 8 pairs
+        const float2* Xn = reinterpret_cast<const float2*>(P.spec + pk_next.spec_off + 1024);
+        float2* B2 = reinterpret_cast<float2*>(T + 2 * K3_PLANE);
+        const int end2 = K3S_END16(rw_next, 1) * 8;
+#pragma unroll
+        for (int q = 0; q < 8; q++)
+          if (64 * q < end2) k3s_cp8(B2 + 72 * q + t, Xn + t + 64 * q);
+        xb_valid = true;
+      }
+#endif
       // ---- output: window + overlap-add + clip, all channels interleaved ----------------------------
       if (emit) {
         const int ls = pk.left_start;
@@ -410,7 +470,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
       // the output loop read this packet's high slot and the previous packet's low slot: both are free
       // once every thread of the group is here
       K3_GSYNC(grp);
-      if (C == 2 && next_long && (mask_next & 2u)) {
+      if (C == 2 && next_long && (mask_next & 2u) && !(K3S_PAIR && (mask_next & 3u) == 3u)) {
         // channel 1 of the next long block -> its Hi slot (X[0..512)) and the Lo slot of the next parity
         // (X[512..1024)), asynchronously; channel 0's transform runs meanwhile
         const float* Xn = P.spec + pk_next.spec_off + 1024;
