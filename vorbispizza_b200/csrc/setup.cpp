@@ -870,6 +870,11 @@ int Setup::parse(const uint8_t* id_pkt, size_t id_len, const uint8_t* setup_pkt,
   }
   bw.align(4);
   h.db_off = bw.put_floats(reinterpret_cast<const float*>(k_db_bits), 256);
+  {
+    std::vector<uint32_t> rcp((size_t)VPZ_RCP_MAX + 1, 0u);
+    for (uint32_t d = 2; d <= VPZ_RCP_MAX; d++) rcp[d] = 0xffffffffu / d + 1u;   // ceil(2^32 / d): d never divides 2^32 - 1 + 1 unevenly here
+    h.rcp_off = bw.put_struct_array(rcp);
+  }
   // ---- K1a shared-memory table plan (vpz_dev.h, VpzSetupHdr.k1a_stage_off) ------------------------------
   for (int flag = 0; flag < 2; flag++) {
     std::vector<int> list;

@@ -138,7 +138,11 @@ struct VpzSetupHdr {
   // offset}}; soff_off: 256 x uint16 shared-memory word offset per book, 0xffff = not staged.
   uint32_t k1a_stage_off[2];
   uint32_t k1a_soff_off[2];
+  // ceil(2^32 / d) for d = 2 .. VPZ_RCP_MAX (d < 2: 0): floor(n / d) = umulhi(n, rcp[d]) exactly while n * d < 2^32 --
+  // the floor-1 line arithmetic (RenderPoint, RenderLineMulti) divides by post distances only
+  uint32_t rcp_off;
 };
+#define VPZ_RCP_MAX 4096
 #define K1A_SM_WORDS 16384    // 64 KB of tables per CTA
 #define K1A_SM_NONE 0xffffu
 
