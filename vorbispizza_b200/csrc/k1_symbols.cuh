@@ -1400,16 +1400,8 @@ VPZ_DEV void k1b_build_packet_gather(const K1Params& P, const K1bPkt& pk, uint32
   const int max_stages = rs->max_stages;
 
   uint32_t* urec = smem;
-#if K1B_PIN_REGS >= 2 && !defined(VPZ_EMU)
-  uint32_t yoff = (uint32_t)max_stages * (uint32_t)U * 2u, sgoff = yoff + (uint32_t)(C * half_max) / 4u;
-  asm volatile("" : "+r"(yoff));
-  asm volatile("" : "+r"(sgoff));
-  uint8_t* ybuf = reinterpret_cast<uint8_t*>(urec + yoff);   // [C][half_max] bytes
-  uint32_t* sgbase = urec + sgoff;                            // [C][4*66]
-#else
   uint8_t* ybuf = reinterpret_cast<uint8_t*>(urec + (size_t)max_stages * U * 2);   // [C][half_max] bytes
   uint32_t* sgbase = reinterpret_cast<uint32_t*>(ybuf) + (C * half_max) / 4;        // [C][4*66]
-#endif
 
   K1Gather G;
   G.urec = urec;

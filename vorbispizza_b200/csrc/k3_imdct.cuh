@@ -180,58 +180,8 @@ VPZ_DEV void k3_load_x(const float* X, int t, float2* xr, int end2) {
     xr[q] = 64 * q < end2 ? VPZ_LDG(reinterpret_cast<const float2*>(X) + (t + 64 * q)) : float2{0.f, 0.f};
 }
 
-// K3S_TW_REGS (bit mask): twiddles that depend on the thread only live in registers for the whole kernel instead
-// of being read from the shared-memory tables for every block: 1 = the 8 pre / post twiddles tw[t + 64 q]
-// (used twice per block), 2 = W2[k][t & 7], 4 = W1[k][t].  The shared-memory pipe is K3's bound.
-#ifndef K3S_TW_REGS
-#define K3S_TW_REGS 0
-#endif
-struct K3TwRegs {
-#if K3S_TW_REGS & 1
-  cpx tw[8];
-#endif
-#if K3S_TW_REGS & 2
-  cpx w2[7];
-#endif
-#if K3S_TW_REGS & 4
-  cpx w1[7];
-#endif
-  int unused;
-};
-VPZ_DEV void k3_tw_regs_load(K3TwRegs& R, const cpx* tab, int t) {
-#if K3S_TW_REGS & 1
-#pragma unroll
-  for (int q = 0; q < 8; q++) R.tw[q] = tab[K3_TAB_TW + t + 64 * q];
-#endif
-#if K3S_TW_REGS & 2
-#pragma unroll
-  for (int k = 1; k < 8; k++) R.w2[k - 1] = tab[K3_TAB_W2 + (k - 1) * 8 + (t & 7)];
-#endif
-#if K3S_TW_REGS & 4
-#pragma unroll
-  for (int k = 1; k < 8; k++) R.w1[k - 1] = tab[K3_TAB_W1 + (k - 1) * 64 + t];
-#endif
-  R.unused = 0;
-}
-#if K3S_TW_REGS & 1
-#define K3_TWQ(q) R.tw[q]
-#else
-#define K3_TWQ(q) tw[t + 64 * (q)]
-#endif
-#if K3S_TW_REGS & 2
-#define K3_W2K(k) R.w2[(k) - 1]
-#else
-#define K3_W2K(k) tab[K3_TAB_W2 + ((k) - 1) * 8 + r2]
-#endif
-#if K3S_TW_REGS & 4
-#define K3_W1K(k) R.w1[(k) - 1]
-#else
-#define K3_W1K(k) tab[K3_TAB_W1 + ((k) - 1) * 64 + t]
-#endif
-
-VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* tab, int t, int grp, const K3TwRegs& R) {   // M = 1024
+VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* tab, int t, int grp) {   // M = 1024
   const cpx* tw = tab + K3_TAB_TW;
-  (void)tw;
   cpx v[8];
   // X[2n+1] = X[M-1-2n'] of the mirrored element n' = 511-n, held by the mirrored lane
 #pragma unroll
@@ -240,10 +190,10 @@ VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* ta
     v[q].y = __shfl_xor_sync(0xffffffffu, xr[7 - q].y, 31);
   }
 #pragma unroll
-  for (int q = 0; q < 8; q++) v[q] = cmul(v[q], K3_TWQ(q));
+  for (int q = 0; q < 8; q++) v[q] = cmul(v[q], tw[t + 64 * q]);
   dft8(v);
 #pragma unroll
-  for (int k = 1; k < 8; k++) v[k] = cmul(v[k], K3_W1K(k));
+  for (int k = 1; k < 8; k++) v[k] = cmul(v[k], tab[K3_TAB_W1 + (k - 1) * 64 + t]);
   // transposes through shared memory with COMPLEX (8-byte) elements: layouts 72 k1 + r and
   // k1 + 8 k2 + 66 r2 are conflict-free for 64-bit accesses (every half-warp touches 16 distinct
   // 8-byte bank pairs) in the writing and in the reading pass
@@ -257,7 +207,7 @@ VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* ta
   K3_GSYNC(grp);  // the second transpose reuses T
   dft8(v);
 #pragma unroll
-  for (int k = 1; k < 8; k++) v[k] = cmul(v[k], K3_W2K(k));
+  for (int k = 1; k < 8; k++) v[k] = cmul(v[k], tab[K3_TAB_W2 + (k - 1) * 8 + r2]);
 #pragma unroll
   for (int k = 0; k < 8; k++) T2[k1 + 8 * k + 66 * r2] = v[k];
   K3_GSYNC(grp);
@@ -272,7 +222,7 @@ VPZ_DEV void fft512_to_D(const float2* xr, float* T, const K3D& D, const cpx* ta
   float ny[8];
 #pragma unroll
   for (int k3 = 0; k3 < 8; k3++) {
-    const cpx c = cmul(v[k3], K3_TWQ(k3));
+    const cpx c = cmul(v[k3], tw[t + 64 * k3]);
     v[k3].x = c.x;
     ny[k3] = -c.y;
   }

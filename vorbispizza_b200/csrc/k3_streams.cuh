@@ -65,9 +65,6 @@
 #ifndef K3S_LEAN
 #define K3S_LEAN 1
 #endif
-#ifndef K3S_PIN_REGS
-#define K3S_PIN_REGS 0
-#endif
 #ifndef K3S_GP_SMEM
 #define K3S_GP_SMEM 1
 #endif
@@ -184,7 +181,7 @@ VPZ_DEV bool k3s_emit_same_size(const float* hi0 /* D[M/2..] of channel 0 */, co
 
 // one work item, C = 1 or 2 channels, by one 64-thread group.  OUT16: 16-bit PCM (k3_s16) instead of fp32
 template <bool OUT16, bool ENDS>
-VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs, float* gbase, int grp, int t64, unsigned& mph, const K3TwRegs& twr) {
+VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs, float* gbase, int grp, int t64, unsigned& mph) {
   const VpzOlaItem it = item;  // the item lives in global memory: read it once
   const uint32_t* blob = P.setups[it.setup_slot];
   const VpzSetupHdr* Hd = reinterpret_cast<const VpzSetupHdr*>(blob);
@@ -366,7 +363,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
           } else if (!(c == 0 && xr_valid)) {
             k3_load_x(X, t, xr, K3S_END16(rw, c) * 8);
           }
-          fft512_to_D(xr, T, D, tab, t, grp, twr);
+          fft512_to_D(xr, T, D, tab, t, grp);
           if (c == 0) xr_valid = false;
 #if !(K3S_BULK & 1)
           k3s_cp_wait();
@@ -515,7 +512,7 @@ VPZ_DEV void k3s_run_item(const K3Params& P, const VpzOlaItem& item, float* tabs
 template <bool OUT16, bool ENDS>
 VPZ_DEV void k3s_cta(const K3Params& P, float* smem) {
   const int tid = threadIdx.x;
-  int grp = tid / K3_THREADS_PER_CH, t64 = tid % K3_THREADS_PER_CH;
+  const int grp = tid / K3_THREADS_PER_CH, t64 = tid % K3_THREADS_PER_CH;
   const int nthreads = blockDim.x;
   {
     // the tables depend on the two block sizes only (256 / 2048 for every setup of this launch)
@@ -546,12 +543,6 @@ VPZ_DEV void k3s_cta(const K3Params& P, float* smem) {
     }
     for (int i = tid; i < 128; i += nthreads) smem[K3S_TAB_S_SLOPE + i] = VPZ_LDG(slope0 + i);
   }
-#if K3S_PIN_REGS && !defined(VPZ_EMU)
-  // opaque copies: the compiler otherwise re-derives the group (barrier id) and the thread index from threadIdx
-  // at every use inside the packet loop
-  asm volatile("" : "+r"(grp));
-  asm volatile("" : "+r"(t64));
-#endif
   float* gbase = smem + K3S_TAB_FLOATS + grp * K3S_GROUP_FLOATS;
   unsigned mph = 0;   // phase bits of the group's two mbarriers
 #if K3S_BULK
@@ -563,14 +554,12 @@ VPZ_DEV void k3s_cta(const K3Params& P, float* smem) {
 #endif
   __syncthreads();
   uint32_t* slot = reinterpret_cast<uint32_t*>(gbase) + (K3S_DESC_FLOATS - 1);
-  K3TwRegs twr;
-  k3_tw_regs_load(twr, reinterpret_cast<const cpx*>(smem), k3_remap64(t64));
   for (;;) {
     K3_GSYNC(grp);
     if (t64 == 0) *slot = atomicAdd(P.counter, 1u);
     K3_GSYNC(grp);
     const uint32_t idx = *slot;
     if (idx >= P.n_items) break;
-    k3s_run_item<OUT16, ENDS>(P, P.items[idx], smem, gbase, grp, t64, mph, twr);
+    k3s_run_item<OUT16, ENDS>(P, P.items[idx], smem, gbase, grp, t64, mph);
   }
 }
