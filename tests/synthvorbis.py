@@ -243,6 +243,9 @@ SHAPES = {
     "floor0_mixed": dict(channels=3, res_types=(2, 1), floor0=True, floor1_too=True, submaps=2, coupling=1),
     "equal_blocks": dict(channels=2, res_types=(2,), lg=(10, 10), coupling=1),
     "blocks_512_4096": dict(channels=1, res_types=(1,), lg=(9, 12)),
+    # partitions of 2,048 positions: above the 2,047 entries per unit that K1b's gather path packs into 16-bit prefix
+    # sums (engine.cpp), so the setup must take the general path
+    "big_partitions": dict(channels=2, res_types=(1,), lg=(9, 13), psize=2048, vq_dims=(1, 2, 4, 8), coupling=1),
 }
 
 
